@@ -1,0 +1,21 @@
+"""autonomouscar_b200 -- B200-native hot path of the WPI AutonomousCar local planner.
+
+Only what the path needs lives here: `csrc/` (CUDA kernels + the C ABI of
+include/prius_planner.h), the ctypes binding (`planner.Planner`), the message-level
+mirror of the reference node (`node.LocalPlannerNode`) and synthetic-workload helpers
+for tests and bench (`worlds`).
+"""
+from .capi import *  # noqa: F401,F403  (enums, structs, default_params, make_query)
+from .results import PlanResult  # noqa: F401
+
+
+def __getattr__(name):
+    # the binding needs torch + the built library; import it lazily so that pure-host
+    # helpers (capi, worlds) stay importable everywhere
+    if name in ("Planner", "PlannerError"):
+        from . import planner
+        return getattr(planner, name)
+    if name == "LocalPlannerNode":
+        from . import node
+        return node.LocalPlannerNode
+    raise AttributeError(name)

@@ -1,0 +1,377 @@
+// pp_api.cu -- the extern "C" boundary of include/prius_planner.h (host side, C++).
+//
+// Everything here is argument checking, memory staging and stream / event plumbing; the
+// arithmetic lives in the kernels.  There is no CPU fallback: without a CUDA device
+// pp_create fails.
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "pp_common.cuh"
+
+namespace pp {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int philox_kat(pp_handle* h, const uint32_t c[4], const uint32_t k[2], uint32_t out[4]);
+
+static int ceil_tol(double q) { return static_cast<int>(std::ceil(q - 1e-9)); }
+
+// DESIGN.md "ORIENTED footprint lattice": nu x nv points spanning length x width, spacing
+// <= one cell.  Same expressions as the oracle's make_lattice.
+Lattice make_lattice(double car_length, double car_width, double res) {
+  Lattice l;
+  const double lu = car_length / res, lv = car_width / res;
+  l.nu = ceil_tol(lu) + 1;
+  l.nv = ceil_tol(lv) + 1;
+  l.su = l.nu > 1 ? lu / (l.nu - 1) : 0.0;
+  l.sv = l.nv > 1 ? lv / (l.nv - 1) : 0.0;
+  l.hu = (l.nu - 1) * 0.5;
+  l.hv = (l.nv - 1) * 0.5;
+  return l;
+}
+bool lattice_supported(const Lattice& l) {
+  const double du = l.su * l.hu, dv = l.sv * l.hv;
+  return std::sqrt(du * du + dv * dv) + 1.0 < 47.0 && l.nu >= 1 && l.nv >= 1;
+}
+
+static int ensure_stage(pp_handle* h, int64_t n) {
+  if (n <= h->stage_cap) return PP_OK;
+  cudaFree(h->d_poses);
+  cudaFree(h->d_flags);
+  h->d_poses = nullptr; h->d_flags = nullptr; h->stage_cap = 0;
+  PP_CUDA(cudaMalloc(&h->d_poses, static_cast<size_t>(n) * 3 * sizeof(float)));
+  PP_CUDA(cudaMalloc(&h->d_flags, static_cast<size_t>(n)));
+  h->stage_cap = n;
+  return PP_OK;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_abi_version(void) { return PP_ABI_VERSION; }
+const char* pp_last_error(void) { return g_last_error.c_str(); }
+
+// full_sim.launch:77-79 (75 m / 0.25 m = 300 cells), :90-97; local_planner.hpp:141;
+// footprint from prius.urdf through LP:328-334
+int pp_default_params(pp_params* p) {
+  if (!p) return PP_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->costmap_res = 0.25;
+  p->costmap_width = 300;
+  p->costmap_height = 300;
+  p->collision_buffer_distance = 1.0;
+  p->time_step_ms = 150.0;
+  p->velocity_res = 0.1;
+  p->heading_res = 0.005;
+  p->heading_diff = 0.065;
+  p->goal_pos_tolerance = 0.1;
+  p->goal_speed_tolerance = 0.5;
+  p->search_res = 0.25;
+  p->max_velocity = 15.0;
+  p->car_length = 4.7;
+  p->car_width = 1.586;
+  p->collision_mode = PP_COLLISION_AS_SHIPPED;
+  p->max_expansions = 100000;
+  p->max_nodes = 10000;
+  p->rrt_samples_per_round = 256;
+  p->rrt_max_samples = 1 << 20;
+  p->rrt_goal_bias = 0.05;
+  p->rrt_goal_tolerance = 1.0;
+  return PP_OK;
+}
+
+int pp_create(const pp_params* params, int device, pp_handle** out) {
+  if (!params || !out) { set_last_error("pp_create: null argument"); return PP_ERR_INVALID; }
+  *out = nullptr;
+  PP_REQUIRE(params->costmap_width > 0 && params->costmap_height > 0, "pp_create: empty grid");
+  PP_REQUIRE(params->costmap_width <= 32768 && params->costmap_height <= 32768, "pp_create: grid too large");
+  PP_REQUIRE(params->costmap_res > 0, "pp_create: costmap_res must be > 0");
+  PP_REQUIRE(params->collision_mode >= 0 && params->collision_mode <= 2, "pp_create: bad collision_mode");
+  PP_REQUIRE(params->car_length > 0 && params->car_width > 0, "pp_create: bad footprint");
+  const Lattice lat = make_lattice(params->car_length, params->car_width, params->costmap_res);
+  if (!lattice_supported(lat)) {
+    set_last_error("pp_create: footprint spans more than 94 cells; not supported by the tile window");
+    return PP_ERR_UNSUPPORTED;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_last_error(std::string("pp_create: no CUDA device (") + cudaGetErrorString(e) +
+                   "); this library has no CPU fallback");
+    return PP_ERR_CUDA;
+  }
+  PP_REQUIRE(device >= 0 && device < n_dev, "pp_create: bad device index");
+  PP_CUDA(cudaSetDevice(device));
+  pp_handle* h = new pp_handle();
+  h->P = *params;
+  h->device = device;
+  h->lat = lat;
+  h->grid.W = params->costmap_width;
+  h->grid.H = params->costmap_height;
+  h->grid.res = params->costmap_res;
+  cudaDeviceProp prop;
+  PP_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  PP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  PP_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) PP_CUDA(cudaEventCreate(&ev));
+  PP_CUDA(cudaMalloc(&h->d_count, 64));
+  PP_CUDA(cudaMemset(h->d_count, 0, 64));
+  PP_CUDA(cudaMallocHost(&h->h_count, 64));
+  std::memset(h->h_count, 0, 64);
+  *out = h;
+  return PP_OK;
+}
+
+int pp_destroy(pp_handle* h) {
+  if (!h) return PP_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  plan_free(h);
+  rrt_free(h);
+  grid_free(h);
+  cudaFree(h->d_poses);
+  cudaFree(h->d_flags);
+  cudaFree(h->d_list);
+  cudaFree(h->d_count);
+  cudaFreeHost(h->h_count);
+  cudaFree(h->scratch);
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return PP_OK;
+}
+
+int pp_get_params(const pp_handle* h, pp_params* out) {
+  if (!h || !out) return PP_ERR_INVALID;
+  *out = h->P;
+  return PP_OK;
+}
+
+int pp_set_collision_mode(pp_handle* h, int mode) {
+  if (!h) return PP_ERR_INVALID;
+  PP_REQUIRE(mode >= 0 && mode <= 2, "pp_set_collision_mode: bad mode");
+  h->P.collision_mode = mode;
+  return PP_OK;
+}
+
+static int set_grid_common(pp_handle* h, const int8_t* data, bool on_device, int32_t width, int32_t height,
+                           double res, int layout) {
+  if (!h || !data) { set_last_error("pp_set_grid: null argument"); return PP_ERR_INVALID; }
+  PP_REQUIRE(width == h->P.costmap_width && height == h->P.costmap_height,
+             "pp_set_grid: width/height differ from the handle's costmap_width/height");
+  PP_REQUIRE(res == h->P.costmap_res, "pp_set_grid: res differs from the handle's costmap_res");
+  PP_REQUIRE(layout == PP_GRID_OCCUPANCY_MSG || layout == PP_GRID_CSPACE, "pp_set_grid: bad layout");
+  PP_CUDA(cudaSetDevice(h->device));
+  return grid_upload(h, data, on_device, layout);
+}
+int pp_set_grid(pp_handle* h, const int8_t* data_host, int32_t width, int32_t height, double res, int layout) {
+  return set_grid_common(h, data_host, false, width, height, res, layout);
+}
+int pp_set_grid_dev(pp_handle* h, const int8_t* data_dev, int32_t width, int32_t height, double res, int layout) {
+  return set_grid_common(h, data_dev, true, width, height, res, layout);
+}
+
+int pp_get_cspace(pp_handle* h, int8_t* out_host, size_t capacity) {
+  if (!h || !out_host) return PP_ERR_INVALID;
+  if (!h->has_grid) { set_last_error("pp_get_cspace: no grid"); return PP_ERR_NO_GRID; }
+  const size_t cells = static_cast<size_t>(h->grid.W) * h->grid.H;
+  if (capacity < cells) { set_last_error("pp_get_cspace: buffer too small"); return PP_ERR_CAPACITY; }
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaMemcpyAsync(out_host, h->grid.cspace, cells, cudaMemcpyDeviceToHost, h->stream));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  return PP_OK;
+}
+
+static int require_grid(pp_handle* h, const char* who) {
+  if (!h) return PP_ERR_INVALID;
+  if (h->P.collision_mode != PP_COLLISION_AS_SHIPPED && !h->has_grid) {
+    set_last_error(std::string(who) + ": pp_set_grid has not been called");
+    return PP_ERR_NO_GRID;
+  }
+  return PP_OK;
+}
+
+int pp_collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* out_flags_dev) {
+  int rc = require_grid(h, "pp_collide_batch_dev");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (poses_dev && out_flags_dev)), "pp_collide_batch_dev: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  return collide_batch_dev(h, n, poses_dev, out_flags_dev);
+}
+
+// Host-pointer entry point: H2D, kernels and D2H pipelined in chunks on two streams so the
+// PCIe copies overlap the gather.
+int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* out_flags_host) {
+  int rc = require_grid(h, "pp_collide_batch");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (poses_host && out_flags_host)), "pp_collide_batch: bad arguments");
+  if (n == 0) return PP_OK;
+  PP_CUDA(cudaSetDevice(h->device));
+  rc = ensure_stage(h, n);
+  if (rc) return rc;
+  const int64_t chunk = 1 << 20;
+  const int64_t n_chunks = (n + chunk - 1) / chunk;
+  cudaStream_t cs = h->copy_stream, ks = h->stream;
+  // all H2D copies are queued on the copy stream; the compute stream waits chunk by chunk,
+  // and the D2H of chunk c is queued behind the H2D of chunk c+1, so both directions of the
+  // link stay busy while the kernels run
+  PP_CUDA(cudaEventRecord(h->ev[0], cs));
+  rc = collide_counter_reset(h);
+  if (rc) return rc;
+  PP_CUDA(cudaEventRecord(h->ev[2], ks));
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int64_t lo = c * chunk, m = (lo + chunk <= n) ? chunk : n - lo;
+    PP_CUDA(cudaMemcpyAsync(h->d_poses + 3 * lo, poses_host + 3 * lo, static_cast<size_t>(m) * 3 * sizeof(float),
+                            cudaMemcpyHostToDevice, cs));
+    PP_CUDA(cudaEventRecord(h->ev[4 + (c & 1)], cs));
+    PP_CUDA(cudaStreamWaitEvent(ks, h->ev[4 + (c & 1)], 0));
+    rc = collide_launch(h, m, h->d_poses + 3 * lo, h->d_flags + lo);
+    if (rc) return rc;
+    PP_CUDA(cudaEventRecord(h->ev[6 + (c & 1)], ks));
+    PP_CUDA(cudaStreamWaitEvent(cs, h->ev[6 + (c & 1)], 0));
+    PP_CUDA(cudaMemcpyAsync(out_flags_host + lo, h->d_flags + lo, static_cast<size_t>(m), cudaMemcpyDeviceToHost, cs));
+  }
+  PP_CUDA(cudaEventRecord(h->ev[3], ks));
+  rc = collide_counter_fetch(h);
+  if (rc) return rc;
+  PP_CUDA(cudaEventRecord(h->ev[1], cs));
+  PP_CUDA(cudaStreamSynchronize(cs));
+  PP_CUDA(cudaStreamSynchronize(ks));
+  if (h->P.collision_mode != PP_COLLISION_ORIENTED) h->last_narrow = n;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->phase_ms[PP_PHASE_H2D] = ms;  // the whole pipelined call as seen by the copy stream
+  return PP_OK;
+}
+
+int pp_collide_edges_dev(pp_handle* h, int64_t n, const float* edges_dev, uint8_t* out_flags_dev) {
+  int rc = require_grid(h, "pp_collide_edges_dev");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (edges_dev && out_flags_dev)), "pp_collide_edges_dev: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  return collide_edges_dev(h, n, edges_dev, out_flags_dev);
+}
+
+int pp_footprint_points(pp_handle* h, double x, double y, double yaw, double* out_xy_host, int32_t capacity,
+                        int32_t* n_points) {
+  if (!h || !out_xy_host || !n_points || capacity < 0) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  double* d = nullptr;
+  int* dn = nullptr;
+  PP_CUDA(cudaMalloc(&d, sizeof(double) * 2 * static_cast<size_t>(capacity) + 16));
+  PP_CUDA(cudaMalloc(&dn, sizeof(int)));
+  int rc = footprint_points_dev(h, x, y, yaw, d, capacity, dn);
+  if (rc == PP_OK) {
+    int n = 0;
+    cudaMemcpyAsync(&n, dn, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpyAsync(out_xy_host, d, sizeof(double) * 2 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    *n_points = n;
+  }
+  cudaFree(d);
+  cudaFree(dn);
+  return rc;
+}
+
+int pp_sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t first_index, int64_t n, float x_lo,
+                        float x_hi, float y_lo, float y_hi, float* out_poses_dev) {
+  if (!h || n < 0 || (n > 0 && !out_poses_dev)) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  return sample_poses_dev(h, seed, stream, first_index, n, x_lo, x_hi, y_lo, y_hi, out_poses_dev);
+}
+
+int pp_philox4x32_10(pp_handle* h, const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+  if (!h || !counter || !key || !out) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  return philox_kat(h, counter, key, out);
+}
+
+int pp_nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy_dev, int64_t n_query,
+                   const float* query_xy_dev, int32_t* out_index_dev, float* out_dist2_dev) {
+  if (!h || n_nodes < 0 || n_query < 0) return PP_ERR_INVALID;
+  if (n_query > 0 && (!query_xy_dev || !out_index_dev || (n_nodes > 0 && !node_xy_dev))) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  return nearest_dev(h, n_nodes, node_xy_dev, n_query, query_xy_dev, out_index_dev, out_dist2_dev);
+}
+
+int pp_find_exact_dev(pp_handle* h, int64_t n_nodes, const double* node_keys_dev, int64_t n_query,
+                      const double* query_keys_dev, int32_t* out_index_dev) {
+  if (!h || n_nodes < 0 || n_query < 0) return PP_ERR_INVALID;
+  if (n_query > 0 && (!query_keys_dev || !out_index_dev || (n_nodes > 0 && !node_keys_dev))) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  return find_exact_dev(h, n_nodes, node_keys_dev, n_query, query_keys_dev, out_index_dev);
+}
+
+int pp_plan(pp_handle* h, const pp_query* query, pp_result* result) { return pp_plan_batch(h, 1, query, result); }
+
+int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results) {
+  int rc = require_grid(h, "pp_plan_batch");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (queries && results)), "pp_plan_batch: bad arguments");
+  if (n == 0) return PP_OK;
+  PP_CUDA(cudaSetDevice(h->device));
+  return plan_batch(h, n, queries, results);
+}
+
+int pp_rrt_plan(pp_handle* h, const pp_query* query, pp_result* result) {
+  return pp_rrt_plan_batch(h, 1, query, result);
+}
+int pp_rrt_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results) {
+  int rc = require_grid(h, "pp_rrt_plan_batch");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (queries && results)), "pp_rrt_plan_batch: bad arguments");
+  if (n == 0) return PP_OK;
+  PP_CUDA(cudaSetDevice(h->device));
+  return rrt_plan_batch(h, n, queries, results);
+}
+
+int pp_sync(pp_handle* h) {
+  if (!h) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  PP_CUDA(cudaStreamSynchronize(h->copy_stream));
+  return PP_OK;
+}
+int pp_stream(pp_handle* h, void** out_stream) {
+  if (!h || !out_stream) return PP_ERR_INVALID;
+  *out_stream = static_cast<void*>(h->stream);
+  return PP_OK;
+}
+int pp_launch_count(const pp_handle* h, uint64_t* out) {
+  if (!h || !out) return PP_ERR_INVALID;
+  *out = h->launches;
+  return PP_OK;
+}
+int pp_last_phase_ms(pp_handle* h, float* out_ms, int32_t n) {
+  if (!h || !out_ms || n < 0) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->phase_ms[PP_PHASE_NARROW] = ms;
+  else cudaGetLastError();
+  for (int k = 0; k < n && k < PP_PHASE_COUNT; ++k) out_ms[k] = h->phase_ms[k];
+  return PP_OK;
+}
+int pp_last_narrow_count(pp_handle* h, int64_t* out) {
+  if (!h || !out) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->last_narrow < 0) h->last_narrow = static_cast<int64_t>(*reinterpret_cast<unsigned long long*>(h->h_count));
+  *out = h->last_narrow;
+  return PP_OK;
+}
+int pp_set_broad_phase(pp_handle* h, int enabled) {
+  if (!h) return PP_ERR_INVALID;
+  h->broad_phase = enabled ? 1 : 0;
+  return PP_OK;
+}
+
+}  // extern "C"

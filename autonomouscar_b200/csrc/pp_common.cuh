@@ -1,0 +1,253 @@
+// pp_common.cuh -- handle layout, device-side grid representations and the per-pose
+// collision primitives shared by the batch kernels and the planner kernels.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <cuda_runtime.h>
+
+#include "../../include/prius_planner.h"
+#include "pp_math.cuh"
+
+namespace pp {
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+void set_last_error(const std::string& msg);
+#define PP_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ::pp::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+      return PP_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+#define PP_REQUIRE(cond, msg)                                                             \
+  do {                                                                                    \
+    if (!(cond)) { ::pp::set_last_error(msg); return PP_ERR_INVALID; }                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// footprint sample lattice (row S3), computed once on the host at pp_create
+// ---------------------------------------------------------------------------------------
+struct Lattice {
+  int nu, nv;      // sample points along the car length / across the width
+  double su, sv;   // lattice step, in cells
+  double hu, hv;   // (nu-1)/2, (nv-1)/2
+};
+constexpr int kAnchorOffset = 48;         // anchor cell = floor(centre) - 48
+constexpr int kFracBits = 24;             // Q7.24 cell coordinates relative to the anchor
+constexpr double kFixedOne = 16777216.0;
+
+// ---------------------------------------------------------------------------------------
+// device-side grid representations, built by pp_set_grid (pp_grid.cu)
+// ---------------------------------------------------------------------------------------
+constexpr int kHaloCells = 128;           // zero halo around the occupancy tiles
+constexpr int kTile = 32;                 // a tile is 32 x 32 cells = 32 words = one 128 B line
+
+struct GridDev {
+  int W, H;                 // m_c_space dimensions: first index i < W, second index j < H
+  double res;
+  int8_t* cspace;           // W*H bytes, cspace[i*H + j] == m_c_space[i][j]  (LP:425-441)
+  // occupancy (cell == 100) as 32x32-bit tiles over cells [-halo, W+halo) x [-halo, H+halo):
+  //   word r of tile (ti,tj) = row i = 32*ti - halo + r, bit b = column j = 32*tj - halo + b
+  uint32_t* occ_tiles;
+  uint8_t* tile_any;        // 1 if any bit of the tile is set
+  int TI, TJ;               // tile counts
+  // REF_AABB box-dilated map over base cells [-aabb_pad_x, W+aabb_pad_x) x [-aabb_pad_y, H+...)
+  //   aabb_map[(bx+pad_x) * aabb_stride + (by+pad_y)] = 1 iff the LP:477-495 box anchored at
+  //   (bx,by) contains a cell == 100
+  uint8_t* aabb_map;
+  int aabb_pad_x, aabb_pad_y, aabb_nx, aabb_ny;
+};
+
+struct CollideParams {
+  Lattice lat;
+  double car_length, car_width, search_res;
+  int mode;
+};
+
+// ---------------------------------------------------------------------------------------
+// per-pose primitives
+// ---------------------------------------------------------------------------------------
+struct PoseFx {
+  int valid;
+  int ai, aj;            // anchor cell
+  int32_t oi, oj;        // lattice origin (a=0,b=0) relative to the anchor, Q7.24
+  int32_t ui, uj;        // step along the length
+  int32_t vi, vj;        // step across the width
+};
+
+__device__ __forceinline__ int32_t to_fixed(double v) {
+  return __double2int_rn(dm::mul(v, kFixedOne));
+}
+
+// Mirrors oracle/collision_ref.h pose_to_fixed operation for operation.
+__device__ __forceinline__ PoseFx pose_to_fixed(const Lattice& l, int W, int H, double res, double x,
+                                                double y, double yaw) {
+  PoseFx p;
+  p.valid = 0;
+  double s, c;
+  dm::sincos(yaw, &s, &c);
+  const double ci = dm::sub(static_cast<double>(W / 2), dm::div(y, res));
+  const double cj = dm::sub(static_cast<double>(H / 2), dm::div(x, res));
+  if (!(fabs(ci) < 1048576.0) || !(fabs(cj) < 1048576.0) || s != s) return p;
+  p.ai = __double2int_rd(ci) - kAnchorOffset;
+  p.aj = __double2int_rd(cj) - kAnchorOffset;
+  const double ui = -dm::mul(s, l.su), uj = -dm::mul(c, l.su);
+  const double vi = -dm::mul(c, l.sv), vj = dm::mul(s, l.sv);
+  const double oi = dm::sub(dm::sub(dm::sub(ci, static_cast<double>(p.ai)), dm::mul(l.hu, ui)), dm::mul(l.hv, vi));
+  const double oj = dm::sub(dm::sub(dm::sub(cj, static_cast<double>(p.aj)), dm::mul(l.hu, uj)), dm::mul(l.hv, vj));
+  p.oi = to_fixed(oi); p.oj = to_fixed(oj);
+  p.ui = to_fixed(ui); p.uj = to_fixed(uj);
+  p.vi = to_fixed(vi); p.vj = to_fixed(vj);
+  p.valid = 1;
+  return p;
+}
+
+// cell range touched by the lattice (min/max over its four corners), in grid cells
+__device__ __forceinline__ void lattice_bbox(const Lattice& l, const PoseFx& p, int* i0, int* i1, int* j0,
+                                             int* j1) {
+  const int32_t eu_i = (l.nu - 1) * p.ui, eu_j = (l.nu - 1) * p.uj;
+  const int32_t ev_i = (l.nv - 1) * p.vi, ev_j = (l.nv - 1) * p.vj;
+  const int32_t ci0 = p.oi, ci1 = p.oi + eu_i, ci2 = p.oi + ev_i, ci3 = p.oi + eu_i + ev_i;
+  const int32_t cj0 = p.oj, cj1 = p.oj + eu_j, cj2 = p.oj + ev_j, cj3 = p.oj + eu_j + ev_j;
+  *i0 = p.ai + (min(min(ci0, ci1), min(ci2, ci3)) >> kFracBits);
+  *i1 = p.ai + (max(max(ci0, ci1), max(ci2, ci3)) >> kFracBits);
+  *j0 = p.aj + (min(min(cj0, cj1), min(cj2, cj3)) >> kFracBits);
+  *j1 = p.aj + (max(max(cj0, cj1), max(cj2, cj3)) >> kFracBits);
+}
+
+__device__ __forceinline__ uint32_t occ_word(const GridDev& g, int i, int jw_tile) {
+  // i: cell row (may be in the halo), jw_tile: tile column index
+  const int ih = i + kHaloCells;
+  return __ldg(&g.occ_tiles[(static_cast<size_t>(ih >> 5) * g.TJ + jw_tile) * kTile + (ih & 31)]);
+}
+
+// ORIENTED, one thread evaluating the whole lattice straight from the tiled bitmap.
+// Used where poses are few and latency-bound (planner candidates, edge steps); the batch
+// path uses the warp-cooperative kernel in pp_collide.cu.
+__device__ __forceinline__ bool oriented_hit_thread(const GridDev& g, const Lattice& l, const PoseFx& p) {
+  if (!p.valid) return false;
+  int i0, i1, j0, j1;
+  lattice_bbox(l, p, &i0, &i1, &j0, &j1);
+  if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return false;
+  uint32_t hit = 0;
+  for (int a = 0; a < l.nu; ++a) {
+    int32_t fi = p.oi + a * p.ui, fj = p.oj + a * p.uj;
+    for (int b = 0; b < l.nv; ++b) {
+      const int gi = p.ai + (fi >> kFracBits), gj = p.aj + (fj >> kFracBits);
+      const int jh = gj + kHaloCells;
+      hit |= occ_word(g, gi, jh >> 5) >> (jh & 31);
+      fi += p.vi;
+      fj += p.vj;
+    }
+    if (hit & 1u) return true;
+  }
+  return (hit & 1u) != 0;
+}
+
+// REF_AABB through the dilated map: LP:471-476 evaluated verbatim for the base cell, then
+// one lookup replaces the LP:477-495 / LP:447-456 loops.
+__device__ __forceinline__ bool aabb_hit(const GridDev& g, double px, double py) {
+  int bx, by;
+  if (!dm::trunc_to_int(dm::sub(static_cast<double>(g.W / 2), dm::div(py, g.res)), &bx)) return false;
+  if (!dm::trunc_to_int(dm::sub(static_cast<double>(g.H / 2), dm::div(px, g.res)), &by)) return false;
+  const int mx = bx + g.aabb_pad_x, my = by + g.aabb_pad_y;
+  if (mx < 0 || mx >= g.aabb_nx || my < 0 || my >= g.aabb_ny) return false;
+  return __ldg(&g.aabb_map[static_cast<size_t>(mx) * g.aabb_ny + my]) != 0;
+}
+
+__device__ __forceinline__ bool collide_pose_thread(const GridDev& g, const CollideParams& cp, double x,
+                                                    double y, double yaw) {
+  if (cp.mode == PP_COLLISION_AS_SHIPPED) return false;  // LP:445
+  if (cp.mode == PP_COLLISION_REF_AABB) return aabb_hit(g, x, y);
+  return oriented_hit_thread(g, cp.lat, pose_to_fixed(cp.lat, g.W, g.H, g.res, x, y, yaw));
+}
+
+// along-edge rule, mirrors oracle collide_edge
+__device__ __forceinline__ bool collide_edge_thread(const GridDev& g, const CollideParams& cp, double x0,
+                                                    double y0, double x1, double y1, double yaw) {
+  const double dx = dm::sub(x1, x0), dy = dm::sub(y1, y0);
+  const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
+  int n;
+  if (!dm::trunc_to_int(dm::mul(dm::div(dist, cp.search_res), 2.0), &n)) return false;
+  if (n < 1) n = 1;
+  for (int k = 1; k <= n; ++k) {
+    const double t = dm::div(static_cast<double>(k), static_cast<double>(n));
+    const double px = dm::add(x0, dm::mul(t, dx)), py = dm::add(y0, dm::mul(t, dy));
+    if (collide_pose_thread(g, cp, px, py, yaw)) return true;
+  }
+  return false;
+}
+
+}  // namespace pp
+
+// ---------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------
+struct PlanWorkspace;   // pp_plan.cu
+struct RrtWorkspace;    // pp_rrt.cu
+
+struct pp_handle {
+  pp_params P;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;      // compute
+  cudaStream_t copy_stream = nullptr; // H2D / D2H of the host-pointer entry points
+  cudaEvent_t ev[16] = {};
+  pp::Lattice lat{};
+  pp::GridDev grid{};
+  bool has_grid = false;
+  int broad_phase = 1;
+  uint64_t launches = 0;
+  float phase_ms[PP_PHASE_COUNT] = {};
+  int64_t last_narrow = 0;
+  // staging for the host-pointer collide entry point
+  float* d_poses = nullptr;
+  uint8_t* d_flags = nullptr;
+  int64_t stage_cap = 0;
+  // compaction scratch for the two-phase ORIENTED path
+  int32_t* d_list = nullptr;       // indices of poses that need the narrow phase
+  int32_t* d_count = nullptr;      // device counter
+  int32_t* h_count = nullptr;      // pinned mirror
+  int64_t list_cap = 0;
+  void* scratch = nullptr;         // grid-prep scratch
+  size_t scratch_bytes = 0;
+  PlanWorkspace* plan_ws = nullptr;
+  RrtWorkspace* rrt_ws = nullptr;
+};
+
+namespace pp {
+inline CollideParams collide_params(const pp_handle* h) {
+  CollideParams cp;
+  cp.lat = h->lat;
+  cp.car_length = h->P.car_length;
+  cp.car_width = h->P.car_width;
+  cp.search_res = h->P.search_res;
+  cp.mode = h->P.collision_mode;
+  return cp;
+}
+// kernels / host helpers implemented across the .cu files
+int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layout);
+void grid_free(pp_handle* h);
+int collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev);
+int collide_launch(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev);
+int collide_counter_reset(pp_handle* h);
+int collide_counter_fetch(pp_handle* h);
+int collide_edges_dev(pp_handle* h, int64_t n, const float* edges_dev, uint8_t* flags_dev);
+int footprint_points_dev(pp_handle* h, double x, double y, double yaw, double* out_dev, int cap, int* n);
+int sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t first, int64_t n, float x_lo,
+                     float x_hi, float y_lo, float y_hi, float* out);
+int nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy, int64_t n_query, const float* q,
+                int32_t* idx, float* d2);
+int find_exact_dev(pp_handle* h, int64_t n_nodes, const double* keys, int64_t n_query, const double* q,
+                   int32_t* idx);
+int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs);
+int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs);
+void plan_free(pp_handle* h);
+void rrt_free(pp_handle* h);
+Lattice make_lattice(double car_length, double car_width, double res);
+bool lattice_supported(const Lattice& l);
+}  // namespace pp

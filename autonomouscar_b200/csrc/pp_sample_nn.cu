@@ -1,0 +1,156 @@
+// pp_sample_nn.cu -- rows S1 / S2 / A6 of the scope table as stand-alone batched kernels:
+//   S1  Philox4x32-10 pose sampler (counter = sample index, never any state in memory)
+//   S2  brute-force nearest neighbour, warp-cooperative, shuffle argmin, ties -> lowest index
+//   A6  the reference's std::find + GraphNode::operator== lookups (local_planner.cpp:56-57,
+//       graph_node.hpp:24-30) as an exact-match query: first index whose 6 key doubles
+//       all compare ==
+#include "pp_common.cuh"
+#include "pp_philox.cuh"
+
+namespace pp {
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+sample_poses_kernel(uint32_t k0, uint32_t k1, uint32_t stream, uint64_t first, int64_t n, float x_lo,
+                    float x_rng, float y_lo, float y_rng, float* __restrict__ out) {
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t idx = first + static_cast<uint64_t>(k);
+    const Philox4 r = philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), stream,
+                                    kTagPose, k0, k1);
+    out[3 * k + 0] = __fmaf_rn(u01_from_bits(r.x), x_rng, x_lo);
+    out[3 * k + 1] = __fmaf_rn(u01_from_bits(r.y), y_rng, y_lo);
+    out[3 * k + 2] = __fmaf_rn(u01_from_bits(r.z), PP_TWOPI_F, -PP_PI_F);
+  }
+}
+
+__global__ void philox_kat_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                  uint32_t* out) {
+  const Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// (d, idx) lexicographic min across the warp
+__device__ __forceinline__ void warp_argmin(float& d, int& idx) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    const bool take = (oi >= 0) && (idx < 0 || od < d || (od == d && oi < idx));
+    if (take) { d = od; idx = oi; }
+  }
+}
+
+constexpr int kQPW = 4;  // queries per warp: each node load is reused for 4 distance evaluations
+
+__global__ void __launch_bounds__(256)
+nearest_kernel(const float2* __restrict__ nodes, int64_t n_nodes, const float2* __restrict__ queries,
+               int64_t n_query, int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t n_groups = (n_query + kQPW - 1) / kQPW;
+  for (int64_t grp = warp; grp < n_groups; grp += n_warps) {
+    float qx[kQPW], qy[kQPW], best[kQPW];
+    int bi[kQPW];
+#pragma unroll
+    for (int q = 0; q < kQPW; ++q) {
+      const int64_t qi = grp * kQPW + q;
+      const float2 v = qi < n_query ? queries[qi] : make_float2(0.f, 0.f);
+      qx[q] = v.x; qy[q] = v.y; best[q] = 0.f; bi[q] = -1;
+    }
+    for (int64_t k = lane; k < n_nodes; k += 32) {
+      const float2 nd = __ldg(&nodes[k]);
+#pragma unroll
+      for (int q = 0; q < kQPW; ++q) {
+        const float dx = __fsub_rn(qx[q], nd.x), dy = __fsub_rn(qy[q], nd.y);
+        const float d = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+        if (bi[q] < 0 || d < best[q]) { best[q] = d; bi[q] = static_cast<int>(k); }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kQPW; ++q) {
+      warp_argmin(best[q], bi[q]);
+      const int64_t qi = grp * kQPW + q;
+      if (lane == 0 && qi < n_query) {
+        out_idx[qi] = bi[q];
+        if (out_d2) out_d2[qi] = best[q];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+find_exact_kernel(const double* __restrict__ keys, int64_t n_nodes, const double* __restrict__ queries,
+                  int64_t n_query, int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t qi = warp; qi < n_query; qi += n_warps) {
+    double q[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) q[c] = queries[6 * qi + c];
+    int found = 0x7fffffff;
+    for (int64_t k = lane; k < n_nodes; k += 32) {
+      const double* e = keys + 6 * k;
+      const bool eq = e[0] == q[0] && e[1] == q[1] && e[2] == q[2] && e[3] == q[3] && e[4] == q[4] && e[5] == q[5];
+      if (eq) { found = static_cast<int>(k); break; }  // lanes scan ascending: first hit is the lane's lowest
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, off));
+    if (lane == 0) out_idx[qi] = found == 0x7fffffff ? -1 : found;
+  }
+}
+
+int blocks_for(const pp_handle* h, int64_t want) {
+  const int64_t cap = static_cast<int64_t>(h->sm_count) * 8;
+  return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+}  // namespace
+
+int sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t first, int64_t n, float x_lo,
+                     float x_hi, float y_lo, float y_hi, float* out) {
+  if (n == 0) return PP_OK;
+  sample_poses_kernel<<<blocks_for(h, (n + 255) / 256), 256, 0, h->stream>>>(
+      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), stream, first, n, x_lo, x_hi - x_lo, y_lo,
+      y_hi - y_lo, out);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int philox_kat(pp_handle* h, const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
+  uint32_t* d = nullptr;
+  PP_CUDA(cudaMalloc(&d, 16));
+  philox_kat_kernel<<<1, 1, 0, h->stream>>>(c[0], c[1], c[2], c[3], k[0], k[1], d);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  PP_CUDA(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, h->stream));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  PP_CUDA(cudaFree(d));
+  return PP_OK;
+}
+
+int nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy, int64_t n_query, const float* q,
+                int32_t* idx, float* d2) {
+  if (n_query == 0) return PP_OK;
+  const int64_t groups = (n_query + kQPW - 1) / kQPW;
+  nearest_kernel<<<blocks_for(h, (groups + 7) / 8), 256, 0, h->stream>>>(
+      reinterpret_cast<const float2*>(node_xy), n_nodes, reinterpret_cast<const float2*>(q), n_query, idx, d2);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int find_exact_dev(pp_handle* h, int64_t n_nodes, const double* keys, int64_t n_query, const double* q,
+                   int32_t* idx) {
+  if (n_query == 0) return PP_OK;
+  find_exact_kernel<<<blocks_for(h, (n_query + 7) / 8), 256, 0, h->stream>>>(keys, n_nodes, q, n_query, idx);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+}  // namespace pp

@@ -1,0 +1,214 @@
+"""Python face of the C ABI (include/prius_planner.h).
+
+PyTorch is used for device memory, streams and torch.distributed only; every computation
+is a call into libprius_planner_b200.so.  Method names follow the reference planner's
+members they stand for (local_planner.cpp): set_grid <- costmapCallback/mapCostmapToCSpace,
+collide <- checkCollision, plan <- localNavCallback/planPath.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .capi import (PP_GRID_CSPACE, PP_OK, PP_PHASE_COUNT, default_params, pp_params, pp_query, pp_result)
+from .results import PlanResult
+
+
+class PlannerError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"pp status {code}: {text}")
+        self.code = code
+
+
+def _dptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class Planner:
+    """One planner instance on one GPU (pp_handle)."""
+
+    def __init__(self, params=None, device=0):
+        self._L = _lib.load()
+        self.params = params if params is not None else default_params()
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self._L.pp_create(C.byref(self.params), self.device, C.byref(h)))
+        self._h = h
+        s = C.c_void_p()
+        self._check(self._L.pp_stream(self._h, C.byref(s)))
+        self.stream = torch.cuda.ExternalStream(s.value, device=self.torch_device)
+
+    def _check(self, rc):
+        if rc != PP_OK:
+            raise PlannerError(rc, self._L.pp_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self._L.pp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- grid ingest -----------------------------------------------------------------
+    def set_grid(self, data, layout=PP_GRID_CSPACE):
+        W, H = self.params.costmap_width, self.params.costmap_height
+        if isinstance(data, torch.Tensor) and data.is_cuda:
+            assert data.dtype == torch.int8 and data.numel() == W * H and data.is_contiguous()
+            torch.cuda.current_stream(self.torch_device).synchronize()
+            self._check(self._L.pp_set_grid_dev(self._h, _dptr(data), W, H, self.params.costmap_res, layout))
+        else:
+            a = np.ascontiguousarray(np.asarray(data), dtype=np.int8)
+            assert a.size == W * H, "grid size differs from costmap_width * costmap_height"
+            self._check(self._L.pp_set_grid(self._h, a.ctypes.data_as(C.c_void_p), W, H,
+                                            self.params.costmap_res, layout))
+
+    def get_cspace(self):
+        W, H = self.params.costmap_width, self.params.costmap_height
+        out = np.zeros(W * H, dtype=np.int8)
+        self._check(self._L.pp_get_cspace(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out.reshape(W, H)
+
+    def set_collision_mode(self, mode):
+        self._check(self._L.pp_set_collision_mode(self._h, mode))
+        self.params.collision_mode = mode
+
+    def set_broad_phase(self, enabled):
+        self._check(self._L.pp_set_broad_phase(self._h, int(bool(enabled))))
+
+    # ---- collision -------------------------------------------------------------------
+    def collide(self, poses_host, out=None):
+        """checkCollision for a batch; host buffers in, host flags out (copies inside)."""
+        if isinstance(poses_host, torch.Tensor):
+            assert not poses_host.is_cuda and poses_host.dtype == torch.float32 and poses_host.is_contiguous()
+            n = poses_host.numel() // 3
+            if out is None:
+                out = torch.empty(n, dtype=torch.uint8, pin_memory=poses_host.is_pinned())
+            self._check(self._L.pp_collide_batch(self._h, n, _dptr(poses_host), _dptr(out)))
+            return out
+        a = np.ascontiguousarray(poses_host, dtype=np.float32).reshape(-1, 3)
+        if out is None:
+            out = np.zeros(len(a), dtype=np.uint8)
+        self._check(self._L.pp_collide_batch(self._h, len(a), a.ctypes.data_as(C.c_void_p),
+                                             out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def collide_dev(self, poses, out=None):
+        """Device tensors; asynchronous on self.stream."""
+        assert poses.is_cuda and poses.dtype == torch.float32 and poses.is_contiguous()
+        n = poses.numel() // 3
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=poses.device)
+        self._check(self._L.pp_collide_batch_dev(self._h, n, _dptr(poses), _dptr(out)))
+        return out
+
+    def collide_edges_dev(self, edges, out=None):
+        assert edges.is_cuda and edges.dtype == torch.float32 and edges.is_contiguous()
+        n = edges.numel() // 5
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=edges.device)
+        self._check(self._L.pp_collide_edges_dev(self._h, n, _dptr(edges), _dptr(out)))
+        return out
+
+    def footprint_points(self, x, y, yaw, capacity=4096):
+        out = np.zeros((capacity, 2), dtype=np.float64)
+        n = C.c_int32()
+        self._check(self._L.pp_footprint_points(self._h, x, y, yaw, out.ctypes.data_as(C.c_void_p), capacity,
+                                                C.byref(n)))
+        return out[: n.value]
+
+    # ---- sampler / nearest neighbour ---------------------------------------------------
+    def sample_poses_dev(self, seed, stream, first, n, x_lo, x_hi, y_lo, y_hi, out=None):
+        if out is None:
+            out = torch.empty((n, 3), dtype=torch.float32, device=self.torch_device)
+        self._check(self._L.pp_sample_poses_dev(self._h, seed, stream, first, n, x_lo, x_hi, y_lo, y_hi,
+                                                _dptr(out)))
+        return out
+
+    def philox(self, ctr, key):
+        c = (C.c_uint32 * 4)(*ctr)
+        k = (C.c_uint32 * 2)(*key)
+        o = (C.c_uint32 * 4)()
+        self._check(self._L.pp_philox4x32_10(self._h, c, k, o))
+        return [int(v) for v in o]
+
+    def nearest_dev(self, node_xy, query_xy):
+        assert node_xy.is_cuda and query_xy.is_cuda and node_xy.dtype == torch.float32
+        nq = query_xy.numel() // 2
+        idx = torch.empty(nq, dtype=torch.int32, device=query_xy.device)
+        d2 = torch.empty(nq, dtype=torch.float32, device=query_xy.device)
+        self._check(self._L.pp_nearest_dev(self._h, node_xy.numel() // 2, _dptr(node_xy), nq, _dptr(query_xy),
+                                           _dptr(idx), _dptr(d2)))
+        return idx, d2
+
+    def find_exact_dev(self, keys, queries):
+        assert keys.is_cuda and queries.is_cuda and keys.dtype == torch.float64
+        nq = queries.numel() // 6
+        idx = torch.empty(nq, dtype=torch.int32, device=queries.device)
+        self._check(self._L.pp_find_exact_dev(self._h, keys.numel() // 6, _dptr(keys), nq, _dptr(queries),
+                                              _dptr(idx)))
+        return idx
+
+    # ---- planning ----------------------------------------------------------------------
+    def plan(self, query, **caps):
+        res = PlanResult(**caps)
+        res.rc = self._L.pp_plan(self._h, C.byref(query), C.byref(res.raw))
+        if res.rc not in (PP_OK, 4):
+            self._check(res.rc)
+        return res
+
+    def plan_batch(self, queries, want_nodes=False, **caps):
+        n = len(queries)
+        qs = (pp_query * n)(*queries)
+        results = [PlanResult(want_nodes=want_nodes, **caps) for _ in range(n)]
+        raw = (pp_result * n)(*[r.raw for r in results])
+        rc = self._L.pp_plan_batch(self._h, n, qs, raw)
+        if rc not in (PP_OK, 4):
+            self._check(rc)
+        for r, rr in zip(results, raw):
+            r.raw = rr
+        return results
+
+    def rrt_plan(self, query, **caps):
+        res = PlanResult(**caps)
+        res.rc = self._L.pp_rrt_plan(self._h, C.byref(query), C.byref(res.raw))
+        if res.rc not in (PP_OK, 4):
+            self._check(res.rc)
+        return res
+
+    def rrt_plan_batch(self, queries, want_nodes=False, **caps):
+        n = len(queries)
+        qs = (pp_query * n)(*queries)
+        results = [PlanResult(want_nodes=want_nodes, **caps) for _ in range(n)]
+        raw = (pp_result * n)(*[r.raw for r in results])
+        rc = self._L.pp_rrt_plan_batch(self._h, n, qs, raw)
+        if rc not in (PP_OK, 4):
+            self._check(rc)
+        for r, rr in zip(results, raw):
+            r.raw = rr
+        return results
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def sync(self):
+        self._check(self._L.pp_sync(self._h))
+
+    def launch_count(self):
+        v = C.c_uint64()
+        self._check(self._L.pp_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def last_phase_ms(self):
+        a = (C.c_float * PP_PHASE_COUNT)()
+        self._check(self._L.pp_last_phase_ms(self._h, a, PP_PHASE_COUNT))
+        return [float(v) for v in a]
+
+    def last_narrow_count(self):
+        v = C.c_int64()
+        self._check(self._L.pp_last_narrow_count(self._h, C.byref(v)))
+        return v.value

@@ -1,0 +1,85 @@
+"""Host-side buffers behind a pp_result (numpy arrays the C side fills in)."""
+import ctypes as C
+
+import numpy as np
+
+from .capi import pp_result
+
+
+class PlanResult:
+    """Owns the output arrays of one plan and exposes them trimmed to the filled length."""
+
+    def __init__(self, cap_nodes=16384, cap_path=4096, cap_expansions=16384, want_nodes=True):
+        self.raw = pp_result()
+        self.raw.cap_nodes = cap_nodes
+        self.raw.cap_path = cap_path
+        self.raw.cap_expansions = cap_expansions
+        self._node_state = np.zeros((cap_nodes, 8), dtype=np.float64) if want_nodes else None
+        self._node_parent = np.full(cap_nodes, -2, dtype=np.int32) if want_nodes else None
+        self._node_closed_seq = np.full(cap_nodes, -2, dtype=np.int32) if want_nodes else None
+        self._expansion_ids = np.full(cap_expansions, -2, dtype=np.int32)
+        self._path_xy = np.zeros((cap_path, 2), dtype=np.float64)
+        self._path_node_ids = np.full(cap_path, -2, dtype=np.int32)
+        self._yaw_rates = np.zeros(cap_path, dtype=np.float64)
+        self._durations = np.zeros(cap_path, dtype=np.float64)
+        self._speeds = np.zeros(cap_path, dtype=np.float64)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        if want_nodes:
+            self.raw.node_state = self._node_state.ctypes.data_as(dp)
+            self.raw.node_parent = self._node_parent.ctypes.data_as(ip)
+            self.raw.node_closed_seq = self._node_closed_seq.ctypes.data_as(ip)
+        self.raw.expansion_ids = self._expansion_ids.ctypes.data_as(ip)
+        self.raw.path_xy = self._path_xy.ctypes.data_as(dp)
+        self.raw.path_node_ids = self._path_node_ids.ctypes.data_as(ip)
+        self.raw.yaw_rates = self._yaw_rates.ctypes.data_as(dp)
+        self.raw.durations = self._durations.ctypes.data_as(dp)
+        self.raw.speeds = self._speeds.ctypes.data_as(dp)
+
+    # scalars -------------------------------------------------------------------------
+    def __getattr__(self, name):
+        if name in ("status", "n_expansions", "n_nodes", "n_open", "n_closed", "n_path", "n_profile",
+                    "n_candidates", "n_collisions", "tree_digest"):
+            return getattr(self.raw, name)
+        raise AttributeError(name)
+
+    # arrays --------------------------------------------------------------------------
+    @property
+    def node_state(self):
+        return self._node_state[: min(self.raw.n_nodes, self.raw.cap_nodes)]
+
+    @property
+    def node_parent(self):
+        return self._node_parent[: min(self.raw.n_nodes, self.raw.cap_nodes)]
+
+    @property
+    def node_closed_seq(self):
+        return self._node_closed_seq[: min(self.raw.n_nodes, self.raw.cap_nodes)]
+
+    @property
+    def expansion_ids(self):
+        return self._expansion_ids[: min(self.raw.n_expansions, self.raw.cap_expansions)]
+
+    @property
+    def path_xy(self):
+        return self._path_xy[: min(self.raw.n_path, self.raw.cap_path)]
+
+    @property
+    def path_node_ids(self):
+        return self._path_node_ids[: min(self.raw.n_path, self.raw.cap_path)]
+
+    @property
+    def yaw_rates(self):
+        return self._yaw_rates[: min(self.raw.n_profile, self.raw.cap_path)]
+
+    @property
+    def durations(self):
+        return self._durations[: min(self.raw.n_profile, self.raw.cap_path)]
+
+    @property
+    def speeds(self):
+        return self._speeds[: min(self.raw.n_profile, self.raw.cap_path)]
+
+    def summary(self):
+        return {k: int(getattr(self.raw, k)) for k in (
+            "status", "n_expansions", "n_nodes", "n_open", "n_closed", "n_path", "n_profile",
+            "n_candidates", "n_collisions", "tree_digest")}

@@ -1,0 +1,167 @@
+"""GPU parity: batched checkCollision through the C ABI vs the CPU oracle, bit-exact.
+
+Every call goes through libprius_planner_b200.so (pp_collide_batch / _dev); the oracle is
+only the checker.
+"""
+import numpy as np
+import pytest
+import torch
+
+from autonomouscar_b200 import (PP_COLLISION_AS_SHIPPED, PP_COLLISION_ORIENTED, PP_COLLISION_REF_AABB,
+                                PP_GRID_CSPACE, PP_GRID_OCCUPANCY_MSG, default_params, worlds)
+
+pytestmark = pytest.mark.gpu
+
+
+def _planner(params, grid, layout=PP_GRID_CSPACE):
+    from autonomouscar_b200 import Planner
+    pl = Planner(params, device=0)
+    pl.set_grid(grid, layout)
+    return pl
+
+
+CASES = [
+    # (res, W, H) : launch-file grid, BASELINE 0.1 m grids, ragged non-multiple-of-32 sizes
+    (0.25, 300, 300),
+    (0.1, 1024, 1024),
+    (0.1, 517, 333),
+    (0.1, 64, 40),
+]
+
+
+@pytest.mark.parametrize("res,W,H", CASES)
+@pytest.mark.parametrize("mode", [PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED])
+def test_collide_matches_oracle(oracle, cuda_device, res, W, H, mode):
+    p = default_params(costmap_res=res, costmap_width=W, costmap_height=H, collision_mode=mode)
+    grid = worlds.block_grid(W, H, frac=0.03, block=8, seed=W + H)
+    poses = worlds.random_poses(p, 60000, seed=7, inset_m=-8.0)  # negative inset: poses beyond the border too
+    pl = _planner(p, grid)
+    got = pl.collide(poses)
+    want, _ = oracle.collide_batch(p, grid, poses)
+    assert got.dtype == np.uint8 and got.shape == want.shape
+    assert 0.0 < want.mean() < 1.0
+    np.testing.assert_array_equal(got, want)
+    # device-pointer entry point, and broad phase off ("direct"), must agree bit for bit
+    d = torch.from_numpy(poses).cuda()
+    f1 = pl.collide_dev(d); pl.sync()
+    pl.set_broad_phase(False)
+    f2 = pl.collide_dev(d); pl.sync()
+    np.testing.assert_array_equal(f1.cpu().numpy(), want)
+    np.testing.assert_array_equal(f2.cpu().numpy(), want)
+    if mode == PP_COLLISION_ORIENTED:
+        assert pl.last_narrow_count() >= int(want.sum())
+    pl.close()
+
+
+def test_as_shipped_is_always_false(cuda_device):
+    # LP:445: the shipped reference returns false unconditionally
+    p = default_params(collision_mode=PP_COLLISION_AS_SHIPPED)
+    pl = _planner(p, np.full((300, 300), 100, dtype=np.int8))
+    assert pl.collide(worlds.random_poses(p, 5000)).sum() == 0
+    pl.close()
+
+
+@pytest.mark.parametrize("mode", [PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED])
+def test_empty_and_full_grids(oracle, cuda_device, mode):
+    p = default_params(costmap_res=0.1, costmap_width=512, costmap_height=512, collision_mode=mode)
+    poses = worlds.random_poses(p, 20000, seed=3, inset_m=3.0)
+    pl = _planner(p, np.zeros((512, 512), dtype=np.int8))
+    assert pl.collide(poses).sum() == 0
+    pl.set_grid(np.full((512, 512), 99, dtype=np.int8))   # 99 is road cost, not an obstacle (LP:451)
+    assert pl.collide(poses).sum() == 0
+    pl.set_grid(np.full((512, 512), 100, dtype=np.int8))
+    assert pl.collide(poses).sum() == len(poses)
+    # far outside the grid / absurd coordinates: no cell can be touched
+    far = np.array([[1e4, 0, 0], [0, -1e4, 1], [3e9, 3e9, 0], [-1e30, 5, 2]], dtype=np.float32)
+    np.testing.assert_array_equal(pl.collide(far), oracle.collide_batch(p, np.full((512, 512), 100, np.int8), far)[0])
+    assert pl.collide(far).sum() == 0
+    # empty batch
+    assert pl.collide(np.zeros((0, 3), np.float32)).shape == (0,)
+    pl.close()
+
+
+def test_permutation_invariance_and_single_cell(oracle, cuda_device):
+    p = default_params(costmap_res=0.1, costmap_width=700, costmap_height=700, collision_mode=PP_COLLISION_ORIENTED)
+    grid = np.zeros((700, 700), dtype=np.int8)
+    grid[350, 350] = 100  # one occupied cell at the vehicle origin
+    poses = worlds.random_poses(p, 40000, seed=11, inset_m=30.0)
+    poses[:, :2] *= 0.15  # concentrate around the obstacle
+    pl = _planner(p, grid)
+    f = pl.collide(poses)
+    want, _ = oracle.collide_batch(p, grid, poses)
+    np.testing.assert_array_equal(f, want)
+    assert 0 < f.sum() < len(f)
+    perm = np.random.default_rng(0).permutation(len(poses))
+    np.testing.assert_array_equal(pl.collide(poses[perm]), f[perm])
+    pl.close()
+
+
+def test_occupancy_msg_layout_flip(oracle, cuda_device):
+    # LP:425-441: cspace[i][j] = data[H*W - i*H - j - 1]
+    W, H = 96, 70
+    p = default_params(costmap_res=0.25, costmap_width=W, costmap_height=H, collision_mode=PP_COLLISION_REF_AABB)
+    msg = np.random.default_rng(5).integers(-1, 101, size=W * H).astype(np.int8)
+    pl = _planner(p, msg, PP_GRID_OCCUPANCY_MSG)
+    want = oracle.cspace_from_msg(msg, W, H)
+    np.testing.assert_array_equal(pl.get_cspace(), want)
+    poses = worlds.random_poses(p, 5000, seed=2, inset_m=-2.0)
+    np.testing.assert_array_equal(pl.collide(poses), oracle.collide_batch(p, want, poses)[0])
+    pl.close()
+
+
+def test_footprint_transform_tolerance(oracle, cuda_device):
+    """north_star: footprint-transform floats agree within 1e-5 m.  The GPU lattice is
+    bit-identical to the oracle's and both sit within 1e-5 m of a float64 libm transform."""
+    p = default_params(costmap_res=0.1, costmap_width=4096, costmap_height=4096, collision_mode=PP_COLLISION_ORIENTED)
+    from autonomouscar_b200 import Planner
+    pl = Planner(p, device=0)
+    nu, nv, ok = oracle.lattice_dims(p)
+    assert (nu, nv, ok) == (48, 17, True)
+    rng = np.random.default_rng(9)
+    for _ in range(40):
+        x, y = rng.uniform(-200, 200, 2)
+        yaw = rng.uniform(-7, 7)
+        got = pl.footprint_points(x, y, yaw)
+        want = oracle.footprint_points(p, x, y, yaw)
+        np.testing.assert_array_equal(got, want)  # bit-exact vs oracle
+        u = np.linspace(-p.car_length / 2, p.car_length / 2, nu)
+        v = np.linspace(-p.car_width / 2, p.car_width / 2, nv)
+        U, V = np.meshgrid(u, v, indexing="ij")
+        ref = np.stack([(x + U * np.cos(yaw) - V * np.sin(yaw)).ravel(),
+                        (y + U * np.sin(yaw) + V * np.cos(yaw)).ravel()], 1)
+        assert np.abs(got - ref).max() < 1e-5  # tolerance stated by BASELINE.json:north_star
+    pl.close()
+
+
+def test_edges_match_oracle(oracle, cuda_device):
+    for mode in (PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED):
+        p = default_params(costmap_res=0.1, costmap_width=800, costmap_height=800, collision_mode=mode)
+        grid = worlds.block_grid(800, 800, frac=0.03, block=8, seed=21)
+        a = worlds.random_poses(p, 20000, seed=4, inset_m=1.0)
+        rng = np.random.default_rng(1)
+        ln = rng.uniform(0, 3.0, len(a)).astype(np.float32)
+        edges = np.empty((len(a), 5), dtype=np.float32)
+        edges[:, 0:2] = a[:, 0:2]
+        edges[:, 2] = a[:, 0] + ln * np.cos(a[:, 2])
+        edges[:, 3] = a[:, 1] + ln * np.sin(a[:, 2])
+        edges[:, 4] = a[:, 2]
+        edges[:50, 2:4] = edges[:50, 0:2]  # zero-length edges
+        pl = _planner(p, grid)
+        got = pl.collide_edges_dev(torch.from_numpy(edges).cuda()); pl.sync()
+        want = oracle.collide_edges(p, grid, edges)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+        assert 0 < want.sum() < len(want)
+        pl.close()
+
+
+def test_errors_are_loud(cuda_device):
+    from autonomouscar_b200 import Planner, PlannerError
+    p = default_params(collision_mode=PP_COLLISION_REF_AABB)
+    pl = Planner(p, device=0)
+    with pytest.raises(PlannerError):  # no grid yet
+        pl.collide(np.zeros((4, 3), np.float32))
+    with pytest.raises(AssertionError):  # wrong grid size
+        pl.set_grid(np.zeros((10, 10), np.int8))
+    pl.close()
+    with pytest.raises(PlannerError):  # footprint wider than the tile window supports
+        Planner(default_params(costmap_res=0.01), device=0)
