@@ -1,5 +1,1002 @@
+// pp_plan.cu -- the reference planner's search loop, one thread block per query.
+//
+// Replaces Prius::LocalPlanner::planPath and everything it calls
+// (catkin_ws/src/local_planner/src/local_planner.cpp, "LP"):
+//   planPath LP:25-82 . initializePlanner LP:84-96 . openNode/closeNode LP:98-113 .
+//   calcH LP:115-137 . calcW LP:139-144 . getNeighbors LP:146-169 . checkGoalDist LP:171-189 .
+//   calcPossibleVelocities LP:191-216 . calcPossibleYaws LP:218-232 . checkForGoal LP:269-287 .
+//   interpolateToGoalPoint LP:289-299 . interpolatePoints LP:301-316 . markVisited LP:318-326 .
+//   calcPathMsg LP:503-540 . calcMPMessage LP:542-583 . GraphNode::operator== graph_node.hpp:24-30 .
+//   CheaperCost + std::priority_queue local_planner.hpp:103-111
+//
+// B200 mapping (not a port of the CPU structure):
+//   - a query is one CTA for its whole life; the tree lives in HBM/L2 as SoA arrays, the
+//     frontier heap in shared memory when it fits (it is the latency-critical structure);
+//   - the frontier reproduces libstdc++'s push_heap / pop_heap element for element, so equal
+//     costs pop in the reference's order; the sift-up is done by one warp in parallel
+//     (each lane owns one ancestor);
+//   - the reference's O(N) std::find lookups per candidate (97 % of its CPU time) are
+//     answered by a per-query hash set of 64-bit key fingerprints in L2; only a fingerprint
+//     hit falls back to the exact brute-force scan, so results are identical to the scan;
+//   - candidate generation, collision and cost are one thread per (velocity, yaw) child;
+//   - path / profile extraction are block-wide first-match / last-match reductions that
+//     reproduce the list scan order (open list in insertion order, then closed list in
+//     closing order).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "pp_common.cuh"
+
 namespace pp {
-int plan_batch(pp_handle*, int, const pp_query*, pp_result*) { set_last_error("pp_plan: not built yet"); return PP_ERR_UNSUPPORTED; }
-void plan_free(pp_handle*) {}
+
+namespace {
+
+constexpr int kT = 256;            // threads per CTA
+constexpr int kWarps = kT / 32;
+constexpr int kMaxVel = 64;        // velocities per expansion the kernel supports
+constexpr int kMaxCand = 8192;     // children per expansion the kernel supports
+constexpr int kIntMax = 0x7fffffff;
+
+struct PlanHdr {                   // per query, device -> host
+  int status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions;
+  int truncated;                   // a caller-visible array was too small
+  unsigned long long digest;
+};
+
+struct PlanArgs {
+  GridDev g;
+  CollideParams cp;
+  pp_params P;
+  const pp_query* queries;
+  int n_queries;
+  int NC;                 // slot capacity per workspace
+  int hash_size;          // power of two
+  int heap_in_smem;
+  int ws_per_query;       // workspace index = query index (node arrays wanted) or CTA index
+  int want_path_ids;
+  int cap_path, cap_exp;
+  size_t ws_stride;       // bytes
+  unsigned char* ws_base;
+  PlanHdr* hdr;
+  double* out_path;       // [n][cap_path][2]
+  int* out_path_ids;      // [n][cap_path]
+  double* out_profile;    // [n][3][cap_path]
+  int* out_exp;           // [n][cap_exp] or null
+  int* work_counter;
+};
+
+// SoA view of one workspace
+struct WS {
+  double *cx, *cy, *px, *py, *hd, *vel, *g, *cost;
+  unsigned long long* fp;     // key fingerprint per slot
+  unsigned long long* hash;   // open-addressing set of fingerprints (0 = empty)
+  double* heap_cost_g;
+  int* closed_seq;
+  int* heap_id_g;
+  int* cand_slot;             // scratch: per candidate, target slot or -1
+};
+
+__host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
+  size_t b = 0;
+  b += sizeof(double) * 8 * NC;
+  b += sizeof(unsigned long long) * NC;
+  b += sizeof(unsigned long long) * hash_size;
+  b += sizeof(double) * NC;           // global heap costs
+  b += sizeof(int) * NC * 2;          // closed_seq, heap ids
+  b += sizeof(int) * kMaxCand;
+  return (b + 255) & ~size_t(255);
 }
+
+__device__ __forceinline__ WS ws_view(unsigned char* base, int NC, int hash_size) {
+  WS w;
+  double* d = reinterpret_cast<double*>(base);
+  w.cx = d; w.cy = d + NC; w.px = d + 2 * NC; w.py = d + 3 * NC;
+  w.hd = d + 4 * NC; w.vel = d + 5 * NC; w.g = d + 6 * NC; w.cost = d + 7 * NC;
+  w.fp = reinterpret_cast<unsigned long long*>(d + 8 * NC);
+  w.hash = w.fp + NC;
+  w.heap_cost_g = reinterpret_cast<double*>(w.hash + hash_size);
+  w.closed_seq = reinterpret_cast<int*>(w.heap_cost_g + NC);
+  w.heap_id_g = w.closed_seq + NC;
+  w.cand_slot = w.heap_id_g + NC;
+  return w;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long dbits(double d) {
+  return static_cast<unsigned long long>(__double_as_longlong(d));
+}
+// fingerprint of the 6 key doubles; -0.0 and +0.0 compare equal, so canonicalise first
+__device__ __forceinline__ unsigned long long key_fingerprint(const double k[6]) {
+  unsigned long long h = 0x5851F42D4C957F2Dull;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) h = mix64(h ^ dbits(__dadd_rn(k[i], 0.0)));
+  return h | 1ull;  // 0 is the empty marker of the hash set
+}
+// tree digest term of pp_result.tree_digest (same as oracle/planner_ref.h node_digest)
+__device__ __forceinline__ unsigned long long node_digest(int id, const double k[6]) {
+  unsigned long long h = static_cast<unsigned long long>(id) + 1ull;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) h = mix64(h ^ dbits(k[i]));
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------
+// block-wide reductions (all threads must call)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_min(int v, int* s_red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) r = min(r, s_red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ int block_max(int v, int* s_red) { return -block_min(-v, s_red); }
+__device__ __forceinline__ int block_sum(int v, int* s_red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) r += s_red[w];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// the frontier: libstdc++ binary heap, comp(a, b) = a.cost > b.cost (local_planner.hpp:103-109)
+// ---------------------------------------------------------------------------------------
+struct Heap {
+  double* cost;
+  int* id;
+};
+
+// std::__push_heap(first, hole, top = 0, value): executed by one full warp.  Lane k >= 1 owns
+// the k-th ancestor of the hole; all ancestors that compare "less" (cost > value) shift down
+// one level at once.
+__device__ __forceinline__ void heap_sift_up_warp(const Heap& h, int hole, double vcost, int vid, int lane) {
+  const unsigned j = static_cast<unsigned>(hole) + 1u;  // 1-based position
+  bool moves = false;
+  double pc = 0;
+  int pid = 0;
+  int my_pos = 0;
+  if (lane >= 1) {
+    const bool valid = (j >> (lane - 1)) >= 2u;  // the (lane-1)-th ancestor is not the root
+    if (valid) {
+      my_pos = static_cast<int>(j >> lane) - 1;
+      pc = h.cost[my_pos];
+      pid = h.id[my_pos];
+      moves = pc > vcost;
+    }
+  }
+  const unsigned stay = __ballot_sync(0xffffffffu, !moves) & ~1u;  // lanes >= 1 that stop the loop
+  const int stop = __ffs(stay) - 1;                               // first k with !moves (always exists: lane 31 at worst)
+  __syncwarp();
+  if (lane >= 1 && lane < stop) {
+    const int dst = static_cast<int>(j >> (lane - 1)) - 1;
+    h.cost[dst] = pc;
+    h.id[dst] = pid;
+  }
+  if (lane == 0) {
+    const int dst = static_cast<int>(j >> (stop - 1)) - 1;
+    h.cost[dst] = vcost;
+    h.id[dst] = vid;
+  }
+  __syncwarp();
+}
+
+// priority_queue::push by warp 0
+__device__ __forceinline__ void heap_push_warp(const Heap& h, int* size, double vcost, int vid, int lane) {
+  const int hole = *size;
+  __syncwarp();
+  heap_sift_up_warp(h, hole, vcost, vid, lane);
+  if (lane == 0) *size = hole + 1;
+  __syncwarp();
+}
+
+// priority_queue::pop by warp 0: std::pop_heap (__pop_heap + __adjust_heap) then pop_back
+__device__ __forceinline__ void heap_pop_warp(const Heap& h, int* size, int lane) {
+  const int n = *size;
+  __syncwarp();
+  if (n <= 1) {
+    if (lane == 0) *size = 0;
+    __syncwarp();
+    return;
+  }
+  const int len = n - 1;
+  const double vcost = h.cost[len];
+  const int vid = h.id[len];
+  int hole = 0;
+  if (lane == 0) {
+    int child = 0;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      if (h.cost[child] > h.cost[child - 1]) child--;
+      h.cost[hole] = h.cost[child];
+      h.id[hole] = h.id[child];
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      h.cost[hole] = h.cost[child - 1];
+      h.id[hole] = h.id[child - 1];
+      hole = child - 1;
+    }
+  }
+  hole = __shfl_sync(0xffffffffu, hole, 0);
+  __syncwarp();
+  heap_sift_up_warp(h, hole, vcost, vid, lane);
+  if (lane == 0) *size = len;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
+// reference arithmetic (deterministic math; operation order as in the cited lines)
+// ---------------------------------------------------------------------------------------
+struct QueryD {
+  double gx, gy, gs, max_speed, max_accel, start_speed;
+};
+
+// LP:171-189
+__device__ __forceinline__ bool check_goal_dist(const pp_params& P, const QueryD& Q, double cx, double cy,
+                                                double heading, double vel) {
+  double next_vel = dm::add(vel, dm::div(dm::mul(Q.max_accel, P.time_step_ms), 1000.0));
+  if (next_vel > Q.max_speed) next_vel = Q.max_speed;
+  const double avg = dm::div(dm::add(next_vel, vel), 2.0);
+  double s, c;
+  dm::sincos(heading, &s, &c);
+  const double step = dm::div(dm::mul(avg, P.time_step_ms), 1000.0);
+  const double x = dm::add(cx, dm::mul(step, c));
+  const double y = dm::add(cy, dm::mul(step, s));
+  const double dx = dm::sub(x, Q.gx), dy = dm::sub(y, Q.gy);
+  const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
+  const double t = dm::div(dm::sub(vel, Q.gs), Q.max_accel);
+  const double d_decel = dm::sub(dm::mul(vel, t), dm::div(dm::mul(Q.max_accel, dm::mul(t, t)), 2.0));
+  return dm::add(dist, P.goal_pos_tolerance) <= d_decel;
+}
+
+// LP:115-137
+__device__ __forceinline__ double calc_h(const pp_params& P, const QueryD& Q, double cx, double cy, double heading,
+                                         double vel) {
+  double speed = vel;
+  if (speed == 0) speed = 0.01;
+  const double max_dist = __dsqrt_rn(dm::add(dm::mul(Q.gx, Q.gx), dm::mul(Q.gy, Q.gy)));
+  const double ex = dm::sub(cx, Q.gx), ey = dm::sub(cy, Q.gy);
+  const double dist_to_goal = __dsqrt_rn(dm::add(dm::mul(ex, ex), dm::mul(ey, ey)));
+  const double dist_h = dm::mul(dm::div(dist_to_goal, max_dist), 100.0);
+  const double yaw_to_goal = dm::atan2_(dm::sub(Q.gy, cy), dm::sub(Q.gx, cx));
+  const double yaw_h = dm::mul(dm::div(fabs(dm::sub(heading, yaw_to_goal)), 6.283185307179586), 100.0);
+  double speed_h = dm::sub(100.0, dm::mul(dm::div(speed, P.max_velocity), 100.0));
+  if (check_goal_dist(P, Q, cx, cy, heading, vel)) speed_h = dm::mul(fabs(dm::sub(speed, Q.gs)), 100.0);
+  return fabs(dm::add(dm::add(dist_h, yaw_h), speed_h));
+}
+
+struct Shared {
+  int n_nodes, n_closed, heap_size, n_exp, status, dup_seen, cur_id, n_vel, n_yaw, n_cand_total, n_coll_total;
+  int goal_hit, path_len, truncated, done;
+  int q;
+  double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
+};
+
+// first slot in scan order (open list by id, then closed list by closing order) whose child
+// point equals (x, y) and whose scan key is >= from_key; returns the scan key or kIntMax.
+// scan key: open slot -> id ; closed slot -> n_nodes + closed_seq
+__device__ __forceinline__ int find_child_from(const WS& w, int n_nodes, double x, double y, int from_key, int* s_red) {
+  int best = kIntMax;
+  for (int id = threadIdx.x; id < n_nodes; id += kT) {
+    if (w.cx[id] == x && w.cy[id] == y) {
+      const int cs = w.closed_seq[id];
+      const int key = cs < 0 ? id : n_nodes + cs;
+      if (key >= from_key && key < best) best = key;
+    }
+  }
+  return block_min(best, s_red);
+}
+// slot id of a scan key (closed keys need a search: which slot has closed_seq == key - n_nodes)
+__device__ __forceinline__ int slot_of_key(const WS& w, int n_nodes, int key, int* s_red) {
+  if (key < n_nodes) return key;
+  const int cs = key - n_nodes;
+  int found = kIntMax;
+  for (int id = threadIdx.x; id < n_nodes; id += kT)
+    if (w.closed_seq[id] == cs) found = id;
+  return block_min(found, s_red);
+}
+
+// exact brute-force lookup of LP:56-57 for one key: first OPEN slot equal to the key (lowest
+// id) and whether ANY closed slot equals it.  Block-wide.
+__device__ __forceinline__ void scan_exact(const WS& w, int n_nodes, const double k[6], int* first_open,
+                                           int* any_closed, int* s_red) {
+  int fo = kIntMax, ac = 0;
+  for (int id = threadIdx.x; id < n_nodes; id += kT) {
+    if (w.cx[id] == k[0] && w.cy[id] == k[1] && w.px[id] == k[2] && w.py[id] == k[3] && w.hd[id] == k[4] &&
+        w.vel[id] == k[5]) {
+      if (w.closed_seq[id] < 0) fo = min(fo, id);
+      else ac = 1;
+    }
+  }
+  *first_open = block_min(fo, s_red);
+  *any_closed = block_max(ac, s_red);
+}
+
+__device__ __forceinline__ bool hash_contains(const WS& w, int hash_size, unsigned long long fp) {
+  unsigned pos = static_cast<unsigned>(fp >> 17) & (hash_size - 1);
+  for (;;) {
+    const unsigned long long e = w.hash[pos];
+    if (e == 0ull) return false;
+    if (e == fp) return true;
+    pos = (pos + 1) & (hash_size - 1);
+  }
+}
+__device__ __forceinline__ void hash_insert(const WS& w, int hash_size, unsigned long long fp) {
+  unsigned pos = static_cast<unsigned>(fp >> 17) & (hash_size - 1);
+  for (;;) {
+    const unsigned long long e = atomicCAS(&w.hash[pos], 0ull, fp);
+    if (e == 0ull || e == fp) return;
+    pos = (pos + 1) & (hash_size - 1);
+  }
+}
+
+// openNode (LP:98-102) for one node by thread 0 + heap push by warp 0.  Called by warp 0 only.
+__device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap, Shared* S, int hash_size,
+                                                 const double k[6], double g, double cost, int lane) {
+  const int id = S->n_nodes;
+  if (lane == 0) {
+    w.cx[id] = k[0]; w.cy[id] = k[1]; w.px[id] = k[2]; w.py[id] = k[3]; w.hd[id] = k[4]; w.vel[id] = k[5];
+    w.g[id] = g; w.cost[id] = cost;
+    w.closed_seq[id] = -1;
+    const unsigned long long fp = key_fingerprint(k);
+    w.fp[id] = fp;
+    if (hash_contains(w, hash_size, fp)) S->dup_seen = 1;
+    hash_insert(w, hash_size, fp);
+  }
+  __syncwarp();
+  heap_push_warp(heap, &S->heap_size, cost, id, lane);
+  if (lane == 0) S->n_nodes = id + 1;
+  __syncwarp();
+}
+
+// closeNode (LP:104-113): find the first open slot equal to frontier.top(), move it to the
+// closed list, pop the frontier.  Block-wide; returns the closed slot id (or -1).
+__device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* S, int* s_red) {
+  const int top_id = heap.id[0];
+  int target = top_id;
+  if (S->dup_seen) {
+    // equal keys may exist: reproduce std::find over m_tree_open (first equal, lowest id)
+    double k[6] = {w.cx[top_id], w.cy[top_id], w.px[top_id], w.py[top_id], w.hd[top_id], w.vel[top_id]};
+    int fo, ac;
+    scan_exact(w, S->n_nodes, k, &fo, &ac, s_red);
+    target = fo == kIntMax ? -1 : fo;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0 && target >= 0) {
+      w.closed_seq[target] = S->n_closed;
+      S->n_closed = S->n_closed + 1;
+    }
+    __syncwarp();
+    heap_pop_warp(heap, &S->heap_size, threadIdx.x);
+  }
+  __syncthreads();
+  return target;
+}
+
+__global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ Shared S;
+  __shared__ int s_red[kWarps];
+  __shared__ int s_scan[kWarps];
+  __shared__ double s_vlist[kMaxVel];
+  __shared__ unsigned long long s_dig[kWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const pp_params& P = A.P;
+  const int NC = A.NC;
+
+  for (;;) {
+    if (tid == 0) S.q = atomicAdd(A.work_counter, 1);
+    __syncthreads();
+    const int q = S.q;
+    __syncthreads();
+    if (q >= A.n_queries) return;
+
+    const WS w = ws_view(A.ws_base + static_cast<size_t>(A.ws_per_query ? q : blockIdx.x) * A.ws_stride, NC,
+                         A.hash_size);
+    Heap heap;
+    if (A.heap_in_smem) {
+      heap.cost = reinterpret_cast<double*>(smem_raw);
+      heap.id = reinterpret_cast<int*>(smem_raw + sizeof(double) * NC);
+    } else {
+      heap.cost = w.heap_cost_g;
+      heap.id = w.heap_id_g;
+    }
+    const pp_query qq = A.queries[q];
+    QueryD Q;
+    Q.gx = qq.goal_x; Q.gy = qq.goal_y; Q.gs = qq.goal_speed;
+    Q.max_speed = qq.max_speed; Q.max_accel = qq.max_accel; Q.start_speed = qq.start_speed;
+    int* exp_out = A.out_exp ? A.out_exp + static_cast<size_t>(q) * A.cap_exp : nullptr;
+
+    // ---- initializePlanner (LP:84-96) ------------------------------------------------
+    for (int k = tid; k < A.hash_size; k += kT) w.hash[k] = 0ull;
+    if (tid == 0) {
+      S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
+      S.n_cand_total = 0; S.n_coll_total = 0; S.goal_hit = 0; S.path_len = 0; S.truncated = 0; S.done = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double k0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, Q.start_speed};
+      open_single_warp0(w, heap, &S, A.hash_size, k0, 0.0, 9999999999.0, lane);
+    }
+    __syncthreads();
+
+    // ---- while(true) of LP:31 ---------------------------------------------------------
+    for (;;) {
+      // caps replace the ros::Time guard of LP:33-39
+      if (S.n_exp >= P.max_expansions || S.n_nodes >= P.max_nodes) { if (tid == 0) S.status = PP_PLAN_CAP; break; }
+      if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }  // top() of an empty queue
+      const int top_id = heap.id[0];                                                  // LP:40
+      // current_node's fields are key fields, identical for every copy of the node
+      const double ncx = w.cx[top_id], ncy = w.cy[top_id], npx = w.px[top_id], npy = w.py[top_id];
+      const double nhd = w.hd[top_id], nvel = w.vel[top_id];
+      __syncthreads();
+      const int closed_id = close_top(w, heap, &S, s_red);                            // LP:41
+      if (tid == 0) {
+        if (exp_out && S.n_exp < A.cap_exp) exp_out[S.n_exp] = closed_id;
+        S.n_exp = S.n_exp + 1;
+        S.goal_hit = 0;
+      }
+      __syncthreads();
+
+      // ---- checkForGoal (LP:269-287) over interpolatePoints(child, parent) (LP:301-316) --
+      if (warp == 0) {
+        const double dx = dm::sub(ncx, npx), dy = dm::sub(ncy, npy);
+        const double angle = dm::atan2_(dy, dx);
+        const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
+        int n_pts;
+        if (!dm::trunc_to_int(dm::mul(dm::div(dist, P.search_res), 2.0), &n_pts)) n_pts = 0;
+        double sa, ca;
+        dm::sincos(angle, &sa, &ca);
+        const bool speed_ok = fabs(dm::sub(nvel, Q.gs)) <= P.goal_speed_tolerance;
+        for (int base = 0; base < n_pts; base += 32) {
+          const int i = base + lane;
+          bool hit = false;
+          double x = 0, y = 0;
+          if (i < n_pts) {
+            const double t = dm::mul(dm::div(static_cast<double>(i), static_cast<double>(n_pts)), dist);
+            x = dm::add(ncx, dm::mul(t, ca));
+            y = dm::add(ncy, dm::mul(t, sa));
+            hit = speed_ok && fabs(dm::sub(x, Q.gx)) <= P.goal_pos_tolerance &&
+                  fabs(dm::sub(y, Q.gy)) <= P.goal_pos_tolerance;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (m) {
+            const int src = __ffs(m) - 1;  // first point in loop order
+            if (lane == src) {
+              // interpolateToGoalPoint (LP:289-299)
+              S.goal_node[0] = x; S.goal_node[1] = y; S.goal_node[2] = ncx; S.goal_node[3] = ncy;
+              S.goal_node[4] = dm::atan2_(dm::sub(y, ncy), dm::sub(x, ncx));
+              S.goal_node[5] = Q.gs;
+              S.goal_hit = 1;
+            }
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      if (S.goal_hit) {
+        if (warp == 0) {
+          double k[6];
+          for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
+          open_single_warp0(w, heap, &S, A.hash_size, k, 0.0, 0.0, lane);             // LP:45
+        }
+        __syncthreads();
+        if (tid == 0) S.status = PP_PLAN_FOUND;
+        break;
+      }
+
+      // ---- getNeighbors (LP:146-169) -------------------------------------------------------
+      if (tid == 0) {
+        // calcPossibleVelocities (LP:191-216)
+        const double time_step = dm::div(P.time_step_ms, 1000.0);
+        const double hi = dm::add(nvel, dm::mul(Q.max_accel, time_step));
+        const double lo = dm::sub(nvel, dm::mul(Q.max_accel, time_step));
+        const double range = dm::sub(hi, lo);
+        int n;
+        if (!dm::trunc_to_int(dm::div(range, P.velocity_res), &n)) n = 0;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+          const double v = dm::add(lo, dm::mul(static_cast<double>(i), P.velocity_res));
+          if (v == 0 && Q.gs != 0) continue;
+          if (v > Q.max_speed || v < 0) continue;
+          if (cnt < kMaxVel) s_vlist[cnt] = v;
+          cnt++;
+        }
+        // calcPossibleYaws (LP:218-232): `for (int i = 0; i < double_n; i++)`
+        const double yhi = dm::add(nhd, P.heading_diff), ylo = dm::sub(nhd, P.heading_diff);
+        const double yn = dm::div(dm::sub(yhi, ylo), P.heading_res);
+        int n_yaw = 0;
+        if (yn > 0) n_yaw = yn >= 4096.0 ? 4096 : __double2int_ru(yn);
+        if (cnt > kMaxVel || static_cast<long long>(cnt) * n_yaw + S.n_nodes + 2 > A.NC) { S.status = PP_PLAN_BROKEN; cnt = 0; }
+        S.n_vel = cnt;
+        S.n_yaw = n_yaw;
+      }
+      __syncthreads();
+      if (S.status == PP_PLAN_BROKEN) break;
+      const int n_yaw = S.n_yaw, n_cand = S.n_vel * n_yaw;
+      const double ylo = dm::sub(nhd, P.heading_diff);
+      const int base_nodes = S.n_nodes;
+      int appended = 0;  // block-uniform running count
+      int collided_local = 0;
+      for (int c0 = 0; c0 < n_cand; c0 += kT) {
+        const int c = c0 + tid;
+        bool alive = false;
+        double k[6] = {0, 0, 0, 0, 0, 0};
+        double g = 0, cost = 0;
+        unsigned long long fp = 0;
+        bool suspicious = false;
+        if (c < n_cand) {
+          const int vi = c / n_yaw, yi = c - vi * n_yaw;
+          const double vel = s_vlist[vi];
+          const double yaw = dm::add(ylo, dm::mul(static_cast<double>(yi), P.heading_res));
+          const double sum_v = dm::add(nvel, vel);                                     // LP:155
+          const double step = dm::div(dm::mul(sum_v, P.time_step_ms), 1000.0);
+          double sy, cyaw;
+          dm::sincos(yaw, &sy, &cyaw);
+          const double x = dm::add(ncx, dm::mul(step, cyaw));                          // LP:156
+          const double y = dm::add(ncy, dm::mul(step, sy));                            // LP:157
+          if (collide_pose_thread(A.g, A.cp, x, y, yaw)) {                             // LP:159
+            collided_local++;
+          } else {
+            alive = true;
+            k[0] = x; k[1] = y; k[2] = ncx; k[3] = ncy; k[4] = yaw; k[5] = vel;
+            const double ddx = dm::sub(x, ncx), ddy = dm::sub(y, ncy);
+            g = __dsqrt_rn(dm::add(dm::mul(ddx, ddx), dm::mul(ddy, ddy)));            // LP:162 (+ LP:139-144)
+            cost = dm::add(g, calc_h(P, Q, x, y, yaw, vel));                           // LP:163
+            fp = key_fingerprint(k);
+            suspicious = hash_contains(w, A.hash_size, fp);
+          }
+        }
+        // LP:56-72.  A fingerprint never seen before cannot equal any node: open it.  A seen
+        // fingerprint takes the exact scan (rare).
+        for (;;) {
+          const int owner = block_min(suspicious ? tid : kIntMax, s_red);
+          if (owner == kIntMax) break;
+          if (tid == owner) {
+            for (int cix = 0; cix < 6; ++cix) S.goal_node[cix] = k[cix];
+          }
+          __syncthreads();
+          double kk[6];
+          for (int cix = 0; cix < 6; ++cix) kk[cix] = S.goal_node[cix];
+          int fo, ac;
+          scan_exact(w, S.n_nodes, kk, &fo, &ac, s_red);
+          if (tid == owner) {
+            if (ac) {
+              alive = false;                               // in closed: dropped (LP:58)
+            } else if (fo != kIntMax) {                    // in open: LP:66-70
+              if (g < w.g[fo]) { w.g[fo] = g; w.cost[fo] = cost; }  // overwrite the stored copy in place
+              S.dup_seen = 1;                              // ... and a duplicate is pushed anyway
+            }
+            suspicious = false;
+          }
+          __syncthreads();
+        }
+        // order-preserving compaction of the survivors of this chunk
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_scan[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) {
+          const int v = s_scan[ww];
+          if (ww < warp) before += v;
+          total += v;
+        }
+        const int rank = appended + before + __popc(bal & ((1u << lane) - 1u));
+        if (alive) {
+          const int id = base_nodes + rank;
+          w.cx[id] = k[0]; w.cy[id] = k[1]; w.px[id] = k[2]; w.py[id] = k[3]; w.hd[id] = k[4]; w.vel[id] = k[5];
+          w.g[id] = g; w.cost[id] = cost;
+          w.closed_seq[id] = -1;
+          w.fp[id] = fp;
+          hash_insert(w, A.hash_size, fp);
+        }
+        appended += total;
+        __syncthreads();
+      }
+      collided_local = block_sum(collided_local, s_red);
+      // openNode for every survivor, in order: frontier pushes by warp 0 (LP:62 / LP:70)
+      if (warp == 0) {
+        for (int r = 0; r < appended; ++r) {
+          const int id = base_nodes + r;
+          heap_push_warp(heap, &S.heap_size, w.cost[id], id, lane);
+        }
+        if (lane == 0) {
+          S.n_nodes = base_nodes + appended;
+          S.n_cand_total += n_cand;
+          S.n_coll_total += collided_local;
+        }
+      }
+      __syncthreads();
+      if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }
+      close_top(w, heap, &S, s_red);                                                  // LP:80
+    }
+    __syncthreads();
+
+    // ---- outputs -----------------------------------------------------------------------
+    const int n_nodes = S.n_nodes;
+    double* path = A.out_path + static_cast<size_t>(q) * A.cap_path * 2;
+    int* path_ids = A.out_path_ids + static_cast<size_t>(q) * A.cap_path;
+    double* prof = A.out_profile + static_cast<size_t>(q) * A.cap_path * 3;
+    int n_path = 0, n_profile = 0;
+    if (S.status == PP_PLAN_FOUND) {
+      // calcPathMsg (LP:503-527): the walk is sequential, each link search is block-parallel.
+      // The reversed path is staged in the (now idle) heap-cost array of this workspace.
+      double* rev = w.heap_cost_g;  // NC doubles: room for NC/2 points
+      const int rev_cap = NC / 2;
+      double cxp = S.goal_node[0], cyp = S.goal_node[1];
+      int len = 0;
+      if (tid == 0) { rev[0] = cxp; rev[1] = cyp; }
+      len = 1;
+      bool broken = false;
+      while (!(cxp == 0 && cyp == 0)) {               // LP:509 -- checked between passes only
+        int pos = 0;
+        bool progressed = false;
+        for (;;) {
+          const int key = find_child_from(w, n_nodes, cxp, cyp, pos, s_red);
+          if (key == kIntMax) break;                   // end of this pass over open + closed
+          const int id = slot_of_key(w, n_nodes, key, s_red);
+          cxp = w.px[id]; cyp = w.py[id];
+          if (len < rev_cap) { if (tid == 0) { rev[2 * len] = cxp; rev[2 * len + 1] = cyp; } }
+          len++;
+          progressed = true;
+          pos = key + 1;
+          if (len > n_nodes + 2) break;
+        }
+        if (!progressed || len > n_nodes + 2 || len >= rev_cap) { broken = true; break; }
+      }
+      __syncthreads();
+      if (broken) {
+        if (tid == 0) S.status = PP_PLAN_BROKEN;
+      } else {
+        n_path = len;
+        for (int k = tid; k < len && k < A.cap_path; k += kT) {   // LP:530-538: reversed
+          path[2 * k] = rev[2 * (len - 1 - k)];
+          path[2 * k + 1] = rev[2 * (len - 1 - k) + 1];
+        }
+        if (len > A.cap_path && tid == 0) S.truncated = 1;
+        __syncthreads();
+        // calcMPMessage (LP:542-583): per consecutive pose pair, LAST match in list order;
+        // `else if` means a node matching the current pose never counts for the next pose
+        n_profile = len >= 2 ? len - 2 : 0;
+        for (int i = warp; i < n_profile; i += kWarps) {
+          const double ax = rev[2 * (len - 1 - i)], ay = rev[2 * (len - 1 - i) + 1];
+          const double bx = rev[2 * (len - 2 - i)], by = rev[2 * (len - 2 - i) + 1];
+          int best_a = -1, best_b = -1, id_a = -1, id_b = -1;
+          for (int id = lane; id < n_nodes; id += 32) {
+            const double ex = w.cx[id], ey = w.cy[id];
+            const int cs = w.closed_seq[id];
+            const int key = cs < 0 ? id : n_nodes + cs;
+            if (ex == ax && ey == ay) { if (key > best_a) { best_a = key; id_a = id; } }
+            else if (ex == bx && ey == by) { if (key > best_b) { best_b = key; id_b = id; } }
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const int oa = __shfl_xor_sync(0xffffffffu, best_a, off), oia = __shfl_xor_sync(0xffffffffu, id_a, off);
+            const int ob = __shfl_xor_sync(0xffffffffu, best_b, off), oib = __shfl_xor_sync(0xffffffffu, id_b, off);
+            if (oa > best_a) { best_a = oa; id_a = oia; }
+            if (ob > best_b) { best_b = ob; id_b = oib; }
+          }
+          if (lane == 0 && i < A.cap_path) {
+            const double cur_heading = id_a >= 0 ? w.hd[id_a] : 0.0;
+            const double next_heading = id_b >= 0 ? w.hd[id_b] : 0.0;
+            const double next_velocity = id_b >= 0 ? w.vel[id_b] : 0.0;
+            prof[i] = dm::div(dm::sub(next_heading, cur_heading), dm::div(P.time_step_ms, 1000.0));  // LP:576-577
+            prof[A.cap_path + i] = P.time_step_ms;                                                    // LP:578
+            prof[2 * A.cap_path + i] = next_velocity;                                                 // LP:579
+          }
+        }
+        __syncthreads();
+        if (A.want_path_ids) {
+          for (int k = 0; k < len && k < A.cap_path; ++k) {
+            const double x = rev[2 * (len - 1 - k)], y = rev[2 * (len - 1 - k) + 1];
+            const int key = find_child_from(w, n_nodes, x, y, 0, s_red);
+            const int id = key == kIntMax ? -1 : slot_of_key(w, n_nodes, key, s_red);
+            if (tid == 0) path_ids[k] = id;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // tree digest over every slot's key
+    unsigned long long dig = 0;
+    for (int id = tid; id < n_nodes; id += kT) {
+      const double k[6] = {w.cx[id], w.cy[id], w.px[id], w.py[id], w.hd[id], w.vel[id]};
+      dig += node_digest(id, k);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dig += __shfl_xor_sync(0xffffffffu, dig, off);
+    if (lane == 0) s_dig[warp] = dig;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long d = 0;
+      for (int ww = 0; ww < kWarps; ++ww) d += s_dig[ww];
+      PlanHdr hd;
+      hd.status = S.status;
+      hd.n_expansions = S.n_exp;
+      hd.n_nodes = n_nodes;
+      hd.n_closed = S.n_closed;
+      hd.n_open = n_nodes - S.n_closed;
+      hd.n_path = S.status == PP_PLAN_FOUND ? n_path : 0;
+      hd.n_profile = S.status == PP_PLAN_FOUND ? n_profile : 0;
+      hd.n_candidates = S.n_cand_total;
+      hd.n_collisions = S.n_coll_total;
+      hd.truncated = S.truncated;
+      hd.digest = d;
+      A.hdr[q] = hd;
+    }
+    __syncthreads();
+  }
+}
+
+// node_parent (first node in scan order whose child_point == this node's parent_point,
+// LP:511-526) for every slot of every query: one warp per target node.
+__global__ void __launch_bounds__(256)
+parent_ids_kernel(const unsigned char* ws_base, size_t ws_stride, int NC, int hash_size, const PlanHdr* hdr,
+                  int n_queries, int* out_parent /* [n][NC] */) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long t = warp; t < static_cast<long long>(n_queries) * NC; t += n_warps) {
+    const int q = static_cast<int>(t / NC), id = static_cast<int>(t % NC);
+    const int n_nodes = hdr[q].n_nodes;
+    if (id >= n_nodes) continue;
+    const WS w = ws_view(const_cast<unsigned char*>(ws_base) + static_cast<size_t>(q) * ws_stride, NC, hash_size);
+    const double x = w.px[id], y = w.py[id];
+    int best = kIntMax, best_id = -1;
+    for (int k = lane; k < n_nodes; k += 32) {
+      if (w.cx[k] == x && w.cy[k] == y) {
+        const int cs = w.closed_seq[k];
+        const int key = cs < 0 ? k : n_nodes + cs;
+        if (key < best) { best = key; best_id = k; }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, off), oi = __shfl_xor_sync(0xffffffffu, best_id, off);
+      if (ob < best) { best = ob; best_id = oi; }
+    }
+    if (lane == 0) out_parent[static_cast<size_t>(q) * NC + id] = best_id;
+  }
+}
+
+}  // namespace
+
+}  // namespace pp
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct PlanWorkspace {
+  unsigned char* ws = nullptr;
+  size_t ws_bytes_total = 0;
+  void* out = nullptr;          // hdr + path + path ids + profile + expansions
+  size_t out_bytes = 0;
+  pp_query* d_queries = nullptr;
+  int queries_cap = 0;
+  int* d_parent = nullptr;
+  size_t parent_bytes = 0;
+  int* d_counter = nullptr;
+  std::vector<unsigned char> h_out;
+};
+
+namespace pp {
+
+void plan_free(pp_handle* h) {
+  if (!h->plan_ws) return;
+  cudaFree(h->plan_ws->ws);
+  cudaFree(h->plan_ws->out);
+  cudaFree(h->plan_ws->d_queries);
+  cudaFree(h->plan_ws->d_parent);
+  cudaFree(h->plan_ws->d_counter);
+  delete h->plan_ws;
+  h->plan_ws = nullptr;
+}
+
+static int grow(void** p, size_t* have, size_t want) {
+  if (want <= *have) return PP_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  PP_CUDA(cudaMalloc(p, want));
+  *have = want;
+  return PP_OK;
+}
+
+int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
+  if (!h->plan_ws) {
+    h->plan_ws = new PlanWorkspace();
+    PP_CUDA(cudaMalloc(&h->plan_ws->d_counter, sizeof(int)));
+  }
+  PlanWorkspace* W = h->plan_ws;
+  cudaStream_t s = h->stream;
+  const pp_params& P = h->P;
+  PP_REQUIRE(P.max_nodes >= 1 && P.max_nodes <= (1 << 24), "pp_plan: max_nodes out of range");
+
+  bool want_nodes = false, want_exp = false, want_path_ids = false;
+  int cap_path = 2, cap_exp = 0;
+  for (int k = 0; k < n; ++k) {
+    want_nodes |= rs[k].node_state || rs[k].node_parent || rs[k].node_closed_seq;
+    want_exp |= rs[k].expansion_ids != nullptr;
+    want_path_ids |= rs[k].path_node_ids != nullptr;
+    cap_path = std::max(cap_path, rs[k].cap_path);
+    if (rs[k].expansion_ids) cap_exp = std::max(cap_exp, rs[k].cap_expansions);
+  }
+  cap_path = std::min(cap_path, 1 << 16);
+
+  // one expansion can add up to kMaxCand children after the cap check, + the goal node
+  // children one expansion can add after the cap check passed (+ the terminal node)
+  long long max_children = 1;
+  for (int k = 0; k < n; ++k) {
+    const double nv = 2.0 * qs[k].max_accel * (P.time_step_ms / 1000.0) / P.velocity_res;
+    const double ny = 2.0 * P.heading_diff / P.heading_res;
+    const long long c = (static_cast<long long>(nv > 0 ? nv : 0) + 2) * (static_cast<long long>(ny > 0 ? ny : 0) + 2);
+    max_children = std::max(max_children, c);
+  }
+  if (max_children > kMaxCand) {
+    set_last_error("pp_plan: more than 8192 children per expansion (velocity_res / heading_res too fine)");
+    return PP_ERR_UNSUPPORTED;
+  }
+  const int NC = P.max_nodes + static_cast<int>(max_children) + 64;
+  int hash_size = 1024;
+  while (hash_size < 2 * NC) hash_size <<= 1;
+  const size_t stride = ws_bytes(NC, hash_size);
+
+  const size_t heap_smem = (sizeof(double) + sizeof(int)) * static_cast<size_t>(NC);
+  const int heap_in_smem = heap_smem <= 200 * 1024 ? 1 : 0;
+  const size_t dyn_smem = heap_in_smem ? heap_smem : 0;
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int ctas_per_sm = 1;
+  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel, kT, dyn_smem));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int max_ctas = h->sm_count * ctas_per_sm;
+  const int grid = std::min(n, max_ctas);
+  const int n_ws = want_nodes ? n : grid;
+
+  int rc = grow(reinterpret_cast<void**>(&W->ws), &W->ws_bytes_total, stride * static_cast<size_t>(n_ws));
+  if (rc) return rc;
+  // output block layout
+  const size_t hdr_b = (sizeof(PlanHdr) * n + 255) & ~size_t(255);
+  const size_t path_b = (sizeof(double) * 2 * cap_path * n + 255) & ~size_t(255);
+  const size_t pid_b = (sizeof(int) * cap_path * static_cast<size_t>(n) + 255) & ~size_t(255);
+  const size_t prof_b = (sizeof(double) * 3 * cap_path * n + 255) & ~size_t(255);
+  const size_t exp_b = want_exp ? ((sizeof(int) * static_cast<size_t>(cap_exp) * n + 255) & ~size_t(255)) : 0;
+  const size_t out_total = hdr_b + path_b + pid_b + prof_b + exp_b;
+  rc = grow(&W->out, &W->out_bytes, out_total);
+  if (rc) return rc;
+  if (n > W->queries_cap) {
+    cudaFree(W->d_queries);
+    W->d_queries = nullptr;
+    W->queries_cap = 0;
+    PP_CUDA(cudaMalloc(&W->d_queries, sizeof(pp_query) * n));
+    W->queries_cap = n;
+  }
+  PP_CUDA(cudaMemcpyAsync(W->d_queries, qs, sizeof(pp_query) * n, cudaMemcpyHostToDevice, s));
+  PP_CUDA(cudaMemsetAsync(W->d_counter, 0, sizeof(int), s));
+
+  unsigned char* ob = static_cast<unsigned char*>(W->out);
+  PlanArgs A;
+  A.g = h->grid;
+  A.cp = collide_params(h);
+  A.P = P;
+  A.queries = W->d_queries;
+  A.n_queries = n;
+  A.NC = NC;
+  A.hash_size = hash_size;
+  A.heap_in_smem = heap_in_smem;
+  A.ws_per_query = want_nodes ? 1 : 0;
+  A.want_path_ids = want_path_ids ? 1 : 0;
+  A.cap_path = cap_path;
+  A.cap_exp = cap_exp;
+  A.ws_stride = stride;
+  A.ws_base = W->ws;
+  A.hdr = reinterpret_cast<PlanHdr*>(ob);
+  A.out_path = reinterpret_cast<double*>(ob + hdr_b);
+  A.out_path_ids = reinterpret_cast<int*>(ob + hdr_b + path_b);
+  A.out_profile = reinterpret_cast<double*>(ob + hdr_b + path_b + pid_b);
+  A.out_exp = want_exp ? reinterpret_cast<int*>(ob + hdr_b + path_b + pid_b + prof_b) : nullptr;
+  A.work_counter = W->d_counter;
+
+  PP_CUDA(cudaEventRecord(h->ev[8], s));
+  plan_kernel<<<grid, kT, dyn_smem, s>>>(A);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  bool want_parent = false;
+  for (int k = 0; k < n; ++k) want_parent |= rs[k].node_parent != nullptr;
+  if (want_parent) {
+    rc = grow(reinterpret_cast<void**>(&W->d_parent), &W->parent_bytes, sizeof(int) * static_cast<size_t>(NC) * n);
+    if (rc) return rc;
+    parent_ids_kernel<<<h->sm_count * 8, 256, 0, s>>>(W->ws, stride, NC, hash_size, A.hdr, n, W->d_parent);
+    h->launches++;
+    PP_CUDA(cudaGetLastError());
+  }
+  PP_CUDA(cudaEventRecord(h->ev[9], s));
+
+  W->h_out.resize(out_total);
+  PP_CUDA(cudaMemcpyAsync(W->h_out.data(), W->out, out_total, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]);
+  h->phase_ms[PP_PHASE_PLAN] = ms;
+
+  const unsigned char* hb = W->h_out.data();
+  const PlanHdr* hdr = reinterpret_cast<const PlanHdr*>(hb);
+  const double* hpath = reinterpret_cast<const double*>(hb + hdr_b);
+  const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + path_b);
+  const double* hprof = reinterpret_cast<const double*>(hb + hdr_b + path_b + pid_b);
+  const int* hexp = want_exp ? reinterpret_cast<const int*>(hb + hdr_b + path_b + pid_b + prof_b) : nullptr;
+  int ret = PP_OK;
+  std::vector<double> soa;
+  std::vector<int> iso;
+  for (int k = 0; k < n; ++k) {
+    pp_result& r = rs[k];
+    const PlanHdr& d = hdr[k];
+    r.status = d.status;
+    r.n_expansions = d.n_expansions;
+    r.n_nodes = d.n_nodes;
+    r.n_open = d.n_open;
+    r.n_closed = d.n_closed;
+    r.n_path = d.n_path;
+    r.n_profile = d.n_profile;
+    r.n_candidates = d.n_candidates;
+    r.n_collisions = d.n_collisions;
+    r.tree_digest = d.digest;
+    const int np = std::min(d.n_path, std::min(r.cap_path, cap_path));
+    if (d.n_path > r.cap_path && (r.path_xy || r.path_node_ids)) ret = PP_ERR_CAPACITY;
+    if (r.path_xy) std::memcpy(r.path_xy, hpath + static_cast<size_t>(k) * cap_path * 2, sizeof(double) * 2 * np);
+    if (r.path_node_ids) std::memcpy(r.path_node_ids, hpid + static_cast<size_t>(k) * cap_path, sizeof(int) * np);
+    const int nm = std::min(d.n_profile, std::min(r.cap_path, cap_path));
+    const double* pr = hprof + static_cast<size_t>(k) * cap_path * 3;
+    if (r.yaw_rates) std::memcpy(r.yaw_rates, pr, sizeof(double) * nm);
+    if (r.durations) std::memcpy(r.durations, pr + cap_path, sizeof(double) * nm);
+    if (r.speeds) std::memcpy(r.speeds, pr + 2 * cap_path, sizeof(double) * nm);
+    if (r.expansion_ids) {
+      const int ne = std::min(d.n_expansions, r.cap_expansions);
+      if (d.n_expansions > r.cap_expansions) ret = PP_ERR_CAPACITY;
+      std::memcpy(r.expansion_ids, hexp + static_cast<size_t>(k) * cap_exp, sizeof(int) * ne);
+    }
+    if (r.node_state || r.node_closed_seq || r.node_parent) {
+      const int nn = std::min(d.n_nodes, r.cap_nodes);
+      if (d.n_nodes > r.cap_nodes) ret = PP_ERR_CAPACITY;
+      const unsigned char* wsq = W->ws + static_cast<size_t>(k) * stride;
+      if (r.node_state) {
+        soa.resize(static_cast<size_t>(8) * NC);
+        PP_CUDA(cudaMemcpyAsync(soa.data(), wsq, sizeof(double) * 8 * NC, cudaMemcpyDeviceToHost, s));
+        PP_CUDA(cudaStreamSynchronize(s));
+        for (int id = 0; id < nn; ++id)
+          for (int c = 0; c < 8; ++c) r.node_state[8 * static_cast<size_t>(id) + c] = soa[static_cast<size_t>(c) * NC + id];
+      }
+      if (r.node_closed_seq) {
+        const size_t off = sizeof(double) * 8 * NC + sizeof(unsigned long long) * NC +
+                           sizeof(unsigned long long) * hash_size + sizeof(double) * NC;
+        PP_CUDA(cudaMemcpyAsync(r.node_closed_seq, wsq + off, sizeof(int) * nn, cudaMemcpyDeviceToHost, s));
+      }
+      if (r.node_parent)
+        PP_CUDA(cudaMemcpyAsync(r.node_parent, W->d_parent + static_cast<size_t>(k) * NC, sizeof(int) * nn,
+                                cudaMemcpyDeviceToHost, s));
+      PP_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  if (ret == PP_ERR_CAPACITY) set_last_error("pp_plan: a caller-provided output array is too small");
+  return ret;
+}
+
+}  // namespace pp

@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- collision checks/s (and plans/s) of the Prius planner hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the CPU arm)
+
+Headline workload = BASELINE.json configs[2], the configuration the metric's
+"collision checks/sec at 1/2/4/8 B200" is quoted on: 2^24 oriented-footprint poses per GPU
+against a 4096 x 4096 synthetic grid at 0.1 m (weak scaling: every rank checks its own
+2^24 poses; flags gathered with one NCCL all-gather inside the timed region).  A "step" is
+one pass of the batch through pp_collide_batch_dev.  The single-query / batched-plan
+figures (configs[1] and [4]) are reported in the same JSON line under "plans".
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POSES = 1 << 24
+GRID = 4096
+RES = 0.1
+ALG_BYTES_ORIENTED = 12 + 1 + 48 * 17   # pose + flag + one byte per lattice sample = 829 B
+ALG_BYTES_AABB = 12 + 1 + 47 * 15       # 718 B
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_grid():
+    from autonomouscar_b200 import worlds
+    return worlds.block_grid(GRID, GRID, frac=0.01, block=16, seed=20181)
+
+
+def params(mode):
+    from autonomouscar_b200 import default_params
+    return default_params(costmap_res=RES, costmap_width=GRID, costmap_height=GRID, collision_mode=mode)
+
+
+# -----------------------------------------------------------------------------------------
+# the CPU arm: the oracle (a port; the reference needs ROS and cannot be built here)
+# -----------------------------------------------------------------------------------------
+def cpu_collide_rate(grid, mode, n_sample, threads, seed=1):
+    from autonomouscar_b200 import worlds
+    from oracle import binding as orc
+    p = params(mode)
+    box = worlds.pose_box(p)
+    poses = orc.sample_poses(seed, 0, 0, n_sample, *box)
+    _, secs = orc.collide_batch(p, grid, poses, n_threads=threads)
+    return n_sample / secs, secs
+
+
+def run_reference(args):
+    from autonomouscar_b200 import PP_COLLISION_ORIENTED
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    grid = make_grid()
+    cores = os.cpu_count() or 1
+    n_sample = 1 << 22
+    rates = []
+    for _ in range(args.warmup):
+        cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 18, cores)
+    t0 = time.time()
+    for _ in range(args.steps):
+        r, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n_sample, cores)
+        rates.append(r)
+    wall = time.time() - t0
+    v = sum(rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": "collision_checks_per_sec", "value": v, "unit": "poses/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 fixed-point Q7.24 + f64 set-up", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: oriented-footprint poses vs 4096x4096 grid @0.1 m, "
+                               "1% area in 16x16-cell blocks", "poses_per_step": n_sample,
+                   "collision_mode": "ORIENTED"},
+        "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} of the 2^24 poses per step, std::thread x{cores}, g++ -O2"},
+        "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -----------------------------------------------------------------------------------------
+# our arm
+# -----------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from autonomouscar_b200 import (PP_COLLISION_ORIENTED, PP_COLLISION_REF_AABB, Planner, default_params,
+                                    make_query, worlds)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+
+    grid = make_grid()
+    p = params(PP_COLLISION_ORIENTED)
+    pl = Planner(p, device=local)
+    pl.set_grid(grid)
+    box = worlds.pose_box(p)
+    n = args.poses
+    # inputs resident in HBM before the timed region: the Philox sampler fills them (row S1)
+    poses = pl.sample_poses_dev(2018, rank, 0, n, *box)
+    flags = torch.empty(n, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(n * world, dtype=torch.uint8, device=dev) if multi else None
+    pl.sync()
+
+    def step():
+        pl.collide_dev(poses, out=flags)
+        if multi:
+            # result gather (north_star: NCCL only to gather results); ordered after the kernel
+            ev = torch.cuda.Event()
+            ev.record(pl.stream)
+            torch.cuda.current_stream().wait_event(ev)
+            dist.all_gather_into_tensor(gathered, flags)
+
+    def barrier():
+        pl.sync()
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    launches0 = pl.launch_count()
+    kernel_ms = []
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(pl.stream)
+        for _ in range(args.steps):
+            step()
+            if not multi:
+                pass
+        if multi:
+            evj = torch.cuda.Event()
+            evj.record(torch.cuda.current_stream())
+            pl.stream.wait_event(evj)
+        e1.record(pl.stream)
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    launches = pl.launch_count() - launches0
+    # per-launch duration of the dominant kernel (events recorded inside the library, on its stream)
+    for _ in range(3):
+        pl.collide_dev(poses, out=flags)
+        kernel_ms.append(pl.last_phase_ms()[2])
+    narrow_units = pl.last_narrow_count()
+    hit_rate = float(flags.float().mean().item())
+    t_ms = torch.tensor([dev_ms], device=dev)
+    if multi:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-pointer C-ABI call: pinned host poses in, host flags out
+    h_poses = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+    h_poses.copy_(poses)
+    h_flags = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        pl.collide(h_poses, out=h_flags)
+    if multi:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pl.collide(h_poses, out=h_flags)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t_e = torch.tensor([e2e_s], device=dev)
+    if multi:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = n * world / float(t_e.item())
+    assert torch.equal(h_flags, flags.cpu()), "host-pointer path and device path disagree"
+
+    # ---- secondary figures on rank 0 only: direct (no broad phase), REF_AABB, plans
+    extra = {}
+    if rank == 0:
+        def timed(fn, reps=5):
+            fn(); pl.sync()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(pl.stream)
+            for _ in range(reps):
+                fn()
+            b.record(pl.stream)
+            pl.sync()
+            return a.elapsed_time(b) / reps
+        pl.set_broad_phase(False)
+        ms_direct = timed(lambda: pl.collide_dev(poses, out=flags))
+        direct_units = pl.last_narrow_count()
+        pl.set_broad_phase(True)
+        pl.set_collision_mode(PP_COLLISION_REF_AABB)
+        ms_aabb = timed(lambda: pl.collide_dev(poses, out=flags))
+        pl.set_collision_mode(PP_COLLISION_ORIENTED)
+        ms_sampler = timed(lambda: pl.sample_poses_dev(2018, rank, 0, n, *box, out=poses))
+        extra = {
+            "oriented_direct_poses_per_s": n / (ms_direct * 1e-3), "oriented_direct_narrow_units": direct_units,
+            "oriented_direct_frac_of_hbm_roofline": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / _peaks()[0],
+            "ref_aabb_poses_per_s": n / (ms_aabb * 1e-3),
+            "ref_aabb_frac_of_hbm_roofline": ALG_BYTES_AABB * n / (ms_aabb * 1e-3) / 1e9 / _peaks()[0],
+            "philox_sampler_poses_per_s": n / (ms_sampler * 1e-3),
+            "philox_sampler_write_GBps": 12 * n / (ms_sampler * 1e-3) / 1e9,
+        }
+    plans = bench_plans(pl, rank, world, dev, multi, args) if not args.skip_plans else None
+
+    if rank == 0:
+        peak, peak_kind = _peaks()
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        achieved = ALG_BYTES_ORIENTED * n / (k_ms * 1e-3) / 1e9
+        cpu = None
+        if not args.skip_cpu:
+            cores = os.cpu_count() or 1
+            n_sample = 1 << 22
+            v, secs = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n_sample, cores)
+            v1, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 20, 1)
+            cpu = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_sample} of the 2^24 poses ({secs:.2f} s), oracle ORIENTED, std::thread x{cores}, "
+                             f"g++ -O2; single thread: {v1:.3e} poses/s"}
+        line = {
+            "metric": "collision_checks_per_sec", "value": value, "unit": "poses/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 fixed-point Q7.24 + f64 set-up", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: 2^24 oriented-footprint poses per GPU vs 4096x4096 "
+                                   "grid @0.1 m, 1% area in 16x16-cell blocks; flags all-gathered (NCCL) when N>1",
+                       "poses_per_gpu": n, "collision_mode": "ORIENTED", "broad_phase": True,
+                       "hit_rate": hit_rate, "l2_policy": "inputs larger than L2 (201 MB poses per step)"},
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": n},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "kernel": "collide_oriented_kernel", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_pose": ALG_BYTES_ORIENTED, "narrow_phase_poses": narrow_units},
+            "cpu_baseline": cpu,
+            "clocks": clk.summary(),
+            "wall_s_timed_region": wall,
+            "extra": extra,
+            "plans": plans,
+        }
+        print(json.dumps(line), flush=True)
+    pl.close()
+    if multi:
+        dist.destroy_process_group()
+
+
+def bench_plans(pl_unused, rank, world, dev, multi, args):
+    """configs[1] (single query, 10k-node cap) and configs[4] (independent queries, sharded
+    contiguously over the ranks, results gathered with NCCL).  Launch-file grid (300x300 @0.25 m)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from autonomouscar_b200 import PP_COLLISION_ORIENTED, PP_PLAN_FOUND, Planner, default_params, worlds
+    p = default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=10000)
+    grid = worlds.block_grid(300, 300, frac=0.01, block=4, seed=9)
+    worlds.clear_disc(grid, p, 0.0, 0.0, 4.0)
+    pl = Planner(p, device=dev.index)
+    pl.set_grid(grid)
+    n_total = args.queries * world
+    qs_all = worlds.forward_queries(n_total, seed=11)
+    lo = rank * args.queries
+    qs = qs_all[lo:lo + args.queries]
+    pl.plan_batch(qs[:64], want_nodes=False, cap_path=256, cap_expansions=1)   # warm-up
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = pl.plan_batch(qs, want_nodes=False, cap_path=256, cap_expansions=1)
+    rec = torch.tensor([[r.status, r.n_nodes, r.n_path, r.tree_digest & 0x7fffffff] for r in res],
+                       dtype=torch.int64, device=dev)
+    if multi:
+        out = torch.empty((n_total, 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, rec)
+        rec = out
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    kernel_ms = pl.last_phase_ms()[4]
+    # single-query latency (config 2)
+    lat = []
+    for k in range(5):
+        t1 = time.perf_counter()
+        r1 = pl.plan(qs[0], cap_nodes=16384)
+        lat.append(time.perf_counter() - t1)
+    out = None
+    if rank == 0:
+        found = int((rec[:, 0] == PP_PLAN_FOUND).sum().item())
+        out = {"batch_queries": n_total, "plans_per_s": n_total / dt, "batch_wall_s": dt,
+               "plan_kernel_ms_rank0": kernel_ms, "found": found,
+               "mean_nodes": float(rec[:, 1].float().mean().item()),
+               "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_nodes": int(r1.n_nodes),
+               "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000"}
+        if not args.skip_cpu:
+            from oracle import binding as orc
+            cores = os.cpu_count() or 1
+            nq = min(len(qs_all), 256)
+            secs, st, nn, dg = orc.plan_batch_timed(p, grid, qs_all[:nq], math_mode=orc.MATH_LIBM, n_threads=cores)
+            out["cpu_plans_per_s"] = nq / secs
+            out["cpu_cores"] = cores
+            secs1, *_ = orc.plan_batch_timed(p, grid, qs_all[:32], math_mode=orc.MATH_LIBM, n_threads=1)
+            out["cpu_plans_per_s_1thread"] = 32 / secs1
+            # parity of the sample against the deterministic oracle
+            secs2, st2, nn2, dg2 = orc.plan_batch_timed(p, grid, qs_all[:nq], math_mode=orc.MATH_DET, n_threads=cores)
+            mine = rec[:nq].cpu().numpy()
+            out["parity_sample_ok"] = bool((mine[:, 0] == st2).all() and (mine[:, 1] == nn2).all() and
+                                           (mine[:, 3] == (dg2 & np.uint64(0x7fffffff)).astype(np.int64)).all())
+    pl.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--poses", type=int, default=N_POSES)
+    ap.add_argument("--queries", type=int, default=1024, help="plan queries per GPU")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-plans", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

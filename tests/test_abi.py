@@ -1,0 +1,111 @@
+"""CPU tests of the boundary: the shared library loads without a GPU, exports every symbol
+include/prius_planner.h declares, the ctypes structs match the C layout, and the library
+refuses to work (loudly) when there is no CUDA device -- no CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "prius_planner.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from autonomouscar_b200 import _lib
+    return _lib.load()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from autonomouscar_b200 import _lib
+    declared = _declared_functions()
+    assert len(declared) >= 30
+    assert sorted(_lib.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layout_matches_c():
+    from autonomouscar_b200.capi import pp_params, pp_query, pp_result
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "prius_planner.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(pp_params), sizeof(pp_query), sizeof(pp_result),
+         offsetof(pp_params, collision_mode), offsetof(pp_params, rrt_goal_bias),
+         offsetof(pp_query, seed), offsetof(pp_result, node_state));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
+                               os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    want = [C.sizeof(pp_params), C.sizeof(pp_query), C.sizeof(pp_result), pp_params.collision_mode.offset,
+            pp_params.rrt_goal_bias.offset, pp_query.seed.offset, pp_result.node_state.offset]
+    assert [int(v) for v in out] == want
+
+
+def test_defaults_match_launch_file(lib):
+    from autonomouscar_b200.capi import default_params, pp_params
+    c = pp_params()
+    assert lib.pp_default_params(C.byref(c)) == 0
+    py = default_params()
+    for name, _ in pp_params._fields_:
+        if name == "reserved":
+            continue
+        assert getattr(c, name) == getattr(py, name), name
+    # full_sim.launch:77-79,90-97
+    assert (c.costmap_res, c.costmap_width, c.costmap_height) == (0.25, 300, 300)
+    assert (c.time_step_ms, c.velocity_res, c.heading_res, c.heading_diff) == (150.0, 0.1, 0.005, 0.065)
+    assert (c.goal_pos_tolerance, c.goal_speed_tolerance, c.search_res, c.max_velocity) == (0.1, 0.5, 0.25, 15.0)
+    assert (c.car_length, c.car_width) == (4.7, 1.586)
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from autonomouscar_b200 import Planner, PlannerError
+    with pytest.raises(PlannerError) as e:
+        Planner()
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_argument_errors_do_not_need_a_device(lib):
+    from autonomouscar_b200.capi import default_params
+    h = C.c_void_p()
+    assert lib.pp_create(None, 0, C.byref(h)) == 1                     # PP_ERR_INVALID
+    bad = default_params(costmap_width=0)
+    assert lib.pp_create(C.byref(bad), 0, C.byref(h)) == 1
+    assert b"empty grid" in lib.pp_last_error()
+    wide = default_params(costmap_res=0.01)                           # footprint wider than the tile window
+    assert lib.pp_create(C.byref(wide), 0, C.byref(h)) == 5           # PP_ERR_UNSUPPORTED
+    assert lib.pp_abi_version() == 1
+
+
+def test_product_never_touches_the_oracle():
+    """The product package must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "autonomouscar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), (dirpath, f)
+                assert not re.search(r"#\s*include\s*[<\"][^>\"]*oracle", text), (dirpath, f)
+                assert "liboracle" not in text and "oracle/build" not in text, (dirpath, f)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libprius_planner_b200.so")], capture_output=True, text=True).stdout
+    assert "liboracle" not in out
