@@ -30,9 +30,13 @@ def test_velocity_lattice(oracle):
     v1 = oracle.possible_velocities(p, q, 1.0)
     assert len(v1) == 4 and v1[0] == 0.775 and np.all(np.diff(v1) > 0)
     # v == 0 is skipped unless the goal speed is 0 (LP:205)
-    q0 = make_query(20, 0, goal_speed=0.0)
-    assert 0.0 in oracle.possible_velocities(p, q0, 0.225)
-    assert 0.0 not in oracle.possible_velocities(p, q, 0.225)
+    # (with the launch values 0.225 - 1.5*0.15 is 2.8e-17, not 0: the branch needs an exact zero)
+    qa = make_query(20, 0, max_accel=2.0)
+    q0 = make_query(20, 0, goal_speed=0.0, max_accel=2.0)
+    v_exact = 2.0 * 0.15
+    assert oracle.possible_velocities(p, q0, v_exact)[0] == 0.0
+    assert 0.0 not in oracle.possible_velocities(p, qa, v_exact)
+    assert oracle.possible_velocities(p, q, 0.225)[0] == 0.225 - 1.5 * 0.15 > 0
 
 
 def test_yaw_lattice_26_or_27(oracle):
