@@ -55,6 +55,10 @@ struct GridDev {
   uint32_t* occ_tiles;
   uint8_t* tile_any;        // 1 if any bit of the tile is set
   int TI, TJ;               // tile counts
+  // one bit per 8x8-cell block of the haloed domain ("any cell of the block occupied"):
+  //   coarse[ci8 * CW8 + (cj8 >> 6)] bit (cj8 & 63), ci8 = (i + halo) >> 3, cj8 = (j + halo) >> 3
+  unsigned long long* coarse;
+  int CI8, CW8;
   // REF_AABB box-dilated map over base cells [-aabb_pad_x, W+aabb_pad_x) x [-aabb_pad_y, H+...)
   //   aabb_map[(bx+pad_x) * aabb_stride + (by+pad_y)] = 1 iff the LP:477-495 box anchored at
   //   (bx,by) contains a cell == 100

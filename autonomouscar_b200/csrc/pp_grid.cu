@@ -60,6 +60,30 @@ __global__ void reduce_tile_any(const uint32_t* __restrict__ tiles, uint8_t* __r
   }
 }
 
+// 8x8-cell coarse occupancy: thread per (coarse row, tile column) ORs 8 tile words -> 4 bits
+__global__ void build_coarse(const uint32_t* __restrict__ tiles, unsigned long long* __restrict__ coarse, int TI,
+                             int TJ, int CW8) {
+  const int64_t total = static_cast<int64_t>(TI) * 4 * TJ;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int tj = static_cast<int>(k % TJ);
+    const int ci8 = static_cast<int>(k / TJ);
+    const int ti = ci8 >> 2, r0 = (ci8 & 3) * 8;
+    const uint32_t* t = tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
+    uint32_t w = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) w |= t[r];
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if ((w >> (8 * b)) & 0xffu) bits |= 1ull << b;
+    if (bits) {
+      const int cj8 = tj * 4;
+      atomicOr(&coarse[static_cast<size_t>(ci8) * CW8 + (cj8 >> 6)], bits << (cj8 & 63));
+    }
+  }
+}
+
 // REF_AABB dilation, pass 1: rows[x][my] = OR over y in [ylo[my], yhi[my]) of (cspace[x][y]==100)
 __global__ void aabb_pass_y(const int8_t* __restrict__ cspace, uint8_t* __restrict__ rows, int W, int H, int ny,
                             const int* __restrict__ ylo, const int* __restrict__ yhi) {
@@ -116,6 +140,7 @@ void grid_free(pp_handle* h) {
   cudaFree(g.cspace);
   cudaFree(g.occ_tiles);
   cudaFree(g.tile_any);
+  cudaFree(g.coarse);
   cudaFree(g.aabb_map);
   g = GridDev{};
   h->has_grid = false;
@@ -137,6 +162,9 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
     PP_CUDA(cudaMalloc(&g.cspace, cells));
     PP_CUDA(cudaMalloc(&g.occ_tiles, static_cast<size_t>(g.TI) * g.TJ * kTile * sizeof(uint32_t)));
     PP_CUDA(cudaMalloc(&g.tile_any, static_cast<size_t>(g.TI) * g.TJ));
+    g.CI8 = g.TI * 4;
+    g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
+    PP_CUDA(cudaMalloc(&g.coarse, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
     PP_CUDA(cudaMalloc(&g.aabb_map, static_cast<size_t>(g.aabb_nx) * g.aabb_ny));
     // scratch: message copy (cells) + pass-1 rows (W * ny) + 4 interval tables
     h->scratch_bytes = cells + static_cast<size_t>(W) * g.aabb_ny + sizeof(int) * 2 * (g.aabb_nx + g.aabb_ny) + 256;
@@ -176,6 +204,9 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
   const int64_t n_tiles = static_cast<int64_t>(g.TI) * g.TJ;
   pack_occ_tiles<<<blocks_for(n_tiles * kTile * 32, T, h->sm_count), T, 0, s>>>(g.cspace, g.occ_tiles, W, H, g.TI, g.TJ);
   reduce_tile_any<<<blocks_for(n_tiles * 32, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.tile_any, n_tiles);
+  PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8, s));
+  build_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.TJ, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.coarse, g.TI, g.TJ, g.CW8);
+  h->launches++;
   aabb_pass_y<<<blocks_for(static_cast<int64_t>(W) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(g.cspace, rows, W, H, g.aabb_ny, ylo, yhi);
   aabb_pass_x<<<blocks_for(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(rows, g.aabb_map, W, g.aabb_nx, g.aabb_ny, xlo, xhi);
   h->launches += 4;
