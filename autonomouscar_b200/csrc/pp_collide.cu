@@ -9,6 +9,7 @@
 //   With broad_phase = 0 every pose that overlaps the grid takes the narrow phase
 //   ("direct" mode, the gather-bound measurement).  Results are identical either way.
 #include "pp_common.cuh"
+#include "pp_narrow.cuh"
 
 namespace pp {
 
@@ -31,168 +32,6 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x)
     flags[k] = 0;
-}
-
-// What the narrow phase needs to know about one pose, relative to the corner of the first
-// tile under its bounding box (so all lattice coordinates are in [0, 96) cells).
-struct NarrowJob {
-  int32_t oi, oj, ui, uj, vi, vj;
-  uint32_t tiles;   // t0i << 16 | t0j : first tile row / column
-  uint32_t box;     // ri0 | ri1 << 7 | rj0 << 14 | rj1 << 21 : lattice bbox relative to the tile corner
-  uint32_t occ;     // bit (a*3+b): tile (t0i+a, t0j+b) is under the box AND holds an obstacle
-};
-
-// 8x8-cell coarse occupancy under the cell box [i0,i1] x [j0,j1] (<= 8 x 8 coarse cells)
-__device__ __forceinline__ bool coarse_box_any(const GridDev& g, int i0, int i1, int j0, int j1) {
-  const int r0 = (i0 + kHaloCells) >> 3, r1 = (i1 + kHaloCells) >> 3;
-  const int c0 = (j0 + kHaloCells) >> 3, c1 = (j1 + kHaloCells) >> 3;
-  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 8 bits starting at bit c0
-  const unsigned long long m = ((1ull << nb) - 1ull);
-  unsigned long long any = 0;
-  for (int r = r0; r <= r1; ++r) {
-    const unsigned long long* row = g.coarse + static_cast<size_t>(r) * g.CW8 + w0;
-    unsigned long long bits = __ldg(row) >> sh;
-    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
-    any |= bits & m;
-  }
-  return any != 0;
-}
-
-// same for a wider square (the yaw-independent bound): up to 64 coarse cells wide
-__device__ __forceinline__ bool coarse_square_any(const GridDev& g, int i0, int i1, int j0, int j1) {
-  const int r0 = (i0 + kHaloCells) >> 3, r1 = (i1 + kHaloCells) >> 3;
-  const int c0 = (j0 + kHaloCells) >> 3, c1 = (j1 + kHaloCells) >> 3;
-  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;
-  const unsigned long long m = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
-  unsigned long long any = 0;
-  for (int r = r0; r <= r1; ++r) {
-    const unsigned long long* row = g.coarse + static_cast<size_t>(r) * g.CW8 + w0;
-    unsigned long long bits = __ldg(row) >> sh;
-    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
-    any |= bits & m;
-  }
-  return any != 0;
-}
-
-// Broad phase for one pose (one thread): false = certainly collision-free.
-__device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, const PoseFx& p, int broad_phase,
-                                         NarrowJob* job) {
-  if (!p.valid) return false;
-  int i0, i1, j0, j1;
-  lattice_bbox(l, p, &i0, &i1, &j0, &j1);
-  if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return false;  // box entirely off the grid
-  const int t0i = (i0 + kHaloCells) >> 5, t0j = (j0 + kHaloCells) >> 5;
-  const int nti = ((i1 + kHaloCells) >> 5) - t0i + 1, ntj = ((j1 + kHaloCells) >> 5) - t0j + 1;
-  uint32_t occ = 0;
-  for (int a = 0; a < nti; ++a)
-    for (int b = 0; b < ntj; ++b) {
-      const uint32_t any = broad_phase ? __ldg(&g.tile_any[static_cast<size_t>(t0i + a) * g.TJ + (t0j + b)]) : 1u;
-      occ |= (any ? 1u : 0u) << (a * 3 + b);
-    }
-  if (occ == 0) return false;                                            // no obstacle in any tile under the box
-  if (broad_phase && !coarse_box_any(g, i0, i1, j0, j1)) return false;   // none in the 8x8 blocks under it
-  // re-base the lattice origin from the anchor cell to the first tile's corner
-  const int ci0 = t0i * kTile - kHaloCells, cj0 = t0j * kTile - kHaloCells;
-  job->oi = p.oi + ((p.ai - ci0) << kFracBits);
-  job->oj = p.oj + ((p.aj - cj0) << kFracBits);
-  job->ui = p.ui; job->uj = p.uj; job->vi = p.vi; job->vj = p.vj;
-  job->tiles = (static_cast<uint32_t>(t0i) << 16) | static_cast<uint32_t>(t0j);
-  job->box = static_cast<uint32_t>(i0 - ci0) | (static_cast<uint32_t>(i1 - ci0) << 7) |
-             (static_cast<uint32_t>(j0 - cj0) << 14) | (static_cast<uint32_t>(j1 - cj0) << 21);
-  job->occ = occ;
-  return true;
-}
-
-// Window of the warp: 96 rows x 96 columns of occupancy bits as sm[wcol * 96 + row]
-// (wcol = column / 32).  Each staged tile is one coalesced 128 B line.
-constexpr int kWinWords = 3 * 96;
-
-__device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& job, uint32_t* sm, int lane) {
-  const int t0i = job.tiles >> 16, t0j = job.tiles & 0xffff;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      uint32_t w = 0;
-      if ((job.occ >> (a * 3 + b)) & 1u)
-        w = __ldg(&g.occ_tiles[(static_cast<size_t>(t0i + a) * g.TJ + (t0j + b)) * kTile + lane]);
-      sm[b * 96 + a * 32 + lane] = w;
-    }
-  }
-  __syncwarp();
-}
-
-// exact "any occupied cell inside the lattice's bounding box" on the staged window
-__device__ __forceinline__ bool window_box_any(const NarrowJob& job, const uint32_t* sm, int lane) {
-  const int ri0 = job.box & 127, ri1 = (job.box >> 7) & 127, rj0 = (job.box >> 14) & 127, rj1 = (job.box >> 21) & 127;
-  // 96-bit column mask [rj0, rj1] split over the three words
-  uint32_t m[3];
-#pragma unroll
-  for (int w = 0; w < 3; ++w) {
-    const int lo = max(rj0 - 32 * w, 0), hi = min(rj1 - 32 * w, 31);
-    m[w] = (lo <= hi) ? ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
-  }
-  uint32_t any = 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int r = lane + 32 * k;
-    if (r >= ri0 && r <= ri1) any |= (sm[r] & m[0]) | (sm[96 + r] & m[1]) | (sm[192 + r] & m[2]);
-  }
-  return __any_sync(0xffffffffu, any != 0);
-}
-
-// Lattice evaluation with a compile-time shape.  The NU columns (fixed a, b = 0..NV-1) are
-// cut into S segments of SEG points; lane l owns segment l % S of columns (l / S) * ROUNDS + c
-// in round c, so EVERY round samples the whole length of the car at 1/ROUNDS density and a
-// colliding pose is almost always caught by the first one (warp-uniform early exit).
-// Everything inside is unrolled; each point costs two IMADs, the window address, one LDS,
-// a shift and an OR.  The last segment of a column overlaps its neighbour instead of
-// overrunning (a sample evaluated twice cannot change an OR).
-template <int NU, int NV, int S>
-__device__ __forceinline__ bool lattice_any_fixed(const NarrowJob& job, const uint32_t* sm, int lane) {
-  constexpr int SEG = (NV + S - 1) / S;
-  constexpr int GROUPS = 32 / S;                          // column groups (lanes / S)
-  constexpr int ROUNDS = (NU + GROUPS - 1) / GROUPS;
-  const int seg = lane % S, grp = lane / S;
-  const int b0 = min(seg * SEG, NV - SEG);
-  const int a0 = grp * ROUNDS;
-  int32_t bi = job.oi + a0 * job.ui + b0 * job.vi;
-  int32_t bj = job.oj + a0 * job.uj + b0 * job.vj;
-#pragma unroll
-  for (int c = 0; c < ROUNDS; ++c) {
-    uint32_t hit = 0;
-    if ((GROUPS - 1) * ROUNDS + c < NU || a0 + c < NU) {   // first test is compile-time
-#pragma unroll
-      for (int t = 0; t < SEG; ++t) {
-        const uint32_t fi = static_cast<uint32_t>(bi + t * job.vi);
-        const uint32_t fj = static_cast<uint32_t>(bj + t * job.vj);
-        const uint32_t w = sm[(fj >> 29) * 96 + (fi >> kFracBits)];
-        hit |= w >> ((fj >> kFracBits) & 31u);
-      }
-    }
-    if (__any_sync(0xffffffffu, (hit & 1u) != 0)) return true;   // early exit, warp-uniform
-    bi += job.ui;
-    bj += job.uj;
-  }
-  return false;
-}
-
-// any lattice shape (run-time nu, nv): lane-strided walk in (a, b) order
-__device__ __forceinline__ bool lattice_any_generic(const Lattice& l, const NarrowJob& job, const uint32_t* sm,
-                                                    int lane) {
-  const int npts = l.nu * l.nv;
-  uint32_t hit = 0;
-  int a = lane / l.nv, b = lane - a * l.nv;
-  const int da = 32 / l.nv, db = 32 - da * l.nv;
-  for (int p = lane; p < npts; p += 32) {
-    const uint32_t fi = static_cast<uint32_t>(job.oi + a * job.ui + b * job.vi);
-    const uint32_t fj = static_cast<uint32_t>(job.oj + a * job.uj + b * job.vj);
-    const uint32_t w = sm[(fj >> 29) * 96 + (fi >> kFracBits)];
-    hit |= w >> ((fj >> kFracBits) & 31u);
-    a += da; b += db;
-    if (b >= l.nv) { b -= l.nv; a += 1; }
-  }
-  return __any_sync(0xffffffffu, (hit & 1u) != 0);
 }
 
 // Fused broad + narrow: each warp takes 32 consecutive poses; the lanes set them up in
