@@ -12,7 +12,7 @@ from .results import PlanResult  # noqa: F401
 def __getattr__(name):
     # the binding needs torch + the built library; import it lazily so that pure-host
     # helpers (capi, worlds) stay importable everywhere
-    if name in ("Planner", "PlannerError"):
+    if name in ("Planner", "PlannerError", "PlannerGroup"):
         from . import planner
         return getattr(planner, name)
     if name == "LocalPlannerNode":

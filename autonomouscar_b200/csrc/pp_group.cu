@@ -1,9 +1,284 @@
+// pp_group.cu -- single-process multi-GPU front end.
+//
+// One pp_handle per device; the grid is replicated, pose batches and plan queries are
+// sharded contiguously by index with NO data-path collective; NCCL (over NVLink 5 /
+// NVSwitch) is used only to gather results: one ncclAllGather of the 1 B/pose flags, or of
+// fixed-stride plan records, after which every device holds the whole result in input
+// order.  NCCL is resolved with dlopen at pp_group_create, so the library itself loads on
+// machines without NCCL (the per-GPU entry points never need it).
+//
+// The reference has no counterpart (single-threaded ROS node, local_planner_node.cpp:14-17);
+// the multi-process variant of the same sharding (one rank per GPU under torchrun) lives in
+// autonomouscar_b200/sharding.py and is what bench.py uses.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <thread>
+#include <vector>
+
 #include "pp_common.cuh"
-extern "C" {
-int pp_group_create(const pp_params*, int, const int*, pp_group**) { pp::set_last_error("pp_group: not built yet"); return PP_ERR_UNSUPPORTED; }
-int pp_group_destroy(pp_group*) { return PP_OK; }
-int pp_group_size(const pp_group*, int*) { return PP_ERR_UNSUPPORTED; }
-int pp_group_set_grid(pp_group*, const int8_t*, int32_t, int32_t, double, int) { return PP_ERR_UNSUPPORTED; }
-int pp_group_collide_batch(pp_group*, int64_t, const float*, uint8_t*) { return PP_ERR_UNSUPPORTED; }
-int pp_group_plan_batch(pp_group*, int32_t, const pp_query*, pp_result*) { return PP_ERR_UNSUPPORTED; }
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef int ncclResult_t;
+constexpr int kNcclUint8 = 1;  // ncclDataType_t::ncclUint8
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
+    GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+    GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    return CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd && GetErrorString;
+  }
+};
+
+// fixed-stride record gathered for every plan query
+struct PlanRecord {
+  int32_t status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions, pad;
+  uint64_t digest;
+};
+
+}  // namespace
+
+struct pp_group {
+  int n = 0;
+  std::vector<int> devices;
+  std::vector<pp_handle*> h;
+  std::vector<ncclComm_t> comms;
+  NcclApi nccl;
+  // gather buffers, one pair per device
+  std::vector<uint8_t*> d_send, d_all;
+  std::vector<size_t> send_cap, all_cap;
+};
+
+#define PP_NCCL(g, expr)                                                                              \
+  do {                                                                                                \
+    ncclResult_t r_ = (expr);                                                                         \
+    if (r_ != 0) {                                                                                    \
+      ::pp::set_last_error(std::string(#expr) + ": " + (g)->nccl.GetErrorString(r_));                 \
+      return PP_ERR_NCCL;                                                                             \
+    }                                                                                                 \
+  } while (0)
+
+static int ensure_gather(pp_group* g, size_t per_rank_bytes) {
+  for (int d = 0; d < g->n; ++d) {
+    PP_CUDA(cudaSetDevice(g->devices[d]));
+    if (per_rank_bytes > g->send_cap[d]) {
+      cudaFree(g->d_send[d]);
+      g->d_send[d] = nullptr; g->send_cap[d] = 0;
+      PP_CUDA(cudaMalloc(&g->d_send[d], per_rank_bytes));
+      g->send_cap[d] = per_rank_bytes;
+    }
+    if (per_rank_bytes * g->n > g->all_cap[d]) {
+      cudaFree(g->d_all[d]);
+      g->d_all[d] = nullptr; g->all_cap[d] = 0;
+      PP_CUDA(cudaMalloc(&g->d_all[d], per_rank_bytes * g->n));
+      g->all_cap[d] = per_rank_bytes * g->n;
+    }
+  }
+  return PP_OK;
 }
+
+static int all_gather(pp_group* g, size_t per_rank_bytes) {
+  PP_NCCL(g, g->nccl.GroupStart());
+  for (int d = 0; d < g->n; ++d) {
+    ncclResult_t r = g->nccl.AllGather(g->d_send[d], g->d_all[d], per_rank_bytes, kNcclUint8, g->comms[d],
+                                       g->h[d]->stream);
+    if (r != 0) {
+      g->nccl.GroupEnd();
+      pp::set_last_error(std::string("ncclAllGather: ") + g->nccl.GetErrorString(r));
+      return PP_ERR_NCCL;
+    }
+  }
+  PP_NCCL(g, g->nccl.GroupEnd());
+  return PP_OK;
+}
+
+extern "C" {
+
+int pp_group_create(const pp_params* params, int n_devices, const int* devices, pp_group** out) {
+  if (!params || !out || n_devices < 1) { pp::set_last_error("pp_group_create: bad arguments"); return PP_ERR_INVALID; }
+  *out = nullptr;
+  pp_group* g = new pp_group();
+  g->n = n_devices;
+  for (int d = 0; d < n_devices; ++d) g->devices.push_back(devices ? devices[d] : d);
+  if (!g->nccl.load()) {
+    pp::set_last_error("pp_group_create: libnccl.so.2 not found or incomplete");
+    delete g;
+    return PP_ERR_NCCL;
+  }
+  g->h.assign(n_devices, nullptr);
+  for (int d = 0; d < n_devices; ++d) {
+    int rc = pp_create(params, g->devices[d], &g->h[d]);
+    if (rc != PP_OK) { pp_group_destroy(g); return rc; }
+  }
+  g->comms.assign(n_devices, nullptr);
+  ncclResult_t r = g->nccl.CommInitAll(g->comms.data(), n_devices, g->devices.data());
+  if (r != 0) {
+    pp::set_last_error(std::string("ncclCommInitAll: ") + g->nccl.GetErrorString(r));
+    g->comms.clear();
+    pp_group_destroy(g);
+    return PP_ERR_NCCL;
+  }
+  g->d_send.assign(n_devices, nullptr);
+  g->d_all.assign(n_devices, nullptr);
+  g->send_cap.assign(n_devices, 0);
+  g->all_cap.assign(n_devices, 0);
+  *out = g;
+  return PP_OK;
+}
+
+int pp_group_destroy(pp_group* g) {
+  if (!g) return PP_OK;
+  for (size_t d = 0; d < g->comms.size(); ++d)
+    if (g->comms[d]) g->nccl.CommDestroy(g->comms[d]);
+  for (size_t d = 0; d < g->d_send.size(); ++d) {
+    cudaSetDevice(g->devices[d]);
+    cudaFree(g->d_send[d]);
+    cudaFree(g->d_all[d]);
+  }
+  for (pp_handle* h : g->h) pp_destroy(h);
+  delete g;
+  return PP_OK;
+}
+
+int pp_group_size(const pp_group* g, int* out) {
+  if (!g || !out) return PP_ERR_INVALID;
+  *out = g->n;
+  return PP_OK;
+}
+
+int pp_group_set_grid(pp_group* g, const int8_t* data_host, int32_t width, int32_t height, double res, int layout) {
+  if (!g) return PP_ERR_INVALID;
+  for (int d = 0; d < g->n; ++d) {
+    int rc = pp_set_grid(g->h[d], data_host, width, height, res, layout);
+    if (rc != PP_OK) return rc;
+  }
+  return PP_OK;
+}
+
+int pp_group_collide_batch(pp_group* g, int64_t n, const float* poses_host, uint8_t* out_flags_host) {
+  if (!g || n < 0 || (n > 0 && (!poses_host || !out_flags_host))) return PP_ERR_INVALID;
+  if (n == 0) return PP_OK;
+  const int G = g->n;
+  const int64_t per = (n + G - 1) / G;   // equal count per rank for the all-gather; the tail is padding
+  int rc = ensure_gather(g, static_cast<size_t>(per));
+  if (rc) return rc;
+  // 1. upload each shard and launch its kernel (asynchronous per device)
+  std::vector<float*> d_poses(G, nullptr);
+  for (int d = 0; d < G; ++d) {
+    const int64_t lo = std::min<int64_t>(n, d * per), hi = std::min<int64_t>(n, lo + per), m = hi - lo;
+    pp_handle* h = g->h[d];
+    PP_CUDA(cudaSetDevice(g->devices[d]));
+    if (m > h->stage_cap) {
+      cudaFree(h->d_poses); cudaFree(h->d_flags);
+      h->d_poses = nullptr; h->d_flags = nullptr; h->stage_cap = 0;
+      PP_CUDA(cudaMalloc(&h->d_poses, static_cast<size_t>(per) * 3 * sizeof(float)));
+      PP_CUDA(cudaMalloc(&h->d_flags, static_cast<size_t>(per)));
+      h->stage_cap = per;
+    }
+    PP_CUDA(cudaMemsetAsync(g->d_send[d], 0, static_cast<size_t>(per), h->stream));
+    if (m > 0) {
+      PP_CUDA(cudaMemcpyAsync(h->d_poses, poses_host + 3 * lo, static_cast<size_t>(m) * 3 * sizeof(float),
+                              cudaMemcpyHostToDevice, h->stream));
+      rc = pp_collide_batch_dev(h, m, h->d_poses, g->d_send[d]);
+      if (rc) return rc;
+    }
+  }
+  // 2. gather the flags: afterwards every device holds all shards in input order
+  rc = all_gather(g, static_cast<size_t>(per));
+  if (rc) return rc;
+  // 3. the host copy comes from device 0
+  PP_CUDA(cudaSetDevice(g->devices[0]));
+  for (int d = 0; d < G; ++d) {
+    const int64_t lo = std::min<int64_t>(n, d * per), hi = std::min<int64_t>(n, lo + per), m = hi - lo;
+    if (m > 0)
+      PP_CUDA(cudaMemcpyAsync(out_flags_host + lo, g->d_all[0] + static_cast<size_t>(d) * per, static_cast<size_t>(m),
+                              cudaMemcpyDeviceToHost, g->h[0]->stream));
+  }
+  for (int d = 0; d < G; ++d) {
+    PP_CUDA(cudaSetDevice(g->devices[d]));
+    PP_CUDA(cudaStreamSynchronize(g->h[d]->stream));
+  }
+  return PP_OK;
+}
+
+int pp_group_plan_batch(pp_group* g, int32_t n, const pp_query* queries, pp_result* results) {
+  if (!g || n < 0 || (n > 0 && (!queries || !results))) return PP_ERR_INVALID;
+  if (n == 0) return PP_OK;
+  const int G = g->n;
+  const int per = (n + G - 1) / G;
+  // 1. every device plans its contiguous block of queries; one host thread per device because
+  //    pp_plan_batch is synchronous (it mirrors the reference's blocking callback)
+  std::vector<int> rcs(G, PP_OK);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> th;
+  for (int d = 0; d < G; ++d) {
+    const int lo = std::min(n, d * per), hi = std::min(n, lo + per);
+    if (hi <= lo) continue;
+    th.emplace_back([=, &rcs, &errs]() {
+      rcs[d] = pp_plan_batch(g->h[d], hi - lo, queries + lo, results + lo);
+      if (rcs[d] != PP_OK) errs[d] = pp_last_error();
+    });
+  }
+  for (auto& t : th) t.join();
+  int ret = PP_OK;
+  for (int d = 0; d < G; ++d)
+    if (rcs[d] != PP_OK) { pp::set_last_error(errs[d]); if (rcs[d] != PP_ERR_CAPACITY) return rcs[d]; ret = rcs[d]; }
+  // 2. gather the fixed-stride records over NCCL; the scalar fields of every result are then
+  //    re-read from the gathered copy (device 0), in input order
+  const size_t per_bytes = sizeof(PlanRecord) * static_cast<size_t>(per);
+  int rc = ensure_gather(g, per_bytes);
+  if (rc) return rc;
+  std::vector<PlanRecord> rec(static_cast<size_t>(per));
+  for (int d = 0; d < G; ++d) {
+    const int lo = std::min(n, d * per), hi = std::min(n, lo + per);
+    std::memset(rec.data(), 0, per_bytes);
+    for (int k = lo; k < hi; ++k) {
+      PlanRecord& r = rec[k - lo];
+      const pp_result& s = results[k];
+      r.status = s.status; r.n_expansions = s.n_expansions; r.n_nodes = s.n_nodes; r.n_open = s.n_open;
+      r.n_closed = s.n_closed; r.n_path = s.n_path; r.n_profile = s.n_profile; r.n_candidates = s.n_candidates;
+      r.n_collisions = s.n_collisions; r.digest = s.tree_digest;
+    }
+    PP_CUDA(cudaSetDevice(g->devices[d]));
+    PP_CUDA(cudaMemcpyAsync(g->d_send[d], rec.data(), per_bytes, cudaMemcpyHostToDevice, g->h[d]->stream));
+    PP_CUDA(cudaStreamSynchronize(g->h[d]->stream));
+  }
+  rc = all_gather(g, per_bytes);
+  if (rc) return rc;
+  std::vector<PlanRecord> all(static_cast<size_t>(per) * G);
+  PP_CUDA(cudaSetDevice(g->devices[0]));
+  PP_CUDA(cudaMemcpyAsync(all.data(), g->d_all[0], per_bytes * G, cudaMemcpyDeviceToHost, g->h[0]->stream));
+  for (int d = 0; d < G; ++d) {
+    PP_CUDA(cudaSetDevice(g->devices[d]));
+    PP_CUDA(cudaStreamSynchronize(g->h[d]->stream));
+  }
+  for (int k = 0; k < n; ++k) {
+    const PlanRecord& r = all[static_cast<size_t>(k / per) * per + (k % per)];
+    pp_result& s = results[k];
+    s.status = r.status; s.n_expansions = r.n_expansions; s.n_nodes = r.n_nodes; s.n_open = r.n_open;
+    s.n_closed = r.n_closed; s.n_path = r.n_path; s.n_profile = r.n_profile; s.n_candidates = r.n_candidates;
+    s.n_collisions = r.n_collisions; s.tree_digest = r.digest;
+  }
+  return ret;
+}
+
+}  // extern "C"

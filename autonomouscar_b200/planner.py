@@ -212,3 +212,66 @@ class Planner:
         v = C.c_int64()
         self._check(self._L.pp_last_narrow_count(self._h, C.byref(v)))
         return v.value
+
+
+class PlannerGroup:
+    """Single-process multi-GPU front end (pp_group_*): one handle per device, pose batches
+    and plan queries sharded contiguously, results gathered with NCCL."""
+
+    def __init__(self, params=None, devices=None):
+        self._L = _lib.load()
+        self.params = params if params is not None else default_params()
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        g = C.c_void_p()
+        self._g = None
+        rc = self._L.pp_group_create(C.byref(self.params), len(self.devices), arr, C.byref(g))
+        if rc != PP_OK:
+            raise PlannerError(rc, self._L.pp_last_error().decode())
+        self._g = g
+
+    def _check(self, rc):
+        if rc != PP_OK:
+            raise PlannerError(rc, self._L.pp_last_error().decode())
+
+    def close(self):
+        if self._g is not None:
+            self._L.pp_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        n = C.c_int()
+        self._check(self._L.pp_group_size(self._g, C.byref(n)))
+        return n.value
+
+    def set_grid(self, data, layout=PP_GRID_CSPACE):
+        a = np.ascontiguousarray(np.asarray(data), dtype=np.int8)
+        self._check(self._L.pp_group_set_grid(self._g, a.ctypes.data_as(C.c_void_p), self.params.costmap_width,
+                                              self.params.costmap_height, self.params.costmap_res, layout))
+
+    def collide(self, poses_host):
+        a = np.ascontiguousarray(poses_host, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(a), dtype=np.uint8)
+        self._check(self._L.pp_group_collide_batch(self._g, len(a), a.ctypes.data_as(C.c_void_p),
+                                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def plan_batch(self, queries, want_nodes=False, **caps):
+        n = len(queries)
+        qs = (pp_query * n)(*queries)
+        results = [PlanResult(want_nodes=want_nodes, **caps) for _ in range(n)]
+        raw = (pp_result * n)(*[r.raw for r in results])
+        rc = self._L.pp_group_plan_batch(self._g, n, qs, raw)
+        if rc not in (PP_OK, 4):
+            self._check(rc)
+        for r, rr in zip(results, raw):
+            r.raw = rr
+        return results
