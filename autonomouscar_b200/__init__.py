@@ -6,7 +6,7 @@ mirror of the reference node (`node.LocalPlannerNode`) and synthetic-workload he
 for tests and bench (`worlds`).
 """
 from .capi import *  # noqa: F401,F403  (enums, structs, default_params, make_query)
-from .results import PlanResult  # noqa: F401
+from .results import PlanBatch, PlanResult  # noqa: F401
 
 
 def __getattr__(name):

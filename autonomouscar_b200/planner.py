@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from .capi import (PP_GRID_CSPACE, PP_OK, PP_PHASE_COUNT, default_params, pp_params, pp_query, pp_result)
-from .results import PlanResult
+from .results import PlanBatch, PlanResult
 
 
 class PlannerError(RuntimeError):
@@ -174,6 +174,15 @@ class Planner:
         for r, rr in zip(results, raw):
             r.raw = rr
         return results
+
+    def plan_batch_into(self, queries_array, batch, rrt=False):
+        """pp_plan_batch / pp_rrt_plan_batch into pre-allocated PlanBatch buffers.
+        `queries_array` is a ctypes (pp_query * n) array."""
+        fn = self._L.pp_rrt_plan_batch if rrt else self._L.pp_plan_batch
+        rc = fn(self._h, batch.n, queries_array, batch.raw)
+        if rc not in (PP_OK, 4):
+            self._check(rc)
+        return batch
 
     def rrt_plan(self, query, **caps):
         res = PlanResult(**caps)

@@ -83,3 +83,38 @@ class PlanResult:
         return {k: int(getattr(self.raw, k)) for k in (
             "status", "n_expansions", "n_nodes", "n_open", "n_closed", "n_path", "n_profile",
             "n_candidates", "n_collisions", "tree_digest")}
+
+
+class PlanBatch:
+    """Output buffers of a whole batch of plans in a few contiguous arrays (one row per
+    query), allocated once and reusable across calls -- the fast path of pp_plan_batch /
+    pp_rrt_plan_batch when only paths, profiles and summaries are wanted."""
+
+    def __init__(self, n, cap_path=256):
+        self.n, self.cap_path = n, cap_path
+        self.path_xy = np.zeros((n, cap_path, 2), dtype=np.float64)
+        self.path_node_ids = np.full((n, cap_path), -2, dtype=np.int32)
+        self.yaw_rates = np.zeros((n, cap_path), dtype=np.float64)
+        self.durations = np.zeros((n, cap_path), dtype=np.float64)
+        self.speeds = np.zeros((n, cap_path), dtype=np.float64)
+        self.raw = (pp_result * n)()
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        for k in range(n):
+            r = self.raw[k]
+            r.cap_nodes, r.cap_path, r.cap_expansions = 0, cap_path, 0
+            r.path_xy = self.path_xy[k].ctypes.data_as(dp)
+            r.path_node_ids = self.path_node_ids[k].ctypes.data_as(ip)
+            r.yaw_rates = self.yaw_rates[k].ctypes.data_as(dp)
+            r.durations = self.durations[k].ctypes.data_as(dp)
+            r.speeds = self.speeds[k].ctypes.data_as(dp)
+
+    def field(self, name):
+        return np.array([getattr(self.raw[k], name) for k in range(self.n)])
+
+    def records(self):
+        """[n, 5] int64: status, n_expansions, n_nodes, n_path, digest (low 63 bits)."""
+        out = np.empty((self.n, 5), dtype=np.int64)
+        for k in range(self.n):
+            r = self.raw[k]
+            out[k] = (r.status, r.n_expansions, r.n_nodes, r.n_path, r.tree_digest & 0x7FFFFFFFFFFFFFFF)
+        return out

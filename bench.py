@@ -313,12 +313,15 @@ def run_ours(args):
 
 def bench_plans(pl_unused, rank, world, dev, multi, args):
     """configs[1] (single query, 10k-node cap) and configs[4] (independent queries, sharded
-    contiguously over the ranks, results gathered with NCCL).  Launch-file grid (300x300 @0.25 m)."""
+    contiguously over the ranks, fixed-stride result records gathered with NCCL).
+    Launch-file grid (300x300 @0.25 m)."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from autonomouscar_b200 import PP_COLLISION_ORIENTED, PP_PLAN_FOUND, Planner, default_params, worlds
+    from autonomouscar_b200 import (PP_COLLISION_ORIENTED, PP_PLAN_FOUND, PlanBatch, Planner, default_params,
+                                    sharding, worlds)
+    from autonomouscar_b200.capi import pp_query
     p = default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=10000)
     grid = worlds.block_grid(300, 300, frac=0.01, block=4, seed=9)
     worlds.clear_disc(grid, p, 0.0, 0.0, 4.0)
@@ -326,41 +329,66 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     pl.set_grid(grid)
     n_total = args.queries * world
     qs_all = worlds.forward_queries(n_total, seed=11)
-    lo = rank * args.queries
-    qs = qs_all[lo:lo + args.queries]
-    pl.plan_batch(qs[:64], want_nodes=False, cap_path=256, cap_expansions=1)   # warm-up
+    lo, hi = sharding.shard_bounds(n_total, rank, world)
+    qs = qs_all[lo:hi]
+    q_arr = (pp_query * len(qs))(*qs)
+    buf = PlanBatch(len(qs), cap_path=256)
+    warm = PlanBatch(64, cap_path=256)
+    pl.plan_batch_into((pp_query * 64)(*qs[:64]), warm)                       # warm-up
+    sharding.gather_blocks(torch.zeros((hi - lo, 5), dtype=torch.int64, device=dev), n_total)
     if multi:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = pl.plan_batch(qs, want_nodes=False, cap_path=256, cap_expansions=1)
-    rec = torch.tensor([[r.status, r.n_nodes, r.n_path, r.tree_digest & 0x7fffffff] for r in res],
-                       dtype=torch.int64, device=dev)
-    if multi:
-        out = torch.empty((n_total, 4), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(out, rec)
-        rec = out
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev)
-    if multi:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    kernel_ms = pl.last_phase_ms()[4]
+    reps, dts, kms = 3, [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pl.plan_batch_into(q_arr, buf)
+        rec = sharding.gather_blocks(torch.from_numpy(buf.records()).to(dev), n_total)
+        torch.cuda.synchronize()
+        dts.append(sharding.max_over_ranks(time.perf_counter() - t0, dev))
+        kms.append(pl.last_phase_ms()[4])
+    dt = sorted(dts)[len(dts) // 2]
     # single-query latency (config 2)
     lat = []
     for k in range(5):
         t1 = time.perf_counter()
         r1 = pl.plan(qs[0], cap_nodes=16384)
         lat.append(time.perf_counter() - t1)
+    # sampling planner (extension rows S1-S3): batch of independent queries on a 1024^2 grid
+    rp = default_params(costmap_res=0.1, costmap_width=1024, costmap_height=1024, collision_mode=PP_COLLISION_ORIENTED,
+                        time_step_ms=1000.0, rrt_samples_per_round=64, rrt_max_samples=10000, max_nodes=10000,
+                        rrt_goal_tolerance=1.5)
+    rg = worlds.block_grid(1024, 1024, frac=0.01, block=16, seed=2, noise=False)
+    worlds.clear_disc(rg, rp, -30.0, -30.0, 5.0)
+    rng = np.random.default_rng(5)
+    from autonomouscar_b200 import make_query
+    n_rrt = 256
+    rqs = []
+    for k in range(n_rrt):
+        gx, gy = rng.uniform(-20, 40, 2)
+        worlds.clear_disc(rg, rp, gx, gy, 4.0)
+        rqs.append(make_query(gx, gy, start_x=-30.0, start_y=-30.0, start_heading=0.7, start_speed=1.0, seed=7,
+                              query_id=rank * n_rrt + k))
+    rpl = Planner(rp, device=dev.index)
+    rpl.set_grid(rg)
+    rq_arr = (pp_query * n_rrt)(*rqs)
+    rbuf = PlanBatch(n_rrt, cap_path=2048)
+    rpl.plan_batch_into(rq_arr, rbuf, rrt=True)
+    t0 = time.perf_counter()
+    rpl.plan_batch_into(rq_arr, rbuf, rrt=True)
+    rrt_dt = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    rrt_samples = int(rbuf.field("n_candidates").sum())
+    rrt_found = int((rbuf.field("status") == PP_PLAN_FOUND).sum())
     out = None
     if rank == 0:
         found = int((rec[:, 0] == PP_PLAN_FOUND).sum().item())
         out = {"batch_queries": n_total, "plans_per_s": n_total / dt, "batch_wall_s": dt,
-               "plan_kernel_ms_rank0": kernel_ms, "found": found,
-               "mean_nodes": float(rec[:, 1].float().mean().item()),
+               "plan_kernel_ms_rank0": sorted(kms)[len(kms) // 2], "found": found,
+               "mean_nodes": float(rec[:, 2].float().mean().item()),
                "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_nodes": int(r1.n_nodes),
-               "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000"}
+               "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000",
+               "rrt": {"queries_per_gpu": n_rrt, "plans_per_s": n_rrt * world / rrt_dt, "found_rank0": rrt_found,
+                       "samples_per_s_rank0": rrt_samples / rrt_dt, "grid": "1024x1024 @0.1 m, 10k-sample cap, K=64"}}
         if not args.skip_cpu:
             from oracle import binding as orc
             cores = os.cpu_count() or 1
@@ -373,16 +401,17 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
             # parity of the sample against the deterministic oracle
             secs2, st2, nn2, dg2 = orc.plan_batch_timed(p, grid, qs_all[:nq], math_mode=orc.MATH_DET, n_threads=cores)
             mine = rec[:nq].cpu().numpy()
-            out["parity_sample_ok"] = bool((mine[:, 0] == st2).all() and (mine[:, 1] == nn2).all() and
-                                           (mine[:, 3] == (dg2 & np.uint64(0x7fffffff)).astype(np.int64)).all())
+            out["parity_sample_ok"] = bool((mine[:, 0] == st2).all() and (mine[:, 2] == nn2).all() and
+                                           (mine[:, 4] == (dg2 & np.uint64(0x7FFFFFFFFFFFFFFF)).astype(np.int64)).all())
     pl.close()
+    rpl.close()
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=N_POSES)
