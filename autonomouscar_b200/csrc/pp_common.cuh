@@ -137,19 +137,25 @@ __device__ __forceinline__ bool oriented_hit_thread(const GridDev& g, const Latt
   int i0, i1, j0, j1;
   lattice_bbox(l, p, &i0, &i1, &j0, &j1);
   if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return false;
+  // all loads of four lattice columns are independent (no early exit in between), so they
+  // overlap in the memory pipeline; the exit test runs once per four columns
   uint32_t hit = 0;
-  for (int a = 0; a < l.nu; ++a) {
-    int32_t fi = p.oi + a * p.ui, fj = p.oj + a * p.uj;
-    for (int b = 0; b < l.nv; ++b) {
-      const int gi = p.ai + (fi >> kFracBits), gj = p.aj + (fj >> kFracBits);
-      const int jh = gj + kHaloCells;
-      hit |= occ_word(g, gi, jh >> 5) >> (jh & 31);
-      fi += p.vi;
-      fj += p.vj;
+  const size_t tj_stride = kTile;
+  for (int a0 = 0; a0 < l.nu; a0 += 4) {
+    const int a1 = min(a0 + 4, l.nu);
+    for (int a = a0; a < a1; ++a) {
+      const int32_t ci = p.oi + a * p.ui, cj = p.oj + a * p.uj;
+#pragma unroll 4
+      for (int b = 0; b < l.nv; ++b) {
+        const int32_t fi = ci + b * p.vi, fj = cj + b * p.vj;
+        const int ih = p.ai + (fi >> kFracBits) + kHaloCells, jh = p.aj + (fj >> kFracBits) + kHaloCells;
+        const uint32_t w = __ldg(&g.occ_tiles[(static_cast<size_t>(ih >> 5) * g.TJ + (jh >> 5)) * tj_stride + (ih & 31)]);
+        hit |= w >> (jh & 31);
+      }
     }
     if (hit & 1u) return true;
   }
-  return (hit & 1u) != 0;
+  return false;
 }
 
 // REF_AABB through the dilated map: LP:471-476 evaluated verbatim for the base cell, then

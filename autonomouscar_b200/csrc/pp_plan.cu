@@ -23,6 +23,7 @@
 //     reproduce the list scan order (open list in insertion order, then closed list in
 //     closing order).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -32,8 +33,10 @@ namespace pp {
 
 namespace {
 
-constexpr int kT = 256;            // threads per CTA
-constexpr int kWarps = kT / 32;
+constexpr int kTMax = 256;         // threads per CTA: 256 for a lone query (latency), 128 in batches (more CTAs per SM)
+constexpr int kWarpsMax = kTMax / 32;
+#define kT (static_cast<int>(blockDim.x))
+#define kWarps (static_cast<int>(blockDim.x) >> 5)
 constexpr int kMaxVel = 64;        // velocities per expansion the kernel supports
 constexpr int kMaxCand = 8192;     // children per expansion the kernel supports
 constexpr int kIntMax = 0x7fffffff;
@@ -42,6 +45,7 @@ struct PlanHdr {                   // per query, device -> host
   int status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions;
   int truncated;                   // a caller-visible array was too small
   unsigned long long digest;
+  long long cyc[8];                // SM cycles per phase (thread 0): init, close, eval, commit, push, close2, extract, total
 };
 
 struct PlanArgs {
@@ -52,10 +56,11 @@ struct PlanArgs {
   int n_queries;
   int NC;                 // slot capacity per workspace
   int hash_size;          // power of two
-  int heap_in_smem;
+  int heap_smem_entries;  // frontier entries kept in shared memory (>= 1)
   int ws_per_query;       // workspace index = query index (node arrays wanted) or CTA index
   int want_path_ids;
   int cap_path, cap_exp;
+  int timing;             // accumulate per-phase SM cycles (PP_PLAN_TIMING=1)
   size_t ws_stride;       // bytes
   unsigned char* ws_base;
   PlanHdr* hdr;
@@ -74,7 +79,7 @@ struct WS {
   double* heap_cost_g;
   int* closed_seq;
   int* heap_id_g;
-  int* cand_slot;             // scratch: per candidate, target slot or -1
+  int* closed_list;           // slot id by closing order (m_tree_closed)
 };
 
 __host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
@@ -82,9 +87,8 @@ __host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
   b += sizeof(double) * 8 * NC;
   b += sizeof(unsigned long long) * NC;
   b += sizeof(unsigned long long) * hash_size;
-  b += sizeof(double) * NC;           // global heap costs
-  b += sizeof(int) * NC * 2;          // closed_seq, heap ids
-  b += sizeof(int) * kMaxCand;
+  b += sizeof(double) * 2 * NC;       // global heap entries (16 B each); reused to stage the reversed path
+  b += sizeof(int) * NC * 3;          // closed_seq, spare, closed_list
   return (b + 255) & ~size_t(255);
 }
 
@@ -96,9 +100,9 @@ __device__ __forceinline__ WS ws_view(unsigned char* base, int NC, int hash_size
   w.fp = reinterpret_cast<unsigned long long*>(d + 8 * NC);
   w.hash = w.fp + NC;
   w.heap_cost_g = reinterpret_cast<double*>(w.hash + hash_size);
-  w.closed_seq = reinterpret_cast<int*>(w.heap_cost_g + NC);
+  w.closed_seq = reinterpret_cast<int*>(w.heap_cost_g + 2 * NC);
   w.heap_id_g = w.closed_seq + NC;
-  w.cand_slot = w.heap_id_g + NC;
+  w.closed_list = w.heap_id_g + NC;
   return w;
 }
 
@@ -135,7 +139,6 @@ __device__ __forceinline__ int block_min(int v, int* s_red) {
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   int r = s_red[0];
-#pragma unroll
   for (int w = 1; w < kWarps; ++w) r = min(r, s_red[w]);
   __syncthreads();
   return r;
@@ -147,7 +150,6 @@ __device__ __forceinline__ int block_sum(int v, int* s_red) {
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   int r = 0;
-#pragma unroll
   for (int w = 0; w < kWarps; ++w) r += s_red[w];
   __syncthreads();
   return r;
@@ -156,88 +158,82 @@ __device__ __forceinline__ int block_sum(int v, int* s_red) {
 // ---------------------------------------------------------------------------------------
 // the frontier: libstdc++ binary heap, comp(a, b) = a.cost > b.cost (local_planner.hpp:103-109)
 // ---------------------------------------------------------------------------------------
-struct Heap {
-  double* cost;
-  int* id;
+struct __align__(16) HeapEnt {
+  double cost;
+  int id;
+  int pad;
 };
+// The top `m` entries (levels near the root, touched by every operation) live in shared
+// memory, deeper levels in the query's workspace in L2.  m = capacity for a single query
+// (lowest latency); a batch uses a small m so that several CTAs share an SM and overlap each
+// other's serial heap phases.
+struct Heap {
+  HeapEnt* s;
+  HeapEnt* g;
+  int m;
+};
+template <bool kAllSmem>
+__device__ __forceinline__ HeapEnt hget(const Heap& h, int pos) {
+  if (kAllSmem) return h.s[pos];
+  return pos < h.m ? h.s[pos] : h.g[pos];
+}
+template <bool kAllSmem>
+__device__ __forceinline__ void hset(const Heap& h, int pos, const HeapEnt& v) {
+  if (kAllSmem || pos < h.m) h.s[pos] = v;
+  else h.g[pos] = v;
+}
 
 // std::__push_heap(first, hole, top = 0, value): executed by one full warp.  Lane k >= 1 owns
 // the k-th ancestor of the hole; all ancestors that compare "less" (cost > value) shift down
-// one level at once.
+// one level at once.  One 16-byte load and at most one 16-byte store per lane.
+template <bool kAllSmem>
 __device__ __forceinline__ void heap_sift_up_warp(const Heap& h, int hole, double vcost, int vid, int lane) {
   const unsigned j = static_cast<unsigned>(hole) + 1u;  // 1-based position
   bool moves = false;
-  double pc = 0;
-  int pid = 0;
-  int my_pos = 0;
-  if (lane >= 1) {
-    const bool valid = (j >> (lane - 1)) >= 2u;  // the (lane-1)-th ancestor is not the root
-    if (valid) {
-      my_pos = static_cast<int>(j >> lane) - 1;
-      pc = h.cost[my_pos];
-      pid = h.id[my_pos];
-      moves = pc > vcost;
-    }
+  HeapEnt mine;
+  mine.cost = 0; mine.id = 0; mine.pad = 0;
+  if (lane >= 1 && (j >> (lane - 1)) >= 2u) {            // the (lane-1)-th ancestor is not the root
+    mine = hget<kAllSmem>(h, static_cast<int>(j >> lane) - 1);
+    moves = mine.cost > vcost;
   }
   const unsigned stay = __ballot_sync(0xffffffffu, !moves) & ~1u;  // lanes >= 1 that stop the loop
-  const int stop = __ffs(stay) - 1;                               // first k with !moves (always exists: lane 31 at worst)
-  __syncwarp();
-  if (lane >= 1 && lane < stop) {
-    const int dst = static_cast<int>(j >> (lane - 1)) - 1;
-    h.cost[dst] = pc;
-    h.id[dst] = pid;
-  }
+  const int stop = __ffs(stay) - 1;                               // first k with !moves (always exists)
+  if (lane >= 1 && lane < stop) hset<kAllSmem>(h, static_cast<int>(j >> (lane - 1)) - 1, mine);
   if (lane == 0) {
-    const int dst = static_cast<int>(j >> (stop - 1)) - 1;
-    h.cost[dst] = vcost;
-    h.id[dst] = vid;
+    HeapEnt v;
+    v.cost = vcost; v.id = vid; v.pad = 0;
+    hset<kAllSmem>(h, static_cast<int>(j >> (stop - 1)) - 1, v);
   }
   __syncwarp();
 }
 
-// priority_queue::push by warp 0
-__device__ __forceinline__ void heap_push_warp(const Heap& h, int* size, double vcost, int vid, int lane) {
-  const int hole = *size;
-  __syncwarp();
-  heap_sift_up_warp(h, hole, vcost, vid, lane);
-  if (lane == 0) *size = hole + 1;
-  __syncwarp();
-}
-
-// priority_queue::pop by warp 0: std::pop_heap (__pop_heap + __adjust_heap) then pop_back
-__device__ __forceinline__ void heap_pop_warp(const Heap& h, int* size, int lane) {
-  const int n = *size;
-  __syncwarp();
-  if (n <= 1) {
-    if (lane == 0) *size = 0;
-    __syncwarp();
-    return;
-  }
-  const int len = n - 1;
-  const double vcost = h.cost[len];
-  const int vid = h.id[len];
+// priority_queue::pop by one warp: std::pop_heap (__pop_heap + __adjust_heap) then pop_back.
+// `size` is the warp-uniform current size; returns the new size.
+template <bool kAllSmem>
+__device__ __forceinline__ int heap_pop_warp(const Heap& h, int size, int lane) {
+  if (size <= 1) return 0;
+  const int len = size - 1;
+  const HeapEnt v = hget<kAllSmem>(h, len);
   int hole = 0;
   if (lane == 0) {
     int child = 0;
     while (child < (len - 1) / 2) {
       child = 2 * (child + 1);
-      if (h.cost[child] > h.cost[child - 1]) child--;
-      h.cost[hole] = h.cost[child];
-      h.id[hole] = h.id[child];
+      const HeapEnt r = hget<kAllSmem>(h, child), l = hget<kAllSmem>(h, child - 1);
+      if (r.cost > l.cost) { child--; hset<kAllSmem>(h, hole, l); }
+      else hset<kAllSmem>(h, hole, r);
       hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
       child = 2 * (child + 1);
-      h.cost[hole] = h.cost[child - 1];
-      h.id[hole] = h.id[child - 1];
+      hset<kAllSmem>(h, hole, hget<kAllSmem>(h, child - 1));
       hole = child - 1;
     }
   }
   hole = __shfl_sync(0xffffffffu, hole, 0);
   __syncwarp();
-  heap_sift_up_warp(h, hole, vcost, vid, lane);
-  if (lane == 0) *size = len;
-  __syncwarp();
+  heap_sift_up_warp<kAllSmem>(h, hole, v.cost, v.id, lane);
+  return len;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -286,15 +282,22 @@ struct Shared {
   int goal_hit, path_len, truncated, done;
   int q;
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
+  double scratch_key[6];  // key broadcast for the exact-scan fallback
+  long long cyc[8];
 };
 
 // first slot in scan order (open list by id, then closed list by closing order) whose child
 // point equals (x, y) and whose scan key is >= from_key; returns the scan key or kIntMax.
-// scan key: open slot -> id ; closed slot -> n_nodes + closed_seq
-__device__ __forceinline__ int find_child_from(const WS& w, int n_nodes, double x, double y, int from_key, int* s_red) {
+// scan key: open slot -> id ; closed slot -> n_nodes + closed_seq.
+// `sxy` (may be null) is a shared-memory copy of (cx, cy) made once the search has ended.
+__device__ __forceinline__ int find_child_from(const WS& w, const double2* sxy, int n_nodes, double x, double y,
+                                               int from_key, int* s_red) {
   int best = kIntMax;
   for (int id = threadIdx.x; id < n_nodes; id += kT) {
-    if (w.cx[id] == x && w.cy[id] == y) {
+    bool eq;
+    if (sxy) { const double2 c = sxy[id]; eq = c.x == x && c.y == y; }
+    else eq = w.cx[id] == x && w.cy[id] == y;
+    if (eq) {
       const int cs = w.closed_seq[id];
       const int key = cs < 0 ? id : n_nodes + cs;
       if (key >= from_key && key < best) best = key;
@@ -302,14 +305,9 @@ __device__ __forceinline__ int find_child_from(const WS& w, int n_nodes, double 
   }
   return block_min(best, s_red);
 }
-// slot id of a scan key (closed keys need a search: which slot has closed_seq == key - n_nodes)
-__device__ __forceinline__ int slot_of_key(const WS& w, int n_nodes, int key, int* s_red) {
-  if (key < n_nodes) return key;
-  const int cs = key - n_nodes;
-  int found = kIntMax;
-  for (int id = threadIdx.x; id < n_nodes; id += kT)
-    if (w.closed_seq[id] == cs) found = id;
-  return block_min(found, s_red);
+// slot id of a scan key
+__device__ __forceinline__ int slot_of_key(const WS& w, int n_nodes, int key) {
+  return key < n_nodes ? key : w.closed_list[key - n_nodes];
 }
 
 // exact brute-force lookup of LP:56-57 for one key: first OPEN slot equal to the key (lowest
@@ -347,9 +345,12 @@ __device__ __forceinline__ void hash_insert(const WS& w, int hash_size, unsigned
 }
 
 // openNode (LP:98-102) for one node by thread 0 + heap push by warp 0.  Called by warp 0 only.
+template <bool kAllSmem>
 __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap, Shared* S, int hash_size,
                                                  const double k[6], double g, double cost, int lane) {
   const int id = S->n_nodes;
+  const int hsize = S->heap_size;
+  __syncwarp();
   if (lane == 0) {
     w.cx[id] = k[0]; w.cy[id] = k[1]; w.px[id] = k[2]; w.py[id] = k[3]; w.hd[id] = k[4]; w.vel[id] = k[5];
     w.g[id] = g; w.cost[id] = cost;
@@ -360,15 +361,16 @@ __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap,
     hash_insert(w, hash_size, fp);
   }
   __syncwarp();
-  heap_push_warp(heap, &S->heap_size, cost, id, lane);
-  if (lane == 0) S->n_nodes = id + 1;
+  heap_sift_up_warp<kAllSmem>(heap, hsize, cost, id, lane);
+  if (lane == 0) { S->n_nodes = id + 1; S->heap_size = hsize + 1; }
   __syncwarp();
 }
 
 // closeNode (LP:104-113): find the first open slot equal to frontier.top(), move it to the
 // closed list, pop the frontier.  Block-wide; returns the closed slot id (or -1).
+template <bool kAllSmem>
 __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* S, int* s_red) {
-  const int top_id = heap.id[0];
+  const int top_id = heap.s[0].id;
   int target = top_id;
   if (S->dup_seen) {
     // equal keys may exist: reproduce std::find over m_tree_open (first equal, lowest id)
@@ -379,24 +381,27 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
   }
   __syncthreads();
   if (threadIdx.x < 32) {
+    const int hsize = S->heap_size;
+    __syncwarp();
     if (threadIdx.x == 0 && target >= 0) {
       w.closed_seq[target] = S->n_closed;
+      w.closed_list[S->n_closed] = target;
       S->n_closed = S->n_closed + 1;
     }
-    __syncwarp();
-    heap_pop_warp(heap, &S->heap_size, threadIdx.x);
+    const int nsize = heap_pop_warp<kAllSmem>(heap, hsize, threadIdx.x);
+    if (threadIdx.x == 0) S->heap_size = nsize;
   }
   __syncthreads();
   return target;
 }
 
-__global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
+template <bool kAllSmem>
+__global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Shared S;
-  __shared__ int s_red[kWarps];
-  __shared__ int s_scan[kWarps];
-  __shared__ double s_vlist[kMaxVel];
-  __shared__ unsigned long long s_dig[kWarps];
+  __shared__ int s_red[kWarpsMax];
+  __shared__ int s_scan[kWarpsMax];
+  __shared__ unsigned long long s_dig[kWarpsMax];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pp_params& P = A.P;
@@ -412,43 +417,48 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
     const WS w = ws_view(A.ws_base + static_cast<size_t>(A.ws_per_query ? q : blockIdx.x) * A.ws_stride, NC,
                          A.hash_size);
     Heap heap;
-    if (A.heap_in_smem) {
-      heap.cost = reinterpret_cast<double*>(smem_raw);
-      heap.id = reinterpret_cast<int*>(smem_raw + sizeof(double) * NC);
-    } else {
-      heap.cost = w.heap_cost_g;
-      heap.id = w.heap_id_g;
-    }
+    heap.s = reinterpret_cast<HeapEnt*>(smem_raw);
+    heap.g = reinterpret_cast<HeapEnt*>(w.heap_cost_g);
+    heap.m = A.heap_smem_entries;
     const pp_query qq = A.queries[q];
     QueryD Q;
     Q.gx = qq.goal_x; Q.gy = qq.goal_y; Q.gs = qq.goal_speed;
     Q.max_speed = qq.max_speed; Q.max_accel = qq.max_accel; Q.start_speed = qq.start_speed;
     int* exp_out = A.out_exp ? A.out_exp + static_cast<size_t>(q) * A.cap_exp : nullptr;
 
+    const long long t_begin = A.timing ? clock64() : 0;
+    long long t_mark = t_begin;
+#define PP_TICK(slot) do { if (A.timing && tid == 0) { const long long now_ = clock64(); S.cyc[slot] += now_ - t_mark; t_mark = now_; } } while (0)
     // ---- initializePlanner (LP:84-96) ------------------------------------------------
-    for (int k = tid; k < A.hash_size; k += kT) w.hash[k] = 0ull;
+    {
+      ulonglong2* hz = reinterpret_cast<ulonglong2*>(w.hash);
+      for (int k = tid; k < A.hash_size / 2; k += kT) hz[k] = make_ulonglong2(0ull, 0ull);
+    }
     if (tid == 0) {
       S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
       S.n_cand_total = 0; S.n_coll_total = 0; S.goal_hit = 0; S.path_len = 0; S.truncated = 0; S.done = 0;
+      for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
     }
     __syncthreads();
     if (warp == 0) {
       const double k0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, Q.start_speed};
-      open_single_warp0(w, heap, &S, A.hash_size, k0, 0.0, 9999999999.0, lane);
+      open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k0, 0.0, 9999999999.0, lane);
     }
     __syncthreads();
 
+    PP_TICK(0);
     // ---- while(true) of LP:31 ---------------------------------------------------------
     for (;;) {
       // caps replace the ros::Time guard of LP:33-39
       if (S.n_exp >= P.max_expansions || S.n_nodes >= P.max_nodes) { if (tid == 0) S.status = PP_PLAN_CAP; break; }
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }  // top() of an empty queue
-      const int top_id = heap.id[0];                                                  // LP:40
+      const int top_id = heap.s[0].id;                                                // LP:40
       // current_node's fields are key fields, identical for every copy of the node
       const double ncx = w.cx[top_id], ncy = w.cy[top_id], npx = w.px[top_id], npy = w.py[top_id];
       const double nhd = w.hd[top_id], nvel = w.vel[top_id];
       __syncthreads();
-      const int closed_id = close_top(w, heap, &S, s_red);                            // LP:41
+      const int closed_id = close_top<kAllSmem>(w, heap, &S, s_red);                            // LP:41
+      PP_TICK(1);
       if (tid == 0) {
         if (exp_out && S.n_exp < A.cap_exp) exp_out[S.n_exp] = closed_id;
         S.n_exp = S.n_exp + 1;
@@ -456,96 +466,86 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
       }
       __syncthreads();
 
-      // ---- checkForGoal (LP:269-287) over interpolatePoints(child, parent) (LP:301-316) --
-      if (warp == 0) {
-        const double dx = dm::sub(ncx, npx), dy = dm::sub(ncy, npy);
-        const double angle = dm::atan2_(dy, dx);
-        const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
-        int n_pts;
-        if (!dm::trunc_to_int(dm::mul(dm::div(dist, P.search_res), 2.0), &n_pts)) n_pts = 0;
-        double sa, ca;
-        dm::sincos(angle, &sa, &ca);
-        const bool speed_ok = fabs(dm::sub(nvel, Q.gs)) <= P.goal_speed_tolerance;
-        for (int base = 0; base < n_pts; base += 32) {
-          const int i = base + lane;
-          bool hit = false;
-          double x = 0, y = 0;
-          if (i < n_pts) {
-            const double t = dm::mul(dm::div(static_cast<double>(i), static_cast<double>(n_pts)), dist);
-            x = dm::add(ncx, dm::mul(t, ca));
-            y = dm::add(ncy, dm::mul(t, sa));
-            hit = speed_ok && fabs(dm::sub(x, Q.gx)) <= P.goal_pos_tolerance &&
-                  fabs(dm::sub(y, Q.gy)) <= P.goal_pos_tolerance;
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (m) {
-            const int src = __ffs(m) - 1;  // first point in loop order
-            if (lane == src) {
-              // interpolateToGoalPoint (LP:289-299)
-              S.goal_node[0] = x; S.goal_node[1] = y; S.goal_node[2] = ncx; S.goal_node[3] = ncy;
-              S.goal_node[4] = dm::atan2_(dm::sub(y, ncy), dm::sub(x, ncx));
-              S.goal_node[5] = Q.gs;
-              S.goal_hit = 1;
-            }
-            break;
-          }
-        }
+      // ---- calcPossibleVelocities (LP:191-216) / calcPossibleYaws (LP:218-232) -----------------
+      // every thread derives the same counts; no serial section
+      const double time_step = dm::div(P.time_step_ms, 1000.0);
+      const double v_hi = dm::add(nvel, dm::mul(Q.max_accel, time_step));
+      const double v_lo = dm::sub(nvel, dm::mul(Q.max_accel, time_step));
+      int n_vraw;
+      if (!dm::trunc_to_int(dm::div(dm::sub(v_hi, v_lo), P.velocity_res), &n_vraw)) n_vraw = 0;
+      bool unsupported = n_vraw > 1024;
+      if (unsupported) n_vraw = 0;
+      int n_vel = 0;
+      for (int i = 0; i < n_vraw; ++i) {
+        const double v = dm::add(v_lo, dm::mul(static_cast<double>(i), P.velocity_res));
+        const bool skip = (v == 0 && Q.gs != 0) || v > Q.max_speed || v < 0;
+        n_vel += skip ? 0 : 1;
       }
-      __syncthreads();
-      if (S.goal_hit) {
-        if (warp == 0) {
-          double k[6];
-          for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
-          open_single_warp0(w, heap, &S, A.hash_size, k, 0.0, 0.0, lane);             // LP:45
-        }
-        __syncthreads();
-        if (tid == 0) S.status = PP_PLAN_FOUND;
-        break;
-      }
-
-      // ---- getNeighbors (LP:146-169) -------------------------------------------------------
-      if (tid == 0) {
-        // calcPossibleVelocities (LP:191-216)
-        const double time_step = dm::div(P.time_step_ms, 1000.0);
-        const double hi = dm::add(nvel, dm::mul(Q.max_accel, time_step));
-        const double lo = dm::sub(nvel, dm::mul(Q.max_accel, time_step));
-        const double range = dm::sub(hi, lo);
-        int n;
-        if (!dm::trunc_to_int(dm::div(range, P.velocity_res), &n)) n = 0;
-        int cnt = 0;
-        for (int i = 0; i < n; ++i) {
-          const double v = dm::add(lo, dm::mul(static_cast<double>(i), P.velocity_res));
-          if (v == 0 && Q.gs != 0) continue;
-          if (v > Q.max_speed || v < 0) continue;
-          if (cnt < kMaxVel) s_vlist[cnt] = v;
-          cnt++;
-        }
-        // calcPossibleYaws (LP:218-232): `for (int i = 0; i < double_n; i++)`
-        const double yhi = dm::add(nhd, P.heading_diff), ylo = dm::sub(nhd, P.heading_diff);
-        const double yn = dm::div(dm::sub(yhi, ylo), P.heading_res);
-        int n_yaw = 0;
-        if (yn > 0) n_yaw = yn >= 4096.0 ? 4096 : __double2int_ru(yn);
-        if (cnt > kMaxVel || static_cast<long long>(cnt) * n_yaw + S.n_nodes + 2 > A.NC) { S.status = PP_PLAN_BROKEN; cnt = 0; }
-        S.n_vel = cnt;
-        S.n_yaw = n_yaw;
-      }
-      __syncthreads();
-      if (S.status == PP_PLAN_BROKEN) break;
-      const int n_yaw = S.n_yaw, n_cand = S.n_vel * n_yaw;
+      // `for (int i = 0; i < double_n; i++)`: ceil of the double bound (the 26 / 27 trap)
       const double ylo = dm::sub(nhd, P.heading_diff);
+      const double yn = dm::div(dm::sub(dm::add(nhd, P.heading_diff), ylo), P.heading_res);
+      int n_yaw = 0;
+      if (yn > 0) n_yaw = yn >= 4096.0 ? 4096 : __double2int_ru(yn);
+      if (n_vel > kMaxVel || static_cast<long long>(n_vel) * n_yaw + S.n_nodes + 2 > A.NC) unsupported = true;
+      const int n_cand = unsupported ? 0 : n_vel * n_yaw;
       const int base_nodes = S.n_nodes;
       int appended = 0;  // block-uniform running count
       int collided_local = 0;
-      for (int c0 = 0; c0 < n_cand; c0 += kT) {
+      bool goal_stop = false;
+
+      for (int c0 = 0; c0 == 0 || c0 < n_cand; c0 += kT) {
+        // ---- checkForGoal (LP:269-287) over interpolatePoints(child, parent) (LP:301-316):
+        // done by the last warp while the other warps already evaluate the children
+        if (c0 == 0 && warp == kWarps - 1) {
+          const double dx = dm::sub(ncx, npx), dy = dm::sub(ncy, npy);
+          const double angle = dm::atan2_(dy, dx);
+          const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
+          int n_pts;
+          if (!dm::trunc_to_int(dm::mul(dm::div(dist, P.search_res), 2.0), &n_pts)) n_pts = 0;
+          double sa, ca;
+          dm::sincos(angle, &sa, &ca);
+          const bool speed_ok = fabs(dm::sub(nvel, Q.gs)) <= P.goal_speed_tolerance;
+          for (int base = 0; base < n_pts; base += 32) {
+            const int i = base + lane;
+            bool hit = false;
+            double x = 0, y = 0;
+            if (i < n_pts) {
+              const double t = dm::mul(dm::div(static_cast<double>(i), static_cast<double>(n_pts)), dist);
+              x = dm::add(ncx, dm::mul(t, ca));
+              y = dm::add(ncy, dm::mul(t, sa));
+              hit = speed_ok && fabs(dm::sub(x, Q.gx)) <= P.goal_pos_tolerance &&
+                    fabs(dm::sub(y, Q.gy)) <= P.goal_pos_tolerance;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+              const int src = __ffs(m) - 1;  // first point in loop order
+              if (lane == src) {
+                // interpolateToGoalPoint (LP:289-299)
+                S.goal_node[0] = x; S.goal_node[1] = y; S.goal_node[2] = ncx; S.goal_node[3] = ncy;
+                S.goal_node[4] = dm::atan2_(dm::sub(y, ncy), dm::sub(x, ncx));
+                S.goal_node[5] = Q.gs;
+                S.goal_hit = 1;
+              }
+              break;
+            }
+          }
+        }
+        // ---- getNeighbors (LP:146-169): one thread per (velocity, yaw) child ------------------
         const int c = c0 + tid;
-        bool alive = false;
+        bool alive = false, collided = false;
         double k[6] = {0, 0, 0, 0, 0, 0};
         double g = 0, cost = 0;
         unsigned long long fp = 0;
         bool suspicious = false;
         if (c < n_cand) {
           const int vi = c / n_yaw, yi = c - vi * n_yaw;
-          const double vel = s_vlist[vi];
+          double vel = 0;
+          int seen = 0;
+          for (int i = 0; i < n_vraw; ++i) {   // the vi-th velocity that passes the filter of LP:205-212
+            const double v = dm::add(v_lo, dm::mul(static_cast<double>(i), P.velocity_res));
+            const bool skip = (v == 0 && Q.gs != 0) || v > Q.max_speed || v < 0;
+            if (!skip) { if (seen == vi) vel = v; seen++; }
+          }
           const double yaw = dm::add(ylo, dm::mul(static_cast<double>(yi), P.heading_res));
           const double sum_v = dm::add(nvel, vel);                                     // LP:155
           const double step = dm::div(dm::mul(sum_v, P.time_step_ms), 1000.0);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
           const double x = dm::add(ncx, dm::mul(step, cyaw));                          // LP:156
           const double y = dm::add(ncy, dm::mul(step, sy));                            // LP:157
           if (collide_pose_thread(A.g, A.cp, x, y, yaw)) {                             // LP:159
-            collided_local++;
+            collided = true;
           } else {
             alive = true;
             k[0] = x; k[1] = y; k[2] = ncx; k[3] = ncy; k[4] = yaw; k[5] = vel;
@@ -565,17 +565,24 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
             suspicious = hash_contains(w, A.hash_size, fp);
           }
         }
+        if (c0 == 0) {
+          __syncthreads();
+          PP_TICK(2);
+          if (S.goal_hit) { goal_stop = true; break; }   // LP:43: the children are never looked at
+        }
+        if (unsupported) break;
+        collided_local += collided ? 1 : 0;
         // LP:56-72.  A fingerprint never seen before cannot equal any node: open it.  A seen
         // fingerprint takes the exact scan (rare).
         for (;;) {
           const int owner = block_min(suspicious ? tid : kIntMax, s_red);
           if (owner == kIntMax) break;
           if (tid == owner) {
-            for (int cix = 0; cix < 6; ++cix) S.goal_node[cix] = k[cix];
+            for (int cix = 0; cix < 6; ++cix) S.scratch_key[cix] = k[cix];
           }
           __syncthreads();
           double kk[6];
-          for (int cix = 0; cix < 6; ++cix) kk[cix] = S.goal_node[cix];
+          for (int cix = 0; cix < 6; ++cix) kk[cix] = S.scratch_key[cix];
           int fo, ac;
           scan_exact(w, S.n_nodes, kk, &fo, &ac, s_red);
           if (tid == owner) {
@@ -594,7 +601,6 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
         if (lane == 0) s_scan[warp] = __popc(bal);
         __syncthreads();
         int before = 0, total = 0;
-#pragma unroll
         for (int ww = 0; ww < kWarps; ++ww) {
           const int v = s_scan[ww];
           if (ww < warp) before += v;
@@ -612,25 +618,49 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
         appended += total;
         __syncthreads();
       }
+      if (goal_stop) {
+        if (warp == 0) {
+          double k[6];
+          for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
+          open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k, 0.0, 0.0, lane);             // LP:45
+        }
+        __syncthreads();
+        if (tid == 0) S.status = PP_PLAN_FOUND;
+        break;
+      }
+      if (unsupported) { if (tid == 0) S.status = PP_PLAN_BROKEN; break; }
       collided_local = block_sum(collided_local, s_red);
-      // openNode for every survivor, in order: frontier pushes by warp 0 (LP:62 / LP:70)
+      PP_TICK(3);
+      // openNode for every survivor, in order: frontier pushes by warp 0 (LP:62 / LP:70).  The
+      // costs are fetched 32 at a time (one L2 round trip) and handed out by shuffle.
       if (warp == 0) {
-        for (int r = 0; r < appended; ++r) {
-          const int id = base_nodes + r;
-          heap_push_warp(heap, &S.heap_size, w.cost[id], id, lane);
+        int hsize = S.heap_size;
+        for (int r0 = 0; r0 < appended; r0 += 32) {
+          const int mine = r0 + lane;
+          const double my_cost = mine < appended ? w.cost[base_nodes + mine] : 0.0;
+          const int cnt = min(32, appended - r0);
+          for (int r = 0; r < cnt; ++r) {
+            const double cst = __shfl_sync(0xffffffffu, my_cost, r);
+            heap_sift_up_warp<kAllSmem>(heap, hsize, cst, base_nodes + r0 + r, lane);
+            hsize++;
+          }
         }
         if (lane == 0) {
+          S.heap_size = hsize;
           S.n_nodes = base_nodes + appended;
           S.n_cand_total += n_cand;
           S.n_coll_total += collided_local;
         }
       }
       __syncthreads();
+      PP_TICK(4);
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }
-      close_top(w, heap, &S, s_red);                                                  // LP:80
+      close_top<kAllSmem>(w, heap, &S, s_red);                                                  // LP:80
+      PP_TICK(5);
     }
     __syncthreads();
 
+    PP_TICK(7);
     // ---- outputs -----------------------------------------------------------------------
     const int n_nodes = S.n_nodes;
     double* path = A.out_path + static_cast<size_t>(q) * A.cap_path * 2;
@@ -640,8 +670,17 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
     if (S.status == PP_PLAN_FOUND) {
       // calcPathMsg (LP:503-527): the walk is sequential, each link search is block-parallel.
       // The reversed path is staged in the (now idle) heap-cost array of this workspace.
-      double* rev = w.heap_cost_g;  // NC doubles: room for NC/2 points
-      const int rev_cap = NC / 2;
+      double* rev = w.heap_cost_g;  // 2*NC doubles: room for NC points
+      const int rev_cap = NC;
+      // the frontier is dead now: reuse its shared memory for a copy of every child point,
+      // so the link searches below scan shared memory instead of L2
+      const double2* sxy = nullptr;
+      if (n_nodes <= A.heap_smem_entries) {
+        double2* dst = reinterpret_cast<double2*>(smem_raw);
+        for (int id = tid; id < n_nodes; id += kT) dst[id] = make_double2(w.cx[id], w.cy[id]);
+        sxy = dst;
+      }
+      __syncthreads();
       double cxp = S.goal_node[0], cyp = S.goal_node[1];
       int len = 0;
       if (tid == 0) { rev[0] = cxp; rev[1] = cyp; }
@@ -651,9 +690,9 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
         int pos = 0;
         bool progressed = false;
         for (;;) {
-          const int key = find_child_from(w, n_nodes, cxp, cyp, pos, s_red);
+          const int key = find_child_from(w, sxy, n_nodes, cxp, cyp, pos, s_red);
           if (key == kIntMax) break;                   // end of this pass over open + closed
-          const int id = slot_of_key(w, n_nodes, key, s_red);
+          const int id = slot_of_key(w, n_nodes, key);
           cxp = w.px[id]; cyp = w.py[id];
           if (len < rev_cap) { if (tid == 0) { rev[2 * len] = cxp; rev[2 * len + 1] = cyp; } }
           len++;
@@ -682,11 +721,16 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
           const double bx = rev[2 * (len - 2 - i)], by = rev[2 * (len - 2 - i) + 1];
           int best_a = -1, best_b = -1, id_a = -1, id_b = -1;
           for (int id = lane; id < n_nodes; id += 32) {
-            const double ex = w.cx[id], ey = w.cy[id];
-            const int cs = w.closed_seq[id];
-            const int key = cs < 0 ? id : n_nodes + cs;
-            if (ex == ax && ey == ay) { if (key > best_a) { best_a = key; id_a = id; } }
-            else if (ex == bx && ey == by) { if (key > best_b) { best_b = key; id_b = id; } }
+            double ex, ey;
+            if (sxy) { const double2 c = sxy[id]; ex = c.x; ey = c.y; }
+            else { ex = w.cx[id]; ey = w.cy[id]; }
+            const bool ma = ex == ax && ey == ay, mb = ex == bx && ey == by;
+            if (ma || mb) {
+              const int cs = w.closed_seq[id];
+              const int key = cs < 0 ? id : n_nodes + cs;
+              if (ma) { if (key > best_a) { best_a = key; id_a = id; } }
+              else if (key > best_b) { best_b = key; id_b = id; }
+            }
           }
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) {
@@ -708,8 +752,8 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
         if (A.want_path_ids) {
           for (int k = 0; k < len && k < A.cap_path; ++k) {
             const double x = rev[2 * (len - 1 - k)], y = rev[2 * (len - 1 - k) + 1];
-            const int key = find_child_from(w, n_nodes, x, y, 0, s_red);
-            const int id = key == kIntMax ? -1 : slot_of_key(w, n_nodes, key, s_red);
+            const int key = find_child_from(w, sxy, n_nodes, x, y, 0, s_red);
+            const int id = key == kIntMax ? -1 : slot_of_key(w, n_nodes, key);
             if (tid == 0) path_ids[k] = id;
           }
         }
@@ -741,6 +785,8 @@ __global__ void __launch_bounds__(kT) plan_kernel(PlanArgs A) {
       hd.n_collisions = S.n_coll_total;
       hd.truncated = S.truncated;
       hd.digest = d;
+      if (A.timing) { const long long now_ = clock64(); S.cyc[6] += now_ - t_mark; S.cyc[7] = now_ - t_begin; }
+      for (int c = 0; c < 8; ++c) hd.cyc[c] = S.cyc[c];
       A.hdr[q] = hd;
     }
     __syncthreads();
@@ -860,12 +906,21 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   while (hash_size < 2 * NC) hash_size <<= 1;
   const size_t stride = ws_bytes(NC, hash_size);
 
-  const size_t heap_smem = (sizeof(double) + sizeof(int)) * static_cast<size_t>(NC);
-  const int heap_in_smem = heap_smem <= 200 * 1024 ? 1 : 0;
-  const size_t dyn_smem = heap_in_smem ? heap_smem : 0;
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  // Frontier placement: a lone query keeps the whole heap in shared memory (lowest latency);
+  // a batch keeps only the top levels there so that several CTAs fit an SM and overlap each
+  // other's serial heap phases.
+  const int smem_cap_entries = 200 * 1024 / 16;
+  int heap_entries = std::min(NC, smem_cap_entries);
+  if (n >= 2 * h->sm_count) heap_entries = std::min(heap_entries, 2048);
+  else if (n > h->sm_count) heap_entries = std::min(heap_entries, 6144);
+  const size_t dyn_smem = 16 * static_cast<size_t>(heap_entries);
+  const bool all_smem = heap_entries >= NC;
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int ctas_per_sm = 1;
-  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel, kT, dyn_smem));
+  const int threads = n > h->sm_count ? 128 : 256;
+  if (all_smem) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<true>, threads, dyn_smem));
+  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<false>, threads, dyn_smem));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_ctas = h->sm_count * ctas_per_sm;
   const int grid = std::min(n, max_ctas);
@@ -901,11 +956,12 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   A.n_queries = n;
   A.NC = NC;
   A.hash_size = hash_size;
-  A.heap_in_smem = heap_in_smem;
+  A.heap_smem_entries = heap_entries;
   A.ws_per_query = want_nodes ? 1 : 0;
   A.want_path_ids = want_path_ids ? 1 : 0;
   A.cap_path = cap_path;
   A.cap_exp = cap_exp;
+  A.timing = getenv("PP_PLAN_TIMING") ? 1 : 0;
   A.ws_stride = stride;
   A.ws_base = W->ws;
   A.hdr = reinterpret_cast<PlanHdr*>(ob);
@@ -916,7 +972,8 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   A.work_counter = W->d_counter;
 
   PP_CUDA(cudaEventRecord(h->ev[8], s));
-  plan_kernel<<<grid, kT, dyn_smem, s>>>(A);
+  if (all_smem) plan_kernel<true><<<grid, threads, dyn_smem, s>>>(A);
+  else plan_kernel<false><<<grid, threads, dyn_smem, s>>>(A);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   bool want_parent = false;
@@ -939,6 +996,10 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
 
   const unsigned char* hb = W->h_out.data();
   const PlanHdr* hdr = reinterpret_cast<const PlanHdr*>(hb);
+  if (getenv("PP_PLAN_TIMING")) {
+    const char* names[8] = {"init", "close", "goal+eval", "commit", "push", "close2", "extract", "total"};
+    for (int c = 0; c < 8; ++c) fprintf(stderr, "[pp_plan] query 0 %-10s %10lld cycles\n", names[c], hdr[0].cyc[c]);
+  }
   const double* hpath = reinterpret_cast<const double*>(hb + hdr_b);
   const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + path_b);
   const double* hprof = reinterpret_cast<const double*>(hb + hdr_b + path_b + pid_b);
@@ -986,7 +1047,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
       }
       if (r.node_closed_seq) {
         const size_t off = sizeof(double) * 8 * NC + sizeof(unsigned long long) * NC +
-                           sizeof(unsigned long long) * hash_size + sizeof(double) * NC;
+                           sizeof(unsigned long long) * hash_size + sizeof(double) * 2 * NC;
         PP_CUDA(cudaMemcpyAsync(r.node_closed_seq, wsq + off, sizeof(int) * nn, cudaMemcpyDeviceToHost, s));
       }
       if (r.node_parent)

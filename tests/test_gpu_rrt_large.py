@@ -1,0 +1,63 @@
+"""Size-independent properties of the sampling planner at a size the CPU oracle cannot
+finish in seconds (BASELINE configs[3]-style run: dense clutter, corner to corner):
+determinism, prefix property across sample budgets, motion-model constraints, and
+cross-kernel consistency (every tree edge re-checked with the batch edge-collision API)."""
+import numpy as np
+import pytest
+import torch
+
+from autonomouscar_b200 import PP_COLLISION_ORIENTED, PP_PLAN_CAP, PP_PLAN_FOUND, default_params, make_query, worlds
+
+pytestmark = pytest.mark.gpu
+
+
+def test_large_rrt_properties(cuda_device):
+    from autonomouscar_b200 import Planner
+    N = 4096
+    p = default_params(costmap_res=0.1, costmap_width=N, costmap_height=N, collision_mode=PP_COLLISION_ORIENTED,
+                       time_step_ms=1000.0, rrt_samples_per_round=256, rrt_max_samples=400000, max_nodes=400001,
+                       rrt_goal_tolerance=2.0)
+    g = worlds.block_grid(N, N, frac=0.01, block=16, seed=4, noise=False)
+    half = N * 0.1 / 2
+    sx, sy, gx, gy = -half + 10.0, -half + 10.0, half - 10.0, half - 10.0
+    worlds.clear_disc(g, p, sx, sy, 6.0)
+    worlds.clear_disc(g, p, gx, gy, 6.0)
+    q = make_query(gx, gy, start_x=sx, start_y=sy, start_heading=0.785, start_speed=1.0, seed=2018, query_id=0)
+    pl = Planner(p, device=0)
+    pl.set_grid(g)
+    full = pl.rrt_plan(q, cap_nodes=400300, cap_path=65536)
+    assert full.status == PP_PLAN_FOUND and full.n_nodes > 20000 and full.n_path > 50
+    again = pl.rrt_plan(q, cap_nodes=8, cap_path=65536, want_nodes=False)
+    assert again.summary() == full.summary()                       # deterministic
+    st, par = full.node_state, full.node_parent
+    ids = full.path_node_ids
+    assert ids[0] == 0 and np.all(par[ids[1:]] == ids[:-1])         # the path is a parent chain
+    assert abs(full.path_xy[-1, 0] - gx) <= 2.0 and abs(full.path_xy[-1, 1] - gy) <= 2.0
+    assert np.all(np.abs(st[1:, 4] - st[par[1:], 4]) <= p.heading_diff + 1e-12)   # steering limit
+    np.testing.assert_allclose(st[1:, 6], (st[par[1:], 5] + st[1:, 5]) * 1.0, rtol=1e-12)   # LP:155 step
+    assert np.all(par[1:] < np.arange(1, len(par)))                 # parents precede children
+    # every tree edge must be collision-free according to the batch edge kernel (float32 inputs:
+    # compare on a sample of edges whose coordinates survive the float round trip unchanged is
+    # not possible in general, so accept a tiny disagreement budget at cell boundaries)
+    sel = np.arange(1, full.n_nodes, 7)
+    edges = np.empty((len(sel), 5), dtype=np.float32)
+    edges[:, 0:2] = st[par[sel], 0:2]
+    edges[:, 2:4] = st[sel, 0:2]
+    edges[:, 4] = st[sel, 4]
+    flags = pl.collide_edges_dev(torch.from_numpy(edges).cuda())
+    pl.sync()
+    assert flags.float().mean().item() < 2e-3
+    # prefix property: a smaller sample budget yields exactly the first rounds of the same tree
+    budget = (full.n_candidates // 256 // 2) * 256
+    p2 = default_params(costmap_res=0.1, costmap_width=N, costmap_height=N, collision_mode=PP_COLLISION_ORIENTED,
+                        time_step_ms=1000.0, rrt_samples_per_round=256, rrt_max_samples=budget, max_nodes=400001,
+                        rrt_goal_tolerance=2.0)
+    pl2 = Planner(p2, device=0)
+    pl2.set_grid(g)
+    half_run = pl2.rrt_plan(q, cap_nodes=400300, cap_path=65536)
+    assert half_run.status == PP_PLAN_CAP and half_run.n_candidates == budget
+    n = half_run.n_nodes
+    np.testing.assert_array_equal(half_run.node_state.view(np.uint64), st[:n].view(np.uint64))
+    np.testing.assert_array_equal(half_run.node_parent, par[:n])
+    pl.close()
+    pl2.close()
