@@ -80,3 +80,39 @@ def forward_queries(n, seed=0, dist=(15.0, 25.0), lateral=3.0, speed=(0.0, 1.5))
         v0 = rng.uniform(*speed)
         qs.append(make_query(gx, gy, start_speed=v0, seed=seed, query_id=k))
     return qs
+
+
+# the 12 waypoints of the reference's global route (global_path_planner.py:101-102), world frame
+ROUTE_X = [26.4527, 39.5884, 52.7228, 69.0941, 83.7454, 105.948, 123.622, 142.292, 162.782, 172.996, 171.868, 171.274]
+ROUTE_Y = [13.998, 14.5571, 14.5571, 15.1161, 15.6748, 16.14200, 16.142, 16.0263, 16.2719, 48.2004, 82.6559, 122.569]
+
+
+def road_world(path):
+    """BASELINE configs[0] world from the committed fixture (see tests/golden/make_road_world.py):
+    int8 [4096, 4096] m_c_space grid in the vehicle frame of the spawn pose, off-road = 100."""
+    z = np.load(path)
+    n = int(z["n"][0])
+    occ = np.unpackbits(z["packed"])[: n * n].reshape(n, n).astype(bool)
+    g = np.zeros((n, n), dtype=np.int8)
+    g[occ] = 100
+    return g, float(z["res"][0]), tuple(float(v) for v in z["spawn"])
+
+
+def route_queries(spawn=(0.0, 15.0), lookahead=20.0, spacing=1.0):
+    """The reference's own query rule (local_navigator.py:27-46, 586-609): densify the route to
+    `spacing` metres and take the first waypoint at least `lookahead` metres from the car.
+    Returns the goal of the first query in the vehicle frame of the spawn pose (yaw 0)."""
+    pts = [(ROUTE_X[0], ROUTE_Y[0])]
+    for k in range(len(ROUTE_X) - 1):
+        x0, y0, x1, y1 = ROUTE_X[k], ROUTE_Y[k], ROUTE_X[k + 1], ROUTE_Y[k + 1]
+        d = float(np.hypot(x1 - x0, y1 - y0)) / spacing
+        if d > 1:
+            n = int(np.ceil(d))
+            for m in range(1, n + 1):
+                pts.append((x0 + m * (x1 - x0) / n, y0 + m * (y1 - y0) / n))
+        else:
+            pts.append((x1, y1))
+    for x, y in pts:
+        if np.hypot(x - spawn[0], y - spawn[1]) >= lookahead:
+            return x - spawn[0], y - spawn[1]
+    return pts[-1][0] - spawn[0], pts[-1][1] - spawn[1]

@@ -354,6 +354,36 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
         t1 = time.perf_counter()
         r1 = pl.plan(qs[0], cap_nodes=16384)
         lat.append(time.perf_counter() - t1)
+    # configs[0] / [1]: the reference's first plan request on the car_demo road world @0.1 m
+    cfg1 = None
+    fixture = os.path.join(ROOT, "tests", "golden", "road_world_4096.npz")
+    if rank == 0 and os.path.exists(fixture):
+        from autonomouscar_b200 import PP_COLLISION_REF_AABB, make_query as mq
+        rgrid, rres, spawn = worlds.road_world(fixture)
+        gx, gy = worlds.route_queries(spawn)
+        p1 = default_params(costmap_res=rres, costmap_width=4096, costmap_height=4096,
+                            collision_mode=PP_COLLISION_REF_AABB, max_nodes=10000)
+        pl1 = Planner(p1, device=dev.index)
+        pl1.set_grid(rgrid)
+        q1 = mq(gx, gy, start_speed=0.0)
+        pl1.plan(q1)
+        l1 = []
+        for _ in range(5):
+            t1 = time.perf_counter()
+            g1 = pl1.plan(q1, cap_nodes=16384)
+            l1.append(time.perf_counter() - t1)
+        cfg1 = {"world": "car_demo road polylines, off-road = occupied, 4096x4096 @0.1 m", "mode": "REF_AABB",
+                "goal_vehicle_frame": [gx, gy], "gpu_ms": 1e3 * sorted(l1)[2], "nodes": int(g1.n_nodes),
+                "path_poses": int(g1.n_path), "status": int(g1.status)}
+        if not args.skip_cpu:
+            from oracle import binding as orc
+            t1 = time.perf_counter()
+            c1 = orc.plan(p1, rgrid, q1, math_mode=orc.MATH_LIBM)
+            cfg1["cpu_oracle_ms_1thread"] = 1e3 * (time.perf_counter() - t1)
+            d1 = orc.plan(p1, rgrid, q1, math_mode=orc.MATH_DET)
+            cfg1["bit_exact_vs_oracle"] = bool(d1.summary() == g1.summary() and np.array_equal(d1.path_xy, g1.path_xy)
+                                               and np.array_equal(d1.node_parent, g1.node_parent))
+        pl1.close()
     # sampling planner (extension rows S1-S3): batch of independent queries on a 1024^2 grid
     rp = default_params(costmap_res=0.1, costmap_width=1024, costmap_height=1024, collision_mode=PP_COLLISION_ORIENTED,
                         time_step_ms=1000.0, rrt_samples_per_round=64, rrt_max_samples=10000, max_nodes=10000,
@@ -387,6 +417,7 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
                "mean_nodes": float(rec[:, 2].float().mean().item()),
                "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_nodes": int(r1.n_nodes),
                "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000",
+               "config1_road_world": cfg1,
                "rrt": {"queries_per_gpu": n_rrt, "plans_per_s": n_rrt * world / rrt_dt, "found_rank0": rrt_found,
                        "samples_per_s_rank0": rrt_samples / rrt_dt, "grid": "1024x1024 @0.1 m, 10k-sample cap, K=64"}}
         if not args.skip_cpu:

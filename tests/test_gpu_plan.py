@@ -131,3 +131,26 @@ def test_plan_batch_matches_single_and_oracle(oracle, cuda_device):
         np.testing.assert_array_equal(batch[k].path_xy, ref.path_xy)
         np.testing.assert_array_equal(batch[k].speeds, ref.speeds)
     pl.close()
+
+
+@pytest.mark.parametrize("mode", [PP_COLLISION_AS_SHIPPED, PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED])
+def test_config1_road_world_query(oracle, cuda_device, mode):
+    """BASELINE configs[0]/[1]: the reference's first plan request (next waypoint >= 20 m ahead of
+    the spawn pose, local_navigator.py:586-609) on the car_demo road world rasterised at 0.1 m
+    (off-road = occupied), 10k-node cap; path / parents / booleans bit-exact vs the oracle."""
+    import os
+    from autonomouscar_b200 import Planner
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "road_world_4096.npz")
+    grid, res, spawn = worlds.road_world(fixture)
+    p = default_params(costmap_res=res, costmap_width=4096, costmap_height=4096, collision_mode=mode, max_nodes=10000)
+    gx, gy = worlds.route_queries(spawn)
+    assert abs(gx - 26.4527) < 1e-9 and abs(gy + 1.002) < 1e-9
+    pl = Planner(p, device=0)
+    pl.set_grid(grid)
+    # the straight first leg, and a goal beside the road so that children run into the verge
+    for q in (make_query(gx, gy, start_speed=0.0), make_query(18.0, 6.5, start_speed=1.0)):
+        got = pl.plan(q)
+        ref = oracle.plan(p, grid, q, math_mode=oracle.MATH_DET)
+        _assert_same(got, ref)
+    assert ref.n_collisions > 0 or mode == PP_COLLISION_AS_SHIPPED
+    pl.close()
