@@ -18,7 +18,7 @@ EXPORTS = [
     "pp_set_collision_mode", "pp_set_grid", "pp_set_grid_dev", "pp_get_cspace", "pp_collide_batch",
     "pp_collide_batch_dev", "pp_collide_edges_dev", "pp_footprint_points", "pp_sample_poses_dev",
     "pp_philox4x32_10", "pp_nearest_dev", "pp_find_exact_dev", "pp_plan", "pp_plan_batch", "pp_rrt_plan",
-    "pp_rrt_plan_batch", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
+    "pp_rrt_plan_batch", "pp_get_visited", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
     "pp_last_narrow_count", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
     "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch",
 ]
@@ -64,6 +64,7 @@ def load():
     L.pp_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_rrt_plan.argtypes = [vp, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_rrt_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
+    L.pp_get_visited.argtypes = [vp, vp, C.c_size_t]
     L.pp_sync.argtypes = [vp]
     L.pp_stream.argtypes = [vp, C.POINTER(vp)]
     L.pp_launch_count.argtypes = [vp, C.POINTER(u64)]

@@ -138,6 +138,7 @@ int pp_destroy(pp_handle* h) {
   cudaFree(h->d_poses);
   cudaFree(h->d_flags);
   cudaFree(h->d_list);
+  cudaFree(h->d_visited);
   cudaFree(h->d_count);
   cudaFreeHost(h->h_count);
   cudaFree(h->scratch);
@@ -319,6 +320,17 @@ int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* r
   if (n == 0) return PP_OK;
   PP_CUDA(cudaSetDevice(h->device));
   return plan_batch(h, n, queries, results);
+}
+
+int pp_get_visited(pp_handle* h, uint8_t* out_host, size_t capacity) {
+  if (!h || !out_host) return PP_ERR_INVALID;
+  const size_t cells = static_cast<size_t>(h->P.costmap_width) * h->P.costmap_height;
+  if (capacity < cells) { set_last_error("pp_get_visited: buffer too small"); return PP_ERR_CAPACITY; }
+  if (!h->d_visited) { set_last_error("pp_get_visited: no single-query plan has run yet"); return PP_ERR_INVALID; }
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaMemcpyAsync(out_host, h->d_visited, cells, cudaMemcpyDeviceToHost, h->stream));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  return PP_OK;
 }
 
 int pp_rrt_plan(pp_handle* h, const pp_query* query, pp_result* result) {

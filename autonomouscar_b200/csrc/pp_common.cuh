@@ -225,6 +225,7 @@ struct pp_handle {
   int64_t list_cap = 0;
   void* scratch = nullptr;         // grid-prep scratch
   size_t scratch_bytes = 0;
+  uint8_t* d_visited = nullptr;    // A12 debug bitmap of the last single plan (W*H bytes)
   PlanWorkspace* plan_ws = nullptr;
   RrtWorkspace* rrt_ws = nullptr;
 };

@@ -69,6 +69,7 @@ struct PlanArgs {
   double* out_profile;    // [n][3][cap_path]
   int* out_exp;           // [n][cap_exp] or null
   int* work_counter;
+  uint8_t* visited;       // A12 debug bitmap (single-query plans only) or null
 };
 
 // SoA view of one workspace
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
         // ---- getNeighbors (LP:146-169): one thread per (velocity, yaw) child ------------------
         const int c = c0 + tid;
         bool alive = false, collided = false;
+        int my_visit = -1;
         double k[6] = {0, 0, 0, 0, 0, 0};
         double g = 0, cost = 0;
         unsigned long long fp = 0;
@@ -565,12 +567,21 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
             suspicious = hash_contains(w, A.hash_size, fp);
           }
         }
+        // markVisited (LP:55 -> LP:318-326) for every child getNeighbors returned, bounds-guarded
+        if (A.visited && c < n_cand && !collided) {
+          int vx, vy;
+          if (dm::trunc_to_int(dm::sub(static_cast<double>(A.g.W / 2), dm::div(k[1], A.g.res)), &vx) &&
+              dm::trunc_to_int(dm::sub(static_cast<double>(A.g.H / 2), dm::div(k[0], A.g.res)), &vy) && vx >= 0 &&
+              vx < A.g.W && vy >= 0 && vy < A.g.H)
+            my_visit = vx * A.g.H + vy;
+        }
         if (c0 == 0) {
           __syncthreads();
           PP_TICK(2);
           if (S.goal_hit) { goal_stop = true; break; }   // LP:43: the children are never looked at
         }
         if (unsupported) break;
+        if (my_visit >= 0) A.visited[my_visit] = 1;   // only reached when the goal test did not end the plan
         collided_local += collided ? 1 : 0;
         // LP:56-72.  A fingerprint never seen before cannot equal any node: open it.  A seen
         // fingerprint takes the exact scan (rare).
@@ -970,6 +981,13 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   A.out_profile = reinterpret_cast<double*>(ob + hdr_b + path_b + pid_b);
   A.out_exp = want_exp ? reinterpret_cast<int*>(ob + hdr_b + path_b + pid_b + prof_b) : nullptr;
   A.work_counter = W->d_counter;
+  A.visited = nullptr;
+  if (n == 1) {   // clearVisited (LP:251-262)
+    const size_t cells = static_cast<size_t>(P.costmap_width) * P.costmap_height;
+    if (!h->d_visited) PP_CUDA(cudaMalloc(&h->d_visited, cells));
+    PP_CUDA(cudaMemsetAsync(h->d_visited, 0, cells, s));
+    A.visited = h->d_visited;
+  }
 
   PP_CUDA(cudaEventRecord(h->ev[8], s));
   if (all_smem) plan_kernel<true><<<grid, threads, dyn_smem, s>>>(A);

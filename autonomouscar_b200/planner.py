@@ -75,6 +75,12 @@ class Planner:
         self._check(self._L.pp_get_cspace(self._h, out.ctypes.data_as(C.c_void_p), out.size))
         return out.reshape(W, H)
 
+    def get_visited(self):
+        W, H = self.params.costmap_width, self.params.costmap_height
+        out = np.zeros(W * H, dtype=np.uint8)
+        self._check(self._L.pp_get_visited(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out.reshape(W, H)
+
     def set_collision_mode(self, mode):
         self._check(self._L.pp_set_collision_mode(self._h, mode))
         self.params.collision_mode = mode

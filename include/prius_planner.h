@@ -141,7 +141,8 @@ typedef struct pp_result {
   int32_t n_profile;       /* entries of the MotionPlanning message (LP:548-581)           */
   int32_t n_candidates;    /* children generated by getNeighbors over the whole plan       */
   int32_t n_collisions;    /* of those, rejected by checkCollision (LP:159)                */
-  uint64_t tree_digest;    /* order-sensitive FNV-1a over every node's 6 key doubles       */
+  uint64_t tree_digest;    /* sum over slots of a splitmix64 chain seeded with the slot id
+                              and fed the bit patterns of the node's 6 key doubles          */
   /* per node, indexed by node id:
        node_state[8*id + 0..7] = child.x child.y parent.x parent.y heading velocity g cost
        node_parent[id]  = first node in scan order (open list, then closed list) whose
@@ -247,6 +248,11 @@ int pp_find_exact_dev(pp_handle* h, int64_t n_nodes, const double* node_keys_dev
 int pp_plan(pp_handle* h, const pp_query* query, pp_result* result);
 /* n independent queries against the same grid (BASELINE config 5) */
 int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results);
+/* Debug bitmap of the most recent single-query pp_plan: out[i*H + j] = 1 for every cell that
+   markVisited (LP:318-326) touched -- one mark per child returned by getNeighbors, cleared at
+   the start of each plan like clearVisited (LP:251-262).  The reference never reads it on the
+   path (checkVisited, LP:239, is unused); unlike the reference the write is bounds-guarded. */
+int pp_get_visited(pp_handle* h, uint8_t* out_host, size_t capacity);
 /* extension: round-synchronous sampling planner (sample -> nearest -> steer -> edge
    collision -> append).  Uses the query's start_*, seed and query_id fields. */
 int pp_rrt_plan(pp_handle* h, const pp_query* query, pp_result* result);

@@ -1,0 +1,41 @@
+"""Small end-to-end pass over every kernel for compute-sanitizer (memcheck)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from autonomouscar_b200 import (PP_COLLISION_ORIENTED, PP_COLLISION_REF_AABB, PP_GRID_OCCUPANCY_MSG, Planner,  # noqa: E402
+                                default_params, make_query, worlds)
+
+for res, W, H in ((0.1, 333, 517), (0.25, 300, 300)):
+    p = default_params(costmap_res=res, costmap_width=W, costmap_height=H, collision_mode=PP_COLLISION_ORIENTED,
+                       max_nodes=1500, rrt_samples_per_round=50, rrt_max_samples=1500, time_step_ms=400.0 if res < 0.2 else 150.0)
+    g = worlds.block_grid(W, H, frac=0.02, block=6, seed=3)
+    worlds.clear_disc(g, p, 0.0, 0.0, 4.0)
+    pl = Planner(p, device=0)
+    pl.set_grid(g)
+    pl.set_grid(np.ascontiguousarray(g.ravel()[::-1]), PP_GRID_OCCUPANCY_MSG)
+    poses = worlds.random_poses(p, 5000, seed=1, inset_m=-6.0)
+    for mode in (PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED):
+        pl.set_collision_mode(mode)
+        pl.collide(poses)
+        for broad in (0, 1):
+            pl.set_broad_phase(broad)
+            pl.collide_dev(torch.from_numpy(poses).cuda())
+        e = np.concatenate([poses[:, :2], poses[:, :2] + 1.0, poses[:, 2:3]], 1).astype(np.float32)
+        pl.collide_edges_dev(torch.from_numpy(e).cuda())
+    pl.sync()
+    pl.footprint_points(1.0, 2.0, 0.3)
+    s = pl.sample_poses_dev(1, 2, 3, 4097, -5, 5, -5, 5)
+    pl.nearest_dev(s[:3000, :2].contiguous(), s[3000:, :2].contiguous())
+    keys = torch.randn(1000, 6, dtype=torch.float64, device="cuda")
+    pl.find_exact_dev(keys, keys[::7].contiguous())
+    pl.plan(make_query(6.0, 0.5, start_speed=1.0))
+    pl.plan_batch([make_query(5.0 + k * 0.1, 0.3, start_speed=1.0) for k in range(5)], want_nodes=True)
+    pl.rrt_plan(make_query(8.0, 3.0, start_speed=1.0, seed=5))
+    pl.rrt_plan_batch([make_query(8.0, 3.0, start_speed=1.0, seed=5, query_id=k) for k in range(3)])
+    pl.sync()
+    pl.close()
+print("sanitize pass done")

@@ -154,3 +154,20 @@ def test_config1_road_world_query(oracle, cuda_device, mode):
         _assert_same(got, ref)
     assert ref.n_collisions > 0 or mode == PP_COLLISION_AS_SHIPPED
     pl.close()
+
+
+def test_visited_debug_bitmap(oracle, cuda_device):
+    """markVisited (LP:318-326, row A12): one mark per child returned by getNeighbors."""
+    from autonomouscar_b200 import Planner
+    p = default_params(collision_mode=PP_COLLISION_REF_AABB, max_nodes=4000)
+    grid = np.zeros((300, 300), dtype=np.int8)
+    grid[150 - 6:150 + 40, 150 - 34:150 - 30] = 100
+    pl = Planner(p, device=0)
+    pl.set_grid(grid)
+    q = make_query(16.0, 0.0, start_speed=1.0)
+    pl.plan(q)
+    ref = oracle.plan(p, grid, q, math_mode=oracle.MATH_DET, want_visited=True)
+    got = pl.get_visited()
+    assert ref.visited.sum() > 10
+    np.testing.assert_array_equal(got, ref.visited)
+    pl.close()
