@@ -34,79 +34,111 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
     flags[k] = 0;
 }
 
-// Fused broad + narrow: each warp takes 32 consecutive poses; the lanes set them up in
-// parallel (fixed-point lattice, bounding box, tile / 8x8-block occupancy), then the warp
-// walks the survivors: stage window -> exact box test -> lattice.
-//   NU == 0 selects the run-time lattice shape.
+// One launch resolves a whole batch.  A CTA takes 1024 consecutive poses at a time and runs
+// three phases, each with dense lanes (survivors are compacted through shared memory):
+//   1. thread per pose : one bit of the dilated 8x8 map ("any obstacle within reach of this
+//                        block, for any yaw") decides ~70 % of the poses; their flag is 0
+//   2. thread per survivor : fp64 fixed-point lattice set-up, bounding box, tile / 8x8-block
+//                        occupancy under the box -> NarrowJob or flag 0
+//   3. warp per job    : stage the occupied tiles under the box (one 128 B line each), exact
+//                        box test on the staged window, then the sample lattice
+//   NU == 0 selects the run-time lattice shape.  broad_phase == 0 ("direct") disables every
+//   pruning test: each pose that overlaps the grid runs the full lattice.
+constexpr int kPosesPerThread = 4;
+constexpr int kChunk = kThreads * kPosesPerThread;
+
+__device__ __forceinline__ int warp_append(int* counter, bool pred, int lane) {
+  const unsigned bal = __ballot_sync(0xffffffffu, pred);
+  int base = 0;
+  if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + __popc(bal & ((1u << lane) - 1u));
+}
+
 template <int NU, int NV, int S>
 __global__ void __launch_bounds__(kThreads)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
                         int64_t n, int broad_phase, unsigned long long* __restrict__ narrow_counter) {
-  __shared__ uint32_t smem[kWarpsPerBlock][kWinWords];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warp = blockIdx.x * static_cast<int64_t>(kWarpsPerBlock) + wib;
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
-  const int64_t n_groups = (n + 31) >> 5;
-  uint32_t* sm = smem[wib];
-  unsigned long long local_narrow = 0;
+  __shared__ uint32_t s_win[kWarpsPerBlock][kWinWords];
+  __shared__ int s_queue[kChunk];
+  __shared__ NarrowJob s_jobs[kThreads];
+  __shared__ int s_job_off[kThreads];
+  __shared__ int s_nq, s_nj;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const float inv_res_f = static_cast<float>(1.0 / g.res);
-  // half diagonal of the footprint in cells, + 1 cell for the floor, + 2 cells of float slack
-  const int reach = static_cast<int>(sqrt(lat.su * lat.hu * lat.su * lat.hu + lat.sv * lat.hv * lat.sv * lat.hv)) + 4;
-  for (int64_t grp = warp; grp < n_groups; grp += n_warps) {
-    const int64_t k = grp * 32 + lane;
-    NarrowJob job;
-    bool need = false;
-    if (k < n) {
-      const float x = poses[3 * k], y = poses[3 * k + 1], yaw = poses[3 * k + 2];
-      // cheapest test first: no 8x8 block with an obstacle inside the square that bounds the
-      // footprint for ANY yaw (float arithmetic + 2 cells of slack: conservative, never decisive
-      // for a colliding pose).  Only survivors pay for the fp64 lattice set-up.
-      bool maybe = true;
-      if (broad_phase) {
-        const float cif = static_cast<float>(g.W / 2) - y * inv_res_f;
-        const float cjf = static_cast<float>(g.H / 2) - x * inv_res_f;
-        if (fabsf(cif) < 1.0e6f && fabsf(cjf) < 1.0e6f) {
-          const int ic = __float2int_rd(cif), jc = __float2int_rd(cjf);
-          const int i0 = ic - reach, i1 = ic + reach, j0 = jc - reach, j1 = jc + reach;
-          if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) maybe = false;
-          else maybe = coarse_square_any(g, max(i0, -kHaloCells), min(i1, g.W + kHaloCells - 1),
-                                         max(j0, -kHaloCells), min(j1, g.H + kHaloCells - 1));
+  const int reach = g.reach_cells;
+  unsigned long long local_narrow = 0;
+  const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t base = chunk * kChunk;
+    if (tid == 0) s_nq = 0;
+    __syncthreads();
+    // ---- phase 1 ------------------------------------------------------------------------
+#pragma unroll
+    for (int p = 0; p < kPosesPerThread; ++p) {
+      const int off = p * kThreads + tid;
+      const int64_t k = base + off;
+      bool survive = false;
+      if (k < n) {
+        survive = true;
+        if (broad_phase) {
+          const float x = poses[3 * k], y = poses[3 * k + 1];
+          const float cif = static_cast<float>(g.W / 2) - y * inv_res_f;
+          const float cjf = static_cast<float>(g.H / 2) - x * inv_res_f;
+          if (fabsf(cif) < 1.0e6f && fabsf(cjf) < 1.0e6f) {   // (NaN / absurd poses take the exact path)
+            const int ic = __float2int_rd(cif), jc = __float2int_rd(cjf);
+            if (ic + reach < 0 || ic - reach >= g.W || jc + reach < 0 || jc - reach >= g.H) {
+              survive = false;                               // the footprint cannot reach the grid
+            } else {
+              const int r8 = (ic + kHaloCells) >> 3, c8 = (jc + kHaloCells) >> 3;
+              survive = (__ldg(&g.near8[static_cast<size_t>(r8) * g.CW8 + (c8 >> 6)]) >> (c8 & 63)) & 1ull;
+            }
+          }
         }
+        if (!survive) flags[k] = 0;
       }
-      if (maybe) {
-        const PoseFx p = pose_to_fixed(lat, g.W, g.H, g.res, static_cast<double>(x), static_cast<double>(y),
-                                       static_cast<double>(yaw));
-        need = make_job(g, lat, p, broad_phase, &job);
-      }
+      const int slot = warp_append(&s_nq, survive, lane);
+      if (survive) s_queue[slot] = off;
     }
-    uint32_t todo = __ballot_sync(0xffffffffu, need);
-    local_narrow += __popc(todo);
-    bool my_hit = false;
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      NarrowJob j;
-      j.oi = __shfl_sync(0xffffffffu, job.oi, src);
-      j.oj = __shfl_sync(0xffffffffu, job.oj, src);
-      j.ui = __shfl_sync(0xffffffffu, job.ui, src);
-      j.uj = __shfl_sync(0xffffffffu, job.uj, src);
-      j.vi = __shfl_sync(0xffffffffu, job.vi, src);
-      j.vj = __shfl_sync(0xffffffffu, job.vj, src);
-      j.tiles = __shfl_sync(0xffffffffu, job.tiles, src);
-      j.box = __shfl_sync(0xffffffffu, job.box, src);
-      j.occ = __shfl_sync(0xffffffffu, job.occ, src);
-      stage_window(g, j, sm, lane);
-      bool hit = false;
-      if (!broad_phase || window_box_any(j, sm, lane)) {
-        if (NU > 0) hit = lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(j, sm, lane);
-        else hit = lattice_any_generic(lat, j, sm, lane);
+    __syncthreads();
+    const int nq = s_nq;
+    // ---- phases 2 + 3, 256 survivors at a time ------------------------------------------------
+    for (int q0 = 0; q0 < nq; q0 += kThreads) {
+      if (tid == 0) s_nj = 0;
+      __syncthreads();
+      const int qi = q0 + tid;
+      NarrowJob job;
+      bool need = false;
+      int off = 0;
+      if (qi < nq) {
+        off = s_queue[qi];
+        const int64_t k = base + off;
+        const float x = poses[3 * k], y = poses[3 * k + 1], yaw = poses[3 * k + 2];
+        const PoseFx px = pose_to_fixed(lat, g.W, g.H, g.res, static_cast<double>(x), static_cast<double>(y),
+                                        static_cast<double>(yaw));
+        need = make_job(g, lat, px, broad_phase, &job);
+        if (!need) flags[k] = 0;
       }
-      __syncwarp();
-      if (lane == src) my_hit = hit;
+      const int slot = warp_append(&s_nj, need, lane);
+      if (need) { s_jobs[slot] = job; s_job_off[slot] = off; }
+      __syncthreads();
+      const int nj = s_nj;
+      if (tid == 0) local_narrow += nj;
+      for (int j = wib; j < nj; j += kWarpsPerBlock) {
+        const NarrowJob jb = s_jobs[j];
+        stage_window(g, jb, s_win[wib], lane);
+        bool hit = false;
+        if (!broad_phase || window_box_any(jb, s_win[wib], lane)) {
+          if (NU > 0) hit = lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, s_win[wib], lane);
+          else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
+        }
+        __syncwarp();
+        if (lane == 0) flags[base + s_job_off[j]] = hit ? 1 : 0;
+      }
+      __syncthreads();
     }
-    if (k < n) flags[k] = my_hit ? 1 : 0;
   }
-  if (lane == 0 && narrow_counter && local_narrow) atomicAdd(narrow_counter, local_narrow);
+  if (tid == 0 && narrow_counter && local_narrow) atomicAdd(narrow_counter, local_narrow);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -157,7 +189,7 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
   } else if (mode == PP_COLLISION_REF_AABB) {
     collide_aabb_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, s>>>(h->grid, poses, flags, n);
   } else {
-    const int blocks = grid_blocks(h, (n + 31) / 32, kWarpsPerBlock, 8);
+    const int blocks = grid_blocks(h, n, kChunk, 8);
     if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
       collide_oriented_kernel<48, 17, 2><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
     else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells

@@ -59,6 +59,10 @@ struct GridDev {
   //   coarse[ci8 * CW8 + (cj8 >> 6)] bit (cj8 & 63), ci8 = (i + halo) >> 3, cj8 = (j + halo) >> 3
   unsigned long long* coarse;
   int CI8, CW8;
+  // `coarse` dilated by `reach8` blocks in every direction: bit set <=> some obstacle cell lies
+  // within the yaw-independent square that bounds the footprint around a pose in that block
+  unsigned long long* near8;
+  int reach_cells;          // half side of that square, in cells (footprint half diagonal + slack)
   // REF_AABB box-dilated map over base cells [-aabb_pad_x, W+aabb_pad_x) x [-aabb_pad_y, H+...)
   //   aabb_map[(bx+pad_x) * aabb_stride + (by+pad_y)] = 1 iff the LP:477-495 box anchored at
   //   (bx,by) contains a cell == 100

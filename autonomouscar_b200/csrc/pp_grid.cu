@@ -84,6 +84,28 @@ __global__ void build_coarse(const uint32_t* __restrict__ tiles, unsigned long l
   }
 }
 
+// near8 = coarse dilated by r8 blocks (square structuring element), one thread per 64-bit word
+__global__ void dilate_coarse(const unsigned long long* __restrict__ coarse, unsigned long long* __restrict__ near8,
+                              int CI8, int CW8, int r8) {
+  const int64_t total = static_cast<int64_t>(CI8) * CW8;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(k % CW8), r = static_cast<int>(k / CW8);
+    unsigned long long acc = 0;
+    for (int rr = max(r - r8, 0); rr <= min(r + r8, CI8 - 1); ++rr) {
+      const unsigned long long* row = coarse + static_cast<size_t>(rr) * CW8;
+      const unsigned long long c = row[w], l = w > 0 ? row[w - 1] : 0ull, h = w + 1 < CW8 ? row[w + 1] : 0ull;
+      unsigned long long d = c;
+      for (int sft = 1; sft <= r8; ++sft) {        // r8 < 64
+        d |= (c << sft) | (l >> (64 - sft));       // bits moving up from lower columns
+        d |= (c >> sft) | (h << (64 - sft));       // bits moving down from higher columns
+      }
+      acc |= d;
+    }
+    near8[k] = acc;
+  }
+}
+
 // REF_AABB dilation, pass 1: rows[x][my] = OR over y in [ylo[my], yhi[my]) of (cspace[x][y]==100)
 __global__ void aabb_pass_y(const int8_t* __restrict__ cspace, uint8_t* __restrict__ rows, int W, int H, int ny,
                             const int* __restrict__ ylo, const int* __restrict__ yhi) {
@@ -141,6 +163,7 @@ void grid_free(pp_handle* h) {
   cudaFree(g.occ_tiles);
   cudaFree(g.tile_any);
   cudaFree(g.coarse);
+  cudaFree(g.near8);
   cudaFree(g.aabb_map);
   g = GridDev{};
   h->has_grid = false;
@@ -165,6 +188,12 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
     g.CI8 = g.TI * 4;
     g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
     PP_CUDA(cudaMalloc(&g.coarse, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
+    PP_CUDA(cudaMalloc(&g.near8, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
+    {
+      // half diagonal of the footprint in cells + 1 (floor) + 2 (float slack of the pre-test)
+      const double du = h->lat.su * h->lat.hu, dv = h->lat.sv * h->lat.hv;
+      g.reach_cells = static_cast<int>(std::sqrt(du * du + dv * dv)) + 4;
+    }
     PP_CUDA(cudaMalloc(&g.aabb_map, static_cast<size_t>(g.aabb_nx) * g.aabb_ny));
     // scratch: message copy (cells) + pass-1 rows (W * ny) + 4 interval tables
     h->scratch_bytes = cells + static_cast<size_t>(W) * g.aabb_ny + sizeof(int) * 2 * (g.aabb_nx + g.aabb_ny) + 256;
@@ -206,7 +235,8 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
   reduce_tile_any<<<blocks_for(n_tiles * 32, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.tile_any, n_tiles);
   PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8, s));
   build_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.TJ, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.coarse, g.TI, g.TJ, g.CW8);
-  h->launches++;
+  dilate_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.CW8, T, h->sm_count), T, 0, s>>>(g.coarse, g.near8, g.CI8, g.CW8, (g.reach_cells + 7) / 8);
+  h->launches += 2;
   aabb_pass_y<<<blocks_for(static_cast<int64_t>(W) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(g.cspace, rows, W, H, g.aabb_ny, ylo, yhi);
   aabb_pass_x<<<blocks_for(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(rows, g.aabb_map, W, g.aabb_nx, g.aabb_ny, xlo, xhi);
   h->launches += 4;

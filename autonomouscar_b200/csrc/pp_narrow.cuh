@@ -87,6 +87,7 @@ constexpr int kWinWords = 3 * 96;
 
 __device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& job, uint32_t* sm, int lane) {
   const int t0i = job.tiles >> 16, t0j = job.tiles & 0xffff;
+  // all nine (predicated) loads are issued back to back: one exposed L2 latency per pose
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
 #pragma unroll
