@@ -119,6 +119,7 @@ int pp_create(const pp_params* params, int device, pp_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   PP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   PP_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  PP_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) PP_CUDA(cudaEventCreate(&ev));
   PP_CUDA(cudaMalloc(&h->d_count, 64));
   PP_CUDA(cudaMemset(h->d_count, 0, 64));
@@ -145,6 +146,9 @@ int pp_destroy(pp_handle* h) {
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->out_stream) cudaStreamDestroy(h->out_stream);
+  for (int k = 0; k < h->chunk_ev_n; ++k) cudaEventDestroy(h->chunk_ev[k]);
+  delete[] h->chunk_ev;
   delete h;
   return PP_OK;
 }
@@ -219,36 +223,44 @@ int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* 
   if (rc) return rc;
   const int64_t chunk = 1 << 20;
   const int64_t n_chunks = (n + chunk - 1) / chunk;
-  cudaStream_t cs = h->copy_stream, ks = h->stream;
-  // all H2D copies are queued on the copy stream; the compute stream waits chunk by chunk,
-  // and the D2H of chunk c is queued behind the H2D of chunk c+1, so both directions of the
-  // link stay busy while the kernels run
-  PP_CUDA(cudaEventRecord(h->ev[0], cs));
+  cudaStream_t in = h->copy_stream, ks = h->stream, out = h->out_stream;
+  if (2 * n_chunks > h->chunk_ev_n) {
+    for (int k = 0; k < h->chunk_ev_n; ++k) cudaEventDestroy(h->chunk_ev[k]);
+    delete[] h->chunk_ev;
+    h->chunk_ev_n = static_cast<int>(2 * n_chunks);
+    h->chunk_ev = new cudaEvent_t[h->chunk_ev_n];
+    for (int k = 0; k < h->chunk_ev_n; ++k) PP_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
+  }
+  // three streams, one per engine: uploads never wait for kernels or downloads, the kernel of
+  // chunk c waits only for its own upload, the download of chunk c only for its own kernel
+  PP_CUDA(cudaEventRecord(h->ev[0], in));
   rc = collide_counter_reset(h);
   if (rc) return rc;
   PP_CUDA(cudaEventRecord(h->ev[2], ks));
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int64_t lo = c * chunk, m = (lo + chunk <= n) ? chunk : n - lo;
+    cudaEvent_t up = h->chunk_ev[2 * c], done = h->chunk_ev[2 * c + 1];
     PP_CUDA(cudaMemcpyAsync(h->d_poses + 3 * lo, poses_host + 3 * lo, static_cast<size_t>(m) * 3 * sizeof(float),
-                            cudaMemcpyHostToDevice, cs));
-    PP_CUDA(cudaEventRecord(h->ev[4 + (c & 1)], cs));
-    PP_CUDA(cudaStreamWaitEvent(ks, h->ev[4 + (c & 1)], 0));
+                            cudaMemcpyHostToDevice, in));
+    PP_CUDA(cudaEventRecord(up, in));
+    PP_CUDA(cudaStreamWaitEvent(ks, up, 0));
     rc = collide_launch(h, m, h->d_poses + 3 * lo, h->d_flags + lo);
     if (rc) return rc;
-    PP_CUDA(cudaEventRecord(h->ev[6 + (c & 1)], ks));
-    PP_CUDA(cudaStreamWaitEvent(cs, h->ev[6 + (c & 1)], 0));
-    PP_CUDA(cudaMemcpyAsync(out_flags_host + lo, h->d_flags + lo, static_cast<size_t>(m), cudaMemcpyDeviceToHost, cs));
+    PP_CUDA(cudaEventRecord(done, ks));
+    PP_CUDA(cudaStreamWaitEvent(out, done, 0));
+    PP_CUDA(cudaMemcpyAsync(out_flags_host + lo, h->d_flags + lo, static_cast<size_t>(m), cudaMemcpyDeviceToHost, out));
   }
   PP_CUDA(cudaEventRecord(h->ev[3], ks));
   rc = collide_counter_fetch(h);
   if (rc) return rc;
-  PP_CUDA(cudaEventRecord(h->ev[1], cs));
-  PP_CUDA(cudaStreamSynchronize(cs));
+  PP_CUDA(cudaEventRecord(h->ev[1], out));
+  PP_CUDA(cudaStreamSynchronize(in));
   PP_CUDA(cudaStreamSynchronize(ks));
+  PP_CUDA(cudaStreamSynchronize(out));
   if (h->P.collision_mode != PP_COLLISION_ORIENTED) h->last_narrow = n;
   float ms = 0;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-  h->phase_ms[PP_PHASE_H2D] = ms;  // the whole pipelined call as seen by the copy stream
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->phase_ms[PP_PHASE_H2D] = ms;
+  else cudaGetLastError();
   return PP_OK;
 }
 
@@ -350,6 +362,7 @@ int pp_sync(pp_handle* h) {
   PP_CUDA(cudaSetDevice(h->device));
   PP_CUDA(cudaStreamSynchronize(h->stream));
   PP_CUDA(cudaStreamSynchronize(h->copy_stream));
+  PP_CUDA(cudaStreamSynchronize(h->out_stream));
   return PP_OK;
 }
 int pp_stream(pp_handle* h, void** out_stream) {

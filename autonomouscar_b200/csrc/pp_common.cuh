@@ -209,7 +209,10 @@ struct pp_handle {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;      // compute
-  cudaStream_t copy_stream = nullptr; // H2D / D2H of the host-pointer entry points
+  cudaStream_t copy_stream = nullptr; // H2D of the host-pointer entry points
+  cudaStream_t out_stream = nullptr;  // D2H of the host-pointer entry points
+  cudaEvent_t* chunk_ev = nullptr;    // 2 events per pipeline chunk (uploaded / computed)
+  int chunk_ev_n = 0;
   cudaEvent_t ev[16] = {};
   pp::Lattice lat{};
   pp::GridDev grid{};
