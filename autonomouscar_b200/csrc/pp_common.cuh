@@ -133,6 +133,22 @@ __device__ __forceinline__ uint32_t occ_word(const GridDev& g, int i, int jw_til
   return __ldg(&g.occ_tiles[(static_cast<size_t>(ih >> 5) * g.TJ + jw_tile) * kTile + (ih & 31)]);
 }
 
+// 8x8-cell coarse occupancy under the cell box [i0,i1] x [j0,j1] (<= 8 x 8 coarse cells)
+__device__ __forceinline__ bool coarse_box_any(const GridDev& g, int i0, int i1, int j0, int j1) {
+  const int r0 = (i0 + kHaloCells) >> 3, r1 = (i1 + kHaloCells) >> 3;
+  const int c0 = (j0 + kHaloCells) >> 3, c1 = (j1 + kHaloCells) >> 3;
+  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 8 bits starting at bit c0
+  const unsigned long long m = ((1ull << nb) - 1ull);
+  unsigned long long any = 0;
+  for (int r = r0; r <= r1; ++r) {
+    const unsigned long long* row = g.coarse + static_cast<size_t>(r) * g.CW8 + w0;
+    unsigned long long bits = __ldg(row) >> sh;
+    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
+    any |= bits & m;
+  }
+  return any != 0;
+}
+
 // ORIENTED, one thread evaluating the whole lattice straight from the tiled bitmap.
 // Used where poses are few and latency-bound (planner candidates, edge steps); the batch
 // path uses the warp-cooperative kernel in pp_collide.cu.
@@ -141,6 +157,17 @@ __device__ __forceinline__ bool oriented_hit_thread(const GridDev& g, const Latt
   int i0, i1, j0, j1;
   lattice_bbox(l, p, &i0, &i1, &j0, &j1);
   if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return false;
+  // exact conservative pruning first (same tests as the batch kernel's broad phase): no obstacle
+  // in the tiles / 8x8 blocks under the bounding box means no sample can hit one
+  {
+    const int t0i = (i0 + kHaloCells) >> 5, t1i = (i1 + kHaloCells) >> 5;
+    const int t0j = (j0 + kHaloCells) >> 5, t1j = (j1 + kHaloCells) >> 5;
+    uint32_t any = 0;
+    for (int a = t0i; a <= t1i; ++a)
+      for (int b = t0j; b <= t1j; ++b) any |= __ldg(&g.tile_any[static_cast<size_t>(a) * g.TJ + b]);
+    if (!any) return false;
+    if (!coarse_box_any(g, i0, i1, j0, j1)) return false;
+  }
   // all loads of four lattice columns are independent (no early exit in between), so they
   // overlap in the memory pipeline; the exit test runs once per four columns
   uint32_t hit = 0;

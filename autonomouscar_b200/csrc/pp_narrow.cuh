@@ -20,22 +20,6 @@ struct NarrowJob {
   uint32_t occ;     // bit (a*3+b): tile (t0i+a, t0j+b) is under the box AND holds an obstacle
 };
 
-// 8x8-cell coarse occupancy under the cell box [i0,i1] x [j0,j1] (<= 8 x 8 coarse cells)
-__device__ __forceinline__ bool coarse_box_any(const GridDev& g, int i0, int i1, int j0, int j1) {
-  const int r0 = (i0 + kHaloCells) >> 3, r1 = (i1 + kHaloCells) >> 3;
-  const int c0 = (j0 + kHaloCells) >> 3, c1 = (j1 + kHaloCells) >> 3;
-  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 8 bits starting at bit c0
-  const unsigned long long m = ((1ull << nb) - 1ull);
-  unsigned long long any = 0;
-  for (int r = r0; r <= r1; ++r) {
-    const unsigned long long* row = g.coarse + static_cast<size_t>(r) * g.CW8 + w0;
-    unsigned long long bits = __ldg(row) >> sh;
-    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
-    any |= bits & m;
-  }
-  return any != 0;
-}
-
 // same for a wider square (the yaw-independent bound): up to 64 coarse cells wide
 __device__ __forceinline__ bool coarse_square_any(const GridDev& g, int i0, int i1, int j0, int j1) {
   const int r0 = (i0 + kHaloCells) >> 3, r1 = (i1 + kHaloCells) >> 3;

@@ -44,6 +44,8 @@ constexpr int kIntMax = 0x7fffffff;
 struct PlanHdr {                   // per query, device -> host
   int status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions;
   int truncated;                   // a caller-visible array was too small
+  int reran;                       // 1 if a cost tie forced the exact-heap re-run
+  int pad_;
   unsigned long long digest;
   long long cyc[8];                // SM cycles per phase (thread 0): init, close, eval, commit, push, close2, extract, total
 };
@@ -61,6 +63,7 @@ struct PlanArgs {
   int want_path_ids;
   int cap_path, cap_exp;
   int timing;             // accumulate per-phase SM cycles (PP_PLAN_TIMING=1)
+  int fast_frontier;      // 1: try the unordered-array frontier first (exact; falls back on cost ties)
   size_t ws_stride;       // bytes
   unsigned char* ws_base;
   PlanHdr* hdr;
@@ -81,6 +84,7 @@ struct WS {
   int* closed_seq;
   int* heap_id_g;
   int* closed_list;           // slot id by closing order (m_tree_closed)
+  int* rev_last;              // path extraction scratch
 };
 
 __host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
@@ -89,7 +93,7 @@ __host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
   b += sizeof(unsigned long long) * NC;
   b += sizeof(unsigned long long) * hash_size;
   b += sizeof(double) * 2 * NC;       // global heap entries (16 B each); reused to stage the reversed path
-  b += sizeof(int) * NC * 3;          // closed_seq, spare, closed_list
+  b += sizeof(int) * NC * 4;          // closed_seq, path scratch, closed_list, path scratch
   return (b + 255) & ~size_t(255);
 }
 
@@ -104,6 +108,7 @@ __device__ __forceinline__ WS ws_view(unsigned char* base, int NC, int hash_size
   w.closed_seq = reinterpret_cast<int*>(w.heap_cost_g + 2 * NC);
   w.heap_id_g = w.closed_seq + NC;
   w.closed_list = w.heap_id_g + NC;
+  w.rev_last = w.closed_list + NC;
   return w;
 }
 
@@ -282,6 +287,9 @@ struct Shared {
   int n_nodes, n_closed, heap_size, n_exp, status, dup_seen, cur_id, n_vel, n_yaw, n_cand_total, n_coll_total;
   int goal_hit, path_len, truncated, done;
   int q;
+  int fast;        // frontier mode of this attempt: 1 = unordered array + block argmin, 0 = exact binary heap
+  int tie_seen;    // fast mode: some pop saw its minimum cost on more than one entry
+  int top_pos, top_id;
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
   double scratch_key[6];  // key broadcast for the exact-scan fallback
   long long cyc[8];
@@ -345,12 +353,68 @@ __device__ __forceinline__ void hash_insert(const WS& w, int hash_size, unsigned
   }
 }
 
-// openNode (LP:98-102) for one node by thread 0 + heap push by warp 0.  Called by warp 0 only.
+// ---------------------------------------------------------------------------------------
+// Fast frontier.  The order in which a priority queue returns its elements does not depend
+// on its internal layout as long as every pop has a UNIQUE minimum.  The fast mode therefore
+// keeps the frontier as an unordered array (pushes are plain parallel appends) and pops by a
+// block-wide argmin; if any pop ever sees its minimum cost on two entries the query is
+// re-run from scratch with the exact libstdc++ heap, so results are always the reference's.
+// ---------------------------------------------------------------------------------------
+template <bool kAllSmem>
+__device__ __forceinline__ void fast_find_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt) {
+  const int n = S->heap_size;
+  double bc = 0;
+  int bp = -1, cnt = 0;
+  for (int k = threadIdx.x; k < n; k += kT) {
+    const HeapEnt e = hget<kAllSmem>(h, k);
+    if (bp < 0 || e.cost < bc) { bc = e.cost; bp = k; cnt = 1; }
+    else if (e.cost == bc) cnt++;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    const int op = __shfl_xor_sync(0xffffffffu, bp, off), on = __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (op >= 0) {
+      if (bp < 0 || oc < bc) { bc = oc; bp = op; cnt = on; }
+      else if (oc == bc) { cnt += on; bp = min(bp, op); }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_cost[warp] = bc; s_pos[warp] = bp; s_cnt[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = s_cost[0];
+    int p = s_pos[0], m = s_cnt[0];
+    for (int w = 1; w < kWarps; ++w) {
+      const int op = s_pos[w];
+      if (op < 0) continue;
+      if (p < 0 || s_cost[w] < c) { c = s_cost[w]; p = op; m = s_cnt[w]; }
+      else if (s_cost[w] == c) { m += s_cnt[w]; p = min(p, op); }
+    }
+    S->top_pos = p;
+    S->top_id = hget<kAllSmem>(h, p).id;
+    if (m > 1) S->tie_seen = 1;
+  }
+  __syncthreads();
+}
+
+// frontier.top(): slot id of the cheapest entry (block-wide; all threads get the same value)
+template <bool kAllSmem>
+__device__ __forceinline__ int frontier_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt) {
+  if (S->fast) {
+    fast_find_top<kAllSmem>(h, S, s_cost, s_pos, s_cnt);
+    return S->top_id;
+  }
+  return h.s[0].id;
+}
+
+// openNode (LP:98-102) for one node by thread 0 + frontier push by warp 0.  Called by warp 0 only.
 template <bool kAllSmem>
 __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap, Shared* S, int hash_size,
                                                  const double k[6], double g, double cost, int lane) {
   const int id = S->n_nodes;
   const int hsize = S->heap_size;
+  const int fast = S->fast;
   __syncwarp();
   if (lane == 0) {
     w.cx[id] = k[0]; w.cy[id] = k[1]; w.px[id] = k[2]; w.py[id] = k[3]; w.hd[id] = k[4]; w.vel[id] = k[5];
@@ -360,18 +424,22 @@ __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap,
     w.fp[id] = fp;
     if (hash_contains(w, hash_size, fp)) S->dup_seen = 1;
     hash_insert(w, hash_size, fp);
+    if (fast) {
+      HeapEnt e;
+      e.cost = cost; e.id = id; e.pad = 0;
+      hset<kAllSmem>(heap, hsize, e);
+    }
   }
   __syncwarp();
-  heap_sift_up_warp<kAllSmem>(heap, hsize, cost, id, lane);
+  if (!fast) heap_sift_up_warp<kAllSmem>(heap, hsize, cost, id, lane);
   if (lane == 0) { S->n_nodes = id + 1; S->heap_size = hsize + 1; }
   __syncwarp();
 }
 
-// closeNode (LP:104-113): find the first open slot equal to frontier.top(), move it to the
-// closed list, pop the frontier.  Block-wide; returns the closed slot id (or -1).
+// closeNode (LP:104-113): find the first open slot equal to frontier.top() (`top_id`), move it
+// to the closed list, pop the frontier.  Block-wide; returns the closed slot id (or -1).
 template <bool kAllSmem>
-__device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* S, int* s_red) {
-  const int top_id = heap.s[0].id;
+__device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* S, int top_id, int* s_red) {
   int target = top_id;
   if (S->dup_seen) {
     // equal keys may exist: reproduce std::find over m_tree_open (first equal, lowest id)
@@ -383,14 +451,23 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
   __syncthreads();
   if (threadIdx.x < 32) {
     const int hsize = S->heap_size;
+    const int fast = S->fast;
     __syncwarp();
     if (threadIdx.x == 0 && target >= 0) {
       w.closed_seq[target] = S->n_closed;
       w.closed_list[S->n_closed] = target;
       S->n_closed = S->n_closed + 1;
     }
-    const int nsize = heap_pop_warp<kAllSmem>(heap, hsize, threadIdx.x);
-    if (threadIdx.x == 0) S->heap_size = nsize;
+    if (fast) {
+      if (threadIdx.x == 0) {   // remove by moving the last entry into the hole
+        const int pos = S->top_pos;
+        if (pos != hsize - 1) hset<kAllSmem>(heap, pos, hget<kAllSmem>(heap, hsize - 1));
+        S->heap_size = hsize - 1;
+      }
+    } else {
+      const int nsize = heap_pop_warp<kAllSmem>(heap, hsize, threadIdx.x);
+      if (threadIdx.x == 0) S->heap_size = nsize;
+    }
   }
   __syncthreads();
   return target;
@@ -403,6 +480,8 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
   __shared__ int s_red[kWarpsMax];
   __shared__ int s_scan[kWarpsMax];
   __shared__ unsigned long long s_dig[kWarpsMax];
+  __shared__ double s_fcost[kWarpsMax];
+  __shared__ int s_fpos[kWarpsMax], s_fcnt[kWarpsMax];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pp_params& P = A.P;
@@ -427,8 +506,10 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
     Q.max_speed = qq.max_speed; Q.max_accel = qq.max_accel; Q.start_speed = qq.start_speed;
     int* exp_out = A.out_exp ? A.out_exp + static_cast<size_t>(q) * A.cap_exp : nullptr;
 
+    // attempt 0 runs with the fast frontier; a detected cost tie re-runs the query with the exact heap
     const long long t_begin = A.timing ? clock64() : 0;
     long long t_mark = t_begin;
+    for (int attempt = 0; attempt < 2; ++attempt) {
 #define PP_TICK(slot) do { if (A.timing && tid == 0) { const long long now_ = clock64(); S.cyc[slot] += now_ - t_mark; t_mark = now_; } } while (0)
     // ---- initializePlanner (LP:84-96) ------------------------------------------------
     {
@@ -438,6 +519,8 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
     if (tid == 0) {
       S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
       S.n_cand_total = 0; S.n_coll_total = 0; S.goal_hit = 0; S.path_len = 0; S.truncated = 0; S.done = 0;
+      S.fast = (attempt == 0 && A.fast_frontier) ? 1 : 0;
+      S.tie_seen = 0; S.top_pos = 0; S.top_id = 0;
       for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
     }
     __syncthreads();
@@ -453,12 +536,12 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       // caps replace the ros::Time guard of LP:33-39
       if (S.n_exp >= P.max_expansions || S.n_nodes >= P.max_nodes) { if (tid == 0) S.status = PP_PLAN_CAP; break; }
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }  // top() of an empty queue
-      const int top_id = heap.s[0].id;                                                // LP:40
+      const int top_id = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt);  // LP:40
       // current_node's fields are key fields, identical for every copy of the node
       const double ncx = w.cx[top_id], ncy = w.cy[top_id], npx = w.px[top_id], npy = w.py[top_id];
       const double nhd = w.hd[top_id], nvel = w.vel[top_id];
       __syncthreads();
-      const int closed_id = close_top<kAllSmem>(w, heap, &S, s_red);                            // LP:41
+      const int closed_id = close_top<kAllSmem>(w, heap, &S, top_id, s_red);                    // LP:41
       PP_TICK(1);
       if (tid == 0) {
         if (exp_out && S.n_exp < A.cap_exp) exp_out[S.n_exp] = closed_id;
@@ -490,6 +573,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       if (n_vel > kMaxVel || static_cast<long long>(n_vel) * n_yaw + S.n_nodes + 2 > A.NC) unsupported = true;
       const int n_cand = unsupported ? 0 : n_vel * n_yaw;
       const int base_nodes = S.n_nodes;
+      const int hs_base = S.heap_size;
       int appended = 0;  // block-uniform running count
       int collided_local = 0;
       bool goal_stop = false;
@@ -625,6 +709,11 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
           w.closed_seq[id] = -1;
           w.fp[id] = fp;
           hash_insert(w, A.hash_size, fp);
+          if (S.fast) {   // openNode's frontier push: a plain append, position = heap size + rank
+            HeapEnt e;
+            e.cost = cost; e.id = id; e.pad = 0;
+            hset<kAllSmem>(heap, hs_base + rank, e);
+          }
         }
         appended += total;
         __syncthreads();
@@ -646,6 +735,8 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       // costs are fetched 32 at a time (one L2 round trip) and handed out by shuffle.
       if (warp == 0) {
         int hsize = S.heap_size;
+        if (S.fast) hsize += appended;
+        else
         for (int r0 = 0; r0 < appended; r0 += 32) {
           const int mine = r0 + lane;
           const double my_cost = mine < appended ? w.cost[base_nodes + mine] : 0.0;
@@ -666,10 +757,21 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       __syncthreads();
       PP_TICK(4);
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }
-      close_top<kAllSmem>(w, heap, &S, s_red);                                                  // LP:80
+      {
+        const int top2 = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt);
+        __syncthreads();
+        close_top<kAllSmem>(w, heap, &S, top2, s_red);                                          // LP:80
+      }
       PP_TICK(5);
     }
     __syncthreads();
+    if (!(S.fast && S.tie_seen)) break;   // the fast attempt is exact unless a pop saw a tied minimum
+    if (A.visited) {                      // the re-run starts from a clean debug bitmap
+      const size_t cells = static_cast<size_t>(A.g.W) * A.g.H;
+      for (size_t c = tid; c < cells; c += kT) A.visited[c] = 0;
+    }
+    __syncthreads();
+    }  // attempt
 
     PP_TICK(7);
     // ---- outputs -----------------------------------------------------------------------
@@ -679,12 +781,17 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
     double* prof = A.out_profile + static_cast<size_t>(q) * A.cap_path * 3;
     int n_path = 0, n_profile = 0;
     if (S.status == PP_PLAN_FOUND) {
-      // calcPathMsg (LP:503-527): the walk is sequential, each link search is block-parallel.
-      // The reversed path is staged in the (now idle) heap-cost array of this workspace.
-      double* rev = w.heap_cost_g;  // 2*NC doubles: room for NC points
+      // calcPathMsg (LP:503-527) and calcMPMessage (LP:542-583).  The walk is sequential; each
+      // link search is ONE block-wide pass over the child points that yields three reductions:
+      //   - first match at or after the scan position   (the link the reference follows)
+      //   - first match overall                         (path_node_ids: LP:511-526 rule)
+      //   - last match overall                          (the node calcMPMessage ends up with)
+      // The frontier is dead now: its shared memory holds a copy of every child point, the
+      // reversed path is staged in the workspace's frontier area.
+      double* rev = w.heap_cost_g;   // 2*NC doubles: room for NC points
+      int* rev_first = w.heap_id_g;  // slot of the first match per reversed pose
+      int* rev_last = w.rev_last;    // slot of the last match per reversed pose
       const int rev_cap = NC;
-      // the frontier is dead now: reuse its shared memory for a copy of every child point,
-      // so the link searches below scan shared memory instead of L2
       const double2* sxy = nullptr;
       if (n_nodes <= A.heap_smem_entries) {
         double2* dst = reinterpret_cast<double2*>(smem_raw);
@@ -692,26 +799,66 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
         sxy = dst;
       }
       __syncthreads();
+      // scan for child == (x, y): *k_from = min key >= from, *k_first = min key, *k_last = max key
+      auto scan3 = [&](double x, double y, int from, int* k_from, int* k_first, int* k_last) {
+        int bf = kIntMax, b0 = kIntMax, bl = -1;
+        for (int id = tid; id < n_nodes; id += kT) {
+          bool eq;
+          if (sxy) { const double2 c = sxy[id]; eq = c.x == x && c.y == y; }
+          else eq = w.cx[id] == x && w.cy[id] == y;
+          if (eq) {
+            const int cs = w.closed_seq[id];
+            const int key = cs < 0 ? id : n_nodes + cs;
+            b0 = min(b0, key);
+            bl = max(bl, key);
+            if (key >= from) bf = min(bf, key);
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          bf = min(bf, __shfl_xor_sync(0xffffffffu, bf, off));
+          b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, off));
+          bl = max(bl, __shfl_xor_sync(0xffffffffu, bl, off));
+        }
+        if (lane == 0) { s_red[warp] = bf; s_scan[warp] = b0; s_fpos[warp] = bl; }
+        __syncthreads();
+        bf = s_red[0]; b0 = s_scan[0]; bl = s_fpos[0];
+        for (int ww = 1; ww < kWarps; ++ww) { bf = min(bf, s_red[ww]); b0 = min(b0, s_scan[ww]); bl = max(bl, s_fpos[ww]); }
+        __syncthreads();
+        *k_from = bf; *k_first = b0; *k_last = bl;
+      };
       double cxp = S.goal_node[0], cyp = S.goal_node[1];
-      int len = 0;
-      if (tid == 0) { rev[0] = cxp; rev[1] = cyp; }
-      len = 1;
+      int len = 1;
+      if (tid == 0) { rev[0] = cxp; rev[1] = cyp; rev_first[0] = -1; rev_last[0] = -1; }
       bool broken = false;
       while (!(cxp == 0 && cyp == 0)) {               // LP:509 -- checked between passes only
         int pos = 0;
         bool progressed = false;
         for (;;) {
-          const int key = find_child_from(w, sxy, n_nodes, cxp, cyp, pos, s_red);
+          int key, kfirst, klast;
+          scan3(cxp, cyp, pos, &key, &kfirst, &klast);
+          if (tid == 0 && len - 1 < rev_cap) {          // ids of the pose currently being resolved
+            rev_first[len - 1] = kfirst == kIntMax ? -1 : slot_of_key(w, n_nodes, kfirst);
+            rev_last[len - 1] = klast < 0 ? -1 : slot_of_key(w, n_nodes, klast);
+          }
           if (key == kIntMax) break;                   // end of this pass over open + closed
           const int id = slot_of_key(w, n_nodes, key);
           cxp = w.px[id]; cyp = w.py[id];
-          if (len < rev_cap) { if (tid == 0) { rev[2 * len] = cxp; rev[2 * len + 1] = cyp; } }
+          if (len < rev_cap && tid == 0) { rev[2 * len] = cxp; rev[2 * len + 1] = cyp; rev_first[len] = -1; rev_last[len] = -1; }
           len++;
           progressed = true;
           pos = key + 1;
           if (len > n_nodes + 2) break;
         }
         if (!progressed || len > n_nodes + 2 || len >= rev_cap) { broken = true; break; }
+      }
+      if (!broken) {   // the terminal pose (0,0) has not been looked up by the walk if the last link closed a pass
+        int key, kfirst, klast;
+        scan3(cxp, cyp, 0, &key, &kfirst, &klast);
+        if (tid == 0) {
+          rev_first[len - 1] = kfirst == kIntMax ? -1 : slot_of_key(w, n_nodes, kfirst);
+          rev_last[len - 1] = klast < 0 ? -1 : slot_of_key(w, n_nodes, klast);
+        }
       }
       __syncthreads();
       if (broken) {
@@ -721,52 +868,25 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
         for (int k = tid; k < len && k < A.cap_path; k += kT) {   // LP:530-538: reversed
           path[2 * k] = rev[2 * (len - 1 - k)];
           path[2 * k + 1] = rev[2 * (len - 1 - k) + 1];
+          if (A.want_path_ids) path_ids[k] = rev_first[len - 1 - k];
         }
         if (len > A.cap_path && tid == 0) S.truncated = 1;
-        __syncthreads();
-        // calcMPMessage (LP:542-583): per consecutive pose pair, LAST match in list order;
-        // `else if` means a node matching the current pose never counts for the next pose
+        // calcMPMessage: pose pair (i, i+1).  current_node = LAST node whose child == pose i;
+        // next_node = LAST node whose child == pose i+1 -- but the reference's `else if` means a
+        // node equal to pose i never counts for pose i+1, so identical consecutive poses leave
+        // next_node at its default GraphNode(cur, next, 0, 0)
         n_profile = len >= 2 ? len - 2 : 0;
-        for (int i = warp; i < n_profile; i += kWarps) {
-          const double ax = rev[2 * (len - 1 - i)], ay = rev[2 * (len - 1 - i) + 1];
-          const double bx = rev[2 * (len - 2 - i)], by = rev[2 * (len - 2 - i) + 1];
-          int best_a = -1, best_b = -1, id_a = -1, id_b = -1;
-          for (int id = lane; id < n_nodes; id += 32) {
-            double ex, ey;
-            if (sxy) { const double2 c = sxy[id]; ex = c.x; ey = c.y; }
-            else { ex = w.cx[id]; ey = w.cy[id]; }
-            const bool ma = ex == ax && ey == ay, mb = ex == bx && ey == by;
-            if (ma || mb) {
-              const int cs = w.closed_seq[id];
-              const int key = cs < 0 ? id : n_nodes + cs;
-              if (ma) { if (key > best_a) { best_a = key; id_a = id; } }
-              else if (key > best_b) { best_b = key; id_b = id; }
-            }
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            const int oa = __shfl_xor_sync(0xffffffffu, best_a, off), oia = __shfl_xor_sync(0xffffffffu, id_a, off);
-            const int ob = __shfl_xor_sync(0xffffffffu, best_b, off), oib = __shfl_xor_sync(0xffffffffu, id_b, off);
-            if (oa > best_a) { best_a = oa; id_a = oia; }
-            if (ob > best_b) { best_b = ob; id_b = oib; }
-          }
-          if (lane == 0 && i < A.cap_path) {
-            const double cur_heading = id_a >= 0 ? w.hd[id_a] : 0.0;
-            const double next_heading = id_b >= 0 ? w.hd[id_b] : 0.0;
-            const double next_velocity = id_b >= 0 ? w.vel[id_b] : 0.0;
-            prof[i] = dm::div(dm::sub(next_heading, cur_heading), dm::div(P.time_step_ms, 1000.0));  // LP:576-577
-            prof[A.cap_path + i] = P.time_step_ms;                                                    // LP:578
-            prof[2 * A.cap_path + i] = next_velocity;                                                 // LP:579
-          }
-        }
-        __syncthreads();
-        if (A.want_path_ids) {
-          for (int k = 0; k < len && k < A.cap_path; ++k) {
-            const double x = rev[2 * (len - 1 - k)], y = rev[2 * (len - 1 - k) + 1];
-            const int key = find_child_from(w, sxy, n_nodes, x, y, 0, s_red);
-            const int id = key == kIntMax ? -1 : slot_of_key(w, n_nodes, key);
-            if (tid == 0) path_ids[k] = id;
-          }
+        for (int i = tid; i < n_profile && i < A.cap_path; i += kT) {
+          const int ra = len - 1 - i, rb = len - 2 - i;
+          const int id_a = rev_last[ra];
+          const bool same = rev[2 * ra] == rev[2 * rb] && rev[2 * ra + 1] == rev[2 * rb + 1];
+          const int id_b = same ? -1 : rev_last[rb];
+          const double cur_heading = id_a >= 0 ? w.hd[id_a] : 0.0;
+          const double next_heading = id_b >= 0 ? w.hd[id_b] : 0.0;
+          const double next_velocity = id_b >= 0 ? w.vel[id_b] : 0.0;
+          prof[i] = dm::div(dm::sub(next_heading, cur_heading), dm::div(P.time_step_ms, 1000.0));   // LP:576-577
+          prof[A.cap_path + i] = P.time_step_ms;                                                     // LP:578
+          prof[2 * A.cap_path + i] = next_velocity;                                                  // LP:579
         }
       }
     }
@@ -795,6 +915,8 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       hd.n_candidates = S.n_cand_total;
       hd.n_collisions = S.n_coll_total;
       hd.truncated = S.truncated;
+      hd.reran = (!S.fast && A.fast_frontier) ? 1 : 0;
+      hd.pad_ = 0;
       hd.digest = d;
       if (A.timing) { const long long now_ = clock64(); S.cyc[6] += now_ - t_mark; S.cyc[7] = now_ - t_begin; }
       for (int c = 0; c < 8; ++c) hd.cyc[c] = S.cyc[c];
@@ -973,6 +1095,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   A.cap_path = cap_path;
   A.cap_exp = cap_exp;
   A.timing = getenv("PP_PLAN_TIMING") ? 1 : 0;
+  A.fast_frontier = getenv("PP_PLAN_EXACT_HEAP") ? 0 : 1;
   A.ws_stride = stride;
   A.ws_base = W->ws;
   A.hdr = reinterpret_cast<PlanHdr*>(ob);
@@ -1017,6 +1140,9 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   if (getenv("PP_PLAN_TIMING")) {
     const char* names[8] = {"init", "close", "goal+eval", "commit", "push", "close2", "extract", "total"};
     for (int c = 0; c < 8; ++c) fprintf(stderr, "[pp_plan] query 0 %-10s %10lld cycles\n", names[c], hdr[0].cyc[c]);
+    int reruns = 0;
+    for (int k = 0; k < n; ++k) reruns += hdr[k].reran;
+    fprintf(stderr, "[pp_plan] exact-heap re-runs (cost ties): %d of %d queries\n", reruns, n);
   }
   const double* hpath = reinterpret_cast<const double*>(hb + hdr_b);
   const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + path_b);

@@ -171,3 +171,22 @@ def test_visited_debug_bitmap(oracle, cuda_device):
     assert ref.visited.sum() > 10
     np.testing.assert_array_equal(got, ref.visited)
     pl.close()
+
+
+def test_cost_ties_follow_libstdcpp_heap_order(oracle, cuda_device):
+    """Mirror-symmetric query with a yaw lattice that is exactly symmetric in binary floating
+    point (heading_diff = 2^-4, heading_res = 2^-7, goal straight ahead): children at +-yaw have
+    bit-identical costs, so the pop order depends on libstdc++'s push_heap / pop_heap layout
+    (local_planner.hpp:111).  The GPU's fast frontier must detect the tie and reproduce it."""
+    from autonomouscar_b200 import Planner
+    p = default_params(heading_diff=0.0625, heading_res=0.0078125, max_nodes=6000)
+    pl = Planner(p, device=0)
+    for q in (make_query(20.0, 0.0, start_speed=0.0), make_query(12.0, 0.0, start_speed=1.5)):
+        ref = oracle.plan(p, None, q, math_mode=oracle.MATH_DET)
+        st = ref.node_state
+        # there really are distinct nodes with bit-identical costs
+        costs = st[1:, 7]
+        assert len(np.unique(costs)) < len(costs)
+        got = pl.plan(q)
+        _assert_same(got, ref)
+    pl.close()
