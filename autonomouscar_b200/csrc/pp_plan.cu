@@ -46,6 +46,7 @@ struct PlanHdr {                   // per query, device -> host
   int truncated;                   // a caller-visible array was too small
   int reran;                       // 1 if a cost tie forced the exact-heap re-run
   int pad_;
+  long long pool_off;              // first slot of this query in the output pools
   unsigned long long digest;
   long long cyc[8];                // SM cycles per phase (thread 0): init, close, eval, commit, push, close2, extract, total
 };
@@ -67,9 +68,13 @@ struct PlanArgs {
   size_t ws_stride;       // bytes
   unsigned char* ws_base;
   PlanHdr* hdr;
-  double* out_path;       // [n][cap_path][2]
-  int* out_path_ids;      // [n][cap_path]
-  double* out_profile;    // [n][3][cap_path]
+  // path / profile outputs are packed: a query reserves min(n_path, cap_path) slots of the
+  // pools with one atomicAdd, so the host copies back only what was produced
+  double* out_path;       // pool [pool_cap][2]
+  int* out_path_ids;      // pool [pool_cap]
+  double* out_profile;    // 3 planes of [pool_cap]: yaw rates, durations, speeds
+  unsigned long long* pool_counter;
+  long long pool_cap;
   int* out_exp;           // [n][cap_exp] or null
   int* work_counter;
   uint8_t* visited;       // A12 debug bitmap (single-query plans only) or null
@@ -127,6 +132,10 @@ __device__ __forceinline__ unsigned long long key_fingerprint(const double k[6])
 #pragma unroll
   for (int i = 0; i < 6; ++i) h = mix64(h ^ dbits(__dadd_rn(k[i], 0.0)));
   return h | 1ull;  // 0 is the empty marker of the hash set
+}
+// 32-bit hash of a point for the extraction scans (== treats -0.0 and +0.0 as equal)
+__device__ __forceinline__ uint32_t point_hash32(double x, double y) {
+  return static_cast<uint32_t>(mix64(dbits(__dadd_rn(x, 0.0)) ^ mix64(dbits(__dadd_rn(y, 0.0)))) >> 32);
 }
 // tree digest term of pp_result.tree_digest (same as oracle/planner_ref.h node_digest)
 __device__ __forceinline__ unsigned long long node_digest(int id, const double k[6]) {
@@ -290,6 +299,7 @@ struct Shared {
   int fast;        // frontier mode of this attempt: 1 = unordered array + block argmin, 0 = exact binary heap
   int tie_seen;    // fast mode: some pop saw its minimum cost on more than one entry
   int top_pos, top_id;
+  long long pool_off;
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
   double scratch_key[6];  // key broadcast for the exact-scan fallback
   long long cyc[8];
@@ -776,9 +786,9 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
     PP_TICK(7);
     // ---- outputs -----------------------------------------------------------------------
     const int n_nodes = S.n_nodes;
-    double* path = A.out_path + static_cast<size_t>(q) * A.cap_path * 2;
-    int* path_ids = A.out_path_ids + static_cast<size_t>(q) * A.cap_path;
-    double* prof = A.out_profile + static_cast<size_t>(q) * A.cap_path * 3;
+    double* path = nullptr;
+    int* path_ids = nullptr;
+    double* prof = nullptr;
     int n_path = 0, n_profile = 0;
     if (S.status == PP_PLAN_FOUND) {
       // calcPathMsg (LP:503-527) and calcMPMessage (LP:542-583).  The walk is sequential; each
@@ -792,19 +802,23 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       int* rev_first = w.heap_id_g;  // slot of the first match per reversed pose
       int* rev_last = w.rev_last;    // slot of the last match per reversed pose
       const int rev_cap = NC;
-      const double2* sxy = nullptr;
-      if (n_nodes <= A.heap_smem_entries) {
-        double2* dst = reinterpret_cast<double2*>(smem_raw);
-        for (int id = tid; id < n_nodes; id += kT) dst[id] = make_double2(w.cx[id], w.cy[id]);
-        sxy = dst;
+      // a 32-bit hash of every child point fits the (dead) frontier's shared memory even in
+      // batch mode; the scans below read it instead of the 16-byte points in L2 and verify
+      // the rare hash hits against the real coordinates
+      const uint32_t* sh32 = nullptr;
+      if (n_nodes <= A.heap_smem_entries * 4) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+        for (int id = tid; id < n_nodes; id += kT) dst[id] = point_hash32(w.cx[id], w.cy[id]);
+        sh32 = dst;
       }
       __syncthreads();
       // scan for child == (x, y): *k_from = min key >= from, *k_first = min key, *k_last = max key
       auto scan3 = [&](double x, double y, int from, int* k_from, int* k_first, int* k_last) {
         int bf = kIntMax, b0 = kIntMax, bl = -1;
+        const uint32_t want = point_hash32(x, y);
         for (int id = tid; id < n_nodes; id += kT) {
           bool eq;
-          if (sxy) { const double2 c = sxy[id]; eq = c.x == x && c.y == y; }
+          if (sh32) eq = sh32[id] == want && w.cx[id] == x && w.cy[id] == y;
           else eq = w.cx[id] == x && w.cy[id] == y;
           if (eq) {
             const int cs = w.closed_seq[id];
@@ -865,6 +879,11 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
         if (tid == 0) S.status = PP_PLAN_BROKEN;
       } else {
         n_path = len;
+        if (tid == 0) S.pool_off = static_cast<long long>(atomicAdd(A.pool_counter, static_cast<unsigned long long>(min(len, A.cap_path))));
+        __syncthreads();
+        path = A.out_path + 2 * S.pool_off;
+        path_ids = A.out_path_ids + S.pool_off;
+        prof = A.out_profile + S.pool_off;
         for (int k = tid; k < len && k < A.cap_path; k += kT) {   // LP:530-538: reversed
           path[2 * k] = rev[2 * (len - 1 - k)];
           path[2 * k + 1] = rev[2 * (len - 1 - k) + 1];
@@ -885,8 +904,8 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
           const double next_heading = id_b >= 0 ? w.hd[id_b] : 0.0;
           const double next_velocity = id_b >= 0 ? w.vel[id_b] : 0.0;
           prof[i] = dm::div(dm::sub(next_heading, cur_heading), dm::div(P.time_step_ms, 1000.0));   // LP:576-577
-          prof[A.cap_path + i] = P.time_step_ms;                                                     // LP:578
-          prof[2 * A.cap_path + i] = next_velocity;                                                  // LP:579
+          prof[A.pool_cap + i] = P.time_step_ms;                                                     // LP:578
+          prof[2 * A.pool_cap + i] = next_velocity;                                                  // LP:579
         }
       }
     }
@@ -917,6 +936,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       hd.truncated = S.truncated;
       hd.reran = (!S.fast && A.fast_frontier) ? 1 : 0;
       hd.pad_ = 0;
+      hd.pool_off = S.status == PP_PLAN_FOUND ? S.pool_off : 0;
       hd.digest = d;
       if (A.timing) { const long long now_ = clock64(); S.cyc[6] += now_ - t_mark; S.cyc[7] = now_ - t_begin; }
       for (int c = 0; c < 8; ++c) hd.cyc[c] = S.cyc[c];
@@ -974,7 +994,8 @@ struct PlanWorkspace {
   int* d_parent = nullptr;
   size_t parent_bytes = 0;
   int* d_counter = nullptr;
-  std::vector<unsigned char> h_out;
+  unsigned char* h_out = nullptr;   // pinned mirror of the output block
+  size_t h_out_bytes = 0;
 };
 
 namespace pp {
@@ -986,6 +1007,7 @@ void plan_free(pp_handle* h) {
   cudaFree(h->plan_ws->d_queries);
   cudaFree(h->plan_ws->d_parent);
   cudaFree(h->plan_ws->d_counter);
+  cudaFreeHost(h->plan_ws->h_out);
   delete h->plan_ws;
   h->plan_ws = nullptr;
 }
@@ -1061,15 +1083,23 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
 
   int rc = grow(reinterpret_cast<void**>(&W->ws), &W->ws_bytes_total, stride * static_cast<size_t>(n_ws));
   if (rc) return rc;
-  // output block layout
+  // output block layout: headers | pool counter | path pool | id pool | 3 profile planes | expansions
+  const long long pool_cap = static_cast<long long>(cap_path) * n;
   const size_t hdr_b = (sizeof(PlanHdr) * n + 255) & ~size_t(255);
-  const size_t path_b = (sizeof(double) * 2 * cap_path * n + 255) & ~size_t(255);
-  const size_t pid_b = (sizeof(int) * cap_path * static_cast<size_t>(n) + 255) & ~size_t(255);
-  const size_t prof_b = (sizeof(double) * 3 * cap_path * n + 255) & ~size_t(255);
+  const size_t cnt_b = 256;
+  const size_t path_b = (sizeof(double) * 2 * pool_cap + 255) & ~size_t(255);
+  const size_t pid_b = (sizeof(int) * pool_cap + 255) & ~size_t(255);
+  const size_t prof_b = (sizeof(double) * 3 * pool_cap + 255) & ~size_t(255);
   const size_t exp_b = want_exp ? ((sizeof(int) * static_cast<size_t>(cap_exp) * n + 255) & ~size_t(255)) : 0;
-  const size_t out_total = hdr_b + path_b + pid_b + prof_b + exp_b;
+  const size_t out_total = hdr_b + cnt_b + path_b + pid_b + prof_b + exp_b;
   rc = grow(&W->out, &W->out_bytes, out_total);
   if (rc) return rc;
+  if (out_total > W->h_out_bytes) {
+    cudaFreeHost(W->h_out);
+    W->h_out = nullptr; W->h_out_bytes = 0;
+    PP_CUDA(cudaMallocHost(&W->h_out, out_total));
+    W->h_out_bytes = out_total;
+  }
   if (n > W->queries_cap) {
     cudaFree(W->d_queries);
     W->d_queries = nullptr;
@@ -1099,10 +1129,13 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   A.ws_stride = stride;
   A.ws_base = W->ws;
   A.hdr = reinterpret_cast<PlanHdr*>(ob);
-  A.out_path = reinterpret_cast<double*>(ob + hdr_b);
-  A.out_path_ids = reinterpret_cast<int*>(ob + hdr_b + path_b);
-  A.out_profile = reinterpret_cast<double*>(ob + hdr_b + path_b + pid_b);
-  A.out_exp = want_exp ? reinterpret_cast<int*>(ob + hdr_b + path_b + pid_b + prof_b) : nullptr;
+  A.pool_counter = reinterpret_cast<unsigned long long*>(ob + hdr_b);
+  A.pool_cap = pool_cap;
+  A.out_path = reinterpret_cast<double*>(ob + hdr_b + cnt_b);
+  A.out_path_ids = reinterpret_cast<int*>(ob + hdr_b + cnt_b + path_b);
+  A.out_profile = reinterpret_cast<double*>(ob + hdr_b + cnt_b + path_b + pid_b);
+  A.out_exp = want_exp ? reinterpret_cast<int*>(ob + hdr_b + cnt_b + path_b + pid_b + prof_b) : nullptr;
+  PP_CUDA(cudaMemsetAsync(A.pool_counter, 0, sizeof(unsigned long long), s));
   A.work_counter = W->d_counter;
   A.visited = nullptr;
   if (n == 1) {   // clearVisited (LP:251-262)
@@ -1128,14 +1161,29 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   }
   PP_CUDA(cudaEventRecord(h->ev[9], s));
 
-  W->h_out.resize(out_total);
-  PP_CUDA(cudaMemcpyAsync(W->h_out.data(), W->out, out_total, cudaMemcpyDeviceToHost, s));
+  // headers + pool counter first, then only the used prefix of every pool
+  unsigned char* hbw = W->h_out;
+  PP_CUDA(cudaMemcpyAsync(hbw, W->out, hdr_b + cnt_b, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  const size_t used = static_cast<size_t>(*reinterpret_cast<unsigned long long*>(hbw + hdr_b));
+  if (used > 0) {
+    const size_t o_path = hdr_b + cnt_b, o_pid = o_path + path_b, o_prof = o_pid + pid_b;
+    PP_CUDA(cudaMemcpyAsync(hbw + o_path, ob + o_path, sizeof(double) * 2 * used, cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaMemcpyAsync(hbw + o_pid, ob + o_pid, sizeof(int) * used, cudaMemcpyDeviceToHost, s));
+    for (int pl = 0; pl < 3; ++pl)
+      PP_CUDA(cudaMemcpyAsync(hbw + o_prof + sizeof(double) * pool_cap * pl, ob + o_prof + sizeof(double) * pool_cap * pl,
+                              sizeof(double) * used, cudaMemcpyDeviceToHost, s));
+  }
+  if (want_exp) {
+    const size_t o_exp = hdr_b + cnt_b + path_b + pid_b + prof_b;
+    PP_CUDA(cudaMemcpyAsync(hbw + o_exp, ob + o_exp, exp_b, cudaMemcpyDeviceToHost, s));
+  }
   PP_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]);
   h->phase_ms[PP_PHASE_PLAN] = ms;
 
-  const unsigned char* hb = W->h_out.data();
+  const unsigned char* hb = W->h_out;
   const PlanHdr* hdr = reinterpret_cast<const PlanHdr*>(hb);
   if (getenv("PP_PLAN_TIMING")) {
     const char* names[8] = {"init", "close", "goal+eval", "commit", "push", "close2", "extract", "total"};
@@ -1144,10 +1192,10 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
     for (int k = 0; k < n; ++k) reruns += hdr[k].reran;
     fprintf(stderr, "[pp_plan] exact-heap re-runs (cost ties): %d of %d queries\n", reruns, n);
   }
-  const double* hpath = reinterpret_cast<const double*>(hb + hdr_b);
-  const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + path_b);
-  const double* hprof = reinterpret_cast<const double*>(hb + hdr_b + path_b + pid_b);
-  const int* hexp = want_exp ? reinterpret_cast<const int*>(hb + hdr_b + path_b + pid_b + prof_b) : nullptr;
+  const double* hpath = reinterpret_cast<const double*>(hb + hdr_b + cnt_b);
+  const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + cnt_b + path_b);
+  const double* hprof = reinterpret_cast<const double*>(hb + hdr_b + cnt_b + path_b + pid_b);
+  const int* hexp = want_exp ? reinterpret_cast<const int*>(hb + hdr_b + cnt_b + path_b + pid_b + prof_b) : nullptr;
   int ret = PP_OK;
   std::vector<double> soa;
   std::vector<int> iso;
@@ -1166,13 +1214,13 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
     r.tree_digest = d.digest;
     const int np = std::min(d.n_path, std::min(r.cap_path, cap_path));
     if (d.n_path > r.cap_path && (r.path_xy || r.path_node_ids)) ret = PP_ERR_CAPACITY;
-    if (r.path_xy) std::memcpy(r.path_xy, hpath + static_cast<size_t>(k) * cap_path * 2, sizeof(double) * 2 * np);
-    if (r.path_node_ids) std::memcpy(r.path_node_ids, hpid + static_cast<size_t>(k) * cap_path, sizeof(int) * np);
+    if (r.path_xy) std::memcpy(r.path_xy, hpath + 2 * d.pool_off, sizeof(double) * 2 * np);
+    if (r.path_node_ids) std::memcpy(r.path_node_ids, hpid + d.pool_off, sizeof(int) * np);
     const int nm = std::min(d.n_profile, std::min(r.cap_path, cap_path));
-    const double* pr = hprof + static_cast<size_t>(k) * cap_path * 3;
+    const double* pr = hprof + d.pool_off;
     if (r.yaw_rates) std::memcpy(r.yaw_rates, pr, sizeof(double) * nm);
-    if (r.durations) std::memcpy(r.durations, pr + cap_path, sizeof(double) * nm);
-    if (r.speeds) std::memcpy(r.speeds, pr + 2 * cap_path, sizeof(double) * nm);
+    if (r.durations) std::memcpy(r.durations, pr + pool_cap, sizeof(double) * nm);
+    if (r.speeds) std::memcpy(r.speeds, pr + 2 * pool_cap, sizeof(double) * nm);
     if (r.expansion_ids) {
       const int ne = std::min(d.n_expansions, r.cap_expansions);
       if (d.n_expansions > r.cap_expansions) ret = PP_ERR_CAPACITY;
