@@ -166,6 +166,33 @@ __device__ __forceinline__ bool lattice_any(const Lattice& l, const NarrowJob& j
   return lattice_any_generic(l, job, sm, lane);
 }
 
+// Up to 32 poses, one per lane (`need` = this lane's pose survived the broad phase and `job`
+// describes it): the warp runs the narrow phase for them in turn and returns true as soon as
+// one collides.  All lanes return the same value.
+__device__ __forceinline__ bool warp_collide_jobs(const GridDev& g, const Lattice& lat, const NarrowJob& job,
+                                                  bool need, uint32_t* sm, int lane) {
+  uint32_t todo = __ballot_sync(0xffffffffu, need);
+  bool hit = false;
+  while (todo && !hit) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    NarrowJob j;
+    j.oi = __shfl_sync(0xffffffffu, job.oi, src);
+    j.oj = __shfl_sync(0xffffffffu, job.oj, src);
+    j.ui = __shfl_sync(0xffffffffu, job.ui, src);
+    j.uj = __shfl_sync(0xffffffffu, job.uj, src);
+    j.vi = __shfl_sync(0xffffffffu, job.vi, src);
+    j.vj = __shfl_sync(0xffffffffu, job.vj, src);
+    j.tiles = __shfl_sync(0xffffffffu, job.tiles, src);
+    j.box = __shfl_sync(0xffffffffu, job.box, src);
+    j.occ = __shfl_sync(0xffffffffu, job.occ, src);
+    stage_window(g, j, sm, lane);
+    if (window_box_any(j, sm, lane)) hit = lattice_any(lat, j, sm, lane);
+    __syncwarp();
+  }
+  return hit;
+}
+
 // One pose, whole warp, all lanes hold the same (x, y, yaw): true iff the footprint collides.
 __device__ __forceinline__ bool warp_collide_oriented(const GridDev& g, const Lattice& lat, double x, double y,
                                                       double yaw, uint32_t* sm, int lane) {

@@ -117,11 +117,19 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
   const pp_query qq = A.queries[q];
   const long long s0 = st.n_samples;
   const int k_round = static_cast<int>(min(static_cast<long long>(A.K), static_cast<long long>(A.P.rrt_max_samples) - s0));
+  // K >= 256: every thread owns up to kSPT samples and scans the whole tile.
+  // K <  256: the threads form G = 256 / Kp groups (Kp = K rounded up to a power of two); a
+  // group's thread owns one sample and scans every G-th node of the tile, so no lane idles.
+  int Kp = 1;
+  while (Kp < A.K) Kp <<= 1;
+  const int G = Kp >= kT ? 1 : kT / Kp;
+  const int grp = G == 1 ? 0 : threadIdx.x / Kp;
   float sx[kSPT], sy[kSPT], bd[kSPT];
-  int bi[kSPT];
+  int bi[kSPT], st_[kSPT];
 #pragma unroll
   for (int u = 0; u < kSPT; ++u) {
-    const int t = threadIdx.x + u * kT;
+    const int t = G == 1 ? threadIdx.x + u * kT : (u == 0 ? threadIdx.x % Kp : k_round);
+    st_[u] = t;
     sx[u] = 0.f; sy[u] = 0.f; bd[u] = 0.f; bi[u] = -1;
     if (t < k_round) draw_sample(A, qq, s0 + t, &sx[u], &sy[u]);
   }
@@ -131,19 +139,28 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
     __syncthreads();
     for (int k = threadIdx.x; k < cnt; k += kT) tile[k] = nodes[base + k];
     __syncthreads();
-    for (int k = 0; k < cnt; ++k) {
-      const float2 nd = tile[k];
+    if (G == 1) {
+      for (int k = 0; k < cnt; ++k) {
+        const float2 nd = tile[k];
 #pragma unroll
-      for (int u = 0; u < kSPT; ++u) {
-        const float dx = __fsub_rn(sx[u], nd.x), dy = __fsub_rn(sy[u], nd.y);
+        for (int u = 0; u < kSPT; ++u) {
+          const float dx = __fsub_rn(sx[u], nd.x), dy = __fsub_rn(sy[u], nd.y);
+          const float d = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+          if (bi[u] < 0 || d < bd[u]) { bd[u] = d; bi[u] = base + k; }
+        }
+      }
+    } else {
+      for (int k = grp; k < cnt; k += G) {
+        const float2 nd = tile[k];
+        const float dx = __fsub_rn(sx[0], nd.x), dy = __fsub_rn(sy[0], nd.y);
         const float d = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-        if (bi[u] < 0 || d < bd[u]) { bd[u] = d; bi[u] = base + k; }
+        if (bi[0] < 0 || d < bd[0]) { bd[0] = d; bi[0] = base + k; }
       }
     }
   }
 #pragma unroll
   for (int u = 0; u < kSPT; ++u) {
-    const int t = threadIdx.x + u * kT;
+    const int t = st_[u];
     if (t < k_round && bi[u] >= 0) {
       const unsigned long long packed = (static_cast<unsigned long long>(__float_as_uint(bd[u])) << 32) |
                                         static_cast<unsigned int>(bi[u]);
@@ -193,11 +210,24 @@ __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A) {
     bool hit = false;
     if (dm::trunc_to_int(dm::mul(dm::div(dist, A.P.search_res), 2.0), &n)) {
       if (n < 1) n = 1;
-      for (int k = 1; k <= n && !hit; ++k) {
-        const double tt = dm::div(static_cast<double>(k), static_cast<double>(n));
-        const double ex = dm::add(px, dm::mul(tt, dx)), ey = dm::add(py, dm::mul(tt, dy));
-        if (A.cp.mode == PP_COLLISION_ORIENTED) hit = warp_collide_oriented(A.g, A.cp.lat, ex, ey, yaw, smem[wib], lane);
-        else if (A.cp.mode == PP_COLLISION_REF_AABB) hit = aabb_hit(A.g, ex, ey);
+      // the edge's poses are a mini-batch: lane l sets up pose base + l + 1 (broad phase, one
+      // thread each), then the warp runs the narrow phase only for the poses that need it
+      for (int base = 0; base < n && !hit; base += 32) {
+        const int k = base + lane + 1;
+        bool need = false;
+        NarrowJob job;
+        if (k <= n) {
+          const double tt = dm::div(static_cast<double>(k), static_cast<double>(n));
+          const double ex = dm::add(px, dm::mul(tt, dx)), ey = dm::add(py, dm::mul(tt, dy));
+          if (A.cp.mode == PP_COLLISION_ORIENTED) {
+            const PoseFx pf = pose_to_fixed(A.cp.lat, A.g.W, A.g.H, A.g.res, ex, ey, yaw);
+            need = make_job(A.g, A.cp.lat, pf, 1, &job);
+          } else if (A.cp.mode == PP_COLLISION_REF_AABB) {
+            hit = aabb_hit(A.g, ex, ey);
+          }
+        }
+        if (A.cp.mode == PP_COLLISION_ORIENTED) hit = warp_collide_jobs(A.g, A.cp.lat, job, need, smem[wib], lane);
+        else hit = __any_sync(0xffffffffu, hit);
       }
     }
     verdict = hit ? 2 : 1;
