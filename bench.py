@@ -29,6 +29,8 @@ GRID = 4096
 RES = 0.1
 ALG_BYTES_ORIENTED = 12 + 1 + 48 * 17   # pose + flag + one byte per lattice sample = 829 B
 ALG_BYTES_AABB = 12 + 1 + 47 * 15       # 718 B
+# ncu --set full, collide_oriented_kernel, 2^22 poses: dram__bytes_read.sum + dram__bytes_write.sum
+DRAM_BYTES_PER_POSE_NCU = (50.627072e6 + 20.48e3) / (1 << 22)
 
 
 def _peaks():
@@ -114,7 +116,8 @@ def run_reference(args):
         return
     grid = make_grid()
     cores = os.cpu_count() or 1
-    n_sample = 1 << 22
+    # bounded sample: ~2^27 poses of CPU work for the whole run, whatever --steps is
+    n_sample = max(1 << 16, min(1 << 22, (1 << 27) // max(1, args.steps)))
     rates = []
     for _ in range(args.warmup):
         cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 18, cores)
@@ -168,18 +171,28 @@ def run_ours(args):
     n = args.poses
     # inputs resident in HBM before the timed region: the Philox sampler fills them (row S1)
     poses = pl.sample_poses_dev(2018, rank, 0, n, *box)
-    flags = torch.empty(n, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(n * world, dtype=torch.uint8, device=dev) if multi else None
+    # two result buffers: the NCCL gather of step k overlaps the kernel of step k+1
+    flags2 = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
+    gathered2 = [torch.empty(n * world, dtype=torch.uint8, device=dev) if multi else None for _ in range(2)]
+    gather_done = [None, None]
+    flags = flags2[0]
+    step_no = [0]
     pl.sync()
 
     def step():
-        pl.collide_dev(poses, out=flags)
+        i = step_no[0] & 1
+        step_no[0] += 1
+        if multi and gather_done[i] is not None:
+            pl.stream.wait_event(gather_done[i])        # the buffer's previous gather has finished
+        pl.collide_dev(poses, out=flags2[i])
         if multi:
-            # result gather (north_star: NCCL only to gather results); ordered after the kernel
+            # result gather (north_star: NCCL only to gather results), ordered after the kernel
             ev = torch.cuda.Event()
             ev.record(pl.stream)
             torch.cuda.current_stream().wait_event(ev)
-            dist.all_gather_into_tensor(gathered, flags)
+            dist.all_gather_into_tensor(gathered2[i], flags2[i])
+            gather_done[i] = torch.cuda.Event()
+            gather_done[i].record(torch.cuda.current_stream())
 
     def barrier():
         pl.sync()
@@ -211,6 +224,8 @@ def run_ours(args):
     dev_ms = e0.elapsed_time(e1)
     launches = pl.launch_count() - launches0
     # per-launch duration of the dominant kernel (events recorded inside the library, on its stream)
+    pl.sync()
+    torch.cuda.synchronize()
     for _ in range(3):
         pl.collide_dev(poses, out=flags)
         kernel_ms.append(pl.last_phase_ms()[2])
@@ -296,7 +311,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": n},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": DRAM_BYTES_PER_POSE_NCU * n, "traffic_unit": "bytes/launch",
+                         "traffic_source": "profiles/r1_ncu_collide_oriented_v3_broad.csv (dram read+write / 2^22 poses)",
+                         "peak_kind": peak_kind,
                          "kernel": "collide_oriented_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_pose": ALG_BYTES_ORIENTED, "narrow_phase_poses": narrow_units},
             "cpu_baseline": cpu,
