@@ -19,7 +19,7 @@ EXPORTS = [
     "pp_collide_batch_dev", "pp_collide_edges_dev", "pp_footprint_points", "pp_sample_poses_dev",
     "pp_philox4x32_10", "pp_nearest_dev", "pp_find_exact_dev", "pp_plan", "pp_plan_batch", "pp_rrt_plan",
     "pp_rrt_plan_batch", "pp_get_visited", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
-    "pp_last_narrow_count", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
+    "pp_last_narrow_count", "pp_bench_l2_gather", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
     "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch",
 ]
 
@@ -70,6 +70,7 @@ def load():
     L.pp_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.pp_last_phase_ms.argtypes = [vp, C.POINTER(f32), i32]
     L.pp_last_narrow_count.argtypes = [vp, C.POINTER(i64)]
+    L.pp_bench_l2_gather.argtypes = [vp, C.c_size_t, C.POINTER(f64)]
     L.pp_set_broad_phase.argtypes = [vp, C.c_int]
     L.pp_group_create.argtypes = [C.POINTER(pp_params), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
     L.pp_group_destroy.argtypes = [vp]

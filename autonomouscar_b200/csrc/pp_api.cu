@@ -393,6 +393,11 @@ int pp_last_narrow_count(pp_handle* h, int64_t* out) {
   *out = h->last_narrow;
   return PP_OK;
 }
+int pp_bench_l2_gather(pp_handle* h, size_t buffer_bytes, double* out_gbps) {
+  if (!h || !out_gbps || buffer_bytes < 64) return PP_ERR_INVALID;
+  PP_CUDA(cudaSetDevice(h->device));
+  return l2_gather_bench(h, buffer_bytes, out_gbps);
+}
 int pp_set_broad_phase(pp_handle* h, int enabled) {
   if (!h) return PP_ERR_INVALID;
   h->broad_phase = enabled ? 1 : 0;

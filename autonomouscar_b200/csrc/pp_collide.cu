@@ -59,7 +59,7 @@ template <int NU, int NV, int S>
 __global__ void __launch_bounds__(kThreads)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
                         int64_t n, int broad_phase, unsigned long long* __restrict__ narrow_counter) {
-  __shared__ uint32_t s_win[kWarpsPerBlock][kWinWords];
+  __shared__ __align__(16) uint32_t s_win[kWarpsPerBlock][kWinWords];
   __shared__ int s_queue[kChunk];
   __shared__ NarrowJob s_jobs[kThreads];
   __shared__ int s_job_off[kThreads];

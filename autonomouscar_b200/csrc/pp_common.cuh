@@ -287,6 +287,7 @@ int sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t firs
                      float x_hi, float y_lo, float y_hi, float* out);
 int nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy, int64_t n_query, const float* q,
                 int32_t* idx, float* d2);
+int l2_gather_bench(pp_handle* h, size_t buffer_bytes, double* out_gbps);
 int find_exact_dev(pp_handle* h, int64_t n_nodes, const double* keys, int64_t n_query, const double* q,
                    int32_t* idx);
 int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs);

@@ -183,7 +183,9 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
     g.aabb_nx = W + 2 * g.aabb_pad_x;
     g.aabb_ny = H + 2 * g.aabb_pad_y;
     PP_CUDA(cudaMalloc(&g.cspace, cells));
-    PP_CUDA(cudaMalloc(&g.occ_tiles, static_cast<size_t>(g.TI) * g.TJ * kTile * sizeof(uint32_t)));
+    // + 2 tiles of padding: the narrow phase reads every tile row three tiles wide
+    PP_CUDA(cudaMalloc(&g.occ_tiles, (static_cast<size_t>(g.TI) * g.TJ + 2) * kTile * sizeof(uint32_t)));
+    PP_CUDA(cudaMemset(g.occ_tiles + static_cast<size_t>(g.TI) * g.TJ * kTile, 0, 2 * kTile * sizeof(uint32_t)));
     PP_CUDA(cudaMalloc(&g.tile_any, static_cast<size_t>(g.TI) * g.TJ));
     g.CI8 = g.TI * 4;
     g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last

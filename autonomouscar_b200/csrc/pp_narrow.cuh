@@ -69,18 +69,20 @@ __device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, con
 // (wcol = column / 32).  Each staged tile is one coalesced 128 B line.
 constexpr int kWinWords = 3 * 96;
 
+// The three tiles of one tile row are 3 x 128 B contiguous in memory, so a row of the window is
+// one 128-bit load by 24 lanes (lane l: tile l / 8, rows 4 (l % 8) .. +3) and one 128-bit store.
+// Tile rows without an obstacle under the box are zero-filled instead of loaded.  Tiles beside
+// the box may be loaded as well; no lattice sample can land there.  (The tile array is padded
+// by two tiles so that the last tile row can be read three tiles wide.)
 __device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& job, uint32_t* sm, int lane) {
   const int t0i = job.tiles >> 16, t0j = job.tiles & 0xffff;
-  // all nine (predicated) loads are issued back to back: one exposed L2 latency per pose
+  const int b = lane >> 3, r4 = (lane & 7) * 4;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      uint32_t w = 0;
-      if ((job.occ >> (a * 3 + b)) & 1u)
-        w = __ldg(&g.occ_tiles[(static_cast<size_t>(t0i + a) * g.TJ + (t0j + b)) * kTile + lane]);
-      sm[b * 96 + a * 32 + lane] = w;
-    }
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 24 && ((job.occ >> (a * 3)) & 7u))
+      w = __ldg(reinterpret_cast<const uint4*>(&g.occ_tiles[(static_cast<size_t>(t0i + a) * g.TJ + t0j) * kTile]) + lane);
+    if (lane < 24) *reinterpret_cast<uint4*>(&sm[b * 96 + a * 32 + r4]) = w;
   }
   __syncwarp();
 }

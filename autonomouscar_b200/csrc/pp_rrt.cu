@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
 }
 
 __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A) {
-  __shared__ uint32_t smem[kT / 32][kWinWords];
+  __shared__ __align__(16) uint32_t smem[kT / 32][kWinWords];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long warp = blockIdx.x * static_cast<long long>(kT / 32) + wib;
   const int q = static_cast<int>(warp / A.K), t = static_cast<int>(warp % A.K);

@@ -103,6 +103,23 @@ find_exact_kernel(const double* __restrict__ keys, int64_t n_nodes, const double
   }
 }
 
+// L2 gather microbenchmark (MEASURED_PEAKS.json has no L2 figure): every
+// thread issues `per_thread` independent 16-byte loads at pseudo-random 32-byte sectors of a
+// buffer that fits L2; the sum keeps the loads alive.
+__global__ void __launch_bounds__(256)
+l2_gather_kernel(const uint4* __restrict__ buf, uint32_t n_sectors_mask, int per_thread, uint32_t* __restrict__ sink) {
+  uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  uint32_t acc = 0;
+#pragma unroll 8
+  for (int k = 0; k < per_thread; ++k) {
+    x = x * 1664525u + 1013904223u;                    // LCG: addresses do not depend on loaded data
+    const uint32_t sector = (x >> 7) & n_sectors_mask;
+    const uint4 v = __ldg(&buf[static_cast<size_t>(sector) * 2]);   // 16 B out of the 32 B sector
+    acc += v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x9e3779b9u) sink[0] = acc;               // practically never taken
+}
+
 int blocks_for(const pp_handle* h, int64_t want) {
   const int64_t cap = static_cast<int64_t>(h->sm_count) * 8;
   return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
@@ -130,6 +147,37 @@ int philox_kat(pp_handle* h, const uint32_t c[4], const uint32_t k[2], uint32_t 
   PP_CUDA(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, h->stream));
   PP_CUDA(cudaStreamSynchronize(h->stream));
   PP_CUDA(cudaFree(d));
+  return PP_OK;
+}
+
+int l2_gather_bench(pp_handle* h, size_t buffer_bytes, double* out_gbps) {
+  size_t sectors = 1;
+  while (sectors * 2 * 32 <= buffer_bytes) sectors *= 2;   // power of two number of 32 B sectors
+  uint4* buf = nullptr;
+  uint32_t* sink = nullptr;
+  PP_CUDA(cudaMalloc(&buf, sectors * 32));
+  PP_CUDA(cudaMalloc(&sink, 64));
+  PP_CUDA(cudaMemsetAsync(buf, 1, sectors * 32, h->stream));
+  const int per_thread = 256, blocks = h->sm_count * 16;
+  cudaEvent_t a, b;
+  PP_CUDA(cudaEventCreate(&a));
+  PP_CUDA(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    PP_CUDA(cudaEventRecord(a, h->stream));
+    l2_gather_kernel<<<blocks, 256, 0, h->stream>>>(buf, static_cast<uint32_t>(sectors - 1), per_thread, sink);
+    PP_CUDA(cudaEventRecord(b, h->stream));
+    PP_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    PP_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+    h->launches++;
+  }
+  *out_gbps = static_cast<double>(blocks) * 256 * per_thread * 32.0 / (best * 1e-3) / 1e9;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(buf);
+  cudaFree(sink);
   return PP_OK;
 }
 

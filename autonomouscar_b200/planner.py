@@ -223,6 +223,11 @@ class Planner:
         self._check(self._L.pp_last_phase_ms(self._h, a, PP_PHASE_COUNT))
         return [float(v) for v in a]
 
+    def bench_l2_gather(self, buffer_bytes=16 << 20):
+        v = C.c_double()
+        self._check(self._L.pp_bench_l2_gather(self._h, buffer_bytes, C.byref(v)))
+        return v.value
+
     def last_narrow_count(self):
         v = C.c_int64()
         self._check(self._L.pp_last_narrow_count(self._h, C.byref(v)))

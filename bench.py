@@ -276,6 +276,7 @@ def run_ours(args):
         ms_aabb = timed(lambda: pl.collide_dev(poses, out=flags))
         pl.set_collision_mode(PP_COLLISION_ORIENTED)
         ms_sampler = timed(lambda: pl.sample_poses_dev(2018, rank, 0, n, *box, out=poses))
+        l2_gbps = pl.bench_l2_gather(16 << 20)      # random 32 B sectors of a 16 MiB (L2-resident) buffer
         extra = {
             "oriented_direct_poses_per_s": n / (ms_direct * 1e-3), "oriented_direct_narrow_units": direct_units,
             "oriented_direct_frac_of_hbm_roofline": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / _peaks()[0],
@@ -283,6 +284,9 @@ def run_ours(args):
             "ref_aabb_frac_of_hbm_roofline": ALG_BYTES_AABB * n / (ms_aabb * 1e-3) / 1e9 / _peaks()[0],
             "philox_sampler_poses_per_s": n / (ms_sampler * 1e-3),
             "philox_sampler_write_GBps": 12 * n / (ms_sampler * 1e-3) / 1e9,
+            "l2_gather_peak_GBps_measured": l2_gbps,
+            "oriented_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_per_step * 1e-3) / 1e9 / l2_gbps,
+            "oriented_direct_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / l2_gbps,
         }
     plans = bench_plans(pl, rank, world, dev, multi, args) if not args.skip_plans else None
 

@@ -273,6 +273,11 @@ enum { PP_PHASE_H2D = 0, PP_PHASE_BROAD = 1, PP_PHASE_NARROW = 2, PP_PHASE_D2H =
 int pp_last_phase_ms(pp_handle* h, float* out_ms, int32_t n);
 /* units (poses / queries) the narrow-phase kernel of the last collide call processed */
 int pp_last_narrow_count(pp_handle* h, int64_t* out);
+/* Roofline helper: random 32-byte-sector gathers (16 B loaded per sector, 32 B counted) from a
+   buffer of `buffer_bytes` (rounded down to a power of two); best of 4 timed launches, GB/s.
+   With a buffer that fits L2 this is the L2 gather bandwidth the collision kernels are bounded
+   by when they read one sector per footprint cell. */
+int pp_bench_l2_gather(pp_handle* h, size_t buffer_bytes, double* out_gbps);
 /* tuning knob: 0 = every pose goes through the full footprint gather ("direct"),
    1 = conservative broad phase first (default).  Results are identical. */
 int pp_set_broad_phase(pp_handle* h, int enabled);
