@@ -42,48 +42,73 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons while the timed region runs: one `nvidia-smi -lms 20`
+    child streams timestamped rows; only rows stamped inside [start(), stop()] are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self.t0 = self.t1 = None
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
 
     def _run(self):
-        while not self._stop.is_set():
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def start(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def stop(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
+    def close(self):
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.proc.wait(timeout=3)
             except Exception:
-                pass
-            self._stop.wait(0.1)
-
-    def __enter__(self):
-        self._t.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+                self.proc.kill()
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        import datetime
+        inside, allrows = [], []
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                float(r[1])
+            except Exception:
+                continue
+            allrows.append(r)
+            if self.t0 and self.t1 and self.t0 <= ts <= self.t1 + datetime.timedelta(milliseconds=30):
+                inside.append(r)
+        use = inside if inside else allrows[-3:]
+        sm = sorted(float(r[1]) for r in use)
+        mx = [float(r[2]) for r in use]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for name, v in zip(names, r[3:7]):
+        for r in use:
+            for name, v in zip(names, r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        pw = [float(r[3]) for r in use if r[3].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(inside), "power_w_max": max(pw) if pw else None}
 
 
 def make_grid():
@@ -201,26 +226,27 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    kernel_ms = []
+    clk = ClockSampler(local)
+    for _ in range(max(3, args.warmup)):    # (re-)warm with the sampler child already streaming
         step()
     barrier()
     launches0 = pl.launch_count()
-    kernel_ms = []
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(pl.stream)
-        for _ in range(args.steps):
-            step()
-            if not multi:
-                pass
-        if multi:
-            evj = torch.cuda.Event()
-            evj.record(torch.cuda.current_stream())
-            pl.stream.wait_event(evj)
-        e1.record(pl.stream)
-        barrier()
-        wall = time.perf_counter() - t0
+    clk.start()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(pl.stream)
+    for _ in range(args.steps):
+        step()
+    if multi:
+        evj = torch.cuda.Event()
+        evj.record(torch.cuda.current_stream())
+        pl.stream.wait_event(evj)
+    e1.record(pl.stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clk.stop()
+    clk.close()
     dev_ms = e0.elapsed_time(e1)
     launches = pl.launch_count() - launches0
     # per-launch duration of the dominant kernel (events recorded inside the library, on its stream)
