@@ -1056,7 +1056,9 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
     set_last_error("pp_plan: more than 8192 children per expansion (velocity_res / heading_res too fine)");
     return PP_ERR_UNSUPPORTED;
   }
-  const int NC = P.max_nodes + static_cast<int>(max_children) + 64;
+  // multiple of 8 slots: every SoA sub-array of the workspace stays 16-byte aligned (the hash set is
+  // cleared and the frontier entries are moved with 128-bit accesses)
+  const int NC = ((P.max_nodes + static_cast<int>(max_children) + 64) + 7) & ~7;
   int hash_size = 1024;
   while (hash_size < 2 * NC) hash_size <<= 1;
   const size_t stride = ws_bytes(NC, hash_size);

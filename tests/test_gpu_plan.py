@@ -190,3 +190,33 @@ def test_cost_ties_follow_libstdcpp_heap_order(oracle, cuda_device):
         got = pl.plan(q)
         _assert_same(got, ref)
     pl.close()
+
+
+def test_exact_heap_path_single_and_hybrid(oracle, cuda_device, monkeypatch):
+    """The libstdc++-exact frontier is normally only used when the fast frontier detects a cost
+    tie; force it (PP_PLAN_EXACT_HEAP=1) and check parity for a lone query (whole heap in shared
+    memory) and for a batch large enough to use the hybrid placement (top 2048 entries in shared
+    memory, deeper levels in L2) with trees of > 4000 nodes."""
+    from autonomouscar_b200 import Planner
+    monkeypatch.setenv("PP_PLAN_EXACT_HEAP", "1")
+    p = default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=6000)
+    grid = worlds.block_grid(300, 300, frac=0.01, block=4, seed=9)
+    worlds.clear_disc(grid, p, 0.0, 0.0, 4.0)
+    pl = Planner(p, device=0)
+    pl.set_grid(grid)
+    qs = worlds.forward_queries(400, seed=21)
+    ref0 = oracle.plan(p, grid, qs[0], math_mode=oracle.MATH_DET)
+    _assert_same(pl.plan(qs[0]), ref0)
+    batch = pl.plan_batch(qs, want_nodes=False)
+    secs, statuses, n_nodes, digests = oracle.plan_batch_timed(p, grid, qs, math_mode=oracle.MATH_DET, n_threads=8)
+    assert [r.status for r in batch] == list(statuses)
+    assert [r.n_nodes for r in batch] == list(n_nodes)
+    assert [r.tree_digest for r in batch] == [int(d) for d in digests]
+    assert max(n_nodes) > 4000
+    monkeypatch.delenv("PP_PLAN_EXACT_HEAP")
+    fast = pl.plan_batch(qs, want_nodes=False)
+    assert [r.tree_digest for r in fast] == [int(d) for d in digests]
+    for a, b in zip(fast[:20], batch[:20]):
+        np.testing.assert_array_equal(a.path_xy, b.path_xy)
+        np.testing.assert_array_equal(a.speeds, b.speeds)
+    pl.close()
