@@ -258,14 +258,19 @@ struct QueryD {
   double gx, gy, gs, max_speed, max_accel, start_speed;
 };
 
-// LP:171-189
-__device__ __forceinline__ bool check_goal_dist(const pp_params& P, const QueryD& Q, double cx, double cy,
-                                                double heading, double vel) {
-  double next_vel = dm::add(vel, dm::div(dm::mul(Q.max_accel, P.time_step_ms), 1000.0));
+// Values that the reference recomputes for every child but that only depend on the query
+// (common sub-expressions: same operations, same bits).
+struct QueryConst {
+  double accel_step;   // max_accel * time_step_ms / 1000          (LP:173)
+  double max_dist;     // sqrt(goal_x^2 + goal_y^2)                (LP:124)
+};
+
+// LP:171-189.  (s, c) = sin / cos of `heading`, already computed by the caller for the same angle.
+__device__ __forceinline__ bool check_goal_dist(const pp_params& P, const QueryD& Q, const QueryConst& K, double cx,
+                                                double cy, double s, double c, double vel) {
+  double next_vel = dm::add(vel, K.accel_step);
   if (next_vel > Q.max_speed) next_vel = Q.max_speed;
   const double avg = dm::div(dm::add(next_vel, vel), 2.0);
-  double s, c;
-  dm::sincos(heading, &s, &c);
   const double step = dm::div(dm::mul(avg, P.time_step_ms), 1000.0);
   const double x = dm::add(cx, dm::mul(step, c));
   const double y = dm::add(cy, dm::mul(step, s));
@@ -277,18 +282,17 @@ __device__ __forceinline__ bool check_goal_dist(const pp_params& P, const QueryD
 }
 
 // LP:115-137
-__device__ __forceinline__ double calc_h(const pp_params& P, const QueryD& Q, double cx, double cy, double heading,
-                                         double vel) {
+__device__ __forceinline__ double calc_h(const pp_params& P, const QueryD& Q, const QueryConst& K, double cx,
+                                         double cy, double heading, double s, double c, double vel) {
   double speed = vel;
   if (speed == 0) speed = 0.01;
-  const double max_dist = __dsqrt_rn(dm::add(dm::mul(Q.gx, Q.gx), dm::mul(Q.gy, Q.gy)));
   const double ex = dm::sub(cx, Q.gx), ey = dm::sub(cy, Q.gy);
   const double dist_to_goal = __dsqrt_rn(dm::add(dm::mul(ex, ex), dm::mul(ey, ey)));
-  const double dist_h = dm::mul(dm::div(dist_to_goal, max_dist), 100.0);
+  const double dist_h = dm::mul(dm::div(dist_to_goal, K.max_dist), 100.0);
   const double yaw_to_goal = dm::atan2_(dm::sub(Q.gy, cy), dm::sub(Q.gx, cx));
   const double yaw_h = dm::mul(dm::div(fabs(dm::sub(heading, yaw_to_goal)), 6.283185307179586), 100.0);
   double speed_h = dm::sub(100.0, dm::mul(dm::div(speed, P.max_velocity), 100.0));
-  if (check_goal_dist(P, Q, cx, cy, heading, vel)) speed_h = dm::mul(fabs(dm::sub(speed, Q.gs)), 100.0);
+  if (check_goal_dist(P, Q, K, cx, cy, s, c, vel)) speed_h = dm::mul(fabs(dm::sub(speed, Q.gs)), 100.0);
   return fabs(dm::add(dm::add(dist_h, yaw_h), speed_h));
 }
 
@@ -514,6 +518,9 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
     QueryD Q;
     Q.gx = qq.goal_x; Q.gy = qq.goal_y; Q.gs = qq.goal_speed;
     Q.max_speed = qq.max_speed; Q.max_accel = qq.max_accel; Q.start_speed = qq.start_speed;
+    QueryConst KQ;
+    KQ.accel_step = dm::div(dm::mul(Q.max_accel, P.time_step_ms), 1000.0);
+    KQ.max_dist = __dsqrt_rn(dm::add(dm::mul(Q.gx, Q.gx), dm::mul(Q.gy, Q.gy)));
     int* exp_out = A.out_exp ? A.out_exp + static_cast<size_t>(q) * A.cap_exp : nullptr;
 
     // attempt 0 runs with the fast frontier; a detected cost tie re-runs the query with the exact heap
@@ -656,7 +663,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
             k[0] = x; k[1] = y; k[2] = ncx; k[3] = ncy; k[4] = yaw; k[5] = vel;
             const double ddx = dm::sub(x, ncx), ddy = dm::sub(y, ncy);
             g = __dsqrt_rn(dm::add(dm::mul(ddx, ddx), dm::mul(ddy, ddy)));            // LP:162 (+ LP:139-144)
-            cost = dm::add(g, calc_h(P, Q, x, y, yaw, vel));                           // LP:163
+            cost = dm::add(g, calc_h(P, Q, KQ, x, y, yaw, sy, cyaw, vel));             // LP:163
             fp = key_fingerprint(k);
             suspicious = hash_contains(w, A.hash_size, fp);
           }
