@@ -122,7 +122,11 @@ def params(mode):
 
 
 # -----------------------------------------------------------------------------------------
-# the CPU arm: the oracle (a port; the reference needs ROS and cannot be built here)
+# the CPU arm.  oracle/_ref = the reference's own local_planner.cpp compiled unmodified against
+# ROS test doubles (oracle/Makefile); when it is present the reference's OWN collision check
+# (checkCollision + calcCollisionMatrix, LP:443-496: axis-aligned cell box, the only footprint
+# test the reference has -- it has no oriented one) is what gets timed, on the same poses and
+# grid, one node instance per host thread.  The oracle's ORIENTED port is reported next to it.
 # -----------------------------------------------------------------------------------------
 def cpu_collide_rate(grid, mode, n_sample, threads, seed=1):
     from autonomouscar_b200 import worlds
@@ -134,6 +138,41 @@ def cpu_collide_rate(grid, mode, n_sample, threads, seed=1):
     return n_sample / secs, secs
 
 
+def grid_as_msg(grid):
+    """nav_msgs/OccupancyGrid.data whose LP:439 flip gives `grid` (planner order)."""
+    import numpy as np
+    return np.ascontiguousarray(grid.reshape(-1)[::-1])
+
+
+class ReferenceCollider:
+    """The reference's checkCollision on `threads` node instances (oracle/_ref, AABB variant)."""
+
+    def __init__(self, grid, threads):
+        from autonomouscar_b200 import PP_COLLISION_REF_AABB, worlds
+        from oracle import ref_binding as ref
+        self.p = params(PP_COLLISION_REF_AABB)
+        self.box = worlds.pose_box(self.p)
+        self.pool = ref.RefPool(self.p, grid_as_msg(grid), threads, ref.AABB)
+
+    def rate(self, n_sample, seed=1):
+        from oracle import binding as orc
+        poses = orc.sample_poses(seed, 0, 0, n_sample, *self.box)
+        flags, secs = self.pool.check_collision(poses)
+        assert int((flags == 2).sum()) == 0      # the bench poses stay clear of the reference's UB
+        return n_sample / secs, secs
+
+    def close(self):
+        self.pool.close()
+
+
+def ref_available():
+    try:
+        from oracle import ref_binding as ref
+        return ref.available()
+    except Exception:
+        return False
+
+
 def run_reference(args):
     from autonomouscar_b200 import PP_COLLISION_ORIENTED
     rank = int(os.environ.get("RANK", "0"))
@@ -141,28 +180,42 @@ def run_reference(args):
         return
     grid = make_grid()
     cores = os.cpu_count() or 1
-    # bounded sample: ~2^27 poses of CPU work for the whole run, whatever --steps is
-    n_sample = max(1 << 16, min(1 << 22, (1 << 27) // max(1, args.steps)))
+    have_ref = ref_available()
+    if have_ref:
+        # ~2^26 poses of CPU work for the whole run (the reference does ~1e5 poses/s per thread)
+        n_sample = max(1 << 14, min(1 << 20, (1 << 26) // max(1, args.steps)))
+        rc = ReferenceCollider(grid, cores)
+        one = lambda n: rc.rate(n)[0]                                              # noqa: E731
+        kind = "reference"
+        what = (f"{n_sample} of the 2^24 poses per step; the reference's own checkCollision/calcCollisionMatrix "
+                f"(local_planner.cpp:443-496 with the `return false;` of :445 dropped; axis-aligned box -- the "
+                f"reference has no oriented test), compiled from /root/reference with g++ -O2, one node instance "
+                f"per thread x{cores}")
+    else:
+        n_sample = max(1 << 16, min(1 << 22, (1 << 27) // max(1, args.steps)))
+        one = lambda n: cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n, cores)[0]  # noqa: E731
+        kind = "port"
+        what = f"{n_sample} of the 2^24 poses per step, oracle ORIENTED, std::thread x{cores}, g++ -O2"
     rates = []
     for _ in range(args.warmup):
-        cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 18, cores)
+        one(1 << 16)
     t0 = time.time()
     for _ in range(args.steps):
-        r, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n_sample, cores)
-        rates.append(r)
+        rates.append(one(n_sample))
     wall = time.time() - t0
     v = sum(rates) / len(rates)
+    port_v, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 21, cores)
     line = {
         "impl": "reference", "metric": "collision_checks_per_sec", "value": v, "unit": "poses/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32 fixed-point Q7.24 + f64 set-up", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: oriented-footprint poses vs 4096x4096 grid @0.1 m, "
+        "vs_baseline": None, "dtype": "f64 -> int cells", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: footprint poses vs 4096x4096 grid @0.1 m, "
                                "1% area in 16x16-cell blocks", "poses_per_step": n_sample,
-                   "collision_mode": "ORIENTED"},
-        "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} of the 2^24 poses per step, std::thread x{cores}, g++ -O2"},
+                   "collision_mode": "REF_AABB (reference code)" if have_ref else "ORIENTED (oracle port)"},
+        "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extra": {"oracle_port_oriented_poses_per_s": port_v, "oracle_port_cores": cores},
     }
     print(json.dumps(line), flush=True)
 
@@ -323,12 +376,27 @@ def run_ours(args):
         cpu = None
         if not args.skip_cpu:
             cores = os.cpu_count() or 1
-            n_sample = 1 << 22
-            v, secs = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n_sample, cores)
+            v_port, secs_port = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 22, cores)
             v1, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 20, 1)
-            cpu = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
-                   "sample": f"{n_sample} of the 2^24 poses ({secs:.2f} s), oracle ORIENTED, std::thread x{cores}, "
-                             f"g++ -O2; single thread: {v1:.3e} poses/s"}
+            port_txt = (f"oracle port, ORIENTED, same poses: {v_port:.3e} poses/s on {cores} threads, "
+                        f"{v1:.3e} on 1 thread (g++ -O2)")
+            if ref_available():
+                n_sample = 1 << 22
+                rc = ReferenceCollider(grid, cores)
+                rc.rate(1 << 16)
+                v, secs = rc.rate(n_sample)
+                rc.close()
+                rc1 = ReferenceCollider(grid, 1)
+                v_1, _ = rc1.rate(1 << 17)
+                rc1.close()
+                cpu = {"value": v, "unit": "poses/s", "cores": cores, "kind": "reference",
+                       "sample": f"{n_sample} of the 2^24 poses ({secs:.2f} s wall): the reference's own checkCollision "
+                                 f"(local_planner.cpp:443-496, axis-aligned box; it has no oriented test) compiled from "
+                                 f"the reference sources, g++ -O2, one node instance per thread x{cores}; "
+                                 f"1 thread: {v_1:.3e} poses/s. " + port_txt}
+            else:
+                cpu = {"value": v_port, "unit": "poses/s", "cores": cores, "kind": "port",
+                       "sample": f"{1 << 22} of the 2^24 poses ({secs_port:.2f} s). " + port_txt}
         line = {
             "metric": "collision_checks_per_sec", "value": value, "unit": "poses/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -486,6 +554,36 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
             mine = rec[:nq].cpu().numpy()
             out["parity_sample_ok"] = bool((mine[:, 0] == st2).all() and (mine[:, 2] == nn2).all() and
                                            (mine[:, 4] == (dg2 & np.uint64(0x7FFFFFFFFFFFFFFF)).astype(np.int64)).all())
+            if ref_available():
+                # the reference node itself (oracle/_ref), REF_AABB = its own collision code enabled:
+                # same queries through the CUDA path in that mode and through the reference binary
+                from autonomouscar_b200 import PP_COLLISION_REF_AABB
+                from oracle import ref_binding as ref
+                p_a = default_params(collision_mode=PP_COLLISION_REF_AABB, max_nodes=10000)
+                pl_a = Planner(p_a, device=dev.index)
+                pl_a.set_grid(grid)
+                qa = qs_all[:nq]
+                qa_arr = (pp_query * nq)(*qa)
+                buf_a = PlanBatch(nq, cap_path=256)
+                pl_a.plan_batch_into(qa_arr, buf_a)
+                t1 = time.perf_counter()
+                pl_a.plan_batch_into(qa_arr, buf_a)
+                gpu_dt = time.perf_counter() - t1
+                pool = ref.RefPool(p_a, grid_as_msg(grid), cores, ref.AABB)
+                r_secs, r_st, r_nn = pool.plan_batch(qa)
+                pool.close()
+                pool1 = ref.RefPool(p_a, grid_as_msg(grid), 1, ref.AABB)
+                r1_secs, _, _ = pool1.plan_batch(qa[:32])
+                pool1.close()
+                g_rec = buf_a.records()
+                out["reference_node"] = {
+                    "what": "Prius::LocalPlanner compiled from the reference sources (oracle/_ref), collision code "
+                            "of LP:446-496 enabled, one node instance per thread; same queries on the GPU in REF_AABB mode",
+                    "queries": nq, "cpu_plans_per_s": nq / r_secs, "cpu_cores": cores,
+                    "cpu_plans_per_s_1thread": 32 / r1_secs, "gpu_plans_per_s_same_queries": nq / gpu_dt,
+                    "same_outcome_and_tree_size_as_reference": bool(((g_rec[:, 0] != 0) == (r_st != 0)).all()
+                                                                    and (g_rec[:, 2] == r_nn).all())}
+                pl_a.close()
     pl.close()
     rpl.close()
     return out

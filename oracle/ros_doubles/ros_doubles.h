@@ -1,0 +1,180 @@
+// TEST INFRASTRUCTURE -- header-only TEST DOUBLES of the handful of ROS types the reference's
+// nodes touch (roscpp, tf, message structs).  Written for this repo; nothing here is ROS
+// source.  Purpose: let oracle/Makefile compile the reference's own .cpp files UNMODIFIED,
+// from where they lie under /root/reference, into oracle/_ref/ so that the CPU oracle (and
+// through it the CUDA path) is pinned against the reference's real code instead of only a
+// restatement of it.  The doubles carry data and nothing else:
+//   * messages are plain structs with the fields of the .msg definitions;
+//   * NodeHandle::getParam reads a thread-local name -> double table the harness fills;
+//   * Publisher::publish appends a copy of the message to a thread-local capture list;
+//   * ros::Time::now() is a deterministic tick counter (the harness turns the reference's
+//     1 s wall-clock guard, local_planner.cpp:33-39, into an expansion / node cap with it);
+//   * tf lookups return transforms the harness registered.
+// All arithmetic of the path stays in the reference's own translation unit + libm + libstdc++.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ros_doubles {
+
+struct State {
+  std::map<std::string, double> params;
+  // clock: now() returns `ticks`, then advances it by one; toSec() = ticks * sec_per_tick.
+  int64_t ticks = 0;
+  double ticks_per_sec = 1e18;      // "never times out" until the harness says otherwise
+  std::function<bool()> force_timeout;  // optional: when it returns true, now() jumps far ahead
+  bool quiet = true;
+};
+inline State& state() { thread_local State s; return s; }
+
+template <class T>
+inline std::vector<T>& captured() { thread_local std::vector<T> v; return v; }
+
+}  // namespace ros_doubles
+
+namespace ros {
+
+struct Duration {
+  double sec = 0;
+  Duration() {}
+  explicit Duration(double s) : sec(s) {}
+  double toSec() const { return sec; }
+  bool sleep() const { return true; }
+};
+
+struct Time {
+  int64_t ticks = 0;
+  bool forced = false;
+  Time() {}
+  explicit Time(double) {}
+  static Time now() {
+    ros_doubles::State& s = ros_doubles::state();
+    Time t;
+    t.ticks = s.ticks++;
+    t.forced = s.force_timeout && s.force_timeout();
+    return t;
+  }
+  double toSec() const { return static_cast<double>(ticks) / ros_doubles::state().ticks_per_sec; }
+};
+inline Duration operator-(const Time& a, const Time& b) {
+  if (a.forced) return Duration(1e9);
+  return Duration(static_cast<double>(a.ticks - b.ticks) / ros_doubles::state().ticks_per_sec);
+}
+
+struct Subscriber {};
+struct Publisher {
+  template <class M>
+  void publish(const M& m) const { ros_doubles::captured<M>().push_back(m); }
+};
+
+class NodeHandle {
+ public:
+  NodeHandle() {}
+  explicit NodeHandle(const std::string&) {}
+  template <class M, class T>
+  Subscriber subscribe(const std::string&, uint32_t, void (T::*)(const std::shared_ptr<const M>&), T*) {
+    return Subscriber();
+  }
+  template <class M>
+  Publisher advertise(const std::string&, uint32_t, bool = false) { return Publisher(); }
+  // names are looked up by their last path component as well, so "~name" and "/node/name" agree
+  bool getParam(const std::string& name, double& out) const {
+    const auto& p = ros_doubles::state().params;
+    auto it = p.find(name);
+    if (it == p.end()) {
+      const size_t k = name.rfind('/');
+      if (k != std::string::npos) it = p.find(name.substr(k + 1));
+    }
+    if (it == p.end()) return false;
+    out = it->second;
+    return true;
+  }
+  bool getParam(const std::string& name, std::string& out) const {
+    (void)name; out.clear(); return false;
+  }
+};
+
+inline void init(int&, char**, const std::string&) {}
+inline bool ok() { return false; }
+inline void spin() {}
+inline void spinOnce() {}
+
+}  // namespace ros
+
+#define ROS_DOUBLES_LOG(tag, expr)                                   \
+  do {                                                               \
+    if (!ros_doubles::state().quiet) {                               \
+      std::ostringstream ros_doubles_ss;                             \
+      ros_doubles_ss << expr;                                        \
+      std::fprintf(stderr, "[%s] %s\n", tag, ros_doubles_ss.str().c_str()); \
+    }                                                                \
+  } while (0)
+#define ROS_INFO_STREAM(expr) ROS_DOUBLES_LOG("INFO", expr)
+#define ROS_WARN_STREAM(expr) ROS_DOUBLES_LOG("WARN", expr)
+#define ROS_ERROR_STREAM(expr) ROS_DOUBLES_LOG("ERROR", expr)
+#define ROS_INFO(...) do { if (!ros_doubles::state().quiet) { std::fprintf(stderr, __VA_ARGS__); std::fputc('\n', stderr); } } while (0)
+#define ROS_WARN(...) ROS_INFO(__VA_ARGS__)
+#define ROS_ERROR(...) ROS_INFO(__VA_ARGS__)
+
+// ---- message structs (fields of the .msg files; float64 -> double, int8[] -> vector<int8_t>)
+namespace std_msgs {
+struct Header { uint32_t seq = 0; ros::Time stamp; std::string frame_id; };
+}
+namespace geometry_msgs {
+struct Vector3 { double x = 0, y = 0, z = 0; };
+struct Point { double x = 0, y = 0, z = 0; };
+struct Point32 { float x = 0, y = 0, z = 0; };
+struct Quaternion { double x = 0, y = 0, z = 0, w = 0; };
+struct Pose { Point position; Quaternion orientation; };
+struct Twist { Vector3 linear, angular; };
+struct PoseStamped { std_msgs::Header header; Pose pose; };
+}
+namespace nav_msgs {
+struct MapMetaData { ros::Time map_load_time; float resolution = 0; uint32_t width = 0, height = 0; geometry_msgs::Pose origin; };
+struct OccupancyGrid {
+  std_msgs::Header header; MapMetaData info; std::vector<int8_t> data;
+  typedef std::shared_ptr<const OccupancyGrid> ConstPtr;
+};
+struct Path {
+  std_msgs::Header header; std::vector<geometry_msgs::PoseStamped> poses;
+  typedef std::shared_ptr<const Path> ConstPtr;
+};
+}
+namespace gazebo_msgs {
+struct ModelStates {
+  std::vector<std::string> name; std::vector<geometry_msgs::Pose> pose; std::vector<geometry_msgs::Twist> twist;
+  typedef std::shared_ptr<const ModelStates> ConstPtr;
+};
+}
+namespace prius_msgs {
+struct LocalNav {   // prius_msgs/msg/LocalNav.msg
+  std_msgs::Header header; double x = 0, y = 0, speed = 0, max_speed = 0, max_accel = 0;
+  typedef std::shared_ptr<const LocalNav> ConstPtr;
+};
+struct MotionPlanning {   // prius_msgs/msg/MotionPlanning.msg
+  std_msgs::Header header; std::vector<double> yaw_rates, durations, speeds; double max_speed = 0, max_accel = 0;
+  typedef std::shared_ptr<const MotionPlanning> ConstPtr;
+};
+}
+namespace sensor_msgs {
+struct LaserScan {
+  std_msgs::Header header;
+  float angle_min = 0, angle_max = 0, angle_increment = 0, time_increment = 0, scan_time = 0, range_min = 0, range_max = 0;
+  std::vector<float> ranges, intensities;
+  typedef std::shared_ptr<const LaserScan> ConstPtr;
+};
+struct ChannelFloat32 { std::string name; std::vector<float> values; };
+struct PointCloud {
+  std_msgs::Header header; std::vector<geometry_msgs::Point32> points; std::vector<ChannelFloat32> channels;
+  typedef std::shared_ptr<const PointCloud> ConstPtr;
+};
+struct Range { std_msgs::Header header; float range = 0; typedef std::shared_ptr<const Range> ConstPtr; };
+}
