@@ -8,6 +8,8 @@
 //     interpolatePoints (edge spacing rule)   LP:301-316
 // plus the ORIENTED extension, whose arithmetic is specified here and
 // in DESIGN.md and must be reproduced bit for bit by the CUDA kernels.
+// Pinned: the grid flip and the REF_AABB booleans equal the reference binary's (oracle/_ref,
+// tests/test_ref_pin.py); ORIENTED has no reference counterpart and is pinned by its own spec.
 #pragma once
 #include <cmath>
 #include <cstdint>

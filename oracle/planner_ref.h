@@ -6,9 +6,11 @@
 // with ROS types replaced by plain structs and the 1 s ros::Time guard (LP:33-39) replaced
 // by expansion / node caps.  Every function names the reference lines it follows.
 //
-// PARITY UNPINNED: the reference has no tests, fixtures or golden vectors for this path
-// and cannot be compiled here (needs ROS), so nothing outside this restatement pins it.
-// What is pinned are hand-derived known answers from the cited lines (tests/test_oracle_*).
+// PINNED AGAINST THE REFERENCE ITSELF: oracle/_ref is the reference's own local_planner.cpp
+// compiled unmodified against ROS test doubles (oracle/Makefile, ref_planner_harness.cpp);
+// tests/test_ref_pin.py shows this restatement (LibmMath policy) equals it bit for bit -- open
+// and closed lists, path, profile, visited bitmap -- live and against tests/golden/ref_planner.npz.
+// (The reference ships no tests or golden vectors of its own.)
 //
 // Math policy `M`:
 //   LibmMath -- glibc sin/cos/atan2/pow, i.e. what the reference binary would call;
