@@ -32,13 +32,35 @@ struct State {
   double ticks_per_sec = 1e18;      // "never times out" until the harness says otherwise
   std::function<bool()> force_timeout;  // optional: when it returns true, now() jumps far ahead
   bool quiet = true;
+  std::function<void()> spin_script;    // what ros::spin() runs (the harness delivers messages from it)
 };
 inline State& state() { thread_local State s; return s; }
 
 template <class T>
 inline std::vector<T>& captured() { thread_local std::vector<T> v; return v; }
 
+// topic -> callbacks registered through NodeHandle::subscribe<M>
+template <class M>
+inline std::map<std::string, std::vector<std::function<void(const std::shared_ptr<const M>&)>>>& subscribers() {
+  thread_local std::map<std::string, std::vector<std::function<void(const std::shared_ptr<const M>&)>>> m;
+  return m;
+}
+// what a publisher on `topic` would cause: every subscriber's callback runs, in order
+template <class M>
+inline int deliver(const std::string& topic, const M& msg) {
+  auto it = subscribers<M>().find(topic);
+  if (it == subscribers<M>().end()) return 0;
+  auto ptr = std::make_shared<const M>(msg);
+  for (auto& cb : it->second) cb(ptr);
+  return static_cast<int>(it->second.size());
+}
+
 }  // namespace ros_doubles
+
+namespace boost {
+template <class S>
+using function = std::function<S>;
+}
 
 namespace ros {
 
@@ -80,7 +102,13 @@ class NodeHandle {
   NodeHandle() {}
   explicit NodeHandle(const std::string&) {}
   template <class M, class T>
-  Subscriber subscribe(const std::string&, uint32_t, void (T::*)(const std::shared_ptr<const M>&), T*) {
+  Subscriber subscribe(const std::string& topic, uint32_t, void (T::*fp)(const std::shared_ptr<const M>&), T* obj) {
+    ros_doubles::subscribers<M>()[topic].push_back([obj, fp](const std::shared_ptr<const M>& m) { (obj->*fp)(m); });
+    return Subscriber();
+  }
+  template <class M>
+  Subscriber subscribe(const std::string& topic, uint32_t, const std::function<void(const std::shared_ptr<const M>&)>& cb) {
+    ros_doubles::subscribers<M>()[topic].push_back(cb);
     return Subscriber();
   }
   template <class M>
@@ -97,6 +125,18 @@ class NodeHandle {
     out = it->second;
     return true;
   }
+  bool getParam(const std::string& name, int& out) const {
+    double d;
+    if (!getParam(name, d)) return false;
+    out = static_cast<int>(d);
+    return true;
+  }
+  template <class T>
+  bool param(const std::string& name, T& out, const T& fallback) const {
+    if (getParam(name, out)) return true;
+    out = fallback;
+    return false;
+  }
   bool getParam(const std::string& name, std::string& out) const {
     (void)name; out.clear(); return false;
   }
@@ -104,7 +144,7 @@ class NodeHandle {
 
 inline void init(int&, char**, const std::string&) {}
 inline bool ok() { return false; }
-inline void spin() {}
+inline void spin() { if (ros_doubles::state().spin_script) ros_doubles::state().spin_script(); }
 inline void spinOnce() {}
 
 }  // namespace ros

@@ -167,6 +167,13 @@ inline void register_transform(const std::string& target, const std::string& sou
   registry()[strip_slash(target) + "<-" + strip_slash(source)] = t;
 }
 
+// yaw of a rotation about z (what tf::getYaw returns for planar motion)
+inline double getYaw(const Quaternion& q) {
+  double roll, pitch, yaw;
+  Matrix3x3(q).getRPY(roll, pitch, yaw);
+  return yaw;
+}
+
 class TransformListener {
  public:
   bool canTransform(const std::string&, const std::string&, const ros::Time&) const { return true; }

@@ -1,0 +1,105 @@
+"""Row N1: ros/local_planner_b200_node.cpp -- the drop-in replacement of the
+reference executable -- is compiled UNCHANGED against the ROS test doubles (the same doubles
+the reference's own node is compiled against for oracle/_ref), fed a scripted sequence of
+/local_costmap, /gazebo/model_states and /local_nav_waypoints messages plus a map->base_link
+tf, and everything it publishes on /goal, /local_path and /mp is compared with what the
+REFERENCE NODE publishes for the same messages."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from autonomouscar_b200 import PP_COLLISION_AS_SHIPPED, PP_COLLISION_REF_AABB, default_params, make_query, worlds
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "test_ros_shim")
+    pkg = os.path.join(ROOT, "autonomouscar_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "oracle", "ros_doubles"),
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "host"),
+                           os.path.join(ROOT, "tests", "cpp", "test_ros_shim.cpp"), "-o", exe,
+                           "-L", pkg, "-lprius_planner_b200", f"-Wl,-rpath,{pkg}"])
+    return exe
+
+
+def _parse(text):
+    """-> list of dicts, one per delivered LocalNav."""
+    out, cur = [], None
+    for line in text.splitlines():
+        w = line.split()
+        if not w:
+            continue
+        if w[0] == "delivered":
+            cur = {"delivered": int(w[1])}
+            out.append(cur)
+        elif w[0] == "goal":
+            cur["goal"] = [(float.fromhex(w[2 + 3 * k]), float.fromhex(w[3 + 3 * k]), w[4 + 3 * k]) for k in range(int(w[1]))]
+        elif w[0] == "path":
+            cur["n_path_msgs"] = int(w[1])
+            if int(w[1]):
+                cur["path_frame"] = w[2]
+                v = [float.fromhex(x) for x in w[4:]]
+                cur["path"] = np.array(v).reshape(int(w[3]), 2)
+        elif w[0] == "mp":
+            cur["n_mp_msgs"] = int(w[1])
+            if int(w[1]):
+                cur["mp_max_speed"], cur["mp_max_accel"] = float.fromhex(w[2]), float.fromhex(w[3])
+                cur["mp"] = np.array([float.fromhex(x) for x in w[5:]]).reshape(int(w[4]), 3)
+    return out
+
+
+@pytest.mark.parametrize("mode", [PP_COLLISION_AS_SHIPPED, PP_COLLISION_REF_AABB])
+def test_ros_shim_publishes_what_the_reference_node_publishes(cuda_device, tmp_path, mode):
+    from oracle import ref_binding as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not present")
+    exe = _build(tmp_path)
+    p = default_params(collision_mode=mode, max_expansions=400, max_nodes=20000)
+    cs = worlds.block_grid(300, 300, frac=0.006, block=4, seed=5)
+    worlds.clear_disc(cs, p, 0.0, 0.0, 4.0)
+    msg = np.ascontiguousarray(cs.reshape(-1)[::-1])
+    gpath = str(tmp_path / "grid.bin")
+    msg.tofile(gpath)
+    # (tf base_link<-map x, y, yaw), twist, LocalNav in the MAP frame
+    steps = [((0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (20.0, 0.0, 1.5)),
+             ((-10.0, -12.0, 0.0), (0.6, 0.8, 0.0), (30.0, 12.0, 1.5)),
+             ((3.0, -2.0, 0.4), (1.2, 0.0, 0.0), (14.0, -3.0, 1.0)),
+             ((-50.0, 8.0, -0.9), (0.3, 0.1, 0.0), (40.0, 40.0, 1.5)),
+             ((0.0, 0.0, 0.0), (1.5, 0.0, 0.0), (2000.0, 0.0, 1.5))]      # far outside: expansion cap, nothing published
+    lines = [f"param local_costmap_res {p.costmap_res!r}", "param local_costmap_height 75", "param local_costmap_width 75",
+             f"param collision_mode {mode}", f"param max_expansions {p.max_expansions}", f"param max_nodes {p.max_nodes}",
+             f"grid {gpath} 300 300 0.25"]
+    for tfm, tw, nav in steps:
+        lines += ["tf %r %r %r" % tfm, "twist %r %r %r" % tw, "nav %r %r %r 1.5 1.5" % nav]
+    scen = tmp_path / "scenario.txt"
+    scen.write_text("\n".join(lines) + "\n")
+    got = _parse(subprocess.check_output([exe, str(scen)]).decode())
+    assert len(got) == len(steps) and all(g["delivered"] == 1 for g in got)
+
+    node = ref.RefNode(p, ref.AABB if mode == PP_COLLISION_REF_AABB else ref.SHIPPED)
+    node.set_grid_msg(msg)
+    n_found = 0
+    for (tfm, tw, nav), g in zip(steps, got):
+        node.set_base_from_map(*tfm)
+        q = make_query(nav[0], nav[1], goal_speed=nav[2], start_speed=float(np.sqrt(tw[0] ** 2 + tw[1] ** 2 + tw[2] ** 2)))
+        r = node.plan(q)
+        # /goal: published before the search, in base_link (LP:633-641)
+        assert len(g["goal"]) == 1 and g["goal"][0][2] == "base_link"
+        np.testing.assert_allclose(g["goal"][0][:2], r.goal, rtol=0, atol=1e-12)
+        if r.status != 0:          # LP:34-39: log, publish nothing
+            assert g["n_path_msgs"] == 0 and g["n_mp_msgs"] == 0
+            continue
+        n_found += 1
+        assert g["n_path_msgs"] == 1 and g["n_mp_msgs"] == 1 and g["path_frame"] == "base_link"
+        assert g["path"].shape == r.path_xy.shape and g["mp"].shape[0] == len(r.yaw_rates)
+        np.testing.assert_allclose(g["path"], r.path_xy, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(g["mp"][:, 0], r.yaw_rates, rtol=0, atol=1e-7)
+        np.testing.assert_array_equal(g["mp"][:, 1], r.durations)
+        np.testing.assert_array_equal(g["mp"][:, 2], r.speeds)
+        assert (g["mp_max_speed"], g["mp_max_accel"]) == (r.mp_max_speed, r.mp_max_accel)
+    assert n_found >= 2 and n_found < len(steps)
+    node.close()
