@@ -15,6 +15,9 @@ def __getattr__(name):
     if name in ("Planner", "PlannerError", "PlannerGroup"):
         from . import planner
         return getattr(planner, name)
+    if name == "LocalCostmap":
+        from . import costmap
+        return costmap.LocalCostmap
     if name == "LocalPlannerNode":
         from . import node
         return node.LocalPlannerNode

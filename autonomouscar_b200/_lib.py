@@ -8,6 +8,7 @@ import ctypes as C
 import os
 
 from .capi import pp_params, pp_query, pp_result
+from .costmap_capi import pc_inputs, pc_params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libprius_planner_b200.so")
@@ -21,6 +22,11 @@ EXPORTS = [
     "pp_rrt_plan_batch", "pp_get_visited", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
     "pp_last_narrow_count", "pp_bench_l2_gather", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
     "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch",
+]
+# every symbol include/prius_costmap.h declares (row N2)
+COSTMAP_EXPORTS = [
+    "pc_default_params", "pc_create", "pc_destroy", "pc_set_global_grid", "pc_build", "pc_grid_dev", "pc_stream",
+    "pc_launch_count", "pc_last_build_ms",
 ]
 
 _lib = None
@@ -39,7 +45,7 @@ def load():
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback.")
     L = C.CDLL(LIB_PATH)
-    missing = [s for s in EXPORTS if not hasattr(L, s)]
+    missing = [s for s in EXPORTS + COSTMAP_EXPORTS if not hasattr(L, s)]
     if missing:
         raise LibraryMissing(f"{LIB_PATH} lacks symbols {missing}")
     vp, i32, i64, u64, u32, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_float, C.c_double
@@ -78,6 +84,15 @@ def load():
     L.pp_group_set_grid.argtypes = [vp, vp, i32, i32, f64, C.c_int]
     L.pp_group_collide_batch.argtypes = [vp, i64, vp, vp]
     L.pp_group_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
+    L.pc_default_params.argtypes = [C.POINTER(pc_params)]
+    L.pc_create.argtypes = [C.POINTER(pc_params), C.c_int, C.POINTER(vp)]
+    L.pc_destroy.argtypes = [vp]
+    L.pc_set_global_grid.argtypes = [vp, vp, i64]
+    L.pc_build.argtypes = [vp, C.POINTER(pc_inputs), vp]
+    L.pc_grid_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
+    L.pc_stream.argtypes = [vp, C.POINTER(vp)]
+    L.pc_launch_count.argtypes = [vp, C.POINTER(u64)]
+    L.pc_last_build_ms.argtypes = [vp, C.POINTER(f32)]
     if L.pp_abi_version() != 1:
         raise LibraryMissing("ABI version mismatch")
     _lib = L

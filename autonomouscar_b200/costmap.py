@@ -1,0 +1,78 @@
+"""Python face of include/prius_costmap.h (row N2): the local costmap node's callbacks
+(local_costmap.cpp:360-385) on top of the C ABI.  Every computation is a call into
+libprius_planner_b200.so; numpy / torch only own memory."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .capi import PP_GRID_OCCUPANCY_MSG, PP_OK
+from .costmap_capi import default_costmap_params
+
+
+class LocalCostmap:
+    """One costmap builder on one GPU (pc_handle).  Method names follow the reference node:
+    globalCostmapCallback <- set_global_grid, centerLaserCallback -> pubOccGrid <- build."""
+
+    def __init__(self, params=None, device=0):
+        self._L = _lib.load()
+        self.params = params if params is not None else default_costmap_params()
+        self.device = int(device)
+        self._h = None
+        h = C.c_void_p()
+        self._check(self._L.pc_create(C.byref(self.params), self.device, C.byref(h)))
+        self._h = h
+        self.n_cells = int(self.params.height_cells * self.params.width_cells)
+
+    def _check(self, rc):
+        if rc != PP_OK:
+            from .planner import PlannerError
+            raise PlannerError(rc, self._L.pp_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self._L.pc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_global_grid(self, grid):
+        """globalCostmapCallback (LC:382-385); pass None / empty for "no global map yet"."""
+        if grid is None:
+            self._check(self._L.pc_set_global_grid(self._h, None, 0))
+            return
+        g = np.ascontiguousarray(grid, dtype=np.int8).ravel()
+        self._check(self._L.pc_set_global_grid(self._h, g.ctypes.data_as(C.c_void_p), g.size))
+
+    def build(self, scene, want_host=True):
+        """One calcOccGrid pass over `scene` (costmap_capi.CostmapScene).  Returns the int8 grid in
+        message order (numpy) or None when only the device grid is wanted."""
+        out = np.empty(self.n_cells, dtype=np.int8) if want_host else None
+        self._check(self._L.pc_build(self._h, C.byref(scene.inputs),
+                                     out.ctypes.data_as(C.c_void_p) if want_host else None))
+        return out
+
+    def grid_dev(self):
+        """(device pointer, width, height) of the most recent grid."""
+        p, w, h = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._check(self._L.pc_grid_dev(self._h, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    def feed_planner(self, planner):
+        """Hand the device grid to a Planner without leaving the GPU (/local_costmap -> costmapCallback)."""
+        p, w, h = self.grid_dev()
+        planner._check(planner._L.pp_set_grid_dev(planner._h, C.c_void_p(p), w, h, self.params.res, PP_GRID_OCCUPANCY_MSG))
+
+    def launch_count(self):
+        v = C.c_uint64()
+        self._check(self._L.pc_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def last_build_ms(self):
+        v = C.c_float()
+        self._check(self._L.pc_last_build_ms(self._h, C.byref(v)))
+        return v.value

@@ -1,0 +1,437 @@
+// pc_costmap.cu -- the local costmap builder on the device (include/prius_costmap.h, row N2).
+//
+// One calcOccGrid pass of catkin_ws/src/local_costmap/src/local_costmap.cpp ("LC"):
+//   clearMap LC:349-358 . mapPlanarScan x2 LC:82-156 . mapCenterScan LC:158-206 .
+//   inflateGrid LC:288-347 . mapRoadVectors LC:208-257 . calcGridLocation LC:259-265 .
+//   calcGlobalGridLocation LC:267-275 . calcCartesianCoords LC:277-286
+//
+// Why this parallelises exactly.  The reference writes its grid sequentially, but every write is
+// one of three monotone rules: an obstacle mark (100) always sticks, a free mark (0) never
+// overwrites 100 (LC:136, 149, 183, 199), unknown is -1; inflateGrid applies "reached by an
+// occupied cell" (100) after "reached by a free cell" (0) (LC:312-330); mapRoadVectors keeps the
+// larger of the cell and the global road cost (LC:250-254).  All of them are max-reductions over
+// {-1 < 0 < 1..99 < 100}, so the pass is five order-independent atomicMax sweeps over an int32
+// working grid -- bit-identical to the sequential result whatever the thread schedule.
+//
+// Arithmetic: the reference's doubles, operation for operation, through the individually rounded
+// helpers of pp_math.cuh (the library is built with -fmad=false); sin/cos/atan2 are the
+// deterministic ones shared with the oracle.
+//
+// Launch structure: inputs are packed into one pinned block (header | right ranges | left ranges |
+// cloud) and copied with ONE cudaMemcpyAsync; the six kernels have fixed arguments and fixed grids
+// (grid-stride loops over counts read from the device header), so the whole pass is one CUDA graph
+// launch.  Work is tiny (9.5 k rays, 90 k cells, 360 k road samples): the bound is launch latency
+// and FP64 issue, not memory.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "../../include/prius_costmap.h"
+#include "pp_common.cuh"
+#include "pp_math.cuh"
+
+namespace pp {
+
+struct PcDevHeader {
+  pc_params P;
+  // scans: 0 = right, 1 = left
+  int n_ray[2];
+  int ray_off[2];            // float offsets into the payload
+  float angle_min[2], angle_increment[2], range_max[2];
+  double roll[2], tf_x[2], tf_y[2], z_map[2], inv_x[2], inv_y[2];
+  int n_cloud;
+  int cloud_off;
+  double center_z;
+  double map_from_base[12];
+  double base_from_map[12];
+  long long global_len;      // 0 = no global grid (LC:210-213)
+};
+
+struct PcGeom {              // derived once per handle from pc_params, host side, plain double ops
+  int len;                   // int(H * W), LC:63
+  int h_int;                 // int(H), the divisor of LC:279
+  int nx, ny;                // int(H * 2), int(W * 2), LC:235-236
+};
+
+__device__ __forceinline__ bool pc_grid_location(const pc_params& P, double x, double y, int* loc) {
+  int wp, hp;
+  if (!dm::trunc_to_int(dm::add(dm::div(x, P.res), dm::div(P.width_cells, 2.0)), &wp)) return false;   // LC:261
+  if (!dm::trunc_to_int(dm::add(dm::div(y, P.res), dm::div(P.height_cells, 2.0)), &hp)) return false;  // LC:262
+  return dm::trunc_to_int(dm::sub(dm::add(static_cast<double>(wp), dm::mul(static_cast<double>(hp), P.width_cells)), 1.0),
+                          loc);                                                                         // LC:263
+}
+
+// ---- mapPlanarScan + mapCenterScan: one warp per ray / point --------------------------------
+__global__ void __launch_bounds__(256)
+pc_mark_kernel(const PcDevHeader* __restrict__ hdr, const float* __restrict__ payload, int* __restrict__ occ, int len) {
+  const PcDevHeader& H = *hdr;
+  const pc_params& P = H.P;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int total = H.n_ray[0] + H.n_ray[1] + H.n_cloud;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warps) {
+    double x, y, ca, sa;
+    int n = 0;
+    bool obstacle, clear_ray = true;
+    if (item < H.n_ray[0] + H.n_ray[1]) {
+      const int s = item < H.n_ray[0] ? 0 : 1;
+      const int i = item - (s ? H.n_ray[0] : 0);
+      const float r = payload[H.ray_off[s] + i];
+      if (r > H.range_max[s]) continue;                                                   // LC:111
+      const float anglef = __fadd_rn(H.angle_min[s], __fmul_rn(static_cast<float>(i), H.angle_increment[s]));  // LC:113
+      double sn, cs, sr, cr;
+      dm::sincos(static_cast<double>(anglef), &sn, &cs);
+      dm::sincos(H.roll[s], &sr, &cr);
+      const double rd = static_cast<double>(r);
+      const double A = dm::mul(dm::mul(rd, cs), cr), B = dm::mul(dm::mul(rd, sn), cr);
+      if (s == 0) { y = -dm::sub(A, H.tf_x[0]); x = dm::sub(B, H.tf_y[0]); }              // LC:117-118
+      else { y = dm::sub(A, H.tf_x[1]); x = -dm::sub(B, H.tf_y[1]); }                     // LC:123-124
+      const double max_range = fabs(dm::div(H.z_map[s], dm::div(sr, cr)));                // LC:127
+      obstacle = fabs(y) < max_range && rd > P.obstacle_range;                            // LC:129
+      const double dx = dm::sub(x, H.inv_x[s]), dy = dm::sub(y, H.inv_y[s]);
+      const double atb = dm::atan2_(dy, dx);                                              // LC:141
+      const double dist = sqrt(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));                // LC:142
+      if (!dm::trunc_to_int(dm::div(dist, P.res), &n)) n = 0;                             // LC:143
+      dm::sincos(atb, &sa, &ca);
+    } else {
+      const float* pt = payload + H.cloud_off + 3 * (item - H.n_ray[0] - H.n_ray[1]);
+      const float pxf = pt[0], pyf = pt[1], pzf = pt[2];
+      x = static_cast<double>(pxf); y = static_cast<double>(pyf);
+      const double dist = sqrt(dm::add(dm::mul(x, x), dm::mul(y, y)));                    // LC:175
+      const double thresh = dm::add(H.center_z, P.z_ground_buffer);
+      obstacle = static_cast<double>(pzf) > thresh && dist > P.obstacle_range;            // LC:176
+      const double atb = dm::atan2_(y, x);                                                // LC:188
+      if (!dm::trunc_to_int(dm::div(dist, P.res), &n)) n = 0;                             // LC:190
+      clear_ray = (pzf == 0.0f ? 1.0 : 0.0) > thresh;                                     // LC:194: `!pt.z > ...`
+      dm::sincos(atb, &sa, &ca);
+    }
+    if (lane == 0) {
+      int loc;
+      if (pc_grid_location(P, x, y, &loc) && loc >= 0 && loc < len) atomicMax(&occ[loc], obstacle ? 100 : 0);
+    }
+    if (!clear_ray) continue;
+    for (int k = 1 + lane; k < n; k += 32) {                                              // LC:144-153, 192-203
+      const double step = dm::mul(static_cast<double>(k), P.res);
+      const double x_ = dm::sub(x, dm::mul(step, ca)), y_ = dm::sub(y, dm::mul(step, sa));
+      int loc;
+      if (pc_grid_location(P, x_, y_, &loc) && loc >= 0 && loc < len) atomicMax(&occ[loc], 0);
+    }
+  }
+}
+
+// ---- inflateGrid (LC:288-325): one thread per source cell ------------------------------------
+__global__ void __launch_bounds__(256)
+pc_inflate_kernel(const PcDevHeader* __restrict__ hdr, const int* __restrict__ occ, int* __restrict__ infl, PcGeom G) {
+  const pc_params& P = hdr->P;
+  const double max_dist = sqrt(dm::add(dm::mul(dm::mul(P.height_cells, P.res), dm::mul(P.height_cells, P.res)),
+                                       dm::mul(dm::mul(P.width_cells, P.res), dm::mul(P.width_cells, P.res))));  // LC:298
+  for (int count = blockIdx.x * blockDim.x + threadIdx.x; count < G.len; count += gridDim.x * blockDim.x) {
+    const int pt = occ[count];
+    if (pt != 0 && pt != 100) continue;        // only free / occupied cells write anything (LC:312-320)
+    const int hp = count / G.h_int, wp = count % G.h_int;                                  // LC:279-281
+    const double x = dm::mul(dm::sub(static_cast<double>(wp), dm::div(P.width_cells, 2.0)), P.res);
+    const double y = dm::mul(dm::sub(static_cast<double>(hp), dm::div(P.height_cells, 2.0)), P.res);
+    const double d = sqrt(dm::add(dm::mul(x, x), dm::mul(y, y)));                          // LC:297
+    const double q = dm::div(d, max_dist);
+    const double rad = dm::mul(dm::mul(q, q), P.max_inflation_radius);                     // LC:299
+    const double num = dm::div(rad, P.res);                                                // LC:300
+    const double angle_inc = dm::div(6.283185307179586, num);                              // 2 * M_PI / num
+    for (int i = 0; static_cast<double>(i) < num; ++i) {
+      double s, c;
+      dm::sincos(dm::mul(static_cast<double>(i), angle_inc), &s, &c);
+      for (int j = 0; static_cast<double>(j) < num; ++j) {
+        const double t = dm::mul(dm::div(static_cast<double>(j), num), rad);
+        const double x_ = dm::add(x, dm::mul(t, c)), y_ = dm::add(y, dm::mul(t, s));      // LC:307-308
+        int loc;
+        if (!pc_grid_location(P, x_, y_, &loc)) continue;
+        if (loc >= 0 && loc < G.len) atomicMax(&infl[loc], pt);                            // LC:310-320, 327-330
+      }
+    }
+  }
+}
+
+// ---- LC:332-346: inflated 0 / 100 replace the cell --------------------------------------------
+__global__ void pc_merge_kernel(int* __restrict__ occ, const int* __restrict__ infl, int len) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
+    const int v = infl[k];
+    if (v == 100 || v == 0) occ[k] = v;
+  }
+}
+
+__device__ __forceinline__ void pc_apply(const double* m, double x, double y, double* ox, double* oy) {
+  // tf::Transform * Vector3(x, y, 0): row . v + origin, left to right
+  *ox = dm::add(dm::add(dm::add(dm::mul(m[0], x), dm::mul(m[1], y)), dm::mul(m[2], 0.0)), m[3]);
+  *oy = dm::add(dm::add(dm::add(dm::mul(m[4], x), dm::mul(m[5], y)), dm::mul(m[6], 0.0)), m[7]);
+}
+
+// ---- mapRoadVectors (LC:208-257): one thread per sample of the 2H x 2W lattice -----------------
+__global__ void __launch_bounds__(256)
+pc_roads_kernel(const PcDevHeader* __restrict__ hdr, const int8_t* __restrict__ global_grid, int* __restrict__ occ, PcGeom G) {
+  const PcDevHeader& H = *hdr;
+  const pc_params& P = H.P;
+  if (H.global_len < 1) return;                                                            // LC:210-213
+  const double total_x = dm::mul(P.height_cells, P.res), total_y = dm::mul(P.width_cells, P.res);
+  const double min_x = dm::div(-total_x, 2.0), min_y = dm::div(-total_y, 2.0);
+  const long long total = static_cast<long long>(G.nx) * G.ny;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(t / G.ny), j = static_cast<int>(t % G.ny);
+    const double ux = dm::add(min_x, dm::mul(dm::div(static_cast<double>(i), static_cast<double>(G.nx)), total_x));  // LC:242
+    const double uy = dm::add(min_y, dm::mul(dm::div(static_cast<double>(j), static_cast<double>(G.ny)), total_y));  // LC:243
+    double gx, gy, lx, ly;
+    pc_apply(H.map_from_base, ux, uy, &gx, &gy);                                           // LC:244
+    int cx, cy, wpos, hpos, gloc;                                                          // LC:269-273
+    if (!dm::trunc_to_int(dm::sub(dm::div(P.global_height_cells, 2.0), dm::div(gx, P.res)), &cx)) continue;
+    if (!dm::trunc_to_int(dm::sub(dm::div(P.global_width_cells, 2.0), dm::div(gy, P.res)), &cy)) continue;
+    if (!dm::trunc_to_int(dm::sub(P.global_width_cells, static_cast<double>(cy)), &wpos)) continue;
+    if (!dm::trunc_to_int(dm::sub(P.global_height_cells, static_cast<double>(cx)), &hpos)) continue;
+    if (!dm::trunc_to_int(dm::add(static_cast<double>(hpos), dm::mul(static_cast<double>(wpos), P.global_height_cells)), &gloc)) continue;
+    if (gloc < 0 || gloc >= H.global_len) continue;
+    pc_apply(H.base_from_map, gx, gy, &lx, &ly);                                           // LC:248
+    int lloc;
+    if (!pc_grid_location(P, lx, ly, &lloc) || lloc < 0 || lloc >= G.len) continue;
+    atomicMax(&occ[lloc], static_cast<int>(__ldg(&global_grid[gloc])));                    // LC:250-254
+  }
+}
+
+__global__ void pc_pack_kernel(const int* __restrict__ occ, int8_t* __restrict__ out, int len) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x)
+    out[k] = static_cast<int8_t>(occ[k]);
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+struct pc_handle {
+  pc_params P;
+  PcGeom G;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int* d_work = nullptr;            // occ | infl, 2 * len int32
+  int8_t* d_out = nullptr;          // len int8 (message order)
+  int8_t* h_out = nullptr;          // pinned mirror
+  int8_t* d_global = nullptr;
+  long long global_len = 0;
+  unsigned char* h_in = nullptr;    // pinned: PcDevHeader | payload floats
+  unsigned char* d_in = nullptr;
+  size_t in_cap = 0;                // bytes
+  cudaGraphExec_t graph = nullptr;
+  uint64_t launches = 0;
+  float last_ms = 0;
+};
+
+namespace {
+
+constexpr size_t kHdrBytes = (sizeof(PcDevHeader) + 255) & ~size_t(255);
+
+int ensure_input(pc_handle* h, size_t bytes) {
+  if (bytes <= h->in_cap) return PP_OK;
+  size_t cap = 1 << 20;
+  while (cap < bytes) cap <<= 1;
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }   // d_in moves: re-capture
+  cudaFreeHost(h->h_in); cudaFree(h->d_in);
+  h->h_in = nullptr; h->d_in = nullptr; h->in_cap = 0;
+  PP_CUDA(cudaMallocHost(&h->h_in, cap));
+  PP_CUDA(cudaMalloc(&h->d_in, cap));
+  h->in_cap = cap;
+  return PP_OK;
+}
+
+// the six launches of one pass, on `s` (captured into a graph by the caller)
+void launch_pass(pc_handle* h, cudaStream_t s) {
+  const int len = h->G.len;
+  int* occ = h->d_work;
+  int* infl = h->d_work + len;
+  const PcDevHeader* hdr = reinterpret_cast<const PcDevHeader*>(h->d_in);
+  const float* payload = reinterpret_cast<const float*>(h->d_in + kHdrBytes);
+  const int T = 256;
+  const int cell_blocks = std::min((len + T - 1) / T, h->sm_count * 8);
+  cudaMemsetAsync(h->d_work, 0xFF, sizeof(int) * 2 * static_cast<size_t>(len), s);               // clearMap: -1
+  pc_mark_kernel<<<h->sm_count * 8, T, 0, s>>>(hdr, payload, occ, len);
+  pc_inflate_kernel<<<cell_blocks, T, 0, s>>>(hdr, occ, infl, h->G);
+  pc_merge_kernel<<<cell_blocks, T, 0, s>>>(occ, infl, len);
+  if (h->d_global) {
+    const long long samples = static_cast<long long>(h->G.nx) * h->G.ny;
+    const int road_blocks = static_cast<int>(std::min<long long>((samples + T - 1) / T, h->sm_count * 16));
+    pc_roads_kernel<<<road_blocks, T, 0, s>>>(hdr, h->d_global, occ, h->G);
+  }
+  pc_pack_kernel<<<cell_blocks, T, 0, s>>>(occ, h->d_out, len);
+}
+
+int capture(pc_handle* h) {
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  cudaGraph_t g = nullptr;
+  PP_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  launch_pass(h, h->stream);
+  PP_CUDA(cudaStreamEndCapture(h->stream, &g));
+  PP_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+  cudaGraphDestroy(g);
+  return PP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pc_default_params(pc_params* p) {
+  if (!p) return PP_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->res = 0.25;                       // full_sim.launch:77
+  p->height_cells = 75 / 0.25;         // :78, LC:20
+  p->width_cells = 75 / 0.25;          // :79, LC:21
+  p->z_ground_buffer = 0.075;          // :80
+  p->obstacle_range = 2;               // :81
+  p->max_inflation_radius = 5;         // :82
+  p->global_height_cells = 3000 / 0.25;  // :71, LC:25
+  p->global_width_cells = 3000 / 0.25;   // :72, LC:26
+  return PP_OK;
+}
+
+int pc_create(const pc_params* params, int device, pc_handle** out) {
+  if (!params || !out) { set_last_error("pc_create: null argument"); return PP_ERR_INVALID; }
+  *out = nullptr;
+  PP_REQUIRE(params->res > 0, "pc_create: res must be > 0");
+  PP_REQUIRE(params->height_cells >= 1 && params->width_cells >= 1, "pc_create: empty grid");
+  PP_REQUIRE(params->height_cells <= 16384 && params->width_cells <= 16384, "pc_create: grid too large");
+  PP_REQUIRE(params->global_height_cells >= 0 && params->global_width_cells >= 0 &&
+             params->global_height_cells * params->global_width_cells < 1073741824.0, "pc_create: global grid too large");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_last_error(std::string("pc_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    return PP_ERR_CUDA;
+  }
+  PP_REQUIRE(device >= 0 && device < n_dev, "pc_create: bad device index");
+  PP_CUDA(cudaSetDevice(device));
+  pc_handle* h = new pc_handle();
+  h->P = *params;
+  h->device = device;
+  h->G.len = static_cast<int>(params->height_cells * params->width_cells);   // LC:63
+  h->G.h_int = static_cast<int>(params->height_cells);                        // LC:279
+  h->G.nx = static_cast<int>(params->height_cells * 2);                       // LC:235
+  h->G.ny = static_cast<int>(params->width_cells * 2);                        // LC:236
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  auto fail = [&](int rc) { pc_destroy(h); return rc; };
+#define PC_TRY(expr) do { if ((expr) != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(cudaGetLastError())); return fail(PP_ERR_CUDA); } } while (0)
+  PC_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  PC_TRY(cudaEventCreate(&h->ev0));
+  PC_TRY(cudaEventCreate(&h->ev1));
+  PC_TRY(cudaMalloc(&h->d_work, sizeof(int) * 2 * static_cast<size_t>(h->G.len)));
+  PC_TRY(cudaMalloc(&h->d_out, static_cast<size_t>(h->G.len)));
+  PC_TRY(cudaMallocHost(&h->h_out, static_cast<size_t>(h->G.len)));
+#undef PC_TRY
+  *out = h;
+  return PP_OK;
+}
+
+int pc_destroy(pc_handle* h) {
+  if (!h) return PP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  cudaFree(h->d_work); cudaFree(h->d_out); cudaFree(h->d_global); cudaFree(h->d_in);
+  cudaFreeHost(h->h_out); cudaFreeHost(h->h_in);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return PP_OK;
+}
+
+int pc_set_global_grid(pc_handle* h, const int8_t* data_host, int64_t len) {
+  if (!h) { set_last_error("pc_set_global_grid: null handle"); return PP_ERR_INVALID; }
+  PP_REQUIRE(len >= 0 && (len == 0 || data_host), "pc_set_global_grid: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  cudaFree(h->d_global);
+  h->d_global = nullptr;
+  h->global_len = 0;
+  if (len > 0) {
+    PP_CUDA(cudaMalloc(&h->d_global, static_cast<size_t>(len)));
+    PP_CUDA(cudaMemcpyAsync(h->d_global, data_host, static_cast<size_t>(len), cudaMemcpyHostToDevice, h->stream));
+    PP_CUDA(cudaStreamSynchronize(h->stream));
+    h->global_len = len;
+  }
+  return PP_OK;
+}
+
+int pc_build(pc_handle* h, const pc_inputs* in, int8_t* out_host) {
+  if (!h || !in) { set_last_error("pc_build: null argument"); return PP_ERR_INVALID; }
+  const pc_planar_scan* scans[2] = {&in->right, &in->left};
+  int n_ray[2];
+  for (int s = 0; s < 2; ++s) {
+    n_ray[s] = scans[s]->ranges ? scans[s]->n : 0;
+    PP_REQUIRE(n_ray[s] >= 0 && n_ray[s] <= (1 << 22), "pc_build: bad scan size");
+  }
+  const int n_cloud = in->cloud_xyz ? in->n_cloud : 0;
+  PP_REQUIRE(n_cloud >= 0 && n_cloud <= (1 << 24), "pc_build: bad cloud size");
+  PP_CUDA(cudaSetDevice(h->device));
+  const size_t n_float = static_cast<size_t>(n_ray[0]) + n_ray[1] + 3 * static_cast<size_t>(n_cloud);
+  const size_t bytes = kHdrBytes + sizeof(float) * n_float;
+  int rc = ensure_input(h, bytes);
+  if (rc) return rc;
+  PcDevHeader* hd = reinterpret_cast<PcDevHeader*>(h->h_in);
+  float* payload = reinterpret_cast<float*>(h->h_in + kHdrBytes);
+  hd->P = h->P;
+  int off = 0;
+  for (int s = 0; s < 2; ++s) {
+    hd->n_ray[s] = n_ray[s];
+    hd->ray_off[s] = off;
+    if (n_ray[s]) std::memcpy(payload + off, scans[s]->ranges, sizeof(float) * n_ray[s]);
+    off += n_ray[s];
+    hd->angle_min[s] = scans[s]->angle_min; hd->angle_increment[s] = scans[s]->angle_increment;
+    hd->range_max[s] = scans[s]->range_max;
+    hd->roll[s] = scans[s]->roll; hd->tf_x[s] = scans[s]->tf_x; hd->tf_y[s] = scans[s]->tf_y;
+    hd->z_map[s] = scans[s]->z_map; hd->inv_x[s] = scans[s]->inv_x; hd->inv_y[s] = scans[s]->inv_y;
+  }
+  hd->n_cloud = n_cloud;
+  hd->cloud_off = off;
+  if (n_cloud) std::memcpy(payload + off, in->cloud_xyz, sizeof(float) * 3 * static_cast<size_t>(n_cloud));
+  hd->center_z = in->center_z;
+  std::memcpy(hd->map_from_base, in->map_from_base, sizeof(hd->map_from_base));
+  std::memcpy(hd->base_from_map, in->base_from_map, sizeof(hd->base_from_map));
+  hd->global_len = h->d_global ? h->global_len : 0;
+
+  if (!h->graph) { rc = capture(h); if (rc) return rc; }
+  PP_CUDA(cudaEventRecord(h->ev0, h->stream));
+  PP_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
+  PP_CUDA(cudaGraphLaunch(h->graph, h->stream));
+  h->launches += h->d_global ? 5 : 4;
+  PP_CUDA(cudaEventRecord(h->ev1, h->stream));
+  if (out_host) PP_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, static_cast<size_t>(h->G.len), cudaMemcpyDeviceToHost, h->stream));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  if (out_host) std::memcpy(out_host, h->h_out, static_cast<size_t>(h->G.len));
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return PP_OK;
+}
+
+int pc_grid_dev(pc_handle* h, const int8_t** out_dev, int32_t* width, int32_t* height) {
+  if (!h || !out_dev) { set_last_error("pc_grid_dev: null argument"); return PP_ERR_INVALID; }
+  *out_dev = h->d_out;
+  if (width) *width = static_cast<int32_t>(h->P.width_cells);
+  if (height) *height = static_cast<int32_t>(h->P.height_cells);
+  return PP_OK;
+}
+
+int pc_stream(pc_handle* h, void** out_stream) {
+  if (!h || !out_stream) return PP_ERR_INVALID;
+  *out_stream = h->stream;
+  return PP_OK;
+}
+int pc_launch_count(const pc_handle* h, uint64_t* out) {
+  if (!h || !out) return PP_ERR_INVALID;
+  *out = h->launches;
+  return PP_OK;
+}
+int pc_last_build_ms(pc_handle* h, float* out_ms) {
+  if (!h || !out_ms) return PP_ERR_INVALID;
+  *out_ms = h->last_ms;
+  return PP_OK;
+}
+
+}  // extern "C"

@@ -116,3 +116,85 @@ def route_queries(spawn=(0.0, 15.0), lookahead=20.0, spacing=1.0):
         if np.hypot(x - spawn[0], y - spawn[1]) >= lookahead:
             return x - spawn[0], y - spawn[1]
     return pts[-1][0] - spawn[0], pts[-1][1] - spawn[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# local costmap scenes (row N2).  Synthetic stand-ins for what Gazebo would publish: two planar
+# 640-ray scans (prius.urdf:537-550, 569-582), one 16 x 512 block-laser cloud (prius.urdf:505-518)
+# and the tf frames local_costmap.cpp looks up.  Everything stays inside the 75 m window, because
+# the reference indexes its grid unchecked (see oracle/ref_costmap_harness.cpp).
+# ---------------------------------------------------------------------------------------------
+def costmap_tfs(car_x, car_y, car_yaw):
+    """(target, source) -> (x, y, z, roll, pitch, yaw) for every lookupTransform of local_costmap.cpp."""
+    c, s = np.cos(car_yaw), np.sin(car_yaw)
+    inv = (-(c * car_x + s * car_y), -(-s * car_x + c * car_y))
+    return {
+        ("base_link", "center_laser_link"): (0.4, 0.0, 1.8, 0.0, 0.0, 0.0),
+        ("front_right_laser_link", "center_laser_link"): (2.7, 1.0, 1.3, 0.05, 0.0, 0.0),
+        ("front_left_laser_link", "center_laser_link"): (2.7, -1.0, 1.3, 0.05, 0.0, 0.0),
+        ("map", "front_right_laser_link"): (car_x, car_y, 0.5, 0.0, 0.0, car_yaw),
+        ("map", "front_left_laser_link"): (car_x, car_y, 0.5, 0.0, 0.0, car_yaw),
+        ("center_laser_link", "map"): (inv[0], inv[1], -1.8, 0.0, 0.0, -car_yaw),
+        ("map", "base_link"): (car_x, car_y, 0.0, 0.0, 0.0, car_yaw),
+    }
+
+
+def costmap_scene(seed, n_planar=640, rings=16, per_ring=512, max_reach=29.0):
+    """Random but plausible sensor messages -> costmap_capi.CostmapScene (tf numbers NOT filled)."""
+    from .costmap_capi import CostmapScene
+    rng = np.random.default_rng(seed)
+    angle_min = np.float32(-2.26889)
+    angle_inc = np.float32((2.2689 + 2.26889) / (n_planar - 1))
+    range_max = np.float32(30.0)
+
+    def planar():
+        r = rng.uniform(0.4, max_reach, n_planar)
+        walls = rng.uniform(3.0, max_reach, 6)          # a few wall-like runs of similar range
+        for w in walls:
+            a = rng.integers(0, n_planar - 40)
+            r[a:a + 40] = w + rng.normal(0, 0.05, 40)
+        r[rng.random(n_planar) < 0.15] = 31.0           # no return: beyond range_max, skipped (LC:111)
+        return np.clip(r, 0.3, 31.0).astype(np.float32)
+
+    n = rings * per_ring
+    ang = np.tile(np.linspace(-3.14, 3.14, per_ring), rings)
+    rad = np.repeat(np.linspace(4.0, max_reach, rings), per_ring) + rng.normal(0, 0.05, n)
+    z = np.full(n, -1.8) + rng.normal(0, 0.01, n)       # ground returns
+    obs = rng.random(n) < 0.12
+    z[obs] = rng.uniform(-1.5, 0.6, obs.sum())          # above the ground buffer: obstacles
+    near = rng.random(n) < 0.03
+    rad[near] = rng.uniform(0.3, 2.0, near.sum())       # inside obstacle_range
+    z[rng.random(n) < 0.01] = 0.0                       # exercises the `!pt.z` quirk of LC:194
+    cloud = np.stack([rad * np.cos(ang), rad * np.sin(ang), z], 1).astype(np.float32)
+    return CostmapScene(planar(), planar(), cloud, (angle_min, angle_inc, range_max))
+
+
+def road_like_global_grid(cells, offset, zero_at=None):
+    """int8 [cells*cells] with values 0..99 in broad diagonal bands (what global_costmap.cpp's lane
+    profile looks like from far away) and 99 elsewhere; pure integer arithmetic, so the same
+    everywhere.  `zero_at` = flat indices forced to 0."""
+    i = np.arange(cells, dtype=np.int64)
+    band = (i[:, None] * 3 + i[None, :] * 2 + int(offset)) % 160
+    g = np.where(band < 100, band, 99).astype(np.int8)
+    g = g.reshape(-1)
+    if zero_at is not None:
+        g[np.asarray(zero_at, dtype=np.int64)] = 0
+    return g
+
+
+def costmap_corner_global_cells(params, car_x, car_y, car_yaw, halo=3):
+    """Flat global-grid indices around the map cell under the window's first road-overlay sample
+    (base_link (-H*res/2, -W*res/2)); its LOCAL index is -1 in the reference (LC:263), i.e. an
+    out-of-bounds write unless the global value there is 0 -- test scenes zero these cells."""
+    ux, uy = -params.height_cells * params.res / 2, -params.width_cells * params.res / 2
+    c, s = np.cos(car_yaw), np.sin(car_yaw)
+    gx, gy = c * ux - s * uy + car_x, s * ux + c * uy + car_y
+    hg, wg = int(params.global_height_cells), int(params.global_width_cells)
+    cx, cy = int(hg / 2 - gx / params.res), int(wg / 2 - gy / params.res)
+    out = []
+    for dx in range(-halo, halo + 1):
+        for dy in range(-halo, halo + 1):
+            loc = (hg - (cx + dx)) + (wg - (cy + dy)) * hg
+            if 0 <= loc < hg * wg:
+                out.append(loc)
+    return out

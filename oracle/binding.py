@@ -182,3 +182,14 @@ def rrt_plan(params, cspace, query, **caps):
     res.rc = lib().orc_rrt_plan(C.byref(params), None if g is None else _p(g, C.c_int8), C.byref(query),
                                 C.byref(res.raw))
     return res
+
+
+def costmap_build(params, scene_inputs, global_grid=None, math_mode=MATH_DET):
+    """One calcOccGrid pass (local_costmap.cpp:71-80) -> (int8 grid in message order, seconds)."""
+    lib().orc_costmap_build.restype = C.c_double
+    n = int(params.height_cells * params.width_cells)
+    out = np.zeros(n, dtype=np.int8)
+    g = None if global_grid is None else np.ascontiguousarray(global_grid, dtype=np.int8).ravel()
+    secs = lib().orc_costmap_build(C.byref(params), C.byref(scene_inputs), None if g is None else _p(g, C.c_int8),
+                                   C.c_int64(0 if g is None else g.size), math_mode, _p(out, C.c_int8))
+    return out, secs

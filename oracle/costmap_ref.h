@@ -8,7 +8,12 @@
 // with ROS / tf types replaced by plain numbers: every tf lookup of the reference becomes an
 // input field (the ROS shim reads them from tf), so no quaternion arithmetic happens here.
 //
-// PARITY UNPINNED by the reference (no tests, cannot be built without ROS).
+// PINNED AGAINST THE REFERENCE ITSELF: oracle/_ref/libref_costmap.so is the reference's own
+// local_costmap.cpp compiled unmodified against the ROS test doubles (ref_costmap_harness.cpp);
+// tests/test_costmap_ref_pin.py shows this restatement (LibmMath policy) gives the same grid byte
+// for byte.  The whole pass is order-independent (obstacle marks win over free marks win over
+// unknown; inflation and the road overlay are max-reductions), which is what lets the CUDA path
+// run it as parallel atomic-max passes.
 //
 // Defined behaviour where the reference has none: calcGridLocation results outside
 // [0, W*H) are ignored wherever the reference indexes without a check (LC:131-151, 178-201,
@@ -19,7 +24,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../include/prius_planner.h"
+#include "../include/prius_costmap.h"
 #include "det_math_ref.h"
 #include "planner_ref.h"   // LibmMath / DetMath, trunc_to_int
 
@@ -35,13 +40,15 @@ struct DetMathC : DetMath {
 template <class M>
 class RefCostmap {
  public:
-  explicit RefCostmap(const pp_costmap_params& p) : P(p) {
+  explicit RefCostmap(const pc_params& p) : P(p) {
     len_ = static_cast<int>(P.height_cells * P.width_cells);   // LC:63
   }
   int length() const { return len_; }
 
   // LC:71-80
-  void build(const pp_costmap_inputs& in, int8_t* out) {
+  void build(const pc_inputs& in, const int8_t* global_grid, int64_t global_len, int8_t* out) {
+    global_grid_ = global_grid;
+    global_len_ = global_len;
     occ_.assign(len_, -1);        // clearMap LC:349-358
     inflated_.assign(len_, -1);
     map_planar_scan(in.right, false);
@@ -68,7 +75,7 @@ class RefCostmap {
   void mark_free(int loc) { if (in_range(loc) && occ_[loc] != 100) occ_[loc] = 0; }
 
   // LC:82-156
-  void map_planar_scan(const pp_planar_scan& s, bool is_left) {
+  void map_planar_scan(const pc_planar_scan& s, bool is_left) {
     if (!s.ranges || s.n <= 0) return;
     for (int i = 0; i < s.n; ++i) {
       const float r = s.ranges[i];
@@ -103,7 +110,7 @@ class RefCostmap {
   }
 
   // LC:158-206
-  void map_center_scan(const pp_costmap_inputs& in) {
+  void map_center_scan(const pc_inputs& in) {
     for (int p = 0; p < in.n_cloud; ++p) {
       const float px = in.cloud_xyz[3 * p], py = in.cloud_xyz[3 * p + 1], pz = in.cloud_xyz[3 * p + 2];
       int loc;
@@ -168,8 +175,8 @@ class RefCostmap {
   }
 
   // LC:208-257
-  void map_road_vectors(const pp_costmap_inputs& in) {
-    if (!in.global_grid || in.global_len < 1) return;
+  void map_road_vectors(const pc_inputs& in) {
+    if (!global_grid_ || global_len_ < 1) return;                        // LC:210-213
     const double total_x = P.height_cells * P.res, total_y = P.width_cells * P.res;
     const double min_x = -total_x / 2, min_y = -total_y / 2;
     const int nx = static_cast<int>(P.height_cells * 2), ny = static_cast<int>(P.width_cells * 2);
@@ -186,18 +193,20 @@ class RefCostmap {
         if (!trunc_to_int(P.global_width_cells - cy, &wpos)) continue;
         if (!trunc_to_int(P.global_height_cells - cx, &hpos)) continue;
         if (!trunc_to_int(hpos + wpos * P.global_height_cells, &gloc)) continue;
-        if (gloc < 0 || gloc >= in.global_len) continue;
+        if (gloc < 0 || gloc >= global_len_) continue;
         apply(in.base_from_map, gx, gy, &lx, &ly);
         int lloc;
         if (!grid_location(lx, ly, &lloc) || !in_range(lloc)) continue;
-        if (occ_[lloc] > in.global_grid[gloc]) continue;
-        occ_[lloc] = in.global_grid[gloc];
+        if (occ_[lloc] > global_grid_[gloc]) continue;                   // LC:250-254
+        occ_[lloc] = global_grid_[gloc];
       }
     }
   }
 
-  pp_costmap_params P;
+  pc_params P;
   int len_;
+  const int8_t* global_grid_ = nullptr;
+  int64_t global_len_ = 0;
   std::vector<int8_t> occ_, inflated_;
 };
 

@@ -12,6 +12,7 @@
 
 #include "../include/prius_planner.h"
 #include "collision_ref.h"
+#include "costmap_ref.h"
 #include "philox_ref.h"
 #include "planner_ref.h"
 #include "sampling_ref.h"
@@ -277,6 +278,15 @@ int orc_rrt_plan(const pp_params* p, const int8_t* cspace, const pp_query* q, pp
   }
   if (r->n_path > r->cap_path && (r->path_xy || r->path_node_ids)) rc = PP_ERR_CAPACITY;
   return rc;
+}
+
+// local costmap (row N2): one calcOccGrid pass (LC:71-80).  Returns wall seconds of the pass.
+double orc_costmap_build(const pc_params* p, const pc_inputs* in, const int8_t* global_grid, int64_t global_len,
+                         int math_mode, int8_t* out) {
+  const auto t0 = std::chrono::steady_clock::now();
+  if (math_mode == 0) { RefCostmap<LibmMathC> c(*p); c.build(*in, global_grid, global_len, out); }
+  else { RefCostmap<DetMathC> c(*p); c.build(*in, global_grid, global_len, out); }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

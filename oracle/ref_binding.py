@@ -208,3 +208,75 @@ def oracle_lists(res):
     closed_ids = np.nonzero(cs >= 0)[0]
     closed_ids = closed_ids[np.argsort(cs[closed_ids], kind="stable")]
     return st[open_ids], st[closed_ids]
+
+
+# ---------------------------------------------------------------------------------------------
+# row N2: the reference's own local_costmap.cpp (oracle/_ref/libref_costmap.so)
+# ---------------------------------------------------------------------------------------------
+_costmap_lib = None
+
+
+def costmap_lib():
+    global _costmap_lib
+    if _costmap_lib is None:
+        build()
+        L = C.CDLL(os.path.join(_DIR, "libref_costmap.so"))
+        L.refc_create.restype = C.c_void_p
+        L.refc_build.restype = C.c_double
+        _costmap_lib = L
+    return _costmap_lib
+
+
+def costmap_available():
+    build()
+    return os.path.exists(os.path.join(_DIR, "libref_costmap.so"))
+
+
+def costmap_set_tfs(tfs):
+    """tfs: (target, source) -> (x, y, z, roll, pitch, yaw); registers them with the tf test double."""
+    L = costmap_lib()
+    for (target, source), v in tfs.items():
+        L.refc_set_tf(target.encode(), source.encode(), *[C.c_double(float(x)) for x in v])
+
+
+def costmap_derive_inputs(scene):
+    """Fill scene.inputs' tf-derived numbers with exactly what the reference node reads from tf."""
+    rc = costmap_lib().refc_derive_inputs(C.byref(scene.inputs))
+    assert rc == 0, "a tf frame is missing"
+
+
+class RefCostmap:
+    """One Prius::LocalCostmap instance of the reference.  Call costmap_set_tfs first."""
+
+    def __init__(self, params):
+        from autonomouscar_b200.costmap_capi import pc_params
+        self.h = None
+        self.L = costmap_lib()
+        self.h = C.c_void_p(self.L.refc_create(C.byref(params)))
+        if not self.h:
+            raise RuntimeError("refc_create failed")
+        self.params = pc_params()
+        self.L.refc_get_params(self.h, C.byref(self.params))
+
+    def close(self):
+        if self.h:
+            self.L.refc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_global(self, grid):
+        g = np.ascontiguousarray(grid, dtype=np.int8).ravel()
+        self.L.refc_set_global(self.h, _p(g, C.c_int8), C.c_int64(g.size))
+
+    def build(self, scene):
+        """right/left LaserScan + centre PointCloud -> the published /local_costmap data, seconds."""
+        am, ai, rm = scene.scan_meta
+        self.L.refc_set_scan(self.h, 0, _p(scene.right, C.c_float), len(scene.right), C.c_float(am), C.c_float(ai), C.c_float(rm))
+        self.L.refc_set_scan(self.h, 1, _p(scene.left, C.c_float), len(scene.left), C.c_float(am), C.c_float(ai), C.c_float(rm))
+        n = int(self.params.height_cells * self.params.width_cells)
+        out = np.zeros(n, dtype=np.int8)
+        secs = self.L.refc_build(self.h, _p(scene.cloud, C.c_float), len(scene.cloud), _p(out, C.c_int8), C.c_int64(n))
+        assert secs >= 0, "the node published nothing"
+        return out, secs

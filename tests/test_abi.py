@@ -37,6 +37,37 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_every_declared_costmap_symbol_is_exported(lib):
+    from autonomouscar_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "prius_costmap.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pc_[a-z0-9_]+)\s*\(", src)))
+    assert sorted(_lib.COSTMAP_EXPORTS) == declared and len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_costmap_struct_layout_matches_c():
+    from autonomouscar_b200.costmap_capi import pc_inputs, pc_params, pc_planar_scan
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "prius_costmap.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pc_params), sizeof(pc_planar_scan), sizeof(pc_inputs),
+         offsetof(pc_planar_scan, roll), offsetof(pc_inputs, center_z), offsetof(pc_inputs, base_from_map));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
+                               os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    want = [C.sizeof(pc_params), C.sizeof(pc_planar_scan), C.sizeof(pc_inputs), pc_planar_scan.roll.offset,
+            pc_inputs.center_z.offset, pc_inputs.base_from_map.offset]
+    assert [int(v) for v in out] == want
+
+
 def test_struct_layout_matches_c():
     from autonomouscar_b200.capi import pp_params, pp_query, pp_result
     prog = r'''

@@ -1,0 +1,56 @@
+"""Row N2 (local costmap): the oracle restatement (oracle/costmap_ref.h) against the REFERENCE's own
+local_costmap.cpp (oracle/_ref/libref_costmap.so, compiled unmodified against ROS test doubles):
+  * against the committed outputs of the reference binary (tests/golden/ref_costmap.npz) -- everywhere;
+  * live, on fresh random scenes and car poses, byte for byte -- where oracle/_ref is present."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLD)
+import make_costmap_golden as mcg  # noqa: E402
+
+
+def test_oracle_reproduces_reference_costmaps(oracle):
+    z = np.load(os.path.join(GOLD, "ref_costmap.npz"))
+    p = mcg.params()
+    for k, (seed, car, offset) in enumerate(mcg.CASES):
+        sc = mcg.scene_from_fixture(z, k)
+        g = mcg.global_grid(p, car, offset)
+        got, _ = oracle.costmap_build(p, sc.inputs, g, math_mode=oracle.MATH_LIBM)
+        want = z[f"c{k}_grid"]
+        np.testing.assert_array_equal(got, want)
+        assert (want == 100).sum() > 1000 and (want == -1).sum() >= 1
+        # the deterministic-math policy (what the GPU reproduces) paints the same picture
+        det, _ = oracle.costmap_build(p, sc.inputs, g, math_mode=oracle.MATH_DET)
+        assert (det != want).mean() < 1e-3
+
+
+def test_oracle_matches_live_reference_costmap(oracle):
+    from autonomouscar_b200 import worlds
+    from oracle import ref_binding as ref
+    if not ref.costmap_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(77)
+    p = mcg.params()
+    for trial in range(5):
+        car = (float(rng.uniform(-150, 150)), float(rng.uniform(-150, 150)), float(rng.uniform(-3.1, 3.1)))
+        ref.costmap_set_tfs(worlds.costmap_tfs(*car))
+        node = ref.RefCostmap(p)
+        sc = worlds.costmap_scene(100 + trial, max_reach=float(rng.uniform(12, 29)))
+        ref.costmap_derive_inputs(sc)
+        g = mcg.global_grid(p, car, int(rng.integers(0, 160))) if trial % 2 == 0 else None
+        if g is not None:
+            node.set_global(g)
+        want, _ = node.build(sc)
+        got, _ = oracle.costmap_build(node.params, sc.inputs, g, math_mode=oracle.MATH_LIBM)
+        np.testing.assert_array_equal(got, want)
+        # a second scan on the same node: clearMap (LC:349-358) must leave no state behind
+        sc2 = worlds.costmap_scene(200 + trial)
+        ref.costmap_derive_inputs(sc2)
+        want2, _ = node.build(sc2)
+        got2, _ = oracle.costmap_build(node.params, sc2.inputs, g, math_mode=oracle.MATH_LIBM)
+        np.testing.assert_array_equal(got2, want2)
+        node.close()

@@ -1,0 +1,111 @@
+"""Row N2 on the GPU: pc_build (csrc/pc_costmap.cu) through the C ABI against the oracle
+(deterministic math, byte for byte) and against the committed outputs of the reference binary."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLD)
+import make_costmap_golden as mcg  # noqa: E402
+
+
+def _fill_tf(sc, car):
+    """tf-derived numbers without the reference: planar, roll about x only (what costmap_tfs encodes)."""
+    from autonomouscar_b200 import worlds
+    tfs = worlds.costmap_tfs(*car)
+    for name, scan in (("front_right_laser_link", sc.inputs.right), ("front_left_laser_link", sc.inputs.left)):
+        x, y, z, roll, _, _ = tfs[(name, "center_laser_link")]
+        cr, sr = np.cos(roll), np.sin(roll)
+        # inverse origin of a pure roll rotation R: -(R^T t)
+        scan.roll, scan.tf_x, scan.tf_y = roll, x, y
+        scan.z_map = tfs[("map", name)][2]
+        scan.inv_x, scan.inv_y = -x, -(cr * y + sr * z)
+    sc.inputs.center_z = tfs[("center_laser_link", "map")][2]
+    c, s = np.cos(car[2]), np.sin(car[2])
+    m = [c, -s, 0, car[0], s, c, 0, car[1], 0, 0, 1, 0]
+    inv = [c, s, 0, -(c * car[0] + s * car[1]), -s, c, 0, -(-s * car[0] + c * car[1]), 0, 0, 1, 0]
+    for i in range(12):
+        sc.inputs.map_from_base[i], sc.inputs.base_from_map[i] = m[i], inv[i]
+
+
+def test_costmap_bit_exact_vs_oracle(oracle, cuda_device):
+    from autonomouscar_b200 import LocalCostmap, worlds
+    p = mcg.params()
+    cm = LocalCostmap(p, device=0)
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        car = (float(rng.uniform(-150, 150)), float(rng.uniform(-150, 150)), float(rng.uniform(-3.1, 3.1)))
+        sc = worlds.costmap_scene(300 + trial, n_planar=int(rng.choice([640, 333])), per_ring=int(rng.choice([512, 100])))
+        _fill_tf(sc, car)
+        g = mcg.global_grid(p, car, int(rng.integers(0, 160))) if trial % 3 != 1 else None
+        cm.set_global_grid(g)
+        got = cm.build(sc)
+        want, _ = oracle.costmap_build(p, sc.inputs, g, math_mode=oracle.MATH_DET)
+        np.testing.assert_array_equal(got, want)
+        assert (got == 100).sum() > 200
+        again = cm.build(sc)                      # graph re-launch on the same handle
+        np.testing.assert_array_equal(again, want)
+    assert cm.launch_count() > 0
+    cm.close()
+
+
+def test_costmap_matches_reference_fixture(cuda_device):
+    """Against what the REFERENCE binary published (glibc math): the only differences allowed are
+    cells where a last-ulp difference of sin/cos/atan2 moves a point across a cell border."""
+    from autonomouscar_b200 import LocalCostmap
+    z = np.load(os.path.join(GOLD, "ref_costmap.npz"))
+    p = mcg.params()
+    cm = LocalCostmap(p, device=0)
+    for k, (seed, car, offset) in enumerate(mcg.CASES):
+        sc = mcg.scene_from_fixture(z, k)
+        cm.set_global_grid(mcg.global_grid(p, car, offset))
+        got = cm.build(sc)
+        want = z[f"c{k}_grid"]
+        assert (got != want).mean() < 1e-3, (k, int((got != want).sum()))
+        assert abs(int((got == 100).sum()) - int((want == 100).sum())) <= 8
+    cm.close()
+
+
+def test_costmap_edge_cases(oracle, cuda_device):
+    from autonomouscar_b200 import LocalCostmap, worlds
+    from autonomouscar_b200.costmap_capi import CostmapScene
+    p = mcg.params()
+    cm = LocalCostmap(p, device=0)
+    # nothing received yet: every cell unknown (clearMap only)
+    empty = CostmapScene(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 3), np.float32),
+                         (np.float32(0), np.float32(0), np.float32(30)))
+    _fill_tf(empty, (0.0, 0.0, 0.0))
+    got = cm.build(empty)
+    assert (got == -1).all()
+    # points far outside the window are ignored (the reference would index out of bounds), NaN / inf ranges too
+    sc = worlds.costmap_scene(9)
+    _fill_tf(sc, (10.0, 5.0, 1.0))
+    sc.right[:50] = 500.0
+    sc.right[50:60] = np.nan
+    sc.left[:10] = np.inf
+    sc.cloud[:100, 0] = 1e6
+    sc.cloud[100:110, 1] = np.nan
+    sc.inputs.right.range_max = np.float32(1000.0)
+    got = cm.build(sc)
+    want, _ = oracle.costmap_build(p, sc.inputs, None, math_mode=oracle.MATH_DET)
+    np.testing.assert_array_equal(got, want)
+    cm.close()
+
+
+def test_costmap_feeds_planner_on_device(oracle, cuda_device):
+    """/local_costmap never leaves the GPU: pc_grid_dev -> pp_set_grid_dev, then the planner's
+    m_c_space equals the LP:439 flip of the grid the costmap node would have published."""
+    from autonomouscar_b200 import LocalCostmap, Planner, default_params, worlds
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    cm = LocalCostmap(default_costmap_params(), device=0)
+    sc = worlds.costmap_scene(5)
+    _fill_tf(sc, (0.0, 0.0, 0.0))
+    msg = cm.build(sc)
+    pl = Planner(default_params(), device=0)
+    cm.feed_planner(pl)
+    np.testing.assert_array_equal(pl.get_cspace(), oracle.cspace_from_msg(msg, 300, 300))
+    pl.close()
+    cm.close()
