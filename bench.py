@@ -368,6 +368,7 @@ def run_ours(args):
             "oriented_direct_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / l2_gbps,
         }
     plans = bench_plans(pl, rank, world, dev, multi, args) if not args.skip_plans else None
+    costmap = bench_costmap(args) if (rank == 0 and not args.skip_plans) else None
 
     if rank == 0:
         peak, peak_kind = _peaks()
@@ -419,11 +420,87 @@ def run_ours(args):
             "wall_s_timed_region": wall,
             "extra": extra,
             "plans": plans,
+            "costmap": costmap,
         }
         print(json.dumps(line), flush=True)
     pl.close()
     if multi:
         dist.destroy_process_group()
+
+
+def bench_costmap(args):
+    """Row N2: grids/s of the local costmap builder (pc_build, launch-file sizes: 300x300 @0.25 m grid,
+    2 x 640-ray scans, 16 x 512 cloud, 12000^2 global road map resident in HBM) through the C ABI with
+    host buffers, next to the reference's own local_costmap.cpp (oracle/_ref) on one host thread --
+    the reference node is single-threaded and builds one grid per centre-laser scan (LC:366-370)."""
+    import numpy as np
+
+    from autonomouscar_b200 import LocalCostmap, worlds
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    G = 12000
+    p = default_costmap_params(global_height_cells=float(G), global_width_cells=float(G))
+    car = (30.0, -12.0, 0.7)
+    tfs = worlds.costmap_tfs(*car)
+    gg = worlds.road_like_global_grid(G, 17, zero_at=worlds.costmap_corner_global_cells(p, *car))
+    scenes = [worlds.costmap_scene(s) for s in range(4)]
+    have_ref = ref_available()
+    if have_ref:
+        from oracle import ref_binding as ref
+        have_ref = ref.costmap_available()
+    if have_ref:
+        ref.costmap_set_tfs(tfs)
+        for sc in scenes:
+            ref.costmap_derive_inputs(sc)        # the tf numbers exactly as the reference node reads them
+    else:
+        for sc in scenes:                        # planar tf numbers computed directly
+            for name, scan in (("front_right_laser_link", sc.inputs.right), ("front_left_laser_link", sc.inputs.left)):
+                x, y, z, roll, _, _ = tfs[(name, "center_laser_link")]
+                scan.roll, scan.tf_x, scan.tf_y, scan.z_map = roll, x, y, tfs[("map", name)][2]
+                scan.inv_x, scan.inv_y = -x, -(np.cos(roll) * y + np.sin(roll) * z)
+            sc.inputs.center_z = tfs[("center_laser_link", "map")][2]
+            c, s_ = np.cos(car[2]), np.sin(car[2])
+            m = [c, -s_, 0, car[0], s_, c, 0, car[1], 0, 0, 1, 0]
+            inv = [c, s_, 0, -(c * car[0] + s_ * car[1]), -s_, c, 0, -(-s_ * car[0] + c * car[1]), 0, 0, 1, 0]
+            for i in range(12):
+                sc.inputs.map_from_base[i], sc.inputs.base_from_map[i] = m[i], inv[i]
+    cm = LocalCostmap(p, device=0)
+    cm.set_global_grid(gg)
+    out = {"config": "300x300 @0.25 m, 2x640 rays, 16x512 cloud, 12000^2 global map (full_sim.launch sizes)"}
+    grids = {}
+    for want_host, key in ((True, "e2e_grids_per_s"), (False, "device_resident_grids_per_s")):
+        for sc in scenes:
+            grids[id(sc)] = cm.build(sc, want_host=want_host)
+        reps, ms = 300, []
+        t0 = time.perf_counter()
+        for k in range(reps):
+            cm.build(scenes[k % 4], want_host=want_host)
+            ms.append(cm.last_build_ms())
+        out[key] = reps / (time.perf_counter() - t0)
+        out["device_ms_per_grid"] = float(np.median(ms))
+    out["kernels_per_grid"] = 5
+    out["h2d_bytes_per_grid"] = int(4 * (len(scenes[0].right) + len(scenes[0].left) + scenes[0].cloud.size))
+    out["d2h_bytes_per_grid"] = cm.n_cells
+    if not args.skip_cpu:
+        from oracle import binding as orc
+        last = cm.build(scenes[0])
+        det, _ = orc.costmap_build(p, scenes[0].inputs, gg, math_mode=orc.MATH_DET)
+        out["bit_exact_vs_oracle"] = bool(np.array_equal(last, det))
+        secs = [orc.costmap_build(p, sc.inputs, gg, math_mode=orc.MATH_LIBM)[1] for sc in scenes]
+        out["cpu_oracle_port_grids_per_s_1thread"] = len(secs) / sum(secs)
+        if have_ref:
+            node = ref.RefCostmap(p)
+            node.set_global(gg)
+            node.build(scenes[0])
+            rs = []
+            for sc in scenes * 3:
+                g_ref, sec = node.build(sc)
+                rs.append(sec)
+            out["cpu_reference_grids_per_s_1thread"] = len(rs) / sum(rs)
+            out["cpu_reference_kind"] = "reference: local_costmap.cpp compiled from the reference sources (oracle/_ref), g++ -O2, 1 thread (the node is single-threaded)"
+            out["cells_differing_from_reference"] = int((cm.build(scenes[0]) != node.build(scenes[0])[0]).sum())
+            node.close()
+    cm.close()
+    return out
 
 
 def bench_plans(pl_unused, rank, world, dev, multi, args):

@@ -103,3 +103,65 @@ def test_ros_shim_publishes_what_the_reference_node_publishes(cuda_device, tmp_p
         assert (g["mp_max_speed"], g["mp_max_accel"]) == (r.mp_max_speed, r.mp_max_accel)
     assert n_found >= 2 and n_found < len(steps)
     node.close()
+
+
+def test_ros_costmap_shim_publishes_the_reference_nodes_grid(cuda_device, tmp_path):
+    """Row N2: ros/local_costmap_b200_node.cpp, compiled unchanged against the ROS test doubles, fed the
+    same LaserScan / PointCloud / OccupancyGrid messages and tf frames as the reference's
+    local_costmap node (oracle/_ref/libref_costmap.so): the /local_costmap it publishes is the
+    reference's (cells may differ only where a last-ulp sin/cos/atan2 difference crosses a cell border)."""
+    import sys
+    from oracle import ref_binding as ref
+    if not ref.costmap_available():
+        pytest.skip("oracle/_ref not present")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_costmap_golden as mcg
+    exe = str(tmp_path / "test_ros_costmap_shim")
+    pkg = os.path.join(ROOT, "autonomouscar_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "oracle", "ros_doubles"),
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "host"),
+                           os.path.join(ROOT, "tests", "cpp", "test_ros_costmap_shim.cpp"), "-o", exe,
+                           "-L", pkg, "-lprius_planner_b200", f"-Wl,-rpath,{pkg}"])
+    p = mcg.params()
+    car = (42.0, -17.5, 1.1)
+    tfs = worlds.costmap_tfs(*car)
+    g = mcg.global_grid(p, car, 23)
+    gpath = str(tmp_path / "global.bin")
+    g.tofile(gpath)
+    lines = ["param local_costmap_res 0.25", "param local_costmap_height 75", "param local_costmap_width 75",
+             "param z_ground_buffer 0.075", "param obstacle_range 2", "param max_inflation_radius 5",
+             f"param global_costmap_height {mcg.GLOBAL_CELLS * 0.25!r}", f"param global_costmap_width {mcg.GLOBAL_CELLS * 0.25!r}"]
+    for (t, s), v in tfs.items():
+        lines.append(f"tf {t} {s} " + " ".join(repr(float(x)) for x in v))
+    scenes = [worlds.costmap_scene(41), worlds.costmap_scene(42)]
+    lines.append(f"global {gpath} {g.size}")
+    for k, sc in enumerate(scenes):
+        for name, arr in (("right", sc.right), ("left", sc.left)):
+            f = str(tmp_path / f"{name}{k}.bin")
+            arr.tofile(f)
+            am, ai, rm = sc.scan_meta
+            lines.append(f"scan {name} {f} {len(arr)} {float(am)!r} {float(ai)!r} {float(rm)!r}")
+        cf = str(tmp_path / f"cloud{k}.bin")
+        sc.cloud.tofile(cf)
+        lines.append(f"cloud {cf} {len(sc.cloud)} {tmp_path / f'grid{k}.bin'}")
+    scen = tmp_path / "costmap_scenario.txt"
+    scen.write_text("\n".join(lines) + "\n")
+    out = subprocess.check_output([exe, str(scen)]).decode().splitlines()
+    pub = [ln.split() for ln in out if ln.startswith("published")]
+    assert len(pub) == 2
+
+    ref.costmap_set_tfs(tfs)
+    node = ref.RefCostmap(p)
+    node.set_global(g)
+    for k, sc in enumerate(scenes):
+        w = pub[k]
+        assert w[1] == "1" and w[2] == "base_link" and (int(w[3]), int(w[4])) == (300, 300)
+        assert float.fromhex(w[5]) == 0.25
+        # origin: -W*res/2 + tf(base_link <- center_laser_link).x (LC:54-55)
+        assert float.fromhex(w[6]) == -300 * 0.25 / 2 + tfs[("base_link", "center_laser_link")][0]
+        got = np.fromfile(str(tmp_path / f"grid{k}.bin"), dtype=np.int8)
+        want, _ = node.build(sc)
+        assert got.shape == want.shape
+        assert (got != want).mean() < 1e-3, int((got != want).sum())
+        assert (got == 100).sum() > 1000
+    node.close()
