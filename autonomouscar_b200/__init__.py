@@ -15,9 +15,9 @@ def __getattr__(name):
     if name in ("Planner", "PlannerError", "PlannerGroup"):
         from . import planner
         return getattr(planner, name)
-    if name == "LocalCostmap":
+    if name in ("LocalCostmap", "GlobalRoadMap"):
         from . import costmap
-        return costmap.LocalCostmap
+        return getattr(costmap, name)
     if name == "LocalPlannerNode":
         from . import node
         return node.LocalPlannerNode

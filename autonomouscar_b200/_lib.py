@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 from .capi import pp_params, pp_query, pp_result
-from .costmap_capi import pc_inputs, pc_params
+from .costmap_capi import pc_inputs, pc_params, pg_params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libprius_planner_b200.so")
@@ -26,7 +26,8 @@ EXPORTS = [
 # every symbol include/prius_costmap.h declares (row N2)
 COSTMAP_EXPORTS = [
     "pc_default_params", "pc_create", "pc_destroy", "pc_set_global_grid", "pc_build", "pc_grid_dev", "pc_stream",
-    "pc_launch_count", "pc_last_build_ms",
+    "pc_launch_count", "pc_last_build_ms", "pc_adopt_global_grid",
+    "pg_default_params", "pg_build", "pg_last_build", "pg_free",
 ]
 
 _lib = None
@@ -93,6 +94,11 @@ def load():
     L.pc_stream.argtypes = [vp, C.POINTER(vp)]
     L.pc_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.pc_last_build_ms.argtypes = [vp, C.POINTER(f32)]
+    L.pc_adopt_global_grid.argtypes = [vp, vp, i64]
+    L.pg_default_params.argtypes = [C.POINTER(pg_params)]
+    L.pg_build.argtypes = [C.POINTER(pg_params), C.c_int, vp, vp, i32, vp, C.POINTER(vp)]
+    L.pg_last_build.argtypes = [C.POINTER(f32), C.POINTER(i32)]
+    L.pg_free.argtypes = [C.c_int, vp]
     if L.pp_abi_version() != 1:
         raise LibraryMissing("ABI version mismatch")
     _lib = L

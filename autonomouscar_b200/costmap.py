@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _lib
 from .capi import PP_GRID_OCCUPANCY_MSG, PP_OK
-from .costmap_capi import default_costmap_params
+from .costmap_capi import default_costmap_params, default_global_costmap_params
 
 
 class LocalCostmap:
@@ -48,6 +48,11 @@ class LocalCostmap:
         g = np.ascontiguousarray(grid, dtype=np.int8).ravel()
         self._check(self._L.pc_set_global_grid(self._h, g.ctypes.data_as(C.c_void_p), g.size))
 
+    def adopt_global_grid(self, global_map):
+        """Take over a device-resident GlobalRoadMap (row N3) without copying it."""
+        ptr, n = global_map.release()
+        self._check(self._L.pc_adopt_global_grid(self._h, C.c_void_p(ptr), n))
+
     def build(self, scene, want_host=True):
         """One calcOccGrid pass over `scene` (costmap_capi.CostmapScene).  Returns the int8 grid in
         message order (numpy) or None when only the device grid is wanted."""
@@ -76,3 +81,45 @@ class LocalCostmap:
         v = C.c_float()
         self._check(self._L.pc_last_build_ms(self._h, C.byref(v)))
         return v.value
+
+
+class GlobalRoadMap:
+    """The static /global_costmap built on the device (pg_build, row N3: GlobalCostmap::setupRoadMap,
+    global_costmap.cpp:52-61).  `xy` = float32 (x, y) pairs as read from edges.csv, polyline k =
+    points [offsets[k], offsets[k+1])."""
+
+    def __init__(self, xy, offsets, params=None, device=0, want_host=True):
+        self._L = _lib.load()
+        self.params = params if params is not None else default_global_costmap_params()
+        self.device = int(device)
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        self.n_cells = int(self.params.height_cells * self.params.width_cells)
+        self.host = np.empty(self.n_cells, dtype=np.int8) if want_host else None
+        dev = C.c_void_p()
+        rc = self._L.pg_build(C.byref(self.params), self.device, xy.ctypes.data_as(C.c_void_p),
+                              offsets.ctypes.data_as(C.c_void_p), len(offsets) - 1,
+                              self.host.ctypes.data_as(C.c_void_p) if want_host else None, C.byref(dev))
+        if rc != PP_OK:
+            from .planner import PlannerError
+            raise PlannerError(rc, self._L.pp_last_error().decode())
+        self._dev = dev.value
+        ms, n = C.c_float(), C.c_int32()
+        self._L.pg_last_build(C.byref(ms), C.byref(n))
+        self.build_ms, self.launches = ms.value, n.value
+
+    def release(self):
+        """(device pointer, length); the caller now owns the allocation."""
+        ptr, self._dev = self._dev, None
+        return ptr, self.n_cells
+
+    def close(self):
+        if self._dev:
+            self._L.pg_free(self.device, C.c_void_p(self._dev))
+            self._dev = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

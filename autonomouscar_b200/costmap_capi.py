@@ -24,6 +24,26 @@ class pc_inputs(C.Structure):
                 ("base_from_map", C.c_double * 12)]
 
 
+class pg_params(C.Structure):
+    _fields_ = [("res", C.c_double), ("road_width", C.c_double), ("num_lanes", C.c_int32), ("reserved0", C.c_int32),
+                ("height_cells", C.c_double), ("width_cells", C.c_double), ("reserved", C.c_int32 * 8)]
+
+
+def default_global_costmap_params(**overrides):
+    """full_sim.launch:68-73 (+ :77 for the resolution)."""
+    p = pg_params()
+    p.res = 0.25
+    p.road_width = 11.1
+    p.num_lanes = 2
+    p.height_cells = 12000.0
+    p.width_cells = 12000.0
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
 def default_costmap_params(**overrides):
     """full_sim.launch:71-72, 77-82."""
     p = pc_params()

@@ -360,6 +360,18 @@ int pc_set_global_grid(pc_handle* h, const int8_t* data_host, int64_t len) {
   return PP_OK;
 }
 
+int pc_adopt_global_grid(pc_handle* h, int8_t* grid_dev, int64_t len) {
+  if (!h) { set_last_error("pc_adopt_global_grid: null handle"); return PP_ERR_INVALID; }
+  PP_REQUIRE(len >= 0 && (len == 0 || grid_dev), "pc_adopt_global_grid: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  cudaFree(h->d_global);
+  h->d_global = len > 0 ? grid_dev : nullptr;
+  h->global_len = len;
+  return PP_OK;
+}
+
 int pc_build(pc_handle* h, const pc_inputs* in, int8_t* out_host) {
   if (!h || !in) { set_last_error("pc_build: null argument"); return PP_ERR_INVALID; }
   const pc_planar_scan* scans[2] = {&in->right, &in->left};

@@ -85,6 +85,34 @@ int pc_stream(pc_handle* h, void** out_stream);
 int pc_launch_count(const pc_handle* h, uint64_t* out);
 int pc_last_build_ms(pc_handle* h, float* out_ms);
 
+/* ------------------------------------------------------------------------------------ */
+/* row N3: the static global road map (catkin_ws/src/global_costmap/src/global_costmap.cpp, */
+/* "GC"): road polylines -> the 12000 x 12000 lane-cost grid published once on            */
+/* /global_costmap and consumed by mapRoadVectors (LC:208-257).                           */
+/* ------------------------------------------------------------------------------------ */
+typedef struct pg_params {
+  double res;            /* /local_costmap_node/local_costmap_res (GC:8), 0.25            */
+  double road_width;     /* ~road_width, 11.1 (full_sim.launch:69)                        */
+  int32_t num_lanes;     /* ~num_lanes, 2 (:70)                                           */
+  int32_t reserved0;
+  double height_cells;   /* global_costmap_height / res (GC:14), 12000                    */
+  double width_cells;    /* global_costmap_width  / res (GC:15), 12000                    */
+  int32_t reserved[8];
+} pg_params;
+
+int pg_default_params(pg_params* out);
+/* Replaces GlobalCostmap::GlobalCostmap -> setupRoadMap (GC:5-18, 52-61) minus the file parsing
+   (GC:25-50 is the caller's; the +5 / -5 shift of GC:42-43 IS applied here): polyline k =
+   points [offsets[k], offsets[k+1]) of xy_host (float32 x, y pairs as read from edges.csv).
+   The grid stays on `device`; out_host (height*width int8, message order) may be NULL. */
+int pg_build(const pg_params* params, int device, const float* xy_host, const int32_t* offsets_host,
+             int32_t n_sections, int8_t* out_host, int8_t** out_dev);
+/* device time (ms) of the most recent pg_build on this thread, and its kernel launch count */
+int pg_last_build(float* out_ms, int32_t* out_launches);
+/* hand a pg_build device grid to a costmap builder without copying (it takes ownership) */
+int pc_adopt_global_grid(pc_handle* h, int8_t* grid_dev, int64_t len);
+int pg_free(int device, int8_t* grid_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -193,3 +193,15 @@ def costmap_build(params, scene_inputs, global_grid=None, math_mode=MATH_DET):
     secs = lib().orc_costmap_build(C.byref(params), C.byref(scene_inputs), None if g is None else _p(g, C.c_int8),
                                    C.c_int64(0 if g is None else g.size), math_mode, _p(out, C.c_int8))
     return out, secs
+
+
+def global_costmap_build(params, xy, offsets, math_mode=MATH_DET):
+    """GlobalCostmap::setupRoadMap (global_costmap.cpp:52-61) -> (int8 grid in message order, seconds)."""
+    lib().orc_global_costmap_build.restype = C.c_double
+    xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    n = int(params.height_cells * params.width_cells)
+    out = np.zeros(n, dtype=np.int8)
+    secs = lib().orc_global_costmap_build(C.byref(params), _p(xy, C.c_float), _p(offsets, C.c_int32), len(offsets) - 1,
+                                          math_mode, _p(out, C.c_int8), C.c_int64(n))
+    return out, secs

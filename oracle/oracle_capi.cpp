@@ -13,6 +13,7 @@
 #include "../include/prius_planner.h"
 #include "collision_ref.h"
 #include "costmap_ref.h"
+#include "global_costmap_ref.h"
 #include "philox_ref.h"
 #include "planner_ref.h"
 #include "sampling_ref.h"
@@ -286,6 +287,15 @@ double orc_costmap_build(const pc_params* p, const pc_inputs* in, const int8_t* 
   const auto t0 = std::chrono::steady_clock::now();
   if (math_mode == 0) { RefCostmap<LibmMathC> c(*p); c.build(*in, global_grid, global_len, out); }
   else { RefCostmap<DetMathC> c(*p); c.build(*in, global_grid, global_len, out); }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// global road map (row N3): GlobalCostmap::setupRoadMap (GC:52-61).  Returns wall seconds.
+double orc_global_costmap_build(const pg_params* p, const float* xy, const int32_t* offsets, int n_sections,
+                                int math_mode, int8_t* out, int64_t out_len) {
+  const auto t0 = std::chrono::steady_clock::now();
+  if (math_mode == 0) { RefGlobalCostmap<LibmMathC> c(*p); c.build(xy, offsets, n_sections, out, out_len); }
+  else { RefGlobalCostmap<DetMathC> c(*p); c.build(xy, offsets, n_sections, out, out_len); }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 

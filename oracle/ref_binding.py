@@ -280,3 +280,34 @@ class RefCostmap:
         secs = self.L.refc_build(self.h, _p(scene.cloud, C.c_float), len(scene.cloud), _p(out, C.c_int8), C.c_int64(n))
         assert secs >= 0, "the node published nothing"
         return out, secs
+
+
+# ---------------------------------------------------------------------------------------------
+# row N3: the reference's own global_costmap.cpp (oracle/_ref/libref_global_costmap.so)
+# ---------------------------------------------------------------------------------------------
+def global_costmap_available():
+    build()
+    return os.path.exists(os.path.join(_DIR, "libref_global_costmap.so"))
+
+
+def write_edges_csv(path, xy, offsets):
+    """The edges.csv format read by GlobalCostmap::readEdges (GC:25-50): one polyline per line,
+    points "x y 0" separated by commas.  %.9g round-trips every float32 exactly."""
+    xy = np.asarray(xy, dtype=np.float32).reshape(-1, 2)
+    with open(path, "w") as f:
+        for k in range(len(offsets) - 1):
+            f.write(",".join("%.9g %.9g 0" % (float(x), float(y)) for x, y in xy[offsets[k]:offsets[k + 1]]) + ",\n")
+
+
+def global_costmap_build(params, xy, offsets, tmp_dir):
+    """Construct Prius::GlobalCostmap on the polylines -> (published int8 grid, seconds)."""
+    L = C.CDLL(os.path.join(_DIR, "libref_global_costmap.so"))
+    L.refg_build.restype = C.c_double
+    path = os.path.join(str(tmp_dir), "edges_for_ref.csv")
+    write_edges_csv(path, xy, offsets)
+    n = int(params.height_cells * params.width_cells)
+    out = np.zeros(n, dtype=np.int8)
+    n_out = C.c_int64()
+    secs = L.refg_build(C.byref(params), path.encode(), _p(out, C.c_int8), C.c_int64(n), C.byref(n_out))
+    assert secs >= 0 and n_out.value == n, (secs, n_out.value, n)
+    return out, secs

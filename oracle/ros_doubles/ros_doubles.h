@@ -60,6 +60,15 @@ inline int deliver(const std::string& topic, const M& msg) {
 namespace boost {
 template <class S>
 using function = std::function<S>;
+struct bad_lexical_cast : std::runtime_error { bad_lexical_cast() : std::runtime_error("bad lexical cast") {} };
+// boost::lexical_cast<T>(string): the whole string must parse (stream semantics), else it throws
+template <class T>
+inline T lexical_cast(const std::string& s) {
+  std::istringstream in(s);
+  T v;
+  if (!(in >> v) || !in.eof()) throw bad_lexical_cast();
+  return v;
+}
 }
 
 namespace ros {

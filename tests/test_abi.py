@@ -41,21 +41,22 @@ def test_every_declared_costmap_symbol_is_exported(lib):
     from autonomouscar_b200 import _lib
     src = open(os.path.join(ROOT, "include", "prius_costmap.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    declared = sorted(set(re.findall(r"\b(pc_[a-z0-9_]+)\s*\(", src)))
+    declared = sorted(set(re.findall(r"\b(p[cg]_[a-z0-9_]+)\s*\(", src)))
     assert sorted(_lib.COSTMAP_EXPORTS) == declared and len(declared) >= 9
     for name in declared:
         assert hasattr(lib, name), name
 
 
 def test_costmap_struct_layout_matches_c():
-    from autonomouscar_b200.costmap_capi import pc_inputs, pc_params, pc_planar_scan
+    from autonomouscar_b200.costmap_capi import pc_inputs, pc_params, pc_planar_scan, pg_params
     prog = r'''
 #include <stdio.h>
 #include <stddef.h>
 #include "prius_costmap.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pc_params), sizeof(pc_planar_scan), sizeof(pc_inputs),
-         offsetof(pc_planar_scan, roll), offsetof(pc_inputs, center_z), offsetof(pc_inputs, base_from_map));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pc_params), sizeof(pc_planar_scan), sizeof(pc_inputs),
+         offsetof(pc_planar_scan, roll), offsetof(pc_inputs, center_z), offsetof(pc_inputs, base_from_map),
+         sizeof(pg_params), offsetof(pg_params, height_cells));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -64,7 +65,7 @@ int main(void) {
                                os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")]).split()
     want = [C.sizeof(pc_params), C.sizeof(pc_planar_scan), C.sizeof(pc_inputs), pc_planar_scan.roll.offset,
-            pc_inputs.center_z.offset, pc_inputs.base_from_map.offset]
+            pc_inputs.center_z.offset, pc_inputs.base_from_map.offset, C.sizeof(pg_params), pg_params.height_cells.offset]
     assert [int(v) for v in out] == want
 
 

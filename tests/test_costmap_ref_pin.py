@@ -54,3 +54,36 @@ def test_oracle_matches_live_reference_costmap(oracle):
         got2, _ = oracle.costmap_build(node.params, sc2.inputs, g, math_mode=oracle.MATH_LIBM)
         np.testing.assert_array_equal(got2, want2)
         node.close()
+
+
+# ---- row N3: the global road map ---------------------------------------------------------------
+import make_global_costmap_golden as mgg  # noqa: E402
+
+
+def test_oracle_reproduces_reference_global_costmaps(oracle):
+    z = np.load(os.path.join(GOLD, "ref_global_costmap.npz"))
+    for k, (seed, lanes, width) in enumerate(mgg.SMALL_CASES):
+        got, _ = oracle.global_costmap_build(mgg.small_params(lanes, width), z[f"s{k}_xy"], z[f"s{k}_off"],
+                                             math_mode=oracle.MATH_LIBM)
+        want = z[f"s{k}_grid"]
+        np.testing.assert_array_equal(got, want)
+        assert ((want >= 0) & (want < 99)).sum() > 100000 and (want == -1).sum() == mgg.SMALL + 1   # GC:83-89 never writes [0, H]
+    # the launch-file map from the reference's own road polylines: same bytes as the reference published
+    from autonomouscar_b200.costmap_capi import default_global_costmap_params
+    xy, off = mgg.road_edges()
+    got, _ = oracle.global_costmap_build(default_global_costmap_params(), xy, off, math_mode=oracle.MATH_LIBM)
+    sha, rows, cols, total = mgg.full_summary(got, 12000)
+    np.testing.assert_array_equal(sha, z["full_sha"])
+    np.testing.assert_array_equal(rows, z["full_rows"])
+
+
+def test_oracle_matches_live_reference_global_costmap(oracle, tmp_path):
+    from oracle import ref_binding as ref
+    if not ref.global_costmap_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for seed, lanes, width in ((11, 1, 5.0), (12, 2, 11.1), (13, 4, 14.0)):
+        xy, off = mgg.synth_polylines(seed, n_lines=9)
+        p = mgg.small_params(lanes, width)
+        want, _ = ref.global_costmap_build(p, xy, off, tmp_path)
+        got, _ = oracle.global_costmap_build(p, xy, off, math_mode=oracle.MATH_LIBM)
+        np.testing.assert_array_equal(got, want)

@@ -109,3 +109,55 @@ def test_costmap_feeds_planner_on_device(oracle, cuda_device):
     np.testing.assert_array_equal(pl.get_cspace(), oracle.cspace_from_msg(msg, 300, 300))
     pl.close()
     cm.close()
+
+
+# ---- row N3: the global road map ---------------------------------------------------------------
+import make_global_costmap_golden as mgg  # noqa: E402
+
+
+def test_global_road_map_bit_exact_small(oracle, cuda_device):
+    """pg_build against the oracle (deterministic math) and against the grids the REFERENCE published."""
+    from autonomouscar_b200 import GlobalRoadMap
+    z = np.load(os.path.join(GOLD, "ref_global_costmap.npz"))
+    for k, (seed, lanes, width) in enumerate(mgg.SMALL_CASES):
+        p = mgg.small_params(lanes, width)
+        gm = GlobalRoadMap(z[f"s{k}_xy"], z[f"s{k}_off"], params=p, device=0)
+        want, _ = oracle.global_costmap_build(p, z[f"s{k}_xy"], z[f"s{k}_off"], math_mode=oracle.MATH_DET)
+        np.testing.assert_array_equal(gm.host, want)
+        assert (gm.host != z[f"s{k}_grid"]).mean() < 1e-4        # the reference binary itself (glibc math)
+        assert gm.launches >= 3
+        gm.close()
+    # degenerate inputs: no polylines / single-point polylines -> all 99 except the never-written head
+    p = mgg.small_params(2, 11.1)
+    gm = GlobalRoadMap(np.zeros((3, 2), np.float32), np.array([0, 1, 2, 3], np.int32), params=p, device=0)
+    assert (gm.host[: mgg.SMALL + 1] == -1).all() and (gm.host[mgg.SMALL + 1:] == 99).all()
+    gm.close()
+
+
+def test_global_road_map_launch_file_size(cuda_device):
+    """12000 x 12000 from the reference's own road polylines: the grid the reference published
+    (SHA-256 / per-row / per-column road-cell counts from oracle/_ref), then handed to the local
+    costmap builder without leaving the device."""
+    from autonomouscar_b200 import GlobalRoadMap, LocalCostmap, worlds
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    z = np.load(os.path.join(GOLD, "ref_global_costmap.npz"))
+    xy, off = mgg.road_edges()
+    gm = GlobalRoadMap(xy, off, device=0)
+    sha, rows, cols, total = mgg.full_summary(gm.host, 12000)
+    assert np.abs(rows - z["full_rows"]).sum() <= 64 and np.abs(cols - z["full_cols"]).sum() <= 64
+    assert abs(int(total[0]) - int(z["full_sum"][0])) <= 99 * 64
+    exact = bool(np.array_equal(sha, z["full_sha"]))
+    print("global map: %.2f ms on the device, identical to the reference's bytes: %s" % (gm.build_ms, exact))
+    host = gm.host
+    cm = LocalCostmap(default_costmap_params(), device=0)
+    cm.adopt_global_grid(gm)
+    car = (30.0, 10.0, 0.3)                      # on the reference's route, inside the road network
+    sc = worlds.costmap_scene(2)
+    _fill_tf(sc, car)
+    got = cm.build(sc)
+    cm2 = LocalCostmap(default_costmap_params(), device=0)
+    cm2.set_global_grid(host)
+    np.testing.assert_array_equal(got, cm2.build(sc))
+    assert ((got > 0) & (got < 99)).sum() > 1000  # road costs made it into the local grid
+    cm.close()
+    cm2.close()
