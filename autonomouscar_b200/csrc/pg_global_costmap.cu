@@ -63,9 +63,17 @@ __global__ void pg_segment_kernel(const float* __restrict__ xy, const int* __res
   counts[s] = g.n;
 }
 
+// x / res.  When res is a power of two (0.25 in the launch file) the quotient equals the product
+// with the exactly representable reciprocal, bit for bit, and costs one multiply instead of a division.
+struct PgRes {
+  double res, inv;
+  bool pow2;
+};
+__device__ __forceinline__ double pg_div_res(const PgRes& r, double x) { return r.pow2 ? dm::mul(x, r.inv) : dm::div(x, r.res); }
+
 // one stroke (GC:124-157): samples from the lane centre `c` towards the lane edge `e`
-__device__ __forceinline__ void pg_stroke(const pg_params& P, int H, int W, float cx, float cy, float ex, float ey,
-                                          int* __restrict__ matrix) {
+__device__ __forceinline__ void pg_stroke(const pg_params& P, const PgRes& R, int H, int W, float cx, float cy, float ex,
+                                          float ey, int* __restrict__ matrix) {
   const double d_x = static_cast<double>(__fsub_rn(cx, ex)), d_y = static_cast<double>(__fsub_rn(cy, ey));
   const double angle = dm::atan2_(d_y, d_x);
   double sa, ca;
@@ -77,13 +85,16 @@ __device__ __forceinline__ void pg_stroke(const pg_params& P, int H, int W, floa
   const double nd = static_cast<double>(n);
   const double half_h = dm::div(P.height_cells, 2.0), half_w = dm::div(P.width_cells, 2.0);
   for (int i = 0; i < n; ++i) {
-    const double t = dm::mul(dm::div(static_cast<double>(i), nd), dist);
+    const double qi = dm::div(static_cast<double>(i), nd);
+    const double t = dm::mul(qi, dist);
     const float px = static_cast<float>(dm::add(static_cast<double>(cx), dm::mul(t, ca)));   // GC:179-181, stored as float
     const float py = static_cast<float>(dm::add(static_cast<double>(cy), dm::mul(t, sa)));
-    const double value = dm::sub(99.0, dm::mul(dm::div(static_cast<double>(count), nd), 99.0));   // GC:130
+    // count == i unless an earlier sample of this stroke was clipped at the map border
+    const double qc = count == i ? qi : dm::div(static_cast<double>(count), nd);
+    const double value = dm::sub(99.0, dm::mul(qc, 99.0));                                   // GC:130
     int xi, yi;
-    if (!dm::trunc_to_int(dm::sub(half_h, dm::div(static_cast<double>(px), P.res)), &xi)) continue;   // GC:188-189
-    if (!dm::trunc_to_int(dm::sub(half_w, dm::div(static_cast<double>(py), P.res)), &yi)) continue;
+    if (!dm::trunc_to_int(dm::sub(half_h, pg_div_res(R, static_cast<double>(px))), &xi)) continue;   // GC:188-189
+    if (!dm::trunc_to_int(dm::sub(half_w, pg_div_res(R, static_cast<double>(py))), &yi)) continue;
     if (xi < 0 || xi > H - 1 || yi < 0 || yi > W - 1) continue;                              // GC:132-135
     atomicMin(&matrix[static_cast<size_t>(xi) * W + yi], __double2int_rz(value));             // GC:136-139
     count++;
@@ -92,7 +103,7 @@ __device__ __forceinline__ void pg_stroke(const pg_params& P, int H, int W, floa
 
 __global__ void __launch_bounds__(256)
 pg_stroke_kernel(const PgSeg* __restrict__ segs, const long long* __restrict__ seg_off, int n_seg, long long n_points,
-                 pg_params P, int H, int W, int* __restrict__ matrix) {
+                 pg_params P, PgRes R, int H, int W, int* __restrict__ matrix) {
   const long long strokes = n_points * P.num_lanes * 2;
   const double lane_width = dm::div(P.road_width, static_cast<double>(P.num_lanes));          // GC:104
   const double first_off = dm::add(dm::div(P.road_width, 2.0), dm::div(lane_width, 2.0));     // GC:108
@@ -126,30 +137,48 @@ pg_stroke_kernel(const PgSeg* __restrict__ segs, const long long* __restrict__ s
       ex = static_cast<float>(dm::add(static_cast<double>(lcx), dm::mul(half_lane, g.cp)));
       ey = static_cast<float>(dm::add(static_cast<double>(lcy), dm::mul(half_lane, g.sp)));
     }
-    pg_stroke(P, H, W, lcx, lcy, ex, ey, matrix);
+    pg_stroke(P, R, H, W, lcx, lcy, ex, ey, matrix);
   }
 }
 
-// calcRoadmap (GC:207-217): out[location(x, y)] = matrix[x][y]
+// calcRoadmap (GC:207-217): out[location(x, y)] = matrix[x][y].  A 64 x 64 tile goes through shared
+// memory: 16-byte loads along y (the matrix's fast axis, four of them in flight per thread), byte
+// stores along x (the message's fast axis: `location` falls by one when x grows by one).
 __global__ void __launch_bounds__(256)
 pg_roadmap_kernel(const int* __restrict__ matrix, int H, int W, pg_params P, int8_t* __restrict__ out, long long out_len) {
-  __shared__ int tile[32][33];
-  const int x0 = blockIdx.y * 32, y0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  for (int r = ty; r < 32; r += 8) {                           // rows of the matrix: fixed x, consecutive y
-    const int x = x0 + r, y = y0 + tx;
-    tile[r][tx] = (x < H && y < W) ? matrix[static_cast<size_t>(x) * W + y] : 99;
+  __shared__ int tile[64][65];
+  const int x0 = blockIdx.y * 64, y0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  const bool vec = (W & 3) == 0;                               // rows stay 16-byte aligned
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {                       // 16 rows x 16 int4 per pass
+    const int r = pass * 16 + (t >> 4), c = (t & 15) * 4;
+    const int x = x0 + r, y = y0 + c;
+    int4 v = make_int4(99, 99, 99, 99);
+    if (x < H) {
+      const int* src = matrix + static_cast<size_t>(x) * W + y;
+      if (vec && y + 3 < W) v = *reinterpret_cast<const int4*>(src);
+      else {
+        if (y < W) v.x = src[0];
+        if (y + 1 < W) v.y = src[1];
+        if (y + 2 < W) v.z = src[2];
+        if (y + 3 < W) v.w = src[3];
+      }
+    }
+    tile[r][c] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {                           // columns: fixed y, consecutive x
-    const int y = y0 + r, x = x0 + tx;
+#pragma unroll 4
+  for (int pass = 0; pass < 16; ++pass) {                      // 4 columns x 64 consecutive x per pass
+    const int r = pass * 4 + (t >> 6), xl = t & 63;
+    const int y = y0 + r, x = x0 + xl;
     if (x >= H || y >= W) continue;
     int wp, hp, loc;
     if (!dm::trunc_to_int(dm::sub(P.width_cells, static_cast<double>(static_cast<float>(y))), &wp)) continue;    // GC:85
     if (!dm::trunc_to_int(dm::sub(P.height_cells, static_cast<double>(static_cast<float>(x))), &hp)) continue;   // GC:86
     if (!dm::trunc_to_int(dm::add(static_cast<double>(hp), dm::mul(static_cast<double>(wp), P.height_cells)), &loc)) continue;
     if (loc < 0 || loc >= out_len) continue;                   // the reference writes past the end here
-    out[loc] = static_cast<int8_t>(tile[tx][r]);
+    out[loc] = static_cast<int8_t>(tile[xl][r]);
   }
 }
 
@@ -266,12 +295,17 @@ int pg_build(const pg_params* params, int device, const float* xy_host, const in
     const long long strokes = off[n_seg] * P.num_lanes * 2;
     if (strokes > 0) {
       const int blocks = static_cast<int>(std::min<long long>((strokes + 255) / 256, static_cast<long long>(sm) * 64));
-      pg_stroke_kernel<<<blocks, 256, 0, st>>>(d_seg, d_off, n_seg, off[n_seg], P, H, W, d_matrix);
+      PgRes R;
+      int ex2 = 0;
+      R.res = P.res;
+      R.pow2 = std::frexp(P.res, &ex2) == 0.5 && ex2 > -900 && ex2 < 900;
+      R.inv = R.pow2 ? 1.0 / P.res : 0.0;
+      pg_stroke_kernel<<<blocks, 256, 0, st>>>(d_seg, d_off, n_seg, off[n_seg], P, R, H, W, d_matrix);
       launches++;
     }
   }
   {
-    dim3 grid((W + 31) / 32, (H + 31) / 32);
+    dim3 grid((W + 63) / 64, (H + 63) / 64);
     pg_roadmap_kernel<<<grid, 256, 0, st>>>(d_matrix, H, W, P, d_out, out_len);
     launches++;
   }

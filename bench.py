@@ -500,6 +500,37 @@ def bench_costmap(args):
             out["cells_differing_from_reference"] = int((cm.build(scenes[0]) != node.build(scenes[0])[0]).sum())
             node.close()
     cm.close()
+    # row N3: the static global road map from the reference's own 303 road polylines (12000^2 cells)
+    edges = os.path.join(ROOT, "tests", "golden", "road_edges.npz")
+    if os.path.exists(edges):
+        from autonomouscar_b200 import GlobalRoadMap
+        z = np.load(edges)
+        ms = []
+        for _ in range(4):
+            gm = GlobalRoadMap(z["xy"], z["offsets"], device=0, want_host=False)
+            ms.append(gm.build_ms)
+            gm.close()
+        t0 = time.perf_counter()
+        gm = GlobalRoadMap(z["xy"], z["offsets"], device=0, want_host=True)
+        wall = time.perf_counter() - t0
+        g = {"config": "12000x12000 @0.25 m from the 303 road polylines of edges.csv (10403 segments)",
+             "device_ms": float(np.median(ms[1:])), "kernels": gm.launches, "e2e_ms_with_144MB_d2h": 1e3 * wall}
+        gold = os.path.join(ROOT, "tests", "golden", "ref_global_costmap.npz")
+        if os.path.exists(gold):
+            import hashlib
+            zz = np.load(gold)
+            sha = np.frombuffer(hashlib.sha256(gm.host.tobytes()).digest(), dtype=np.uint8)
+            g["identical_to_reference_published_grid"] = bool(np.array_equal(sha, zz["full_sha"]))
+            g["cpu_reference_ms_recorded_in_container"] = 1e3 * float(zz["full_ref_seconds"][0])
+        if not args.skip_cpu and have_ref and ref.global_costmap_available():
+            import tempfile
+            from autonomouscar_b200.costmap_capi import default_global_costmap_params
+            with tempfile.TemporaryDirectory() as d:
+                _, secs = ref.global_costmap_build(default_global_costmap_params(), z["xy"], z["offsets"], d)
+            g["cpu_reference_ms_1thread"] = 1e3 * secs
+            g["cpu_reference_kind"] = "reference: global_costmap.cpp compiled from the reference sources (oracle/_ref), g++ -O2, 1 thread"
+        gm.close()
+        out["global_road_map"] = g
     return out
 
 
