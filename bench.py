@@ -217,7 +217,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "extra": {"oracle_port_oriented_poses_per_s": port_v, "oracle_port_cores": cores},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # -----------------------------------------------------------------------------------------
@@ -422,7 +422,7 @@ def run_ours(args):
             "plans": plans,
             "costmap": costmap,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     pl.close()
     if multi:
         dist.destroy_process_group()
@@ -697,7 +697,25 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     return out
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE stdout line of the contract.  Everything else any library prints to fd 1 during the run
+    (NCCL's version banner, for one) has been diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
