@@ -40,6 +40,7 @@ constexpr int kWarpsMax = kTMax / 32;
 constexpr int kMaxVel = 64;        // velocities per expansion the kernel supports
 constexpr int kMaxCand = 8192;     // children per expansion the kernel supports
 constexpr int kIntMax = 0x7fffffff;
+constexpr int kFxMaxPoses = 512;   // longest path the pointer-walk extraction handles (longer: exact scan walk)
 
 struct PlanHdr {                   // per query, device -> host
   int status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions;
@@ -303,6 +304,7 @@ struct Shared {
   int fast;        // frontier mode of this attempt: 1 = unordered array + block argmin, 0 = exact binary heap
   int tie_seen;    // fast mode: some pop saw its minimum cost on more than one entry
   int top_pos, top_id;
+  int fx_len, fx_bad;   // pointer-walk extraction: path length, 1 = cannot be used
   long long pool_off;
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
   double scratch_key[6];  // key broadcast for the exact-scan fallback
@@ -425,7 +427,7 @@ __device__ __forceinline__ int frontier_top(const Heap& h, Shared* S, double* s_
 // openNode (LP:98-102) for one node by thread 0 + frontier push by warp 0.  Called by warp 0 only.
 template <bool kAllSmem>
 __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap, Shared* S, int hash_size,
-                                                 const double k[6], double g, double cost, int lane) {
+                                                 const double k[6], double g, double cost, int parent_slot, int lane) {
   const int id = S->n_nodes;
   const int hsize = S->heap_size;
   const int fast = S->fast;
@@ -434,6 +436,7 @@ __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap,
     w.cx[id] = k[0]; w.cy[id] = k[1]; w.px[id] = k[2]; w.py[id] = k[3]; w.hd[id] = k[4]; w.vel[id] = k[5];
     w.g[id] = g; w.cost[id] = cost;
     w.closed_seq[id] = -1;
+    w.rev_last[id] = parent_slot;   // slot that was being expanded when this node was opened (extraction hint)
     const unsigned long long fp = key_fingerprint(k);
     w.fp[id] = fp;
     if (hash_contains(w, hash_size, fp)) S->dup_seen = 1;
@@ -496,6 +499,8 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
   __shared__ unsigned long long s_dig[kWarpsMax];
   __shared__ double s_fcost[kWarpsMax];
   __shared__ int s_fpos[kWarpsMax], s_fcnt[kWarpsMax];
+  __shared__ uint32_t s_ph[kFxMaxPoses];   // hashes of the path poses (pointer-walk extraction)
+  __shared__ uint32_t s_bloom[64];         // 2048-bit filter over them
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pp_params& P = A.P;
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
     __syncthreads();
     if (warp == 0) {
       const double k0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, Q.start_speed};
-      open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k0, 0.0, 9999999999.0, lane);
+      open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k0, 0.0, 9999999999.0, -1, lane);
     }
     __syncthreads();
 
@@ -724,6 +729,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
           w.cx[id] = k[0]; w.cy[id] = k[1]; w.px[id] = k[2]; w.py[id] = k[3]; w.hd[id] = k[4]; w.vel[id] = k[5];
           w.g[id] = g; w.cost[id] = cost;
           w.closed_seq[id] = -1;
+          w.rev_last[id] = top_id;
           w.fp[id] = fp;
           hash_insert(w, A.hash_size, fp);
           if (S.fast) {   // openNode's frontier push: a plain append, position = heap size + rank
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
         if (warp == 0) {
           double k[6];
           for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
-          open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k, 0.0, 0.0, lane);             // LP:45
+          open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k, 0.0, 0.0, top_id, lane);     // LP:45
         }
         __syncthreads();
         if (tid == 0) S.status = PP_PLAN_FOUND;
@@ -809,6 +815,65 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
       int* rev_first = w.heap_id_g;  // slot of the first match per reversed pose
       int* rev_last = w.rev_last;    // slot of the last match per reversed pose
       const int rev_cap = NC;
+      int len = 1;
+      bool broken = false;
+      // ---- pointer walk (the common case) --------------------------------------------------
+      // Every node remembers the slot that was being expanded when it was opened (w.rev_last
+      // during the search).  Following those slots from the terminal node gives a chain whose
+      // consecutive child points are exactly parent_point links.  The reference walks by POINT
+      // equality (LP:509-527) and resolves poses to nodes by point equality (LP:554-575); the two
+      // agree whenever every pose of the chain is the child point of exactly one node, which one
+      // parallel pass over the tree verifies.  Otherwise (a goal hit at i = 0 repeats a pose, a
+      // duplicate was opened, ...) the exact scan walk below runs instead.
+      bool fast_walk = false;
+      {
+        int* sp = reinterpret_cast<int*>(smem_raw);                  // parent slots in the dead frontier's smem
+        const bool sp_fits = n_nodes <= A.heap_smem_entries * 4;
+        if (sp_fits) for (int id = tid; id < n_nodes; id += kT) sp[id] = w.rev_last[id];
+        if (tid < 64) s_bloom[tid] = 0u;
+        __syncthreads();
+        if (tid == 0) {
+          int id = n_nodes - 1, n = 0, bad = 0;                       // the terminal node was opened last (LP:45)
+          for (;;) {
+            if (n >= kFxMaxPoses || n >= rev_cap) { bad = 1; break; }
+            rev_first[n++] = id;
+            if (id == 0) break;                                       // the start node: child (0, 0), LP:509
+            id = sp_fits ? sp[id] : w.rev_last[id];
+            if (id < 0) { bad = 1; break; }
+          }
+          S.fx_len = n; S.fx_bad = bad;
+        }
+        __syncthreads();
+        if (!S.fx_bad) {
+          const int n = S.fx_len;
+          for (int k = tid; k < n; k += kT) {
+            const int id = rev_first[k];
+            const double x = w.cx[id], y = w.cy[id];
+            rev[2 * k] = x; rev[2 * k + 1] = y;
+            const uint32_t h = point_hash32(x, y);
+            s_ph[k] = h;
+            atomicOr(&s_bloom[(h >> 5) & 63], 1u << (h & 31));
+          }
+          __syncthreads();
+          int bad = 0;
+          for (int id = tid; id < n_nodes; id += kT) {
+            const double x = w.cx[id], y = w.cy[id];
+            const uint32_t h = point_hash32(x, y);
+            if ((s_bloom[(h >> 5) & 63] >> (h & 31)) & 1u) {
+              for (int k = 0; k < n; ++k)
+                if (s_ph[k] == h && rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y) bad = 1;
+            }
+          }
+          // consecutive poses must differ as well (LP:560 `else if`) -- implied by uniqueness, checked anyway
+          for (int k = tid; k + 1 < n; k += kT)
+            if (rev[2 * k] == rev[2 * k + 2] && rev[2 * k + 1] == rev[2 * k + 3]) bad = 1;
+          bad = block_max(bad, s_red);
+          if (!bad) { fast_walk = true; len = n; rev_last = rev_first; }
+        }
+        __syncthreads();
+      }
+      if (!fast_walk) {
+      // restore the slow path's scratch: w.rev_last is plain scratch from here on
       // a 32-bit hash of every child point fits the (dead) frontier's shared memory even in
       // batch mode; the scans below read it instead of the 16-byte points in L2 and verify
       // the rare hash hits against the real coordinates
@@ -849,9 +914,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
         *k_from = bf; *k_first = b0; *k_last = bl;
       };
       double cxp = S.goal_node[0], cyp = S.goal_node[1];
-      int len = 1;
       if (tid == 0) { rev[0] = cxp; rev[1] = cyp; rev_first[0] = -1; rev_last[0] = -1; }
-      bool broken = false;
       while (!(cxp == 0 && cyp == 0)) {               // LP:509 -- checked between passes only
         int pos = 0;
         bool progressed = false;
@@ -881,6 +944,7 @@ __global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
           rev_last[len - 1] = klast < 0 ? -1 : slot_of_key(w, n_nodes, klast);
         }
       }
+      }  // !fast_walk
       __syncthreads();
       if (broken) {
         if (tid == 0) S.status = PP_PLAN_BROKEN;
