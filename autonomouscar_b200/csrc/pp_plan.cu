@@ -490,8 +490,14 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
   return target;
 }
 
-template <bool kAllSmem>
-__global__ void __launch_bounds__(kTMax) plan_kernel(PlanArgs A) {
+// kBatchCtas > 0: the batch build -- 128 threads per CTA and a register budget that lets
+// kBatchCtas CTAs share an SM (each query is latency-bound on its own; throughput comes from
+// overlapping many of them).  0: the lone-query build, 256 threads, no register cap.
+#ifndef PP_PLAN_BATCH_CTAS
+#define PP_PLAN_BATCH_CTAS 6
+#endif
+template <bool kAllSmem, int kBatchCtas>
+__global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchCtas : 1) plan_kernel(PlanArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Shared S;
   __shared__ int s_red[kWarpsMax];
@@ -1143,12 +1149,17 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   else if (n > h->sm_count) heap_entries = std::min(heap_entries, 6144);
   const size_t dyn_smem = 16 * static_cast<size_t>(heap_entries);
   const bool all_smem = heap_entries >= NC;
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel<true, PP_PLAN_BATCH_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PP_CUDA(cudaFuncSetAttribute(plan_kernel<false, PP_PLAN_BATCH_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int ctas_per_sm = 1;
   const int threads = n > h->sm_count ? 128 : 256;
-  if (all_smem) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<true>, threads, dyn_smem));
-  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<false>, threads, dyn_smem));
+  const bool batch = threads == 128;
+  if (all_smem && batch) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<true, PP_PLAN_BATCH_CTAS>, threads, dyn_smem));
+  else if (all_smem) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<true, 0>, threads, dyn_smem));
+  else if (batch) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<false, PP_PLAN_BATCH_CTAS>, threads, dyn_smem));
+  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<false, 0>, threads, dyn_smem));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_ctas = h->sm_count * ctas_per_sm;
   const int grid = std::min(n, max_ctas);
@@ -1219,8 +1230,10 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   }
 
   PP_CUDA(cudaEventRecord(h->ev[8], s));
-  if (all_smem) plan_kernel<true><<<grid, threads, dyn_smem, s>>>(A);
-  else plan_kernel<false><<<grid, threads, dyn_smem, s>>>(A);
+  if (all_smem && batch) plan_kernel<true, PP_PLAN_BATCH_CTAS><<<grid, threads, dyn_smem, s>>>(A);
+  else if (all_smem) plan_kernel<true, 0><<<grid, threads, dyn_smem, s>>>(A);
+  else if (batch) plan_kernel<false, PP_PLAN_BATCH_CTAS><<<grid, threads, dyn_smem, s>>>(A);
+  else plan_kernel<false, 0><<<grid, threads, dyn_smem, s>>>(A);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   bool want_parent = false;
