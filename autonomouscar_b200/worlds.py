@@ -198,3 +198,44 @@ def costmap_corner_global_cells(params, car_x, car_y, car_yaw, halo=3):
             if 0 <= loc < hg * wg:
                 out.append(loc)
     return out
+
+
+def fill_costmap_tf(scene, car):
+    """Fill scene.inputs' tf-derived numbers for the frames of costmap_tfs(*car) directly (planar
+    car pose, lasers rolled about x only) -- what ros/local_costmap_b200_node.cpp reads from tf."""
+    tfs = costmap_tfs(*car)
+    for name, scan in (("front_right_laser_link", scene.inputs.right), ("front_left_laser_link", scene.inputs.left)):
+        x, y, z, roll, _, _ = tfs[(name, "center_laser_link")]
+        scan.roll, scan.tf_x, scan.tf_y = roll, x, y
+        scan.z_map = tfs[("map", name)][2]
+        scan.inv_x, scan.inv_y = -x, -(np.cos(roll) * y + np.sin(roll) * z)   # origin of the inverse: -(R^T t)
+    scene.inputs.center_z = tfs[("center_laser_link", "map")][2]
+    c, s = np.cos(car[2]), np.sin(car[2])
+    m = [c, -s, 0, car[0], s, c, 0, car[1], 0, 0, 1, 0]
+    inv = [c, s, 0, -(c * car[0] + s * car[1]), -s, c, 0, -(-s * car[0] + c * car[1]), 0, 0, 1, 0]
+    for i in range(12):
+        scene.inputs.map_from_base[i], scene.inputs.base_from_map[i] = m[i], inv[i]
+
+
+def densified_route(spacing=1.0):
+    """local_navigator.py:27-46: the global route with way-points every `spacing` metres (map frame)."""
+    pts = [(ROUTE_X[0], ROUTE_Y[0])]
+    for k in range(len(ROUTE_X) - 1):
+        x0, y0, x1, y1 = ROUTE_X[k], ROUTE_Y[k], ROUTE_X[k + 1], ROUTE_Y[k + 1]
+        d = float(np.hypot(x1 - x0, y1 - y0)) / spacing
+        if d > 1:
+            n = int(np.ceil(d))
+            for m in range(1, n + 1):
+                pts.append((x0 + m * (x1 - x0) / n, y0 + m * (y1 - y0) / n))
+        else:
+            pts.append((x1, y1))
+    return pts
+
+
+def next_waypoint(route, start_index, x, y, lookahead=20.0):
+    """local_navigator.py:586-609: the first way-point from `start_index` on that is at least
+    `lookahead` metres from the car.  Returns (index, (wx, wy)); the last one if none is that far."""
+    for k in range(start_index, len(route)):
+        if np.hypot(route[k][0] - x, route[k][1] - y) >= lookahead:
+            return k, route[k]
+    return len(route) - 1, route[-1]

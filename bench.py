@@ -453,16 +453,7 @@ def bench_costmap(args):
             ref.costmap_derive_inputs(sc)        # the tf numbers exactly as the reference node reads them
     else:
         for sc in scenes:                        # planar tf numbers computed directly
-            for name, scan in (("front_right_laser_link", sc.inputs.right), ("front_left_laser_link", sc.inputs.left)):
-                x, y, z, roll, _, _ = tfs[(name, "center_laser_link")]
-                scan.roll, scan.tf_x, scan.tf_y, scan.z_map = roll, x, y, tfs[("map", name)][2]
-                scan.inv_x, scan.inv_y = -x, -(np.cos(roll) * y + np.sin(roll) * z)
-            sc.inputs.center_z = tfs[("center_laser_link", "map")][2]
-            c, s_ = np.cos(car[2]), np.sin(car[2])
-            m = [c, -s_, 0, car[0], s_, c, 0, car[1], 0, 0, 1, 0]
-            inv = [c, s_, 0, -(c * car[0] + s_ * car[1]), -s_, c, 0, -(-s_ * car[0] + c * car[1]), 0, 0, 1, 0]
-            for i in range(12):
-                sc.inputs.map_from_base[i], sc.inputs.base_from_map[i] = m[i], inv[i]
+            worlds.fill_costmap_tf(sc, car)
     cm = LocalCostmap(p, device=0)
     cm.set_global_grid(gg)
     out = {"config": "300x300 @0.25 m, 2x640 rays, 16x512 cloud, 12000^2 global map (full_sim.launch sizes)"}
@@ -531,7 +522,61 @@ def bench_costmap(args):
             g["cpu_reference_kind"] = "reference: global_costmap.cpp compiled from the reference sources (oracle/_ref), g++ -O2, 1 thread"
         gm.close()
         out["global_road_map"] = g
+        out["stack_rollout"] = bench_stack(args, z)
     return out
+
+
+def bench_stack(args, edges, cycles=150):
+    """Rows N1-N3 chained with the hot path, everything resident on the GPU: the global road map is built
+    once (pg_build) and adopted by the costmap builder; then, per 20 Hz cycle along the reference's own route
+    (global_path_planner.py:101-102, densified and looked ahead as local_navigator.py:27-46,586-609 do):
+    pc_build (synthetic laser messages) -> pc_grid_dev -> pp_set_grid_dev -> pp_plan (as shipped) -> the car
+    advances along the planned path for one 50 ms period (kinematic stand-in for Gazebo)."""
+    import numpy as np
+
+    from autonomouscar_b200 import (PP_COLLISION_AS_SHIPPED, PP_PLAN_FOUND, GlobalRoadMap, LocalCostmap, Planner,
+                                    default_params, make_query, worlds)
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    gm = GlobalRoadMap(edges["xy"], edges["offsets"], device=0, want_host=False)
+    cm = LocalCostmap(default_costmap_params(), device=0)
+    cm.adopt_global_grid(gm)
+    pl = Planner(default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000), device=0)
+    route = worlds.densified_route()
+    scenes = [worlds.costmap_scene(50 + k) for k in range(8)]
+    x, y, yaw, v, wp = 0.0, 15.0, 0.0, 0.0, 0
+    t_cost, t_ingest, t_plan, found, dist = [], [], [], 0, 0.0
+    for k in range(cycles + 5):
+        sc = scenes[k % 8]
+        worlds.fill_costmap_tf(sc, (x, y, yaw))
+        t0 = time.perf_counter()
+        cm.build(sc, want_host=False)
+        t1 = time.perf_counter()
+        cm.feed_planner(pl)
+        pl.sync()
+        t2 = time.perf_counter()
+        wp, (wx, wy) = worlds.next_waypoint(route, wp, x, y)
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        gx, gy = c * (wx - x) + s_ * (wy - y), -s_ * (wx - x) + c * (wy - y)     # convertGoalToLocalFrame
+        r = pl.plan(make_query(gx, gy, start_speed=v), cap_nodes=8, want_nodes=False)
+        t3 = time.perf_counter()
+        if k >= 5:
+            t_cost.append(t1 - t0); t_ingest.append(t2 - t1); t_plan.append(t3 - t2)
+        if r.status == PP_PLAN_FOUND and r.n_profile > 0:
+            found += k >= 5
+            v = float(r.speeds[0])
+            yaw += float(r.yaw_rates[0]) * 0.05
+            x += v * 0.05 * np.cos(yaw)
+            y += v * 0.05 * np.sin(yaw)
+            dist += v * 0.05
+    cm.close()
+    pl.close()
+    med = lambda a: 1e3 * float(np.median(a))                                       # noqa: E731
+    tot = np.array(t_cost) + np.array(t_ingest) + np.array(t_plan)
+    return {"cycles": cycles, "plans_found": int(found), "metres_driven": dist,
+            "ms_costmap": med(t_cost), "ms_grid_ingest": med(t_ingest), "ms_plan": med(t_plan),
+            "ms_cycle": med(tot), "cycles_per_s": float(len(tot) / tot.sum()),
+            "note": "20 Hz is the reference's plan rate (local_navigator.py:529); its own nodes need ~20 ms for the "
+                    "costmap and 3-5 ms for a free-space plan per cycle on one core each"}
 
 
 def bench_plans(pl_unused, rank, world, dev, multi, args):

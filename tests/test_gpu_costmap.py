@@ -13,22 +13,8 @@ import make_costmap_golden as mcg  # noqa: E402
 
 
 def _fill_tf(sc, car):
-    """tf-derived numbers without the reference: planar, roll about x only (what costmap_tfs encodes)."""
     from autonomouscar_b200 import worlds
-    tfs = worlds.costmap_tfs(*car)
-    for name, scan in (("front_right_laser_link", sc.inputs.right), ("front_left_laser_link", sc.inputs.left)):
-        x, y, z, roll, _, _ = tfs[(name, "center_laser_link")]
-        cr, sr = np.cos(roll), np.sin(roll)
-        # inverse origin of a pure roll rotation R: -(R^T t)
-        scan.roll, scan.tf_x, scan.tf_y = roll, x, y
-        scan.z_map = tfs[("map", name)][2]
-        scan.inv_x, scan.inv_y = -x, -(cr * y + sr * z)
-    sc.inputs.center_z = tfs[("center_laser_link", "map")][2]
-    c, s = np.cos(car[2]), np.sin(car[2])
-    m = [c, -s, 0, car[0], s, c, 0, car[1], 0, 0, 1, 0]
-    inv = [c, s, 0, -(c * car[0] + s * car[1]), -s, c, 0, -(-s * car[0] + c * car[1]), 0, 0, 1, 0]
-    for i in range(12):
-        sc.inputs.map_from_base[i], sc.inputs.base_from_map[i] = m[i], inv[i]
+    worlds.fill_costmap_tf(sc, car)
 
 
 def test_costmap_bit_exact_vs_oracle(oracle, cuda_device):
@@ -161,3 +147,44 @@ def test_global_road_map_launch_file_size(cuda_device):
     assert ((got > 0) & (got < 99)).sum() > 1000  # road costs made it into the local grid
     cm.close()
     cm2.close()
+
+
+def test_stack_rollout_on_device(oracle, cuda_device):
+    """Rows N1-N3 chained with the hot path: global road map -> local costmap -> planner, the grid
+    never leaving the GPU, along the reference's own route; every cycle's plan equals the oracle's
+    plan for the same goal (as shipped: the grid does not influence the search, LP:445)."""
+    from autonomouscar_b200 import (PP_COLLISION_AS_SHIPPED, PP_PLAN_FOUND, GlobalRoadMap, LocalCostmap, Planner,
+                                    default_params, make_query, worlds)
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    xy, off = mgg.road_edges()
+    gm = GlobalRoadMap(xy, off, device=0, want_host=False)
+    cm = LocalCostmap(default_costmap_params(), device=0)
+    cm.adopt_global_grid(gm)
+    p = default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000)
+    pl = Planner(p, device=0)
+    route = worlds.densified_route()
+    x, y, yaw, v, wp = 0.0, 15.0, 0.0, 0.0, 0
+    road_cells = 0
+    for k in range(12):
+        sc = worlds.costmap_scene(70 + k)
+        worlds.fill_costmap_tf(sc, (x, y, yaw))
+        msg = cm.build(sc, want_host=True)
+        road_cells += int(((msg > 0) & (msg < 99)).sum())
+        cm.feed_planner(pl)
+        np.testing.assert_array_equal(pl.get_cspace(), oracle.cspace_from_msg(msg, 300, 300))
+        wp, (wx, wy) = worlds.next_waypoint(route, wp, x, y)
+        c, s = np.cos(yaw), np.sin(yaw)
+        q = make_query(c * (wx - x) + s * (wy - y), -s * (wx - x) + c * (wy - y), start_speed=v)
+        r = pl.plan(q)
+        ref = oracle.plan(p, None, q, math_mode=oracle.MATH_DET)
+        assert r.status == PP_PLAN_FOUND and r.summary() == ref.summary()
+        np.testing.assert_array_equal(r.path_xy, ref.path_xy)
+        np.testing.assert_array_equal(r.yaw_rates, ref.yaw_rates)
+        v = float(r.speeds[0])
+        yaw += float(r.yaw_rates[0]) * 0.05
+        x += v * 0.05 * np.cos(yaw)
+        y += v * 0.05 * np.sin(yaw)
+    assert x > 0.02, x                      # the car moved (it starts from rest, 12 cycles of 50 ms)
+    assert road_cells > 12 * 1000, road_cells   # the road overlay reached every local grid
+    cm.close()
+    pl.close()
