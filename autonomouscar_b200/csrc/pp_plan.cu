@@ -23,6 +23,8 @@
 //     reproduce the list scan order (open list in insertion order, then closed list in
 //     closing order).
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -1285,33 +1287,53 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   int ret = PP_OK;
   std::vector<double> soa;
   std::vector<int> iso;
-  for (int k = 0; k < n; ++k) {
+  // scatter of the packed pools into the caller's per-query arrays: plain memcpys, split over a
+  // few host threads for big batches (8192 queries = ~40 k small copies)
+  std::atomic<int> cap_err{0};
+  auto unpack = [&](int k_lo, int k_hi) {
+    for (int k = k_lo; k < k_hi; ++k) {
+      pp_result& r = rs[k];
+      const PlanHdr& d = hdr[k];
+      r.status = d.status;
+      r.n_expansions = d.n_expansions;
+      r.n_nodes = d.n_nodes;
+      r.n_open = d.n_open;
+      r.n_closed = d.n_closed;
+      r.n_path = d.n_path;
+      r.n_profile = d.n_profile;
+      r.n_candidates = d.n_candidates;
+      r.n_collisions = d.n_collisions;
+      r.tree_digest = d.digest;
+      const int np = std::min(d.n_path, std::min(r.cap_path, cap_path));
+      if (d.n_path > r.cap_path && (r.path_xy || r.path_node_ids)) cap_err.store(1);
+      if (r.path_xy) std::memcpy(r.path_xy, hpath + 2 * d.pool_off, sizeof(double) * 2 * np);
+      if (r.path_node_ids) std::memcpy(r.path_node_ids, hpid + d.pool_off, sizeof(int) * np);
+      const int nm = std::min(d.n_profile, std::min(r.cap_path, cap_path));
+      const double* pr = hprof + d.pool_off;
+      if (r.yaw_rates) std::memcpy(r.yaw_rates, pr, sizeof(double) * nm);
+      if (r.durations) std::memcpy(r.durations, pr + pool_cap, sizeof(double) * nm);
+      if (r.speeds) std::memcpy(r.speeds, pr + 2 * pool_cap, sizeof(double) * nm);
+      if (r.expansion_ids) {
+        const int ne = std::min(d.n_expansions, r.cap_expansions);
+        if (d.n_expansions > r.cap_expansions) cap_err.store(1);
+        std::memcpy(r.expansion_ids, hexp + static_cast<size_t>(k) * cap_exp, sizeof(int) * ne);
+      }
+    }
+  };
+  {
+    const int n_thr = n >= 2048 ? 4 : 1;
+    if (n_thr == 1) unpack(0, n);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < n_thr; ++t) th.emplace_back(unpack, static_cast<int>(static_cast<long long>(n) * t / n_thr),
+                                                      static_cast<int>(static_cast<long long>(n) * (t + 1) / n_thr));
+      for (auto& t : th) t.join();
+    }
+    if (cap_err.load()) ret = PP_ERR_CAPACITY;
+  }
+  for (int k = 0; k < n && want_nodes; ++k) {
     pp_result& r = rs[k];
     const PlanHdr& d = hdr[k];
-    r.status = d.status;
-    r.n_expansions = d.n_expansions;
-    r.n_nodes = d.n_nodes;
-    r.n_open = d.n_open;
-    r.n_closed = d.n_closed;
-    r.n_path = d.n_path;
-    r.n_profile = d.n_profile;
-    r.n_candidates = d.n_candidates;
-    r.n_collisions = d.n_collisions;
-    r.tree_digest = d.digest;
-    const int np = std::min(d.n_path, std::min(r.cap_path, cap_path));
-    if (d.n_path > r.cap_path && (r.path_xy || r.path_node_ids)) ret = PP_ERR_CAPACITY;
-    if (r.path_xy) std::memcpy(r.path_xy, hpath + 2 * d.pool_off, sizeof(double) * 2 * np);
-    if (r.path_node_ids) std::memcpy(r.path_node_ids, hpid + d.pool_off, sizeof(int) * np);
-    const int nm = std::min(d.n_profile, std::min(r.cap_path, cap_path));
-    const double* pr = hprof + d.pool_off;
-    if (r.yaw_rates) std::memcpy(r.yaw_rates, pr, sizeof(double) * nm);
-    if (r.durations) std::memcpy(r.durations, pr + pool_cap, sizeof(double) * nm);
-    if (r.speeds) std::memcpy(r.speeds, pr + 2 * pool_cap, sizeof(double) * nm);
-    if (r.expansion_ids) {
-      const int ne = std::min(d.n_expansions, r.cap_expansions);
-      if (d.n_expansions > r.cap_expansions) ret = PP_ERR_CAPACITY;
-      std::memcpy(r.expansion_ids, hexp + static_cast<size_t>(k) * cap_exp, sizeof(int) * ne);
-    }
     if (r.node_state || r.node_closed_seq || r.node_parent) {
       const int nn = std::min(d.n_nodes, r.cap_nodes);
       if (d.n_nodes > r.cap_nodes) ret = PP_ERR_CAPACITY;

@@ -108,13 +108,25 @@ class PlanBatch:
             r.durations = self.durations[k].ctypes.data_as(dp)
             r.speeds = self.speeds[k].ctypes.data_as(dp)
 
+    def _view(self):
+        """The pp_result array as a numpy structured array (no copy)."""
+        if getattr(self, "_np_view", None) is None:
+            names, formats, offsets = [], [], []
+            for name, ctype in pp_result._fields_:
+                names.append(name)
+                formats.append(np.dtype(ctype) if not hasattr(ctype, "contents") else np.dtype(np.uintp))
+                offsets.append(getattr(pp_result, name).offset)
+            dt = np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": C.sizeof(pp_result)})
+            self._np_view = np.frombuffer(self.raw, dtype=dt, count=self.n)
+        return self._np_view
+
     def field(self, name):
-        return np.array([getattr(self.raw[k], name) for k in range(self.n)])
+        return np.array(self._view()[name])
 
     def records(self):
         """[n, 5] int64: status, n_expansions, n_nodes, n_path, digest (low 63 bits)."""
+        v = self._view()
         out = np.empty((self.n, 5), dtype=np.int64)
-        for k in range(self.n):
-            r = self.raw[k]
-            out[k] = (r.status, r.n_expansions, r.n_nodes, r.n_path, r.tree_digest & 0x7FFFFFFFFFFFFFFF)
+        out[:, 0], out[:, 1], out[:, 2], out[:, 3] = v["status"], v["n_expansions"], v["n_nodes"], v["n_path"]
+        out[:, 4] = (v["tree_digest"] & np.uint64(0x7FFFFFFFFFFFFFFF)).astype(np.int64)
         return out
