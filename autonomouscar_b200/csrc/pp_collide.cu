@@ -8,6 +8,8 @@
 //              split the nu x nv sample lattice between them.
 //   With broad_phase = 0 every pose that overlaps the grid takes the narrow phase
 //   ("direct" mode, the gather-bound measurement).  Results are identical either way.
+#include <cstdlib>
+
 #include "pp_common.cuh"
 #include "pp_narrow.cuh"
 
@@ -44,7 +46,10 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
 //                        box test on the staged window, then the sample lattice
 //   NU == 0 selects the run-time lattice shape.  broad_phase == 0 ("direct") disables every
 //   pruning test: each pose that overlaps the grid runs the full lattice.
-constexpr int kPosesPerThread = 4;
+#ifndef PP_COLLIDE_PPT
+#define PP_COLLIDE_PPT 4
+#endif
+constexpr int kPosesPerThread = PP_COLLIDE_PPT;
 constexpr int kChunk = kThreads * kPosesPerThread;
 
 __device__ __forceinline__ int warp_append(int* counter, bool pred, int lane) {
@@ -189,7 +194,8 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
   } else if (mode == PP_COLLISION_REF_AABB) {
     collide_aabb_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, s>>>(h->grid, poses, flags, n);
   } else {
-    const int blocks = grid_blocks(h, n, kChunk, 8);
+    static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : 64;
+    const int blocks = grid_blocks(h, n, kChunk, bps);
     if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
       collide_oriented_kernel<48, 17, 2><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
     else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells

@@ -239,7 +239,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     multi = world > 1
     if multi:
-        dist.init_process_group("nccl", device_id=dev)
+        # result gathers run on a high-priority stream so that their (few) CTAs are scheduled as soon as
+        # collision-kernel CTAs retire instead of queueing behind the whole next launch
+        opts = None
+        if os.environ.get("PP_BENCH_NCCL_PRIORITY", "1") == "1":
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:
+                opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     grid = make_grid()
     p = params(PP_COLLISION_ORIENTED)
