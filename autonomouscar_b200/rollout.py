@@ -1,0 +1,175 @@
+"""Closed-loop route roll-outs without Gazebo.
+
+Host-side mirrors of the two small loops either side of the planner, so that "N independent
+queries" become N full drives along the reference's route:
+
+  * the query generator: catkin_ws/src/local_navigator/src/local_navigator.py
+      densify_route     :27-46    way-points every `distBetweenWP` = 1 m
+      WaypointSelector  :586-609  closest way-point from the current index on, then forward
+                                  until it is at least `mindistToNextWP` = 20 m away
+      query constants   :521-527  speed = max_speed = max_accel = 1.5, 20 Hz
+  * the profile follower: catkin_ws/src/prius_controller/src/controller.cpp
+      ProfileFollower   :144-158, 178-185   cursor through the /mp profile: entry k lasts
+                                  durations[k] / 1000 s of wall time, restarted on every new message
+
+The vehicle itself (Gazebo + the two PIDs of controller.cpp:44-132) is replaced by an ideal tracker:
+yaw rate and speed are taken from the profile entry under the cursor and integrated at the
+controller's 100 Hz (controller_node.cpp:14).  That stand-in is this repository's, not the
+reference's; everything it feeds -- every LocalNav goal, every plan, every profile -- goes through
+the same code paths as a live system.  The navigator is Python 2 / rospy and cannot be imported
+here, so these few lines are restated by hand ("parity unpinned" for them); the planner inside the
+loop is pinned (tests/test_rollout.py drives the REFERENCE node and the oracle through the same loop).
+
+`plan_batch` is any callable (list of pp_query) -> list of (found, yaw_rates, durations_ms, speeds):
+the CUDA planner (plan_batch_cuda), the oracle or the reference node (tests).
+"""
+import math
+
+import numpy as np
+
+from . import worlds
+from .capi import PP_PLAN_FOUND, make_query
+
+PLAN_HZ = 20            # local_navigator.py:529
+CONTROL_HZ = 100        # controller_node.cpp:14
+DIST_BETWEEN_WP = 1.0   # local_navigator.py:521
+MIN_DIST_TO_NEXT_WP = 20.0   # local_navigator.py:522
+SPEED = MAX_SPEED = MAX_ACCEL = 1.5   # local_navigator.py:524-527
+
+
+def densify_route(path, spacing=DIST_BETWEEN_WP):
+    """local_navigator.py:27-46."""
+    out = [list(path[0])]
+    for i in range(len(path) - 1):
+        (x0, y0), (x1, y1) = path[i], path[i + 1]
+        divide = math.sqrt((x1 - x0) ** 2 + (y1 - y0) ** 2) / spacing
+        if divide > 1:
+            n = math.ceil(divide)
+            dx, dy = (x1 - x0) / n, (y1 - y0) / n
+            for k in range(1, int(n + 1)):
+                out.append([x0 + k * dx, y0 + k * dy])
+        else:
+            out.append([x1, y1])
+    return out
+
+
+def reference_route():
+    """The 12 way-points global_path_planner.py:101-102 publishes on /path, densified."""
+    return densify_route(list(zip(worlds.ROUTE_X, worlds.ROUTE_Y)))
+
+
+class WaypointSelector:
+    """local_navigator.py:586-609 (the no-obstacle branch): one instance per car."""
+
+    def __init__(self, route, min_dist=MIN_DIST_TO_NEXT_WP):
+        self.route, self.min_dist, self.path_index = route, min_dist, 0
+
+    def select(self, x, y):
+        r, n = self.route, len(self.route)
+        closest = 5000.0
+        for i in range(self.path_index, n):                      # :590-597
+            d = math.sqrt((x - r[i][0]) ** 2 + (y - r[i][1]) ** 2)
+            if d < closest:
+                self.path_index, closest = i, d
+            else:
+                break
+        d = math.sqrt((x - r[self.path_index][0]) ** 2 + (y - r[self.path_index][1]) ** 2)
+        while d < self.min_dist:                                  # :603-609
+            if self.path_index >= n - 1:                          # (the reference would run off the list here)
+                break
+            self.path_index += 1
+            if self.path_index == n - 1:
+                break
+            d = math.sqrt((x - r[self.path_index][0]) ** 2 + (y - r[self.path_index][1]) ** 2)
+        return r[self.path_index]
+
+
+class ProfileFollower:
+    """controller.cpp:144-158 / 178-185: which profile entry is being tracked at time t."""
+
+    def __init__(self):
+        self.yaw_rates, self.durations, self.speeds = (), (), ()
+        self.it, self.start = 0, 0.0
+
+    def new_profile(self, t, yaw_rates, durations_ms, speeds):     # motionPlanningCallback
+        self.yaw_rates, self.durations, self.speeds = yaw_rates, durations_ms, speeds
+        self.it, self.start = 0, t
+
+    def command(self, t):
+        """(yaw_rate, speed) at time t, or None when there is no entry left ("good luck", :154-157)."""
+        if self.it < len(self.durations) and (t - self.start) >= self.durations[self.it] / 1000:   # :148-153
+            self.start = t
+            self.it += 1
+        if self.it >= len(self.yaw_rates):
+            return None
+        return self.yaw_rates[self.it], self.speeds[self.it]
+
+
+class RouteRollout:
+    """S independent cars on the reference route, stepped in lock-step at the 20 Hz plan rate."""
+
+    def __init__(self, starts, route=None):
+        """starts: iterable of (x, y, yaw, speed) in the map frame."""
+        self.route = route if route is not None else reference_route()
+        st = np.array(list(starts), dtype=np.float64).reshape(-1, 4)
+        self.x, self.y, self.yaw, self.v = st[:, 0].copy(), st[:, 1].copy(), st[:, 2].copy(), st[:, 3].copy()
+        self.n = len(st)
+        self.selectors = [WaypointSelector(self.route) for _ in range(self.n)]
+        self.followers = [ProfileFollower() for _ in range(self.n)]
+        self.t = 0.0
+        self.plans = self.found = 0
+        self.trace = []
+
+    def queries(self):
+        """One LocalNav per car, goal converted to its base_link frame (LP:670-691)."""
+        qs = []
+        for k in range(self.n):
+            wx, wy = self.selectors[k].select(self.x[k], self.y[k])
+            c, s = math.cos(self.yaw[k]), math.sin(self.yaw[k])
+            dx, dy = wx - self.x[k], wy - self.y[k]
+            qs.append(make_query(c * dx + s * dy, -s * dx + c * dy, goal_speed=SPEED, max_speed=MAX_SPEED,
+                                 max_accel=MAX_ACCEL, start_speed=float(self.v[k]), query_id=k))
+        return qs
+
+    def tick(self, plan_batch):
+        results = plan_batch(self.queries())
+        self.plans += self.n
+        for k, (found, yaw_rates, durations, speeds) in enumerate(results):
+            if found:                                   # a failed plan publishes nothing: the old profile stays
+                self.found += 1
+                self.followers[k].new_profile(self.t, yaw_rates, durations, speeds)
+        dt = 1.0 / CONTROL_HZ
+        for _ in range(CONTROL_HZ // PLAN_HZ):          # ideal tracking of the profile at the controller rate
+            for k in range(self.n):
+                cmd = self.followers[k].command(self.t)
+                if cmd is None:
+                    continue
+                self.yaw[k] += cmd[0] * dt
+                self.v[k] = cmd[1]
+                self.x[k] += self.v[k] * dt * math.cos(self.yaw[k])
+                self.y[k] += self.v[k] * dt * math.sin(self.yaw[k])
+            self.t += dt
+        self.trace.append(np.stack([self.x, self.y, self.yaw, self.v], 1).copy())
+
+    def run(self, plan_batch, ticks):
+        for _ in range(ticks):
+            self.tick(plan_batch)
+        return np.array(self.trace)
+
+
+def plan_batch_cuda(planner, cap_path=256):
+    """plan_batch callable on top of pp_plan_batch (one C-ABI call per tick for all cars)."""
+    from .capi import pp_query
+    from .results import PlanBatch
+    cache = {}
+
+    def run(queries):
+        n = len(queries)
+        if n not in cache:
+            cache[n] = PlanBatch(n, cap_path=cap_path)
+        buf = cache[n]
+        planner.plan_batch_into((pp_query * n)(*queries), buf)
+        st, npf = buf.field("status"), buf.field("n_profile")
+        return [(st[k] == PP_PLAN_FOUND, buf.yaw_rates[k, :npf[k]].copy(), buf.durations[k, :npf[k]].copy(),
+                 buf.speeds[k, :npf[k]].copy()) for k in range(n)]
+    return run

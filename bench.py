@@ -531,7 +531,38 @@ def bench_costmap(args):
         gm.close()
         out["global_road_map"] = g
         out["stack_rollout"] = bench_stack(args, z)
+    out["route_rollouts"] = bench_rollouts(args)
     return out
+
+
+def bench_rollouts(args, cars=1024, ticks=20):
+    """Row N4: `cars` independent closed-loop drives along the reference route, one pp_plan_batch call per
+    20 Hz tick (way-point rule of local_navigator.py:586-609, profile follower of controller.cpp:144-158,
+    ideal tracker).  The host loop around the call is plain Python; the planning share is timed separately."""
+    from autonomouscar_b200 import PP_COLLISION_AS_SHIPPED, Planner, default_params, rollout
+    pl = Planner(default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000), device=0)
+    starts = [(0.12 * k, 15.0 + 0.05 * (k % 5), 0.02 * ((k % 7) - 3), 0.1 * (k % 12)) for k in range(cars)]
+    ro = rollout.RouteRollout(starts)
+    inner = rollout.plan_batch_cuda(pl)
+    t_plan = [0.0]
+
+    def timed(qs):
+        t0 = time.perf_counter()
+        r = inner(qs)
+        t_plan[0] += time.perf_counter() - t0
+        return r
+    ro.tick(timed)                      # warm-up tick
+    t_plan[0] = 0.0
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        ro.tick(timed)
+    wall = time.perf_counter() - t0
+    pl.close()
+    sim_s = ticks / 20.0
+    return {"cars": cars, "ticks": ticks, "plans": cars * ticks, "found": int(ro.found - cars),
+            "plans_per_s_in_plan_calls": cars * ticks / t_plan[0], "car_ticks_per_s_whole_loop": cars * ticks / wall,
+            "real_time_factor_planning_only": sim_s / t_plan[0], "real_time_factor_whole_loop": sim_s / wall,
+            "mean_metres_driven": float((ro.x - [s_[0] for s_ in starts]).mean())}
 
 
 def bench_stack(args, edges, cycles=150):
