@@ -1,9 +1,10 @@
 """autonomouscar_b200 -- B200-native hot path of the WPI AutonomousCar local planner.
 
 Only what the path needs lives here: `csrc/` (CUDA kernels + the C ABI of
-include/prius_planner.h), the ctypes binding (`planner.Planner`), the message-level
-mirror of the reference node (`node.LocalPlannerNode`) and synthetic-workload helpers
-for tests and bench (`worlds`).
+include/prius_planner.h, prius_costmap.h), the ctypes bindings (`planner.Planner`,
+`costmap.LocalCostmap`, `costmap.GlobalRoadMap`), the C++ host mirrors of the reference nodes
+(`host/`), closed-loop roll-outs (`rollout`) and synthetic-workload helpers for tests and
+bench (`worlds`).
 """
 from .capi import *  # noqa: F401,F403  (enums, structs, default_params, make_query)
 from .results import PlanBatch, PlanResult  # noqa: F401
@@ -18,7 +19,4 @@ def __getattr__(name):
     if name in ("LocalCostmap", "GlobalRoadMap"):
         from . import costmap
         return getattr(costmap, name)
-    if name == "LocalPlannerNode":
-        from . import node
-        return node.LocalPlannerNode
     raise AttributeError(name)
