@@ -383,7 +383,7 @@ def run_ours(args):
         k_ms = sum(kernel_ms) / len(kernel_ms)
         achieved = ALG_BYTES_ORIENTED * n / (k_ms * 1e-3) / 1e9
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             v_port, secs_port = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 22, cores)
             v1, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 20, 1)
