@@ -207,3 +207,21 @@ def test_cuda_search_equals_the_reference_search(cuda_device):
             np.testing.assert_array_equal(res.speeds, z[pre + "speeds"])
             np.testing.assert_array_equal(res.durations, z[pre + "durations"])
             pl.close()
+
+
+@pytest.mark.gpu
+def test_cuda_ref_aabb_collision_equals_the_reference_booleans(cuda_device):
+    """pp_collide_batch in REF_AABB mode against the booleans the REFERENCE's own checkCollision
+    returned (fixture from oracle/_ref; `2` marks poses where the reference indexes out of bounds)."""
+    from autonomouscar_b200 import Planner
+    z = _gold()
+    p = mrg.params(PP_COLLISION_REF_AABB, 10, 10)
+    pl = Planner(p, device=0)
+    pl.set_grid(mrg.msg_grid().reshape(300, 300), layout=PP_GRID_OCCUPANCY_MSG)
+    poses = mrg.collision_poses()
+    got = pl.collide(poses)
+    want = z["collision_flags"]
+    defined = want < 2
+    np.testing.assert_array_equal(got[defined], want[defined])
+    assert want[defined].sum() > 500
+    pl.close()
