@@ -307,6 +307,11 @@ struct Shared {
   int tie_seen;    // fast mode: some pop saw its minimum cost on more than one entry
   int top_pos, top_id;
   int fx_len, fx_bad;   // pointer-walk extraction: path length, 1 = cannot be used
+  // fast frontier: the runner-up found by an argmin pass serves the NEXT pop when no push happens in
+  // between (planPath pops twice in a row: LP:80, then LP:40 of the next iteration)
+  int next_valid, next_pos;
+  int chk_valid;            // a runner-up was popped from the cache; its cost must be shown unique by the next pass
+  double next_cost, chk_cost;
   long long pool_off;
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
   double scratch_key[6];  // key broadcast for the exact-scan fallback
@@ -378,49 +383,76 @@ __device__ __forceinline__ void hash_insert(const WS& w, int hash_size, unsigned
 // block-wide argmin; if any pop ever sees its minimum cost on two entries the query is
 // re-run from scratch with the exact libstdc++ heap, so results are always the reference's.
 // ---------------------------------------------------------------------------------------
+// One pass finds the cheapest entry AND the runner-up (c2 == c1 exactly when the minimum is tied).
+// If the previous pop came out of the runner-up cache, the pass also looks for entries that share
+// that pop's cost (`chk`): such an entry means the cached pop was tied (or a child pushed since has
+// the same cost -- a false alarm that only costs the exact re-run).
+__device__ __forceinline__ void top2_insert(double& c1, int& p1, double& c2, int& p2, double c, int p) {
+  if (p < 0) return;
+  if (p1 < 0 || c < c1) { c2 = c1; p2 = p1; c1 = c; p1 = p; }
+  else if (p2 < 0 || c < c2) { c2 = c; p2 = p; }
+}
 template <bool kAllSmem>
 __device__ __forceinline__ void fast_find_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt) {
   const int n = S->heap_size;
-  double bc = 0;
-  int bp = -1, cnt = 0;
+  const bool chk_on = S->chk_valid != 0;
+  const double chk = S->chk_cost;
+  double c1 = 0, c2 = 0;
+  int p1 = -1, p2 = -1, tie = 0;
   for (int k = threadIdx.x; k < n; k += kT) {
-    const HeapEnt e = hget<kAllSmem>(h, k);
-    if (bp < 0 || e.cost < bc) { bc = e.cost; bp = k; cnt = 1; }
-    else if (e.cost == bc) cnt++;
+    const double c = hget<kAllSmem>(h, k).cost;
+    if (chk_on && c == chk) tie = 1;
+    top2_insert(c1, p1, c2, p2, c, k);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
-    const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
-    const int op = __shfl_xor_sync(0xffffffffu, bp, off), on = __shfl_xor_sync(0xffffffffu, cnt, off);
-    if (op >= 0) {
-      if (bp < 0 || oc < bc) { bc = oc; bp = op; cnt = on; }
-      else if (oc == bc) { cnt += on; bp = min(bp, op); }
-    }
+    const double oc1 = __shfl_xor_sync(0xffffffffu, c1, off), oc2 = __shfl_xor_sync(0xffffffffu, c2, off);
+    const int op1 = __shfl_xor_sync(0xffffffffu, p1, off), op2 = __shfl_xor_sync(0xffffffffu, p2, off);
+    top2_insert(c1, p1, c2, p2, oc1, op1);
+    top2_insert(c1, p1, c2, p2, oc2, op2);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_cost[warp] = bc; s_pos[warp] = bp; s_cnt[warp] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double c = s_cost[0];
-    int p = s_pos[0], m = s_cnt[0];
-    for (int w = 1; w < kWarps; ++w) {
-      const int op = s_pos[w];
-      if (op < 0) continue;
-      if (p < 0 || s_cost[w] < c) { c = s_cost[w]; p = op; m = s_cnt[w]; }
-      else if (s_cost[w] == c) { m += s_cnt[w]; p = min(p, op); }
-    }
-    S->top_pos = p;
-    S->top_id = hget<kAllSmem>(h, p).id;
-    if (m > 1) S->tie_seen = 1;
+  if (lane == 0) {
+    s_cost[2 * warp] = c1; s_pos[2 * warp] = p1;
+    s_cost[2 * warp + 1] = c2; s_pos[2 * warp + 1] = p2;
   }
+  const int any_tie = __syncthreads_or(tie);
+  if (threadIdx.x == 0) {
+    double r1 = 0, r2 = 0;
+    int q1 = -1, q2 = -1;
+    for (int w = 0; w < 2 * kWarps; ++w) top2_insert(r1, q1, r2, q2, s_cost[w], s_pos[w]);
+    S->top_pos = q1;
+    S->top_id = hget<kAllSmem>(h, q1).id;
+    if ((q2 >= 0 && r2 == r1) || any_tie) S->tie_seen = 1;
+    S->next_valid = q2 >= 0 ? 1 : 0;
+    S->next_pos = q2;
+    S->next_cost = r2;
+    S->chk_valid = 0;
+  }
+  (void)s_cnt;
   __syncthreads();
 }
 
 // frontier.top(): slot id of the cheapest entry (block-wide; all threads get the same value)
+// `use_cached`: the previous pop was the last frontier operation (no push since), so the
+// runner-up it found is the minimum now.
 template <bool kAllSmem>
-__device__ __forceinline__ int frontier_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt) {
+__device__ __forceinline__ int frontier_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt,
+                                            bool use_cached) {
   if (S->fast) {
-    fast_find_top<kAllSmem>(h, S, s_cost, s_pos, s_cnt);
+    if (use_cached && S->next_valid) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        S->top_pos = S->next_pos;
+        S->top_id = hget<kAllSmem>(h, S->next_pos).id;
+        S->chk_valid = 1;                // uniqueness of this cost is established by the next pass
+        S->chk_cost = S->next_cost;
+        S->next_valid = 0;
+      }
+      __syncthreads();
+    } else {
+      fast_find_top<kAllSmem>(h, S, s_cost, s_pos, s_cnt);
+    }
     return S->top_id;
   }
   return h.s[0].id;
@@ -451,7 +483,7 @@ __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap,
   }
   __syncwarp();
   if (!fast) heap_sift_up_warp<kAllSmem>(heap, hsize, cost, id, lane);
-  if (lane == 0) { S->n_nodes = id + 1; S->heap_size = hsize + 1; }
+  if (lane == 0) { S->n_nodes = id + 1; S->heap_size = hsize + 1; S->next_valid = 0; }
   __syncwarp();
 }
 
@@ -481,6 +513,7 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
       if (threadIdx.x == 0) {   // remove by moving the last entry into the hole
         const int pos = S->top_pos;
         if (pos != hsize - 1) hset<kAllSmem>(heap, pos, hget<kAllSmem>(heap, hsize - 1));
+        if (S->next_valid && S->next_pos == hsize - 1) S->next_pos = pos;   // the runner-up was that last entry
         S->heap_size = hsize - 1;
       }
     } else {
@@ -505,8 +538,8 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
   __shared__ int s_red[kWarpsMax];
   __shared__ int s_scan[kWarpsMax];
   __shared__ unsigned long long s_dig[kWarpsMax];
-  __shared__ double s_fcost[kWarpsMax];
-  __shared__ int s_fpos[kWarpsMax], s_fcnt[kWarpsMax];
+  __shared__ double s_fcost[2 * kWarpsMax];
+  __shared__ int s_fpos[2 * kWarpsMax], s_fcnt[2 * kWarpsMax];
   __shared__ uint32_t s_ph[kFxMaxPoses];   // hashes of the path poses (pointer-walk extraction)
   __shared__ uint32_t s_bloom[64];         // 2048-bit filter over them
 
@@ -550,7 +583,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
       S.n_cand_total = 0; S.n_coll_total = 0; S.goal_hit = 0; S.path_len = 0; S.truncated = 0; S.done = 0;
       S.fast = (attempt == 0 && A.fast_frontier) ? 1 : 0;
-      S.tie_seen = 0; S.top_pos = 0; S.top_id = 0;
+      S.tie_seen = 0; S.top_pos = 0; S.top_id = 0; S.next_valid = 0; S.next_pos = 0; S.chk_valid = 0; S.next_cost = 0; S.chk_cost = 0;
       for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
     }
     __syncthreads();
@@ -566,7 +599,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       // caps replace the ros::Time guard of LP:33-39
       if (S.n_exp >= P.max_expansions || S.n_nodes >= P.max_nodes) { if (tid == 0) S.status = PP_PLAN_CAP; break; }
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }  // top() of an empty queue
-      const int top_id = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt);  // LP:40
+      const int top_id = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt, true);   // LP:40 (runner-up of LP:80's pass)
       // current_node's fields are key fields, identical for every copy of the node
       const double ncx = w.cx[top_id], ncy = w.cy[top_id], npx = w.px[top_id], npy = w.py[top_id];
       const double nhd = w.hd[top_id], nvel = w.vel[top_id];
@@ -750,6 +783,13 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         __syncthreads();
       }
       if (goal_stop) {
+        if (S.fast && S.chk_valid) {      // the pop that led here came from the runner-up cache: show it was unique
+          const double chk = S.chk_cost;
+          int tie = 0;
+          for (int k2 = tid; k2 < S.heap_size; k2 += kT) tie |= hget<kAllSmem>(heap, k2).cost == chk ? 1 : 0;
+          if (__syncthreads_or(tie) && tid == 0) S.tie_seen = 1;
+          __syncthreads();
+        }
         if (warp == 0) {
           double k[6];
           for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
@@ -780,6 +820,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         }
         if (lane == 0) {
           S.heap_size = hsize;
+          if (appended > 0) S.next_valid = 0;
           S.n_nodes = base_nodes + appended;
           S.n_cand_total += n_cand;
           S.n_coll_total += collided_local;
@@ -789,7 +830,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       PP_TICK(4);
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }
       {
-        const int top2 = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt);
+        const int top2 = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt, false);
         __syncthreads();
         close_top<kAllSmem>(w, heap, &S, top2, s_red);                                          // LP:80
       }
