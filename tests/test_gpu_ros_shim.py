@@ -165,3 +165,33 @@ def test_ros_costmap_shim_publishes_the_reference_nodes_grid(cuda_device, tmp_pa
         assert (got != want).mean() < 1e-3, int((got != want).sum())
         assert (got == 100).sum() > 1000
     node.close()
+
+
+def test_ros_global_costmap_shim_publishes_the_reference_nodes_map(cuda_device, tmp_path):
+    """Row N3: ros/global_costmap_b200_node.cpp, compiled unchanged against the ROS test doubles, reads the
+    same edges.csv-format file as the reference's global_costmap node (oracle/_ref) and publishes the same
+    /global_costmap, byte for byte."""
+    import sys
+    from oracle import ref_binding as ref
+    if not ref.global_costmap_available():
+        pytest.skip("oracle/_ref not present")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_global_costmap_golden as mgg
+    exe = str(tmp_path / "test_ros_global_costmap_shim")
+    pkg = os.path.join(ROOT, "autonomouscar_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "oracle", "ros_doubles"),
+                           "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_ros_global_costmap_shim.cpp"), "-o", exe,
+                           "-L", pkg, "-lprius_planner_b200", f"-Wl,-rpath,{pkg}"])
+    xy, off = mgg.synth_polylines(31, n_lines=10)
+    p = mgg.small_params(2, 11.1)
+    want, _ = ref.global_costmap_build(p, xy, off, tmp_path)          # also leaves edges_for_ref.csv in tmp_path
+    out = str(tmp_path / "global.bin")
+    line = subprocess.check_output([exe, str(tmp_path / "edges_for_ref.csv"), out, "0.25", "11.1", "2",
+                                    repr(mgg.SMALL * 0.25), repr(mgg.SMALL * 0.25)]).decode().split()
+    assert line[0] == "published" and line[1] == "1" and line[2] == "map"
+    assert (int(line[3]), int(line[4])) == (mgg.SMALL, mgg.SMALL) and float.fromhex(line[5]) == 0.25
+    assert float.fromhex(line[6]) == -mgg.SMALL / 8 and float.fromhex(line[7]) == -mgg.SMALL / 8      # GC:69-70
+    got = np.fromfile(out, dtype=np.int8)
+    np.testing.assert_array_equal(got, want)
+    assert ((got >= 0) & (got < 99)).sum() > 100000
