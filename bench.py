@@ -111,6 +111,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(inside), "power_w_max": max(pw) if pw else None}
 
 
+def bind_to_gpu_cpus(local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end leg are first-touched on the GPU's NUMA node (8 ranks pulling 52 GB/s each through one node's
+    memory controller is what limits e2e otherwise).  Best effort; returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                idx = int(ids[local])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def make_grid():
     from autonomouscar_b200 import worlds
     return worlds.block_grid(GRID, GRID, frac=0.01, block=16, seed=20181)
@@ -238,6 +258,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     multi = world > 1
+    numa = bind_to_gpu_cpus(local) if multi else None   # pinned host buffers of the e2e leg land next to the GPU
+    if multi:
+        args.skip_cpu = True                            # CPU-side figures are reported at N = 1 only
     if multi:
         # result gathers run on a high-priority stream so that their (few) CTAs are scheduled as soon as
         # collision-kernel CTAs retire instead of queueing behind the whole next launch
@@ -414,7 +437,8 @@ def run_ours(args):
             "config": {"workload": "BASELINE configs[2]: 2^24 oriented-footprint poses per GPU vs 4096x4096 "
                                    "grid @0.1 m, 1% area in 16x16-cell blocks; flags all-gathered (NCCL) when N>1",
                        "poses_per_gpu": n, "collision_mode": "ORIENTED", "broad_phase": True,
-                       "hit_rate": hit_rate, "l2_policy": "inputs larger than L2 (201 MB poses per step)"},
+                       "hit_rate": hit_rate, "l2_policy": "inputs larger than L2 (201 MB poses per step)",
+                       "rank_cpu_affinity": numa},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": n},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
