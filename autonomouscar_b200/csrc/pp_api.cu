@@ -140,6 +140,7 @@ int pp_destroy(pp_handle* h) {
   cudaFree(h->d_flags);
   cudaFree(h->d_list);
   cudaFree(h->d_visited);
+  cudaFree(h->d_nn_best);
   cudaFree(h->d_count);
   cudaFreeHost(h->h_count);
   cudaFree(h->scratch);

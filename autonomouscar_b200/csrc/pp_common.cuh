@@ -260,6 +260,8 @@ struct pp_handle {
   void* scratch = nullptr;         // grid-prep scratch
   size_t scratch_bytes = 0;
   uint8_t* d_visited = nullptr;    // A12 debug bitmap of the last single plan (W*H bytes)
+  unsigned long long* d_nn_best = nullptr;   // nearest-neighbour merge cells, one per query
+  int64_t nn_cap = 0;
   PlanWorkspace* plan_ws = nullptr;
   RrtWorkspace* rrt_ws = nullptr;
 };

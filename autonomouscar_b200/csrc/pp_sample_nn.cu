@@ -4,6 +4,9 @@
 //   A6  the reference's std::find + GraphNode::operator== lookups (local_planner.cpp:56-57,
 //       graph_node.hpp:24-30) as an exact-match query: first index whose 6 key doubles
 //       all compare ==
+#include <algorithm>
+#include <cstdlib>
+
 #include "pp_common.cuh"
 #include "pp_philox.cuh"
 
@@ -78,6 +81,63 @@ nearest_kernel(const float2* __restrict__ nodes, int64_t n_nodes, const float2* 
         if (out_d2) out_d2[qi] = best[q];
       }
     }
+  }
+}
+
+// Large problems: register-blocked and tiled.  A CTA owns kTQ * 256 queries (kTQ per thread, in
+// registers) and one slice of the nodes; node tiles go through shared memory once per CTA and every
+// LDS.64 feeds kTQ distance evaluations.  Slices are merged with one 64-bit atomicMin per query on
+// (dist2 bits << 32 | index): squared distances are >= +0, so their bit patterns order like the
+// values and the low word breaks ties towards the lowest index -- the same rule as the warp kernel
+// (within a thread the scan is ascending with a strict <).
+constexpr int kTQ = 4;
+constexpr int kTNodeTile = 2048;
+__global__ void __launch_bounds__(256)
+nearest_tiled_kernel(const float2* __restrict__ nodes, int64_t n_nodes, int64_t slice_nodes,
+                     const float2* __restrict__ queries, int64_t n_query, unsigned long long* __restrict__ best_cells) {
+  __shared__ float2 tile[kTNodeTile];
+  const int64_t q0 = (static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x) * kTQ;
+  const int64_t lo = static_cast<int64_t>(blockIdx.x) * slice_nodes;
+  const int64_t hi = min(lo + slice_nodes, n_nodes);
+  float qx[kTQ], qy[kTQ], best[kTQ];
+  int bi[kTQ];
+#pragma unroll
+  for (int q = 0; q < kTQ; ++q) {
+    const float2 v = q0 + q < n_query ? queries[q0 + q] : make_float2(0.f, 0.f);
+    qx[q] = v.x; qy[q] = v.y; best[q] = __int_as_float(0x7f800000); bi[q] = -1;
+  }
+  for (int64_t t0 = lo; t0 < hi; t0 += kTNodeTile) {
+    const int64_t left = hi - t0;
+    const int cnt = left < kTNodeTile ? static_cast<int>(left) : kTNodeTile;
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) tile[j] = __ldg(&nodes[t0 + j]);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const float2 nd = tile[j];
+      const int k = static_cast<int>(t0) + j;
+#pragma unroll
+      for (int q = 0; q < kTQ; ++q) {
+        const float dx = __fsub_rn(qx[q], nd.x), dy = __fsub_rn(qy[q], nd.y);
+        const float d = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+        if (d < best[q]) { best[q] = d; bi[q] = k; }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kTQ; ++q)
+    if (q0 + q < n_query && bi[q] >= 0)
+      atomicMin(&best_cells[q0 + q], (static_cast<unsigned long long>(__float_as_uint(best[q])) << 32) |
+                                         static_cast<unsigned>(bi[q]));
+}
+__global__ void nearest_unpack_kernel(const unsigned long long* __restrict__ best_cells, int64_t n_query,
+                                      int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n_query;
+       q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const unsigned long long c = best_cells[q];
+    const bool none = c == ~0ull;
+    out_idx[q] = none ? -1 : static_cast<int32_t>(static_cast<unsigned>(c));
+    if (out_d2) out_d2[q] = none ? 0.f : __uint_as_float(static_cast<unsigned>(c >> 32));
   }
 }
 
@@ -184,6 +244,29 @@ int l2_gather_bench(pp_handle* h, size_t buffer_bytes, double* out_gbps) {
 int nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy, int64_t n_query, const float* q,
                 int32_t* idx, float* d2) {
   if (n_query == 0) return PP_OK;
+  // the tiled kernel assumes finite coordinates, int-sized node counts and enough work to fill the GPU
+  if (n_nodes >= 4096 && n_nodes < (1ll << 31) && n_query >= 1024 && !getenv("PP_NN_WARP_KERNEL")) {
+    if (n_query > h->nn_cap) {
+      cudaFree(h->d_nn_best);
+      h->d_nn_best = nullptr; h->nn_cap = 0;
+      PP_CUDA(cudaMalloc(&h->d_nn_best, sizeof(unsigned long long) * static_cast<size_t>(n_query)));
+      h->nn_cap = n_query;
+    }
+    PP_CUDA(cudaMemsetAsync(h->d_nn_best, 0xFF, sizeof(unsigned long long) * static_cast<size_t>(n_query), h->stream));
+    const int64_t qblocks = (n_query + 256 * kTQ - 1) / (256 * kTQ);
+    int64_t slices = std::max<int64_t>(1, (4ll * h->sm_count + qblocks - 1) / qblocks);
+    slices = std::min<int64_t>(slices, (n_nodes + kTNodeTile - 1) / kTNodeTile);
+    int64_t slice_nodes = (n_nodes + slices - 1) / slices;
+    slice_nodes = (slice_nodes + kTNodeTile - 1) / kTNodeTile * kTNodeTile;
+    slices = (n_nodes + slice_nodes - 1) / slice_nodes;
+    dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(qblocks));
+    nearest_tiled_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const float2*>(node_xy), n_nodes, slice_nodes,
+                                                     reinterpret_cast<const float2*>(q), n_query, h->d_nn_best);
+    nearest_unpack_kernel<<<blocks_for(h, (n_query + 255) / 256), 256, 0, h->stream>>>(h->d_nn_best, n_query, idx, d2);
+    h->launches += 2;
+    PP_CUDA(cudaGetLastError());
+    return PP_OK;
+  }
   const int64_t groups = (n_query + kQPW - 1) / kQPW;
   nearest_kernel<<<blocks_for(h, (groups + 7) / 8), 256, 0, h->stream>>>(
       reinterpret_cast<const float2*>(node_xy), n_nodes, reinterpret_cast<const float2*>(q), n_query, idx, d2);

@@ -387,6 +387,13 @@ def run_ours(args):
         pl.set_collision_mode(PP_COLLISION_ORIENTED)
         ms_sampler = timed(lambda: pl.sample_poses_dev(2018, rank, 0, n, *box, out=poses))
         l2_gbps = pl.bench_l2_gather(16 << 20)      # random 32 B sectors of a 16 MiB (L2-resident) buffer
+        # row S2 stand-alone: brute-force nearest neighbour, 2^20 tree nodes (a config-4 sized tree) x 16384 queries
+        nn_nodes, nn_q = 1 << 20, 1 << 14
+        gen = torch.Generator(device=dev).manual_seed(7)
+        node_xy = (torch.rand((nn_nodes, 2), generator=gen, device=dev) - 0.5) * 800.0
+        query_xy = (torch.rand((nn_q, 2), generator=gen, device=dev) - 0.5) * 800.0
+        torch.cuda.synchronize()
+        ms_nn = timed(lambda: pl.nearest_dev(node_xy, query_xy), reps=3)
         extra = {
             "oriented_direct_poses_per_s": n / (ms_direct * 1e-3), "oriented_direct_narrow_units": direct_units,
             "oriented_direct_frac_of_hbm_roofline": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / _peaks()[0],
@@ -395,6 +402,9 @@ def run_ours(args):
             "philox_sampler_poses_per_s": n / (ms_sampler * 1e-3),
             "philox_sampler_write_GBps": 12 * n / (ms_sampler * 1e-3) / 1e9,
             "l2_gather_peak_GBps_measured": l2_gbps,
+            "nearest_neighbour": {"nodes": nn_nodes, "queries": nn_q, "ms": ms_nn,
+                                  "distance_evals_per_s": nn_nodes * nn_q / (ms_nn * 1e-3),
+                                  "algorithmic_GBps_8B_per_node_per_query": 8.0 * nn_nodes * nn_q / (ms_nn * 1e-3) / 1e9},
             "oriented_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_per_step * 1e-3) / 1e9 / l2_gbps,
             "oriented_direct_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / l2_gbps,
         }

@@ -47,7 +47,7 @@ def test_sampler_matches_oracle(pl, oracle):
     np.testing.assert_array_equal(part.cpu().numpy(), full[1000:1050])
 
 
-@pytest.mark.parametrize("n_nodes,n_query", [(1, 5), (31, 33), (1000, 257), (20011, 1024)])
+@pytest.mark.parametrize("n_nodes,n_query", [(1, 5), (31, 33), (1000, 257), (20011, 1024), (150001, 2500)])
 def test_nearest_matches_oracle(pl, oracle, n_nodes, n_query):
     rng = np.random.default_rng(n_nodes)
     nodes = rng.uniform(-50, 50, (n_nodes, 2)).astype(np.float32)
