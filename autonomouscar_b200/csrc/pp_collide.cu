@@ -146,6 +146,8 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
   if (tid == 0 && narrow_counter && local_narrow) atomicAdd(narrow_counter, local_narrow);
 }
 
+// Along-edge test (row S3), thread per edge: every step evaluated by one thread.  Kept for the
+// non-ORIENTED modes (one map lookup per step) and as the small-batch path.
 __global__ void __launch_bounds__(kThreads)
 collide_edges_kernel(GridDev g, CollideParams cp, const float* __restrict__ edges, uint8_t* __restrict__ flags,
                      int64_t n) {
@@ -155,6 +157,43 @@ collide_edges_kernel(GridDev g, CollideParams cp, const float* __restrict__ edge
     flags[k] = collide_edge_thread(g, cp, static_cast<double>(e[0]), static_cast<double>(e[1]),
                                    static_cast<double>(e[2]), static_cast<double>(e[3]),
                                    static_cast<double>(e[4])) ? 1 : 0;
+  }
+}
+
+// ORIENTED along-edge test, warp per edge: the steps of the edge are a mini-batch -- lane l sets up
+// step base + l + 1 (fixed-point lattice, broad phase: one thread each), then the warp runs the
+// staged-window narrow phase only for the steps that need it, stopping at the first hit.  Same
+// step rule as collide_edge_thread / the oracle: n = max(int(dist / search_res * 2), 1) poses at
+// t = k / n, k = 1..n (spacing rule of LP:308).
+__global__ void __launch_bounds__(kThreads)
+collide_edges_warp_kernel(GridDev g, CollideParams cp, const float* __restrict__ edges, uint8_t* __restrict__ flags,
+                          int64_t n) {
+  __shared__ __align__(16) uint32_t s_win[kWarpsPerBlock][kWinWords];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t e = warp; e < n; e += n_warps) {
+    const float* ed = edges + 5 * e;
+    const double x0 = ed[0], y0 = ed[1], x1 = ed[2], y1 = ed[3], yaw = ed[4];
+    const double dx = dm::sub(x1, x0), dy = dm::sub(y1, y0);
+    const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
+    int steps;
+    bool hit = false;
+    if (dm::trunc_to_int(dm::mul(dm::div(dist, cp.search_res), 2.0), &steps)) {
+      if (steps < 1) steps = 1;
+      for (int base = 0; base < steps && !hit; base += 32) {
+        const int k = base + lane + 1;
+        bool need = false;
+        NarrowJob job;
+        if (k <= steps) {
+          const double t = dm::div(static_cast<double>(k), static_cast<double>(steps));
+          const PoseFx pf = pose_to_fixed(cp.lat, g.W, g.H, g.res, dm::add(x0, dm::mul(t, dx)), dm::add(y0, dm::mul(t, dy)), yaw);
+          need = make_job(g, cp.lat, pf, 1, &job);
+        }
+        hit = warp_collide_jobs(g, cp.lat, job, need, s_win[wib], lane);
+      }
+    }
+    if (lane == 0) flags[e] = hit ? 1 : 0;
   }
 }
 
@@ -235,8 +274,12 @@ int collide_batch_dev(pp_handle* h, int64_t n, const float* poses, uint8_t* flag
 
 int collide_edges_dev(pp_handle* h, int64_t n, const float* edges, uint8_t* flags) {
   if (n == 0) return PP_OK;
-  collide_edges_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, h->stream>>>(h->grid, collide_params(h),
-                                                                                  edges, flags, n);
+  if (h->P.collision_mode == PP_COLLISION_ORIENTED && !getenv("PP_EDGES_THREAD_KERNEL"))
+    collide_edges_warp_kernel<<<grid_blocks(h, n, kWarpsPerBlock, 16), kThreads, 0, h->stream>>>(h->grid, collide_params(h),
+                                                                                                edges, flags, n);
+  else
+    collide_edges_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, h->stream>>>(h->grid, collide_params(h),
+                                                                                    edges, flags, n);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   return PP_OK;

@@ -387,6 +387,18 @@ def run_ours(args):
         pl.set_collision_mode(PP_COLLISION_ORIENTED)
         ms_sampler = timed(lambda: pl.sample_poses_dev(2018, rank, 0, n, *box, out=poses))
         l2_gbps = pl.bench_l2_gather(16 << 20)      # random 32 B sectors of a 16 MiB (L2-resident) buffer
+        # row S3 stand-alone: 2^22 random 0.45 m edges (one 150 ms step at 1.5 m/s), oriented footprint at every
+        # search_res / 2 along each
+        n_edges = 1 << 22
+        e_xy = poses[:n_edges]
+        edges = torch.empty((n_edges, 5), dtype=torch.float32, device=dev)
+        edges[:, 0], edges[:, 1] = e_xy[:, 0], e_xy[:, 1]
+        edges[:, 2] = e_xy[:, 0] + 0.45 * torch.cos(e_xy[:, 2])
+        edges[:, 3] = e_xy[:, 1] + 0.45 * torch.sin(e_xy[:, 2])
+        edges[:, 4] = e_xy[:, 2]
+        e_flags = torch.empty(n_edges, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ms_edges = timed(lambda: pl.collide_edges_dev(edges, out=e_flags), reps=3)
         # row S2 stand-alone: brute-force nearest neighbour, 2^20 tree nodes (a config-4 sized tree) x 16384 queries
         nn_nodes, nn_q = 1 << 20, 1 << 14
         gen = torch.Generator(device=dev).manual_seed(7)
@@ -402,6 +414,8 @@ def run_ours(args):
             "philox_sampler_poses_per_s": n / (ms_sampler * 1e-3),
             "philox_sampler_write_GBps": 12 * n / (ms_sampler * 1e-3) / 1e9,
             "l2_gather_peak_GBps_measured": l2_gbps,
+            "edge_collision": {"edges": n_edges, "steps_per_edge": 3, "ms": ms_edges, "edges_per_s": n_edges / (ms_edges * 1e-3),
+                               "hit_rate": float(e_flags.float().mean().item())},
             "nearest_neighbour": {"nodes": nn_nodes, "queries": nn_q, "ms": ms_nn,
                                   "distance_evals_per_s": nn_nodes * nn_q / (ms_nn * 1e-3),
                                   "algorithmic_GBps_8B_per_node_per_query": 8.0 * nn_nodes * nn_q / (ms_nn * 1e-3) / 1e9},
