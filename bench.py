@@ -30,7 +30,7 @@ RES = 0.1
 ALG_BYTES_ORIENTED = 12 + 1 + 48 * 17   # pose + flag + one byte per lattice sample = 829 B
 ALG_BYTES_AABB = 12 + 1 + 47 * 15       # 718 B
 # ncu --set full, collide_oriented_kernel, 2^22 poses: dram__bytes_read.sum + dram__bytes_write.sum
-DRAM_BYTES_PER_POSE_NCU = (50.627072e6 + 20.48e3) / (1 << 22)
+DRAM_BYTES_PER_POSE_NCU = (51.002880e6 + 39.424e3) / (1 << 22)
 
 
 def _peaks():
@@ -467,7 +467,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": DRAM_BYTES_PER_POSE_NCU * n, "traffic_unit": "bytes/launch",
-                         "traffic_source": "profiles/r1_ncu_collide_oriented_v3_broad.csv (dram read+write / 2^22 poses)",
+                         "traffic_source": "profiles/r1_ncu_collide_oriented_v4_broad.csv (dram read+write / 2^22 poses)",
                          "peak_kind": peak_kind,
                          "kernel": "collide_oriented_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_pose": ALG_BYTES_ORIENTED, "narrow_phase_poses": narrow_units},
