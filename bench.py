@@ -768,6 +768,47 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     rrt_dt = sharding.max_over_ranks(time.perf_counter() - t0, dev)
     rrt_samples = int(rbuf.field("n_candidates").sum())
     rrt_found = int((rbuf.field("status") == PP_PLAN_FOUND).sum())
+    # BASELINE configs[3]: 8192^2 grid @0.1 m, 1 % of the area in 16x16-cell blocks, one 1M-sample query corner to corner
+    cfg4 = None
+    if rank == 0:
+        N4 = 8192
+        g4 = worlds.block_grid(N4, N4, frac=0.01, block=16, seed=4, noise=False)
+        half = N4 * 0.1 / 2
+        sx, sy, gx4, gy4 = -half + 10.0, -half + 10.0, half - 10.0, half - 10.0
+        cfg4 = {"grid": "8192x8192 @0.1 m, 1% area in 16x16-cell blocks, start / goal at opposite corners inset 10 m"}
+        for K4 in (256, 1024):
+            p4 = default_params(costmap_res=0.1, costmap_width=N4, costmap_height=N4, collision_mode=PP_COLLISION_ORIENTED,
+                                time_step_ms=1000.0, rrt_samples_per_round=K4, rrt_max_samples=1 << 20,
+                                max_nodes=(1 << 20) + 1, rrt_goal_tolerance=2.0, rrt_goal_bias=0.05)
+            if K4 == 256:
+                worlds.clear_disc(g4, p4, sx, sy, 6.0)
+                worlds.clear_disc(g4, p4, gx4, gy4, 6.0)
+            pl4 = Planner(p4, device=dev.index)
+            pl4.set_grid(g4)
+            q4 = make_query(gx4, gy4, start_x=sx, start_y=sy, start_heading=0.785, start_speed=1.0, max_speed=1.5,
+                            seed=2018, query_id=0)
+            pl4.rrt_plan(q4, cap_nodes=8, cap_path=65536, want_nodes=False)
+            t0 = time.perf_counter()
+            r4 = pl4.rrt_plan(q4, cap_nodes=8, cap_path=65536, want_nodes=False)
+            w4 = time.perf_counter() - t0
+            cfg4[f"K{K4}"] = {"status": int(r4.status), "samples": int(r4.n_candidates), "nodes": int(r4.n_nodes),
+                              "rounds": int(r4.n_expansions), "path_nodes": int(r4.n_path), "wall_s": w4,
+                              "samples_per_s": r4.n_candidates / w4}
+            if K4 == 256 and not args.skip_cpu:
+                # parity + CPU rate on a bounded prefix of the same run (the oracle's nearest neighbour is O(N) per sample)
+                from oracle import binding as orc
+                p4.rrt_max_samples = 16384
+                pl4.close()
+                pl4 = Planner(p4, device=dev.index)
+                pl4.set_grid(g4)
+                gpre = pl4.rrt_plan(q4, cap_nodes=8, cap_path=64, want_nodes=False)
+                t0 = time.perf_counter()
+                cpre = orc.rrt_plan(p4, g4, q4, cap_nodes=8, cap_path=64, want_nodes=False)
+                c4 = time.perf_counter() - t0
+                cfg4["first_16384_samples"] = {"cpu_oracle_samples_per_s_1thread": 16384 / c4,
+                                               "bit_exact_vs_oracle": bool(gpre.summary() == cpre.summary())}
+            pl4.close()
+        del g4
     out = None
     if rank == 0:
         found = int((rec[:, 0] == PP_PLAN_FOUND).sum().item())
@@ -777,7 +818,7 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
                "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_kernel_ms": sorted(lat_k)[len(lat_k) // 2],
                "single_query_nodes": int(r1.n_nodes),
                "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000",
-               "config1_road_world": cfg1,
+               "config1_road_world": cfg1, "config4_dense_clutter_1M_samples": cfg4,
                "rrt": {"queries_per_gpu": n_rrt, "plans_per_s": n_rrt * world / rrt_dt, "found_rank0": rrt_found,
                        "samples_per_s_rank0": rrt_samples / rrt_dt, "grid": "1024x1024 @0.1 m, 10k-sample cap, K=64"}}
         if not args.skip_cpu:
