@@ -1,6 +1,8 @@
 """Randomised GPU-vs-oracle parity over parameter space (seeded): grid sizes / resolutions,
 lattice parameters (26 / 27-yaw trap, 3..9 velocities), collision modes, caps, goal speeds,
 sampling-planner round sizes.  Bit-exact or fail."""
+import os
+
 import numpy as np
 import pytest
 
@@ -23,9 +25,10 @@ def _same_plan(got, ref):
 
 def test_plan_fuzz(oracle, cuda_device):
     from autonomouscar_b200 import Planner
-    rng = np.random.default_rng(20181)
+    # PP_FUZZ_SEED / PP_FUZZ_CASES widen the sweep for one-off soak runs
+    rng = np.random.default_rng(int(os.environ.get("PP_FUZZ_SEED", "20181")))
     statuses = []
-    for case in range(24):
+    for case in range(int(os.environ.get("PP_FUZZ_CASES", "24"))):
         res = float(rng.choice([0.1, 0.2, 0.25, 0.5]))
         W, H = int(rng.integers(120, 420)), int(rng.integers(120, 420))
         p = default_params(
@@ -55,8 +58,8 @@ def test_plan_fuzz(oracle, cuda_device):
 
 def test_collide_and_rrt_fuzz(oracle, cuda_device):
     from autonomouscar_b200 import Planner
-    rng = np.random.default_rng(77)
-    for case in range(10):
+    rng = np.random.default_rng(int(os.environ.get("PP_FUZZ_SEED", "77")))
+    for case in range(int(os.environ.get("PP_FUZZ_CASES", "10")) * 10 // 24 or 1):
         res = float(rng.choice([0.1, 0.125, 0.2, 0.25]))
         W, H = int(rng.integers(200, 900)), int(rng.integers(200, 900))
         length, width = float(rng.uniform(3.0, 5.5)), float(rng.uniform(1.2, 2.2))
