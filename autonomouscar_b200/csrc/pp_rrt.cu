@@ -36,6 +36,7 @@ constexpr int kT = 256;
 constexpr int kMaxK = 1024;               // samples per round the kernels support
 constexpr int kSPT = kMaxK / kT;          // samples per thread in rrt_nearest
 constexpr int kNodeTile = 1024;           // float2 nodes staged per step
+constexpr int kSliceGrain = 128;          // node slices handed to CTAs are multiples of this
 constexpr unsigned long long kBestInit = ~0ull;
 
 struct RrtState {
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__(kT) rrt_init(RrtArgs A) {
   for (int k = threadIdx.x; k < A.K; k += kT) A.best[static_cast<size_t>(q) * A.K + k] = kBestInit;
 }
 
+// SPT = samples owned by one thread (ceil(K / 256), 1 / 2 / 4): the distance loop is unrolled over exactly
+// the samples that exist.
+template <int SPT>
 __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
   __shared__ float2 tile[kNodeTile];
   const int q = blockIdx.y;
@@ -117,17 +121,17 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
   const pp_query qq = A.queries[q];
   const long long s0 = st.n_samples;
   const int k_round = static_cast<int>(min(static_cast<long long>(A.K), static_cast<long long>(A.P.rrt_max_samples) - s0));
-  // K >= 256: every thread owns up to kSPT samples and scans the whole tile.
+  // K >= 256: every thread owns up to SPT samples and scans the whole tile.
   // K <  256: the threads form G = 256 / Kp groups (Kp = K rounded up to a power of two); a
   // group's thread owns one sample and scans every G-th node of the tile, so no lane idles.
   int Kp = 1;
   while (Kp < A.K) Kp <<= 1;
   const int G = Kp >= kT ? 1 : kT / Kp;
   const int grp = G == 1 ? 0 : threadIdx.x / Kp;
-  float sx[kSPT], sy[kSPT], bd[kSPT];
-  int bi[kSPT], st_[kSPT];
+  float sx[SPT], sy[SPT], bd[SPT];
+  int bi[SPT], st_[SPT];
 #pragma unroll
-  for (int u = 0; u < kSPT; ++u) {
+  for (int u = 0; u < SPT; ++u) {
     const int t = G == 1 ? threadIdx.x + u * kT : (u == 0 ? threadIdx.x % Kp : k_round);
     st_[u] = t;
     sx[u] = 0.f; sy[u] = 0.f; bd[u] = 0.f; bi[u] = -1;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
       for (int k = 0; k < cnt; ++k) {
         const float2 nd = tile[k];
 #pragma unroll
-        for (int u = 0; u < kSPT; ++u) {
+        for (int u = 0; u < SPT; ++u) {
           const float dx = __fsub_rn(sx[u], nd.x), dy = __fsub_rn(sy[u], nd.y);
           const float d = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
           if (bi[u] < 0 || d < bd[u]) { bd[u] = d; bi[u] = base + k; }
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
     }
   }
 #pragma unroll
-  for (int u = 0; u < kSPT; ++u) {
+  for (int u = 0; u < SPT; ++u) {
     const int t = st_[u];
     if (t < k_round && bi[u] >= 0) {
       const unsigned long long packed = (static_cast<unsigned long long>(__float_as_uint(bd[u])) << 32) |
@@ -500,14 +504,18 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   while (round < max_rounds) {
     for (int c = 0; c < chunk && round < max_rounds; ++c, ++round) {
       // enough node slices to occupy the GPU when there are few queries
+      // slices of at least kSliceGrain nodes: a lone query's early rounds (a few thousand nodes) are spread over
+      // many SMs instead of one CTA scanning a whole 1024-node tile for all K samples
       const long long want_ctas = std::max<long long>(1, (4LL * h->sm_count + n - 1) / n);
-      long long slices = std::min<long long>(want_ctas, (nodes_bound + kNodeTile - 1) / kNodeTile);
+      long long slices = std::min<long long>(want_ctas, (nodes_bound + kSliceGrain - 1) / kSliceGrain);
       if (slices < 1) slices = 1;
       int slice_nodes = static_cast<int>((nodes_bound + slices - 1) / slices);
-      slice_nodes = ((slice_nodes + kNodeTile - 1) / kNodeTile) * kNodeTile;
+      slice_nodes = ((slice_nodes + kSliceGrain - 1) / kSliceGrain) * kSliceGrain;
       slices = (nodes_bound + slice_nodes - 1) / slice_nodes;
       dim3 grid_nn(static_cast<unsigned>(slices), static_cast<unsigned>(n));
-      rrt_nearest<<<grid_nn, kT, 0, s>>>(A, slice_nodes);
+      if (K <= kT) rrt_nearest<1><<<grid_nn, kT, 0, s>>>(A, slice_nodes);
+      else if (K <= 2 * kT) rrt_nearest<2><<<grid_nn, kT, 0, s>>>(A, slice_nodes);
+      else rrt_nearest<4><<<grid_nn, kT, 0, s>>>(A, slice_nodes);
       rrt_extend<<<extend_blocks, kT, 0, s>>>(A);
       rrt_append<<<n, kT, 0, s>>>(A);
       h->launches += 3;
