@@ -37,6 +37,7 @@ constexpr int kMaxK = 1024;               // samples per round the kernels suppo
 constexpr int kSPT = kMaxK / kT;          // samples per thread in rrt_nearest
 constexpr int kNodeTile = 1024;           // float2 nodes staged per step
 constexpr int kSliceGrain = 128;          // node slices handed to CTAs are multiples of this
+constexpr int kExtSplitMax = 4;           // warps that share the poses of one edge in rrt_extend (few samples per round)
 constexpr unsigned long long kBestInit = ~0ull;
 
 struct RrtState {
@@ -103,7 +104,10 @@ __global__ void __launch_bounds__(kT) rrt_init(RrtArgs A) {
     A.state[q] = st;
     if (!st.done) atomicAdd(A.n_active, 1);
   }
-  for (int k = threadIdx.x; k < A.K; k += kT) A.best[static_cast<size_t>(q) * A.K + k] = kBestInit;
+  for (int k = threadIdx.x; k < A.K; k += kT) {
+    A.best[static_cast<size_t>(q) * A.K + k] = kBestInit;
+    A.cand_valid[static_cast<size_t>(q) * A.K + k] = 0;
+  }
 }
 
 // SPT = samples owned by one thread (ceil(K / 256), 1 / 2 / 4): the distance loop is unrolled over exactly
@@ -173,17 +177,22 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
   }
 }
 
-__global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A) {
+__global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A, int ext_split) {
   __shared__ __align__(16) uint32_t smem[kT / 32][kWinWords];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long warp = blockIdx.x * static_cast<long long>(kT / 32) + wib;
+  // ext_split warps share one sample: all of them steer (identical arithmetic), each tests its share of the
+  // edge's poses; verdicts are combined with atomicMax (2 = collision beats 1 = free); cand_valid is zero at
+  // the start of every round (rrt_init / rrt_append)
+  const long long gwarp = blockIdx.x * static_cast<long long>(kT / 32) + wib;
+  const int part = static_cast<int>(gwarp % ext_split);
+  const long long warp = gwarp / ext_split;
   const int q = static_cast<int>(warp / A.K), t = static_cast<int>(warp % A.K);
   if (q >= A.n_queries) return;
   const RrtState st = A.state[q];
   if (st.done) return;
   const long long s = static_cast<long long>(st.n_samples) + t;
   const size_t slot = static_cast<size_t>(q) * A.K + t;
-  if (s >= A.P.rrt_max_samples) { if (lane == 0) A.cand_valid[slot] = 0; return; }
+  if (s >= A.P.rrt_max_samples) return;
   const pp_query qq = A.queries[q];
   float sx, sy;
   draw_sample(A, qq, s, &sx, &sy);
@@ -216,11 +225,13 @@ __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A) {
       if (n < 1) n = 1;
       // the edge's poses are a mini-batch: lane l sets up pose base + l + 1 (broad phase, one
       // thread each), then the warp runs the narrow phase only for the poses that need it
-      for (int base = 0; base < n && !hit; base += 32) {
+      const int k_lo = static_cast<int>(static_cast<long long>(n) * part / ext_split);        // poses k_lo+1 .. k_hi
+      const int k_hi = static_cast<int>(static_cast<long long>(n) * (part + 1) / ext_split);
+      for (int base = k_lo; base < k_hi && !hit; base += 32) {
         const int k = base + lane + 1;
         bool need = false;
         NarrowJob job;
-        if (k <= n) {
+        if (k <= k_hi) {
           const double tt = dm::div(static_cast<double>(k), static_cast<double>(n));
           const double ex = dm::add(px, dm::mul(tt, dx)), ey = dm::add(py, dm::mul(tt, dy));
           if (A.cp.mode == PP_COLLISION_ORIENTED) {
@@ -236,8 +247,8 @@ __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A) {
     }
     verdict = hit ? 2 : 1;
   }
-  if (lane == 0) {
-    A.cand_valid[slot] = verdict;
+  if (lane == 0 && verdict) atomicMax(&A.cand_valid[slot], verdict);
+  if (lane == 0 && part == 0) {
     A.cand_near[slot] = near;
     double* c = A.cand + slot * 5;
     c[0] = nx; c[1] = ny; c[2] = yaw; c[3] = v_next; c[4] = step;
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(kT) rrt_append(RrtArgs A) {
     const int t = base + threadIdx.x;
     const size_t slot = static_cast<size_t>(q) * A.K + t;
     const int verdict = t < k_round ? A.cand_valid[slot] : 0;
+    if (t < k_round) A.cand_valid[slot] = 0;          // re-armed for the next round's atomicMax
     const bool ok = verdict == 1;
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     coll += verdict == 2;
@@ -496,7 +508,9 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   rrt_init<<<n, kT, 0, s>>>(A);
   h->launches++;
   const long long max_rounds = (static_cast<long long>(P.rrt_max_samples) + K - 1) / K;
-  const long long warps_total = static_cast<long long>(n) * K;
+  // a lone query's round has too few samples to fill the GPU with one warp per edge: split each edge's poses
+  const int ext_split = static_cast<long long>(n) * K <= 2048 ? kExtSplitMax : 1;
+  const long long warps_total = static_cast<long long>(n) * K * ext_split;
   const int extend_blocks = static_cast<int>((warps_total + (kT / 32) - 1) / (kT / 32));
   long long round = 0;
   long long nodes_bound = 1;   // upper bound of any query's tree size
@@ -516,7 +530,7 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
       if (K <= kT) rrt_nearest<1><<<grid_nn, kT, 0, s>>>(A, slice_nodes);
       else if (K <= 2 * kT) rrt_nearest<2><<<grid_nn, kT, 0, s>>>(A, slice_nodes);
       else rrt_nearest<4><<<grid_nn, kT, 0, s>>>(A, slice_nodes);
-      rrt_extend<<<extend_blocks, kT, 0, s>>>(A);
+      rrt_extend<<<extend_blocks, kT, 0, s>>>(A, ext_split);
       rrt_append<<<n, kT, 0, s>>>(A);
       h->launches += 3;
       nodes_bound = std::min<long long>(nodes_bound + K, NC);
