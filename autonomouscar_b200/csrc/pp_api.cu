@@ -138,7 +138,6 @@ int pp_destroy(pp_handle* h) {
   grid_free(h);
   cudaFree(h->d_poses);
   cudaFree(h->d_flags);
-  cudaFree(h->d_list);
   cudaFree(h->d_visited);
   cudaFree(h->d_nn_best);
   cudaFree(h->d_count);

@@ -253,10 +253,8 @@ struct pp_handle {
   uint8_t* d_flags = nullptr;
   int64_t stage_cap = 0;
   // compaction scratch for the two-phase ORIENTED path
-  int32_t* d_list = nullptr;       // indices of poses that need the narrow phase
   int32_t* d_count = nullptr;      // device counter
   int32_t* h_count = nullptr;      // pinned mirror
-  int64_t list_cap = 0;
   void* scratch = nullptr;         // grid-prep scratch
   size_t scratch_bytes = 0;
   uint8_t* d_visited = nullptr;    // A12 debug bitmap of the last single plan (W*H bytes)

@@ -318,25 +318,8 @@ struct Shared {
   long long cyc[8];
 };
 
-// first slot in scan order (open list by id, then closed list by closing order) whose child
-// point equals (x, y) and whose scan key is >= from_key; returns the scan key or kIntMax.
-// scan key: open slot -> id ; closed slot -> n_nodes + closed_seq.
-// `sxy` (may be null) is a shared-memory copy of (cx, cy) made once the search has ended.
-__device__ __forceinline__ int find_child_from(const WS& w, const double2* sxy, int n_nodes, double x, double y,
-                                               int from_key, int* s_red) {
-  int best = kIntMax;
-  for (int id = threadIdx.x; id < n_nodes; id += kT) {
-    bool eq;
-    if (sxy) { const double2 c = sxy[id]; eq = c.x == x && c.y == y; }
-    else eq = w.cx[id] == x && w.cy[id] == y;
-    if (eq) {
-      const int cs = w.closed_seq[id];
-      const int key = cs < 0 ? id : n_nodes + cs;
-      if (key >= from_key && key < best) best = key;
-    }
-  }
-  return block_min(best, s_red);
-}
+// scan key of a slot: open slot -> id ; closed slot -> n_nodes + closed_seq (open list by id, then closed
+// list by closing order: the order LP:511-526 scans in)
 // slot id of a scan key
 __device__ __forceinline__ int slot_of_key(const WS& w, int n_nodes, int key) {
   return key < n_nodes ? key : w.closed_list[key - n_nodes];

@@ -34,7 +34,6 @@ namespace {
 
 constexpr int kT = 256;
 constexpr int kMaxK = 1024;               // samples per round the kernels support
-constexpr int kSPT = kMaxK / kT;          // samples per thread in rrt_nearest
 constexpr int kNodeTile = 1024;           // float2 nodes staged per step
 constexpr int kSliceGrain = 128;          // node slices handed to CTAs are multiples of this
 constexpr int kExtSplitMax = 4;           // warps that share the poses of one edge in rrt_extend (few samples per round)
