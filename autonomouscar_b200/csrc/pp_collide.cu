@@ -60,8 +60,11 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred, int lane) {
   return base + __popc(bal & ((1u << lane) - 1u));
 }
 
+#ifndef PP_COLLIDE_MIN_BLOCKS
+#define PP_COLLIDE_MIN_BLOCKS 4
+#endif
 template <int NU, int NV, int S>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, PP_COLLIDE_MIN_BLOCKS)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
                         int64_t n, int broad_phase, unsigned long long* __restrict__ narrow_counter) {
   __shared__ __align__(16) uint32_t s_win[kWarpsPerBlock][kWinWords];
