@@ -129,6 +129,34 @@ def test_argument_errors_do_not_need_a_device(lib):
     assert lib.pp_abi_version() == 1
 
 
+def test_costmap_argument_errors_do_not_need_a_device(lib):
+    from autonomouscar_b200.costmap_capi import default_costmap_params, default_global_costmap_params, pc_params, pg_params
+    h = C.c_void_p()
+    assert lib.pc_create(None, 0, C.byref(h)) == 1                               # PP_ERR_INVALID
+    bad = default_costmap_params(res=0.0)
+    assert lib.pc_create(C.byref(bad), 0, C.byref(h)) == 1 and b"res" in lib.pp_last_error()
+    huge = default_costmap_params(global_height_cells=1e6, global_width_cells=1e6)
+    assert lib.pc_create(C.byref(huge), 0, C.byref(h)) == 1
+    dev = C.c_void_p()
+    g = default_global_costmap_params(num_lanes=0)
+    assert lib.pg_build(C.byref(g), 0, None, None, 0, None, C.byref(dev)) == 1
+    g = default_global_costmap_params(height_cells=1200.5)
+    assert lib.pg_build(C.byref(g), 0, None, None, 0, None, C.byref(dev)) == 1 and b"whole numbers" in lib.pp_last_error()
+    # defaults = launch file (full_sim.launch:68-82)
+    c, d = pc_params(), pg_params()
+    assert lib.pc_default_params(C.byref(c)) == 0 and lib.pg_default_params(C.byref(d)) == 0
+    py = default_costmap_params()
+    for name, _ in pc_params._fields_:
+        if name != "reserved":
+            assert getattr(c, name) == getattr(py, name), name
+    pyg = default_global_costmap_params()
+    for name, _ in pg_params._fields_:
+        if not name.startswith("reserved"):
+            assert getattr(d, name) == getattr(pyg, name), name
+    assert (c.res, c.height_cells, c.width_cells, c.max_inflation_radius) == (0.25, 300.0, 300.0, 5.0)
+    assert (d.road_width, d.num_lanes, d.height_cells) == (11.1, 2, 12000.0)
+
+
 def test_product_never_touches_the_oracle():
     """The product package must not import, link or execute anything under oracle/."""
     pkg = os.path.join(ROOT, "autonomouscar_b200")
