@@ -239,3 +239,29 @@ def next_waypoint(route, start_index, x, y, lookahead=20.0):
         if np.hypot(route[k][0] - x, route[k][1] - y) >= lookahead:
             return k, route[k]
     return len(route) - 1, route[-1]
+
+
+def corridor_scene(seed, half_width=6.0, reach=29.0, rings=16, per_ring=512, gap_at=None):
+    """Sensor messages of a car driving between two walls (block-laser returns at y = +-half_width, 0.8 m above
+    the ground buffer) over open ground; the planar lasers see nothing (ranges beyond range_max).  `gap_at` =
+    (x0, x1) removes the LEFT wall there and puts a 2 m box on the centre line instead (something to steer round)."""
+    from .costmap_capi import CostmapScene
+    rng = np.random.default_rng(seed)
+    n = rings * per_ring
+    ang = np.tile(np.linspace(-3.14, 3.14, per_ring), rings)
+    rad = np.repeat(np.linspace(2.5, reach, rings), per_ring) + rng.normal(0, 0.03, n)
+    gx, gy = rad * np.cos(ang), rad * np.sin(ang)
+    keep = np.abs(gy) < half_width - 0.3                       # ground returns inside the corridor only
+    ground = np.stack([gx[keep], gy[keep], np.full(keep.sum(), -1.8) + rng.normal(0, 0.005, keep.sum())], 1)
+    wx = np.arange(-reach, reach, 0.2)
+    left = np.stack([wx, np.full_like(wx, half_width), np.full_like(wx, -1.0)], 1)
+    right = np.stack([wx, np.full_like(wx, -half_width), np.full_like(wx, -1.0)], 1)
+    parts = [ground, right]
+    if gap_at is not None:
+        left = left[(wx < gap_at[0]) | (wx > gap_at[1])]
+        bx, by = np.meshgrid(np.arange(gap_at[0], gap_at[0] + 2.0, 0.2), np.arange(-1.0, 1.0, 0.2))
+        parts.append(np.stack([bx.ravel(), by.ravel(), np.full(bx.size, -1.0)], 1))
+    parts.append(left)
+    cloud = np.concatenate(parts).astype(np.float32)
+    none = np.full(640, 31.0, dtype=np.float32)               # beyond range_max: skipped (LC:111)
+    return CostmapScene(none, none.copy(), cloud, (np.float32(-2.26889), np.float32(0.0071), np.float32(30.0)))

@@ -579,6 +579,7 @@ def bench_costmap(args):
         gm.close()
         out["global_road_map"] = g
         out["stack_rollout"] = bench_stack(args, z)
+        out["stack_rollout_oriented_corridor"] = bench_stack(args, z, oriented=True)
     out["route_rollouts"] = bench_rollouts(args)
     return out
 
@@ -613,7 +614,7 @@ def bench_rollouts(args, cars=1024, ticks=20):
             "mean_metres_driven": float((ro.x - [s_[0] for s_ in starts]).mean())}
 
 
-def bench_stack(args, edges, cycles=150):
+def bench_stack(args, edges, cycles=150, oriented=False):
     """Rows N1-N3 chained with the hot path, everything resident on the GPU: the global road map is built
     once (pg_build) and adopted by the costmap builder; then, per 20 Hz cycle along the reference's own route
     (global_path_planner.py:101-102, densified and looked ahead as local_navigator.py:27-46,586-609 do):
@@ -621,16 +622,20 @@ def bench_stack(args, edges, cycles=150):
     advances along the planned path for one 50 ms period (kinematic stand-in for Gazebo)."""
     import numpy as np
 
-    from autonomouscar_b200 import (PP_COLLISION_AS_SHIPPED, PP_PLAN_FOUND, GlobalRoadMap, LocalCostmap, Planner,
-                                    default_params, make_query, worlds)
+    from autonomouscar_b200 import (PP_COLLISION_AS_SHIPPED, PP_COLLISION_ORIENTED, PP_PLAN_FOUND, GlobalRoadMap,
+                                    LocalCostmap, Planner, default_params, make_query, worlds)
     from autonomouscar_b200.costmap_capi import default_costmap_params
     gm = GlobalRoadMap(edges["xy"], edges["offsets"], device=0, want_host=False)
     cm = LocalCostmap(default_costmap_params(), device=0)
     cm.adopt_global_grid(gm)
-    pl = Planner(default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000), device=0)
+    mode = PP_COLLISION_ORIENTED if oriented else PP_COLLISION_AS_SHIPPED
+    pl = Planner(default_params(collision_mode=mode, max_nodes=20000), device=0)
     route = worlds.densified_route()
-    scenes = [worlds.costmap_scene(50 + k) for k in range(8)]
-    x, y, yaw, v, wp = 0.0, 15.0, 0.0, 0.0, 0
+    # as shipped: random laser returns (the grid does not influence the search, LP:445); oriented: two walls
+    # 2.5 m either side of the car, which the footprint test has to respect
+    scenes = [worlds.corridor_scene(50 + k, half_width=2.5) if oriented else worlds.costmap_scene(50 + k) for k in range(8)]
+    x, y, yaw, v, wp = 0.0, 12.6 if oriented else 15.0, 0.0, 0.0, 0
+    rejected = 0
     t_cost, t_ingest, t_plan, found, dist = [], [], [], 0, 0.0
     for k in range(cycles + 5):
         sc = scenes[k % 8]
@@ -646,6 +651,7 @@ def bench_stack(args, edges, cycles=150):
         gx, gy = c * (wx - x) + s_ * (wy - y), -s_ * (wx - x) + c * (wy - y)     # convertGoalToLocalFrame
         r = pl.plan(make_query(gx, gy, start_speed=v), cap_nodes=8, want_nodes=False)
         t3 = time.perf_counter()
+        rejected += int(r.n_collisions)
         if k >= 5:
             t_cost.append(t1 - t0); t_ingest.append(t2 - t1); t_plan.append(t3 - t2)
         if r.status == PP_PLAN_FOUND and r.n_profile > 0:
@@ -659,7 +665,8 @@ def bench_stack(args, edges, cycles=150):
     pl.close()
     med = lambda a: 1e3 * float(np.median(a))                                       # noqa: E731
     tot = np.array(t_cost) + np.array(t_ingest) + np.array(t_plan)
-    return {"cycles": cycles, "plans_found": int(found), "metres_driven": dist,
+    return {"cycles": cycles, "collision_mode": "ORIENTED, corridor scenes" if oriented else "AS_SHIPPED, random scenes",
+            "plans_found": int(found), "candidate_poses_rejected": rejected, "metres_driven": dist,
             "ms_costmap": med(t_cost), "ms_grid_ingest": med(t_ingest), "ms_plan": med(t_plan),
             "ms_cycle": med(tot), "cycles_per_s": float(len(tot) / tot.sum()),
             "note": "20 Hz is the reference's plan rate (local_navigator.py:529); its own nodes need ~20 ms for the "

@@ -188,3 +188,46 @@ def test_stack_rollout_on_device(oracle, cuda_device):
     assert road_cells > 12 * 1000, road_cells   # the road overlay reached every local grid
     cm.close()
     pl.close()
+
+
+def test_stack_rollout_oriented_corridor(oracle, cuda_device):
+    """The same chain with the collision check switched on (ORIENTED footprint): the lasers see two walls,
+    pc_build inflates them, the grid goes to the planner on the device, and the plan that avoids them equals
+    the oracle's plan on the oracle's costmap of the same messages -- every cycle, bit for bit."""
+    from autonomouscar_b200 import (PP_COLLISION_ORIENTED, PP_PLAN_FOUND, LocalCostmap, Planner, default_params,
+                                    make_query, worlds)
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    cp = default_costmap_params()
+    cm = LocalCostmap(cp, device=0)
+    p = default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=20000)
+    pl = Planner(p, device=0)
+    route = worlds.densified_route()
+    x, y, yaw, v, wp = 0.0, 12.6, 0.0, 0.5, 0          # 1.4 m to the right of the route: goals pull towards a wall
+    collisions = found = 0
+    for k in range(10):
+        sc = worlds.corridor_scene(90 + k, half_width=2.5)
+        worlds.fill_costmap_tf(sc, (x, y, yaw))
+        msg = cm.build(sc, want_host=True)
+        want_msg, _ = oracle.costmap_build(cp, sc.inputs, None, math_mode=oracle.MATH_DET)
+        np.testing.assert_array_equal(msg, want_msg)
+        assert (msg == 100).sum() > 300
+        cm.feed_planner(pl)
+        wp, (wx, wy) = worlds.next_waypoint(route, wp, x, y)
+        c, s = np.cos(yaw), np.sin(yaw)
+        q = make_query(c * (wx - x) + s * (wy - y), -s * (wx - x) + c * (wy - y), start_speed=v)
+        r = pl.plan(q)
+        ref = oracle.plan(p, oracle.cspace_from_msg(want_msg, 300, 300), q, math_mode=oracle.MATH_DET)
+        assert r.summary() == ref.summary()
+        np.testing.assert_array_equal(r.path_xy, ref.path_xy)
+        np.testing.assert_array_equal(r.yaw_rates, ref.yaw_rates)
+        collisions += r.n_collisions
+        if r.status == PP_PLAN_FOUND and r.n_profile > 0:
+            found += 1
+            v = float(r.speeds[0])
+            yaw += float(r.yaw_rates[0]) * 0.05
+            x += v * 0.05 * np.cos(yaw)
+            y += v * 0.05 * np.sin(yaw)
+    assert found >= 8 and collisions > 0, (found, collisions)
+    print("corridor roll-out: %d plans found, %d candidate poses rejected by the footprint test" % (found, collisions))
+    cm.close()
+    pl.close()
