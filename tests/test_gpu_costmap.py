@@ -231,3 +231,52 @@ def test_stack_rollout_oriented_corridor(oracle, cuda_device):
     print("corridor roll-out: %d plans found, %d candidate poses rejected by the footprint test" % (found, collisions))
     cm.close()
     pl.close()
+
+
+def test_gpu_chain_equals_reference_node_chain(cuda_device):
+    """Two REFERENCE nodes in a row (local_costmap.cpp -> local_planner.cpp with its collision code enabled,
+    both compiled from the reference sources: oracle/_ref) against the two CUDA components in a row
+    (pc_build -> pp_plan, REF_AABB), fed the same sensor messages and LocalNav goals for several 20 Hz cycles:
+    same published grid, same plan outcome and tree size, /local_path within 1e-9 m, /mp speeds identical."""
+    from autonomouscar_b200 import (PP_COLLISION_REF_AABB, PP_PLAN_FOUND, LocalCostmap, Planner, default_params,
+                                    make_query, worlds)
+    from oracle import ref_binding as ref
+    if not (ref.available() and ref.costmap_available()):
+        pytest.skip("oracle/_ref not present")
+    cp = mcg.params()
+    p = default_params(collision_mode=PP_COLLISION_REF_AABB, max_nodes=20000, max_expansions=2000)
+    route = worlds.densified_route()
+    x, y, yaw, v, wp = 0.0, 13.2, 0.0, 0.5, 0
+    ref.costmap_set_tfs(worlds.costmap_tfs(x, y, yaw))
+    ref_costmap, ref_planner = ref.RefCostmap(cp), ref.RefNode(p, ref.AABB)
+    cm, pl = LocalCostmap(cp, device=0), Planner(p, device=0)
+    rejected = found = 0
+    for k in range(6):
+        sc = worlds.corridor_scene(90 + k, half_width=3.5)
+        ref.costmap_set_tfs(worlds.costmap_tfs(x, y, yaw))
+        ref.costmap_derive_inputs(sc)                       # the tf numbers exactly as the reference node reads them
+        ref_grid, _ = ref_costmap.build(sc)
+        grid = cm.build(sc, want_host=True)
+        assert (grid != ref_grid).sum() <= 2, int((grid != ref_grid).sum())
+        ref_planner.set_grid_msg(ref_grid)
+        cm.feed_planner(pl)
+        wp, (wx, wy) = worlds.next_waypoint(route, wp, x, y)
+        c, s = np.cos(yaw), np.sin(yaw)
+        q = make_query(c * (wx - x) + s * (wy - y), -s * (wx - x) + c * (wy - y), start_speed=v)
+        want = ref_planner.plan(q)
+        got = pl.plan(q)
+        assert (got.status == PP_PLAN_FOUND) == (want.status == 0)
+        assert (got.n_open, got.n_closed) == (want.n_open, want.n_closed)
+        np.testing.assert_allclose(got.path_xy, want.path_xy, rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(got.speeds, want.speeds)
+        np.testing.assert_allclose(got.yaw_rates, want.yaw_rates, rtol=0, atol=1e-7)
+        rejected += got.n_collisions
+        if want.status == 0 and len(want.speeds):
+            found += 1
+            v = float(want.speeds[0])
+            yaw += float(want.yaw_rates[0]) * 0.05
+            x += v * 0.05 * np.cos(yaw)
+            y += v * 0.05 * np.sin(yaw)
+    assert found >= 5 and rejected > 0, (found, rejected)
+    for o in (ref_costmap, ref_planner, cm, pl):
+        o.close()
