@@ -608,7 +608,22 @@ def bench_rollouts(args, cars=1024, ticks=20):
     wall = time.perf_counter() - t0
     pl.close()
     sim_s = ticks / 20.0
-    return {"cars": cars, "ticks": ticks, "plans": cars * ticks, "found": int(ro.found - cars),
+    native = None
+    try:    # the same loop as native host code (autonomouscar_b200/host/route_rollout_b200.hpp), no interpreter in between
+        import subprocess
+        import tempfile
+        pkg = os.path.join(ROOT, "autonomouscar_b200")
+        with tempfile.TemporaryDirectory() as d:
+            exe = os.path.join(d, "route_rollout")
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "host"),
+                                   os.path.join(ROOT, "tests", "cpp", "test_route_rollout.cpp"), "-o", exe, "-L", pkg,
+                                   "-lprius_planner_b200", f"-Wl,-rpath,{pkg}"], stderr=subprocess.DEVNULL)
+            first = subprocess.check_output([exe, str(cars), str(ticks), "0.12", "1"]).decode().splitlines()[0].split()
+        native = {"wall_s": float(first[0]), "plans": int(first[1]) - cars, "real_time_factor_whole_loop": sim_s / float(first[0]),
+                  "car_ticks_per_s": cars * ticks / float(first[0])}
+    except Exception as e:      # no compiler on the box: the Python figures stand alone
+        native = {"unavailable": str(e)[:100]}
+    return {"cars": cars, "ticks": ticks, "plans": cars * ticks, "found": int(ro.found - cars), "native_host_loop": native,
             "plans_per_s_in_plan_calls": cars * ticks / t_plan[0], "car_ticks_per_s_whole_loop": cars * ticks / wall,
             "real_time_factor_planning_only": sim_s / t_plan[0], "real_time_factor_whole_loop": sim_s / wall,
             "mean_metres_driven": float((ro.x - [s_[0] for s_ in starts]).mean())}

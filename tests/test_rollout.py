@@ -91,3 +91,26 @@ def test_cuda_rollout_equals_oracle_rollout(oracle, cuda_device):
     np.testing.assert_array_equal(got, want)
     assert ro.found == ro.plans == 640
     pl.close()
+
+
+@pytest.mark.gpu
+def test_native_rollout_equals_python_rollout(cuda_device, tmp_path):
+    """autonomouscar_b200/host/route_rollout_b200.hpp (C++ on the C ABI) drives the same cars to the same
+    states, bit for bit, as the Python loop around the same CUDA planner."""
+    import os
+    import subprocess
+    from autonomouscar_b200 import Planner
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "autonomouscar_b200")
+    exe = str(tmp_path / "test_route_rollout")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(pkg, "host"),
+                           os.path.join(root, "tests", "cpp", "test_route_rollout.cpp"), "-o", exe,
+                           "-L", pkg, "-lprius_planner_b200", f"-Wl,-rpath,{pkg}"])
+    lines = subprocess.check_output([exe, "64", "10", "2.0"]).decode().splitlines()
+    secs, plans, found = lines[0].split()
+    assert int(plans) == 640 and int(found) == 640
+    got = np.array([[float.fromhex(v) for v in ln.split()] for ln in lines[1:]])
+    pl = Planner(default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000), device=0)
+    want = rollout.RouteRollout(_starts(64)).run(rollout.plan_batch_cuda(pl), 10)[-1]
+    np.testing.assert_array_equal(got, want)
+    pl.close()
