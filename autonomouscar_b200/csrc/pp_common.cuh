@@ -59,6 +59,9 @@ struct GridDev {
   //   coarse[ci8 * CW8 + (cj8 >> 6)] bit (cj8 & 63), ci8 = (i + halo) >> 3, cj8 = (j + halo) >> 3
   unsigned long long* coarse;
   int CI8, CW8;
+  // the same per 4x4-cell block (tighter pre-test of the batch kernel's bounding box): ci4 = (i + halo) >> 2
+  unsigned long long* coarse4;
+  int CI4, CW4;
   // `coarse` dilated by `reach8` blocks in every direction: bit set <=> some obstacle cell lies
   // within the yaw-independent square that bounds the footprint around a pose in that block
   unsigned long long* near8;
@@ -142,6 +145,22 @@ __device__ __forceinline__ bool coarse_box_any(const GridDev& g, int i0, int i1,
   unsigned long long any = 0;
   for (int r = r0; r <= r1; ++r) {
     const unsigned long long* row = g.coarse + static_cast<size_t>(r) * g.CW8 + w0;
+    unsigned long long bits = __ldg(row) >> sh;
+    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
+    any |= bits & m;
+  }
+  return any != 0;
+}
+
+// 4x4-cell coarse occupancy under the cell box [i0,i1] x [j0,j1] (<= 16 x 16 coarse cells)
+__device__ __forceinline__ bool coarse4_box_any(const GridDev& g, int i0, int i1, int j0, int j1) {
+  const int r0 = (i0 + kHaloCells) >> 2, r1 = (i1 + kHaloCells) >> 2;
+  const int c0 = (j0 + kHaloCells) >> 2, c1 = (j1 + kHaloCells) >> 2;
+  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 16 bits starting at bit c0
+  const unsigned long long m = ((1ull << nb) - 1ull);
+  unsigned long long any = 0;
+  for (int r = r0; r <= r1; ++r) {
+    const unsigned long long* row = g.coarse4 + static_cast<size_t>(r) * g.CW4 + w0;
     unsigned long long bits = __ldg(row) >> sh;
     if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
     any |= bits & m;

@@ -84,6 +84,28 @@ __global__ void build_coarse(const uint32_t* __restrict__ tiles, unsigned long l
   }
 }
 
+// 4x4-cell coarse occupancy: thread per (coarse row, tile column) ORs 4 tile words -> 8 bits
+__global__ void build_coarse4(const uint32_t* __restrict__ tiles, unsigned long long* __restrict__ coarse4, int TI,
+                              int TJ, int CW4) {
+  const int64_t total = static_cast<int64_t>(TI) * 8 * TJ;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int tj = static_cast<int>(k % TJ);
+    const int ci4 = static_cast<int>(k / TJ);
+    const int ti = ci4 >> 3, r0 = (ci4 & 7) * 4;
+    const uint32_t* t = tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
+    const uint32_t w = t[0] | t[1] | t[2] | t[3];
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      if ((w >> (4 * b)) & 0xfu) bits |= 1ull << b;
+    if (bits) {
+      const int cj4 = tj * 8;
+      atomicOr(&coarse4[static_cast<size_t>(ci4) * CW4 + (cj4 >> 6)], bits << (cj4 & 63));
+    }
+  }
+}
+
 // near8 = coarse dilated by r8 blocks (square structuring element), one thread per 64-bit word
 __global__ void dilate_coarse(const unsigned long long* __restrict__ coarse, unsigned long long* __restrict__ near8,
                               int CI8, int CW8, int r8) {
@@ -163,6 +185,7 @@ void grid_free(pp_handle* h) {
   cudaFree(g.occ_tiles);
   cudaFree(g.tile_any);
   cudaFree(g.coarse);
+  cudaFree(g.coarse4);
   cudaFree(g.near8);
   cudaFree(g.aabb_map);
   g = GridDev{};
@@ -191,6 +214,9 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
     g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
     PP_CUDA(cudaMalloc(&g.coarse, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
     PP_CUDA(cudaMalloc(&g.near8, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
+    g.CI4 = g.TI * 8;
+    g.CW4 = (g.TJ * 8 + 63) / 64 + 1;
+    PP_CUDA(cudaMalloc(&g.coarse4, sizeof(unsigned long long) * static_cast<size_t>(g.CI4) * g.CW4));
     {
       // half diagonal of the footprint in cells + 1 (floor) + 2 (float slack of the pre-test)
       const double du = h->lat.su * h->lat.hu, dv = h->lat.sv * h->lat.hv;
@@ -238,7 +264,9 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
   PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8, s));
   build_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.TJ, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.coarse, g.TI, g.TJ, g.CW8);
   dilate_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.CW8, T, h->sm_count), T, 0, s>>>(g.coarse, g.near8, g.CI8, g.CW8, (g.reach_cells + 7) / 8);
-  h->launches += 2;
+  PP_CUDA(cudaMemsetAsync(g.coarse4, 0, sizeof(unsigned long long) * static_cast<size_t>(g.CI4) * g.CW4, s));
+  build_coarse4<<<blocks_for(static_cast<int64_t>(g.CI4) * g.TJ, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.coarse4, g.TI, g.TJ, g.CW4);
+  h->launches += 3;
   aabb_pass_y<<<blocks_for(static_cast<int64_t>(W) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(g.cspace, rows, W, H, g.aabb_ny, ylo, yhi);
   aabb_pass_x<<<blocks_for(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(rows, g.aabb_map, W, g.aabb_nx, g.aabb_ny, xlo, xhi);
   h->launches += 4;

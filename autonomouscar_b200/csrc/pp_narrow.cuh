@@ -52,7 +52,7 @@ __device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, con
       occ |= (any ? 1u : 0u) << (a * 3 + b);
     }
   if (occ == 0) return false;                                            // no obstacle in any tile under the box
-  if (broad_phase && !coarse_box_any(g, i0, i1, j0, j1)) return false;   // none in the 8x8 blocks under it
+  if (broad_phase && !coarse4_box_any(g, i0, i1, j0, j1)) return false;  // none in the 4x4 blocks under it
   // re-base the lattice origin from the anchor cell to the first tile's corner
   const int ci0 = t0i * kTile - kHaloCells, cj0 = t0j * kTile - kHaloCells;
   job->oi = p.oi + ((p.ai - ci0) << kFracBits);
