@@ -60,6 +60,9 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred, int lane) {
   return base + __popc(bal & ((1u << lane) - 1u));
 }
 
+#ifndef PP_LATTICE_S
+#define PP_LATTICE_S 2
+#endif
 #ifndef PP_COLLIDE_MIN_BLOCKS
 #define PP_COLLIDE_MIN_BLOCKS 4
 #endif
@@ -239,7 +242,7 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
     static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : 64;
     const int blocks = grid_blocks(h, n, kChunk, bps);
     if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
-      collide_oriented_kernel<48, 17, 2><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
+      collide_oriented_kernel<48, 17, PP_LATTICE_S><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
     else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells
       collide_oriented_kernel<20, 8, 4><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
     else
