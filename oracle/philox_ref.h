@@ -5,7 +5,7 @@
 // ten rounds of two 32x32->64 multiplies, key bumped by the Weyl constants between
 // rounds.  The reference repository has no RNG in its planner; this is
 // row S1 of the scope table, an extension.  Known-answer vectors from the paper's
-// reference implementation are pinned in tests/test_oracle_philox.py.
+// reference implementation are pinned in tests/test_oracle_kat.py::test_philox_known_answers.
 #pragma once
 #include <cstdint>
 

@@ -4,6 +4,11 @@
 // sampling and no nearest-neighbour query, so the semantics below are defined
 // by this build (DESIGN.md "Sampling planner") and the CUDA kernels must match them bit
 // for bit.  The motion model is the reference's forward step, LP:155-157.
+//
+// PARITY UNPINNED BY THE REFERENCE for these rows: there is no reference code, test or golden vector
+// to pin a sampler, a nearest-neighbour query or an oriented footprint against.  They are pinned by
+// their own specification, the Random123 known answers for Philox and hand-derived cases
+// (tests/test_oracle_kat.py); everything the reference DOES contain is pinned against oracle/_ref.
 #pragma once
 #include <cmath>
 #include <cstdint>
