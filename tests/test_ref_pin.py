@@ -225,3 +225,55 @@ def test_cuda_ref_aabb_collision_equals_the_reference_booleans(cuda_device):
     np.testing.assert_array_equal(got[defined], want[defined])
     assert want[defined].sum() > 500
     pl.close()
+
+
+def test_oracle_matches_live_reference_on_random_parameters(oracle):
+    """The launch-file values are one point; the reference's arithmetic has parameter-dependent traps (the
+    26 / 27-heading loop bound, the int() of the velocity count, search_res in the goal test).  Randomised
+    node parameters, window sizes and footprints: the oracle still equals the reference node bit for bit."""
+    ref = _ref()
+    from autonomouscar_b200 import default_params, worlds
+    rng = np.random.default_rng(424242)
+    outcomes = set()
+    for trial in range(14):
+        aabb = trial % 2 == 0
+        res = float(rng.choice([0.1, 0.2, 0.25, 0.5]))
+        # windows of 40 - 60 m: no candidate can leave them (the reference's markVisited is unchecked, LP:318-326)
+        W, H = int(rng.integers(40, 60) / res), int(rng.integers(40, 60) / res)
+        p = default_params(
+            costmap_res=res, costmap_width=W, costmap_height=H,
+            collision_mode=PP_COLLISION_REF_AABB if aabb else PP_COLLISION_AS_SHIPPED,
+            time_step_ms=float(rng.choice([100.0, 150.0, 200.0, 300.0])),
+            velocity_res=float(rng.choice([0.05, 0.1, 0.15])),
+            heading_res=float(rng.choice([0.005, 0.01, 0.0078125, 0.004])),
+            heading_diff=float(rng.choice([0.03, 0.065, 0.0625, 0.1])),
+            goal_pos_tolerance=float(rng.choice([0.1, 0.3])), goal_speed_tolerance=float(rng.choice([0.5, 0.2])),
+            search_res=float(rng.choice([0.1, 0.25, 0.4])),
+            car_length=float(rng.uniform(3.0, 5.2)), car_width=float(rng.uniform(1.2, 2.0)),
+            max_nodes=int(rng.integers(400, 6000)), max_expansions=int(rng.choice([40, 300])))
+        cs0 = worlds.block_grid(W, H, frac=float(rng.choice([0.0, 0.01, 0.02])), block=int(rng.choice([2, 4, 8])), seed=trial)
+        worlds.clear_disc(cs0, p, 0.0, 0.0, 4.0)
+        msg = np.ascontiguousarray(cs0.reshape(-1)[::-1])
+        extent = min(W, H) * res / 2
+        q = make_query(float(rng.uniform(2.0, min(18.0, extent - 8.0))), float(rng.uniform(-3.0, 3.0)),
+                       goal_speed=float(rng.choice([0.0, 1.0, 1.5])), max_speed=float(rng.choice([1.5, 3.0])),
+                       max_accel=float(rng.choice([1.0, 1.5, 2.0])), start_speed=float(rng.uniform(0.0, 1.5)))
+        o = oracle.plan(p, cs0, q, math_mode=oracle.MATH_LIBM, want_visited=True, cap_nodes=1 << 15, cap_expansions=1 << 15)
+        if o.status not in (PP_PLAN_FOUND, PP_PLAN_CAP):
+            continue
+        node = ref.RefNode(p, ref.AABB if aabb else ref.SHIPPED)
+        assert node.footprint() == (p.car_length, p.car_width)
+        node.set_grid_msg(msg)
+        r = node.plan(q, cap_nodes=1 << 15, want_visited=True)
+        oo, oc = _lists(o)
+        assert (r.status == 0) == (o.status == PP_PLAN_FOUND), trial
+        np.testing.assert_array_equal(r.open_state[:, :7], oo[:, :7])
+        np.testing.assert_array_equal(r.closed_state, oc)
+        np.testing.assert_array_equal(r.path_xy, o.path_xy)
+        np.testing.assert_array_equal(r.yaw_rates, o.yaw_rates)
+        np.testing.assert_array_equal(r.speeds, o.speeds)
+        np.testing.assert_array_equal(r.durations, o.durations)
+        np.testing.assert_array_equal(r.visited, o.visited)
+        outcomes.add(o.status)
+        node.close()
+    assert outcomes == {PP_PLAN_FOUND, PP_PLAN_CAP}
