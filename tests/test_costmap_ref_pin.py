@@ -87,3 +87,39 @@ def test_oracle_matches_live_reference_global_costmap(oracle, tmp_path):
         want, _ = ref.global_costmap_build(p, xy, off, tmp_path)
         got, _ = oracle.global_costmap_build(p, xy, off, math_mode=oracle.MATH_LIBM)
         np.testing.assert_array_equal(got, want)
+
+
+def test_oracle_matches_live_reference_costmap_over_parameters(oracle):
+    """Other resolutions, non-square windows (the reference divides by the HEIGHT where it should use the
+    width, LC:279 -- restated, not repaired), other buffers / ranges / inflation radii."""
+    from autonomouscar_b200 import worlds
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    from oracle import ref_binding as ref
+    if not ref.costmap_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    cases = [  # res, height_cells, width_cells, z buffer, obstacle range, max inflation, global map?
+        (0.25, 300.0, 260.0, 0.075, 2.0, 5.0, False),
+        (0.25, 260.0, 300.0, 0.2, 1.0, 8.0, False),
+        (0.5, 150.0, 150.0, 0.075, 2.0, 5.0, True),
+        (0.2, 400.0, 400.0, 0.0, 3.5, 2.0, True),
+        (0.125, 520.0, 500.0, 0.075, 2.0, 10.0, False),
+    ]
+    for k, (res, hc, wc, zb, orange, infl, with_global) in enumerate(cases):
+        G = 1200
+        p = default_costmap_params(res=res, height_cells=hc, width_cells=wc, z_ground_buffer=zb, obstacle_range=orange,
+                                   max_inflation_radius=infl, global_height_cells=float(G), global_width_cells=float(G))
+        car = (20.0 + 7 * k, -15.0 + 3 * k, 0.3 * k - 0.5)
+        ref.costmap_set_tfs(worlds.costmap_tfs(*car))
+        node = ref.RefCostmap(p)
+        assert (node.params.height_cells, node.params.width_cells) == (hc, wc)
+        sc = worlds.costmap_scene(500 + k, max_reach=28.0)
+        ref.costmap_derive_inputs(sc)
+        g = None
+        if with_global:
+            g = worlds.road_like_global_grid(G, 11 * k, zero_at=worlds.costmap_corner_global_cells(p, *car))
+            node.set_global(g)
+        want, _ = node.build(sc)
+        got, _ = oracle.costmap_build(node.params, sc.inputs, g, math_mode=oracle.MATH_LIBM)
+        np.testing.assert_array_equal(got, want)
+        assert (want == 100).sum() > 200
+        node.close()

@@ -280,3 +280,27 @@ def test_gpu_chain_equals_reference_node_chain(cuda_device):
     assert found >= 5 and rejected > 0, (found, rejected)
     for o in (ref_costmap, ref_planner, cm, pl):
         o.close()
+
+
+def test_costmap_parameter_variants_bit_exact(oracle, cuda_device):
+    """Other resolutions, non-square windows, buffers, ranges, inflation radii, global-map sizes."""
+    from autonomouscar_b200 import LocalCostmap, worlds
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    cases = [(0.25, 300.0, 260.0, 0.075, 2.0, 5.0, False), (0.25, 260.0, 300.0, 0.2, 1.0, 8.0, True),
+             (0.5, 150.0, 150.0, 0.075, 2.0, 5.0, True), (0.2, 400.0, 400.0, 0.0, 3.5, 2.0, True),
+             (0.125, 520.0, 500.0, 0.075, 2.0, 10.0, False), (0.1, 1024.0, 1024.0, 0.075, 2.0, 5.0, True)]
+    for k, (res, hc, wc, zb, orange, infl, with_global) in enumerate(cases):
+        G = 1200
+        p = default_costmap_params(res=res, height_cells=hc, width_cells=wc, z_ground_buffer=zb, obstacle_range=orange,
+                                   max_inflation_radius=infl, global_height_cells=float(G), global_width_cells=float(G))
+        car = (20.0 + 7 * k, -15.0 + 3 * k, 0.3 * k - 0.5)
+        sc = worlds.costmap_scene(500 + k, max_reach=28.0)
+        _fill_tf(sc, car)
+        g = worlds.road_like_global_grid(G, 11 * k) if with_global else None
+        cm = LocalCostmap(p, device=0)
+        cm.set_global_grid(g)
+        got = cm.build(sc)
+        want, _ = oracle.costmap_build(p, sc.inputs, g, math_mode=oracle.MATH_DET)
+        np.testing.assert_array_equal(got, want)
+        assert (got == 100).sum() > 200
+        cm.close()
