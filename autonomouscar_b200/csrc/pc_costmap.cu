@@ -268,8 +268,9 @@ int capture(pc_handle* h) {
   PP_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   launch_pass(h, h->stream);
   PP_CUDA(cudaStreamEndCapture(h->stream, &g));
-  PP_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+  const cudaError_t e = cudaGraphInstantiate(&h->graph, g, 0);
   cudaGraphDestroy(g);
+  PP_CUDA(e);
   return PP_OK;
 }
 

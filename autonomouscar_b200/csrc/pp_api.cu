@@ -276,22 +276,26 @@ int pp_footprint_points(pp_handle* h, double x, double y, double yaw, double* ou
                         int32_t* n_points) {
   if (!h || !out_xy_host || !n_points || capacity < 0) return PP_ERR_INVALID;
   PP_CUDA(cudaSetDevice(h->device));
-  double* d = nullptr;
-  int* dn = nullptr;
-  PP_CUDA(cudaMalloc(&d, sizeof(double) * 2 * static_cast<size_t>(capacity) + 16));
-  PP_CUDA(cudaMalloc(&dn, sizeof(int)));
+  // one allocation: [count | pad | 2*capacity doubles]; debug entry point, not on the hot path
+  char* blk = nullptr;
+  const size_t bytes = 16 + sizeof(double) * 2 * static_cast<size_t>(capacity);
+  PP_CUDA(cudaMalloc(&blk, bytes));
+  int* dn = reinterpret_cast<int*>(blk);
+  double* d = reinterpret_cast<double*>(blk + 16);
   int rc = footprint_points_dev(h, x, y, yaw, d, capacity, dn);
-  if (rc == PP_OK) {
-    int n = 0;
-    cudaMemcpyAsync(&n, dn, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
-    cudaMemcpyAsync(out_xy_host, d, sizeof(double) * 2 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
-    *n_points = n;
+  int n = 0;
+  cudaError_t e = cudaSuccess;
+  if (rc == PP_OK) e = cudaMemcpyAsync(&n, dn, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (rc == PP_OK && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (rc == PP_OK && e == cudaSuccess && n > 0) {
+    e = cudaMemcpyAsync(out_xy_host, d, sizeof(double) * 2 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   }
-  cudaFree(d);
-  cudaFree(dn);
-  return rc;
+  cudaFree(blk);
+  if (rc != PP_OK) return rc;
+  PP_CUDA(e);
+  *n_points = n;
+  return PP_OK;
 }
 
 int pp_sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t first_index, int64_t n, float x_lo,
