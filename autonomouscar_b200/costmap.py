@@ -72,6 +72,19 @@ class LocalCostmap:
         p, w, h = self.grid_dev()
         planner._check(planner._L.pp_set_grid_dev(planner._h, C.c_void_p(p), w, h, self.params.res, PP_GRID_OCCUPANCY_MSG))
 
+    def front_regions(self):
+        """Region mask of the most recent grid as the query generator reads it (local_navigator.py:81-257,
+        bits PC_REGION_* of prius_costmap.h; decode with rollout.RegionFlags)."""
+        m = C.c_uint32()
+        self._check(self._L.pc_front_regions(self._h, C.byref(m)))
+        return m.value
+
+    def front_regions_of(self, grid_dev_ptr, info_width, n_cells):
+        """The same scan over any device-resident OccupancyGrid.data (e.g. a torch int8 tensor's data_ptr())."""
+        m = C.c_uint32()
+        self._check(self._L.pc_front_regions_dev(self._h, C.c_void_p(grid_dev_ptr), int(info_width), int(n_cells), C.byref(m)))
+        return m.value
+
     def launch_count(self):
         v = C.c_uint64()
         self._check(self._L.pc_launch_count(self._h, C.byref(v)))

@@ -200,6 +200,36 @@ __global__ void pc_pack_kernel(const int* __restrict__ occ, int8_t* __restrict__
     out[k] = static_cast<int8_t>(occ[k]);
 }
 
+// Row N4 (query generator): the region scan of local_navigator.py:112-257 on the device grid.  The
+// navigator unpacks the message as board[x][y] = data[x * info.width + y] (:101-110) and walks
+// x ascending, y from 100 up; only x in 120..179, y in 180..299 is ever looked at.  Per 30-cell band
+// k (F1..F4 at y 180.., 210.., 240.., 270..): F_k = ANY cell == 100 in x 140..159; R_k / L_k keep the
+// verdict of the LAST cell scanned in x 120..139 / 160..179 (their else-branches reset the flag).
+// Bit layout of the mask: PC_REGION_* in prius_costmap.h.
+__global__ void pc_front_regions_kernel(const int8_t* __restrict__ grid, int W, unsigned* __restrict__ out) {
+  __shared__ unsigned s_mask;
+  if (threadIdx.x == 0) s_mask = 0;
+  __syncthreads();
+  unsigned m = 0;
+  for (int t = threadIdx.x; t < 60 * 120; t += blockDim.x) {
+    const int x = 120 + t / 120, y = 180 + t % 120;
+    if (x >= W || y >= W) continue;
+    const bool hit = grid[static_cast<long long>(x) * W + y] == 100;
+    const int band = (y - 180) / 30, col = (x - 120) / 20;
+    if (col == 1) {
+      if (hit) m |= 1u << band;
+    } else {
+      const int x_last = min(col == 0 ? 139 : 179, W - 1), y_last = min(209 + 30 * band, W - 1);
+      if (col == 2 && hit) m |= PC_REGION_ANY_L_HIT;
+      if (x == x_last && y == y_last) m |= (hit ? 1u : 0u) << ((col == 0 ? 4 : 8) + band) | 1u << ((col == 0 ? 16 : 20) + band);
+    }
+  }
+  m = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_mask, m);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s_mask;
+}
+
 }  // namespace pp
 
 using namespace pp;
@@ -216,6 +246,7 @@ struct pc_handle {
   int8_t* h_out = nullptr;          // pinned mirror
   int8_t* d_global = nullptr;
   long long global_len = 0;
+  unsigned* d_regions = nullptr;    // pc_front_regions result
   unsigned char* h_in = nullptr;    // pinned: PcDevHeader | payload floats
   unsigned char* d_in = nullptr;
   size_t in_cap = 0;                // bytes
@@ -324,6 +355,7 @@ int pc_create(const pc_params* params, int device, pc_handle** out) {
   PC_TRY(cudaMalloc(&h->d_work, sizeof(int) * 2 * static_cast<size_t>(h->G.len)));
   PC_TRY(cudaMalloc(&h->d_out, static_cast<size_t>(h->G.len)));
   PC_TRY(cudaMallocHost(&h->h_out, static_cast<size_t>(h->G.len)));
+  PC_TRY(cudaMalloc(&h->d_regions, sizeof(unsigned)));
 #undef PC_TRY
   *out = h;
   return PP_OK;
@@ -334,7 +366,7 @@ int pc_destroy(pc_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph) cudaGraphExecDestroy(h->graph);
-  cudaFree(h->d_work); cudaFree(h->d_out); cudaFree(h->d_global); cudaFree(h->d_in);
+  cudaFree(h->d_work); cudaFree(h->d_out); cudaFree(h->d_global); cudaFree(h->d_in); cudaFree(h->d_regions);
   cudaFreeHost(h->h_out); cudaFreeHost(h->h_in);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -429,6 +461,28 @@ int pc_grid_dev(pc_handle* h, const int8_t** out_dev, int32_t* width, int32_t* h
   if (width) *width = static_cast<int32_t>(h->P.width_cells);
   if (height) *height = static_cast<int32_t>(h->P.height_cells);
   return PP_OK;
+}
+
+int pc_front_regions_dev(pc_handle* h, const int8_t* grid_dev, int32_t info_width, int64_t len, uint32_t* out_mask) {
+  if (!h || !grid_dev || !out_mask) { set_last_error("pc_front_regions: null argument"); return PP_ERR_INVALID; }
+  // the navigator reads info.width * info.width entries (local_navigator.py:82-83, 104-110)
+  PP_REQUIRE(info_width >= 0 && info_width <= 16384 && static_cast<int64_t>(info_width) * info_width <= len,
+             "pc_front_regions: fewer than width * width cells (the reference runs off msg.data)");
+  PP_CUDA(cudaSetDevice(h->device));
+  pc_front_regions_kernel<<<1, 256, 0, h->stream>>>(grid_dev, info_width, h->d_regions);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  unsigned m = 0;
+  PP_CUDA(cudaMemcpyAsync(&m, h->d_regions, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  if ((m & 0xFu) && !(m & PC_REGION_ANY_L_HIT)) m |= PC_REGION_OBSTACLE;   // self.obstacle once the scan is over
+  *out_mask = m;
+  return PP_OK;
+}
+
+int pc_front_regions(pc_handle* h, uint32_t* out_mask) {
+  if (!h) { set_last_error("pc_front_regions: null handle"); return PP_ERR_INVALID; }
+  return pc_front_regions_dev(h, h->d_out, static_cast<int32_t>(h->P.width_cells), h->G.len, out_mask);
 }
 
 int pc_stream(pc_handle* h, void** out_stream) {

@@ -7,6 +7,10 @@ queries" become N full drives along the reference's route:
       densify_route     :27-46    way-points every `distBetweenWP` = 1 m
       WaypointSelector  :586-609  closest way-point from the current index on, then forward
                                   until it is at least `mindistToNextWP` = 20 m away
+      RegionFlags       :81-257   which of the F / R / L regions in front of the car hold a cell == 100
+                                  (the scan itself runs on the device grid: pc_front_regions)
+      LocalNavigator    :13-78, 259-368, 546-716   the node: three callbacks and one 20 Hz loop pass,
+                                  with the obstacle branch (slow down / swerve left / stop way-points)
       query constants   :521-527  speed = max_speed = max_accel = 1.5, 20 Hz
   * the profile follower: catkin_ws/src/prius_controller/src/controller.cpp
       ProfileFollower   :144-158, 178-185   cursor through the /mp profile: entry k lasts
@@ -17,8 +21,11 @@ yaw rate and speed are taken from the profile entry under the cursor and integra
 controller's 100 Hz (controller_node.cpp:14).  That stand-in is this repository's, not the
 reference's; everything it feeds -- every LocalNav goal, every plan, every profile -- goes through
 the same code paths as a live system.  The navigator is Python 2 / rospy and cannot be imported
-here, so these few lines are restated by hand ("parity unpinned" for them); the planner inside the
-loop is pinned (tests/test_rollout.py drives the REFERENCE node and the oracle through the same loop).
+here as a ROS node, but it parses as Python 3: tests/test_navigator_ref_pin.py imports it UNMODIFIED against
+rospy test doubles (oracle/ref_navigator.py) and checks every published LocalNav, the path index and the
+region flags against this mirror (live in this container, committed outputs in tests/golden/ elsewhere).
+The controller's cursor is restated by hand; the planner inside the loop is pinned (tests/test_rollout.py
+drives the REFERENCE planner node and the oracle through the same loop).
 
 `plan_batch` is any callable (list of pp_query) -> list of (found, yaw_rates, durations_ms, speeds):
 the CUDA planner (plan_batch_cuda), the oracle or the reference node (tests).
@@ -82,6 +89,96 @@ class WaypointSelector:
                 break
             d = math.sqrt((x - r[self.path_index][0]) ** 2 + (y - r[self.path_index][1]) ** 2)
         return r[self.path_index]
+
+
+# bits of the region mask (include/prius_costmap.h, PC_REGION_*)
+def _region_bit(base, k):
+    return 1 << (base + k - 1)
+
+
+class RegionFlags:
+    """Decoded pc_front_regions mask: F[k-1], R[k-1], L[k-1] for k = 1..4, `obstacle`, and which of the
+    R / L flags the scan rewrote (a grid narrower than 300 cells leaves some untouched)."""
+
+    def __init__(self, mask):
+        self.mask = mask
+        self.F = [bool(mask & _region_bit(0, k)) for k in (1, 2, 3, 4)]
+        self.R = [bool(mask & _region_bit(4, k)) for k in (1, 2, 3, 4)]
+        self.L = [bool(mask & _region_bit(8, k)) for k in (1, 2, 3, 4)]
+        self.obstacle = bool(mask & (1 << 12))
+        self.R_scanned = [bool(mask & _region_bit(16, k)) for k in (1, 2, 3, 4)]
+        self.L_scanned = [bool(mask & _region_bit(20, k)) for k in (1, 2, 3, 4)]
+
+
+def yaw_from_quaternion(qw, qx, qy, qz):
+    """local_navigator.py:70-75."""
+    return math.atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz))
+
+
+class LocalNavigator:
+    """The query generator node (local_navigator.py) as its three callbacks and one loop pass.
+
+    on_path / on_pose / on_costmap are callbackPath / callbackCarPos / callbackOccGrid; the last takes
+    the region mask of the costmap (LocalCostmap.front_regions(), computed on the device) instead of the
+    OccupancyGrid message.  spin_once() is one pass of the 20 Hz loop (:551-716) and returns the
+    LocalNav it publishes as (x, y, speed, max_speed, max_accel), or None."""
+
+    def __init__(self, spacing=DIST_BETWEEN_WP, min_dist=MIN_DIST_TO_NEXT_WP):
+        self.spacing, self.min_dist = spacing, min_dist
+        self.selector = None
+        self.pose = [0.0, 0.0, 0.0, 0.0]                 # x, y, 0, theta (:76)
+        self.got_pose = False
+        self.obstacle = False
+        self.F, self.R, self.L = [False] * 4, [False] * 4, [False] * 4
+        self.avoid = (0.0, 0.0, 0.0)                     # obstacle_avoid_wpx, _wpy, _spd (:498-500)
+        self.intermediate_wp = False
+
+    @property
+    def path_index(self):
+        return self.selector.path_index if self.selector else 0
+
+    def on_path(self, xy):                               # :13-62, acts on the first message only
+        if self.selector is None:
+            self.selector = WaypointSelector(densify_route([list(p) for p in xy], self.spacing), self.min_dist)
+
+    def on_pose(self, x, y, yaw):                        # :66-78
+        self.pose = [x, y, 0, yaw]
+        self.got_pose = True
+
+    def on_odometry(self, x, y, qw, qx, qy, qz):
+        self.on_pose(x, y, yaw_from_quaternion(qw, qx, qy, qz))
+
+    def on_costmap(self, mask):                          # :81-368
+        f = mask if isinstance(mask, RegionFlags) else RegionFlags(mask)
+        self.obstacle, self.F = f.obstacle, list(f.F)
+        self.R = [v if seen else old for v, seen, old in zip(f.R, f.R_scanned, self.R)]
+        self.L = [v if seen else old for v, seen, old in zip(f.L, f.L_scanned, self.L)]
+        x, y, heading = self.pose[0], self.pose[1], self.pose[3]
+        c, s = math.cos(heading), math.sin(heading)
+        cl, sl = math.cos(heading + 1.5708), math.sin(heading + 1.5708)
+        ax, ay, spd = self.avoid
+        if self.F[3]:                                    # :278-290  far: keep straight, slow down
+            ax, ay, spd = x + c * 22.5, y + s * 22.5, 2.0
+        if self.F[2]:                                    # :292-305  nearer: pass on the left
+            ax, ay, spd = x + c * 15 + cl * 6, y + s * 15 + sl * 6, 1.5
+        if self.F[1]:                                    # :307-320
+            ax, ay, spd = x + c * 7.5 + cl * 7, y + s * 7.5 + sl * 7, 1.0
+        if self.F[0]:                                    # :322-335  directly ahead: stop
+            ax, ay, spd = x + c * 5, y + s * 5, 0.0
+        self.avoid = (ax, ay, spd)
+
+    def spin_once(self):                                 # :551-716
+        if not self.got_pose:
+            return None
+        self.got_pose = False
+        if self.selector is None:
+            return None
+        if self.obstacle:                                # :561-583
+            self.intermediate_wp = True
+            return (self.avoid[0], self.avoid[1], self.avoid[2], MAX_SPEED, MAX_ACCEL)
+        wx, wy = self.selector.select(self.pose[0], self.pose[1])     # :586-624
+        self.intermediate_wp = False
+        return (wx, wy, SPEED, MAX_SPEED, MAX_ACCEL)
 
 
 class ProfileFollower:

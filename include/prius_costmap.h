@@ -85,6 +85,25 @@ int pc_stream(pc_handle* h, void** out_stream);
 int pc_launch_count(const pc_handle* h, uint64_t* out);
 int pc_last_build_ms(pc_handle* h, float* out_ms);
 
+/* Row N4: the region scan of the query generator, local_navigator.py:81-257 (callbackOccGrid), on the
+   most recent device grid -- the costmap does not cross PCIe for it either.  The navigator reads
+   board[x][y] = data[x * info.width + y] and looks at x 120..179, y 180..299 only:
+     F_k (x 140..159), k = 1..4 for y 180.., 210.., 240.., 270..: ANY cell == 100
+     R_k (x 120..139), L_k (x 160..179): the verdict of the LAST cell scanned (their else-branches)
+     obstacle: self.obstacle once the scan is over = (any F_k) and no L cell == 100 (the L regions are
+               scanned last and their hits write False, :214-257) */
+#define PC_REGION_F(k) (1u << ((k) - 1))          /* k = 1..4 */
+#define PC_REGION_R(k) (1u << (4 + (k) - 1))
+#define PC_REGION_L(k) (1u << (8 + (k) - 1))
+#define PC_REGION_OBSTACLE (1u << 12)
+#define PC_REGION_ANY_L_HIT (1u << 13)
+#define PC_REGION_R_SCANNED(k) (1u << (16 + (k) - 1)) /* region non-empty at this grid size: flag was rewritten */
+#define PC_REGION_L_SCANNED(k) (1u << (20 + (k) - 1))
+int pc_front_regions(pc_handle* h, uint32_t* out_mask);
+/* the same scan over any device-resident OccupancyGrid.data (len cells, info.width = info_width), on the
+   handle's stream */
+int pc_front_regions_dev(pc_handle* h, const int8_t* grid_dev, int32_t info_width, int64_t len, uint32_t* out_mask);
+
 /* ------------------------------------------------------------------------------------ */
 /* row N3: the static global road map (catkin_ws/src/global_costmap/src/global_costmap.cpp, */
 /* "GC"): road polylines -> the 12000 x 12000 lane-cost grid published once on            */

@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE: runs the reference's OWN query generator,
+  /root/reference/catkin_ws/src/local_navigator/src/local_navigator.py   (UNMODIFIED, imported where it lies)
+against the rospy test doubles of oracle/rospy_doubles/ and returns what it publishes on
+/local_nav_waypoints.  Used to pin autonomouscar_b200/rollout.py (row N4) and to generate
+tests/golden/ref_navigator.npz (tests/golden/make_navigator_golden.py).  Only tests/ may use this
+module; /root/reference does not exist on the GPU box, so GPU tests read the committed fixture.
+
+The node's whole life is its constructor (subscribe, then `while not rospy.is_shutdown()` at
+20 Hz, local_navigator.py:546-716).  The doubles deliver the scripted messages from inside
+Rate.sleep() and end the loop when the script is exhausted; time.sleep(35) (:531) is skipped.
+"""
+import contextlib
+import importlib.util
+import os
+import sys
+import time
+
+REFERENCE_FILE = "/root/reference/catkin_ws/src/local_navigator/src/local_navigator.py"
+_DOUBLES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "rospy_doubles")
+_FAKE = ("rospy", "nav_msgs", "nav_msgs.msg", "std_msgs", "std_msgs.msg", "geometry_msgs", "geometry_msgs.msg",
+         "prius_msgs", "prius_msgs.msg", "_msg")
+
+
+def available():
+    return os.path.exists(REFERENCE_FILE)
+
+
+@contextlib.contextmanager
+def _doubles():
+    saved = {k: sys.modules.pop(k) for k in _FAKE if k in sys.modules}
+    sys.path.insert(0, _DOUBLES)
+    real_sleep = time.sleep
+    time.sleep = lambda _s: None
+    try:
+        yield
+    finally:
+        time.sleep = real_sleep
+        sys.path.remove(_DOUBLES)
+        for k in _FAKE:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+
+
+def yaw_to_quaternion(yaw):
+    import math
+    return math.cos(yaw / 2), 0.0, 0.0, math.sin(yaw / 2)     # w, x, y, z
+
+
+def run(route_xy, passes):
+    """Drive the reference node.
+
+    route_xy: the /path way-points [(x, y), ...] (delivered once, before the first pass that sees a pose).
+    passes:   one dict per 20 Hz loop pass, delivered just before it:
+                {"pose": (x, y, qw, qx, qy, qz) | None,     # base_pose_ground_truth
+                 "grid": (info_width, flat int sequence) | None,   # local_costmap, delivered AFTER the pose
+                 "grid_first": bool}                        # deliver the grid before the pose instead
+    Returns (published, states): published[k] = dict of the LocalNav published in pass k or None;
+    states[k] = {"pathIndex", "obstacle", "F": [F1..F4], "R": [...], "L": [...], "avoid": (x, y, speed)}
+    read from the node object after pass k.
+    """
+    with _doubles():
+        import rospy
+        from nav_msgs.msg import OccupancyGrid, Odometry, Path
+        rospy.state.reset()
+        spec = importlib.util.spec_from_file_location("reference_local_navigator", REFERENCE_FILE)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)          # __name__ != "__main__": defines the class only
+
+        node_box, states = [], []
+
+        def snapshot():
+            n = node_box[0]
+            states.append({"pathIndex": n.pathIndex, "obstacle": bool(n.obstacle),
+                           "F": [bool(getattr(n, "regionF%d" % k)) for k in (1, 2, 3, 4)],
+                           "R": [bool(getattr(n, "regionR%d" % k)) for k in (1, 2, 3, 4)],
+                           "L": [bool(getattr(n, "regionL%d" % k)) for k in (1, 2, 3, 4)],
+                           "avoid": (n.obstacle_avoid_wpx, n.obstacle_avoid_wpy, n.obstacle_avoid_spd)})
+
+        script = [[("/path", Path(route_xy))]]
+        for p in passes:
+            ev = []
+            if p.get("pose") is not None:
+                ev.append(("base_pose_ground_truth", Odometry(*p["pose"])))
+            if p.get("grid") is not None:
+                w, data = p["grid"]
+                g = ("local_costmap", OccupancyGrid(width=w, height=w, resolution=0.25, data=data))
+                ev.insert(0, g) if p.get("grid_first") else ev.append(g)
+            script.append(ev)
+        rospy.state.script = script
+
+        # the subscribers are bound methods: the first one registered hands us the node object, and
+        # wrapping Rate.sleep lets us snapshot its state after every pass
+        real_sub = rospy.Subscriber.__init__
+
+        def sub_init(self, topic, typ, cb, queue_size=None):
+            if not node_box:
+                node_box.append(cb.__self__)
+            real_sub(self, topic, typ, cb, queue_size)
+
+        real_rate_sleep = rospy.Rate.sleep
+
+        def rate_sleep(self):
+            if rospy.state.passes >= 2:      # pass 0 saw nothing, pass 1 saw only /path
+                snapshot()
+            real_rate_sleep(self)
+
+        rospy.Subscriber.__init__ = sub_init
+        rospy.Rate.sleep = rate_sleep
+        mod.LocalNavigator()                  # returns when the script is exhausted
+        published = [None] * len(passes)
+        for k, _topic, fields in rospy.state.published:
+            # loop pass k processed script entry k-1; script entry 0 is /path, entry j+1 is passes[j]
+            published[k - 2] = fields
+        return published, states

@@ -1,0 +1,1 @@
+"""TEST INFRASTRUCTURE (see ../rospy/__init__.py)."""
