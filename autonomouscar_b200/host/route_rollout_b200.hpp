@@ -5,6 +5,8 @@
 //   densify_route     local_navigator.py:27-46      way-points every 1 m
 //   WaypointSelector  local_navigator.py:586-609    closest way-point from the current index on, then forward
 //                                                   until it is >= 20 m away
+//   LocalNavigator    local_navigator.py:13-78, 259-368, 546-716   the node: callbacks + one loop pass, with the
+//                                                   obstacle branch fed by the pc_front_regions mask (prius_costmap.h)
 //   ProfileFollower   controller.cpp:144-158,178-185  cursor through the /mp profile
 //   RouteRollout::tick  one LocalNav per car (goal in its base_link frame, LP:670-691), ONE pp_plan_batch call
 //                       for all cars, then the profile is tracked ideally at the controller's 100 Hz
@@ -65,6 +67,56 @@ struct WaypointSelector {
   }
 };
 
+// One LocalNav message (prius_msgs/LocalNav)
+struct LocalNavGoal { double x, y, speed, max_speed, max_accel; };
+
+// The query generator node as its callbacks and one 20 Hz loop pass; on_costmap takes the region mask the
+// device scan produced (pc_front_regions, bits PC_REGION_*) instead of the OccupancyGrid message.
+struct LocalNavigator {
+  WaypointSelector selector;
+  bool got_path = false, got_pose = false, obstacle = false;
+  bool F[4] = {false, false, false, false}, R[4] = {false, false, false, false}, L[4] = {false, false, false, false};
+  double x = 0, y = 0, heading = 0;                   // currentCarPose (:76)
+  double avoid_x = 0, avoid_y = 0, avoid_speed = 0;   // obstacle_avoid_wpx / _wpy / _spd (:498-500)
+  std::vector<RoutePoint> dense;                      // owned copy when on_path() densifies
+
+  void on_path(const std::vector<RoutePoint>& path) {               // :13-62, first message only
+    if (got_path) return;
+    dense = densify_route(path);
+    selector.route = &dense;
+    got_path = true;
+  }
+  void share_route(const std::vector<RoutePoint>* already_dense) { selector.route = already_dense; got_path = true; }
+  void on_pose(double px, double py, double yaw) { x = px; y = py; heading = yaw; got_pose = true; }   // :66-78
+  void on_odometry(double px, double py, double qw, double qx, double qy, double qz) {
+    on_pose(px, py, std::atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz)));                 // :70-75
+  }
+  void on_costmap(uint32_t mask) {                                   // :81-368
+    obstacle = (mask >> 12) & 1u;
+    for (int k = 0; k < 4; ++k) {
+      F[k] = (mask >> k) & 1u;
+      if ((mask >> (16 + k)) & 1u) R[k] = (mask >> (4 + k)) & 1u;
+      if ((mask >> (20 + k)) & 1u) L[k] = (mask >> (8 + k)) & 1u;
+    }
+    const double c = std::cos(heading), s = std::sin(heading);
+    const double cl = std::cos(heading + 1.5708), sl = std::sin(heading + 1.5708);
+    if (F[3]) { avoid_x = x + c * 22.5; avoid_y = y + s * 22.5; avoid_speed = 2.0; }                      // :278-290
+    if (F[2]) { avoid_x = x + c * 15 + cl * 6; avoid_y = y + s * 15 + sl * 6; avoid_speed = 1.5; }        // :292-305
+    if (F[1]) { avoid_x = x + c * 7.5 + cl * 7; avoid_y = y + s * 7.5 + sl * 7; avoid_speed = 1.0; }      // :307-320
+    if (F[0]) { avoid_x = x + c * 5; avoid_y = y + s * 5; avoid_speed = 0.0; }                            // :322-335
+  }
+  // one loop pass (:551-716); false = nothing published
+  bool spin_once(LocalNavGoal* out) {
+    if (!got_pose) return false;
+    got_pose = false;
+    if (!got_path) return false;
+    if (obstacle) { *out = LocalNavGoal{avoid_x, avoid_y, avoid_speed, 1.5, 1.5}; return true; }          // :561-583
+    const RoutePoint wp = selector.select(x, y);                                                          // :586-624
+    *out = LocalNavGoal{wp.first, wp.second, 1.5, 1.5, 1.5};
+    return true;
+  }
+};
+
 struct ProfileFollower {
   std::vector<double> yaw_rates, durations, speeds;
   int it = 0;
@@ -87,26 +139,30 @@ class RouteRollout {
   RouteRollout(pp_handle* planner, std::vector<RoutePoint> route, const std::vector<Car>& starts, int cap_path = 256)
       : h_(planner), route_(std::move(route)), cars_(starts), cap_(cap_path) {
     const size_t n = cars_.size();
-    selectors_.resize(n); followers_.resize(n); queries_.resize(n); results_.resize(n);
+    navigators_.resize(n); followers_.resize(n); queries_.resize(n); results_.resize(n);
     path_.resize(n * 2 * cap_); yr_.resize(n * cap_); du_.resize(n * cap_); sp_.resize(n * cap_);
     for (size_t k = 0; k < n; ++k) {
-      selectors_[k].route = &route_;
+      navigators_[k].share_route(&route_);
       pp_result r{};
       r.cap_path = cap_;
       r.path_xy = &path_[k * 2 * cap_]; r.yaw_rates = &yr_[k * cap_]; r.durations = &du_[k * cap_]; r.speeds = &sp_[k * cap_];
       results_[k] = r;
     }
   }
-  // one 20 Hz tick; returns the pp_status of the batch call
-  int tick() {
+  // one 20 Hz tick; returns the pp_status of the batch call.  masks (optional, one per car) = the region
+  // mask of each car's current costmap (pc_front_regions): enables the navigator's obstacle branch.
+  int tick(const uint32_t* masks = nullptr) {
     const int n = static_cast<int>(cars_.size());
     for (int k = 0; k < n; ++k) {
       const Car& c = cars_[k];
-      const RoutePoint wp = selectors_[k].select(c.x, c.y);
-      const double cs = std::cos(c.yaw), sn = std::sin(c.yaw), dx = wp.first - c.x, dy = wp.second - c.y;
+      LocalNavGoal wp{};
+      navigators_[k].on_pose(c.x, c.y, c.yaw);
+      if (masks) navigators_[k].on_costmap(masks[k]);
+      navigators_[k].spin_once(&wp);
+      const double cs = std::cos(c.yaw), sn = std::sin(c.yaw), dx = wp.x - c.x, dy = wp.y - c.y;
       pp_query q{};
       q.goal_x = cs * dx + sn * dy; q.goal_y = -sn * dx + cs * dy;            // LP:687-690
-      q.goal_speed = 1.5; q.max_speed = 1.5; q.max_accel = 1.5;                // local_navigator.py:524-527
+      q.goal_speed = wp.speed; q.max_speed = wp.max_speed; q.max_accel = wp.max_accel;   // local_navigator.py:524-527
       q.start_speed = c.v; q.query_id = static_cast<uint32_t>(k);
       queries_[k] = q;
     }
@@ -144,7 +200,7 @@ class RouteRollout {
   std::vector<Car> cars_;
   int cap_;
   double t_ = 0;
-  std::vector<WaypointSelector> selectors_;
+  std::vector<LocalNavigator> navigators_;
   std::vector<ProfileFollower> followers_;
   std::vector<pp_query> queries_;
   std::vector<pp_result> results_;

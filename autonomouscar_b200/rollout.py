@@ -211,25 +211,32 @@ class RouteRollout:
         st = np.array(list(starts), dtype=np.float64).reshape(-1, 4)
         self.x, self.y, self.yaw, self.v = st[:, 0].copy(), st[:, 1].copy(), st[:, 2].copy(), st[:, 3].copy()
         self.n = len(st)
-        self.selectors = [WaypointSelector(self.route) for _ in range(self.n)]
+        self.navigators = [LocalNavigator() for _ in range(self.n)]
+        for nav in self.navigators:                     # the route is already dense: share it
+            nav.selector = WaypointSelector(self.route)
         self.followers = [ProfileFollower() for _ in range(self.n)]
         self.t = 0.0
         self.plans = self.found = 0
         self.trace = []
 
-    def queries(self):
-        """One LocalNav per car, goal converted to its base_link frame (LP:670-691)."""
+    def queries(self, masks=None):
+        """One LocalNav per car, goal converted to its base_link frame (LP:670-691).  masks[k] (optional) is the
+        region mask of car k's current costmap (LocalCostmap.front_regions()): with it the navigator's obstacle
+        branch may replace the route way-point by a slow-down / swerve / stop way-point."""
         qs = []
-        for k in range(self.n):
-            wx, wy = self.selectors[k].select(self.x[k], self.y[k])
+        for k, nav in enumerate(self.navigators):
+            nav.on_pose(float(self.x[k]), float(self.y[k]), float(self.yaw[k]))
+            if masks is not None:
+                nav.on_costmap(masks[k])
+            wx, wy, speed, max_speed, max_accel = nav.spin_once()
             c, s = math.cos(self.yaw[k]), math.sin(self.yaw[k])
             dx, dy = wx - self.x[k], wy - self.y[k]
-            qs.append(make_query(c * dx + s * dy, -s * dx + c * dy, goal_speed=SPEED, max_speed=MAX_SPEED,
-                                 max_accel=MAX_ACCEL, start_speed=float(self.v[k]), query_id=k))
+            qs.append(make_query(c * dx + s * dy, -s * dx + c * dy, goal_speed=speed, max_speed=max_speed,
+                                 max_accel=max_accel, start_speed=float(self.v[k]), query_id=k))
         return qs
 
-    def tick(self, plan_batch):
-        results = plan_batch(self.queries())
+    def tick(self, plan_batch, masks=None):
+        results = plan_batch(self.queries(masks))
         self.plans += self.n
         for k, (found, yaw_rates, durations, speeds) in enumerate(results):
             if found:                                   # a failed plan publishes nothing: the old profile stays

@@ -110,3 +110,33 @@ def test_reference_navigator_known_answers():
                                         "grid": (300, g.reshape(-1).tolist())}])
         assert st[0]["F"] == [True, False, False, False] and st[0]["obstacle"]
         assert pub[0]["speed"] == 0.0 and pub[0]["y"] == 5.0
+
+
+def test_native_navigator_reproduces_reference_fixture(tmp_path):
+    """The C++ mirror (host/route_rollout_b200.hpp, used by the native roll-out) through the same script."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_local_navigator")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
+                           "-I", os.path.join(root, "autonomouscar_b200", "host"),
+                           os.path.join(root, "tests", "cpp", "test_local_navigator.cpp"), "-o", exe])
+    z = np.load(os.path.join(GOLD, "ref_navigator.npz"))
+    for seed in mng.SEEDS:
+        passes = mng.passes_from_fixture(z, seed)
+        rt = mng.route()
+        lines = ["route %d " % len(rt) + " ".join("%r %r" % p for p in rt)]
+        for p in passes:
+            ev = []
+            if p["pose"] is not None:
+                ev.append("odom " + " ".join(repr(float(v)) for v in p["pose"]))
+            if p["grid"] is not None:
+                w, g = p["grid"]
+                m = "mask %d" % navigator_ref.region_mask(g.reshape(-1), w)
+                ev.insert(0, m) if p["grid_first"] else ev.append(m)
+            lines += ev + ["spin"]
+        out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+        rows = np.array([[float(v) for v in ln.split()] for ln in out.strip().split("\n")])
+        assert len(rows) == len(passes)
+        pub = np.where(rows[:, :1] == 1, rows[:, 1:6], np.nan)
+        assert_same((pub, rows[:, 6:20].astype(np.int32), rows[:, 20:23]),
+                    (z[f"s{seed}_pub"], z[f"s{seed}_state"], z[f"s{seed}_avoid"]))
