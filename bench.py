@@ -525,6 +525,12 @@ def bench_costmap(args):
         out[key] = reps / (time.perf_counter() - t0)
         out["device_ms_per_grid"] = float(np.median(ms))
     out["kernels_per_grid"] = 5
+    # the query generator's region scan on the device grid (row N4, local_navigator.py:81-257)
+    t0 = time.perf_counter()
+    for k in range(300):
+        mask = cm.front_regions()
+    out["front_regions_call_us"] = (time.perf_counter() - t0) / 300 * 1e6
+    out["front_regions_mask"] = int(mask)
     out["h2d_bytes_per_grid"] = int(4 * (len(scenes[0].right) + len(scenes[0].left) + scenes[0].cloud.size))
     out["d2h_bytes_per_grid"] = cm.n_cells
     if not args.skip_cpu:
@@ -532,6 +538,9 @@ def bench_costmap(args):
         last = cm.build(scenes[0])
         det, _ = orc.costmap_build(p, scenes[0].inputs, gg, math_mode=orc.MATH_DET)
         out["bit_exact_vs_oracle"] = bool(np.array_equal(last, det))
+        from oracle import navigator_ref
+        cm.build(scenes[0], want_host=False)
+        out["front_regions_equal_oracle"] = bool(cm.front_regions() == navigator_ref.region_mask(det, int(p.width_cells)))
         secs = [orc.costmap_build(p, sc.inputs, gg, math_mode=orc.MATH_LIBM)[1] for sc in scenes]
         out["cpu_oracle_port_grids_per_s_1thread"] = len(secs) / sum(secs)
         if have_ref:
