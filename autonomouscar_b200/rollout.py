@@ -15,6 +15,7 @@ queries" become N full drives along the reference's route:
   * the profile follower: catkin_ws/src/prius_controller/src/controller.cpp
       ProfileFollower   :144-158, 178-185   cursor through the /mp profile: entry k lasts
                                   durations[k] / 1000 s of wall time, restarted on every new message
+      PriusController   :29-189   the node: that cursor + the steering / pedal PIDs -> prius_msgs/Control
 
 The vehicle itself (Gazebo + the two PIDs of controller.cpp:44-132) is replaced by an ideal tracker:
 yaw rate and speed are taken from the profile entry under the cursor and integrated at the
@@ -24,7 +25,8 @@ the same code paths as a live system.  The navigator is Python 2 / rospy and can
 here as a ROS node, but it parses as Python 3: tests/test_navigator_ref_pin.py imports it UNMODIFIED against
 rospy test doubles (oracle/ref_navigator.py) and checks every published LocalNav, the path index and the
 region flags against this mirror (live in this container, committed outputs in tests/golden/ elsewhere).
-The controller's cursor is restated by hand; the planner inside the loop is pinned (tests/test_rollout.py
+The controller (cursor and PIDs) is checked the same way against the reference's own controller.cpp compiled
+unmodified (oracle/_ref/libref_controller.so, tests/test_controller_ref_pin.py); the planner inside the loop is pinned (tests/test_rollout.py
 drives the REFERENCE planner node and the oracle through the same loop).
 
 `plan_batch` is any callable (list of pp_query) -> list of (found, yaw_rates, durations_ms, speeds):
@@ -200,6 +202,101 @@ class ProfileFollower:
         if self.it >= len(self.yaw_rates):
             return None
         return self.yaw_rates[self.it], self.speeds[self.it]
+
+
+def _ieee_div(a, b):
+    """a / b as C++ doubles do it (the reference divides by dt = 0 when two passes share a clock value)."""
+    if b != 0.0:
+        return a / b
+    if a == 0.0 or a != a:
+        return math.nan
+    return math.copysign(math.inf, a) * math.copysign(1.0, b)
+
+
+class PriusController:
+    """The whole controller node (controller.cpp): the /mp cursor plus the steering and pedal PIDs, producing
+    prius_msgs/Control.  The roll-outs do not need it (they track the profile ideally); it is here so that the
+    cursor they share with it is checked against the reference's own object (tests/test_controller_ref_pin.py,
+    oracle/_ref/libref_controller.so) and for anyone putting a vehicle model behind the loop.
+
+    Gains are the dynamic_reconfigure defaults (cfg/prius_controller.cfg).  m_speed is uninitialised in the
+    reference (controller.hpp:55); it starts at 0 here and in the harness.  step() returns False where the
+    reference would index past the end of the profile (:148, :47) -- "good luck" (:154-157)."""
+    NO_COMMAND, NEUTRAL, FORWARD, REVERSE = 0, 1, 2, 3
+
+    def __init__(self, t0=0.0, kp_s=7.5, ki_s=0.05, kd_s=0.15, kp_p=0.25, ki_p=0.075, kd_p=0.055):
+        self.kp_s, self.ki_s, self.kd_s, self.kp_p, self.ki_p, self.kd_p = kp_s, ki_s, kd_s, kp_p, ki_p, kd_p
+        self.cursor = ProfileFollower()
+        self.cursor.start = t0
+        self.prev_t_s = self.prev_t_p = t0
+        self.prev_err_s = self.int_s = self.prev_err_p = self.int_p = 0.0
+        self.m_speed = 0.0
+        self.state_speed = self.state_yaw_rate = 0.0          # m_prius_state.twist.linear.x / angular.z
+        self.max_speed = self.max_accel = 0.0
+        self.throttle = self.brake = self.steer = 0.0
+        self.shift_gears = self.NO_COMMAND
+        self.received = False
+        self.published = 0
+
+    @property
+    def control_it(self):
+        return self.cursor.it
+
+    def on_model_state(self, speed, yaw_rate):                 # :160-174, 185-189
+        self.state_speed, self.state_yaw_rate = speed, yaw_rate
+
+    def on_profile(self, t, yaw_rates, durations_ms, speeds, max_speed, max_accel):      # :176-183
+        self.received = True
+        self.cursor.new_profile(t, yaw_rates, durations_ms, speeds)
+        self.max_speed, self.max_accel = max_speed, max_accel
+        return self.step(t)
+
+    def step(self, t):                                         # calculateAndPublishControls :29-42
+        cmd = self.cursor.command(t)                           # getCurrentCommandIterator :144-158
+        if cmd is None:
+            return False
+        yaw_rate_cmd, speed_cmd = cmd
+        # calculateSteering :44-63
+        dt = t - self.prev_t_s
+        err = yaw_rate_cmd - self.state_yaw_rate
+        self.int_s += err * dt
+        der = _ieee_div(err - self.prev_err_s, dt)
+        steer = self.kp_s * err + self.ki_s * self.int_s - self.kd_s * der
+        if steer > 1:
+            steer = 1.0
+        if steer < -1:
+            steer = -1.0
+        self.steer, self.prev_t_s, self.prev_err_s = steer, t, err
+        # calculateGear :65-76 (m_speed still holds the previous pass's profile speed)
+        if self.m_speed > 0:
+            self.shift_gears = self.FORWARD
+        if self.m_speed < 0:
+            self.shift_gears = self.REVERSE
+        # calculatePedals :78-132
+        dt = t - self.prev_t_p
+        self.m_speed = speed_cmd
+        speed = self.state_speed
+        if speed > self.max_speed:
+            speed = self.max_speed
+        if self.m_speed < speed:                               # (the `>` branch is overwritten by the else, :90-103)
+            set_point = speed - self.max_accel * dt
+        else:
+            set_point = self.m_speed
+        err = set_point - speed
+        self.int_p += err * dt
+        der = _ieee_div(err - self.prev_err_p, dt)
+        u = self.kp_p * err + self.ki_p * self.int_p - self.kd_p * der
+        if u > 1:
+            u = 1.0
+        if u < -1:
+            u = -1.0
+        if u >= 0:
+            self.throttle, self.brake = u, 0.0
+        if u < 0:
+            self.brake, self.throttle = -u, 0.0
+        self.prev_t_p, self.prev_err_p = t, err
+        self.published += 1                                    # publishControls :134-137
+        return True
 
 
 class RouteRollout:

@@ -311,3 +311,66 @@ def global_costmap_build(params, xy, offsets, tmp_dir):
     secs = L.refg_build(C.byref(params), path.encode(), _p(out, C.c_int8), C.c_int64(n), C.byref(n_out))
     assert secs >= 0 and n_out.value == n, (secs, n_out.value, n)
     return out, secs
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's controller (prius_controller/src/controller.cpp), row N4
+# ----------------------------------------------------------------------------------------------
+_controller_lib = None
+
+
+def controller_available():
+    build()
+    return os.path.exists(os.path.join(_DIR, "libref_controller.so"))
+
+
+def _controller():
+    global _controller_lib
+    if _controller_lib is None:
+        L = C.CDLL(os.path.join(_DIR, "libref_controller.so"))
+        L.refk_create.restype = C.c_void_p
+        L.refk_create.argtypes = [C.c_double]
+        L.refk_destroy.argtypes = [C.c_void_p]
+        L.refk_set_time.argtypes = [C.c_double]
+        L.refk_model_state.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.refk_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.refk_step.argtypes = [C.c_void_p]
+        L.refk_state.argtypes = [C.c_void_p, C.c_void_p]
+        _controller_lib = L
+    return _controller_lib
+
+
+class RefController:
+    """The reference's PriusController object behind a manual clock (oracle/ref_controller_harness.cpp)."""
+
+    def __init__(self, t0=0.0):
+        self.h = None
+        self.L = _controller()
+        self.h = self.L.refk_create(t0)
+
+    def close(self):
+        if self.h:
+            self.L.refk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def model_state(self, speed, yaw_rate):
+        self.L.refk_model_state(self.h, speed, yaw_rate)
+
+    def profile(self, t, yaw_rates, durations, speeds, max_speed, max_accel):
+        a, b, c = (np.ascontiguousarray(v, dtype=np.float64) for v in (yaw_rates, durations, speeds))
+        self.L.refk_set_time(t)
+        self.L.refk_profile(self.h, len(a), a.ctypes.data, b.ctypes.data, c.ctypes.data, max_speed, max_accel)
+
+    def step(self, t):
+        """One pass of the 100 Hz loop at clock t; False when the reference would run off the profile."""
+        self.L.refk_set_time(t)
+        return self.L.refk_step(self.h) == 0
+
+    def state(self):
+        """(m_control_it, throttle, brake, steer, shift_gears, messages published)"""
+        out = np.zeros(6)
+        self.L.refk_state(self.h, out.ctypes.data)
+        return tuple(out)

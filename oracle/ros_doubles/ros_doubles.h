@@ -31,6 +31,9 @@ struct State {
   int64_t ticks = 0;
   double ticks_per_sec = 1e18;      // "never times out" until the harness says otherwise
   std::function<bool()> force_timeout;  // optional: when it returns true, now() jumps far ahead
+  // manual clock (controller harness): now() returns `manual_sec` and does not tick
+  bool manual_clock = false;
+  double manual_sec = 0;
   bool quiet = true;
   std::function<void()> spin_script;    // what ros::spin() runs (the harness delivers messages from it)
 };
@@ -84,18 +87,26 @@ struct Duration {
 struct Time {
   int64_t ticks = 0;
   bool forced = false;
+  bool manual = false;
+  double sec = 0;                   // manual clock only
   Time() {}
   explicit Time(double) {}
   static Time now() {
     ros_doubles::State& s = ros_doubles::state();
     Time t;
+    if (s.manual_clock) {
+      t.manual = true;
+      t.sec = s.manual_sec;
+      return t;
+    }
     t.ticks = s.ticks++;
     t.forced = s.force_timeout && s.force_timeout();
     return t;
   }
-  double toSec() const { return static_cast<double>(ticks) / ros_doubles::state().ticks_per_sec; }
+  double toSec() const { return manual ? sec : static_cast<double>(ticks) / ros_doubles::state().ticks_per_sec; }
 };
 inline Duration operator-(const Time& a, const Time& b) {
+  if (a.manual || b.manual) return Duration(a.sec - b.sec);
   if (a.forced) return Duration(1e9);
   return Duration(static_cast<double>(a.ticks - b.ticks) / ros_doubles::state().ticks_per_sec);
 }
@@ -202,11 +213,17 @@ struct ModelStates {
   std::vector<std::string> name; std::vector<geometry_msgs::Pose> pose; std::vector<geometry_msgs::Twist> twist;
   typedef std::shared_ptr<const ModelStates> ConstPtr;
 };
+struct ModelState { std::string model_name; geometry_msgs::Pose pose; geometry_msgs::Twist twist; std::string reference_frame; };
 }
 namespace prius_msgs {
 struct LocalNav {   // prius_msgs/msg/LocalNav.msg
   std_msgs::Header header; double x = 0, y = 0, speed = 0, max_speed = 0, max_accel = 0;
   typedef std::shared_ptr<const LocalNav> ConstPtr;
+};
+struct Control {   // prius_msgs/msg/Control.msg
+  enum { NO_COMMAND = 0, NEUTRAL = 1, FORWARD = 2, REVERSE = 3 };
+  std_msgs::Header header; double throttle = 0, brake = 0, steer = 0; uint8_t shift_gears = 0;
+  typedef std::shared_ptr<const Control> ConstPtr;
 };
 struct MotionPlanning {   // prius_msgs/msg/MotionPlanning.msg
   std_msgs::Header header; std::vector<double> yaw_rates, durations, speeds; double max_speed = 0, max_accel = 0;
@@ -227,3 +244,30 @@ struct PointCloud {
 };
 struct Range { std_msgs::Header header; float range = 0; typedef std::shared_ptr<const Range> ConstPtr; };
 }
+
+// ---- dynamic_reconfigure + the generated config of prius_controller (cfg/prius_controller.cfg: name, default)
+namespace prius_controller {
+struct PriusControllerConfig { double kp_s = 7.5, ki_s = 0.05, kd_s = 0.15, kp_p = 0.25, ki_p = 0.075, kd_p = 0.055; };
+}
+namespace dynamic_reconfigure {
+template <class Config>
+class Server {
+ public:
+  typedef boost::function<void(Config&, uint32_t)> CallbackType;
+  // like the real server, setCallback calls back at once with the current (default) configuration
+  void setCallback(const CallbackType& cb) { cb_ = cb; if (cb_) cb_(config, ~uint32_t(0)); }
+  void update(const Config& c) { config = c; if (cb_) cb_(config, 0); }
+  Config config;
+ private:
+  CallbackType cb_;
+};
+}
+// boost::bind(&Class::method, obj, _1, _2) -- the one shape the controller uses
+namespace boost {
+namespace doubles_placeholders { struct P1 {}; struct P2 {}; }
+template <class C, class A, class B>
+inline std::function<void(A, B)> bind(void (C::*m)(A, B), C* obj, doubles_placeholders::P1, doubles_placeholders::P2) {
+  return [obj, m](A a, B b) { (obj->*m)(a, b); };
+}
+}
+namespace { const boost::doubles_placeholders::P1 _1{}; const boost::doubles_placeholders::P2 _2{}; }
