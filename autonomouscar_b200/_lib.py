@@ -26,7 +26,7 @@ EXPORTS = [
 # every symbol include/prius_costmap.h declares (row N2)
 COSTMAP_EXPORTS = [
     "pc_default_params", "pc_create", "pc_destroy", "pc_set_global_grid", "pc_build", "pc_grid_dev", "pc_stream",
-    "pc_launch_count", "pc_last_build_ms", "pc_adopt_global_grid", "pc_front_regions", "pc_front_regions_dev",
+    "pc_launch_count", "pc_last_build_ms", "pc_adopt_global_grid", "pc_front_regions", "pc_front_regions_dev", "pc_build_batch", "pc_batch_grids_dev",
     "pg_default_params", "pg_build", "pg_last_build", "pg_free",
 ]
 
@@ -97,6 +97,8 @@ def load():
     L.pc_adopt_global_grid.argtypes = [vp, vp, i64]
     L.pc_front_regions.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.pc_front_regions_dev.argtypes = [vp, vp, i32, i64, C.POINTER(C.c_uint32)]
+    L.pc_build_batch.argtypes = [vp, i32, vp, vp, vp]
+    L.pc_batch_grids_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
     L.pg_default_params.argtypes = [C.POINTER(pg_params)]
     L.pg_build.argtypes = [C.POINTER(pg_params), C.c_int, vp, vp, i32, vp, C.POINTER(vp)]
     L.pg_last_build.argtypes = [C.POINTER(f32), C.POINTER(i32)]

@@ -61,6 +61,25 @@ class LocalCostmap:
                                      out.ctypes.data_as(C.c_void_p) if want_host else None))
         return out
 
+    def build_batch(self, scenes, want_host=True, want_masks=True):
+        """n independent scenes (one per simulated car) in ONE set of kernel launches.  Returns
+        (grids, masks): grids = (n, n_cells) int8 in message order or None, masks = the n region masks of
+        front_regions() (uint32) or None.  Identical to n build() calls."""
+        from .costmap_capi import pc_inputs
+        n = len(scenes)
+        arr = (pc_inputs * n)(*[sc.inputs for sc in scenes])       # (copies the structs; they point into the scenes' arrays)
+        grids = np.empty((n, self.n_cells), dtype=np.int8) if want_host else None
+        masks = np.zeros(n, dtype=np.uint32) if want_masks else None
+        self._check(self._L.pc_build_batch(self._h, n, arr, grids.ctypes.data_as(C.c_void_p) if want_host else None,
+                                           masks.ctypes.data_as(C.c_void_p) if want_masks else None))
+        return grids, masks
+
+    def batch_grids_dev(self):
+        """(device pointer, n_scenes) of the most recent batch's grids, scene-major."""
+        p, n = C.c_void_p(), C.c_int32()
+        self._check(self._L.pc_batch_grids_dev(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     def grid_dev(self):
         """(device pointer, width, height) of the most recent grid."""
         p, w, h = C.c_void_p(), C.c_int32(), C.c_int32()

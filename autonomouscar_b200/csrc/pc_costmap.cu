@@ -26,6 +26,8 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/prius_costmap.h"
 #include "pp_common.cuh"
@@ -54,6 +56,20 @@ struct PcGeom {              // derived once per handle from pc_params, host sid
   int nx, ny;                // int(H * 2), int(W * 2), LC:235-236
 };
 
+// Every kernel takes a scene index from blockIdx.y (pc_build: one scene; pc_build_batch: n of them in
+// the same launches).  Scene s reads header s, shares the payload block, and owns work / out slice s.
+struct PcScenes {
+  const unsigned char* hdrs;   // n headers, kHdrBytes apart
+  const float* payload;        // all scenes' floats; the headers hold offsets into it
+  int* work;                   // n x (occ | infl), 2 * len int32 each
+  int8_t* out;                 // n x len int8 (message order)
+  size_t hdr_stride;           // bytes
+};
+__device__ __forceinline__ const PcDevHeader& pc_hdr(const PcScenes& S) {
+  return *reinterpret_cast<const PcDevHeader*>(S.hdrs + blockIdx.y * S.hdr_stride);
+}
+__device__ __forceinline__ int* pc_occ(const PcScenes& S, int len) { return S.work + static_cast<size_t>(blockIdx.y) * 2 * len; }
+
 __device__ __forceinline__ bool pc_grid_location(const pc_params& P, double x, double y, int* loc) {
   int wp, hp;
   if (!dm::trunc_to_int(dm::add(dm::div(x, P.res), dm::div(P.width_cells, 2.0)), &wp)) return false;   // LC:261
@@ -64,9 +80,11 @@ __device__ __forceinline__ bool pc_grid_location(const pc_params& P, double x, d
 
 // ---- mapPlanarScan + mapCenterScan: one warp per ray / point --------------------------------
 __global__ void __launch_bounds__(256)
-pc_mark_kernel(const PcDevHeader* __restrict__ hdr, const float* __restrict__ payload, int* __restrict__ occ, int len) {
-  const PcDevHeader& H = *hdr;
+pc_mark_kernel(PcScenes S, int len) {
+  const PcDevHeader& H = pc_hdr(S);
   const pc_params& P = H.P;
+  const float* __restrict__ payload = S.payload;
+  int* __restrict__ occ = pc_occ(S, len);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int total = H.n_ray[0] + H.n_ray[1] + H.n_cloud;
@@ -122,8 +140,10 @@ pc_mark_kernel(const PcDevHeader* __restrict__ hdr, const float* __restrict__ pa
 
 // ---- inflateGrid (LC:288-325): one thread per source cell ------------------------------------
 __global__ void __launch_bounds__(256)
-pc_inflate_kernel(const PcDevHeader* __restrict__ hdr, const int* __restrict__ occ, int* __restrict__ infl, PcGeom G) {
-  const pc_params& P = hdr->P;
+pc_inflate_kernel(PcScenes S, PcGeom G) {
+  const pc_params& P = pc_hdr(S).P;
+  const int* __restrict__ occ = pc_occ(S, G.len);
+  int* __restrict__ infl = pc_occ(S, G.len) + G.len;
   const double max_dist = sqrt(dm::add(dm::mul(dm::mul(P.height_cells, P.res), dm::mul(P.height_cells, P.res)),
                                        dm::mul(dm::mul(P.width_cells, P.res), dm::mul(P.width_cells, P.res))));  // LC:298
   for (int count = blockIdx.x * blockDim.x + threadIdx.x; count < G.len; count += gridDim.x * blockDim.x) {
@@ -152,7 +172,9 @@ pc_inflate_kernel(const PcDevHeader* __restrict__ hdr, const int* __restrict__ o
 }
 
 // ---- LC:332-346: inflated 0 / 100 replace the cell --------------------------------------------
-__global__ void pc_merge_kernel(int* __restrict__ occ, const int* __restrict__ infl, int len) {
+__global__ void pc_merge_kernel(PcScenes S, int len) {
+  int* __restrict__ occ = pc_occ(S, len);
+  const int* __restrict__ infl = occ + len;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
     const int v = infl[k];
     if (v == 100 || v == 0) occ[k] = v;
@@ -167,8 +189,9 @@ __device__ __forceinline__ void pc_apply(const double* m, double x, double y, do
 
 // ---- mapRoadVectors (LC:208-257): one thread per sample of the 2H x 2W lattice -----------------
 __global__ void __launch_bounds__(256)
-pc_roads_kernel(const PcDevHeader* __restrict__ hdr, const int8_t* __restrict__ global_grid, int* __restrict__ occ, PcGeom G) {
-  const PcDevHeader& H = *hdr;
+pc_roads_kernel(PcScenes S, const int8_t* __restrict__ global_grid, PcGeom G) {
+  const PcDevHeader& H = pc_hdr(S);
+  int* __restrict__ occ = pc_occ(S, G.len);
   const pc_params& P = H.P;
   if (H.global_len < 1) return;                                                            // LC:210-213
   const double total_x = dm::mul(P.height_cells, P.res), total_y = dm::mul(P.width_cells, P.res);
@@ -195,7 +218,9 @@ pc_roads_kernel(const PcDevHeader* __restrict__ hdr, const int8_t* __restrict__ 
   }
 }
 
-__global__ void pc_pack_kernel(const int* __restrict__ occ, int8_t* __restrict__ out, int len) {
+__global__ void pc_pack_kernel(PcScenes S, int len) {
+  const int* __restrict__ occ = pc_occ(S, len);
+  int8_t* __restrict__ out = S.out + static_cast<size_t>(blockIdx.y) * len;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x)
     out[k] = static_cast<int8_t>(occ[k]);
 }
@@ -206,7 +231,9 @@ __global__ void pc_pack_kernel(const int* __restrict__ occ, int8_t* __restrict__
 // k (F1..F4 at y 180.., 210.., 240.., 270..): F_k = ANY cell == 100 in x 140..159; R_k / L_k keep the
 // verdict of the LAST cell scanned in x 120..139 / 160..179 (their else-branches reset the flag).
 // Bit layout of the mask: PC_REGION_* in prius_costmap.h.
-__global__ void pc_front_regions_kernel(const int8_t* __restrict__ grid, int W, unsigned* __restrict__ out) {
+// One CTA per grid (grids `stride` cells apart).
+__global__ void pc_front_regions_kernel(const int8_t* __restrict__ grids, size_t stride, int W, unsigned* __restrict__ out) {
+  const int8_t* __restrict__ grid = grids + blockIdx.x * stride;
   __shared__ unsigned s_mask;
   if (threadIdx.x == 0) s_mask = 0;
   __syncthreads();
@@ -227,7 +254,11 @@ __global__ void pc_front_regions_kernel(const int8_t* __restrict__ grid, int W, 
   m = __reduce_or_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_mask, m);
   __syncthreads();
-  if (threadIdx.x == 0) *out = s_mask;
+  if (threadIdx.x == 0) {
+    unsigned r = s_mask;
+    if ((r & 0xFu) && !(r & PC_REGION_ANY_L_HIT)) r |= PC_REGION_OBSTACLE;   // self.obstacle once the scan is over
+    out[blockIdx.x] = r;
+  }
 }
 
 }  // namespace pp
@@ -253,6 +284,14 @@ struct pc_handle {
   cudaGraphExec_t graph = nullptr;
   uint64_t launches = 0;
   float last_ms = 0;
+  // pc_build_batch: n scenes at once (buffers grow on demand)
+  int batch_cap = 0, batch_n = 0;
+  int* d_work_b = nullptr;          // batch_cap x 2 * len int32
+  int8_t* d_out_b = nullptr;        // batch_cap x len int8
+  unsigned* d_regions_b = nullptr;  // batch_cap masks
+  unsigned char* h_in_b = nullptr;  // pinned: n headers | payloads
+  unsigned char* d_in_b = nullptr;
+  size_t in_cap_b = 0;
 };
 
 namespace {
@@ -272,32 +311,75 @@ int ensure_input(pc_handle* h, size_t bytes) {
   return PP_OK;
 }
 
-// the six launches of one pass, on `s` (captured into a graph by the caller)
-void launch_pass(pc_handle* h, cudaStream_t s) {
+// the six launches of one pass over n scenes, on `s` (the single-scene pass is captured into a graph)
+void launch_pass(pc_handle* h, cudaStream_t s, const PcScenes& S, int n) {
   const int len = h->G.len;
-  int* occ = h->d_work;
-  int* infl = h->d_work + len;
-  const PcDevHeader* hdr = reinterpret_cast<const PcDevHeader*>(h->d_in);
-  const float* payload = reinterpret_cast<const float*>(h->d_in + kHdrBytes);
   const int T = 256;
-  const int cell_blocks = std::min((len + T - 1) / T, h->sm_count * 8);
-  cudaMemsetAsync(h->d_work, 0xFF, sizeof(int) * 2 * static_cast<size_t>(len), s);               // clearMap: -1
-  pc_mark_kernel<<<h->sm_count * 8, T, 0, s>>>(hdr, payload, occ, len);
-  pc_inflate_kernel<<<cell_blocks, T, 0, s>>>(hdr, occ, infl, h->G);
-  pc_merge_kernel<<<cell_blocks, T, 0, s>>>(occ, infl, len);
+  // a lone scene spreads over the whole GPU; a batch gives every scene a slice and lets the scenes fill it
+  const int per_scene = n == 1 ? h->sm_count * 8 : std::max(4, h->sm_count * 16 / n);
+  const unsigned cell_blocks = static_cast<unsigned>(std::min((len + T - 1) / T, per_scene));
+  const unsigned ny = static_cast<unsigned>(n);
+  cudaMemsetAsync(S.work, 0xFF, sizeof(int) * 2 * static_cast<size_t>(len) * n, s);              // clearMap: -1
+  pc_mark_kernel<<<dim3(static_cast<unsigned>(per_scene), ny), T, 0, s>>>(S, len);
+  pc_inflate_kernel<<<dim3(cell_blocks, ny), T, 0, s>>>(S, h->G);
+  pc_merge_kernel<<<dim3(cell_blocks, ny), T, 0, s>>>(S, len);
   if (h->d_global) {
     const long long samples = static_cast<long long>(h->G.nx) * h->G.ny;
-    const int road_blocks = static_cast<int>(std::min<long long>((samples + T - 1) / T, h->sm_count * 16));
-    pc_roads_kernel<<<road_blocks, T, 0, s>>>(hdr, h->d_global, occ, h->G);
+    const unsigned road_blocks = static_cast<unsigned>(std::min<long long>((samples + T - 1) / T, 2 * per_scene));
+    pc_roads_kernel<<<dim3(road_blocks, ny), T, 0, s>>>(S, h->d_global, h->G);
   }
-  pc_pack_kernel<<<cell_blocks, T, 0, s>>>(occ, h->d_out, len);
+  pc_pack_kernel<<<dim3(cell_blocks, ny), T, 0, s>>>(S, len);
+}
+
+PcScenes single_scene(const pc_handle* h) {
+  return PcScenes{h->d_in, reinterpret_cast<const float*>(h->d_in + kHdrBytes), h->d_work, h->d_out, kHdrBytes};
+}
+
+// number of payload floats of one scene (+ argument checks shared by pc_build / pc_build_batch)
+int scene_floats(const pc_inputs* in, const char* who, size_t* out) {
+  const pc_planar_scan* scans[2] = {&in->right, &in->left};
+  size_t n = 0;
+  for (int s = 0; s < 2; ++s) {
+    const int nr = scans[s]->ranges ? scans[s]->n : 0;
+    if (nr < 0 || nr > (1 << 22)) { set_last_error(std::string(who) + ": bad scan size"); return PP_ERR_INVALID; }
+    n += static_cast<size_t>(nr);
+  }
+  const int nc = in->cloud_xyz ? in->n_cloud : 0;
+  if (nc < 0 || nc > (1 << 24)) { set_last_error(std::string(who) + ": bad cloud size"); return PP_ERR_INVALID; }
+  *out = n + 3 * static_cast<size_t>(nc);
+  return PP_OK;
+}
+
+// header + floats of one scene into the pinned block; `off` = this scene's first float in `payload`
+void pack_scene(const pc_handle* h, const pc_inputs* in, PcDevHeader* hd, float* payload, int off) {
+  const pc_planar_scan* scans[2] = {&in->right, &in->left};
+  hd->P = h->P;
+  for (int s = 0; s < 2; ++s) {
+    const int nr = scans[s]->ranges ? scans[s]->n : 0;
+    hd->n_ray[s] = nr;
+    hd->ray_off[s] = off;
+    if (nr) std::memcpy(payload + off, scans[s]->ranges, sizeof(float) * nr);
+    off += nr;
+    hd->angle_min[s] = scans[s]->angle_min; hd->angle_increment[s] = scans[s]->angle_increment;
+    hd->range_max[s] = scans[s]->range_max;
+    hd->roll[s] = scans[s]->roll; hd->tf_x[s] = scans[s]->tf_x; hd->tf_y[s] = scans[s]->tf_y;
+    hd->z_map[s] = scans[s]->z_map; hd->inv_x[s] = scans[s]->inv_x; hd->inv_y[s] = scans[s]->inv_y;
+  }
+  const int nc = in->cloud_xyz ? in->n_cloud : 0;
+  hd->n_cloud = nc;
+  hd->cloud_off = off;
+  if (nc) std::memcpy(payload + off, in->cloud_xyz, sizeof(float) * 3 * static_cast<size_t>(nc));
+  hd->center_z = in->center_z;
+  std::memcpy(hd->map_from_base, in->map_from_base, sizeof(hd->map_from_base));
+  std::memcpy(hd->base_from_map, in->base_from_map, sizeof(hd->base_from_map));
+  hd->global_len = h->d_global ? h->global_len : 0;
 }
 
 int capture(pc_handle* h) {
   if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
   cudaGraph_t g = nullptr;
   PP_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  launch_pass(h, h->stream);
+  launch_pass(h, h->stream, single_scene(h), 1);
   PP_CUDA(cudaStreamEndCapture(h->stream, &g));
   const cudaError_t e = cudaGraphInstantiate(&h->graph, g, 0);
   cudaGraphDestroy(g);
@@ -367,7 +449,8 @@ int pc_destroy(pc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   cudaFree(h->d_work); cudaFree(h->d_out); cudaFree(h->d_global); cudaFree(h->d_in); cudaFree(h->d_regions);
-  cudaFreeHost(h->h_out); cudaFreeHost(h->h_in);
+  cudaFree(h->d_work_b); cudaFree(h->d_out_b); cudaFree(h->d_regions_b); cudaFree(h->d_in_b);
+  cudaFreeHost(h->h_out); cudaFreeHost(h->h_in); cudaFreeHost(h->h_in_b);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -407,40 +490,14 @@ int pc_adopt_global_grid(pc_handle* h, int8_t* grid_dev, int64_t len) {
 
 int pc_build(pc_handle* h, const pc_inputs* in, int8_t* out_host) {
   if (!h || !in) { set_last_error("pc_build: null argument"); return PP_ERR_INVALID; }
-  const pc_planar_scan* scans[2] = {&in->right, &in->left};
-  int n_ray[2];
-  for (int s = 0; s < 2; ++s) {
-    n_ray[s] = scans[s]->ranges ? scans[s]->n : 0;
-    PP_REQUIRE(n_ray[s] >= 0 && n_ray[s] <= (1 << 22), "pc_build: bad scan size");
-  }
-  const int n_cloud = in->cloud_xyz ? in->n_cloud : 0;
-  PP_REQUIRE(n_cloud >= 0 && n_cloud <= (1 << 24), "pc_build: bad cloud size");
-  PP_CUDA(cudaSetDevice(h->device));
-  const size_t n_float = static_cast<size_t>(n_ray[0]) + n_ray[1] + 3 * static_cast<size_t>(n_cloud);
-  const size_t bytes = kHdrBytes + sizeof(float) * n_float;
-  int rc = ensure_input(h, bytes);
+  size_t n_float = 0;
+  int rc = scene_floats(in, "pc_build", &n_float);
   if (rc) return rc;
-  PcDevHeader* hd = reinterpret_cast<PcDevHeader*>(h->h_in);
-  float* payload = reinterpret_cast<float*>(h->h_in + kHdrBytes);
-  hd->P = h->P;
-  int off = 0;
-  for (int s = 0; s < 2; ++s) {
-    hd->n_ray[s] = n_ray[s];
-    hd->ray_off[s] = off;
-    if (n_ray[s]) std::memcpy(payload + off, scans[s]->ranges, sizeof(float) * n_ray[s]);
-    off += n_ray[s];
-    hd->angle_min[s] = scans[s]->angle_min; hd->angle_increment[s] = scans[s]->angle_increment;
-    hd->range_max[s] = scans[s]->range_max;
-    hd->roll[s] = scans[s]->roll; hd->tf_x[s] = scans[s]->tf_x; hd->tf_y[s] = scans[s]->tf_y;
-    hd->z_map[s] = scans[s]->z_map; hd->inv_x[s] = scans[s]->inv_x; hd->inv_y[s] = scans[s]->inv_y;
-  }
-  hd->n_cloud = n_cloud;
-  hd->cloud_off = off;
-  if (n_cloud) std::memcpy(payload + off, in->cloud_xyz, sizeof(float) * 3 * static_cast<size_t>(n_cloud));
-  hd->center_z = in->center_z;
-  std::memcpy(hd->map_from_base, in->map_from_base, sizeof(hd->map_from_base));
-  std::memcpy(hd->base_from_map, in->base_from_map, sizeof(hd->base_from_map));
-  hd->global_len = h->d_global ? h->global_len : 0;
+  PP_CUDA(cudaSetDevice(h->device));
+  const size_t bytes = kHdrBytes + sizeof(float) * n_float;
+  rc = ensure_input(h, bytes);
+  if (rc) return rc;
+  pack_scene(h, in, reinterpret_cast<PcDevHeader*>(h->h_in), reinterpret_cast<float*>(h->h_in + kHdrBytes), 0);
 
   if (!h->graph) { rc = capture(h); if (rc) return rc; }
   PP_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -452,6 +509,85 @@ int pc_build(pc_handle* h, const pc_inputs* in, int8_t* out_host) {
   PP_CUDA(cudaStreamSynchronize(h->stream));
   if (out_host) std::memcpy(out_host, h->h_out, static_cast<size_t>(h->G.len));
   cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return PP_OK;
+}
+
+int pc_build_batch(pc_handle* h, int32_t n, const pc_inputs* in, int8_t* out_host, uint32_t* out_masks) {
+  if (!h || (n > 0 && !in)) { set_last_error("pc_build_batch: null argument"); return PP_ERR_INVALID; }
+  PP_REQUIRE(n >= 0 && n <= 65535, "pc_build_batch: 0 <= n <= 65535 scenes");
+  // (the region scan reads info.width^2 cells per grid; a grid with height < width has no defined answer)
+  PP_REQUIRE(!out_masks || h->P.height_cells >= h->P.width_cells, "pc_build_batch: masks need height >= width (see pc_front_regions)");
+  h->batch_n = 0;
+  if (n == 0) return PP_OK;
+  const size_t len = static_cast<size_t>(h->G.len);
+  std::vector<size_t> off(static_cast<size_t>(n) + 1, 0);
+  for (int k = 0; k < n; ++k) {
+    size_t nf = 0;
+    const int rc = scene_floats(&in[k], "pc_build_batch", &nf);
+    if (rc) return rc;
+    off[k + 1] = off[k] + nf;
+  }
+  PP_REQUIRE(off[n] < (size_t(1) << 31), "pc_build_batch: more than 2^31 input floats");
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  if (n > h->batch_cap) {
+    cudaFree(h->d_work_b); cudaFree(h->d_out_b); cudaFree(h->d_regions_b);
+    h->d_work_b = nullptr; h->d_out_b = nullptr; h->d_regions_b = nullptr; h->batch_cap = 0;
+    PP_CUDA(cudaMalloc(&h->d_work_b, sizeof(int) * 2 * len * n));
+    PP_CUDA(cudaMalloc(&h->d_out_b, len * n));
+    PP_CUDA(cudaMalloc(&h->d_regions_b, sizeof(unsigned) * n));
+    h->batch_cap = n;
+  }
+  const size_t hdr_bytes = kHdrBytes * static_cast<size_t>(n);
+  const size_t bytes = hdr_bytes + sizeof(float) * off[n];
+  if (bytes > h->in_cap_b) {
+    size_t cap = 1 << 20;
+    while (cap < bytes) cap <<= 1;
+    cudaFreeHost(h->h_in_b); cudaFree(h->d_in_b);
+    h->h_in_b = nullptr; h->d_in_b = nullptr; h->in_cap_b = 0;
+    PP_CUDA(cudaMallocHost(&h->h_in_b, cap));
+    PP_CUDA(cudaMalloc(&h->d_in_b, cap));
+    h->in_cap_b = cap;
+  }
+  // pack: n headers, then every scene's floats; scenes are independent, so split them over a few threads
+  float* payload = reinterpret_cast<float*>(h->h_in_b + hdr_bytes);
+  auto pack_range = [&](int k0, int k1) {
+    for (int k = k0; k < k1; ++k)
+      pack_scene(h, &in[k], reinterpret_cast<PcDevHeader*>(h->h_in_b + kHdrBytes * static_cast<size_t>(k)), payload,
+                 static_cast<int>(off[k]));
+  };
+  const int n_thr = n >= 64 ? std::min<int>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (n_thr == 1) {
+    pack_range(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t) pool.emplace_back(pack_range, static_cast<int>(static_cast<long long>(n) * t / n_thr),
+                                                      static_cast<int>(static_cast<long long>(n) * (t + 1) / n_thr));
+    for (auto& t : pool) t.join();
+  }
+  const PcScenes S{h->d_in_b, reinterpret_cast<const float*>(h->d_in_b + hdr_bytes), h->d_work_b, h->d_out_b, kHdrBytes};
+  PP_CUDA(cudaEventRecord(h->ev0, h->stream));
+  PP_CUDA(cudaMemcpyAsync(h->d_in_b, h->h_in_b, bytes, cudaMemcpyHostToDevice, h->stream));
+  launch_pass(h, h->stream, S, n);
+  pc_front_regions_kernel<<<static_cast<unsigned>(n), 256, 0, h->stream>>>(h->d_out_b, len, static_cast<int>(h->P.width_cells),
+                                                                           h->d_regions_b);
+  h->launches += h->d_global ? 6 : 5;
+  PP_CUDA(cudaGetLastError());
+  PP_CUDA(cudaEventRecord(h->ev1, h->stream));
+  if (out_host) PP_CUDA(cudaMemcpyAsync(out_host, h->d_out_b, len * n, cudaMemcpyDeviceToHost, h->stream));
+  if (out_masks) {
+    PP_CUDA(cudaMemcpyAsync(out_masks, h->d_regions_b, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->batch_n = n;
+  return PP_OK;
+}
+
+int pc_batch_grids_dev(pc_handle* h, const int8_t** out_dev, int32_t* n_scenes) {
+  if (!h || !out_dev) { set_last_error("pc_batch_grids_dev: null argument"); return PP_ERR_INVALID; }
+  *out_dev = h->batch_n > 0 ? h->d_out_b : nullptr;
+  if (n_scenes) *n_scenes = h->batch_n;
   return PP_OK;
 }
 
@@ -469,13 +605,12 @@ int pc_front_regions_dev(pc_handle* h, const int8_t* grid_dev, int32_t info_widt
   PP_REQUIRE(info_width >= 0 && info_width <= 16384 && static_cast<int64_t>(info_width) * info_width <= len,
              "pc_front_regions: fewer than width * width cells (the reference runs off msg.data)");
   PP_CUDA(cudaSetDevice(h->device));
-  pc_front_regions_kernel<<<1, 256, 0, h->stream>>>(grid_dev, info_width, h->d_regions);
+  pc_front_regions_kernel<<<1, 256, 0, h->stream>>>(grid_dev, 0, info_width, h->d_regions);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   unsigned m = 0;
   PP_CUDA(cudaMemcpyAsync(&m, h->d_regions, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
   PP_CUDA(cudaStreamSynchronize(h->stream));
-  if ((m & 0xFu) && !(m & PC_REGION_ANY_L_HIT)) m |= PC_REGION_OBSTACLE;   // self.obstacle once the scan is over
   *out_mask = m;
   return PP_OK;
 }

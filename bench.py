@@ -531,6 +531,14 @@ def bench_costmap(args):
         mask = cm.front_regions()
     out["front_regions_call_us"] = (time.perf_counter() - t0) / 300 * 1e6
     out["front_regions_mask"] = int(mask)
+    # scenario sweep: 256 scenes (one per simulated car) through one set of launches, masks back only
+    batch = [scenes[k % 4] for k in range(256)]
+    cm.build_batch(batch, want_host=False)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        cm.build_batch(batch, want_host=False)
+    out["batch256_grids_per_s_masks_only"] = 5 * 256 / (time.perf_counter() - t0)
+    out["batch256_device_ms"] = cm.last_build_ms()
     out["h2d_bytes_per_grid"] = int(4 * (len(scenes[0].right) + len(scenes[0].left) + scenes[0].cloud.size))
     out["d2h_bytes_per_grid"] = cm.n_cells
     if not args.skip_cpu:

@@ -78,6 +78,13 @@ int pc_set_global_grid(pc_handle* h, const int8_t* data_host, int64_t len);
    mapPlanarScan x 2, mapCenterScan, inflateGrid, mapRoadVectors.  out_host (width*height int8, the
    nav_msgs/OccupancyGrid.data of /local_costmap) may be NULL when only the device grid is wanted. */
 int pc_build(pc_handle* h, const pc_inputs* in, int8_t* out_host);
+/* n independent scenes (scenario sweeps: one per simulated car) through the same kernels in ONE set of
+   launches -- a scene index rides on blockIdx.y.  Results are identical to n pc_build calls.  out_host
+   (n * width*height int8, scene-major) and out_masks (n region masks as pc_front_regions returns them)
+   may each be NULL; the grids stay on the device (pc_batch_grids_dev) until the next batch.  The global
+   grid, if set, is shared by all scenes.  Does not disturb the pc_build grid. */
+int pc_build_batch(pc_handle* h, int32_t n, const pc_inputs* in, int8_t* out_host, uint32_t* out_masks);
+int pc_batch_grids_dev(pc_handle* h, const int8_t** out_dev, int32_t* n_scenes);
 /* device pointer of the most recent grid (message order), valid until the next pc_build */
 int pc_grid_dev(pc_handle* h, const int8_t** out_dev, int32_t* width, int32_t* height);
 /* cudaStream_t of the handle; kernels launched since creation; device ms of the last pc_build */

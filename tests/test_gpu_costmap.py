@@ -304,3 +304,47 @@ def test_costmap_parameter_variants_bit_exact(oracle, cuda_device):
         np.testing.assert_array_equal(got, want)
         assert (got == 100).sum() > 200
         cm.close()
+
+
+def test_costmap_batch_equals_single_builds(oracle, cuda_device):
+    """pc_build_batch: n scenes (different sensor data, car poses, sizes of scan / cloud, with the shared global
+    map) through one set of launches == n pc_build calls, byte for byte, region masks included; the first
+    grids are also checked against the oracle directly."""
+    from autonomouscar_b200 import LocalCostmap, worlds
+    from oracle import navigator_ref
+    p = mcg.params()
+    rng = np.random.default_rng(12)
+    for with_global, n in ((True, 37), (False, 5), (True, 1), (False, 130)):
+        cm = LocalCostmap(p, device=0)
+        g = mcg.global_grid(p, (10.0, -20.0, 0.3), 40) if with_global else None
+        if g is not None:
+            cm.set_global_grid(g)
+        scenes = []
+        for k in range(n):
+            kind = k % 3
+            if kind == 0:
+                sc = worlds.costmap_scene(500 + k, n_planar=int(rng.choice([640, 333])), per_ring=int(rng.choice([512, 100])))
+            elif kind == 1:
+                sc = worlds.corridor_scene(600 + k, half_width=float(rng.uniform(3, 10)), gap_at=(8.0 + k % 17, 11.0 + k % 17))
+            else:
+                sc = worlds.costmap_scene(700 + k, max_reach=float(rng.uniform(12, 29)))
+            _fill_tf(sc, (float(rng.uniform(-60, 60)), float(rng.uniform(-60, 60)), float(rng.uniform(-3.1, 3.1))))
+            scenes.append(sc)
+        grids, masks = cm.build_batch(scenes)
+        assert grids.shape == (n, cm.n_cells) and masks.shape == (n,)
+        ptr, nb = cm.batch_grids_dev()
+        assert nb == n and ptr
+        for k, sc in enumerate(scenes):
+            single = cm.build(sc)
+            np.testing.assert_array_equal(grids[k], single, err_msg=f"scene {k}")
+            assert int(masks[k]) == cm.front_regions() == navigator_ref.region_mask(single, 300), k
+            if k < 3:
+                want, _ = oracle.costmap_build(p, sc.inputs, g, math_mode=oracle.MATH_DET)
+                np.testing.assert_array_equal(grids[k], want)
+        assert len({int(m) & 0xF for m in masks}) >= (2 if n > 20 else 1)
+        # a second, smaller batch on the same handle; device-only outputs
+        g2, m2 = cm.build_batch(scenes[: max(1, n // 2)], want_host=False, want_masks=True)
+        assert g2 is None
+        np.testing.assert_array_equal(m2, masks[: max(1, n // 2)])
+        assert cm.build_batch([], want_host=False, want_masks=False) == (None, None)
+        cm.close()
