@@ -125,3 +125,55 @@ def test_obstacle_branch_in_the_device_chain(oracle, cuda_device):
     assert len(set(flags)) >= 3
     cm.close()
     pl.close()
+
+
+def test_sweep_with_per_car_costmaps(oracle, cuda_device):
+    """A scenario sweep with sensors in the loop: every tick, ALL cars' costmaps and region masks come from one
+    pc_build_batch call, the navigators turn them into goals (route / slow down / swerve / stop) and one
+    pp_plan_batch call plans for all cars.  The same loop on the CPU (oracle costmap -> numpy scan -> oracle
+    planner) drives every car to bit-identical states."""
+    from autonomouscar_b200 import PP_COLLISION_AS_SHIPPED, PP_PLAN_FOUND, LocalCostmap, Planner, default_params, rollout, worlds
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    from oracle import navigator_ref
+    cp = default_costmap_params()
+    cm = LocalCostmap(cp, device=0)
+    p = default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000)
+    pl = Planner(p, device=0)
+    route = rollout.densify_route([[-50.0, 0.0], [200.0, 0.0]])
+    n = 12
+    starts = [(2.5 * k, 0.02 * (k % 3), 0.0, 1.0) for k in range(n)]
+    box_x = [40.0 if k % 2 == 0 else None for k in range(n)]       # even cars meet a box, odd cars an open road
+    gpu, cpu = rollout.RouteRollout(starts, route=route), rollout.RouteRollout(starts, route=route)
+
+    def oracle_batch(queries):
+        out = []
+        for q in queries:
+            r = oracle.plan(p, None, q, math_mode=oracle.MATH_DET, want_nodes=False, cap_nodes=8)
+            out.append((r.status == PP_PLAN_FOUND, r.yaw_rates.copy(), r.durations.copy(), r.speeds.copy()))
+        return out
+
+    speeds_seen = set()
+    for tick in range(8):
+        np.testing.assert_array_equal(gpu.trace[-1] if gpu.trace else np.array(starts), cpu.trace[-1] if cpu.trace else np.array(starts))
+        scenes = []
+        for k in range(n):
+            d = None if box_x[k] is None else box_x[k] - float(gpu.x[k])
+            sc = worlds.corridor_scene(1000 + 17 * tick + k, half_width=9.0, gap_at=(d, d + 3.0) if d is not None and 3 < d < 29 else None)
+            worlds.fill_costmap_tf(sc, (float(gpu.x[k]), float(gpu.y[k]), float(gpu.yaw[k])))
+            scenes.append(sc)
+        _, masks = cm.build_batch(scenes, want_host=False)
+        cpu_masks = [navigator_ref.region_mask(oracle.costmap_build(cp, sc.inputs, None, math_mode=oracle.MATH_DET)[0], 300)
+                     for sc in scenes]
+        assert [int(m) for m in masks] == cpu_masks
+        qs = gpu.queries(masks)
+        speeds_seen |= {q.goal_speed for q in qs}
+        gpu.tick(rollout.plan_batch_cuda(pl), masks)
+        cpu.tick(oracle_batch, cpu_masks)
+        # the cars crawl (1 m/s): push the even ones forward so that the box passes through every region
+        for ro in (gpu, cpu):
+            ro.x[::2] += 4.0
+    np.testing.assert_array_equal(np.array(gpu.trace), np.array(cpu.trace))
+    assert gpu.found > 0.5 * gpu.plans
+    assert {1.5, 1.0, 0.0} <= speeds_seen, speeds_seen        # route, swerve and stop goals all occurred
+    cm.close()
+    pl.close()
