@@ -46,6 +46,48 @@ def yaw_to_quaternion(yaw):
     return math.cos(yaw / 2), 0.0, 0.0, math.sin(yaw / 2)     # w, x, y, z
 
 
+def _script(route_xy, passes, Path, Odometry, OccupancyGrid):
+    script = [[("/path", Path(route_xy))]]
+    for p in passes:
+        ev = []
+        if p.get("pose") is not None:
+            ev.append(("base_pose_ground_truth", Odometry(*p["pose"])))
+        if p.get("grid") is not None:
+            w, data = p["grid"]
+            g = ("local_costmap", OccupancyGrid(width=w, height=w, resolution=0.25, data=data))
+            ev.insert(0, g) if p.get("grid_first") else ev.append(g)
+        script.append(ev)
+    return script
+
+
+def _drive(rospy, passes, start, snapshot_of):
+    """Common part of run() / run_shim(): `start()` constructs the node and blocks in its loop until the
+    script is exhausted; `snapshot_of(node)` reads its state after every pass."""
+    node_box, states = [], []
+    real_sub = rospy.Subscriber.__init__
+
+    def sub_init(self, topic, typ, cb, queue_size=None):       # the callbacks are bound methods of the node
+        if not node_box:
+            node_box.append(cb.__self__)
+        real_sub(self, topic, typ, cb, queue_size)
+
+    real_rate_sleep = rospy.Rate.sleep
+
+    def rate_sleep(self):
+        if rospy.state.passes >= 2:      # pass 0 saw nothing, pass 1 saw only /path
+            states.append(snapshot_of(node_box[0]))
+        real_rate_sleep(self)
+
+    rospy.Subscriber.__init__ = sub_init
+    rospy.Rate.sleep = rate_sleep
+    start()                              # returns when the script is exhausted
+    published = [None] * len(passes)
+    for k, _topic, fields in rospy.state.published:
+        # loop pass k processed script entry k-1; script entry 0 is /path, entry j+1 is passes[j]
+        published[k - 2] = fields
+    return published, states
+
+
 def run(route_xy, passes):
     """Drive the reference node.
 
@@ -65,50 +107,31 @@ def run(route_xy, passes):
         spec = importlib.util.spec_from_file_location("reference_local_navigator", REFERENCE_FILE)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)          # __name__ != "__main__": defines the class only
+        rospy.state.script = _script(route_xy, passes, Path, Odometry, OccupancyGrid)
 
-        node_box, states = [], []
+        def snapshot(n):
+            return {"pathIndex": n.pathIndex, "obstacle": bool(n.obstacle),
+                    "F": [bool(getattr(n, "regionF%d" % k)) for k in (1, 2, 3, 4)],
+                    "R": [bool(getattr(n, "regionR%d" % k)) for k in (1, 2, 3, 4)],
+                    "L": [bool(getattr(n, "regionL%d" % k)) for k in (1, 2, 3, 4)],
+                    "avoid": (n.obstacle_avoid_wpx, n.obstacle_avoid_wpy, n.obstacle_avoid_spd)}
+        return _drive(rospy, passes, mod.LocalNavigator, snapshot)      # the node's life is its constructor
 
-        def snapshot():
-            n = node_box[0]
-            states.append({"pathIndex": n.pathIndex, "obstacle": bool(n.obstacle),
-                           "F": [bool(getattr(n, "regionF%d" % k)) for k in (1, 2, 3, 4)],
-                           "R": [bool(getattr(n, "regionR%d" % k)) for k in (1, 2, 3, 4)],
-                           "L": [bool(getattr(n, "regionL%d" % k)) for k in (1, 2, 3, 4)],
-                           "avoid": (n.obstacle_avoid_wpx, n.obstacle_avoid_wpy, n.obstacle_avoid_spd)})
 
-        script = [[("/path", Path(route_xy))]]
-        for p in passes:
-            ev = []
-            if p.get("pose") is not None:
-                ev.append(("base_pose_ground_truth", Odometry(*p["pose"])))
-            if p.get("grid") is not None:
-                w, data = p["grid"]
-                g = ("local_costmap", OccupancyGrid(width=w, height=w, resolution=0.25, data=data))
-                ev.insert(0, g) if p.get("grid_first") else ev.append(g)
-            script.append(ev)
-        rospy.state.script = script
+def run_shim(shim_file, route_xy, passes, device=0):
+    """The same script through this repository's drop-in node (ros/local_navigator_b200.py), run UNCHANGED
+    against the same rospy doubles.  Needs a GPU (the shim scans costmaps on the device)."""
+    with _doubles():
+        import rospy
+        from nav_msgs.msg import OccupancyGrid, Odometry, Path
+        rospy.state.reset()
+        spec = importlib.util.spec_from_file_location("local_navigator_b200_shim", shim_file)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        rospy.state.script = _script(route_xy, passes, Path, Odometry, OccupancyGrid)
 
-        # the subscribers are bound methods: the first one registered hands us the node object, and
-        # wrapping Rate.sleep lets us snapshot its state after every pass
-        real_sub = rospy.Subscriber.__init__
-
-        def sub_init(self, topic, typ, cb, queue_size=None):
-            if not node_box:
-                node_box.append(cb.__self__)
-            real_sub(self, topic, typ, cb, queue_size)
-
-        real_rate_sleep = rospy.Rate.sleep
-
-        def rate_sleep(self):
-            if rospy.state.passes >= 2:      # pass 0 saw nothing, pass 1 saw only /path
-                snapshot()
-            real_rate_sleep(self)
-
-        rospy.Subscriber.__init__ = sub_init
-        rospy.Rate.sleep = rate_sleep
-        mod.LocalNavigator()                  # returns when the script is exhausted
-        published = [None] * len(passes)
-        for k, _topic, fields in rospy.state.published:
-            # loop pass k processed script entry k-1; script entry 0 is /path, entry j+1 is passes[j]
-            published[k - 2] = fields
-        return published, states
+        def snapshot(node):
+            n = node.nav
+            return {"pathIndex": n.path_index, "obstacle": bool(n.obstacle), "F": list(n.F), "R": list(n.R),
+                    "L": list(n.L), "avoid": tuple(n.avoid)}
+        return _drive(rospy, passes, lambda: mod.LocalNavigatorNode(device=device).spin(), snapshot)

@@ -195,3 +195,24 @@ def test_ros_global_costmap_shim_publishes_the_reference_nodes_map(cuda_device, 
     got = np.fromfile(out, dtype=np.int8)
     np.testing.assert_array_equal(got, want)
     assert ((got >= 0) & (got < 99)).sum() > 100000
+
+
+def test_navigator_shim_publishes_what_the_reference_published(cuda_device):
+    """ros/local_navigator_b200.py, run unchanged against the rospy test doubles, fed the scripted messages of
+    tests/golden/ref_navigator.npz: every LocalNav it publishes, and its path index / flags / avoidance
+    way-point after every loop pass, equal what the REFERENCE node (local_navigator.py, imported unmodified
+    when the fixture was made) published and held.  The costmaps are scanned on the device."""
+    import sys
+    gold = os.path.join(ROOT, "tests", "golden")
+    sys.path.insert(0, gold)
+    import make_navigator_golden as mng
+    from oracle import ref_navigator as rn
+    from test_navigator_ref_pin import assert_same
+    shim = os.path.join(ROOT, "ros", "local_navigator_b200.py")
+    z = np.load(os.path.join(gold, "ref_navigator.npz"))
+    for seed in mng.SEEDS:
+        passes = mng.passes_from_fixture(z, seed)
+        script = [dict(p, grid=(p["grid"][0], p["grid"][1].reshape(-1).tolist()) if p["grid"] is not None else None)
+                  for p in passes]
+        got = mng.pack(*rn.run_shim(shim, mng.route(), script))
+        assert_same(got, (z[f"s{seed}_pub"], z[f"s{seed}_state"], z[f"s{seed}_avoid"]))
