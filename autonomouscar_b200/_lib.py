@@ -21,7 +21,7 @@ EXPORTS = [
     "pp_philox4x32_10", "pp_nearest_dev", "pp_find_exact_dev", "pp_plan", "pp_plan_batch", "pp_rrt_plan",
     "pp_rrt_plan_batch", "pp_get_visited", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
     "pp_last_narrow_count", "pp_bench_l2_gather", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
-    "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch",
+    "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch", "pp_set_grid_bank_dev", "pp_plan_batch_banked",
 ]
 # every symbol include/prius_costmap.h declares (row N2)
 COSTMAP_EXPORTS = [
@@ -69,6 +69,8 @@ def load():
     L.pp_find_exact_dev.argtypes = [vp, i64, vp, i64, vp, vp]
     L.pp_plan.argtypes = [vp, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
+    L.pp_plan_batch_banked.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
+    L.pp_set_grid_bank_dev.argtypes = [vp, i32, vp, i32, i32, f64, C.c_int]
     L.pp_rrt_plan.argtypes = [vp, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_rrt_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_get_visited.argtypes = [vp, vp, C.c_size_t]

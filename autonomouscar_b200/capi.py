@@ -124,9 +124,11 @@ def default_params(**overrides):
 
 
 def make_query(goal_x, goal_y, goal_speed=1.5, max_speed=1.5, max_accel=1.5, start_speed=0.0,
-               start_x=0.0, start_y=0.0, start_heading=0.0, seed=0, query_id=0):
-    """LocalNav defaults from local_navigator.py:524-527."""
+               start_x=0.0, start_y=0.0, start_heading=0.0, seed=0, query_id=0, grid_index=0):
+    """LocalNav defaults from local_navigator.py:524-527.  grid_index: which grid of the planner's bank this
+    query plans on (pp_plan_batch_banked only)."""
     q = pp_query()
+    q.reserved = grid_index
     q.goal_x, q.goal_y, q.goal_speed = goal_x, goal_y, goal_speed
     q.max_speed, q.max_accel, q.start_speed = max_speed, max_accel, start_speed
     q.start_x, q.start_y, q.start_heading = start_x, start_y, start_heading

@@ -80,6 +80,12 @@ class LocalCostmap:
         self._check(self._L.pc_batch_grids_dev(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def feed_planner_bank(self, planner):
+        """Hand the most recent batch's grids to a Planner as a grid bank, without leaving the GPU."""
+        ptr, n = self.batch_grids_dev()
+        planner.set_grid_bank_dev(ptr, n, layout=PP_GRID_OCCUPANCY_MSG)
+        return n
+
     def grid_dev(self):
         """(device pointer, width, height) of the most recent grid."""
         p, w, h = C.c_void_p(), C.c_int32(), C.c_int32()

@@ -329,6 +329,30 @@ int pp_find_exact_dev(pp_handle* h, int64_t n_nodes, const double* node_keys_dev
 
 int pp_plan(pp_handle* h, const pp_query* query, pp_result* result) { return pp_plan_batch(h, 1, query, result); }
 
+int pp_set_grid_bank_dev(pp_handle* h, int32_t n, const int8_t* grids_dev, int32_t width, int32_t height, double res,
+                         int layout) {
+  if (!h) return PP_ERR_INVALID;
+  PP_REQUIRE(n >= 1 && n <= 65535 && grids_dev, "pp_set_grid_bank_dev: 1 <= n <= 65535 grids on the device");
+  PP_REQUIRE(width == h->P.costmap_width && height == h->P.costmap_height && res == h->P.costmap_res,
+             "pp_set_grid_bank_dev: grid shape differs from the handle's parameters");
+  PP_REQUIRE(layout == PP_GRID_OCCUPANCY_MSG || layout == PP_GRID_CSPACE, "pp_set_grid_bank_dev: unknown layout");
+  return grid_bank_upload(h, n, grids_dev, layout);
+}
+
+int pp_plan_batch_banked(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results) {
+  if (!h) return PP_ERR_INVALID;
+  PP_REQUIRE(n >= 0 && (n == 0 || (queries && results)), "pp_plan_batch_banked: bad arguments");
+  if (n == 0) return PP_OK;
+  if (h->bank.n < 1) {
+    set_last_error("pp_plan_batch_banked: pp_set_grid_bank_dev has not been called");
+    return PP_ERR_NO_GRID;
+  }
+  for (int32_t k = 0; k < n; ++k)
+    PP_REQUIRE(queries[k].reserved < static_cast<uint32_t>(h->bank.n), "pp_plan_batch_banked: query.reserved (grid index) outside the bank");
+  PP_CUDA(cudaSetDevice(h->device));
+  return plan_batch(h, n, queries, results, true);
+}
+
 int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results) {
   int rc = require_grid(h, "pp_plan_batch");
   if (rc) return rc;

@@ -73,6 +73,24 @@ struct GridDev {
   int aabb_pad_x, aabb_pad_y, aabb_nx, aabb_ny;
 };
 
+// A bank = n grids of ONE shape stored back to back: every array of grid k starts k * stride elements
+// after grid 0's.  The planner's own grid is a bank of one (strides unused).  pp_set_grid_bank_dev builds
+// banks; pp_plan_batch_banked lets every query name its grid.
+struct GridBank {
+  int n = 0;
+  size_t cspace = 0, occ_tiles = 0, tile_any = 0, coarse = 0, coarse4 = 0, near8 = 0, aabb_map = 0;
+};
+__host__ __device__ inline GridDev grid_at(GridDev g, const GridBank& b, unsigned k) {
+  g.cspace += k * b.cspace;
+  g.occ_tiles += k * b.occ_tiles;
+  g.tile_any += k * b.tile_any;
+  g.coarse += k * b.coarse;
+  g.coarse4 += k * b.coarse4;
+  g.near8 += k * b.near8;
+  g.aabb_map += k * b.aabb_map;
+  return g;
+}
+
 struct CollideParams {
   Lattice lat;
   double car_length, car_width, search_res;
@@ -263,6 +281,12 @@ struct pp_handle {
   pp::Lattice lat{};
   pp::GridDev grid{};
   bool has_grid = false;
+  // grid bank (pp_set_grid_bank_dev): bank_grid describes grid 0, bank the strides; bank.n == 0: none
+  pp::GridDev bank_grid{};
+  pp::GridBank bank{};
+  int bank_cap = 0;
+  uint8_t* bank_rows = nullptr;    // REF_AABB pass-1 scratch of the bank
+  int* d_box_tables = nullptr;     // LP:473-476 interval tables (xlo | xhi | ylo | yhi)
   int broad_phase = 1;
   uint64_t launches = 0;
   float phase_ms[PP_PHASE_COUNT] = {};
@@ -295,6 +319,7 @@ inline CollideParams collide_params(const pp_handle* h) {
 }
 // kernels / host helpers implemented across the .cu files
 int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layout);
+int grid_bank_upload(pp_handle* h, int n, const int8_t* grids_dev, int layout);
 void grid_free(pp_handle* h);
 int collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev);
 int collide_launch(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev);
@@ -309,7 +334,7 @@ int nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy, int64_t n_q
 int l2_gather_bench(pp_handle* h, size_t buffer_bytes, double* out_gbps);
 int find_exact_dev(pp_handle* h, int64_t n_nodes, const double* keys, int64_t n_query, const double* q,
                    int32_t* idx);
-int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs);
+int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool banked = false);
 int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs);
 void plan_free(pp_handle* h);
 void rrt_free(pp_handle* h);

@@ -19,22 +19,38 @@ namespace pp {
 
 namespace {
 
+// Every build kernel handles grid blockIdx.y of a bank (grids of one shape stored back to back, pp_common.cuh);
+// the planner's own single grid is a bank of one with zero strides.
+struct BuildArgs {
+  GridDev g;                 // grid 0 of the bank
+  GridBank b;
+  const int8_t* src;         // OccupancyGrid.data of grid 0 (message order), src_stride cells apart
+  size_t src_stride;
+  uint8_t* rows;             // REF_AABB pass-1 scratch of grid 0, rows_stride bytes apart
+  size_t rows_stride;
+  const int *xlo, *xhi, *ylo, *yhi;
+};
+__device__ __forceinline__ GridDev build_grid(const BuildArgs& a) { return grid_at(a.g, a.b, blockIdx.y); }
+
 // LP:437-441: location = H*W - i*H - j - 1 (exact in double for any grid that fits memory)
-__global__ void flip_msg_to_cspace(const int8_t* __restrict__ msg, int8_t* __restrict__ cspace, int W, int H) {
-  const int64_t total = static_cast<int64_t>(W) * H;
+__global__ void flip_msg_to_cspace(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const int8_t* __restrict__ msg = a.src + blockIdx.y * a.src_stride;
+  const int64_t total = static_cast<int64_t>(g.W) * g.H;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     // k = i*H + j  ->  location = total - k - 1
-    cspace[k] = msg[total - k - 1];
+    g.cspace[k] = msg[total - k - 1];
   }
 }
 
 // one warp packs 32 consecutive cells of a row into one word with a ballot
-__global__ void pack_occ_tiles(const int8_t* __restrict__ cspace, uint32_t* __restrict__ tiles, int W, int H,
-                               int TI, int TJ) {
+__global__ void pack_occ_tiles(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const int W = g.W, H = g.H, TJ = g.TJ;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t n_words = static_cast<int64_t>(TI) * TJ * kTile;
+  const int64_t n_words = static_cast<int64_t>(g.TI) * TJ * kTile;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t w = warp; w < n_words; w += n_warps) {
     const int r = static_cast<int>(w & 31);
@@ -43,33 +59,36 @@ __global__ void pack_occ_tiles(const int8_t* __restrict__ cspace, uint32_t* __re
     const int i = ti * kTile - kHaloCells + r;
     const int j = tj * kTile - kHaloCells + lane;
     bool occ = false;
-    if (i >= 0 && i < W && j >= 0 && j < H) occ = cspace[static_cast<size_t>(i) * H + j] == 100;
+    if (i >= 0 && i < W && j >= 0 && j < H) occ = g.cspace[static_cast<size_t>(i) * H + j] == 100;
     const uint32_t word = __ballot_sync(0xffffffffu, occ);
-    if (lane == 0) tiles[w] = word;
+    if (lane == 0) g.occ_tiles[w] = word;
   }
 }
 
-__global__ void reduce_tile_any(const uint32_t* __restrict__ tiles, uint8_t* __restrict__ tile_any, int64_t n_tiles) {
+__global__ void reduce_tile_any(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const int64_t n_tiles = static_cast<int64_t>(g.TI) * g.TJ;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t t = warp; t < n_tiles; t += n_warps) {
-    const uint32_t w = tiles[t * kTile + lane];
+    const uint32_t w = g.occ_tiles[t * kTile + lane];
     const bool any = __any_sync(0xffffffffu, w != 0);
-    if (lane == 0) tile_any[t] = any ? 1 : 0;
+    if (lane == 0) g.tile_any[t] = any ? 1 : 0;
   }
 }
 
 // 8x8-cell coarse occupancy: thread per (coarse row, tile column) ORs 8 tile words -> 4 bits
-__global__ void build_coarse(const uint32_t* __restrict__ tiles, unsigned long long* __restrict__ coarse, int TI,
-                             int TJ, int CW8) {
-  const int64_t total = static_cast<int64_t>(TI) * 4 * TJ;
+__global__ void build_coarse(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const int TJ = g.TJ;
+  const int64_t total = static_cast<int64_t>(g.TI) * 4 * TJ;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int tj = static_cast<int>(k % TJ);
     const int ci8 = static_cast<int>(k / TJ);
     const int ti = ci8 >> 2, r0 = (ci8 & 3) * 8;
-    const uint32_t* t = tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
+    const uint32_t* t = g.occ_tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
     uint32_t w = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) w |= t[r];
@@ -79,21 +98,22 @@ __global__ void build_coarse(const uint32_t* __restrict__ tiles, unsigned long l
       if ((w >> (8 * b)) & 0xffu) bits |= 1ull << b;
     if (bits) {
       const int cj8 = tj * 4;
-      atomicOr(&coarse[static_cast<size_t>(ci8) * CW8 + (cj8 >> 6)], bits << (cj8 & 63));
+      atomicOr(&g.coarse[static_cast<size_t>(ci8) * g.CW8 + (cj8 >> 6)], bits << (cj8 & 63));
     }
   }
 }
 
 // 4x4-cell coarse occupancy: thread per (coarse row, tile column) ORs 4 tile words -> 8 bits
-__global__ void build_coarse4(const uint32_t* __restrict__ tiles, unsigned long long* __restrict__ coarse4, int TI,
-                              int TJ, int CW4) {
-  const int64_t total = static_cast<int64_t>(TI) * 8 * TJ;
+__global__ void build_coarse4(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const int TJ = g.TJ;
+  const int64_t total = static_cast<int64_t>(g.TI) * 8 * TJ;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int tj = static_cast<int>(k % TJ);
     const int ci4 = static_cast<int>(k / TJ);
     const int ti = ci4 >> 3, r0 = (ci4 & 7) * 4;
-    const uint32_t* t = tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
+    const uint32_t* t = g.occ_tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
     const uint32_t w = t[0] | t[1] | t[2] | t[3];
     unsigned long long bits = 0;
 #pragma unroll
@@ -101,21 +121,22 @@ __global__ void build_coarse4(const uint32_t* __restrict__ tiles, unsigned long 
       if ((w >> (4 * b)) & 0xfu) bits |= 1ull << b;
     if (bits) {
       const int cj4 = tj * 8;
-      atomicOr(&coarse4[static_cast<size_t>(ci4) * CW4 + (cj4 >> 6)], bits << (cj4 & 63));
+      atomicOr(&g.coarse4[static_cast<size_t>(ci4) * g.CW4 + (cj4 >> 6)], bits << (cj4 & 63));
     }
   }
 }
 
 // near8 = coarse dilated by r8 blocks (square structuring element), one thread per 64-bit word
-__global__ void dilate_coarse(const unsigned long long* __restrict__ coarse, unsigned long long* __restrict__ near8,
-                              int CI8, int CW8, int r8) {
+__global__ void dilate_coarse(BuildArgs a, int r8) {
+  const GridDev g = build_grid(a);
+  const int CI8 = g.CI8, CW8 = g.CW8;
   const int64_t total = static_cast<int64_t>(CI8) * CW8;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int w = static_cast<int>(k % CW8), r = static_cast<int>(k / CW8);
     unsigned long long acc = 0;
     for (int rr = max(r - r8, 0); rr <= min(r + r8, CI8 - 1); ++rr) {
-      const unsigned long long* row = coarse + static_cast<size_t>(rr) * CW8;
+      const unsigned long long* row = g.coarse + static_cast<size_t>(rr) * CW8;
       const unsigned long long c = row[w], l = w > 0 ? row[w - 1] : 0ull, h = w + 1 < CW8 ? row[w + 1] : 0ull;
       unsigned long long d = c;
       for (int sft = 1; sft <= r8; ++sft) {        // r8 < 64
@@ -124,36 +145,40 @@ __global__ void dilate_coarse(const unsigned long long* __restrict__ coarse, uns
       }
       acc |= d;
     }
-    near8[k] = acc;
+    g.near8[k] = acc;
   }
 }
 
 // REF_AABB dilation, pass 1: rows[x][my] = OR over y in [ylo[my], yhi[my]) of (cspace[x][y]==100)
-__global__ void aabb_pass_y(const int8_t* __restrict__ cspace, uint8_t* __restrict__ rows, int W, int H, int ny,
-                            const int* __restrict__ ylo, const int* __restrict__ yhi) {
-  const int64_t total = static_cast<int64_t>(W) * ny;
+__global__ void aabb_pass_y(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  uint8_t* __restrict__ rows = a.rows + blockIdx.y * a.rows_stride;
+  const int H = g.H, ny = g.aabb_ny;
+  const int64_t total = static_cast<int64_t>(g.W) * ny;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int my = static_cast<int>(k % ny);
     const int x = static_cast<int>(k / ny);
-    int lo = max(ylo[my], 0), hi = min(yhi[my], H);
+    int lo = max(a.ylo[my], 0), hi = min(a.yhi[my], H);
     uint8_t any = 0;
-    for (int y = lo; y < hi; ++y) any |= (cspace[static_cast<size_t>(x) * H + y] == 100);
+    for (int y = lo; y < hi; ++y) any |= (g.cspace[static_cast<size_t>(x) * H + y] == 100);
     rows[k] = any;
   }
 }
 // pass 2: map[mx][my] = OR over x in [xlo[mx], xhi[mx]) of rows[x][my]
-__global__ void aabb_pass_x(const uint8_t* __restrict__ rows, uint8_t* __restrict__ map, int W, int nx, int ny,
-                            const int* __restrict__ xlo, const int* __restrict__ xhi) {
-  const int64_t total = static_cast<int64_t>(nx) * ny;
+__global__ void aabb_pass_x(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const uint8_t* __restrict__ rows = a.rows + blockIdx.y * a.rows_stride;
+  const int W = g.W, ny = g.aabb_ny;
+  const int64_t total = static_cast<int64_t>(g.aabb_nx) * ny;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int my = static_cast<int>(k % ny);
     const int mx = static_cast<int>(k / ny);
-    int lo = max(xlo[mx], 0), hi = min(xhi[mx], W);
+    int lo = max(a.xlo[mx], 0), hi = min(a.xhi[mx], W);
     uint8_t any = 0;
     for (int x = lo; x < hi; ++x) any |= rows[static_cast<size_t>(x) * ny + my];
-    map[k] = any;
+    g.aabb_map[k] = any;
   }
 }
 
@@ -171,24 +196,128 @@ void box_interval_table(int n_cells, int pad, double extent, double res, std::ve
   }
 }
 
-int blocks_for(int64_t work, int threads, int sm_count) {
+int blocks_for(int64_t work, int threads, int sm_count, int n_grids = 1) {
   const int64_t want = (work + threads - 1) / threads;
-  const int64_t cap = static_cast<int64_t>(sm_count) * 8;
+  const int64_t cap = std::max<int64_t>(4, static_cast<int64_t>(sm_count) * 8 / n_grids);
   return static_cast<int>(std::max<int64_t>(1, std::min(want, cap)));
+}
+
+// shapes of every representation for the handle's parameters; pointers left null
+GridDev grid_shape(const pp_handle* h) {
+  GridDev g{};
+  const int W = h->P.costmap_width, H = h->P.costmap_height;
+  g.W = W; g.H = H; g.res = h->P.costmap_res;
+  g.TI = (W + 2 * kHaloCells + kTile - 1) / kTile;
+  g.TJ = (H + 2 * kHaloCells + kTile - 1) / kTile;
+  g.aabb_pad_x = static_cast<int>(std::ceil(h->P.car_length / 2 / g.res)) + 2;
+  g.aabb_pad_y = static_cast<int>(std::ceil(h->P.car_width / 2 / g.res)) + 2;
+  g.aabb_nx = W + 2 * g.aabb_pad_x;
+  g.aabb_ny = H + 2 * g.aabb_pad_y;
+  g.CI8 = g.TI * 4;
+  g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
+  g.CI4 = g.TI * 8;
+  g.CW4 = (g.TJ * 8 + 63) / 64 + 1;
+  // half diagonal of the footprint in cells + 1 (floor) + 2 (float slack of the pre-test)
+  const double du = h->lat.su * h->lat.hu, dv = h->lat.sv * h->lat.hv;
+  g.reach_cells = static_cast<int>(std::sqrt(du * du + dv * dv)) + 4;
+  return g;
+}
+
+// element strides between consecutive grids of a bank (16-byte aligned sub-arrays)
+GridBank bank_strides(const GridDev& g, int n) {
+  auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+  GridBank b;
+  b.n = n;
+  b.cspace = up(static_cast<size_t>(g.W) * g.H, 16);
+  // + 2 tiles of padding: the narrow phase reads every tile row three tiles wide
+  b.occ_tiles = (static_cast<size_t>(g.TI) * g.TJ + 2) * kTile;
+  b.tile_any = up(static_cast<size_t>(g.TI) * g.TJ, 16);
+  b.coarse = static_cast<size_t>(g.CI8) * g.CW8;
+  b.near8 = b.coarse;
+  b.coarse4 = static_cast<size_t>(g.CI4) * g.CW4;
+  b.aabb_map = up(static_cast<size_t>(g.aabb_nx) * g.aabb_ny, 16);
+  return b;
+}
+
+void grid_free_arrays(GridDev* g) {
+  cudaFree(g->cspace);
+  cudaFree(g->occ_tiles);
+  cudaFree(g->tile_any);
+  cudaFree(g->coarse);
+  cudaFree(g->coarse4);
+  cudaFree(g->near8);
+  cudaFree(g->aabb_map);
+  *g = GridDev{};
+}
+
+int grid_alloc(GridDev* g, const GridBank& b) {
+  const size_t n = static_cast<size_t>(b.n);
+  PP_CUDA(cudaMalloc(&g->cspace, b.cspace * n));
+  PP_CUDA(cudaMalloc(&g->occ_tiles, b.occ_tiles * n * sizeof(uint32_t)));
+  PP_CUDA(cudaMemset(g->occ_tiles, 0, b.occ_tiles * n * sizeof(uint32_t)));      // (the padding tiles stay zero)
+  PP_CUDA(cudaMalloc(&g->tile_any, b.tile_any * n));
+  PP_CUDA(cudaMalloc(&g->coarse, sizeof(unsigned long long) * b.coarse * n));
+  PP_CUDA(cudaMalloc(&g->near8, sizeof(unsigned long long) * b.near8 * n));
+  PP_CUDA(cudaMalloc(&g->coarse4, sizeof(unsigned long long) * b.coarse4 * n));
+  PP_CUDA(cudaMalloc(&g->aabb_map, b.aabb_map * n));
+  return PP_OK;
+}
+
+// the LP:473-476 interval tables depend only on the parameters: built once per handle
+int ensure_box_tables(pp_handle* h, const GridDev& g) {
+  if (h->d_box_tables) return PP_OK;
+  std::vector<int> xlo, xhi, ylo, yhi;
+  box_interval_table(g.W, g.aabb_pad_x, h->P.car_length, g.res, &xlo, &xhi);
+  box_interval_table(g.H, g.aabb_pad_y, h->P.car_width, g.res, &ylo, &yhi);
+  PP_CUDA(cudaMalloc(&h->d_box_tables, sizeof(int) * 2 * (g.aabb_nx + g.aabb_ny)));
+  int* t = h->d_box_tables;
+  PP_CUDA(cudaMemcpy(t, xlo.data(), sizeof(int) * g.aabb_nx, cudaMemcpyHostToDevice));
+  PP_CUDA(cudaMemcpy(t + g.aabb_nx, xhi.data(), sizeof(int) * g.aabb_nx, cudaMemcpyHostToDevice));
+  PP_CUDA(cudaMemcpy(t + 2 * g.aabb_nx, ylo.data(), sizeof(int) * g.aabb_ny, cudaMemcpyHostToDevice));
+  PP_CUDA(cudaMemcpy(t + 2 * g.aabb_nx + g.aabb_ny, yhi.data(), sizeof(int) * g.aabb_ny, cudaMemcpyHostToDevice));
+  return PP_OK;
+}
+
+// all derived representations of the n grids of a bank from their cspace (or message) bytes, on h->stream
+int grid_build(pp_handle* h, const GridDev& g, const GridBank& b, const int8_t* msg_src, size_t src_stride, uint8_t* rows,
+               size_t rows_stride) {
+  cudaStream_t s = h->stream;
+  const int T = 256, n = b.n;
+  const unsigned ny = static_cast<unsigned>(n);
+  BuildArgs a;
+  a.g = g; a.b = b; a.src = msg_src; a.src_stride = src_stride; a.rows = rows; a.rows_stride = rows_stride;
+  a.xlo = h->d_box_tables; a.xhi = a.xlo + g.aabb_nx; a.ylo = a.xhi + g.aabb_nx; a.yhi = a.ylo + g.aabb_ny;
+  auto blocks = [&](int64_t work) { return dim3(static_cast<unsigned>(blocks_for(work, T, h->sm_count, n)), ny); };
+  const int64_t cells = static_cast<int64_t>(g.W) * g.H;
+  if (msg_src) {
+    flip_msg_to_cspace<<<blocks(cells), T, 0, s>>>(a);
+    h->launches++;
+  }
+  const int64_t n_tiles = static_cast<int64_t>(g.TI) * g.TJ;
+  pack_occ_tiles<<<blocks(n_tiles * kTile * 32), T, 0, s>>>(a);
+  reduce_tile_any<<<blocks(n_tiles * 32), T, 0, s>>>(a);
+  PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * b.coarse * n, s));
+  build_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.TJ), T, 0, s>>>(a);
+  dilate_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.CW8), T, 0, s>>>(a, (g.reach_cells + 7) / 8);
+  PP_CUDA(cudaMemsetAsync(g.coarse4, 0, sizeof(unsigned long long) * b.coarse4 * n, s));
+  build_coarse4<<<blocks(static_cast<int64_t>(g.CI4) * g.TJ), T, 0, s>>>(a);
+  h->launches += 3;
+  aabb_pass_y<<<blocks(static_cast<int64_t>(g.W) * g.aabb_ny), T, 0, s>>>(a);
+  aabb_pass_x<<<blocks(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny), T, 0, s>>>(a);
+  h->launches += 4;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
 }
 
 }  // namespace
 
 void grid_free(pp_handle* h) {
-  GridDev& g = h->grid;
-  cudaFree(g.cspace);
-  cudaFree(g.occ_tiles);
-  cudaFree(g.tile_any);
-  cudaFree(g.coarse);
-  cudaFree(g.coarse4);
-  cudaFree(g.near8);
-  cudaFree(g.aabb_map);
-  g = GridDev{};
+  grid_free_arrays(&h->grid);
+  grid_free_arrays(&h->bank_grid);
+  cudaFree(h->bank_rows);
+  cudaFree(h->d_box_tables);
+  h->bank_rows = nullptr; h->d_box_tables = nullptr;
+  h->bank = GridBank{};
   h->has_grid = false;
 }
 
@@ -198,81 +327,66 @@ int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layou
   const int W = h->P.costmap_width, H = h->P.costmap_height;
   const size_t cells = static_cast<size_t>(W) * H;
   if (!g.cspace) {  // first grid: allocate every representation once
-    g.W = W; g.H = H; g.res = h->P.costmap_res;
-    g.TI = (W + 2 * kHaloCells + kTile - 1) / kTile;
-    g.TJ = (H + 2 * kHaloCells + kTile - 1) / kTile;
-    g.aabb_pad_x = static_cast<int>(std::ceil(h->P.car_length / 2 / g.res)) + 2;
-    g.aabb_pad_y = static_cast<int>(std::ceil(h->P.car_width / 2 / g.res)) + 2;
-    g.aabb_nx = W + 2 * g.aabb_pad_x;
-    g.aabb_ny = H + 2 * g.aabb_pad_y;
-    PP_CUDA(cudaMalloc(&g.cspace, cells));
-    // + 2 tiles of padding: the narrow phase reads every tile row three tiles wide
-    PP_CUDA(cudaMalloc(&g.occ_tiles, (static_cast<size_t>(g.TI) * g.TJ + 2) * kTile * sizeof(uint32_t)));
-    PP_CUDA(cudaMemset(g.occ_tiles + static_cast<size_t>(g.TI) * g.TJ * kTile, 0, 2 * kTile * sizeof(uint32_t)));
-    PP_CUDA(cudaMalloc(&g.tile_any, static_cast<size_t>(g.TI) * g.TJ));
-    g.CI8 = g.TI * 4;
-    g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
-    PP_CUDA(cudaMalloc(&g.coarse, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
-    PP_CUDA(cudaMalloc(&g.near8, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8));
-    g.CI4 = g.TI * 8;
-    g.CW4 = (g.TJ * 8 + 63) / 64 + 1;
-    PP_CUDA(cudaMalloc(&g.coarse4, sizeof(unsigned long long) * static_cast<size_t>(g.CI4) * g.CW4));
-    {
-      // half diagonal of the footprint in cells + 1 (floor) + 2 (float slack of the pre-test)
-      const double du = h->lat.su * h->lat.hu, dv = h->lat.sv * h->lat.hv;
-      g.reach_cells = static_cast<int>(std::sqrt(du * du + dv * dv)) + 4;
-    }
-    PP_CUDA(cudaMalloc(&g.aabb_map, static_cast<size_t>(g.aabb_nx) * g.aabb_ny));
-    // scratch: message copy (cells) + pass-1 rows (W * ny) + 4 interval tables
-    h->scratch_bytes = cells + static_cast<size_t>(W) * g.aabb_ny + sizeof(int) * 2 * (g.aabb_nx + g.aabb_ny) + 256;
+    g = grid_shape(h);
+    const int rc = grid_alloc(&g, bank_strides(g, 1));
+    if (rc) return rc;
+    // scratch: message copy (cells) + pass-1 rows (W * ny)
+    h->scratch_bytes = cells + static_cast<size_t>(W) * g.aabb_ny + 256;
     PP_CUDA(cudaMalloc(&h->scratch, h->scratch_bytes));
-    // interval tables depend only on the parameters: upload once
-    std::vector<int> xlo, xhi, ylo, yhi;
-    box_interval_table(W, g.aabb_pad_x, h->P.car_length, g.res, &xlo, &xhi);
-    box_interval_table(H, g.aabb_pad_y, h->P.car_width, g.res, &ylo, &yhi);
-    char* base = static_cast<char*>(h->scratch) + ((cells + static_cast<size_t>(W) * g.aabb_ny + 255) & ~size_t(255));
-    int* t = reinterpret_cast<int*>(base);
-    PP_CUDA(cudaMemcpy(t, xlo.data(), sizeof(int) * g.aabb_nx, cudaMemcpyHostToDevice));
-    PP_CUDA(cudaMemcpy(t + g.aabb_nx, xhi.data(), sizeof(int) * g.aabb_nx, cudaMemcpyHostToDevice));
-    PP_CUDA(cudaMemcpy(t + 2 * g.aabb_nx, ylo.data(), sizeof(int) * g.aabb_ny, cudaMemcpyHostToDevice));
-    PP_CUDA(cudaMemcpy(t + 2 * g.aabb_nx + g.aabb_ny, yhi.data(), sizeof(int) * g.aabb_ny, cudaMemcpyHostToDevice));
   }
+  int rc = ensure_box_tables(h, g);
+  if (rc) return rc;
   int8_t* msg = static_cast<int8_t*>(h->scratch);
   uint8_t* rows = reinterpret_cast<uint8_t*>(h->scratch) + cells;
-  char* tbase = static_cast<char*>(h->scratch) + ((cells + static_cast<size_t>(W) * g.aabb_ny + 255) & ~size_t(255));
-  const int* xlo = reinterpret_cast<const int*>(tbase);
-  const int* xhi = xlo + g.aabb_nx;
-  const int* ylo = xhi + g.aabb_nx;
-  const int* yhi = ylo + g.aabb_ny;
-
   cudaStream_t s = h->stream;
-  const int T = 256;
+  const int8_t* src = nullptr;
   if (layout == PP_GRID_OCCUPANCY_MSG) {
-    const int8_t* src = data;
+    src = data;
     if (!data_on_device) {
       PP_CUDA(cudaMemcpyAsync(msg, data, cells, cudaMemcpyHostToDevice, s));
       src = msg;
     }
-    flip_msg_to_cspace<<<blocks_for(cells, T, h->sm_count), T, 0, s>>>(src, g.cspace, W, H);
-    h->launches++;
   } else {
     PP_CUDA(cudaMemcpyAsync(g.cspace, data, cells, data_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   }
-  const int64_t n_tiles = static_cast<int64_t>(g.TI) * g.TJ;
-  pack_occ_tiles<<<blocks_for(n_tiles * kTile * 32, T, h->sm_count), T, 0, s>>>(g.cspace, g.occ_tiles, W, H, g.TI, g.TJ);
-  reduce_tile_any<<<blocks_for(n_tiles * 32, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.tile_any, n_tiles);
-  PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * static_cast<size_t>(g.CI8) * g.CW8, s));
-  build_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.TJ, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.coarse, g.TI, g.TJ, g.CW8);
-  dilate_coarse<<<blocks_for(static_cast<int64_t>(g.CI8) * g.CW8, T, h->sm_count), T, 0, s>>>(g.coarse, g.near8, g.CI8, g.CW8, (g.reach_cells + 7) / 8);
-  PP_CUDA(cudaMemsetAsync(g.coarse4, 0, sizeof(unsigned long long) * static_cast<size_t>(g.CI4) * g.CW4, s));
-  build_coarse4<<<blocks_for(static_cast<int64_t>(g.CI4) * g.TJ, T, h->sm_count), T, 0, s>>>(g.occ_tiles, g.coarse4, g.TI, g.TJ, g.CW4);
-  h->launches += 3;
-  aabb_pass_y<<<blocks_for(static_cast<int64_t>(W) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(g.cspace, rows, W, H, g.aabb_ny, ylo, yhi);
-  aabb_pass_x<<<blocks_for(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny, T, h->sm_count), T, 0, s>>>(rows, g.aabb_map, W, g.aabb_nx, g.aabb_ny, xlo, xhi);
-  h->launches += 4;
-  PP_CUDA(cudaGetLastError());
+  GridBank one;
+  one.n = 1;
+  rc = grid_build(h, g, one, src, 0, rows, 0);
+  if (rc) return rc;
   PP_CUDA(cudaStreamSynchronize(s));
   h->has_grid = true;
+  return PP_OK;
+}
+
+// n grids of the handle's shape, already on the device, `cells` bytes apart (e.g. pc_batch_grids_dev)
+int grid_bank_upload(pp_handle* h, int n, const int8_t* grids_dev, int layout) {
+  PP_CUDA(cudaSetDevice(h->device));
+  PP_CUDA(cudaStreamSynchronize(h->stream));
+  const GridDev shape = grid_shape(h);
+  const size_t cells = static_cast<size_t>(shape.W) * shape.H;
+  if (n > h->bank_cap) {
+    grid_free_arrays(&h->bank_grid);
+    cudaFree(h->bank_rows);
+    h->bank_rows = nullptr; h->bank_cap = 0; h->bank = GridBank{};
+    h->bank_grid = shape;
+    const GridBank b = bank_strides(shape, n);
+    int rc = grid_alloc(&h->bank_grid, b);
+    if (rc) return rc;
+    PP_CUDA(cudaMalloc(&h->bank_rows, static_cast<size_t>(shape.W) * shape.aabb_ny * n));
+    h->bank_cap = n;
+  }
+  int rc = ensure_box_tables(h, shape);
+  if (rc) return rc;
+  GridBank b = bank_strides(shape, n);
+  const GridDev& g = h->bank_grid;
+  cudaStream_t s = h->stream;
+  if (layout != PP_GRID_OCCUPANCY_MSG)
+    PP_CUDA(cudaMemcpy2DAsync(g.cspace, b.cspace, grids_dev, cells, cells, static_cast<size_t>(n), cudaMemcpyDeviceToDevice, s));
+  rc = grid_build(h, g, b, layout == PP_GRID_OCCUPANCY_MSG ? grids_dev : nullptr, cells, h->bank_rows,
+                  static_cast<size_t>(shape.W) * shape.aabb_ny);
+  if (rc) return rc;
+  PP_CUDA(cudaStreamSynchronize(s));
+  h->bank = b;
   return PP_OK;
 }
 

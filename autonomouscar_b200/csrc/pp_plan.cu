@@ -55,7 +55,8 @@ struct PlanHdr {                   // per query, device -> host
 };
 
 struct PlanArgs {
-  GridDev g;
+  GridDev g;              // the handle's grid, or grid 0 of its bank
+  GridBank bank;          // bank.n > 0: query.reserved names the grid (pp_plan_batch_banked)
   CollideParams cp;
   pp_params P;
   const pp_query* queries;
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
           dm::sincos(yaw, &sy, &cyaw);
           const double x = dm::add(ncx, dm::mul(step, cyaw));                          // LP:156
           const double y = dm::add(ncy, dm::mul(step, sy));                            // LP:157
-          if (collide_pose_thread(A.g, A.cp, x, y, yaw)) {                             // LP:159
+          if (collide_pose_thread(grid_at(A.g, A.bank, qq.reserved), A.cp, x, y, yaw)) {   // LP:159
             collided = true;
           } else {
             alive = true;
@@ -1125,7 +1126,7 @@ static int grow(void** p, size_t* have, size_t want) {
   return PP_OK;
 }
 
-int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
+int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool banked) {
   if (!h->plan_ws) {
     h->plan_ws = new PlanWorkspace();
     PP_CUDA(cudaMalloc(&h->plan_ws->d_counter, sizeof(int)));
@@ -1222,7 +1223,8 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
 
   unsigned char* ob = static_cast<unsigned char*>(W->out);
   PlanArgs A;
-  A.g = h->grid;
+  A.g = banked ? h->bank_grid : h->grid;
+  A.bank = banked ? h->bank : GridBank{};
   A.cp = collide_params(h);
   A.P = P;
   A.queries = W->d_queries;

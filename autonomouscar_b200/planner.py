@@ -69,6 +69,13 @@ class Planner:
             self._check(self._L.pp_set_grid(self._h, a.ctypes.data_as(C.c_void_p), W, H,
                                             self.params.costmap_res, layout))
 
+    def set_grid_bank_dev(self, grids_dev_ptr, n, layout=PP_GRID_CSPACE):
+        """A bank of n grids of this planner's shape, already on the device, width*height bytes apart (e.g.
+        LocalCostmap.batch_grids_dev()).  Queries name their grid with make_query(..., grid_index=k) and go
+        through plan_batch(..., banked=True)."""
+        self._check(self._L.pp_set_grid_bank_dev(self._h, int(n), C.c_void_p(grids_dev_ptr), self.params.costmap_width,
+                                                 self.params.costmap_height, self.params.costmap_res, layout))
+
     def get_cspace(self):
         W, H = self.params.costmap_width, self.params.costmap_height
         out = np.zeros(W * H, dtype=np.int8)
@@ -169,22 +176,22 @@ class Planner:
             self._check(res.rc)
         return res
 
-    def plan_batch(self, queries, want_nodes=False, **caps):
+    def plan_batch(self, queries, want_nodes=False, banked=False, **caps):
         n = len(queries)
         qs = (pp_query * n)(*queries)
         results = [PlanResult(want_nodes=want_nodes, **caps) for _ in range(n)]
         raw = (pp_result * n)(*[r.raw for r in results])
-        rc = self._L.pp_plan_batch(self._h, n, qs, raw)
+        rc = (self._L.pp_plan_batch_banked if banked else self._L.pp_plan_batch)(self._h, n, qs, raw)
         if rc not in (PP_OK, 4):
             self._check(rc)
         for r, rr in zip(results, raw):
             r.raw = rr
         return results
 
-    def plan_batch_into(self, queries_array, batch, rrt=False):
-        """pp_plan_batch / pp_rrt_plan_batch into pre-allocated PlanBatch buffers.
+    def plan_batch_into(self, queries_array, batch, rrt=False, banked=False):
+        """pp_plan_batch / pp_rrt_plan_batch / pp_plan_batch_banked into pre-allocated PlanBatch buffers.
         `queries_array` is a ctypes (pp_query * n) array."""
-        fn = self._L.pp_rrt_plan_batch if rrt else self._L.pp_plan_batch
+        fn = self._L.pp_rrt_plan_batch if rrt else (self._L.pp_plan_batch_banked if banked else self._L.pp_plan_batch)
         rc = fn(self._h, batch.n, queries_array, batch.raw)
         if rc not in (PP_OK, 4):
             self._check(rc)

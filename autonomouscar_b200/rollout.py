@@ -329,7 +329,7 @@ class RouteRollout:
             c, s = math.cos(self.yaw[k]), math.sin(self.yaw[k])
             dx, dy = wx - self.x[k], wy - self.y[k]
             qs.append(make_query(c * dx + s * dy, -s * dx + c * dy, goal_speed=speed, max_speed=max_speed,
-                                 max_accel=max_accel, start_speed=float(self.v[k]), query_id=k))
+                                 max_accel=max_accel, start_speed=float(self.v[k]), query_id=k, grid_index=k))
         return qs
 
     def tick(self, plan_batch, masks=None):
@@ -358,8 +358,9 @@ class RouteRollout:
         return np.array(self.trace)
 
 
-def plan_batch_cuda(planner, cap_path=256):
-    """plan_batch callable on top of pp_plan_batch (one C-ABI call per tick for all cars)."""
+def plan_batch_cuda(planner, cap_path=256, banked=False):
+    """plan_batch callable on top of pp_plan_batch (one C-ABI call per tick for all cars).  banked=True: car k
+    plans on grid k of the planner's grid bank (pp_plan_batch_banked; fill it with LocalCostmap.feed_planner_bank)."""
     from .capi import pp_query
     from .results import PlanBatch
     cache = {}
@@ -369,7 +370,7 @@ def plan_batch_cuda(planner, cap_path=256):
         if n not in cache:
             cache[n] = PlanBatch(n, cap_path=cap_path)
         buf = cache[n]
-        planner.plan_batch_into((pp_query * n)(*queries), buf)
+        planner.plan_batch_into((pp_query * n)(*queries), buf, banked=banked)
         st, npf = buf.field("status"), buf.field("n_profile")
         return [(st[k] == PP_PLAN_FOUND, buf.yaw_rates[k, :npf[k]].copy(), buf.durations[k, :npf[k]].copy(),
                  buf.speeds[k, :npf[k]].copy()) for k in range(n)]

@@ -120,7 +120,7 @@ typedef struct pp_query {
   double start_x, start_y, start_heading;
   uint64_t seed;
   uint32_t query_id;       /* Philox stream id                                             */
-  uint32_t reserved;
+  uint32_t reserved;       /* pp_plan_batch_banked: index of this query's grid in the bank; else ignored */
 } pp_query;
 
 /* Output of one plan.  The caller sets the cap_* fields and the array pointers (any array
@@ -193,6 +193,11 @@ int pp_set_grid(pp_handle* h, const int8_t* data_host, int32_t width, int32_t he
 /* same, `data_dev` already on the handle's device (no H2D copy) */
 int pp_set_grid_dev(pp_handle* h, const int8_t* data_dev, int32_t width, int32_t height,
                     double res, int layout);
+/* Scenario sweeps with one costmap per simulated car: a BANK of n grids of the handle's shape, already on
+   the device, width*height bytes apart (e.g. what pc_batch_grids_dev returns), built in one set of launches.
+   Independent of pp_set_grid: the handle's own grid is untouched. */
+int pp_set_grid_bank_dev(pp_handle* h, int32_t n, const int8_t* grids_dev, int32_t width, int32_t height,
+                         double res, int layout);
 /* read back the planner-order grid (m_c_space, 1 byte per cell) for inspection */
 int pp_get_cspace(pp_handle* h, int8_t* out_host, size_t capacity);
 
@@ -248,6 +253,9 @@ int pp_find_exact_dev(pp_handle* h, int64_t n_nodes, const double* node_keys_dev
 int pp_plan(pp_handle* h, const pp_query* query, pp_result* result);
 /* n independent queries against the same grid (BASELINE config 5) */
 int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results);
+/* n independent queries, query k against grid queries[k].reserved of the bank (pp_set_grid_bank_dev):
+   N simulated cars, each planning on its own costmap, in one launch */
+int pp_plan_batch_banked(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results);
 /* Debug bitmap of the most recent single-query pp_plan: out[i*H + j] = 1 for every cell that
    markVisited (LP:318-326) touched -- one mark per child returned by getNeighbors, cleared at
    the start of each plan like clearVisited (LP:251-262).  The reference never reads it on the
