@@ -317,6 +317,7 @@ struct Shared {
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
   double scratch_key[6];  // key broadcast for the exact-scan fallback
   long long cyc[8];
+  GridDev gq;      // banked batches: this query's grid (pointers of A.g moved to grid query.reserved)
 };
 
 // scan key of a slot: open slot -> id ; closed slot -> n_nodes + closed_seq (open list by id, then closed
@@ -515,7 +516,7 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
 #ifndef PP_PLAN_BATCH_CTAS
 #define PP_PLAN_BATCH_CTAS 6
 #endif
-template <bool kAllSmem, int kBatchCtas>
+template <bool kAllSmem, int kBatchCtas, bool kBanked>
 __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchCtas : 1) plan_kernel(PlanArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Shared S;
@@ -569,6 +570,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       S.fast = (attempt == 0 && A.fast_frontier) ? 1 : 0;
       S.tie_seen = 0; S.top_pos = 0; S.top_id = 0; S.next_valid = 0; S.next_pos = 0; S.chk_valid = 0; S.next_cost = 0; S.chk_cost = 0;
       for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
+      if (kBanked) S.gq = grid_at(A.g, A.bank, qq.reserved);
     }
     __syncthreads();
     if (warp == 0) {
@@ -686,7 +688,9 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
           dm::sincos(yaw, &sy, &cyaw);
           const double x = dm::add(ncx, dm::mul(step, cyaw));                          // LP:156
           const double y = dm::add(ncy, dm::mul(step, sy));                            // LP:157
-          if (collide_pose_thread(grid_at(A.g, A.bank, qq.reserved), A.cp, x, y, yaw)) {   // LP:159
+          // (kBanked is a template parameter on purpose: the plain instantiation keeps its grid pointers in
+          // the constant bank; reading them through a run-time select cost 25 % on ORIENTED single plans)
+          if (kBanked ? collide_pose_thread(S.gq, A.cp, x, y, yaw) : collide_pose_thread(A.g, A.cp, x, y, yaw)) {   // LP:159
             collided = true;
           } else {
             alive = true;
@@ -1176,17 +1180,18 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   else if (n > h->sm_count) heap_entries = std::min(heap_entries, 6144);
   const size_t dyn_smem = 16 * static_cast<size_t>(heap_entries);
   const bool all_smem = heap_entries >= NC;
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel<true, PP_PLAN_BATCH_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PP_CUDA(cudaFuncSetAttribute(plan_kernel<false, PP_PLAN_BATCH_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int ctas_per_sm = 1;
   const int threads = n > h->sm_count ? 128 : 256;
   const bool batch = threads == 128;
-  if (all_smem && batch) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<true, PP_PLAN_BATCH_CTAS>, threads, dyn_smem));
-  else if (all_smem) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<true, 0>, threads, dyn_smem));
-  else if (batch) PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<false, PP_PLAN_BATCH_CTAS>, threads, dyn_smem));
-  else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plan_kernel<false, 0>, threads, dyn_smem));
+  // the instantiation this call runs: frontier placement x CTA packing x (plain grid | grid bank)
+  typedef void (*PlanKernel)(PlanArgs);
+  static const PlanKernel kKernels[8] = {
+      plan_kernel<false, 0, false>, plan_kernel<true, 0, false>, plan_kernel<false, PP_PLAN_BATCH_CTAS, false>,
+      plan_kernel<true, PP_PLAN_BATCH_CTAS, false>, plan_kernel<false, 0, true>, plan_kernel<true, 0, true>,
+      plan_kernel<false, PP_PLAN_BATCH_CTAS, true>, plan_kernel<true, PP_PLAN_BATCH_CTAS, true>};
+  const PlanKernel kernel = kKernels[(all_smem ? 1 : 0) + (batch ? 2 : 0) + (banked ? 4 : 0)];
+  PP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, threads, dyn_smem));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_ctas = h->sm_count * ctas_per_sm;
   const int grid = std::min(n, max_ctas);
@@ -1258,10 +1263,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   }
 
   PP_CUDA(cudaEventRecord(h->ev[8], s));
-  if (all_smem && batch) plan_kernel<true, PP_PLAN_BATCH_CTAS><<<grid, threads, dyn_smem, s>>>(A);
-  else if (all_smem) plan_kernel<true, 0><<<grid, threads, dyn_smem, s>>>(A);
-  else if (batch) plan_kernel<false, PP_PLAN_BATCH_CTAS><<<grid, threads, dyn_smem, s>>>(A);
-  else plan_kernel<false, 0><<<grid, threads, dyn_smem, s>>>(A);
+  kernel<<<grid, threads, dyn_smem, s>>>(A);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   bool want_parent = false;

@@ -597,6 +597,7 @@ def bench_costmap(args):
         out["global_road_map"] = g
         out["stack_rollout"] = bench_stack(args, z)
         out["stack_rollout_oriented_corridor"] = bench_stack(args, z, oriented=True)
+        out["sweep_256_cars_own_costmaps"] = bench_sweep(args)
     out["route_rollouts"] = bench_rollouts(args)
     return out
 
@@ -703,6 +704,49 @@ def bench_stack(args, edges, cycles=150, oriented=False):
             "ms_cycle": med(tot), "cycles_per_s": float(len(tot) / tot.sum()),
             "note": "20 Hz is the reference's plan rate (local_navigator.py:529); its own nodes need ~20 ms for the "
                     "costmap and 3-5 ms for a free-space plan per cycle on one core each"}
+
+
+def bench_sweep(args, cars=256, ticks=8):
+    """Scenario sweep with sensors in the loop, everything batched: per 20 Hz tick ONE pc_build_batch (all cars'
+    costmaps + region masks), ONE pp_set_grid_bank_dev (all grids' derived maps, fed on the device) and ONE
+    pp_plan_batch_banked (car k plans on grid k with the ORIENTED footprint test)."""
+    import numpy as np
+
+    from autonomouscar_b200 import PP_COLLISION_ORIENTED, PP_PLAN_FOUND, LocalCostmap, Planner, default_params, make_query, worlds
+    from autonomouscar_b200.capi import pp_query
+    from autonomouscar_b200.costmap_capi import default_costmap_params
+    from autonomouscar_b200.results import PlanBatch
+    cm = LocalCostmap(default_costmap_params(), device=0)
+    pl = Planner(default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=20000), device=0)
+    base = []
+    for k in range(16):
+        sc = worlds.corridor_scene(300 + k, half_width=2.5 + 0.25 * (k % 6), gap_at=(9.0 + k, 12.0 + k) if k % 3 == 0 else None)
+        worlds.fill_costmap_tf(sc, (2.0 * k, 0.0, 0.0))
+        base.append(sc)
+    scenes = [base[k % 16] for k in range(cars)]
+    qs = (pp_query * cars)(*[make_query(18.0, 1.2 - 0.3 * (k % 5), start_speed=0.5, grid_index=k, query_id=k) for k in range(cars)])
+    buf = PlanBatch(cars, cap_path=256)
+    t_cost, t_bank, t_plan = [], [], []
+    for k in range(ticks + 2):
+        t0 = time.perf_counter()
+        cm.build_batch(scenes, want_host=False, want_masks=True)
+        t1 = time.perf_counter()
+        cm.feed_planner_bank(pl)
+        t2 = time.perf_counter()
+        pl.plan_batch_into(qs, buf, banked=True)
+        t3 = time.perf_counter()
+        if k >= 2:
+            t_cost.append(t1 - t0); t_bank.append(t2 - t1); t_plan.append(t3 - t2)
+    found = int((buf.field("status") == PP_PLAN_FOUND).sum())
+    rejected = int(buf.field("n_collisions").sum())
+    cm.close()
+    pl.close()
+    med = lambda a: 1e3 * float(np.median(a))                                       # noqa: E731
+    tick = med(np.array(t_cost) + np.array(t_bank) + np.array(t_plan))
+    return {"cars": cars, "collision_mode": "ORIENTED, corridor scenes, one costmap per car", "plans_found": found,
+            "candidate_poses_rejected": rejected, "ms_costmaps": med(t_cost), "ms_grid_bank": med(t_bank),
+            "ms_plans": med(t_plan), "ms_tick": tick, "car_ticks_per_s": cars / (tick / 1e3),
+            "x_real_time_at_20hz": cars / (tick / 1e3) / 20.0 / cars}
 
 
 def bench_plans(pl_unused, rank, world, dev, multi, args):
