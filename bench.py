@@ -720,11 +720,11 @@ def bench_sweep(args, cars=256, ticks=8):
     pl = Planner(default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=20000), device=0)
     base = []
     for k in range(16):
-        sc = worlds.corridor_scene(300 + k, half_width=2.5 + 0.25 * (k % 6), gap_at=(9.0 + k, 12.0 + k) if k % 3 == 0 else None)
+        sc = worlds.corridor_scene(300 + k, half_width=2.5 + 0.1 * (k % 4))       # walls 2.5 .. 2.8 m either side
         worlds.fill_costmap_tf(sc, (2.0 * k, 0.0, 0.0))
         base.append(sc)
     scenes = [base[k % 16] for k in range(cars)]
-    qs = (pp_query * cars)(*[make_query(18.0, 1.2 - 0.3 * (k % 5), start_speed=0.5, grid_index=k, query_id=k) for k in range(cars)])
+    qs = (pp_query * cars)(*[make_query(18.0, 1.4 - 0.7 * (k % 5), start_speed=0.5, grid_index=k, query_id=k) for k in range(cars)])
     buf = PlanBatch(cars, cap_path=256)
     t_cost, t_bank, t_plan = [], [], []
     for k in range(ticks + 2):
