@@ -151,7 +151,8 @@ class RouteRollout {
   }
   // one 20 Hz tick; returns the pp_status of the batch call.  masks (optional, one per car) = the region
   // mask of each car's current costmap (pc_front_regions): enables the navigator's obstacle branch.
-  int tick(const uint32_t* masks = nullptr) {
+  // banked: car k plans on grid k of the planner's grid bank (pp_set_grid_bank_dev) instead of the shared grid.
+  int tick(const uint32_t* masks = nullptr, bool banked = false) {
     const int n = static_cast<int>(cars_.size());
     for (int k = 0; k < n; ++k) {
       const Car& c = cars_[k];
@@ -163,10 +164,11 @@ class RouteRollout {
       pp_query q{};
       q.goal_x = cs * dx + sn * dy; q.goal_y = -sn * dx + cs * dy;            // LP:687-690
       q.goal_speed = wp.speed; q.max_speed = wp.max_speed; q.max_accel = wp.max_accel;   // local_navigator.py:524-527
-      q.start_speed = c.v; q.query_id = static_cast<uint32_t>(k);
+      q.start_speed = c.v; q.query_id = static_cast<uint32_t>(k); q.reserved = static_cast<uint32_t>(k);
       queries_[k] = q;
     }
-    const int rc = pp_plan_batch(h_, n, queries_.data(), results_.data());
+    const int rc = banked ? pp_plan_batch_banked(h_, n, queries_.data(), results_.data())
+                          : pp_plan_batch(h_, n, queries_.data(), results_.data());
     if (rc != PP_OK && rc != PP_ERR_CAPACITY) return rc;
     plans += n;
     for (int k = 0; k < n; ++k) {
