@@ -134,3 +134,44 @@ def test_costmap_batch_feeds_a_grid_bank(oracle, cuda_device):
     cm.close()
     pl.close()
     one.close()
+
+
+def test_bank_fuzz_shapes_and_parameters(oracle, cuda_device):
+    """Random grid shapes (non-square), resolutions, lattice parameters and collision modes: banked plans equal the
+    oracle's plans on the same grids, bit for bit."""
+    import os
+    import torch
+    from autonomouscar_b200 import Planner
+    rng = np.random.default_rng(int(os.environ.get("PP_FUZZ_SEED", "4711")))
+    statuses, collisions = [], 0
+    for case in range(int(os.environ.get("PP_FUZZ_CASES", "8"))):
+        res = float(rng.choice([0.1, 0.2, 0.25, 0.5]))
+        W, H = int(rng.integers(120, 400)), int(rng.integers(120, 400))
+        p = default_params(costmap_res=res, costmap_width=W, costmap_height=H, collision_mode=int(rng.integers(1, 3)),
+                           time_step_ms=float(rng.choice([150.0, 200.0])), velocity_res=float(rng.choice([0.05, 0.1])),
+                           heading_diff=float(rng.choice([0.065, 0.1])), search_res=float(rng.choice([0.1, 0.25])),
+                           max_nodes=int(rng.integers(300, 4000)), max_expansions=int(rng.choice([25, 100000])))
+        n_grids = int(rng.integers(1, 9))
+        grids = []
+        for k in range(n_grids):
+            g = worlds.block_grid(W, H, frac=float(rng.choice([0.0, 0.02, 0.05])), block=int(rng.choice([2, 4, 8])), seed=case * 16 + k)
+            worlds.clear_disc(g, p, 0.0, 0.0, 3.5)
+            grids.append(g)
+        layout = int(rng.choice([PP_GRID_CSPACE, PP_GRID_OCCUPANCY_MSG]))
+        wire = [g.reshape(-1) if layout == PP_GRID_CSPACE else g.reshape(-1)[::-1] for g in grids]
+        bank = torch.from_numpy(np.ascontiguousarray(np.stack(wire))).cuda()
+        pl = Planner(p, device=0)
+        pl.set_grid_bank_dev(bank.data_ptr(), n_grids, layout=layout)
+        extent = min(W, H) * res / 2
+        qs = [make_query(float(rng.uniform(2.0, min(25.0, extent))), float(rng.uniform(-4.0, 4.0)),
+                         goal_speed=float(rng.choice([0.0, 1.5])), start_speed=float(rng.uniform(0.0, 1.5)),
+                         grid_index=int(rng.integers(0, n_grids)), query_id=k) for k in range(6)]
+        for q, got in zip(qs, pl.plan_batch(qs, banked=True)):
+            ref = oracle.plan(p, grids[q.reserved], q, math_mode=oracle.MATH_DET)
+            assert got.summary() == ref.summary(), (case, got.summary(), ref.summary())
+            np.testing.assert_array_equal(got.path_xy, ref.path_xy)
+            np.testing.assert_array_equal(got.yaw_rates, ref.yaw_rates)
+            statuses.append(ref.status)
+            collisions += ref.n_collisions
+        pl.close()
+    assert len(set(statuses)) >= 2 and collisions > 0
