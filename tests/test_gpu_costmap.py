@@ -303,6 +303,19 @@ def test_costmap_parameter_variants_bit_exact(oracle, cuda_device):
         want, _ = oracle.costmap_build(p, sc.inputs, g, math_mode=oracle.MATH_DET)
         np.testing.assert_array_equal(got, want)
         assert (got == 100).sum() > 200
+        # the batched path with these parameters: two more scenes next to this one, masks when the window allows
+        sc2, sc3 = worlds.costmap_scene(600 + k, max_reach=20.0), worlds.corridor_scene(700 + k, half_width=4.0)
+        _fill_tf(sc2, car)
+        _fill_tf(sc3, car)
+        square_enough = hc >= wc
+        grids, masks = cm.build_batch([sc, sc2, sc3], want_masks=square_enough)
+        np.testing.assert_array_equal(grids[0], want)
+        for j, s_ in enumerate((sc2, sc3)):
+            w_j, _ = oracle.costmap_build(p, s_.inputs, g, math_mode=oracle.MATH_DET)
+            np.testing.assert_array_equal(grids[j + 1], w_j)
+            if square_enough:
+                from oracle import navigator_ref
+                assert int(masks[j + 1]) == navigator_ref.region_mask(w_j, int(wc))
         cm.close()
 
 
