@@ -21,13 +21,13 @@ The vehicle itself (Gazebo + the two PIDs of controller.cpp:44-132) is replaced 
 yaw rate and speed are taken from the profile entry under the cursor and integrated at the
 controller's 100 Hz (controller_node.cpp:14).  That stand-in is this repository's, not the
 reference's; everything it feeds -- every LocalNav goal, every plan, every profile -- goes through
-the same code paths as a live system.  The navigator is Python 2 / rospy and cannot be imported
+the same code paths as a live system.  The navigator is a rospy node written for Python 2 and cannot run
 here as a ROS node, but it parses as Python 3: tests/test_navigator_ref_pin.py imports it UNMODIFIED against
 rospy test doubles (oracle/ref_navigator.py) and checks every published LocalNav, the path index and the
 region flags against this mirror (live in this container, committed outputs in tests/golden/ elsewhere).
 The controller (cursor and PIDs) is checked the same way against the reference's own controller.cpp compiled
-unmodified (oracle/_ref/libref_controller.so, tests/test_controller_ref_pin.py); the planner inside the loop is pinned (tests/test_rollout.py
-drives the REFERENCE planner node and the oracle through the same loop).
+unmodified (oracle/_ref/libref_controller.so, tests/test_controller_ref_pin.py); the planner inside the loop is
+pinned (tests/test_rollout.py drives the REFERENCE planner node and the oracle through the same loop).
 
 `plan_batch` is any callable (list of pp_query) -> list of (found, yaw_rates, durations_ms, speeds):
 the CUDA planner (plan_batch_cuda), the oracle or the reference node (tests).
