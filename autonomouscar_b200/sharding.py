@@ -56,3 +56,23 @@ def plan_records(results, device):
     rows = [[r.status, r.n_expansions, r.n_nodes, r.n_path, int(r.tree_digest) & 0x7FFFFFFFFFFFFFFF]
             for r in results]
     return torch.tensor(rows, dtype=torch.int64, device=device).reshape(-1, 5)
+
+
+def rollout_sharded(starts, plan_batch, ticks, device, route=None, masks_of=None, group=None):
+    """Scenario sweep over the ranks (row N4 at N > 1): the cars are independent, so every rank drives its own
+    contiguous block of them (rollout.RouteRollout around ITS planner) with no data-path collective, and the
+    car states after every tick are gathered once at the end.  Returns the [ticks, n_cars, 4] trace in input
+    order on every rank.  `plan_batch` as in rollout.RouteRollout.tick; `masks_of(rollout)` (optional) returns the
+    region masks of the block's costmaps for the coming tick."""
+    from . import rollout
+    starts = [tuple(s) for s in starts]
+    n = len(starts)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    lo, hi = shard_bounds(n, rank, world)
+    ro = rollout.RouteRollout(starts[lo:hi], route=route)
+    for _ in range(ticks):
+        ro.tick(plan_batch, masks_of(ro) if masks_of is not None else None)
+    local = torch.tensor(ro.trace, dtype=torch.float64, device=device).reshape(ticks, hi - lo, 4)
+    # gather_blocks concatenates along dim 0: make the car index the leading dimension
+    return gather_blocks(local.permute(1, 0, 2).contiguous(), n, group=group).permute(1, 0, 2).contiguous()

@@ -49,9 +49,14 @@ def _worker(rank, world, port, n, ret):
         qlo, qhi = sharding.shard_bounds(len(queries), rank, world)
         rec = sharding.plan_records(pl.plan_batch(queries[qlo:qhi]), torch.device("cuda", rank))
         recs = sharding.gather_blocks(rec, len(queries))
+        # row N4 sharded: this rank's block of cars around this rank's planner, states gathered once
+        from autonomouscar_b200 import rollout
+        from test_rollout import _starts
+        trace = sharding.rollout_sharded(_starts(37), rollout.plan_batch_cuda(pl), 5, torch.device("cuda", rank))
         if rank == 0:
             ret["flags"] = flags.cpu().numpy().copy()
             ret["recs"] = recs.cpu().numpy().copy()
+            ret["trace"] = trace.cpu().numpy().copy()
         pl.close()
     finally:
         dist.destroy_process_group()
@@ -74,4 +79,7 @@ def test_nccl_gather_equals_single_gpu(cuda_device):
     want_rec = sharding.plan_records(pl.plan_batch(queries), torch.device("cpu")).numpy()
     np.testing.assert_array_equal(ret["recs"], want_rec)
     assert 0 < want.sum() < n
+    from autonomouscar_b200 import rollout
+    from test_rollout import _starts
+    np.testing.assert_array_equal(ret["trace"], rollout.RouteRollout(_starts(37)).run(rollout.plan_batch_cuda(pl), 5))
     pl.close()

@@ -67,3 +67,34 @@ def test_two_rank_gather_restores_input_order(oracle, n):
     np.testing.assert_array_equal(ret["flags"], want)
     assert 0 < want.sum() < n
     assert ret["rec_ok"] and ret["slow"] == 2.0
+
+
+def _rollout_worker(rank, world, port, n, ticks, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import binding as orc
+        from test_rollout import _oracle_batch, _starts
+        from autonomouscar_b200 import PP_COLLISION_AS_SHIPPED
+        p = default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000)
+        trace = sharding.rollout_sharded(_starts(n), _oracle_batch(orc, p, orc.MATH_DET), ticks, torch.device("cpu"))
+        if rank == 0:
+            ret["trace"] = trace.numpy().copy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_rollout_equals_single_process(oracle):
+    """Cars sharded over two ranks (5 = 3 + 2), each rank driving its own block, states gathered once: the
+    trace equals the single-process roll-out of all five cars."""
+    from test_rollout import _oracle_batch, _starts
+    from autonomouscar_b200 import PP_COLLISION_AS_SHIPPED, rollout
+    n, ticks = 5, 4
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rollout_worker, args=(2, _free_port(), n, ticks, ret), nprocs=2, join=True)
+    p = default_params(collision_mode=PP_COLLISION_AS_SHIPPED, max_nodes=20000)
+    want = rollout.RouteRollout(_starts(n)).run(_oracle_batch(oracle, p, oracle.MATH_DET), ticks)
+    np.testing.assert_array_equal(ret["trace"], want)
+    assert ret["trace"].shape == (ticks, n, 4) and ret["trace"][-1, 0, 0] > ret["trace"][0, 0, 0]
