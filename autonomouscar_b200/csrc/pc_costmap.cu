@@ -18,7 +18,7 @@
 // deterministic ones shared with the oracle.
 //
 // Launch structure: inputs are packed into one pinned block (header | right ranges | left ranges |
-// cloud) and copied with ONE cudaMemcpyAsync; the six kernels have fixed arguments and fixed grids
+// cloud) and copied with ONE cudaMemcpyAsync; the memset and five kernels have fixed arguments and fixed grids
 // (grid-stride loops over counts read from the device header), so the whole pass is one CUDA graph
 // launch.  Work is tiny (9.5 k rays, 90 k cells, 360 k road samples): the bound is launch latency
 // and FP64 issue, not memory.
