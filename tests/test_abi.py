@@ -142,6 +142,13 @@ def test_costmap_argument_errors_do_not_need_a_device(lib):
     assert lib.pg_build(C.byref(g), 0, None, None, 0, None, C.byref(dev)) == 1
     g = default_global_costmap_params(height_cells=1200.5)
     assert lib.pg_build(C.byref(g), 0, None, None, 0, None, C.byref(dev)) == 1 and b"whole numbers" in lib.pp_last_error()
+    # the batched / region-scan / grid-bank entry points refuse null handles before touching CUDA
+    m = C.c_uint32()
+    assert lib.pc_build_batch(None, 1, None, None, None) == 1
+    assert lib.pc_batch_grids_dev(None, C.byref(dev), None) == 1
+    assert lib.pc_front_regions(None, C.byref(m)) == 1 and lib.pc_front_regions_dev(None, None, 300, 90000, C.byref(m)) == 1
+    assert lib.pp_set_grid_bank_dev(None, 1, None, 300, 300, 0.25, 0) == 1
+    assert lib.pp_plan_batch_banked(None, 0, None, None) == 1
     # defaults = launch file (full_sim.launch:68-82)
     c, d = pc_params(), pg_params()
     assert lib.pc_default_params(C.byref(c)) == 0 and lib.pg_default_params(C.byref(d)) == 0
