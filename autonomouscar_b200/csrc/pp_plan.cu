@@ -43,6 +43,8 @@ constexpr int kMaxVel = 64;        // velocities per expansion the kernel suppor
 constexpr int kMaxCand = 8192;     // children per expansion the kernel supports
 constexpr int kIntMax = 0x7fffffff;
 constexpr int kFxMaxPoses = 512;   // longest path the pointer-walk extraction handles (longer: exact scan walk)
+constexpr int kFxTable = 1024;     // slots of its pose table (power of two)
+constexpr unsigned short kFxShared = 0xFFFFu;
 
 struct PlanHdr {                   // per query, device -> host
   int status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions;
@@ -525,8 +527,9 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
   __shared__ unsigned long long s_dig[kWarpsMax];
   __shared__ double s_fcost[2 * kWarpsMax];
   __shared__ int s_fpos[2 * kWarpsMax], s_fcnt[2 * kWarpsMax];
-  __shared__ uint32_t s_ph[kFxMaxPoses];   // hashes of the path poses (pointer-walk extraction)
-  __shared__ uint32_t s_bloom[64];         // 2048-bit filter over them
+  // pointer-walk extraction: direct-mapped table over the path poses' point hashes.  Entry = pose index + 1,
+  // 0 = no pose hashes here, kFxShared = more than one does (those few slots fall back to a scan of the path)
+  __shared__ unsigned short s_ptab[kFxTable];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pp_params& P = A.P;
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         int* sp = reinterpret_cast<int*>(smem_raw);                  // parent slots in the dead frontier's smem
         const bool sp_fits = n_nodes <= A.heap_smem_entries * 4;
         if (sp_fits) for (int id = tid; id < n_nodes; id += kT) sp[id] = w.rev_last[id];
-        if (tid < 64) s_bloom[tid] = 0u;
+        for (int k = tid; k < kFxTable; k += kT) s_ptab[k] = 0;
         __syncthreads();
         if (tid == 0) {
           int id = n_nodes - 1, n = 0, bad = 0;                       // the terminal node was opened last (LP:45)
@@ -887,18 +890,22 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
             const int id = rev_first[k];
             const double x = w.cx[id], y = w.cy[id];
             rev[2 * k] = x; rev[2 * k + 1] = y;
-            const uint32_t h = point_hash32(x, y);
-            s_ph[k] = h;
-            atomicOr(&s_bloom[(h >> 5) & 63], 1u << (h & 31));
+            unsigned short* slot = &s_ptab[point_hash32(x, y) & (kFxTable - 1)];
+            if (atomicCAS(slot, static_cast<unsigned short>(0), static_cast<unsigned short>(k + 1)) != 0) *slot = kFxShared;
           }
           __syncthreads();
           int bad = 0;
           for (int id = tid; id < n_nodes; id += kT) {
             const double x = w.cx[id], y = w.cy[id];
-            const uint32_t h = point_hash32(x, y);
-            if ((s_bloom[(h >> 5) & 63] >> (h & 31)) & 1u) {
+            // equal points hash alike, so only the pose(s) of this node's slot can share its child point
+            const unsigned short e = s_ptab[point_hash32(x, y) & (kFxTable - 1)];
+            if (e == 0) continue;
+            if (e != kFxShared) {
+              const int k = e - 1;
+              if (rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y) bad = 1;
+            } else {
               for (int k = 0; k < n; ++k)
-                if (s_ph[k] == h && rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y) bad = 1;
+                if (rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y) bad = 1;
             }
           }
           // consecutive poses must differ as well (LP:560 `else if`) -- implied by uniqueness, checked anyway
