@@ -310,6 +310,7 @@ struct Shared {
   int tie_seen;    // fast mode: some pop saw its minimum cost on more than one entry
   int top_pos, top_id;
   int fx_len, fx_bad;   // pointer-walk extraction: path length, 1 = cannot be used
+  int fx_slow;          // diagnostics: this query's path was extracted by the exact scan walk
   // fast frontier: the runner-up found by an argmin pass serves the NEXT pop when no push happens in
   // between (planPath pops twice in a row: LP:80, then LP:40 of the next iteration)
   int next_valid, next_pos;
@@ -571,6 +572,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
       S.n_cand_total = 0; S.n_coll_total = 0; S.goal_hit = 0; S.path_len = 0; S.truncated = 0; S.done = 0;
       S.fast = (attempt == 0 && A.fast_frontier) ? 1 : 0;
+      S.fx_slow = 0;
       S.tie_seen = 0; S.top_pos = 0; S.top_id = 0; S.next_valid = 0; S.next_pos = 0; S.chk_valid = 0; S.next_cost = 0; S.chk_cost = 0;
       for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
       if (kBanked) S.gq = grid_at(A.g, A.bank, qq.reserved);
@@ -917,6 +919,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         __syncthreads();
       }
       if (!fast_walk) {
+      if (tid == 0) S.fx_slow = 1;
       // restore the slow path's scratch: w.rev_last is plain scratch from here on
       // a 32-bit hash of every child point fits the (dead) frontier's shared memory even in
       // batch mode; the scans below read it instead of the 16-byte points in L2 and verify
@@ -932,17 +935,31 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       auto scan3 = [&](double x, double y, int from, int* k_from, int* k_first, int* k_last) {
         int bf = kIntMax, b0 = kIntMax, bl = -1;
         const uint32_t want = point_hash32(x, y);
-        for (int id = tid; id < n_nodes; id += kT) {
-          bool eq;
-          if (sh32) eq = sh32[id] == want && w.cx[id] == x && w.cy[id] == y;
-          else eq = w.cx[id] == x && w.cy[id] == y;
-          if (eq) {
+        auto consider = [&](int id) {                   // hash hit (or no hashes): the real coordinates decide
+          if (w.cx[id] == x && w.cy[id] == y) {
             const int cs = w.closed_seq[id];
             const int key = cs < 0 ? id : n_nodes + cs;
             b0 = min(b0, key);
             bl = max(bl, key);
             if (key >= from) bf = min(bf, key);
           }
+        };
+        // four hashes per 128-bit shared load -- only where registers are plentiful: in the 80-register batch
+        // instantiation the wider loop spills and costs 4 % overall (measured), so it keeps the scalar scan
+        if (kBatchCtas == 0 && sh32) {
+          const uint4* sh4 = reinterpret_cast<const uint4*>(sh32);
+          for (int id = 4 * tid; id < n_nodes; id += 4 * kT) {
+            const uint4 v = sh4[id >> 2];
+            if (v.x == want) consider(id);
+            if (v.y == want && id + 1 < n_nodes) consider(id + 1);
+            if (v.z == want && id + 2 < n_nodes) consider(id + 2);
+            if (v.w == want && id + 3 < n_nodes) consider(id + 3);
+          }
+        } else if (sh32) {
+          for (int id = tid; id < n_nodes; id += kT)
+            if (sh32[id] == want) consider(id);
+        } else {
+          for (int id = tid; id < n_nodes; id += kT) consider(id);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -1050,7 +1067,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       hd.n_collisions = S.n_coll_total;
       hd.truncated = S.truncated;
       hd.reran = (!S.fast && A.fast_frontier) ? 1 : 0;
-      hd.pad_ = 0;
+      hd.pad_ = S.fx_slow;
       hd.pool_off = S.status == PP_PLAN_FOUND ? S.pool_off : 0;
       hd.digest = d;
       if (A.timing) { const long long now_ = clock64(); S.cyc[6] += now_ - t_mark; S.cyc[7] = now_ - t_begin; }
@@ -1314,6 +1331,9 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
     int reruns = 0;
     for (int k = 0; k < n; ++k) reruns += hdr[k].reran;
     fprintf(stderr, "[pp_plan] exact-heap re-runs (cost ties): %d of %d queries\n", reruns, n);
+    int slow = 0, found = 0;
+    for (int k = 0; k < n; ++k) { slow += hdr[k].pad_; found += hdr[k].status == PP_PLAN_FOUND; }
+    fprintf(stderr, "[pp_plan] paths extracted by the exact scan walk: %d of %d found plans\n", slow, found);
   }
   const double* hpath = reinterpret_cast<const double*>(hb + hdr_b + cnt_b);
   const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + cnt_b + path_b);
