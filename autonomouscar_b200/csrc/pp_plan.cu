@@ -896,7 +896,15 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
             if (atomicCAS(slot, static_cast<unsigned short>(0), static_cast<unsigned short>(k + 1)) != 0) *slot = kFxShared;
           }
           __syncthreads();
-          int bad = 0;
+          // One shared point is part of the common case: a goal hit at i = 0 (LP:276-283) makes the terminal
+          // node T a copy of the popped node N's child point, so the chain starts T, N with identical poses and
+          // that point has two owners.  The reference then walks T (open list, scanned first) -> N (closed list)
+          // -> N's parent, i.e. exactly the chain; first match = T and last match = N for both poses.  Any OTHER
+          // node on that point, or any other shared pose, still sends the query to the exact scan walk.
+          const bool goal_dup = n >= 2 && rev[0] == rev[2] && rev[1] == rev[3];
+          const int id_t = rev_first[0], id_n = n >= 2 ? rev_first[1] : -1;
+          // (a goal hit on the start node itself ends the reference's walk before it begins, LP:509: scan walk)
+          int bad = (goal_dup && rev[0] == 0.0 && rev[1] == 0.0) ? 1 : 0;
           for (int id = tid; id < n_nodes; id += kT) {
             const double x = w.cx[id], y = w.cy[id];
             // equal points hash alike, so only the pose(s) of this node's slot can share its child point
@@ -907,19 +915,31 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
               if (rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y) bad = 1;
             } else {
               for (int k = 0; k < n; ++k)
-                if (rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y) bad = 1;
+                if (rev_first[k] != id && rev[2 * k] == x && rev[2 * k + 1] == y &&
+                    !(goal_dup && k < 2 && (id == id_t || id == id_n)))
+                  bad = 1;
             }
           }
           // consecutive poses must differ as well (LP:560 `else if`) -- implied by uniqueness, checked anyway
-          for (int k = tid; k + 1 < n; k += kT)
+          for (int k = tid + (goal_dup ? 1 : 0); k + 1 < n; k += kT)
             if (rev[2 * k] == rev[2 * k + 2] && rev[2 * k + 1] == rev[2 * k + 3]) bad = 1;
           bad = block_max(bad, s_red);
-          if (!bad) { fast_walk = true; len = n; rev_last = rev_first; }
+          if (!bad) {
+            fast_walk = true;
+            len = n;
+            if (!goal_dup) {
+              rev_last = rev_first;
+            } else {                                   // first / last match per pose as the scans would find them
+              for (int k = tid; k < n; k += kT) rev_last[k] = k < 2 ? id_n : rev_first[k];
+              __syncthreads();
+              if (tid == 0) rev_first[1] = id_t;
+            }
+          }
         }
         __syncthreads();
       }
       if (!fast_walk) {
-      if (tid == 0) S.fx_slow = 1;
+      if (tid == 0) S.fx_slow = S.fx_bad ? 1 : 2;
       // restore the slow path's scratch: w.rev_last is plain scratch from here on
       // a 32-bit hash of every child point fits the (dead) frontier's shared memory even in
       // batch mode; the scans below read it instead of the 16-byte points in L2 and verify
@@ -1331,9 +1351,9 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
     int reruns = 0;
     for (int k = 0; k < n; ++k) reruns += hdr[k].reran;
     fprintf(stderr, "[pp_plan] exact-heap re-runs (cost ties): %d of %d queries\n", reruns, n);
-    int slow = 0, found = 0;
-    for (int k = 0; k < n; ++k) { slow += hdr[k].pad_; found += hdr[k].status == PP_PLAN_FOUND; }
-    fprintf(stderr, "[pp_plan] paths extracted by the exact scan walk: %d of %d found plans\n", slow, found);
+    int slow = 0, slow_dup = 0, found = 0;
+    for (int k = 0; k < n; ++k) { slow += hdr[k].pad_ != 0; slow_dup += hdr[k].pad_ == 2; found += hdr[k].status == PP_PLAN_FOUND; }
+    fprintf(stderr, "[pp_plan] paths extracted by the exact scan walk: %d of %d found plans (%d because a path pose is shared by two nodes)\n", slow, found, slow_dup);
   }
   const double* hpath = reinterpret_cast<const double*>(hb + hdr_b + cnt_b);
   const int* hpid = reinterpret_cast<const int*>(hb + hdr_b + cnt_b + path_b);
