@@ -143,6 +143,13 @@ __device__ __forceinline__ unsigned long long key_fingerprint(const double k[6])
 __device__ __forceinline__ uint32_t point_hash32(double x, double y) {
   return static_cast<uint32_t>(mix64(dbits(__dadd_rn(x, 0.0)) ^ mix64(dbits(__dadd_rn(y, 0.0)))) >> 32);
 }
+// slot of a point in the pointer-walk extraction's pose table: equal points (== on doubles, so -0.0 and +0.0
+// alike) must land in the same slot, nothing more -- a few shifted xors of the raw bits instead of two mix64
+__device__ __forceinline__ uint32_t point_slot(double x, double y, uint32_t mask) {
+  const unsigned long long a = dbits(__dadd_rn(x, 0.0)), b = dbits(__dadd_rn(y, 0.0));
+  const unsigned long long m = (a ^ (a >> 23)) + (b ^ (b >> 17)) * 0x9E3779B1ull;
+  return static_cast<uint32_t>(m ^ (m >> 29)) & mask;
+}
 // tree digest term of pp_result.tree_digest (same as oracle/planner_ref.h node_digest)
 __device__ __forceinline__ unsigned long long node_digest(int id, const double k[6]) {
   unsigned long long h = static_cast<unsigned long long>(id) + 1ull;
@@ -892,7 +899,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
             const int id = rev_first[k];
             const double x = w.cx[id], y = w.cy[id];
             rev[2 * k] = x; rev[2 * k + 1] = y;
-            unsigned short* slot = &s_ptab[point_hash32(x, y) & (kFxTable - 1)];
+            unsigned short* slot = &s_ptab[point_slot(x, y, kFxTable - 1)];
             if (atomicCAS(slot, static_cast<unsigned short>(0), static_cast<unsigned short>(k + 1)) != 0) *slot = kFxShared;
           }
           __syncthreads();
@@ -908,7 +915,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
           for (int id = tid; id < n_nodes; id += kT) {
             const double x = w.cx[id], y = w.cy[id];
             // equal points hash alike, so only the pose(s) of this node's slot can share its child point
-            const unsigned short e = s_ptab[point_hash32(x, y) & (kFxTable - 1)];
+            const unsigned short e = s_ptab[point_slot(x, y, kFxTable - 1)];
             if (e == 0) continue;
             if (e != kFxShared) {
               const int k = e - 1;
