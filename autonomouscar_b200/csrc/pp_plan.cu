@@ -523,9 +523,13 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
 // kBatchCtas > 0: the batch build -- 128 threads per CTA and a register budget that lets
 // kBatchCtas CTAs share an SM (each query is latency-bound on its own; throughput comes from
 // overlapping many of them).  0: the lone-query build, 256 threads, no register cap.
-#ifndef PP_PLAN_BATCH_CTAS
+// Two batch builds (measured on B200, profiles/README.md): while all queries fit one wave of 6 CTAs per SM the
+// 80-register build is faster (fewer spills, 5-8 %); beyond that the 64-register build with 8 CTAs per SM wins by
+// 6-22 %: the queries are latency-bound, so more of them in flight per SM pays, and the last wave is fuller.
 #define PP_PLAN_BATCH_CTAS 6
-#endif
+#define PP_PLAN_BATCH_HEAP 2048        // frontier entries a CTA of that build keeps in shared memory (32 KB)
+#define PP_PLAN_BATCH_CTAS_WIDE 8
+#define PP_PLAN_BATCH_HEAP_WIDE 1280   // 20 KB
 template <bool kAllSmem, int kBatchCtas, bool kBanked>
 __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchCtas : 1) plan_kernel(PlanArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1227,7 +1231,9 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   // other's serial heap phases.
   const int smem_cap_entries = 200 * 1024 / 16;
   int heap_entries = std::min(NC, smem_cap_entries);
-  if (n >= 2 * h->sm_count) heap_entries = std::min(heap_entries, 2048);
+  const bool wide = n > PP_PLAN_BATCH_CTAS * h->sm_count;          // more than one wave of the 6-CTA build
+  if (wide) heap_entries = std::min(heap_entries, PP_PLAN_BATCH_HEAP_WIDE);
+  else if (n >= 2 * h->sm_count) heap_entries = std::min(heap_entries, PP_PLAN_BATCH_HEAP);
   else if (n > h->sm_count) heap_entries = std::min(heap_entries, 6144);
   const size_t dyn_smem = 16 * static_cast<size_t>(heap_entries);
   const bool all_smem = heap_entries >= NC;
@@ -1236,11 +1242,14 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   const bool batch = threads == 128;
   // the instantiation this call runs: frontier placement x CTA packing x (plain grid | grid bank)
   typedef void (*PlanKernel)(PlanArgs);
-  static const PlanKernel kKernels[8] = {
-      plan_kernel<false, 0, false>, plan_kernel<true, 0, false>, plan_kernel<false, PP_PLAN_BATCH_CTAS, false>,
-      plan_kernel<true, PP_PLAN_BATCH_CTAS, false>, plan_kernel<false, 0, true>, plan_kernel<true, 0, true>,
-      plan_kernel<false, PP_PLAN_BATCH_CTAS, true>, plan_kernel<true, PP_PLAN_BATCH_CTAS, true>};
-  const PlanKernel kernel = kKernels[(all_smem ? 1 : 0) + (batch ? 2 : 0) + (banked ? 4 : 0)];
+  static const PlanKernel kKernels[12] = {
+      plan_kernel<false, 0, false>, plan_kernel<true, 0, false>,
+      plan_kernel<false, PP_PLAN_BATCH_CTAS, false>, plan_kernel<true, PP_PLAN_BATCH_CTAS, false>,
+      plan_kernel<false, PP_PLAN_BATCH_CTAS_WIDE, false>, plan_kernel<true, PP_PLAN_BATCH_CTAS_WIDE, false>,
+      plan_kernel<false, 0, true>, plan_kernel<true, 0, true>,
+      plan_kernel<false, PP_PLAN_BATCH_CTAS, true>, plan_kernel<true, PP_PLAN_BATCH_CTAS, true>,
+      plan_kernel<false, PP_PLAN_BATCH_CTAS_WIDE, true>, plan_kernel<true, PP_PLAN_BATCH_CTAS_WIDE, true>};
+  const PlanKernel kernel = kKernels[(all_smem ? 1 : 0) + (batch ? (wide ? 4 : 2) : 0) + (banked ? 6 : 0)];
   PP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, threads, dyn_smem));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
