@@ -118,6 +118,24 @@ def run(route_xy, passes):
         return _drive(rospy, passes, mod.LocalNavigator, snapshot)      # the node's life is its constructor
 
 
+PATH_PLANNER_FILE = "/root/reference/catkin_ws/src/global_navigator/src/global_path_planner.py"
+
+
+def reference_route(passes=2):
+    """The /path messages the reference's global_path_planner.py publishes (its talker() run for `passes` loop
+    passes against the doubles): list of [(x, y), ...], one per message."""
+    with _doubles():
+        import rospy
+        rospy.state.reset()
+        rospy.state.script = [[] for _ in range(max(passes - 1, 0))]
+        spec = importlib.util.spec_from_file_location("reference_global_path_planner", PATH_PLANNER_FILE)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.talker()
+        return [[(ps.pose.position.x, ps.pose.position.y) for ps in fields["poses"]]
+                for _k, topic, fields in rospy.state.published if topic == "path"]
+
+
 def run_shim(shim_file, route_xy, passes, device=0):
     """The same script through this repository's drop-in node (ros/local_navigator_b200.py), run UNCHANGED
     against the same rospy doubles.  Needs a GPU (the shim scans costmaps on the device)."""

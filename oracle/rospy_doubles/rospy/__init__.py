@@ -41,6 +41,17 @@ def init_node(*_a, **_k):
     pass
 
 
+class Time:
+    """rospy.Time.now(): the double's clock is the number of loop passes so far."""
+
+    def __init__(self, secs=0.0):
+        self.secs = secs
+
+    @staticmethod
+    def now():
+        return Time(float(state.passes))
+
+
 def is_shutdown():
     return state.passes > len(state.script)
 

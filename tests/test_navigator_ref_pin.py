@@ -140,3 +140,19 @@ def test_native_navigator_reproduces_reference_fixture(tmp_path):
         pub = np.where(rows[:, :1] == 1, rows[:, 1:6], np.nan)
         assert_same((pub, rows[:, 6:20].astype(np.int32), rows[:, 20:23]),
                     (z[f"s{seed}_pub"], z[f"s{seed}_state"], z[f"s{seed}_avoid"]))
+
+
+def test_route_constants_are_what_the_reference_publishes():
+    """worlds.ROUTE_X / ROUTE_Y (the way-points every roll-out, bench and golden script starts from) against the
+    /path message of the reference's own global_path_planner.py, run against the rospy doubles; then the whole
+    chain reference path planner -> reference navigator against the mirror fed from the constants."""
+    from autonomouscar_b200 import worlds
+    from oracle import ref_navigator as rn
+    if not rn.available():
+        pytest.skip("needs /root/reference")
+    msgs = rn.reference_route(passes=3)
+    assert len(msgs) == 3 and msgs[0] == msgs[1] == msgs[2]
+    assert msgs[0] == list(zip(worlds.ROUTE_X, worlds.ROUTE_Y)) == [tuple(p) for p in mng.route()]
+    _, passes = mng.scenario(55)
+    want = mng.pack(*mng.run_reference(msgs[0], passes))          # the reference planner's route into the reference navigator
+    assert_same(drive_mirror(mng.route(), passes), want)
