@@ -277,3 +277,42 @@ def test_oracle_matches_live_reference_on_random_parameters(oracle):
         outcomes.add(o.status)
         node.close()
     assert outcomes == {PP_PLAN_FOUND, PP_PLAN_CAP}
+
+
+def test_default_footprint_is_the_references_urdf():
+    """setupCollision (LP:328-360) reads the footprint from the URDF through tf: car length = |dx| of
+    tf(front_right_middle_sonar_link -> back_right_middle_sonar_link), car width = |dx| of
+    tf(rear_right_wheel -> rear_left_wheel).  Re-derived here from the reference's own prius.urdf; the build's
+    defaults (4.7 x 1.586) are those numbers, and the 2e-8 m the sonar's yaw of 1.5707 (not pi/2) takes off the
+    length never moves a cell boundary of the REF_AABB box (LP:473-476)."""
+    import math
+    import xml.etree.ElementTree as ET
+    urdf = "/root/reference/catkin_ws/src/prius_description/urdf/prius.urdf"
+    if not os.path.exists(urdf):
+        pytest.skip("needs /root/reference")
+    joints = {}
+    for j in ET.parse(urdf).getroot().iter("joint"):
+        o = j.find("origin")
+        if o is not None and j.find("child") is not None:
+            joints[j.find("child").get("link")] = (j.find("parent").get("link"),
+                                                   [float(v) for v in o.get("xyz").split()],
+                                                   [float(v) for v in (o.get("rpy") or "0 0 0").split()])
+
+    def in_frame_of(a, b):
+        """origin of link b in the frame of link a (both fixed to the chassis, yaw-only rotations)"""
+        (pa, xa, ra), (pb, xb, rb) = joints[a], joints[b]
+        assert pa == pb == "chassis" and ra[:2] == [0.0, 0.0] and rb[:2] == [0.0, 0.0]
+        dx, dy = xb[0] - xa[0], xb[1] - xa[1]
+        c, s = math.cos(ra[2]), math.sin(ra[2])
+        return c * dx + s * dy, -s * dx + c * dy            # R_a^T (p_b - p_a)
+    from autonomouscar_b200 import default_params
+    length = abs(in_frame_of("front_right_middle_sonar_link", "back_right_middle_sonar_link")[0])
+    width = abs(in_frame_of("rear_right_wheel", "rear_left_wheel")[0])
+    p = default_params()
+    assert width == p.car_width == 1.586
+    assert abs(length - p.car_length) < 1e-7 and p.car_length == 4.7
+    for res in (0.25, 0.1):
+        for base in range(0, 8192):
+            for ext_ref, ext in ((length, p.car_length), (width, p.car_width)):
+                assert int(base - ext_ref / 2 / res) == int(base - ext / 2 / res)
+                assert int(base + ext_ref / 2 / res) == int(base + ext / 2 / res)
