@@ -316,3 +316,38 @@ def test_default_footprint_is_the_references_urdf():
             for ext_ref, ext in ((length, p.car_length), (width, p.car_width)):
                 assert int(base - ext_ref / 2 / res) == int(base - ext / 2 / res)
                 assert int(base + ext_ref / 2 / res) == int(base + ext / 2 / res)
+
+
+def test_library_defaults_are_the_references_launch_file():
+    """pp_default_params / pc_default_params / pg_default_params against the <param> values of the reference's own
+    full_sim.launch (parsed here, not copied)."""
+    import xml.etree.ElementTree as ET
+    launch = "/root/reference/catkin_ws/src/prius_sim/launch/full_sim.launch"
+    if not os.path.exists(launch):
+        pytest.skip("needs /root/reference")
+    from autonomouscar_b200 import default_params
+    from autonomouscar_b200.costmap_capi import default_costmap_params, default_global_costmap_params
+    val = {}
+    for node in ET.parse(launch).getroot().iter("node"):
+        for prm in node.findall("param"):
+            if prm.get("value") is not None:
+                val[(node.get("name"), prm.get("name"))] = prm.get("value")
+    f = lambda node, name: float(val[(node, name)])                                   # noqa: E731
+    p, c, g = default_params(), default_costmap_params(), default_global_costmap_params()
+    lp = "local_planner_node"
+    for ours, theirs in ((p.time_step_ms, "time_step_ms"), (p.velocity_res, "velocity_res"), (p.heading_res, "heading_res"),
+                         (p.heading_diff, "heading_diff"), (p.goal_pos_tolerance, "goal_pos_tolerance"),
+                         (p.goal_speed_tolerance, "goal_speed_tolerance"), (p.search_res, "search_res"),
+                         (p.collision_buffer_distance, "collision_buffer_distance")):
+        assert ours == f(lp, theirs), theirs
+    lc = "local_costmap_node"
+    res = f(lc, "local_costmap_res")
+    assert p.costmap_res == c.res == g.res == res
+    assert p.costmap_height == c.height_cells == f(lc, "local_costmap_height") / res          # LC:20-21, LP:401-417
+    assert p.costmap_width == c.width_cells == f(lc, "local_costmap_width") / res
+    assert (c.z_ground_buffer, c.obstacle_range, c.max_inflation_radius) == (f(lc, "z_ground_buffer"), f(lc, "obstacle_range"),
+                                                                             f(lc, "max_inflation_radius"))
+    gc = "global_costmap_node"
+    assert g.road_width == f(gc, "road_width") and g.num_lanes == int(f(gc, "num_lanes"))
+    assert g.height_cells == c.global_height_cells == f(gc, "global_costmap_height") / res      # GC:14-15, LC:25-26
+    assert g.width_cells == c.global_width_cells == f(gc, "global_costmap_width") / res
