@@ -7,7 +7,7 @@ include/prius_planner.h, prius_costmap.h), the ctypes bindings (`planner.Planner
 bench (`worlds`).
 """
 from .capi import *  # noqa: F401,F403  (enums, structs, default_params, make_query)
-from .results import PlanBatch, PlanResult  # noqa: F401
+from .results import PlanBatch, PlanRecords, PlanResult  # noqa: F401
 
 
 def __getattr__(name):

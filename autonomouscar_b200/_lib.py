@@ -22,6 +22,8 @@ EXPORTS = [
     "pp_rrt_plan_batch", "pp_get_visited", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
     "pp_last_narrow_count", "pp_bench_l2_gather", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
     "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch", "pp_set_grid_bank_dev", "pp_plan_batch_banked",
+    "pp_pack_flags_dev", "pp_unpack_flags_dev", "pp_plan_record_stride", "pp_plan_batch_dev", "pp_plan_records_unpack",
+    "pp_group_records_dev",
 ]
 # every symbol include/prius_costmap.h declares (row N2)
 COSTMAP_EXPORTS = [
@@ -62,6 +64,8 @@ def load():
     L.pp_collide_batch.argtypes = [vp, i64, vp, vp]
     L.pp_collide_batch_dev.argtypes = [vp, i64, vp, vp]
     L.pp_collide_edges_dev.argtypes = [vp, i64, vp, vp]
+    L.pp_pack_flags_dev.argtypes = [vp, i64, vp, vp]
+    L.pp_unpack_flags_dev.argtypes = [vp, i64, vp, vp]
     L.pp_footprint_points.argtypes = [vp, f64, f64, f64, vp, i32, C.POINTER(i32)]
     L.pp_sample_poses_dev.argtypes = [vp, u64, u32, u64, i64, f32, f32, f32, f32, vp]
     L.pp_philox4x32_10.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
@@ -70,6 +74,11 @@ def load():
     L.pp_plan.argtypes = [vp, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_plan_batch_banked.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]
+    L.pp_plan_record_stride.argtypes = [i32]
+    L.pp_plan_record_stride.restype = C.c_size_t
+    L.pp_plan_batch_dev.argtypes = [vp, i32, C.POINTER(pp_query), i32, vp]
+    L.pp_plan_records_unpack.argtypes = [vp, i32, i32, C.POINTER(pp_result)]
+    L.pp_group_records_dev.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.pp_set_grid_bank_dev.argtypes = [vp, i32, vp, i32, i32, f64, C.c_int]
     L.pp_rrt_plan.argtypes = [vp, C.POINTER(pp_query), C.POINTER(pp_result)]
     L.pp_rrt_plan_batch.argtypes = [vp, i32, C.POINTER(pp_query), C.POINTER(pp_result)]

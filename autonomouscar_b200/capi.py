@@ -44,7 +44,8 @@ class pp_params(C.Structure):
         ("rrt_max_samples", C.c_int32),
         ("rrt_goal_bias", C.c_double),
         ("rrt_goal_tolerance", C.c_double),
-        ("reserved", C.c_int32 * 8),
+        ("goal_test_int_abs", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

@@ -3,6 +3,7 @@
 // Everything here is argument checking, memory staging and stream / event plumbing; the
 // arithmetic lives in the kernels.  There is no CPU fallback: without a CUDA device
 // pp_create fails.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -85,6 +86,21 @@ int pp_default_params(pp_params* p) {
   return PP_OK;
 }
 
+static int create_resources(pp_handle* h) {
+  cudaDeviceProp prop;
+  PP_CUDA(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  PP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  PP_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  PP_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) PP_CUDA(cudaEventCreate(&ev));
+  PP_CUDA(cudaMalloc(&h->d_count, 64));
+  PP_CUDA(cudaMemset(h->d_count, 0, 64));
+  PP_CUDA(cudaMallocHost(&h->h_count, 64));
+  std::memset(h->h_count, 0, 64);
+  return PP_OK;
+}
+
 int pp_create(const pp_params* params, int device, pp_handle** out) {
   if (!params || !out) { set_last_error("pp_create: null argument"); return PP_ERR_INVALID; }
   *out = nullptr;
@@ -114,17 +130,11 @@ int pp_create(const pp_params* params, int device, pp_handle** out) {
   h->grid.W = params->costmap_width;
   h->grid.H = params->costmap_height;
   h->grid.res = params->costmap_res;
-  cudaDeviceProp prop;
-  PP_CUDA(cudaGetDeviceProperties(&prop, device));
-  h->sm_count = prop.multiProcessorCount;
-  PP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  PP_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  PP_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
-  for (auto& ev : h->ev) PP_CUDA(cudaEventCreate(&ev));
-  PP_CUDA(cudaMalloc(&h->d_count, 64));
-  PP_CUDA(cudaMemset(h->d_count, 0, 64));
-  PP_CUDA(cudaMallocHost(&h->h_count, 64));
-  std::memset(h->h_count, 0, 64);
+  const int rc = create_resources(h);
+  if (rc != PP_OK) {          // streams / events / buffers created so far are released again
+    pp_destroy(h);
+    return rc;
+  }
   *out = h;
   return PP_OK;
 }
@@ -132,7 +142,7 @@ int pp_create(const pp_params* params, int device, pp_handle** out) {
 int pp_destroy(pp_handle* h) {
   if (!h) return PP_OK;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   plan_free(h);
   rrt_free(h);
   grid_free(h);
@@ -141,7 +151,7 @@ int pp_destroy(pp_handle* h) {
   cudaFree(h->d_visited);
   cudaFree(h->d_nn_best);
   cudaFree(h->d_count);
-  cudaFreeHost(h->h_count);
+  if (h->h_count) cudaFreeHost(h->h_count);
   cudaFree(h->scratch);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -166,12 +176,19 @@ int pp_set_collision_mode(pp_handle* h, int mode) {
   return PP_OK;
 }
 
+// nav_msgs/MapMetaData.resolution is float32: a launch-file 0.1 arrives as 0.100000001490116.  The reference
+// never looks at the message's resolution at all (LP:425-435 uses its own parameter), so the check only
+// guards against a grid of a different scale: equal as float32, or within 1e-6 relative.
+static bool same_resolution(double res, double want) {
+  return static_cast<float>(res) == static_cast<float>(want) || std::fabs(res - want) <= 1e-6 * std::fabs(want);
+}
+
 static int set_grid_common(pp_handle* h, const int8_t* data, bool on_device, int32_t width, int32_t height,
                            double res, int layout) {
   if (!h || !data) { set_last_error("pp_set_grid: null argument"); return PP_ERR_INVALID; }
   PP_REQUIRE(width == h->P.costmap_width && height == h->P.costmap_height,
              "pp_set_grid: width/height differ from the handle's costmap_width/height");
-  PP_REQUIRE(res == h->P.costmap_res, "pp_set_grid: res differs from the handle's costmap_res");
+  PP_REQUIRE(same_resolution(res, h->P.costmap_res), "pp_set_grid: res differs from the handle's costmap_res");
   PP_REQUIRE(layout == PP_GRID_OCCUPANCY_MSG || layout == PP_GRID_CSPACE, "pp_set_grid: bad layout");
   PP_CUDA(cudaSetDevice(h->device));
   return grid_upload(h, data, on_device, layout);
@@ -264,6 +281,19 @@ int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* 
   return PP_OK;
 }
 
+int pp_pack_flags_dev(pp_handle* h, int64_t n, const uint8_t* flags_dev, uint32_t* out_bits_dev) {
+  if (!h) return PP_ERR_INVALID;
+  PP_REQUIRE(n >= 0 && (n == 0 || (flags_dev && out_bits_dev)), "pp_pack_flags_dev: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  return pack_flags_dev(h, n, flags_dev, out_bits_dev);
+}
+int pp_unpack_flags_dev(pp_handle* h, int64_t n, const uint32_t* bits_dev, uint8_t* out_flags_dev) {
+  if (!h) return PP_ERR_INVALID;
+  PP_REQUIRE(n >= 0 && (n == 0 || (bits_dev && out_flags_dev)), "pp_unpack_flags_dev: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  return unpack_flags_dev(h, n, bits_dev, out_flags_dev);
+}
+
 int pp_collide_edges_dev(pp_handle* h, int64_t n, const float* edges_dev, uint8_t* out_flags_dev) {
   int rc = require_grid(h, "pp_collide_edges_dev");
   if (rc) return rc;
@@ -333,7 +363,7 @@ int pp_set_grid_bank_dev(pp_handle* h, int32_t n, const int8_t* grids_dev, int32
                          int layout) {
   if (!h) return PP_ERR_INVALID;
   PP_REQUIRE(n >= 1 && n <= 65535 && grids_dev, "pp_set_grid_bank_dev: 1 <= n <= 65535 grids on the device");
-  PP_REQUIRE(width == h->P.costmap_width && height == h->P.costmap_height && res == h->P.costmap_res,
+  PP_REQUIRE(width == h->P.costmap_width && height == h->P.costmap_height && same_resolution(res, h->P.costmap_res),
              "pp_set_grid_bank_dev: grid shape differs from the handle's parameters");
   PP_REQUIRE(layout == PP_GRID_OCCUPANCY_MSG || layout == PP_GRID_CSPACE, "pp_set_grid_bank_dev: unknown layout");
   return grid_bank_upload(h, n, grids_dev, layout);
@@ -360,6 +390,51 @@ int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* r
   if (n == 0) return PP_OK;
   PP_CUDA(cudaSetDevice(h->device));
   return plan_batch(h, n, queries, results);
+}
+
+size_t pp_plan_record_stride(int32_t cap_path) {
+  if (cap_path < 0) return 0;
+  return (sizeof(pp_plan_record_header) + static_cast<size_t>(cap_path) * 44 + 15) & ~size_t(15);
+}
+
+int pp_plan_batch_dev(pp_handle* h, int32_t n, const pp_query* queries_host, int32_t cap_path, void* out_records_dev) {
+  int rc = require_grid(h, "pp_plan_batch_dev");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (queries_host && out_records_dev)), "pp_plan_batch_dev: bad arguments");
+  PP_REQUIRE((reinterpret_cast<uintptr_t>(out_records_dev) & 15) == 0, "pp_plan_batch_dev: records must be 16-byte aligned");
+  if (n == 0) return PP_OK;
+  PP_CUDA(cudaSetDevice(h->device));
+  return plan_batch(h, n, queries_host, nullptr, false, static_cast<unsigned char*>(out_records_dev), cap_path);
+}
+
+// host helper: records (host memory, e.g. a copy of the gathered device block) -> the caller's pp_result arrays
+int pp_plan_records_unpack(const void* records_host, int32_t n, int32_t cap_path, pp_result* results) {
+  PP_REQUIRE(n >= 0 && cap_path >= 0 && (n == 0 || (records_host && results)), "pp_plan_records_unpack: bad arguments");
+  const size_t stride = pp_plan_record_stride(cap_path);
+  int ret = PP_OK;
+  for (int32_t k = 0; k < n; ++k) {
+    const unsigned char* rec = static_cast<const unsigned char*>(records_host) + stride * k;
+    pp_plan_record_header hd;
+    std::memcpy(&hd, rec, sizeof(hd));
+    pp_result& r = results[k];
+    PP_REQUIRE(r.cap_path >= 0, "pp_plan_records_unpack: negative capacity in a pp_result");
+    r.status = hd.status; r.n_expansions = hd.n_expansions; r.n_nodes = hd.n_nodes; r.n_open = hd.n_open;
+    r.n_closed = hd.n_closed; r.n_path = hd.n_path; r.n_profile = hd.n_profile; r.n_candidates = hd.n_candidates;
+    r.n_collisions = hd.n_collisions; r.tree_digest = hd.tree_digest;
+    const double* path = reinterpret_cast<const double*>(rec + sizeof(hd));
+    const double* prof = path + 2 * static_cast<size_t>(cap_path);
+    const int32_t* ids = reinterpret_cast<const int32_t*>(prof + 3 * static_cast<size_t>(cap_path));
+    const int np = std::min(hd.n_path, std::min(r.cap_path, cap_path));
+    const int nm = std::min(hd.n_profile, std::min(r.cap_path, cap_path));
+    if (hd.n_path > std::min(r.cap_path, cap_path) && (r.path_xy || r.path_node_ids)) ret = PP_ERR_CAPACITY;
+    if (r.path_xy) std::memcpy(r.path_xy, path, sizeof(double) * 2 * np);
+    if (r.path_node_ids) std::memcpy(r.path_node_ids, ids, sizeof(int32_t) * np);
+    if (r.yaw_rates) std::memcpy(r.yaw_rates, prof, sizeof(double) * nm);
+    if (r.durations) std::memcpy(r.durations, prof + cap_path, sizeof(double) * nm);
+    if (r.speeds) std::memcpy(r.speeds, prof + 2 * static_cast<size_t>(cap_path), sizeof(double) * nm);
+  }
+  if (ret == PP_ERR_CAPACITY) set_last_error("pp_plan_records_unpack: a caller-provided output array (or cap_path) is too small");
+  return ret;
 }
 
 int pp_get_visited(pp_handle* h, uint8_t* out_host, size_t capacity) {
@@ -410,6 +485,11 @@ int pp_last_phase_ms(pp_handle* h, float* out_ms, int32_t n) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->phase_ms[PP_PHASE_NARROW] = ms;
   else cudaGetLastError();
+  if (h->plan_timing_pending) {       // an asynchronous pp_plan_batch_dev: its events have completed by now
+    if (cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]) == cudaSuccess) h->phase_ms[PP_PHASE_PLAN] = ms;
+    else cudaGetLastError();
+    h->plan_timing_pending = false;
+  }
   for (int k = 0; k < n && k < PP_PHASE_COUNT; ++k) out_ms[k] = h->phase_ms[k];
   return PP_OK;
 }

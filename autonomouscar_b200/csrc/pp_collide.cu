@@ -20,13 +20,185 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
+// ---- REF_AABB (rows A10 / A11) --------------------------------------------------------------
+// LP:471-472: base cell = int(W/2 - y/res), int(H/2 - x/res), float64, truncation toward zero.  The division
+// is replaced by a multiplication with 1/res whenever that provably truncates to the same integer: both
+// quotients are within 3 ulp of y/res, so for |result| < 2^20 the two differences lie within 1.2e-9 of each
+// other and agree on the integer part unless the fast value is within 2^-20 of an integer -- those (and
+// anything large or NaN) take the exact division.
+__device__ __forceinline__ bool aabb_base_cell(double half, double inv_res, double res, float v, int* out) {
+  const double vd = static_cast<double>(v);
+  const double s = dm::sub(half, dm::mul(vd, inv_res));
+  if (fabs(dm::sub(s, rint(s))) >= 9.5367431640625e-07 && fabs(s) < 1048576.0) {
+    *out = __double2int_rz(s);
+    return true;
+  }
+  return dm::trunc_to_int(dm::sub(half, dm::div(vd, res)), out);
+}
+
+// map cell of a pose + its 2-bit block summary: 0 = free, 1 = look the cell up, 3 = hit (-1 = outside the map)
+struct AabbProbe {
+  size_t cell;
+  int code;
+};
+__device__ __forceinline__ AabbProbe aabb_probe(const GridDev& g, const uint32_t* coarse, double half_w, double half_h,
+                                                double inv_res, float x, float y) {
+  AabbProbe p;
+  p.cell = 0;
+  p.code = 0;
+  int bx, by;
+  if (!aabb_base_cell(half_w, inv_res, g.res, y, &bx) || !aabb_base_cell(half_h, inv_res, g.res, x, &by)) return p;
+  const int mx = bx + g.aabb_pad_x, my = by + g.aabb_pad_y;
+  if (mx < 0 || mx >= g.aabb_nx || my < 0 || my >= g.aabb_ny) return p;
+  const int cy = my >> g.aabb_cshift;
+  p.code = static_cast<int>((coarse[(mx >> g.aabb_cshift) * g.aabb_cwpr + (cy >> 4)] >> ((cy & 15) * 2)) & 3u);
+  p.cell = static_cast<size_t>(mx) * g.aabb_ny + my;
+  return p;
+}
+__device__ __forceinline__ uint32_t aabb_resolve(const GridDev& g, const AabbProbe& p) {
+  if (p.code == 1) return __ldg(&g.aabb_map[p.cell]) != 0 ? 1u : 0u;
+  return static_cast<uint32_t>(p.code) >> 1;
+}
+
+// plain variant (any alignment, any n): one pose per thread, the block summary read through L1
 __global__ void __launch_bounds__(kThreads)
 collide_aabb_kernel(GridDev g, const float* __restrict__ poses, uint8_t* __restrict__ flags, int64_t n) {
+  const double half_w = static_cast<double>(g.W / 2), half_h = static_cast<double>(g.H / 2);
+  const double inv_res = dm::div(1.0, g.res);
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float x = poses[3 * k], y = poses[3 * k + 1];
-    flags[k] = aabb_hit(g, static_cast<double>(x), static_cast<double>(y)) ? 1 : 0;
+    const AabbProbe p = aabb_probe(g, g.aabb_coarse, half_w, half_h, inv_res, poses[3 * k], poses[3 * k + 1]);
+    flags[k] = static_cast<uint8_t>(aabb_resolve(g, p));
   }
+}
+
+// Streaming variant: the pose stream is the only HBM traffic that matters (12 B in, 1 B out per pose), so it is
+// moved by the TMA unit -- one 1-D bulk copy (cp.async.bulk, completion on an mbarrier) per 2048-pose chunk into
+// a ring of kAabbStages shared-memory buffers, issued by one thread -- while the 512 threads of the CTA (one
+// persistent CTA per SM) work on the chunk that has landed: 4 consecutive poses per thread (three conflict-free
+// LDS.128), block summary from shared memory, the rare cell look-up from L2, one 32-bit store of 4 flags.
+constexpr int kAabbThreads = 512;
+constexpr int kAabbChunk = kAabbThreads * 4;          // poses per chunk (24 KB)
+constexpr int kAabbStages = 5;
+constexpr uint32_t kAabbChunkBytes = kAabbChunk * 12;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kAabbThreads, 1)
+collide_aabb_stream_kernel(GridDev g, const float* __restrict__ poses, uint8_t* __restrict__ flags, int64_t n) {
+  extern __shared__ __align__(128) unsigned char aabb_smem[];
+  float* stage = reinterpret_cast<float*>(aabb_smem);
+  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(aabb_smem + static_cast<size_t>(kAabbStages) * kAabbChunkBytes);
+  const int n_cw = g.aabb_cnbx * g.aabb_cwpr;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_coarse + ((n_cw + 3) & ~3));
+  const int tid = threadIdx.x;
+  const int64_t n_full = n / kAabbChunk;
+  if (tid == 0) {
+    for (int s = 0; s < kAabbStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = tid; k < n_cw; k += kAabbThreads) s_coarse[k] = __ldg(&g.aabb_coarse[k]);
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < kAabbStages; ++s) {
+      const int64_t chunk = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
+      if (chunk < n_full) {
+        mbar_expect_tx(&bars[s], kAabbChunkBytes);
+        bulk_copy_g2s(stage + static_cast<size_t>(s) * kAabbChunk * 3, poses + chunk * kAabbChunk * 3, kAabbChunkBytes, &bars[s]);
+      }
+    }
+  }
+  const double half_w = static_cast<double>(g.W / 2), half_h = static_cast<double>(g.H / 2);
+  const double inv_res = dm::div(1.0, g.res);
+  uint32_t* flags4 = reinterpret_cast<uint32_t*>(flags);
+  int s = 0;
+  uint32_t parity = 0;
+  for (int64_t chunk = blockIdx.x; chunk < n_full; chunk += gridDim.x) {
+    mbar_wait(&bars[s], parity);
+    const float4* sp = reinterpret_cast<const float4*>(stage + static_cast<size_t>(s) * kAabbChunk * 3) + tid * 3;
+    const float4 a = sp[0], b = sp[1], c = sp[2];      // (x0 y0 w0 x1) (y1 w1 x2 y2) (w2 x3 y3 w3)
+    const AabbProbe p0 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, a.x, a.y);
+    const AabbProbe p1 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, a.w, b.x);
+    const AabbProbe p2 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, b.z, b.w);
+    const AabbProbe p3 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, c.y, c.z);
+    const uint32_t out = aabb_resolve(g, p0) | (aabb_resolve(g, p1) << 8) | (aabb_resolve(g, p2) << 16) |
+                         (aabb_resolve(g, p3) << 24);
+    flags4[chunk * (kAabbChunk / 4) + tid] = out;
+    __syncthreads();                                   // every thread has read buffer s: refill it
+    if (tid == 0) {
+      const int64_t next = chunk + static_cast<int64_t>(kAabbStages) * gridDim.x;
+      if (next < n_full) {
+        mbar_expect_tx(&bars[s], kAabbChunkBytes);
+        bulk_copy_g2s(stage + static_cast<size_t>(s) * kAabbChunk * 3, poses + next * kAabbChunk * 3, kAabbChunkBytes, &bars[s]);
+      }
+    }
+    if (++s == kAabbStages) { s = 0; parity ^= 1u; }
+  }
+  // the last < 2048 poses: plain loads, spread over the CTAs
+  for (int64_t k = n_full * kAabbChunk + blockIdx.x * static_cast<int64_t>(kAabbThreads) + tid; k < n;
+       k += static_cast<int64_t>(gridDim.x) * kAabbThreads) {
+    const AabbProbe p = aabb_probe(g, s_coarse, half_w, half_h, inv_res, poses[3 * k], poses[3 * k + 1]);
+    flags[k] = static_cast<uint8_t>(aabb_resolve(g, p));
+  }
+}
+
+// ---- flags <-> bits (the N > 1 result gather moves 1 bit per pose instead of 1 byte) ---------------------
+// word k bit b = flags[32 k + b] != 0.  One thread per 16 flags (one 128-bit load), two threads per word.
+__global__ void __launch_bounds__(kThreads)
+pack_flags_kernel(const uint8_t* __restrict__ flags, uint32_t* __restrict__ bits, int64_t n) {
+  const int64_t n_words = (n + 31) / 32;
+  const int64_t total = n_words * 2;                   // (whole warps run every round: the shuffle below needs its neighbour)
+  const int64_t total32 = (total + 31) & ~int64_t(31);
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total32;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint32_t v = 0;
+    const int64_t base = t * 16;
+    if (base + 16 <= n) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(flags + base));
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // any non-zero byte -> 1, then four 0/1 bytes -> one nibble: the partial products of the multiplication land
+        // on distinct bit positions (no carries), bits 28..31 hold the result
+        const uint32_t x = ws[q];
+        const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3) | (x >> 4) | (x >> 5) | (x >> 6) | (x >> 7)) & 0x01010101u;
+        v |= ((nz * 0x10204080u) >> 28) << (4 * q);
+      }
+    } else {
+      for (int b = 0; b < 16; ++b)
+        if (base + b < n && flags[base + b]) v |= 1u << b;
+    }
+    const uint32_t hi = __shfl_down_sync(0xffffffffu, v, 1);
+    if ((t & 1) == 0 && (t >> 1) < n_words) bits[t >> 1] = v | (hi << 16);
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+unpack_flags_kernel(const uint32_t* __restrict__ bits, uint8_t* __restrict__ flags, int64_t n) {
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    flags[k] = (__ldg(&bits[k >> 5]) >> (k & 31)) & 1u;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -237,7 +409,21 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
   if (mode == PP_COLLISION_AS_SHIPPED) {
     fill_zero_kernel<<<grid_blocks(h, n, kThreads * 16, 8), kThreads, 0, s>>>(flags, n);
   } else if (mode == PP_COLLISION_REF_AABB) {
-    collide_aabb_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, s>>>(h->grid, poses, flags, n);
+    const GridDev& g = h->grid;
+    const size_t smem = static_cast<size_t>(kAabbStages) * kAabbChunkBytes +
+                        sizeof(uint32_t) * ((static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr + 3) & ~size_t(3)) + 8 * kAabbStages;
+    const bool aligned = (reinterpret_cast<uintptr_t>(poses) & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0;
+    if (aligned && n >= 4 * kAabbChunk && !getenv("PP_AABB_PLAIN_KERNEL")) {
+      if (!h->aabb_stream_ready) {       // (per device: the attribute lives in the context)
+        PP_CUDA(cudaFuncSetAttribute(collide_aabb_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        h->aabb_stream_ready = true;
+      }
+      const int64_t chunks = n / kAabbChunk;
+      const int blocks = static_cast<int>(chunks < h->sm_count ? chunks : h->sm_count);
+      collide_aabb_stream_kernel<<<blocks, kAabbThreads, smem, s>>>(g, poses, flags, n);
+    } else {
+      collide_aabb_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, s>>>(g, poses, flags, n);
+    }
   } else {
     static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : 64;
     const int blocks = grid_blocks(h, n, kChunk, bps);
@@ -286,6 +472,22 @@ int collide_edges_dev(pp_handle* h, int64_t n, const float* edges, uint8_t* flag
   else
     collide_edges_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, h->stream>>>(h->grid, collide_params(h),
                                                                                     edges, flags, n);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int pack_flags_dev(pp_handle* h, int64_t n, const uint8_t* flags, uint32_t* bits) {
+  if (n == 0) return PP_OK;
+  if (reinterpret_cast<uintptr_t>(flags) & 15) { set_last_error("pp_pack_flags_dev: flags must be 16-byte aligned"); return PP_ERR_INVALID; }
+  pack_flags_kernel<<<grid_blocks(h, (n + 31) / 32 * 2, kThreads, 8), kThreads, 0, h->stream>>>(flags, bits, n);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+int unpack_flags_dev(pp_handle* h, int64_t n, const uint32_t* bits, uint8_t* flags) {
+  if (n == 0) return PP_OK;
+  unpack_flags_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, h->stream>>>(bits, flags, n);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   return PP_OK;

@@ -71,6 +71,12 @@ struct GridDev {
   //   (bx,by) contains a cell == 100
   uint8_t* aabb_map;
   int aabb_pad_x, aabb_pad_y, aabb_nx, aabb_ny;
+  // aabb_map summarised per block of 2^aabb_cshift x 2^aabb_cshift map cells, 2 bits per block
+  // (bit 0: some cell of the block is 1, bit 1: the block lies inside the map and all its cells are 1),
+  // 16 blocks per word along my: word (mx >> s) * aabb_cwpr + (my >> s >> 4).  Small enough for shared
+  // memory (<= 96 KB), so the batch kernel answers ~94 % of the poses without touching L2.
+  uint32_t* aabb_coarse;
+  int aabb_cshift, aabb_cnbx, aabb_cwpr;
 };
 
 // A bank = n grids of ONE shape stored back to back: every array of grid k starts k * stride elements
@@ -78,7 +84,7 @@ struct GridDev {
 // banks; pp_plan_batch_banked lets every query name its grid.
 struct GridBank {
   int n = 0;
-  size_t cspace = 0, occ_tiles = 0, tile_any = 0, coarse = 0, coarse4 = 0, near8 = 0, aabb_map = 0;
+  size_t cspace = 0, occ_tiles = 0, tile_any = 0, coarse = 0, coarse4 = 0, near8 = 0, aabb_map = 0, aabb_coarse = 0;
 };
 __host__ __device__ inline GridDev grid_at(GridDev g, const GridBank& b, unsigned k) {
   g.cspace += k * b.cspace;
@@ -88,6 +94,7 @@ __host__ __device__ inline GridDev grid_at(GridDev g, const GridBank& b, unsigne
   g.coarse4 += k * b.coarse4;
   g.near8 += k * b.near8;
   g.aabb_map += k * b.aabb_map;
+  g.aabb_coarse += k * b.aabb_coarse;
   return g;
 }
 
@@ -288,6 +295,8 @@ struct pp_handle {
   uint8_t* bank_rows = nullptr;    // REF_AABB pass-1 scratch of the bank
   int* d_box_tables = nullptr;     // LP:473-476 interval tables (xlo | xhi | ylo | yhi)
   int broad_phase = 1;
+  bool plan_timing_pending = false;   // ev[8] / ev[9] of an asynchronous pp_plan_batch_dev not read yet
+  bool aabb_stream_ready = false;  // dynamic shared-memory limit of collide_aabb_stream_kernel raised on this device
   uint64_t launches = 0;
   float phase_ms[PP_PHASE_COUNT] = {};
   int64_t last_narrow = 0;
@@ -326,6 +335,8 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* fla
 int collide_counter_reset(pp_handle* h);
 int collide_counter_fetch(pp_handle* h);
 int collide_edges_dev(pp_handle* h, int64_t n, const float* edges_dev, uint8_t* flags_dev);
+int pack_flags_dev(pp_handle* h, int64_t n, const uint8_t* flags_dev, uint32_t* bits_dev);
+int unpack_flags_dev(pp_handle* h, int64_t n, const uint32_t* bits_dev, uint8_t* flags_dev);
 int footprint_points_dev(pp_handle* h, double x, double y, double yaw, double* out_dev, int cap, int* n);
 int sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t first, int64_t n, float x_lo,
                      float x_hi, float y_lo, float y_hi, float* out);
@@ -334,7 +345,8 @@ int nearest_dev(pp_handle* h, int64_t n_nodes, const float* node_xy, int64_t n_q
 int l2_gather_bench(pp_handle* h, size_t buffer_bytes, double* out_gbps);
 int find_exact_dev(pp_handle* h, int64_t n_nodes, const double* keys, int64_t n_query, const double* q,
                    int32_t* idx);
-int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool banked = false);
+int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool banked = false, unsigned char* rec_dev = nullptr,
+               int rec_cap_path = 0);
 int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs);
 void plan_free(pp_handle* h);
 void rrt_free(pp_handle* h);

@@ -182,6 +182,28 @@ __global__ void aabb_pass_x(BuildArgs a) {
   }
 }
 
+// 2-bit summary of aabb_map per block of (1 << s)^2 map cells (pp_common.cuh): one thread per block
+__global__ void aabb_coarse_kernel(BuildArgs a) {
+  const GridDev g = build_grid(a);
+  const int s = g.aabb_cshift, B = 1 << s, nby = (g.aabb_ny + B - 1) >> s;
+  const int64_t total = static_cast<int64_t>(g.aabb_cnbx) * nby;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cy = static_cast<int>(k % nby), cx = static_cast<int>(k / nby);
+    const int x0 = cx << s, y0 = cy << s;
+    const int x1 = min(x0 + B, g.aabb_nx), y1 = min(y0 + B, g.aabb_ny);
+    unsigned any = 0, all = (x1 - x0 == B && y1 - y0 == B) ? 1u : 0u;
+    for (int x = x0; x < x1; ++x)
+      for (int y = y0; y < y1; ++y) {
+        const unsigned v = g.aabb_map[static_cast<size_t>(x) * g.aabb_ny + y] != 0;
+        any |= v;
+        all &= v;
+      }
+    const unsigned bits = any | (all << 1);
+    if (bits) atomicOr(&g.aabb_coarse[static_cast<size_t>(cx) * g.aabb_cwpr + (cy >> 4)], bits << ((cy & 15) * 2));
+  }
+}
+
 // LP:473-476 evaluated on the host in double exactly as the reference would:
 //   lo = int(base - extent/2/res), hi = int(base + extent/2/res)  (truncation toward zero)
 void box_interval_table(int n_cells, int pad, double extent, double res, std::vector<int>* lo,
@@ -217,6 +239,13 @@ GridDev grid_shape(const pp_handle* h) {
   g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
   g.CI4 = g.TI * 8;
   g.CW4 = (g.TJ * 8 + 63) / 64 + 1;
+  // block size of the 2-bit summary: the smallest (>= 8 cells) whose map fits 96 KB of shared memory
+  for (g.aabb_cshift = 3;; ++g.aabb_cshift) {
+    const int B = 1 << g.aabb_cshift;
+    g.aabb_cnbx = (g.aabb_nx + B - 1) / B;
+    g.aabb_cwpr = ((g.aabb_ny + B - 1) / B + 15) / 16;
+    if (static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr * sizeof(uint32_t) <= 96 * 1024) break;
+  }
   // half diagonal of the footprint in cells + 1 (floor) + 2 (float slack of the pre-test)
   const double du = h->lat.su * h->lat.hu, dv = h->lat.sv * h->lat.hv;
   g.reach_cells = static_cast<int>(std::sqrt(du * du + dv * dv)) + 4;
@@ -236,6 +265,7 @@ GridBank bank_strides(const GridDev& g, int n) {
   b.near8 = b.coarse;
   b.coarse4 = static_cast<size_t>(g.CI4) * g.CW4;
   b.aabb_map = up(static_cast<size_t>(g.aabb_nx) * g.aabb_ny, 16);
+  b.aabb_coarse = up(static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr, 4);
   return b;
 }
 
@@ -247,6 +277,7 @@ void grid_free_arrays(GridDev* g) {
   cudaFree(g->coarse4);
   cudaFree(g->near8);
   cudaFree(g->aabb_map);
+  cudaFree(g->aabb_coarse);
   *g = GridDev{};
 }
 
@@ -260,6 +291,7 @@ int grid_alloc(GridDev* g, const GridBank& b) {
   PP_CUDA(cudaMalloc(&g->near8, sizeof(unsigned long long) * b.near8 * n));
   PP_CUDA(cudaMalloc(&g->coarse4, sizeof(unsigned long long) * b.coarse4 * n));
   PP_CUDA(cudaMalloc(&g->aabb_map, b.aabb_map * n));
+  PP_CUDA(cudaMalloc(&g->aabb_coarse, sizeof(uint32_t) * b.aabb_coarse * n));
   return PP_OK;
 }
 
@@ -296,15 +328,21 @@ int grid_build(pp_handle* h, const GridDev& g, const GridBank& b, const int8_t* 
   const int64_t n_tiles = static_cast<int64_t>(g.TI) * g.TJ;
   pack_occ_tiles<<<blocks(n_tiles * kTile * 32), T, 0, s>>>(a);
   reduce_tile_any<<<blocks(n_tiles * 32), T, 0, s>>>(a);
-  PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * b.coarse * n, s));
+  // (the planner's own grid is a bank of one with ZERO strides: sizes come from the shape then)
+  const size_t coarse_n = n > 1 ? b.coarse * n : static_cast<size_t>(g.CI8) * g.CW8;
+  const size_t coarse4_n = n > 1 ? b.coarse4 * n : static_cast<size_t>(g.CI4) * g.CW4;
+  const size_t acoarse_n = n > 1 ? b.aabb_coarse * n : static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr;
+  PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * coarse_n, s));
   build_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.TJ), T, 0, s>>>(a);
   dilate_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.CW8), T, 0, s>>>(a, (g.reach_cells + 7) / 8);
-  PP_CUDA(cudaMemsetAsync(g.coarse4, 0, sizeof(unsigned long long) * b.coarse4 * n, s));
+  PP_CUDA(cudaMemsetAsync(g.coarse4, 0, sizeof(unsigned long long) * coarse4_n, s));
   build_coarse4<<<blocks(static_cast<int64_t>(g.CI4) * g.TJ), T, 0, s>>>(a);
   h->launches += 3;
   aabb_pass_y<<<blocks(static_cast<int64_t>(g.W) * g.aabb_ny), T, 0, s>>>(a);
   aabb_pass_x<<<blocks(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny), T, 0, s>>>(a);
-  h->launches += 4;
+  PP_CUDA(cudaMemsetAsync(g.aabb_coarse, 0, sizeof(uint32_t) * acoarse_n, s));
+  aabb_coarse_kernel<<<blocks(static_cast<int64_t>(g.aabb_cnbx) * ((g.aabb_ny >> g.aabb_cshift) + 1)), T, 0, s>>>(a);
+  h->launches += 5;
   PP_CUDA(cudaGetLastError());
   return PP_OK;
 }

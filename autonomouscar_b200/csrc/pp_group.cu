@@ -12,7 +12,9 @@
 // autonomouscar_b200/sharding.py and is what bench.py uses.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -47,12 +49,6 @@ struct NcclApi {
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
     return CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd && GetErrorString;
   }
-};
-
-// fixed-stride record gathered for every plan query
-struct PlanRecord {
-  int32_t status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions, pad;
-  uint64_t digest;
 };
 
 }  // namespace
@@ -225,60 +221,70 @@ int pp_group_plan_batch(pp_group* g, int32_t n, const pp_query* queries, pp_resu
   if (n == 0) return PP_OK;
   const int G = g->n;
   const int per = (n + G - 1) / G;
-  // 1. every device plans its contiguous block of queries; one host thread per device because
-  //    pp_plan_batch is synchronous (it mirrors the reference's blocking callback)
-  std::vector<int> rcs(G, PP_OK);
-  std::vector<std::string> errs(G);
-  std::vector<std::thread> th;
-  for (int d = 0; d < G; ++d) {
-    const int lo = std::min(n, d * per), hi = std::min(n, lo + per);
-    if (hi <= lo) continue;
-    th.emplace_back([=, &rcs, &errs]() {
-      rcs[d] = pp_plan_batch(g->h[d], hi - lo, queries + lo, results + lo);
-      if (rcs[d] != PP_OK) errs[d] = pp_last_error();
-    });
+  bool want_nodes = false;
+  int cap_path = 2;
+  for (int k = 0; k < n; ++k) {
+    want_nodes |= results[k].node_state || results[k].node_parent || results[k].node_closed_seq || results[k].expansion_ids;
+    if (results[k].cap_path < 0) { pp::set_last_error("pp_group_plan_batch: negative capacity"); return PP_ERR_INVALID; }
+    cap_path = std::max(cap_path, results[k].cap_path);
   }
-  for (auto& t : th) t.join();
-  int ret = PP_OK;
-  for (int d = 0; d < G; ++d)
-    if (rcs[d] != PP_OK) { pp::set_last_error(errs[d]); if (rcs[d] != PP_ERR_CAPACITY) return rcs[d]; ret = rcs[d]; }
-  // 2. gather the fixed-stride records over NCCL; the scalar fields of every result are then
-  //    re-read from the gathered copy (device 0), in input order
-  const size_t per_bytes = sizeof(PlanRecord) * static_cast<size_t>(per);
+  cap_path = std::min(cap_path, 1 << 12);
+  if (want_nodes) {
+    // whole trees are a debugging aid and stay per device: every device plans its contiguous block through the
+    // host-pointer call (one host thread each, the call is synchronous) and the results are complete after the join
+    std::vector<int> rcs(G, PP_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int d = 0; d < G; ++d) {
+      const int lo = std::min(n, d * per), hi = std::min(n, lo + per);
+      if (hi <= lo) continue;
+      th.emplace_back([=, &rcs, &errs]() {
+        rcs[d] = pp_plan_batch(g->h[d], hi - lo, queries + lo, results + lo);
+        if (rcs[d] != PP_OK) errs[d] = pp_last_error();
+      });
+    }
+    for (auto& t : th) t.join();
+    int ret = PP_OK;
+    for (int d = 0; d < G; ++d)
+      if (rcs[d] != PP_OK) { pp::set_last_error(errs[d]); if (rcs[d] != PP_ERR_CAPACITY) return rcs[d]; ret = rcs[d]; }
+    return ret;
+  }
+  // 1. every device plans its contiguous block of queries and leaves fixed-stride records (summary + path + profile,
+  //    LP:503-583) in ITS send buffer: asynchronous launches, no host thread per device, nothing crosses PCIe
+  const size_t stride = pp_plan_record_stride(cap_path);
+  const size_t per_bytes = stride * static_cast<size_t>(per);
   int rc = ensure_gather(g, per_bytes);
   if (rc) return rc;
-  std::vector<PlanRecord> rec(static_cast<size_t>(per));
   for (int d = 0; d < G; ++d) {
     const int lo = std::min(n, d * per), hi = std::min(n, lo + per);
-    std::memset(rec.data(), 0, per_bytes);
-    for (int k = lo; k < hi; ++k) {
-      PlanRecord& r = rec[k - lo];
-      const pp_result& s = results[k];
-      r.status = s.status; r.n_expansions = s.n_expansions; r.n_nodes = s.n_nodes; r.n_open = s.n_open;
-      r.n_closed = s.n_closed; r.n_path = s.n_path; r.n_profile = s.n_profile; r.n_candidates = s.n_candidates;
-      r.n_collisions = s.n_collisions; r.digest = s.tree_digest;
-    }
     PP_CUDA(cudaSetDevice(g->devices[d]));
-    PP_CUDA(cudaMemcpyAsync(g->d_send[d], rec.data(), per_bytes, cudaMemcpyHostToDevice, g->h[d]->stream));
-    PP_CUDA(cudaStreamSynchronize(g->h[d]->stream));
+    if (hi - lo < per)     // the padding records of the last block(s)
+      PP_CUDA(cudaMemsetAsync(g->d_send[d] + stride * (hi - lo), 0, stride * (per - (hi - lo)), g->h[d]->stream));
+    if (hi > lo) {
+      rc = pp_plan_batch_dev(g->h[d], hi - lo, queries + lo, cap_path, g->d_send[d]);
+      if (rc) return rc;
+    }
   }
+  // 2. one ncclAllGather of the records over NVLink: afterwards every device holds all results in input order
   rc = all_gather(g, per_bytes);
   if (rc) return rc;
-  std::vector<PlanRecord> all(static_cast<size_t>(per) * G);
+  // 3. the host copy comes from device 0, once
+  std::vector<unsigned char> all(per_bytes * G);
   PP_CUDA(cudaSetDevice(g->devices[0]));
   PP_CUDA(cudaMemcpyAsync(all.data(), g->d_all[0], per_bytes * G, cudaMemcpyDeviceToHost, g->h[0]->stream));
   for (int d = 0; d < G; ++d) {
     PP_CUDA(cudaSetDevice(g->devices[d]));
     PP_CUDA(cudaStreamSynchronize(g->h[d]->stream));
   }
-  for (int k = 0; k < n; ++k) {
-    const PlanRecord& r = all[static_cast<size_t>(k / per) * per + (k % per)];
-    pp_result& s = results[k];
-    s.status = r.status; s.n_expansions = r.n_expansions; s.n_nodes = r.n_nodes; s.n_open = r.n_open;
-    s.n_closed = r.n_closed; s.n_path = r.n_path; s.n_profile = r.n_profile; s.n_candidates = r.n_candidates;
-    s.n_collisions = r.n_collisions; s.tree_digest = r.digest;
-  }
-  return ret;
+  return pp_plan_records_unpack(all.data(), n, cap_path, results);
+}
+
+// device d's copy of the records gathered by the last pp_group_plan_batch (n x pp_plan_record_stride(cap_path)
+// bytes, input order) -- for callers that keep working on the device
+int pp_group_records_dev(pp_group* g, int device_index, const void** out_records_dev) {
+  if (!g || !out_records_dev || device_index < 0 || device_index >= g->n) return PP_ERR_INVALID;
+  *out_records_dev = g->d_all[device_index];
+  return PP_OK;
 }
 
 }  // extern "C"

@@ -39,7 +39,7 @@ constexpr int kTMax = 256;         // threads per CTA: 256 for a lone query (lat
 constexpr int kWarpsMax = kTMax / 32;
 #define kT (static_cast<int>(blockDim.x))
 #define kWarps (static_cast<int>(blockDim.x) >> 5)
-constexpr int kMaxVel = 64;        // velocities per expansion the kernel supports
+constexpr int kMaxVelRaw = 1024;   // raw velocity lattice points per expansion (LP:200-203) the kernel walks
 constexpr int kMaxCand = 8192;     // children per expansion the kernel supports
 constexpr int kIntMax = 0x7fffffff;
 constexpr int kFxMaxPoses = 512;   // longest path the pointer-walk extraction handles (longer: exact scan walk)
@@ -81,6 +81,11 @@ struct PlanArgs {
   double* out_profile;    // 3 planes of [pool_cap]: yaw rates, durations, speeds
   unsigned long long* pool_counter;
   long long pool_cap;
+  // record mode (pp_plan_batch_dev): query q writes a fixed-stride record at rec_base + q * rec_stride
+  // (pp_plan_record_header | path_xy | yaw_rates | durations | speeds | path_node_ids, each padded to cap_path)
+  // instead of reserving pool slots; the records stay on the device for the result gather
+  unsigned char* rec_base;
+  size_t rec_stride;
   int* out_exp;           // [n][cap_exp] or null
   int* work_counter;
   uint8_t* visited;       // A12 debug bitmap (single-query plans only) or null
@@ -307,6 +312,14 @@ __device__ __forceinline__ double calc_h(const pp_params& P, const QueryD& Q, co
   double speed_h = dm::sub(100.0, dm::mul(dm::div(speed, P.max_velocity), 100.0));
   if (check_goal_dist(P, Q, K, cx, cy, s, c, vel)) speed_h = dm::mul(fabs(dm::sub(speed, Q.gs)), 100.0);
   return fabs(dm::add(dm::add(dist_h, yaw_h), speed_h));
+}
+
+// one comparison of checkForGoal (LP:276-283): abs(d) <= tol under the double or the int overload of abs
+__device__ __forceinline__ bool goal_tol_ok(double d, double tol, bool int_abs) {
+  if (!int_abs) return fabs(d) <= tol;
+  int t;
+  if (!dm::trunc_to_int(d, &t)) return false;
+  return static_cast<double>(abs(t)) <= tol;
 }
 
 struct Shared {
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       const double v_lo = dm::sub(nvel, dm::mul(Q.max_accel, time_step));
       int n_vraw;
       if (!dm::trunc_to_int(dm::div(dm::sub(v_hi, v_lo), P.velocity_res), &n_vraw)) n_vraw = 0;
-      bool unsupported = n_vraw > 1024;
+      bool unsupported = n_vraw > kMaxVelRaw;   // (the host has refused such queries already: PP_ERR_UNSUPPORTED)
       if (unsupported) n_vraw = 0;
       int n_vel = 0;
       for (int i = 0; i < n_vraw; ++i) {
@@ -635,7 +648,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       const double yn = dm::div(dm::sub(dm::add(nhd, P.heading_diff), ylo), P.heading_res);
       int n_yaw = 0;
       if (yn > 0) n_yaw = yn >= 4096.0 ? 4096 : __double2int_ru(yn);
-      if (n_vel > kMaxVel || static_cast<long long>(n_vel) * n_yaw + S.n_nodes + 2 > A.NC) unsupported = true;
+      if (static_cast<long long>(n_vel) * n_yaw + S.n_nodes + 2 > A.NC) unsupported = true;
       const int n_cand = unsupported ? 0 : n_vel * n_yaw;
       const int base_nodes = S.n_nodes;
       const int hs_base = S.heap_size;
@@ -654,7 +667,10 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
           if (!dm::trunc_to_int(dm::mul(dm::div(dist, P.search_res), 2.0), &n_pts)) n_pts = 0;
           double sa, ca;
           dm::sincos(angle, &sa, &ca);
-          const bool speed_ok = fabs(dm::sub(nvel, Q.gs)) <= P.goal_speed_tolerance;
+          // A18: P.goal_test_int_abs selects the `int abs(int)` reading of LP:276-283 (differences truncated
+          // toward zero by the implicit conversion; outside +-2^30 = "too far", like the oracle's trunc_int)
+          const bool int_abs = P.goal_test_int_abs != 0;
+          const bool speed_ok = goal_tol_ok(dm::sub(nvel, Q.gs), P.goal_speed_tolerance, int_abs);
           for (int base = 0; base < n_pts; base += 32) {
             const int i = base + lane;
             bool hit = false;
@@ -663,8 +679,8 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
               const double t = dm::mul(dm::div(static_cast<double>(i), static_cast<double>(n_pts)), dist);
               x = dm::add(ncx, dm::mul(t, ca));
               y = dm::add(ncy, dm::mul(t, sa));
-              hit = speed_ok && fabs(dm::sub(x, Q.gx)) <= P.goal_pos_tolerance &&
-                    fabs(dm::sub(y, Q.gy)) <= P.goal_pos_tolerance;
+              hit = speed_ok && goal_tol_ok(dm::sub(x, Q.gx), P.goal_pos_tolerance, int_abs) &&
+                    goal_tol_ok(dm::sub(y, Q.gy), P.goal_pos_tolerance, int_abs);
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m) {
@@ -1042,11 +1058,19 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         if (tid == 0) S.status = PP_PLAN_BROKEN;
       } else {
         n_path = len;
-        if (tid == 0) S.pool_off = static_cast<long long>(atomicAdd(A.pool_counter, static_cast<unsigned long long>(min(len, A.cap_path))));
-        __syncthreads();
-        path = A.out_path + 2 * S.pool_off;
-        path_ids = A.out_path_ids + S.pool_off;
-        prof = A.out_profile + S.pool_off;
+        if (A.rec_base) {
+          unsigned char* rec = A.rec_base + static_cast<size_t>(q) * A.rec_stride + sizeof(pp_plan_record_header);
+          path = reinterpret_cast<double*>(rec);
+          prof = path + 2 * static_cast<size_t>(A.cap_path);
+          path_ids = reinterpret_cast<int*>(prof + 3 * static_cast<size_t>(A.cap_path));
+        } else {
+          if (tid == 0) S.pool_off = static_cast<long long>(atomicAdd(A.pool_counter, static_cast<unsigned long long>(min(len, A.cap_path))));
+          __syncthreads();
+          path = A.out_path + 2 * S.pool_off;
+          path_ids = A.out_path_ids + S.pool_off;
+          prof = A.out_profile + S.pool_off;
+        }
+        const long long plane = A.rec_base ? static_cast<long long>(A.cap_path) : A.pool_cap;   // distance between the profile's three arrays
         for (int k = tid; k < len && k < A.cap_path; k += kT) {   // LP:530-538: reversed
           path[2 * k] = rev[2 * (len - 1 - k)];
           path[2 * k + 1] = rev[2 * (len - 1 - k) + 1];
@@ -1067,8 +1091,8 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
           const double next_heading = id_b >= 0 ? w.hd[id_b] : 0.0;
           const double next_velocity = id_b >= 0 ? w.vel[id_b] : 0.0;
           prof[i] = dm::div(dm::sub(next_heading, cur_heading), dm::div(P.time_step_ms, 1000.0));   // LP:576-577
-          prof[A.pool_cap + i] = P.time_step_ms;                                                     // LP:578
-          prof[2 * A.pool_cap + i] = next_velocity;                                                  // LP:579
+          prof[plane + i] = P.time_step_ms;                                                          // LP:578
+          prof[2 * plane + i] = next_velocity;                                                       // LP:579
         }
       }
     }
@@ -1104,6 +1128,27 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       if (A.timing) { const long long now_ = clock64(); S.cyc[6] += now_ - t_mark; S.cyc[7] = now_ - t_begin; }
       for (int c = 0; c < 8; ++c) hd.cyc[c] = S.cyc[c];
       A.hdr[q] = hd;
+      if (A.rec_base) {
+        pp_plan_record_header rh;
+        rh.status = hd.status; rh.n_expansions = hd.n_expansions; rh.n_nodes = hd.n_nodes; rh.n_open = hd.n_open;
+        rh.n_closed = hd.n_closed; rh.n_path = hd.n_path; rh.n_profile = hd.n_profile;
+        rh.n_candidates = hd.n_candidates; rh.n_collisions = hd.n_collisions; rh.truncated = hd.truncated;
+        rh.cap_path = A.cap_path; rh.reserved = 0; rh.tree_digest = d; rh.reserved2 = 0;
+        *reinterpret_cast<pp_plan_record_header*>(A.rec_base + static_cast<size_t>(q) * A.rec_stride) = rh;
+      }
+    }
+    if (A.rec_base) {
+      // the unused tail of every array is zero, so that gathered records are comparable byte for byte
+      unsigned char* rec = A.rec_base + static_cast<size_t>(q) * A.rec_stride + sizeof(pp_plan_record_header);
+      double* r_path = reinterpret_cast<double*>(rec);
+      double* r_prof = r_path + 2 * static_cast<size_t>(A.cap_path);
+      int* r_ids = reinterpret_cast<int*>(r_prof + 3 * static_cast<size_t>(A.cap_path));
+      const int np_ = S.status == PP_PLAN_FOUND ? min(n_path, A.cap_path) : 0;
+      const int nm_ = S.status == PP_PLAN_FOUND ? min(n_profile, A.cap_path) : 0;
+      for (int k = np_ + tid; k < A.cap_path; k += kT) { r_path[2 * k] = 0.0; r_path[2 * k + 1] = 0.0; r_ids[k] = -1; }
+      for (int k = nm_ + tid; k < A.cap_path; k += kT) { r_prof[k] = 0.0; r_prof[A.cap_path + k] = 0.0; r_prof[2 * A.cap_path + k] = 0.0; }
+      const size_t used = sizeof(pp_plan_record_header) + static_cast<size_t>(A.cap_path) * 44;
+      for (size_t b = used + tid; b < A.rec_stride; b += kT) (A.rec_base + static_cast<size_t>(q) * A.rec_stride)[b] = 0;
     }
     __syncthreads();
   }
@@ -1185,7 +1230,10 @@ static int grow(void** p, size_t* have, size_t want) {
   return PP_OK;
 }
 
-int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool banked) {
+// rec_dev != nullptr: record mode -- `rs` is ignored, every query leaves a fixed-stride record
+// (pp_plan_record_stride(rec_cap_path) bytes) at rec_dev on the device, nothing is copied back and the call
+// returns without waiting for the kernel.
+int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool banked, unsigned char* rec_dev, int rec_cap_path) {
   if (!h->plan_ws) {
     h->plan_ws = new PlanWorkspace();
     PP_CUDA(cudaMalloc(&h->plan_ws->d_counter, sizeof(int)));
@@ -1197,14 +1245,24 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
 
   bool want_nodes = false, want_exp = false, want_path_ids = false;
   int cap_path = 2, cap_exp = 0;
-  for (int k = 0; k < n; ++k) {
-    want_nodes |= rs[k].node_state || rs[k].node_parent || rs[k].node_closed_seq;
-    want_exp |= rs[k].expansion_ids != nullptr;
-    want_path_ids |= rs[k].path_node_ids != nullptr;
-    cap_path = std::max(cap_path, rs[k].cap_path);
-    if (rs[k].expansion_ids) cap_exp = std::max(cap_exp, rs[k].cap_expansions);
+  const bool record_mode = rec_dev != nullptr;
+  if (record_mode) {
+    PP_REQUIRE(rec_cap_path >= 2 && rec_cap_path <= (1 << 16), "pp_plan_batch_dev: cap_path must be in [2, 65536]");
+    cap_path = rec_cap_path;
+    want_path_ids = true;
+  } else {
+    for (int k = 0; k < n; ++k)
+      PP_REQUIRE(rs[k].cap_nodes >= 0 && rs[k].cap_path >= 0 && rs[k].cap_expansions >= 0,
+                 "pp_plan: negative capacity in a pp_result");
+    for (int k = 0; k < n; ++k) {
+      want_nodes |= rs[k].node_state || rs[k].node_parent || rs[k].node_closed_seq;
+      want_exp |= rs[k].expansion_ids != nullptr;
+      want_path_ids |= rs[k].path_node_ids != nullptr;
+      cap_path = std::max(cap_path, rs[k].cap_path);
+      if (rs[k].expansion_ids) cap_exp = std::max(cap_exp, rs[k].cap_expansions);
+    }
+    cap_path = std::min(cap_path, 1 << 16);
   }
-  cap_path = std::min(cap_path, 1 << 16);
 
   // one expansion can add up to kMaxCand children after the cap check, + the goal node
   // children one expansion can add after the cap check passed (+ the terminal node)
@@ -1212,6 +1270,11 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   for (int k = 0; k < n; ++k) {
     const double nv = 2.0 * qs[k].max_accel * (P.time_step_ms / 1000.0) / P.velocity_res;
     const double ny = 2.0 * P.heading_diff / P.heading_res;
+    if (!(nv < kMaxVelRaw - 2) || !(ny < 4094.0)) {   // (also catches NaN / inf parameters)
+      set_last_error("pp_plan: more than 1024 velocities or 4096 yaws per expansion (max_accel * time_step / velocity_res, "
+                     "heading_diff / heading_res): outside what the kernel implements");
+      return PP_ERR_UNSUPPORTED;
+    }
     const long long c = (static_cast<long long>(nv > 0 ? nv : 0) + 2) * (static_cast<long long>(ny > 0 ? ny : 0) + 2);
     max_children = std::max(max_children, c);
   }
@@ -1260,7 +1323,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   int rc = grow(reinterpret_cast<void**>(&W->ws), &W->ws_bytes_total, stride * static_cast<size_t>(n_ws));
   if (rc) return rc;
   // output block layout: headers | pool counter | path pool | id pool | 3 profile planes | expansions
-  const long long pool_cap = static_cast<long long>(cap_path) * n;
+  const long long pool_cap = record_mode ? 0 : static_cast<long long>(cap_path) * n;   // (records replace the pools)
   const size_t hdr_b = (sizeof(PlanHdr) * n + 255) & ~size_t(255);
   const size_t cnt_b = 256;
   const size_t path_b = (sizeof(double) * 2 * pool_cap + 255) & ~size_t(255);
@@ -1270,7 +1333,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   const size_t out_total = hdr_b + cnt_b + path_b + pid_b + prof_b + exp_b;
   rc = grow(&W->out, &W->out_bytes, out_total);
   if (rc) return rc;
-  if (out_total > W->h_out_bytes) {
+  if (!record_mode && out_total > W->h_out_bytes) {
     cudaFreeHost(W->h_out);
     W->h_out = nullptr; W->h_out_bytes = 0;
     PP_CUDA(cudaMallocHost(&W->h_out, out_total));
@@ -1312,10 +1375,12 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   A.out_path_ids = reinterpret_cast<int*>(ob + hdr_b + cnt_b + path_b);
   A.out_profile = reinterpret_cast<double*>(ob + hdr_b + cnt_b + path_b + pid_b);
   A.out_exp = want_exp ? reinterpret_cast<int*>(ob + hdr_b + cnt_b + path_b + pid_b + prof_b) : nullptr;
+  A.rec_base = rec_dev;
+  A.rec_stride = record_mode ? pp_plan_record_stride(cap_path) : 0;
   PP_CUDA(cudaMemsetAsync(A.pool_counter, 0, sizeof(unsigned long long), s));
   A.work_counter = W->d_counter;
   A.visited = nullptr;
-  if (n == 1) {   // clearVisited (LP:251-262)
+  if (n == 1 && !record_mode) {   // clearVisited (LP:251-262)
     const size_t cells = static_cast<size_t>(P.costmap_width) * P.costmap_height;
     if (!h->d_visited) PP_CUDA(cudaMalloc(&h->d_visited, cells));
     PP_CUDA(cudaMemsetAsync(h->d_visited, 0, cells, s));
@@ -1327,7 +1392,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   h->launches++;
   PP_CUDA(cudaGetLastError());
   bool want_parent = false;
-  for (int k = 0; k < n; ++k) want_parent |= rs[k].node_parent != nullptr;
+  for (int k = 0; k < n && !record_mode; ++k) want_parent |= rs[k].node_parent != nullptr;
   if (want_parent) {
     rc = grow(reinterpret_cast<void**>(&W->d_parent), &W->parent_bytes, sizeof(int) * static_cast<size_t>(NC) * n);
     if (rc) return rc;
@@ -1336,6 +1401,8 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
     PP_CUDA(cudaGetLastError());
   }
   PP_CUDA(cudaEventRecord(h->ev[9], s));
+  h->plan_timing_pending = true;
+  if (record_mode) return PP_OK;      // results stay on the device; the caller orders / waits on the handle's stream
 
   // headers + pool counter first, then only the used prefix of every pool
   unsigned char* hbw = W->h_out;
@@ -1358,6 +1425,7 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]);
   h->phase_ms[PP_PHASE_PLAN] = ms;
+  h->plan_timing_pending = false;
 
   const unsigned char* hb = W->h_out;
   const PlanHdr* hdr = reinterpret_cast<const PlanHdr*>(hb);

@@ -424,6 +424,9 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   PP_REQUIRE(P.rrt_samples_per_round >= 1 && P.rrt_samples_per_round <= kMaxK,
              "pp_rrt_plan: rrt_samples_per_round must be in [1, 1024]");
   PP_REQUIRE(P.max_nodes >= 1 && P.rrt_max_samples >= 0, "pp_rrt_plan: bad caps");
+  for (int k = 0; k < n; ++k)
+    PP_REQUIRE(rs[k].cap_nodes >= 0 && rs[k].cap_path >= 0 && rs[k].cap_expansions >= 0,
+               "pp_rrt_plan: negative capacity in a pp_result");
   if (!h->rrt_ws) {
     h->rrt_ws = new RrtWorkspace();
     PP_CUDA(cudaMalloc(&h->rrt_ws->d_active, sizeof(int)));

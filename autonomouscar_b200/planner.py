@@ -121,6 +121,20 @@ class Planner:
         self._check(self._L.pp_collide_batch_dev(self._h, n, _dptr(poses), _dptr(out)))
         return out
 
+    def pack_flags_dev(self, flags, out=None):
+        """1 B/pose flags -> 1 bit/pose (int32 words, bit b of word k = flag 32k + b); asynchronous on self.stream."""
+        n = flags.numel()
+        if out is None:
+            out = torch.empty((n + 31) // 32, dtype=torch.int32, device=flags.device)
+        self._check(self._L.pp_pack_flags_dev(self._h, n, _dptr(flags), _dptr(out)))
+        return out
+
+    def unpack_flags_dev(self, bits, n, out=None):
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=bits.device)
+        self._check(self._L.pp_unpack_flags_dev(self._h, n, _dptr(bits), _dptr(out)))
+        return out
+
     def collide_edges_dev(self, edges, out=None):
         assert edges.is_cuda and edges.dtype == torch.float32 and edges.is_contiguous()
         n = edges.numel() // 5
@@ -196,6 +210,17 @@ class Planner:
         if rc not in (PP_OK, 4):
             self._check(rc)
         return batch
+
+    def plan_batch_dev(self, queries_array, n, cap_path=128, out=None):
+        """pp_plan_batch_dev: n queries (ctypes pp_query array, host) -> fixed-stride records that STAY on the device
+        (uint8 tensor [n, pp_plan_record_stride(cap_path)]).  Asynchronous on self.stream; results.PlanRecords views
+        a host copy."""
+        stride = int(self._L.pp_plan_record_stride(int(cap_path)))
+        if out is None:
+            out = torch.empty((n, stride), dtype=torch.uint8, device=self.torch_device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= n * stride
+        self._check(self._L.pp_plan_batch_dev(self._h, int(n), queries_array, int(cap_path), _dptr(out)))
+        return out
 
     def rrt_plan(self, query, **caps):
         res = PlanResult(**caps)
@@ -291,10 +316,26 @@ class PlannerGroup:
                                                    out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def records_dev(self, device_index, n, cap_path):
+        """Device `device_index`'s copy of the records gathered by the last plan_batch, as a zero-copy uint8 tensor
+        [n, stride] (valid until the next call on the group)."""
+        ptr = C.c_void_p()
+        self._check(self._L.pp_group_records_dev(self._g, device_index, C.byref(ptr)))
+        stride = int(self._L.pp_plan_record_stride(int(cap_path)))
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n * stride,), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+        dev = torch.device("cuda", self.devices[device_index])
+        return torch.as_tensor(_View(), device=dev).reshape(n, stride)
+
     def plan_batch(self, queries, want_nodes=False, **caps):
         n = len(queries)
         qs = (pp_query * n)(*queries)
         results = [PlanResult(want_nodes=want_nodes, **caps) for _ in range(n)]
+        if not want_nodes:       # paths + profiles only: the device-resident records + NCCL gather path
+            for r in results:
+                r.raw.expansion_ids = None
+                r.raw.cap_expansions = 0
         raw = (pp_result * n)(*[r.raw for r in results])
         rc = self._L.pp_group_plan_batch(self._g, n, qs, raw)
         if rc not in (PP_OK, 4):

@@ -130,3 +130,54 @@ class PlanBatch:
         out[:, 0], out[:, 1], out[:, 2], out[:, 3] = v["status"], v["n_expansions"], v["n_nodes"], v["n_path"]
         out[:, 4] = (v["tree_digest"] & np.uint64(0x7FFFFFFFFFFFFFFF)).astype(np.int64)
         return out
+
+
+RECORD_HEADER = np.dtype([("status", "<i4"), ("n_expansions", "<i4"), ("n_nodes", "<i4"), ("n_open", "<i4"),
+                          ("n_closed", "<i4"), ("n_path", "<i4"), ("n_profile", "<i4"), ("n_candidates", "<i4"),
+                          ("n_collisions", "<i4"), ("truncated", "<i4"), ("cap_path", "<i4"), ("reserved", "<i4"),
+                          ("tree_digest", "<u8"), ("reserved2", "<u8")])
+
+
+def record_stride(cap_path):
+    """pp_plan_record_stride: header (64 B) + 44 B per path slot, rounded up to 16 B."""
+    return (RECORD_HEADER.itemsize + 44 * int(cap_path) + 15) & ~15
+
+
+def record_dtype(cap_path):
+    """numpy view of one pp_plan_batch_dev record (include/prius_planner.h: pp_plan_record_header | path_xy |
+    yaw_rates | durations | speeds | path_node_ids)."""
+    c = int(cap_path)
+    o = RECORD_HEADER.itemsize
+    return np.dtype({"names": ["hdr", "path_xy", "yaw_rates", "durations", "speeds", "path_node_ids"],
+                     "formats": [RECORD_HEADER, ("<f8", (c, 2)), ("<f8", (c,)), ("<f8", (c,)), ("<f8", (c,)), ("<i4", (c,))],
+                     "offsets": [0, o, o + 16 * c, o + 24 * c, o + 32 * c, o + 40 * c],
+                     "itemsize": record_stride(c)})
+
+
+class PlanRecords:
+    """Host view of a block of fixed-stride plan records (a uint8 array [n, stride] copied from the device, e.g.
+    the gathered block of sharding.plan_batch_gather)."""
+
+    def __init__(self, raw, cap_path):
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        self.cap_path = int(cap_path)
+        self.rec = raw.reshape(-1).view(record_dtype(cap_path))
+        self.n = len(self.rec)
+
+    def field(self, name):
+        return self.rec["hdr"][name]
+
+    def path_xy(self, k):
+        return self.rec["path_xy"][k][: min(int(self.rec["hdr"]["n_path"][k]), self.cap_path)]
+
+    def path_node_ids(self, k):
+        return self.rec["path_node_ids"][k][: min(int(self.rec["hdr"]["n_path"][k]), self.cap_path)]
+
+    def profile(self, k):
+        m = min(int(self.rec["hdr"]["n_profile"][k]), self.cap_path)
+        return self.rec["yaw_rates"][k][:m], self.rec["durations"][k][:m], self.rec["speeds"][k][:m]
+
+    def summary(self, k):
+        h = self.rec["hdr"][k]
+        return {f: int(h[f]) for f in ("status", "n_expansions", "n_nodes", "n_open", "n_closed", "n_path", "n_profile",
+                                        "n_candidates", "n_collisions", "tree_digest")}

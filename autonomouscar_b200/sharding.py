@@ -42,6 +42,54 @@ def gather_blocks(local, n_total, group=None):
     return torch.cat(pieces, dim=0)
 
 
+def plan_batch_gather(planner, queries, n_total, cap_path=128, group=None, buffers=None):
+    """BASELINE configs[4]: this rank plans ITS contiguous block of the n_total queries (`queries` = that block,
+    from shard_bounds) with pp_plan_batch_dev -- the fixed-stride records (summary + path + profile of every plan,
+    local_planner.cpp:503-583) stay on the device -- and ONE all-gather moves them over NVLink, so that every rank
+    holds all n_total records in input order as a uint8 tensor [n_total (padded to world * per), stride].  Nothing
+    is copied to the host here; a rank that wants the results reads them once (results.PlanRecords).
+    `buffers` (optional dict) keeps the send / receive tensors across calls."""
+    import torch
+    from .capi import pp_query
+    from .results import record_stride
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    per = padded_block(n_total, world)
+    stride = record_stride(cap_path)
+    dev = planner.torch_device
+    buffers = buffers if buffers is not None else {}
+    key = (per, stride, world)
+    if buffers.get("key") != key:
+        buffers["key"] = key
+        buffers["send"] = torch.zeros((per, stride), dtype=torch.uint8, device=dev)
+        buffers["all"] = torch.empty((per * world, stride), dtype=torch.uint8, device=dev) if world > 1 else None
+    send = buffers["send"]
+    m = len(queries)
+    assert m <= per
+    q_arr = queries if not isinstance(queries, (list, tuple)) else (pp_query * m)(*queries)
+    if m:
+        planner.plan_batch_dev(q_arr, m, cap_path, out=send)
+    if world == 1:
+        return send
+    if dev.type == "cuda":
+        ev = torch.cuda.Event()
+        ev.record(planner.stream)
+        torch.cuda.current_stream(dev).wait_event(ev)      # the gather is ordered after the plan kernel, on the device
+    dist.all_gather_into_tensor(buffers["all"], send, group=group)
+    return buffers["all"]
+
+
+def gathered_rows(n_total, world):
+    """Row indices of the n_total real records inside a gathered [world * per, ...] block (the last ranks' blocks
+    end in padding when n_total is not a multiple of world)."""
+    import numpy as np
+    per = padded_block(n_total, world)
+    idx = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        idx.append(np.arange(r * per, r * per + (hi - lo)))
+    return np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
+
+
 def max_over_ranks(value, device, group=None):
     """Timing rule of the bench contract: the slowest rank defines the step."""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

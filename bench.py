@@ -193,51 +193,66 @@ def ref_available():
         return False
 
 
+WORKLOAD = "BASELINE configs[2]: 2^24 oriented-footprint poses per GPU vs 4096^2 grid @0.1 m, 1% area in 16x16 blocks"
+
+
+def headline_config(n_poses):
+    """The static description of the headline workload -- identical in both arms (ours and --impl reference)."""
+    return {"workload": WORKLOAD, "poses_per_gpu": int(n_poses), "collision_mode": "ORIENTED",
+            "grid": "4096x4096 int8 @0.1 m", "footprint_m": [4.7, 1.586], "lattice": "48x17 samples",
+            "l2_policy": "inputs larger than L2 (201 MB poses per step)"}
+
+
 def run_reference(args):
+    """The CPU arm on the SAME workload as ours (oriented footprint, same grid, same Philox poses): the reference
+    has no oriented test (its checkCollision is an axis-aligned cell box, LP:443-496), so the headline value is the
+    oracle's port of the ORIENTED test on all host threads (kind "port"); the reference's OWN collision code
+    (oracle/_ref, REF_AABB semantics) is timed next to it on the same poses and reported inside cpu_baseline,
+    where it pairs with our arm's roofline.ref_aabb figures."""
     from autonomouscar_b200 import PP_COLLISION_ORIENTED
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     grid = make_grid()
     cores = os.cpu_count() or 1
-    have_ref = ref_available()
-    if have_ref:
-        # ~2^26 poses of CPU work for the whole run (the reference does ~1e5 poses/s per thread)
-        n_sample = max(1 << 14, min(1 << 20, (1 << 26) // max(1, args.steps)))
-        rc = ReferenceCollider(grid, cores)
-        one = lambda n: rc.rate(n)[0]                                              # noqa: E731
-        kind = "reference"
-        what = (f"{n_sample} of the 2^24 poses per step; the reference's own checkCollision/calcCollisionMatrix "
-                f"(local_planner.cpp:443-496 with the `return false;` of :445 dropped; axis-aligned box -- the "
-                f"reference has no oriented test), compiled from /root/reference with g++ -O2, one node instance "
-                f"per thread x{cores}")
-    else:
-        n_sample = max(1 << 16, min(1 << 22, (1 << 27) // max(1, args.steps)))
-        one = lambda n: cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n, cores)[0]  # noqa: E731
-        kind = "port"
-        what = f"{n_sample} of the 2^24 poses per step, oracle ORIENTED, std::thread x{cores}, g++ -O2"
-    rates = []
+    # ~2^25 poses of CPU work for the whole run
+    n_sample = max(1 << 15, min(1 << 21, (1 << 25) // max(1, args.steps)))
+    one = lambda n: cpu_collide_rate(grid, PP_COLLISION_ORIENTED, n, cores)[0]      # noqa: E731
     for _ in range(args.warmup):
         one(1 << 16)
+    rates = []
     t0 = time.time()
     for _ in range(args.steps):
         rates.append(one(n_sample))
     wall = time.time() - t0
     v = sum(rates) / len(rates)
-    port_v, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 21, cores)
+    v1, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 17, 1)
+    cb = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
+          "sample": f"{n_sample} of the 2^24 poses per step, oracle port of the ORIENTED test, {cores} threads, g++ -O2",
+          "one_thread_poses_per_s": v1}
+    if ref_available():
+        rc = ReferenceCollider(grid, cores)
+        rc.rate(1 << 16)
+        va, _ = rc.rate(1 << 21)
+        rc.close()
+        cb["ref_aabb"] = {"poses_per_s": va, "cores": cores, "kind": "reference",
+                          "what": "the reference's own checkCollision (LP:443-496, :445 dropped) from oracle/_ref, REF_AABB semantics"}
     line = {
         "impl": "reference", "metric": "collision_checks_per_sec", "value": v, "unit": "poses/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64 -> int cells", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: footprint poses vs 4096x4096 grid @0.1 m, "
-                               "1% area in 16x16-cell blocks", "poses_per_step": n_sample,
-                   "collision_mode": "REF_AABB (reference code)" if have_ref else "ORIENTED (oracle port)"},
-        "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": kind, "sample": what},
+        "vs_baseline": None, "dtype": "int32 fixed-point Q7.24 + f64 set-up", "data": "synthetic",
+        "config": headline_config(args.poses),
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "extra": {"oracle_port_oriented_poses_per_s": port_v, "oracle_port_cores": cores},
     }
     emit(line)
+
+
+# ncu --set full, collide_oriented_kernel, 2^22 poses (profiles/, see README): warp instructions and DRAM bytes per pose
+NCU_ORIENTED = {"warp_inst_per_pose": 49.4, "dram_bytes_per_pose": 12.17,
+                "source": "profiles/r1_ncu_collide_oriented_v4_broad.csv"}
+NCU_DIRECT = {"warp_inst_per_pose": 390.0, "source": "profiles/README.md (direct mode, 82 % issue active)"}
 
 
 # -----------------------------------------------------------------------------------------
@@ -278,11 +293,14 @@ def run_ours(args):
     pl.set_grid(grid)
     box = worlds.pose_box(p)
     n = args.poses
-    # inputs resident in HBM before the timed region: the Philox sampler fills them (row S1)
+    n_words = (n + 31) // 32
+    # inputs resident in HBM before the timed region: the Philox sampler fills them (row S1), stream = rank
     poses = pl.sample_poses_dev(2018, rank, 0, n, *box)
-    # two result buffers: the NCCL gather of step k overlaps the kernel of step k+1
+    # two result buffers: the NCCL gather of step k overlaps the kernel of step k+1.  What is gathered is one BIT
+    # per pose (pp_pack_flags_dev): 2 MiB per rank instead of 16 MiB
     flags2 = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
-    gathered2 = [torch.empty(n * world, dtype=torch.uint8, device=dev) if multi else None for _ in range(2)]
+    bits2 = [torch.empty(n_words, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
+    gathered2 = [torch.empty(n_words * world, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
     gather_done = [None, None]
     flags = flags2[0]
     step_no = [0]
@@ -295,13 +313,15 @@ def run_ours(args):
             pl.stream.wait_event(gather_done[i])        # the buffer's previous gather has finished
         pl.collide_dev(poses, out=flags2[i])
         if multi:
-            # result gather (north_star: NCCL only to gather results), ordered after the kernel
+            # result gather (north_star: NCCL only to gather results), ordered after the kernels
+            pl.pack_flags_dev(flags2[i], out=bits2[i])
             ev = torch.cuda.Event()
             ev.record(pl.stream)
             torch.cuda.current_stream().wait_event(ev)
-            dist.all_gather_into_tensor(gathered2[i], flags2[i])
+            dist.all_gather_into_tensor(gathered2[i], bits2[i])
             gather_done[i] = torch.cuda.Event()
             gather_done[i].record(torch.cuda.current_stream())
+        return i
 
     def barrier():
         pl.sync()
@@ -320,8 +340,9 @@ def run_ours(args):
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(pl.stream)
+    last = 0
     for _ in range(args.steps):
-        step()
+        last = step()
     if multi:
         evj = torch.cuda.Event()
         evj.record(torch.cuda.current_stream())
@@ -333,6 +354,22 @@ def run_ours(args):
     clk.close()
     dev_ms = e0.elapsed_time(e1)
     launches = pl.launch_count() - launches0
+    # ---- N > 1: the gathered result equals what ONE GPU computes for every rank's shard (bit for bit)
+    parity = None
+    if multi:
+        ok = True
+        if rank == 0:
+            got = gathered2[last].view(world, n_words)
+            tmp_p = torch.empty_like(poses)
+            tmp_f = torch.empty(n, dtype=torch.uint8, device=dev)
+            for r in range(world):
+                pl.sample_poses_dev(2018, r, 0, n, *box, out=tmp_p)     # rank r's pose stream, regenerated here
+                pl.collide_dev(tmp_p, out=tmp_f)
+                mine = pl.pack_flags_dev(tmp_f)
+                pl.sync()
+                ok = ok and bool(torch.equal(mine, got[r]))
+            del tmp_p, tmp_f
+        parity = {"gathered_flag_bits_equal_single_gpu_recompute": ok if rank == 0 else None, "ranks_checked": world}
     # per-launch duration of the dominant kernel (events recorded inside the library, on its stream)
     pl.sync()
     torch.cuda.synchronize()
@@ -365,9 +402,10 @@ def run_ours(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = n * world / float(t_e.item())
     assert torch.equal(h_flags, flags.cpu()), "host-pointer path and device path disagree"
+    e2e_aabb = None
 
     # ---- secondary figures on rank 0 only: direct (no broad phase), REF_AABB, plans
-    extra = {}
+    extra, roof_extra = {}, {}
     if rank == 0:
         def timed(fn, reps=5):
             fn(); pl.sync()
@@ -383,9 +421,16 @@ def run_ours(args):
         direct_units = pl.last_narrow_count()
         pl.set_broad_phase(True)
         pl.set_collision_mode(PP_COLLISION_REF_AABB)
-        ms_aabb = timed(lambda: pl.collide_dev(poses, out=flags))
+        ms_aabb = timed(lambda: pl.collide_dev(poses, out=flags), reps=20)
+        aabb_hit = float(flags.float().mean().item())
+        pl.collide(h_poses, out=h_flags)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pl.collide(h_poses, out=h_flags)
+        e2e_aabb = 3 * n / (time.perf_counter() - t0)
         pl.set_collision_mode(PP_COLLISION_ORIENTED)
         ms_sampler = timed(lambda: pl.sample_poses_dev(2018, rank, 0, n, *box, out=poses))
+        ms_pack = timed(lambda: pl.pack_flags_dev(flags), reps=10)
         l2_gbps = pl.bench_l2_gather(16 << 20)      # random 32 B sectors of a 16 MiB (L2-resident) buffer
         # row S3 stand-alone: 2^22 random 0.45 m edges (one 150 ms step at 1.5 m/s), oriented footprint at every
         # search_res / 2 along each
@@ -406,36 +451,53 @@ def run_ours(args):
         query_xy = (torch.rand((nn_q, 2), generator=gen, device=dev) - 0.5) * 800.0
         torch.cuda.synchronize()
         ms_nn = timed(lambda: pl.nearest_dev(node_xy, query_xy), reps=3)
+        peak_hbm = _peaks()[0]
+        stream_bytes = 13 * n                      # what REF_AABB has to move: 12 B pose in + 1 B flag out
+        roof_extra = {
+            # the only variant that does SURVEY 8(d)'s per-pose work: every pose runs all 816 lattice samples
+            "oriented_direct": {"poses_per_s": n / (ms_direct * 1e-3), "kernel_ms": ms_direct,
+                                "algorithmic_GBps_829B_per_pose": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / peak_hbm,
+                                "frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / l2_gbps,
+                                "bound": "issue", "narrow_units": direct_units},
+            "l2_gather_peak_GBps_measured": l2_gbps,
+            # REF_AABB (rows A10/A11, the reference-faithful test): one map look-up per pose, HBM-stream bound
+            "ref_aabb": {"kernel": "collide_aabb_stream_kernel", "poses_per_s": n / (ms_aabb * 1e-3), "kernel_ms": ms_aabb,
+                         "bound": "hbm", "bytes_per_launch": stream_bytes,
+                         "achieved_GBps": stream_bytes / (ms_aabb * 1e-3) / 1e9, "peak_GBps": peak_hbm,
+                         "frac": stream_bytes / (ms_aabb * 1e-3) / 1e9 / peak_hbm, "hit_rate": aabb_hit,
+                         "e2e_poses_per_s_host_buffers": e2e_aabb},
+        }
         extra = {
-            "oriented_direct_poses_per_s": n / (ms_direct * 1e-3), "oriented_direct_narrow_units": direct_units,
-            "oriented_direct_frac_of_hbm_roofline": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / _peaks()[0],
-            "ref_aabb_poses_per_s": n / (ms_aabb * 1e-3),
-            "ref_aabb_frac_of_hbm_roofline": ALG_BYTES_AABB * n / (ms_aabb * 1e-3) / 1e9 / _peaks()[0],
             "philox_sampler_poses_per_s": n / (ms_sampler * 1e-3),
             "philox_sampler_write_GBps": 12 * n / (ms_sampler * 1e-3) / 1e9,
-            "l2_gather_peak_GBps_measured": l2_gbps,
+            "pack_flags_ms": ms_pack,
             "edge_collision": {"edges": n_edges, "steps_per_edge": 3, "ms": ms_edges, "edges_per_s": n_edges / (ms_edges * 1e-3),
                                "hit_rate": float(e_flags.float().mean().item())},
             "nearest_neighbour": {"nodes": nn_nodes, "queries": nn_q, "ms": ms_nn,
                                   "distance_evals_per_s": nn_nodes * nn_q / (ms_nn * 1e-3),
                                   "algorithmic_GBps_8B_per_node_per_query": 8.0 * nn_nodes * nn_q / (ms_nn * 1e-3) / 1e9},
-            "oriented_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_per_step * 1e-3) / 1e9 / l2_gbps,
-            "oriented_direct_frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / l2_gbps,
         }
+        del edges, e_flags, node_xy, query_xy
     plans = bench_plans(pl, rank, world, dev, multi, args) if not args.skip_plans else None
     costmap = bench_costmap(args) if (rank == 0 and not args.skip_plans) else None
 
     if rank == 0:
         peak, peak_kind = _peaks()
+        clocks = clk.summary()
         k_ms = sum(kernel_ms) / len(kernel_ms)
-        achieved = ALG_BYTES_ORIENTED * n / (k_ms * 1e-3) / 1e9
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        issue_peak = sm_count * 4 * sm_mhz * 1e6 / 1e9          # G warp-instructions/s: 4 schedulers per SM, 1 per clock
+        issue_achieved = NCU_ORIENTED["warp_inst_per_pose"] * n / (k_ms * 1e-3) / 1e9
         cpu = None
         if not args.skip_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             v_port, secs_port = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 22, cores)
             v1, _ = cpu_collide_rate(grid, PP_COLLISION_ORIENTED, 1 << 20, 1)
-            port_txt = (f"oracle port, ORIENTED, same poses: {v_port:.3e} poses/s on {cores} threads, "
-                        f"{v1:.3e} on 1 thread (g++ -O2)")
+            cpu = {"value": v_port, "unit": "poses/s", "cores": cores, "kind": "port",
+                   "sample": f"{1 << 22} of the 2^24 poses ({secs_port:.2f} s), oracle port of the ORIENTED test, g++ -O2",
+                   "one_thread_poses_per_s": v1}
             if ref_available():
                 n_sample = 1 << 22
                 rc = ReferenceCollider(grid, cores)
@@ -445,35 +507,44 @@ def run_ours(args):
                 rc1 = ReferenceCollider(grid, 1)
                 v_1, _ = rc1.rate(1 << 17)
                 rc1.close()
-                cpu = {"value": v, "unit": "poses/s", "cores": cores, "kind": "reference",
-                       "sample": f"{n_sample} of the 2^24 poses ({secs:.2f} s wall): the reference's own checkCollision "
-                                 f"(local_planner.cpp:443-496, axis-aligned box; it has no oriented test) compiled from "
-                                 f"the reference sources, g++ -O2, one node instance per thread x{cores}; "
-                                 f"1 thread: {v_1:.3e} poses/s. " + port_txt}
-            else:
-                cpu = {"value": v_port, "unit": "poses/s", "cores": cores, "kind": "port",
-                       "sample": f"{1 << 22} of the 2^24 poses ({secs_port:.2f} s). " + port_txt}
+                cpu["ref_aabb"] = {"poses_per_s": v, "cores": cores, "one_thread_poses_per_s": v_1, "kind": "reference",
+                                   "what": "the reference's own checkCollision (LP:443-496) from oracle/_ref; pairs with roofline.ref_aabb"}
+        roofline = {"bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                    "frac": issue_achieved / issue_peak,
+                    "how": "ncu warp instructions per pose x poses / CUDA-event kernel time vs SMs x 4 x SM clock",
+                    "warp_inst_per_pose": NCU_ORIENTED["warp_inst_per_pose"], "inst_source": NCU_ORIENTED["source"],
+                    "traffic": NCU_ORIENTED["dram_bytes_per_pose"] * n, "traffic_unit": "bytes/launch",
+                    "kernel": "collide_oriented_kernel", "kernel_ms": k_ms, "narrow_phase_poses": narrow_units,
+                    # the byte view of the same launch: what it really moves (12 B pose + 1 B flag) against HBM
+                    "hbm": {"bytes_per_launch": 13 * n, "achieved_GBps": 13 * n / (k_ms * 1e-3) / 1e9, "peak_GBps": peak,
+                            "frac": 13 * n / (k_ms * 1e-3) / 1e9 / peak, "peak_kind": peak_kind},
+                    "survey_829B_per_pose_GBps": ALG_BYTES_ORIENTED * n / (k_ms * 1e-3) / 1e9}
+        roofline.update(roof_extra)
+        if plans:
+            roofline["plans"] = {k: plans[k] for k in ("batch_queries", "plan_kernel_ms_rank0", "plans_per_s_kernel_rank0")
+                                 if k in plans}
+        e2e = {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": n,
+               "h2d_GBps_per_rank": 12 * n / float(t_e.item()) / 1e9}
+        if plans:
+            e2e["plans"] = {k: plans[k] for k in ("batch_queries", "plans_per_s", "gathered_records_equal_single_gpu",
+                                                  "record_bytes", "single_query_ms", "found") if k in plans}
+        if parity:
+            roofline["parity_at_n_gpus"] = parity
+        cfg = headline_config(n)
         line = {
             "metric": "collision_checks_per_sec", "value": value, "unit": "poses/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 fixed-point Q7.24 + f64 set-up", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: 2^24 oriented-footprint poses per GPU vs 4096x4096 "
-                                   "grid @0.1 m, 1% area in 16x16-cell blocks; flags all-gathered (NCCL) when N>1",
-                       "poses_per_gpu": n, "collision_mode": "ORIENTED", "broad_phase": True,
-                       "hit_rate": hit_rate, "l2_policy": "inputs larger than L2 (201 MB poses per step)",
-                       "rank_cpu_affinity": numa},
-            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": n},
+            "config": cfg,
+            "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": DRAM_BYTES_PER_POSE_NCU * n, "traffic_unit": "bytes/launch",
-                         "traffic_source": "profiles/r1_ncu_collide_oriented_v4_broad.csv (dram read+write / 2^22 poses)",
-                         "peak_kind": peak_kind,
-                         "kernel": "collide_oriented_kernel", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_pose": ALG_BYTES_ORIENTED, "narrow_phase_poses": narrow_units},
+            "roofline": roofline,
             "cpu_baseline": cpu,
-            "clocks": clk.summary(),
+            "clocks": clocks,
             "wall_s_timed_region": wall,
+            "run": {"hit_rate": hit_rate, "broad_phase": True, "rank_cpu_affinity": numa,
+                    "gather": "1 bit per pose (pp_pack_flags_dev), ncclAllGather" if multi else None, "parity": parity},
             "extra": extra,
             "plans": plans,
             "costmap": costmap,
@@ -499,17 +570,14 @@ def bench_costmap(args):
     tfs = worlds.costmap_tfs(*car)
     gg = worlds.road_like_global_grid(G, 17, zero_at=worlds.costmap_corner_global_cells(p, *car))
     scenes = [worlds.costmap_scene(s) for s in range(4)]
-    have_ref = ref_available()
+    have_ref = ref_available() and not args.skip_cpu
     if have_ref:
         from oracle import ref_binding as ref
         have_ref = ref.costmap_available()
     if have_ref:
-        ref.costmap_set_tfs(tfs)
-        for sc in scenes:
-            ref.costmap_derive_inputs(sc)        # the tf numbers exactly as the reference node reads them
-    else:
-        for sc in scenes:                        # planar tf numbers computed directly
-            worlds.fill_costmap_tf(sc, car)
+        ref.costmap_set_tfs(tfs)                 # only the CPU leg (the reference node reads tf itself)
+    for sc in scenes:                            # the GPU arm: planar tf numbers computed directly, no reference code
+        worlds.fill_costmap_tf(sc, car)
     cm = LocalCostmap(p, device=0)
     cm.set_global_grid(gg)
     out = {"config": "300x300 @0.25 m, 2x640 rays, 16x512 cloud, 12000^2 global map (full_sim.launch sizes)"}
@@ -757,9 +825,10 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     import torch
     import torch.distributed as dist
 
-    from autonomouscar_b200 import (PP_COLLISION_ORIENTED, PP_PLAN_FOUND, PlanBatch, Planner, default_params,
+    from autonomouscar_b200 import (PP_COLLISION_ORIENTED, PP_PLAN_FOUND, PlanBatch, PlanRecords, Planner, default_params,
                                     sharding, worlds)
     from autonomouscar_b200.capi import pp_query
+    from autonomouscar_b200.results import record_stride
     p = default_params(collision_mode=PP_COLLISION_ORIENTED, max_nodes=10000)
     grid = worlds.block_grid(300, 300, frac=0.01, block=4, seed=9)
     worlds.clear_disc(grid, p, 0.0, 0.0, 4.0)
@@ -770,22 +839,44 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     lo, hi = sharding.shard_bounds(n_total, rank, world)
     qs = qs_all[lo:hi]
     q_arr = (pp_query * len(qs))(*qs)
-    buf = PlanBatch(len(qs), cap_path=256)
+    CAP = 128                                                   # path slots per record (longest path here: ~70 poses)
+    stride = record_stride(CAP)
     warm = PlanBatch(64, cap_path=256)
     pl.plan_batch_into((pp_query * 64)(*qs[:64]), warm)                       # warm-up
-    sharding.gather_blocks(torch.zeros((hi - lo, 5), dtype=torch.int64, device=dev), n_total)
+    buffers = {}
+    sharding.plan_batch_gather(pl, q_arr, n_total, cap_path=CAP, buffers=buffers)
+    h_rec = torch.empty((sharding.padded_block(n_total, world) * world, stride), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
     if multi:
         dist.barrier()
     torch.cuda.synchronize()
-    reps, dts, kms = 3, [], []
+    # BASELINE configs[4]: every rank plans its block, the fixed-stride records (summary + path + profile) stay on
+    # the device, ONE all-gather over NVLink; the rank that wants the results (rank 0) copies them to the host once
+    reps, dts, kms = 5, [], []
     for _ in range(reps):
         t0 = time.perf_counter()
-        pl.plan_batch_into(q_arr, buf)
-        rec = sharding.gather_blocks(torch.from_numpy(buf.records()).to(dev), n_total)
+        allrec = sharding.plan_batch_gather(pl, q_arr, n_total, cap_path=CAP, buffers=buffers)
+        if rank == 0:
+            h_rec.copy_(allrec, non_blocking=True)
+        pl.sync()
         torch.cuda.synchronize()
         dts.append(sharding.max_over_ranks(time.perf_counter() - t0, dev))
         kms.append(pl.last_phase_ms()[4])
     dt = sorted(dts)[len(dts) // 2]
+    rows = sharding.gathered_rows(n_total, world)
+    rec_view = PlanRecords(h_rec.numpy()[rows], CAP) if rank == 0 else None
+    # the same queries through the host-pointer call (pp_plan_batch: results scattered into caller arrays)
+    buf = PlanBatch(len(qs), cap_path=256)
+    pl.plan_batch_into(q_arr, buf)
+    t0 = time.perf_counter()
+    pl.plan_batch_into(q_arr, buf)
+    dt_host = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    records_equal = None
+    if rank == 0 and multi:
+        # N > 1 parity: ONE GPU plans all n_total queries; the gathered records must equal that run byte for byte
+        one = pl.plan_batch_dev((pp_query * n_total)(*qs_all), n_total, cap_path=CAP)
+        pl.sync()
+        records_equal = bool(np.array_equal(one.cpu().numpy(), h_rec.numpy()[rows]))
+        del one
     # single-query latency (config 2)
     lat, lat_k = [], []
     one = PlanBatch(1, cap_path=256)
@@ -822,6 +913,17 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
             t1 = time.perf_counter()
             c1 = orc.plan(p1, rgrid, q1, math_mode=orc.MATH_LIBM)
             cfg1["cpu_oracle_ms_1thread"] = 1e3 * (time.perf_counter() - t1)
+            if ref_available():
+                # BASELINE configs[0]: the reference planner itself, headless (oracle/_ref = its own local_planner.cpp
+                # with the collision code of LP:446-496 enabled), one thread like the node
+                from oracle import ref_binding as ref
+                pool1 = ref.RefPool(p1, grid_as_msg(rgrid), 1, ref.AABB)
+                pool1.plan_batch([q1])
+                r_secs, r_st, r_nn = pool1.plan_batch([q1])
+                pool1.close()
+                cfg1["cpu_reference_ms_1thread"] = 1e3 * r_secs
+                cfg1["cpu_reference_kind"] = "reference: local_planner.cpp from /root/reference (oracle/_ref), g++ -O2"
+                cfg1["reference_same_outcome_and_tree_size"] = bool((int(r_st[0]) != 0) == (int(g1.status) != 0) and int(r_nn[0]) == int(g1.n_nodes))
             d1 = orc.plan(p1, rgrid, q1, math_mode=orc.MATH_DET)
             cfg1["bit_exact_vs_oracle"] = bool(d1.summary() == g1.summary() and np.array_equal(d1.path_xy, g1.path_xy)
                                                and np.array_equal(d1.node_parent, g1.node_parent))
@@ -894,10 +996,15 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
         del g4
     out = None
     if rank == 0:
-        found = int((rec[:, 0] == PP_PLAN_FOUND).sum().item())
+        found = int((rec_view.field("status") == PP_PLAN_FOUND).sum())
+        k_ms = sorted(kms)[len(kms) // 2]
         out = {"batch_queries": n_total, "plans_per_s": n_total / dt, "batch_wall_s": dt,
-               "plan_kernel_ms_rank0": sorted(kms)[len(kms) // 2], "found": found,
-               "mean_nodes": float(rec[:, 2].float().mean().item()),
+               "what": "pp_plan_batch_dev per rank + one all-gather of fixed-stride records + one D2H on rank 0",
+               "record_bytes": stride, "gathered_records_equal_single_gpu": records_equal,
+               "plans_per_s_host_pointer_call": n_total / dt_host,
+               "plan_kernel_ms_rank0": k_ms, "plans_per_s_kernel_rank0": len(qs) / (k_ms * 1e-3), "found": found,
+               "mean_nodes": float(rec_view.field("n_nodes").mean()),
+               "longest_path": int(rec_view.field("n_path").max()),
                "single_query_ms": 1e3 * sorted(lat)[len(lat) // 2], "single_query_kernel_ms": sorted(lat_k)[len(lat_k) // 2],
                "single_query_nodes": int(r1.n_nodes),
                "grid": "300x300 @0.25 m (full_sim.launch), ORIENTED, node cap 10000",
@@ -915,9 +1022,8 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
             out["cpu_plans_per_s_1thread"] = 32 / secs1
             # parity of the sample against the deterministic oracle
             secs2, st2, nn2, dg2 = orc.plan_batch_timed(p, grid, qs_all[:nq], math_mode=orc.MATH_DET, n_threads=cores)
-            mine = rec[:nq].cpu().numpy()
-            out["parity_sample_ok"] = bool((mine[:, 0] == st2).all() and (mine[:, 2] == nn2).all() and
-                                           (mine[:, 4] == (dg2 & np.uint64(0x7FFFFFFFFFFFFFFF)).astype(np.int64)).all())
+            out["parity_sample_ok"] = bool((rec_view.field("status")[:nq] == st2).all() and (rec_view.field("n_nodes")[:nq] == nn2).all()
+                                           and (rec_view.field("tree_digest")[:nq] == dg2.astype(np.uint64)).all())
             if ref_available():
                 # the reference node itself (oracle/_ref), REF_AABB = its own collision code enabled:
                 # same queries through the CUDA path in that mode and through the reference binary

@@ -104,7 +104,13 @@ typedef struct pp_params {
   int32_t rrt_max_samples;          /* total sample budget                                 */
   double rrt_goal_bias;             /* probability that a sample is the goal itself        */
   double rrt_goal_tolerance;        /* |dx|,|dy| box around the goal that ends the search  */
-  int32_t reserved[8];
+  /* A18: LP:276-283 calls an UNQUALIFIED abs().  With the toolchain the reference mandates (ROS Kinetic =
+     Ubuntu 16.04 / GCC 5, whose <cmath> predates the <stdlib.h> overload wrapper) that may resolve to
+     int abs(int): the differences are truncated toward zero before the comparison, i.e. the tolerances
+     silently become "< 1.0".  0 (default) = the double overload, what g++ 13 and oracle/_ref resolve to;
+     1 = the int reading.                                                                              */
+  int32_t goal_test_int_abs;
+  int32_t reserved[7];
 } pp_params;
 
 /* one plan request == one prius_msgs/LocalNav message (already in the base_link frame,
@@ -211,6 +217,12 @@ int pp_get_cspace(pp_handle* h, int8_t* out_host, size_t capacity);
 int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* out_flags_host);
 /* device pointers; asynchronous on the handle's stream; pp_sync() to wait */
 int pp_collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* out_flags_dev);
+/* Result flags as one bit per pose (word k bit b = flag 32k + b; (n + 31) / 32 words, the unused bits of the
+   last word are 0): what the multi-GPU result gather moves (NCCL only to gather
+   results -- 2 MiB instead of 16 MiB per 2^24 poses).  Asynchronous on the handle's stream; flags_dev must be
+   16-byte aligned. */
+int pp_pack_flags_dev(pp_handle* h, int64_t n, const uint8_t* flags_dev, uint32_t* out_bits_dev);
+int pp_unpack_flags_dev(pp_handle* h, int64_t n, const uint32_t* bits_dev, uint8_t* out_flags_dev);
 /* along-edge variant (row S3): edge k runs from (x0,y0) to (x1,y1) with constant yaw; the
    footprint is tested every search_res/2 (the spacing rule of LP:308).
    edges = n x (x0, y0, x1, y1, yaw) float32 */
@@ -256,6 +268,30 @@ int pp_plan_batch(pp_handle* h, int32_t n, const pp_query* queries, pp_result* r
 /* n independent queries, query k against grid queries[k].reserved of the bank (pp_set_grid_bank_dev):
    N simulated cars, each planning on its own costmap, in one launch */
 int pp_plan_batch_banked(pp_handle* h, int32_t n, const pp_query* queries, pp_result* results);
+/* Device-resident results ("fixed-stride result records gathered via NCCL").
+   Query k leaves one record of pp_plan_record_stride(cap_path) bytes at out_records_dev + k * stride:
+
+     pp_plan_record_header (64 B) | path_xy[cap_path][2] f64 | yaw_rates[cap_path] f64 | durations[cap_path] f64 |
+     speeds[cap_path] f64 | path_node_ids[cap_path] i32        (unused entries: 0 / -1; padded to 16 B)
+
+   i.e. everything planPath publishes (LP:503-583) plus the tree summary.  The call is ASYNCHRONOUS on the
+   handle's stream: nothing is copied back, so the records can go straight into an NCCL all-gather
+   (autonomouscar_b200/sharding.py, pp_group_plan_batch) and only the rank that wants them copies them to the
+   host, once.  `queries_host` is read before the call returns when it is pageable memory; pinned memory must
+   stay valid until the stream reaches the kernel.  A path longer than cap_path sets `truncated`. */
+typedef struct pp_plan_record_header {
+  int32_t status, n_expansions, n_nodes, n_open, n_closed, n_path, n_profile, n_candidates, n_collisions;
+  int32_t truncated;       /* 1: n_path > cap_path, the arrays hold the first cap_path poses                    */
+  int32_t cap_path;        /* the array length this record was written with                                     */
+  int32_t reserved;
+  uint64_t tree_digest;
+  uint64_t reserved2;
+} pp_plan_record_header;
+size_t pp_plan_record_stride(int32_t cap_path);
+int pp_plan_batch_dev(pp_handle* h, int32_t n, const pp_query* queries_host, int32_t cap_path, void* out_records_dev);
+/* host-side helper: scatter n records (HOST memory, written with `cap_path`) into pp_result structs whose
+   cap_path / array pointers the caller has set, like pp_plan_batch would have filled them */
+int pp_plan_records_unpack(const void* records_host, int32_t n, int32_t cap_path, pp_result* results);
 /* Debug bitmap of the most recent single-query pp_plan: out[i*H + j] = 1 for every cell that
    markVisited (LP:318-326) touched -- one mark per child returned by getNeighbors, cleared at
    the start of each plan like clearVisited (LP:251-262).  The reference never reads it on the
@@ -303,8 +339,12 @@ int pp_group_set_grid(pp_group* g, const int8_t* data_host, int32_t width, int32
    ncclAllGather so every device (and the host copy) holds all n flags in input order */
 int pp_group_collide_batch(pp_group* g, int64_t n, const float* poses_host,
                            uint8_t* out_flags_host);
-/* queries sharded contiguously by index; fixed-stride result records gathered via NCCL */
+/* queries sharded contiguously by index; every device leaves fixed-stride records (pp_plan_batch_dev) in its send
+   buffer, ONE ncclAllGather moves them over NVLink, the host copy comes from device 0.  (Results that ask for node
+   arrays / expansion ids are planned per device through pp_plan_batch instead, without a gather.) */
 int pp_group_plan_batch(pp_group* g, int32_t n, const pp_query* queries, pp_result* results);
+/* device `device_index`'s copy of the records gathered by the last pp_group_plan_batch, input order */
+int pp_group_records_dev(pp_group* g, int device_index, const void** out_records_dev);
 
 #ifdef __cplusplus
 }

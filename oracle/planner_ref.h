@@ -42,6 +42,14 @@ struct DetMath {
   static double sq(double x) { return x * x; }
 };
 
+// The implicit double -> int conversion of an `int abs(int)` call (A18).  C++ leaves values outside the int
+// range undefined; the build defines them (as everywhere else) as "too far away":
+// anything not strictly inside +-2^30, NaN included, fails the tolerance test.
+inline bool int_abs_within(double v, double tol) {
+  if (!(std::fabs(v) < 1073741824.0)) return false;
+  return std::abs(static_cast<int>(v)) <= tol;
+}
+
 // graph_node.hpp:7-31.  `id` (slot number = order of openNode calls) and `closed_seq` are
 // book-keeping added here; they take no part in equality or ordering.
 struct TreeNode {
@@ -258,15 +266,20 @@ class RefPlanner {
   bool check_for_goal(const TreeNode& node, TreeNode* goal_node) const {
     const auto pts = interpolate_points(node.cx, node.cy, node.px, node.py);
     for (const auto& pt : pts) {
+      // A18: pp_params.goal_test_int_abs (or the ORACLE_INT_ABS build switch) selects the int abs(int)
+      // reading: the double differences are truncated toward zero by the implicit conversion
 #ifdef ORACLE_INT_ABS
-      const bool hit = std::abs(static_cast<int>(pt.first - Q.goal_x)) <= P.goal_pos_tolerance &&
-                       std::abs(static_cast<int>(pt.second - Q.goal_y)) <= P.goal_pos_tolerance &&
-                       std::abs(static_cast<int>(node.velocity - Q.goal_speed)) <= P.goal_speed_tolerance;
+      const bool int_abs = true;
 #else
-      const bool hit = std::fabs(pt.first - Q.goal_x) <= P.goal_pos_tolerance &&
-                       std::fabs(pt.second - Q.goal_y) <= P.goal_pos_tolerance &&
-                       std::fabs(node.velocity - Q.goal_speed) <= P.goal_speed_tolerance;
+      const bool int_abs = P.goal_test_int_abs != 0;
 #endif
+      const bool hit = int_abs
+          ? (int_abs_within(pt.first - Q.goal_x, P.goal_pos_tolerance) &&
+             int_abs_within(pt.second - Q.goal_y, P.goal_pos_tolerance) &&
+             int_abs_within(node.velocity - Q.goal_speed, P.goal_speed_tolerance))
+          : (std::fabs(pt.first - Q.goal_x) <= P.goal_pos_tolerance &&
+             std::fabs(pt.second - Q.goal_y) <= P.goal_pos_tolerance &&
+             std::fabs(node.velocity - Q.goal_speed) <= P.goal_speed_tolerance);
       if (hit) {
         const double dx = pt.first - node.cx, dy = pt.second - node.cy;  // LP:293-295
         TreeNode gn;

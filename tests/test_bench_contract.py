@@ -21,6 +21,10 @@ def test_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert "workload" in d["config"]
+    # the static description of the workload is the SAME object in both arms (same_config for the driver)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.headline_config(bench.N_POSES) and d["config"]["collision_mode"] == "ORIENTED"
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

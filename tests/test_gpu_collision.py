@@ -221,3 +221,52 @@ def test_8192_grid_matches_oracle(oracle, cuda_device):
         np.testing.assert_array_equal(got, want)
         assert 0 < want.sum() < len(want)
         pl.close()
+
+
+@pytest.mark.parametrize("res,W,H", [(0.1, 4096, 4096), (0.25, 300, 300), (0.1, 517, 333), (0.05, 8192, 2048)])
+def test_ref_aabb_stream_kernel_cell_boundaries(oracle, cuda_device, res, W, H):
+    """REF_AABB batch kernel (TMA-staged pose stream, fast base-cell arithmetic with an exact fallback): poses ON
+    cell boundaries (k * res as float32 and its float32 neighbours, where int(W/2 - y/res) of LP:471-472 flips),
+    at the map border, far away, NaN / inf -- against the oracle's float64 division, bit for bit; the aligned
+    streaming variant, the misaligned plain variant and a ragged tail."""
+    p = default_params(costmap_res=res, costmap_width=W, costmap_height=H, collision_mode=PP_COLLISION_REF_AABB)
+    grid = worlds.block_grid(W, H, frac=0.02, block=8, seed=W ^ H)
+    rng = np.random.default_rng(99)
+    n = 200003
+    poses = worlds.random_poses(p, n, seed=5, inset_m=-6.0).copy()
+    k = rng.integers(-W, W, n // 2)
+    on = (k * res).astype(np.float32)
+    on = np.nextafter(on, np.where(rng.integers(0, 3, on.size) == 0, np.float32(-1e9), np.where(rng.integers(0, 2, on.size) == 0, np.float32(1e9), on)).astype(np.float32))
+    poses[: n // 2, 1] = on                                              # y decides the first index (LP:471)
+    poses[n // 4: 3 * n // 4, 0] = (rng.integers(-H, H, 3 * n // 4 - n // 4) * res).astype(np.float32)
+    poses[-8:, 0] = [np.nan, np.inf, -np.inf, 3e9, -3e9, 1e30, 0.0, -0.0]
+    poses[-16:-8, 1] = [np.nan, np.inf, -np.inf, 3e9, -3e9, 1e30, 0.0, -0.0]
+    want, _ = oracle.collide_batch(p, grid, poses)
+    assert 0.0 < want.mean() < 1.0
+    pl = _planner(p, grid)
+    d = torch.from_numpy(poses).cuda()
+    got = pl.collide_dev(d); pl.sync()
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # misaligned views (pose pointer 12 B off a 16 B boundary, flag pointer 1 B off): the plain kernel
+    out = torch.zeros(n + 1, dtype=torch.uint8, device="cuda")
+    pl.collide_dev(d[1:], out=out[1:n]); pl.sync()
+    np.testing.assert_array_equal(out[1:n].cpu().numpy(), want[1:])
+    # host-pointer entry (chunked pipeline) agrees
+    np.testing.assert_array_equal(pl.collide(poses), want)
+    pl.close()
+
+
+def test_pack_unpack_flags(cuda_device):
+    """pp_pack_flags_dev / pp_unpack_flags_dev: word k bit b = flag 32k + b, ragged lengths, unused bits zero."""
+    from autonomouscar_b200 import Planner
+    pl = Planner(default_params(), device=0)
+    rng = np.random.default_rng(3)
+    for n in (1, 15, 16, 31, 32, 33, 1000, 65536, 100003):
+        f = (rng.random(n) < 0.3).astype(np.uint8)
+        d = torch.from_numpy(f).cuda()
+        bits = pl.pack_flags_dev(d); pl.sync()
+        want = np.packbits(np.pad(f, (0, (-n) % 32)), bitorder="little").view(np.uint32)
+        np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32), want)
+        back = pl.unpack_flags_dev(bits, n); pl.sync()
+        np.testing.assert_array_equal(back.cpu().numpy(), f)
+    pl.close()

@@ -63,6 +63,20 @@ def test_probe_numbers_from_survey(cuda_device):
     pl.close()
 
 
+def test_goal_test_int_abs_reading_matches_oracle(oracle, cuda_device):
+    """A18 on the CUDA path: pp_params.goal_test_int_abs = 1 is the `int abs(int)` reading of LP:276-283."""
+    from autonomouscar_b200 import Planner
+    p = default_params(goal_test_int_abs=1, max_nodes=12000)
+    pl = Planner(p, device=0)
+    for kw in QUERIES[:4] + [dict(goal_x=5e9, goal_y=0.0, start_speed=1.0)]:
+        q = make_query(**kw)
+        got = pl.plan(q)
+        ref = oracle.plan(p, None, q, math_mode=oracle.MATH_DET)
+        _assert_same(got, ref)
+    assert pl.plan(make_query(**QUERIES[0])).n_expansions < 56          # the double reading needs 56 (SURVEY section 6)
+    pl.close()
+
+
 def test_caps_replace_the_wall_clock_guard(oracle, cuda_device):
     from autonomouscar_b200 import Planner
     # unreachable goal speed -> never found; node cap and expansion cap both bite

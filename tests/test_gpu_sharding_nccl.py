@@ -49,6 +49,9 @@ def _worker(rank, world, port, n, ret):
         qlo, qhi = sharding.shard_bounds(len(queries), rank, world)
         rec = sharding.plan_records(pl.plan_batch(queries[qlo:qhi]), torch.device("cuda", rank))
         recs = sharding.gather_blocks(rec, len(queries))
+        # the real thing: device-resident fixed-stride records (summary + path + profile), one all-gather over NVLink
+        full = sharding.plan_batch_gather(pl, queries[qlo:qhi], len(queries), cap_path=128)
+        torch.cuda.synchronize()
         # row N4 sharded: this rank's block of cars around this rank's planner, states gathered once
         from autonomouscar_b200 import rollout
         from test_rollout import _starts
@@ -56,6 +59,7 @@ def _worker(rank, world, port, n, ret):
         if rank == 0:
             ret["flags"] = flags.cpu().numpy().copy()
             ret["recs"] = recs.cpu().numpy().copy()
+            ret["full"] = full.cpu().numpy()[sharding.gathered_rows(len(queries), world)].copy()
             ret["trace"] = trace.cpu().numpy().copy()
         pl.close()
     finally:
@@ -78,6 +82,10 @@ def test_nccl_gather_equals_single_gpu(cuda_device):
     np.testing.assert_array_equal(ret["flags"], want)
     want_rec = sharding.plan_records(pl.plan_batch(queries), torch.device("cpu")).numpy()
     np.testing.assert_array_equal(ret["recs"], want_rec)
+    from autonomouscar_b200.capi import pp_query
+    one = pl.plan_batch_dev((pp_query * len(queries))(*queries), len(queries), cap_path=128)
+    pl.sync()
+    np.testing.assert_array_equal(ret["full"], one.cpu().numpy())      # gathered paths byte-identical to the 1-GPU run
     assert 0 < want.sum() < n
     from autonomouscar_b200 import rollout
     from test_rollout import _starts

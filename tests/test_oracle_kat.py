@@ -185,6 +185,28 @@ def test_planner_caps_and_exhaustion(oracle):
     assert r.status == PP_PLAN_EXHAUSTED and r.n_nodes == 1 and r.n_collisions == r.n_candidates > 0
 
 
+def test_goal_test_int_abs_reading(oracle):
+    """A18: with `int abs(int)` (the overload the reference's mandated GCC 5 toolchain may pick at LP:276-283)
+    every difference is truncated toward zero first, so the 0.1 m / 0.5 m/s tolerances act as "< 1.0": the goal
+    test fires on the first extrapolated point within 1 m of the goal, at any speed within 1 m/s of the goal's.
+    The double reading is the default (what g++ 13 and oracle/_ref resolve to)."""
+    q = make_query(20, 0, start_speed=0.0)
+    dbl = oracle.plan(default_params(), None, q)
+    iab = oracle.plan(default_params(goal_test_int_abs=1), None, q)
+    assert dbl.status == iab.status == PP_PLAN_FOUND
+    assert iab.n_expansions < dbl.n_expansions and iab.n_nodes < dbl.n_nodes
+    end_d, end_i = dbl.path_xy[-1], iab.path_xy[-1]
+    assert abs(end_d[0] - 20) <= 0.1 and abs(end_d[1]) <= 0.1
+    assert 0.1 < abs(end_i[0] - 20) < 1.0 and abs(end_i[1]) < 1.0          # inside the truncated box, outside the real one
+    # the searches are identical up to the expansion at which the int reading stops
+    np.testing.assert_array_equal(iab.expansion_ids, dbl.expansion_ids[: iab.n_expansions])
+    n = iab.n_nodes - 1                                                      # (the terminal node differs)
+    np.testing.assert_array_equal(iab.node_state[:n, :6], dbl.node_state[:n, :6])
+    # out-of-range differences never pass (defined behaviour where the conversion would be UB)
+    far = oracle.plan(default_params(goal_test_int_abs=1, max_expansions=3), None, make_query(5e9, 0, start_speed=1.0))
+    assert far.status == PP_PLAN_CAP
+
+
 def test_sampling_planner_oracle(oracle):
     p = default_params(costmap_res=0.1, costmap_width=1024, costmap_height=1024, collision_mode=PP_COLLISION_ORIENTED,
                        time_step_ms=1000.0, rrt_samples_per_round=64, rrt_max_samples=200000, max_nodes=100000,
