@@ -25,39 +25,86 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 // is replaced by a multiplication with 1/res whenever that provably truncates to the same integer: both
 // quotients are within 3 ulp of y/res, so for |result| < 2^20 the two differences lie within 1.2e-9 of each
 // other and agree on the integer part unless the fast value is within 2^-20 of an integer -- those (and
-// anything large or NaN) take the exact division.
-__device__ __forceinline__ bool aabb_base_cell(double half, double inv_res, double res, float v, int* out) {
-  const double vd = static_cast<double>(v);
-  const double s = dm::sub(half, dm::mul(vd, inv_res));
-  if (fabs(dm::sub(s, rint(s))) >= 9.5367431640625e-07 && fabs(s) < 1048576.0) {
-    *out = __double2int_rz(s);
-    return true;
-  }
-  return dm::trunc_to_int(dm::sub(half, dm::div(vd, res)), out);
+// anything large or NaN) take the exact division.  The fast path is straight-line code (no conversion
+// instructions, no branches), so the coordinates of several poses overlap in the pipelines.
+constexpr int kAabbFar = -(1 << 30);      // "base cell" of a coordinate that cannot touch the map
+
+// exact: LP:471-472 verbatim; coordinates outside +-2^30 cells (the conversion would be UB) never touch the map
+__device__ __noinline__ int aabb_base_cell_exact(double half, double res, float v) {
+  int out;
+  if (!dm::trunc_to_int(dm::sub(half, dm::div(static_cast<double>(v), res)), &out)) return kAabbFar;
+  return out;
+}
+// fast: returns false when the result needs the exact path
+__device__ __forceinline__ bool aabb_base_cell_fast(double half, double inv_res, float v, int* out) {
+  const double s = dm::fma(-static_cast<double>(v), inv_res, half);      // one rounding: at least as close as mul + sub
+  // nearest integer of s without a conversion instruction: adding 1.5 * 2^52 leaves it in the low word of the sum
+  const double t = dm::add(s, 6755399441055744.0);
+  const double frac = dm::sub(s, dm::sub(t, 6755399441055744.0));       // in [-0.5, 0.5], exact
+  // floor = nearest - (frac < 0); truncation toward zero adds one back for negative non-integers
+  *out = __double2loint(t) + (__double2hiint(frac) >> 31) - (__double2hiint(s) >> 31);
+  return fabs(frac) >= 9.5367431640625e-07 && fabs(s) < 1048576.0;      // (false for NaN)
+}
+__device__ __forceinline__ int aabb_base_cell(double half, double inv_res, double res, float v) {
+  int out;
+  if (aabb_base_cell_fast(half, inv_res, v, &out)) return out;
+  return aabb_base_cell_exact(half, res, v);
 }
 
-// map cell of a pose + its 2-bit block summary: 0 = free, 1 = look the cell up, 3 = hit (-1 = outside the map)
+// map cell of a pose + its 2-bit block summary: 0 = free (or outside the map), 1 = look the cell up, 3 = hit
 struct AabbProbe {
-  size_t cell;
+  uint32_t cell;
   int code;
 };
+__device__ __forceinline__ AabbProbe aabb_probe_cells(const GridDev& g, const uint32_t* coarse, int bx, int by) {
+  AabbProbe p;
+  const int mx = bx + g.aabb_pad_x, my = by + g.aabb_pad_y;
+  const bool inside = static_cast<unsigned>(mx) < static_cast<unsigned>(g.aabb_nx) &&
+                      static_cast<unsigned>(my) < static_cast<unsigned>(g.aabb_ny);
+  const int cx = inside ? mx >> g.aabb_cshift : 0, cy = inside ? my >> g.aabb_cshift : 0;
+  const uint32_t w = coarse[cx * g.aabb_cwpr + (cy >> 4)];
+  p.code = inside ? static_cast<int>((w >> ((cy & 15) * 2)) & 3u) : 0;
+  p.cell = static_cast<uint32_t>(mx) * static_cast<uint32_t>(g.aabb_ny) + static_cast<uint32_t>(my);   // (< 2^31: grids <= 32768^2)
+  return p;
+}
 __device__ __forceinline__ AabbProbe aabb_probe(const GridDev& g, const uint32_t* coarse, double half_w, double half_h,
                                                 double inv_res, float x, float y) {
-  AabbProbe p;
-  p.cell = 0;
-  p.code = 0;
-  int bx, by;
-  if (!aabb_base_cell(half_w, inv_res, g.res, y, &bx) || !aabb_base_cell(half_h, inv_res, g.res, x, &by)) return p;
-  const int mx = bx + g.aabb_pad_x, my = by + g.aabb_pad_y;
-  if (mx < 0 || mx >= g.aabb_nx || my < 0 || my >= g.aabb_ny) return p;
-  const int cy = my >> g.aabb_cshift;
-  p.code = static_cast<int>((coarse[(mx >> g.aabb_cshift) * g.aabb_cwpr + (cy >> 4)] >> ((cy & 15) * 2)) & 3u);
-  p.cell = static_cast<size_t>(mx) * g.aabb_ny + my;
-  return p;
+  return aabb_probe_cells(g, coarse, aabb_base_cell(half_w, inv_res, g.res, y), aabb_base_cell(half_h, inv_res, g.res, x));
 }
 __device__ __forceinline__ uint32_t aabb_resolve(const GridDev& g, const AabbProbe& p) {
   if (p.code == 1) return __ldg(&g.aabb_map[p.cell]) != 0 ? 1u : 0u;
   return static_cast<uint32_t>(p.code) >> 1;
+}
+
+// four poses at once (xs / ys = their coordinates): every stage is straight-line over the four, ONE branch for the
+// (practically never taken) exact path, the cell look-ups as four independent predicated loads.  Returns the
+// four flags in the bytes of a word.
+__device__ __forceinline__ uint32_t aabb_quad(const GridDev& g, const uint32_t* coarse, double half_w, double half_h,
+                                              double inv_res, const float xs[4], const float ys[4]) {
+  int bx[4], by[4];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ok &= aabb_base_cell_fast(half_w, inv_res, ys[k], &bx[k]);
+    ok &= aabb_base_cell_fast(half_h, inv_res, xs[k], &by[k]);
+  }
+  if (!ok) {            // some coordinate sits within 2^-20 of a cell border (or is huge / NaN): all eight exactly
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bx[k] = aabb_base_cell_exact(half_w, g.res, ys[k]);
+      by[k] = aabb_base_cell_exact(half_h, g.res, xs[k]);
+    }
+  }
+  AabbProbe p[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p[k] = aabb_probe_cells(g, coarse, bx[k], by[k]);
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint8_t m = p[k].code == 1 ? __ldg(&g.aabb_map[p[k].cell]) : static_cast<uint8_t>(p[k].code >> 1);
+    out |= (m ? 1u : 0u) << (8 * k);
+  }
+  return out;
 }
 
 // plain variant (any alignment, any n): one pose per thread, the block summary read through L1
@@ -72,14 +119,51 @@ collide_aabb_kernel(GridDev g, const float* __restrict__ poses, uint8_t* __restr
   }
 }
 
+// 4 consecutive poses per thread straight from global memory (three 128-bit loads in flight per thread, poses
+// 16-byte and flags 4-byte aligned), block summary through L1, one 32-bit store; the tail takes single poses
+__global__ void __launch_bounds__(kThreads)
+collide_aabb_quad_kernel(GridDev g, const float* __restrict__ poses, uint8_t* __restrict__ flags, int64_t n) {
+  const double half_w = static_cast<double>(g.W / 2), half_h = static_cast<double>(g.H / 2);
+  const double inv_res = dm::div(1.0, g.res);
+  const int64_t n4 = n / 4;
+  const float4* p4 = reinterpret_cast<const float4*>(poses);
+  uint32_t* flags4 = reinterpret_cast<uint32_t*>(flags);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n4; q += stride) {
+    const float4 a = __ldg(&p4[3 * q]), b = __ldg(&p4[3 * q + 1]), c = __ldg(&p4[3 * q + 2]);
+    const float xs[4] = {a.x, a.w, b.z, c.y}, ys[4] = {a.y, b.x, b.w, c.z};   // (x0 y0 w0 x1) (y1 w1 x2 y2) (w2 x3 y3 w3)
+    flags4[q] = aabb_quad(g, g.aabb_coarse, half_w, half_h, inv_res, xs, ys);
+  }
+  for (int64_t k = n4 * 4 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n; k += stride) {
+    const AabbProbe p = aabb_probe(g, g.aabb_coarse, half_w, half_h, inv_res, poses[3 * k], poses[3 * k + 1]);
+    flags[k] = static_cast<uint8_t>(aabb_resolve(g, p));
+  }
+}
+
 // Streaming variant: the pose stream is the only HBM traffic that matters (12 B in, 1 B out per pose), so it is
-// moved by the TMA unit -- one 1-D bulk copy (cp.async.bulk, completion on an mbarrier) per 2048-pose chunk into
-// a ring of kAabbStages shared-memory buffers, issued by one thread -- while the 512 threads of the CTA (one
-// persistent CTA per SM) work on the chunk that has landed: 4 consecutive poses per thread (three conflict-free
-// LDS.128), block summary from shared memory, the rare cell look-up from L2, one 32-bit store of 4 flags.
-constexpr int kAabbThreads = 512;
-constexpr int kAabbChunk = kAabbThreads * 4;          // poses per chunk (24 KB)
-constexpr int kAabbStages = 5;
+// moved by the TMA unit.  One persistent CTA per SM = one PRODUCER warp + kAabbWarps CONSUMER warps around a ring of
+// kAabbStages shared-memory buffers with a full / empty mbarrier pair each:
+//   producer (one lane): wait empty[s] -> arm full[s] with the byte count -> ONE 1-D bulk copy (cp.async.bulk) of a
+//                        2048-pose chunk (24 KB); completion is signalled on full[s] by the copy engine
+//   consumer warp:       wait full[s] -> its 128 poses of the chunk, 4 consecutive poses per thread (three conflict-
+//                        free LDS.128), block summary from shared memory, the rare cell look-ups from L2 as four
+//                        independent predicated loads, one 32-bit store of 4 flags -> arrive on empty[s]
+// No __syncthreads in the loop: warps drift up to kAabbStages - 1 chunks apart, which hides the L2 latency of the
+// look-ups behind the other warps' arithmetic.
+#ifndef PP_AABB_WARPS
+#define PP_AABB_WARPS 16
+#endif
+#ifndef PP_AABB_CTAS
+#define PP_AABB_CTAS 2
+#endif
+constexpr int kAabbWarps = PP_AABB_WARPS;             // consumer warps
+constexpr int kAabbCtasPerSm = PP_AABB_CTAS;
+constexpr int kAabbThreads = (kAabbWarps + 1) * 32;
+constexpr int kAabbChunk = kAabbWarps * 32 * 4;       // poses per chunk (24 KB)
+#ifndef PP_AABB_STAGES
+#define PP_AABB_STAGES 3
+#endif
+constexpr int kAabbStages = PP_AABB_STAGES;
 constexpr uint32_t kAabbChunkBytes = kAabbChunk * 12;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -89,13 +173,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
-  while (!done) {
+  for (uint32_t spins = 0; !done; ++spins) {
+    if (spins == (1u << 26)) __trap();     // a copy that never lands is a bug, not something to wait out
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -106,61 +194,62 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-__global__ void __launch_bounds__(kAabbThreads, 1)
+__global__ void __launch_bounds__(kAabbThreads, kAabbCtasPerSm)
 collide_aabb_stream_kernel(GridDev g, const float* __restrict__ poses, uint8_t* __restrict__ flags, int64_t n) {
   extern __shared__ __align__(128) unsigned char aabb_smem[];
   float* stage = reinterpret_cast<float*>(aabb_smem);
   uint32_t* s_coarse = reinterpret_cast<uint32_t*>(aabb_smem + static_cast<size_t>(kAabbStages) * kAabbChunkBytes);
   const int n_cw = g.aabb_cnbx * g.aabb_cwpr;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_coarse + ((n_cw + 3) & ~3));
-  const int tid = threadIdx.x;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_coarse + ((n_cw + 3) & ~3));
+  uint64_t* empty = full + kAabbStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_full = n / kAabbChunk;
   if (tid == 0) {
-    for (int s = 0; s < kAabbStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kAabbStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kAabbWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int k = tid; k < n_cw; k += kAabbThreads) s_coarse[k] = __ldg(&g.aabb_coarse[k]);
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < kAabbStages; ++s) {
-      const int64_t chunk = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
-      if (chunk < n_full) {
-        mbar_expect_tx(&bars[s], kAabbChunkBytes);
-        bulk_copy_g2s(stage + static_cast<size_t>(s) * kAabbChunk * 3, poses + chunk * kAabbChunk * 3, kAabbChunkBytes, &bars[s]);
-      }
-    }
-  }
   const double half_w = static_cast<double>(g.W / 2), half_h = static_cast<double>(g.H / 2);
   const double inv_res = dm::div(1.0, g.res);
-  uint32_t* flags4 = reinterpret_cast<uint32_t*>(flags);
-  int s = 0;
-  uint32_t parity = 0;
-  for (int64_t chunk = blockIdx.x; chunk < n_full; chunk += gridDim.x) {
-    mbar_wait(&bars[s], parity);
-    const float4* sp = reinterpret_cast<const float4*>(stage + static_cast<size_t>(s) * kAabbChunk * 3) + tid * 3;
-    const float4 a = sp[0], b = sp[1], c = sp[2];      // (x0 y0 w0 x1) (y1 w1 x2 y2) (w2 x3 y3 w3)
-    const AabbProbe p0 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, a.x, a.y);
-    const AabbProbe p1 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, a.w, b.x);
-    const AabbProbe p2 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, b.z, b.w);
-    const AabbProbe p3 = aabb_probe(g, s_coarse, half_w, half_h, inv_res, c.y, c.z);
-    const uint32_t out = aabb_resolve(g, p0) | (aabb_resolve(g, p1) << 8) | (aabb_resolve(g, p2) << 16) |
-                         (aabb_resolve(g, p3) << 24);
-    flags4[chunk * (kAabbChunk / 4) + tid] = out;
-    __syncthreads();                                   // every thread has read buffer s: refill it
-    if (tid == 0) {
-      const int64_t next = chunk + static_cast<int64_t>(kAabbStages) * gridDim.x;
-      if (next < n_full) {
-        mbar_expect_tx(&bars[s], kAabbChunkBytes);
-        bulk_copy_g2s(stage + static_cast<size_t>(s) * kAabbChunk * 3, poses + next * kAabbChunk * 3, kAabbChunkBytes, &bars[s]);
+  if (warp == kAabbWarps) {
+    // ---- producer ------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t parity = 1;             // a fresh barrier passes a wait on the "previous" phase: the ring starts empty
+      for (int64_t chunk = blockIdx.x; chunk < n_full; chunk += gridDim.x) {
+        mbar_wait(&empty[s], parity);
+        mbar_expect_tx(&full[s], kAabbChunkBytes);
+        bulk_copy_g2s(stage + static_cast<size_t>(s) * kAabbChunk * 3, poses + chunk * kAabbChunk * 3, kAabbChunkBytes, &full[s]);
+        if (++s == kAabbStages) { s = 0; parity ^= 1u; }
       }
     }
-    if (++s == kAabbStages) { s = 0; parity ^= 1u; }
-  }
-  // the last < 2048 poses: plain loads, spread over the CTAs
-  for (int64_t k = n_full * kAabbChunk + blockIdx.x * static_cast<int64_t>(kAabbThreads) + tid; k < n;
-       k += static_cast<int64_t>(gridDim.x) * kAabbThreads) {
-    const AabbProbe p = aabb_probe(g, s_coarse, half_w, half_h, inv_res, poses[3 * k], poses[3 * k + 1]);
-    flags[k] = static_cast<uint8_t>(aabb_resolve(g, p));
+  } else {
+    // ---- consumers -----------------------------------------------------------------------------------------
+    uint32_t* flags4 = reinterpret_cast<uint32_t*>(flags);
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t chunk = blockIdx.x; chunk < n_full; chunk += gridDim.x) {
+      mbar_wait(&full[s], parity);
+      const float4* sp = reinterpret_cast<const float4*>(stage + static_cast<size_t>(s) * kAabbChunk * 3) + tid * 3;
+      const float4 a = sp[0], b = sp[1], c = sp[2];      // (x0 y0 w0 x1) (y1 w1 x2 y2) (w2 x3 y3 w3)
+      // release the buffer as soon as the poses are in registers: the (unused) operand makes the arrive wait for
+      // all three loads of this lane, the shuffle-free __syncwarp for those of the other lanes' program order
+      const uint32_t landed = __float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(c.x);
+      asm volatile("" ::"r"(landed) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      const float xs[4] = {a.x, a.w, b.z, c.y}, ys[4] = {a.y, b.x, b.w, c.z};
+      const uint32_t out = aabb_quad(g, s_coarse, half_w, half_h, inv_res, xs, ys);
+      flags4[chunk * (kAabbChunk / 4) + tid] = out;
+      if (++s == kAabbStages) { s = 0; parity ^= 1u; }
+    }
+    // the last < 2048 poses: plain loads, spread over the CTAs
+    for (int64_t k = n_full * kAabbChunk + blockIdx.x * static_cast<int64_t>(kAabbWarps * 32) + tid; k < n;
+         k += static_cast<int64_t>(gridDim.x) * kAabbWarps * 32) {
+      const AabbProbe p = aabb_probe(g, s_coarse, half_w, half_h, inv_res, poses[3 * k], poses[3 * k + 1]);
+      flags[k] = static_cast<uint8_t>(aabb_resolve(g, p));
+    }
   }
 }
 
@@ -411,16 +500,19 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
   } else if (mode == PP_COLLISION_REF_AABB) {
     const GridDev& g = h->grid;
     const size_t smem = static_cast<size_t>(kAabbStages) * kAabbChunkBytes +
-                        sizeof(uint32_t) * ((static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr + 3) & ~size_t(3)) + 8 * kAabbStages;
+                        sizeof(uint32_t) * ((static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr + 3) & ~size_t(3)) + 16 * kAabbStages;
     const bool aligned = (reinterpret_cast<uintptr_t>(poses) & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0;
-    if (aligned && n >= 4 * kAabbChunk && !getenv("PP_AABB_PLAIN_KERNEL")) {
+    static const int variant = getenv("PP_AABB_VARIANT") ? atoi(getenv("PP_AABB_VARIANT")) : 2;   // 0 plain, 1 quad, 2 TMA stream
+    if (aligned && n >= 4 * kAabbChunk && variant == 2) {
       if (!h->aabb_stream_ready) {       // (per device: the attribute lives in the context)
         PP_CUDA(cudaFuncSetAttribute(collide_aabb_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         h->aabb_stream_ready = true;
       }
       const int64_t chunks = n / kAabbChunk;
-      const int blocks = static_cast<int>(chunks < h->sm_count ? chunks : h->sm_count);
-      collide_aabb_stream_kernel<<<blocks, kAabbThreads, smem, s>>>(g, poses, flags, n);
+      const int64_t cap = static_cast<int64_t>(kAabbCtasPerSm) * h->sm_count;   // persistent CTAs
+      collide_aabb_stream_kernel<<<static_cast<int>(chunks < cap ? chunks : cap), kAabbThreads, smem, s>>>(g, poses, flags, n);
+    } else if (aligned && variant >= 1) {
+      collide_aabb_quad_kernel<<<grid_blocks(h, (n + 3) / 4, kThreads, 8), kThreads, 0, s>>>(g, poses, flags, n);
     } else {
       collide_aabb_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, s>>>(g, poses, flags, n);
     }
@@ -452,15 +544,16 @@ int collide_counter_fetch(pp_handle* h) {
 int collide_batch_dev(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) {
   if (n == 0) return PP_OK;
   cudaStream_t s = h->stream;
-  int rc = collide_counter_reset(h);
+  const bool counted = h->P.collision_mode == PP_COLLISION_ORIENTED;   // only the ORIENTED kernel counts narrow-phase jobs
+  int rc = counted ? collide_counter_reset(h) : PP_OK;
   if (rc) return rc;
   PP_CUDA(cudaEventRecord(h->ev[2], s));
   rc = collide_launch(h, n, poses, flags);
   if (rc) return rc;
   PP_CUDA(cudaEventRecord(h->ev[3], s));
-  rc = collide_counter_fetch(h);
+  rc = counted ? collide_counter_fetch(h) : PP_OK;
   if (rc) return rc;
-  if (h->P.collision_mode != PP_COLLISION_ORIENTED) h->last_narrow = n;
+  if (!counted) h->last_narrow = n;
   return PP_OK;
 }
 

@@ -74,7 +74,7 @@ struct GridDev {
   // aabb_map summarised per block of 2^aabb_cshift x 2^aabb_cshift map cells, 2 bits per block
   // (bit 0: some cell of the block is 1, bit 1: the block lies inside the map and all its cells are 1),
   // 16 blocks per word along my: word (mx >> s) * aabb_cwpr + (my >> s >> 4).  Small enough for shared
-  // memory (<= 96 KB), so the batch kernel answers ~94 % of the poses without touching L2.
+  // memory (<= 24 KB), so the batch kernel answers ~90 % of the poses without touching L2.
   uint32_t* aabb_coarse;
   int aabb_cshift, aabb_cnbx, aabb_cwpr;
 };

@@ -239,12 +239,13 @@ GridDev grid_shape(const pp_handle* h) {
   g.CW8 = (g.TJ * 4 + 63) / 64 + 1;  // +1: the bbox test may read one word past the last
   g.CI4 = g.TI * 8;
   g.CW4 = (g.TJ * 8 + 63) / 64 + 1;
-  // block size of the 2-bit summary: the smallest (>= 8 cells) whose map fits 96 KB of shared memory
-  for (g.aabb_cshift = 3;; ++g.aabb_cshift) {
+  // block size of the 2-bit summary: the smallest (>= 16 cells) whose map fits 24 KB, so that two CTAs of the
+  // streaming kernel share an SM (4096^2: 16-cell blocks, 17.7 KB, ~10 % of the poses need the cell look-up)
+  for (g.aabb_cshift = 4;; ++g.aabb_cshift) {
     const int B = 1 << g.aabb_cshift;
     g.aabb_cnbx = (g.aabb_nx + B - 1) / B;
     g.aabb_cwpr = ((g.aabb_ny + B - 1) / B + 15) / 16;
-    if (static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr * sizeof(uint32_t) <= 96 * 1024) break;
+    if (static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr * sizeof(uint32_t) <= 24 * 1024) break;
   }
   // half diagonal of the footprint in cells + 1 (floor) + 2 (float slack of the pre-test)
   const double du = h->lat.su * h->lat.hu, dv = h->lat.sv * h->lat.hv;

@@ -223,7 +223,7 @@ def test_8192_grid_matches_oracle(oracle, cuda_device):
         pl.close()
 
 
-@pytest.mark.parametrize("res,W,H", [(0.1, 4096, 4096), (0.25, 300, 300), (0.1, 517, 333), (0.05, 8192, 2048)])
+@pytest.mark.parametrize("res,W,H", [(0.1, 4096, 4096), (0.25, 300, 300), (0.1, 517, 333), (0.1, 8192, 2048)])
 def test_ref_aabb_stream_kernel_cell_boundaries(oracle, cuda_device, res, W, H):
     """REF_AABB batch kernel (TMA-staged pose stream, fast base-cell arithmetic with an exact fallback): poses ON
     cell boundaries (k * res as float32 and its float32 neighbours, where int(W/2 - y/res) of LP:471-472 flips),

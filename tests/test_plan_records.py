@@ -156,7 +156,9 @@ def test_device_records_equal_host_results_and_oracle(oracle, cuda_device, mode)
         pl.sync()
         assert torch.equal(again, dev)                          # every byte of a record is written
     ref = [oracle.plan(p, grid, q, math_mode=oracle.MATH_DET) for q in qs[:40] + qs[-1:]]
-    np.testing.assert_array_equal(records_from_results(ref, 160), pl.plan_batch_dev((pp_query * 41)(*(qs[:40] + qs[-1:])), 41, 160).cpu().numpy())
+    sub = pl.plan_batch_dev((pp_query * 41)(*(qs[:40] + qs[-1:])), 41, 160)
+    pl.sync()                                                   # (the call is asynchronous on the handle's stream)
+    np.testing.assert_array_equal(records_from_results(ref, 160), sub.cpu().numpy())
     assert host[-1].status == PP_PLAN_CAP and PlanRecords(raw, 24).field("truncated").sum() > 0
     assert pl.last_phase_ms()[4] > 0.0
     pl.close()
