@@ -176,6 +176,67 @@ __global__ void __launch_bounds__(kT) rrt_nearest(RrtArgs A, int slice_nodes) {
   }
 }
 
+// steer from tree node `near` toward the sample (sx, sy): heading change clamped to +-heading_diff, speed
+// v' = min(v + a dt, max_speed), step (v + v') dt (LP:155-157).  Shared by the per-round kernels and the
+// persistent kernel, so both build the same tree bit for bit.
+struct Steer {
+  double px, py, yaw, v_next, step, nx, ny, dx, dy;
+  int n;        // edge poses k = 1..n (LP:308 spacing), 0 = no edge (zero step / unrepresentable length)
+  bool moves;   // step > 0
+};
+__device__ __forceinline__ Steer steer_from(const RrtArgs& A, const pp_query& qq, int near, float sx, float sy) {
+  Steer S;
+  const size_t nb = near;
+  S.px = __ldcg(&A.nx[nb]); S.py = __ldcg(&A.ny[nb]);
+  const double ph = __ldcg(&A.nhd[nb]), pv = __ldcg(&A.nvel[nb]);
+  const double th = dm::atan2_(dm::sub(static_cast<double>(sy), S.py), dm::sub(static_cast<double>(sx), S.px));
+  double d = dm::wrap_pi(dm::sub(th, ph));
+  if (d > A.P.heading_diff) d = A.P.heading_diff;
+  if (d < -A.P.heading_diff) d = -A.P.heading_diff;
+  S.yaw = dm::add(ph, d);
+  S.v_next = dm::add(pv, dm::div(dm::mul(qq.max_accel, A.P.time_step_ms), 1000.0));
+  if (S.v_next > qq.max_speed) S.v_next = qq.max_speed;
+  const double sum_v = dm::add(pv, S.v_next);                                  // LP:155
+  S.step = dm::div(dm::mul(sum_v, A.P.time_step_ms), 1000.0);
+  S.moves = S.step > 0;
+  S.nx = 0; S.ny = 0; S.dx = 0; S.dy = 0; S.n = 0;
+  if (S.moves) {
+    double sn, cs;
+    dm::sincos(S.yaw, &sn, &cs);
+    S.nx = dm::add(S.px, dm::mul(S.step, cs));                                  // LP:156
+    S.ny = dm::add(S.py, dm::mul(S.step, sn));                                  // LP:157
+    // edge collision, poses k = 1..max(n,1) with n = int(dist / search_res * 2) (LP:308)
+    S.dx = dm::sub(S.nx, S.px); S.dy = dm::sub(S.ny, S.py);
+    const double dist = __dsqrt_rn(dm::add(dm::mul(S.dx, S.dx), dm::mul(S.dy, S.dy)));
+    int n = 0;
+    if (dm::trunc_to_int(dm::mul(dm::div(dist, A.P.search_res), 2.0), &n)) S.n = n < 1 ? 1 : n;
+  }
+  return S;
+}
+// poses k_lo+1 .. k_hi of the edge, by one warp: the poses are a mini-batch -- lane l sets up pose base + l + 1
+// (broad phase, one thread each), then the warp runs the narrow phase only for the poses that need it
+__device__ __forceinline__ bool edge_part_hit(const RrtArgs& A, const Steer& S, int k_lo, int k_hi, uint32_t* smem, int lane) {
+  bool hit = false;
+  for (int base = k_lo; base < k_hi && !hit; base += 32) {
+    const int k = base + lane + 1;
+    bool need = false;
+    NarrowJob job;
+    if (k <= k_hi) {
+      const double tt = dm::div(static_cast<double>(k), static_cast<double>(S.n));
+      const double ex = dm::add(S.px, dm::mul(tt, S.dx)), ey = dm::add(S.py, dm::mul(tt, S.dy));
+      if (A.cp.mode == PP_COLLISION_ORIENTED) {
+        const PoseFx pf = pose_to_fixed(A.cp.lat, A.g.W, A.g.H, A.g.res, ex, ey, S.yaw);
+        need = make_job(A.g, A.cp.lat, pf, 1, &job);
+      } else if (A.cp.mode == PP_COLLISION_REF_AABB) {
+        hit = aabb_hit(A.g, ex, ey);
+      }
+    }
+    if (A.cp.mode == PP_COLLISION_ORIENTED) hit = warp_collide_jobs(A.g, A.cp.lat, job, need, smem, lane);
+    else hit = __any_sync(0xffffffffu, hit);
+  }
+  return hit;
+}
+
 __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A, int ext_split) {
   __shared__ __align__(16) uint32_t smem[kT / 32][kWinWords];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -196,53 +257,17 @@ __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A, int ext_split) {
   float sx, sy;
   draw_sample(A, qq, s, &sx, &sy);
   const int near = static_cast<int>(A.best[slot] & 0xffffffffull);
-  const size_t nb = static_cast<size_t>(q) * A.NC + near;
-  const double px = A.nx[nb], py = A.ny[nb], ph = A.nhd[nb], pv = A.nvel[nb];
-  // steer: heading toward the sample, limited to +-heading_diff per step
-  const double th = dm::atan2_(dm::sub(static_cast<double>(sy), py), dm::sub(static_cast<double>(sx), px));
-  double d = dm::wrap_pi(dm::sub(th, ph));
-  if (d > A.P.heading_diff) d = A.P.heading_diff;
-  if (d < -A.P.heading_diff) d = -A.P.heading_diff;
-  const double yaw = dm::add(ph, d);
-  double v_next = dm::add(pv, dm::div(dm::mul(qq.max_accel, A.P.time_step_ms), 1000.0));
-  if (v_next > qq.max_speed) v_next = qq.max_speed;
-  const double sum_v = dm::add(pv, v_next);                                  // LP:155
-  const double step = dm::div(dm::mul(sum_v, A.P.time_step_ms), 1000.0);
+  RrtArgs Aq = A;                                    // node arrays of this query
+  const size_t nb = static_cast<size_t>(q) * A.NC;
+  Aq.nx += nb; Aq.ny += nb; Aq.nhd += nb; Aq.nvel += nb;
+  const Steer S = steer_from(Aq, qq, near, sx, sy);
   int verdict = 0;
-  double nx = 0, ny = 0;
-  if (step > 0) {
-    double sn, cs;
-    dm::sincos(yaw, &sn, &cs);
-    nx = dm::add(px, dm::mul(step, cs));                                      // LP:156
-    ny = dm::add(py, dm::mul(step, sn));                                      // LP:157
-    // edge collision, poses k = 1..max(n,1) with n = int(dist / search_res * 2) (LP:308)
-    const double dx = dm::sub(nx, px), dy = dm::sub(ny, py);
-    const double dist = __dsqrt_rn(dm::add(dm::mul(dx, dx), dm::mul(dy, dy)));
-    int n = 0;
+  if (S.moves) {
     bool hit = false;
-    if (dm::trunc_to_int(dm::mul(dm::div(dist, A.P.search_res), 2.0), &n)) {
-      if (n < 1) n = 1;
-      // the edge's poses are a mini-batch: lane l sets up pose base + l + 1 (broad phase, one
-      // thread each), then the warp runs the narrow phase only for the poses that need it
-      const int k_lo = static_cast<int>(static_cast<long long>(n) * part / ext_split);        // poses k_lo+1 .. k_hi
-      const int k_hi = static_cast<int>(static_cast<long long>(n) * (part + 1) / ext_split);
-      for (int base = k_lo; base < k_hi && !hit; base += 32) {
-        const int k = base + lane + 1;
-        bool need = false;
-        NarrowJob job;
-        if (k <= k_hi) {
-          const double tt = dm::div(static_cast<double>(k), static_cast<double>(n));
-          const double ex = dm::add(px, dm::mul(tt, dx)), ey = dm::add(py, dm::mul(tt, dy));
-          if (A.cp.mode == PP_COLLISION_ORIENTED) {
-            const PoseFx pf = pose_to_fixed(A.cp.lat, A.g.W, A.g.H, A.g.res, ex, ey, yaw);
-            need = make_job(A.g, A.cp.lat, pf, 1, &job);
-          } else if (A.cp.mode == PP_COLLISION_REF_AABB) {
-            hit = aabb_hit(A.g, ex, ey);
-          }
-        }
-        if (A.cp.mode == PP_COLLISION_ORIENTED) hit = warp_collide_jobs(A.g, A.cp.lat, job, need, smem[wib], lane);
-        else hit = __any_sync(0xffffffffu, hit);
-      }
+    if (S.n > 0) {
+      const int k_lo = static_cast<int>(static_cast<long long>(S.n) * part / ext_split);        // poses k_lo+1 .. k_hi
+      const int k_hi = static_cast<int>(static_cast<long long>(S.n) * (part + 1) / ext_split);
+      hit = edge_part_hit(A, S, k_lo, k_hi, smem[wib], lane);
     }
     verdict = hit ? 2 : 1;
   }
@@ -250,7 +275,7 @@ __global__ void __launch_bounds__(kT) rrt_extend(RrtArgs A, int ext_split) {
   if (lane == 0 && part == 0) {
     A.cand_near[slot] = near;
     double* c = A.cand + slot * 5;
-    c[0] = nx; c[1] = ny; c[2] = yaw; c[3] = v_next; c[4] = step;
+    c[0] = S.nx; c[1] = S.ny; c[2] = S.yaw; c[3] = S.v_next; c[4] = S.step;
   }
 }
 
@@ -311,6 +336,371 @@ __global__ void __launch_bounds__(kT) rrt_append(RrtArgs A) {
     st.done = !(st.goal_id < 0 && st.n_samples < A.P.rrt_max_samples && st.n_nodes < A.P.max_nodes);
     A.state[q] = st;
     if (st.done) atomicSub(A.n_active, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One query, one kernel: the whole round loop runs inside a cooperative launch (all CTAs co-resident) with two
+// grid-wide barriers per round instead of three launches, and the nearest-neighbour query goes through a bucket
+// grid once the tree is large.  Results are those of the per-round kernels bit for bit (same sample stream, same
+// float32 (distance, index) minimum, same steering / collision arithmetic, same append order).
+//
+//   phase A  CTA per sample: draw the sample, nearest node (exact, below), steer, edge collision with one warp per
+//            share of the edge's poses -> verdict + candidate
+//   ------ grid barrier ------
+//   phase B  every CTA reads the K verdicts and derives the same survivor ranks (order-preserving append);
+//            the CTA of a surviving sample writes its node, bins it, tests the goal box (atomicMin = first in
+//            sample order).  The round counters are replicated in every CTA (a deterministic function of the
+//            verdicts), so nothing central has to be waited for
+//   ------ grid barrier ------
+//   every ~16 rounds: the nodes are regrouped by bucket (counting sort: scan by CTA 0, scatter by all; two more
+//   barriers), so that the next rounds scan whole buckets with coalesced loads
+//
+// Nearest neighbour (S2), exact: nodes [0, n_sorted) sit grouped by the cell of a kGridSide^2 bucket grid over
+// the sampling box (16-byte records x, y, id), nodes [n_sorted, n_nodes) -- the "tail", <= kTailMax -- are scanned
+// directly.  Every CTA keeps the cell offsets and the list of non-empty cells in shared memory.  Per sample:
+// (1) the non-empty cell with the smallest box distance, its nodes (whole CTA) and the tail give an upper bound;
+// (2) every other non-empty cell whose (conservatively rounded) box distance does not exceed it is scanned too,
+//     one warp per cell so that the cells' L2 round trips overlap.
+// The minimum over (dist2 bits << 32 | index) is exactly "minimum distance, ties -> lowest index".
+#ifndef PP_RRT_WARP_CELLS
+#define PP_RRT_WARP_CELLS 0
+#endif
+#ifndef PP_RRT_TAIL
+#define PP_RRT_TAIL 4096
+#endif
+#ifndef PP_RRT_GRID
+#define PP_RRT_GRID 48
+#endif
+constexpr int kGridSide = PP_RRT_GRID;             // (kGridSide^2 must be a multiple of the CTA size)
+constexpr int kGridCells = kGridSide * kGridSide;
+constexpr int kTailMax = PP_RRT_TAIL;
+constexpr int kGridFrom = 8192;              // smaller trees are scanned whole
+constexpr int kWorkCap = 1024;               // candidate cells of step (2) kept in shared memory
+
+struct RrtPersist {
+  int* cell_count;       // [cells]      nodes per cell, all nodes
+  int* cell_start;       // [cells + 1]  first slot of each cell in the sorted arrays (nodes [0, n_sorted))
+  int* cell_cursor;      // [cells]      scatter cursors of a rebuild
+  float4* sorted;        // [NC]  (x, y, id as bits, 0) grouped by cell
+  int* goal_id;          // atomicMin of the node ids inside the goal box (INT_MAX = none)
+  unsigned* barrier;     // monotonic arrival counter of the grid barrier
+  float x_lo, y_lo, cell_x, cell_y, inv_cell_x, inv_cell_y;
+  long long* cycles;     // PP_RRT_TIMING: SM cycles of CTA 0 per phase (nearest, edge, barrier 1, append, barrier 2, regroup), else null
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned* generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *generation += 1;
+    const unsigned target = *generation * gridDim.x;
+    __threadfence();                                   // this CTA's writes are visible before it arrives
+    atomicAdd(counter, 1u);
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+      if (++spins > (1u << 28)) __trap();              // a CTA that never arrives is a bug, not something to wait out
+    }
+    __threadfence();                                   // (gpu-scope fence: also drops this SM's stale L1 lines)
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int grid_cell_of(const RrtPersist& G, float x, float y) {
+  const float fx = (x - G.x_lo) * G.inv_cell_x, fy = (y - G.y_lo) * G.inv_cell_y;
+  int ix = fx > 0.f ? (fx >= static_cast<float>(kGridSide) ? kGridSide - 1 : static_cast<int>(fx)) : 0;   // (NaN -> 0)
+  int iy = fy > 0.f ? (fy >= static_cast<float>(kGridSide) ? kGridSide - 1 : static_cast<int>(fy)) : 0;
+  return ix * kGridSide + iy;
+}
+// conservative lower bound of dist2 between a sample and any node binned into cell (ix, iy), split per axis: d2 of
+// the sample to column ix / row iy of the grid; the box is widened by a slack that covers the float32 binning
+// arithmetic, border cells extend to infinity (they hold the clamped far nodes).
+// bound(cell) = (axis_x[ix] + axis_y[iy]) * 0.9999f
+__device__ __forceinline__ float grid_axis_d2(float lo0, float cell, int i, float q) {
+  const float sl = 1e-3f * cell + 1e-3f;
+  const float lo = lo0 + i * cell - sl, hi = lo0 + (i + 1) * cell + sl;
+  float d = 0.f;
+  if (i > 0 && q < lo) d = lo - q;
+  if (i < kGridSide - 1 && q > hi) d = q - hi;
+  return d * d;
+}
+__device__ __forceinline__ unsigned long long pack_best(float d, int idx) {
+  return (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | static_cast<unsigned int>(idx);
+}
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long* s_red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = o < v ? o : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long r = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kT / 32; ++w) r = s_red[w] < r ? s_red[w] : r;
+  return r;
+}
+
+// minimum of (dist2, id) over the sorted records [a, b), this thread taking first, first + stride, ...: four
+// independent 16-byte loads in flight
+__device__ __forceinline__ unsigned long long scan_sorted(const RrtPersist& G, int a, int b, int first, int stride, float sx,
+                                                          float sy, unsigned long long best) {
+  for (int k0 = a + first; k0 < b; k0 += 4 * stride) {
+    float4 nd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; nd[u] = k < b ? __ldcg(&G.sorted[k]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float dx = __fsub_rn(sx, nd[u].x), dy = __fsub_rn(sy, nd[u].y);
+      const unsigned long long c = k0 + u * stride < b ? pack_best(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)), __float_as_int(nd[u].z)) : kBestInit;
+      best = c < best ? c : best;
+    }
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(kT) rrt_persistent(RrtArgs A, RrtPersist G) {
+  __shared__ __align__(16) uint32_t s_win[kT / 32][kWinWords];
+  __shared__ unsigned long long s_red[kT / 32];
+  extern __shared__ __align__(16) unsigned char rrt_dyn_smem[];
+  int* s_start = reinterpret_cast<int*>(rrt_dyn_smem);                                  // [cells + 1] copy of G.cell_start
+  unsigned short* s_cells = reinterpret_cast<unsigned short*>(s_start + kGridCells + 4); // non-empty cells, ascending
+  __shared__ int s_ncells;
+  __shared__ float s_ax[kGridSide], s_ay[kGridSide];       // per-axis box distances of the current sample
+  __shared__ unsigned short s_work[kWorkCap];
+  __shared__ int s_nwork, s_hit, s_scan[kT / 32];
+  __shared__ unsigned s_gen;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const pp_query qq = A.queries[0];
+  if (tid == 0) s_gen = 0;
+  // replicated round state (identical in every CTA)
+  int n_nodes = 1, n_samples = 0, n_rounds = 0, n_coll = 0, n_sorted = 0, goal_id = -1;
+  if (blockIdx.x == 0 && tid == 0)                       // node 0 (written by rrt_init) joins its bucket
+    atomicAdd(&G.cell_count[grid_cell_of(G, static_cast<float>(qq.start_x), static_cast<float>(qq.start_y))], 1);
+  grid_barrier(G.barrier, &s_gen);
+  const int max_samples = A.P.rrt_max_samples, max_nodes = A.P.max_nodes;
+
+  long long cyc[6] = {0, 0, 0, 0, 0, 0};
+  long long t_mark = clock64();
+#define RRT_TICK(slot) do { if (G.cycles && blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); cyc[slot] += now_ - t_mark; t_mark = now_; } } while (0)
+  while (goal_id < 0 && n_samples < max_samples && n_nodes < max_nodes) {
+    const int k_round = min(A.K, max_samples - n_samples);
+    // ---- phase A ---------------------------------------------------------------------------------------
+    for (int t = blockIdx.x; t < k_round; t += gridDim.x) {
+      const long long t_round = G.cycles ? clock64() : 0;
+      float sx, sy;
+      draw_sample(A, qq, static_cast<long long>(n_samples) + t, &sx, &sy);
+      unsigned long long best = kBestInit;
+      // the tail (or the whole tree while it is small): eight independent loads in flight per thread
+      for (int k0 = n_sorted + tid; k0 < n_nodes; k0 += 8 * kT) {
+        float2 nd[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int k = k0 + u * kT; nd[u] = k < n_nodes ? __ldcg(&A.nxy[k]) : make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + u * kT;
+          const float dx = __fsub_rn(sx, nd[u].x), dy = __fsub_rn(sy, nd[u].y);
+          const unsigned long long c = k < n_nodes ? pack_best(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)), k) : kBestInit;
+          best = c < best ? c : best;
+        }
+      }
+      int c0 = -1;
+      const int n_cells = n_sorted > 0 ? s_ncells : 0;
+      if (n_cells > 0) {
+        if (tid < kGridSide) s_ax[tid] = grid_axis_d2(G.x_lo, G.cell_x, tid, sx);
+        else if (tid < 2 * kGridSide) s_ay[tid - kGridSide] = grid_axis_d2(G.y_lo, G.cell_y, tid - kGridSide, sy);
+        __syncthreads();
+        unsigned long long mine = kBestInit;                           // (lower bound, cell) of the closest non-empty cell
+        for (int k = tid; k < n_cells; k += kT) {
+          const int c = s_cells[k];
+          const unsigned long long v = pack_best((s_ax[c / kGridSide] + s_ay[c % kGridSide]) * 0.9999f, c);
+          mine = v < mine ? v : mine;
+        }
+        c0 = static_cast<int>(block_min_u64(mine, s_red) & 0xffffffffull);
+        if (G.cycles && tid == 0) {
+          atomicAdd(reinterpret_cast<unsigned long long*>(&G.cycles[13]), static_cast<unsigned long long>(s_start[c0 + 1] - s_start[c0]));
+          atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[14]), static_cast<unsigned long long>(s_start[c0 + 1] - s_start[c0]));
+          atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[15]), static_cast<unsigned long long>(n_nodes - n_sorted));
+        }
+        best = scan_sorted(G, s_start[c0], s_start[c0 + 1], tid, kT, sx, sy, best);
+      }
+      best = block_min_u64(best, s_red);
+      if (n_cells > 0) {
+        const float bound = __uint_as_float(static_cast<unsigned>(best >> 32));
+        if (tid == 0) s_nwork = 0;
+        __syncthreads();
+        for (int k = tid; k < n_cells; k += kT) {
+          const int c = s_cells[k];
+          if (c != c0 && (s_ax[c / kGridSide] + s_ay[c % kGridSide]) * 0.9999f <= bound) {
+            const int slot = atomicAdd(&s_nwork, 1);
+            if (slot < kWorkCap) s_work[slot] = static_cast<unsigned short>(c);
+          }
+        }
+        __syncthreads();
+        const int nw = s_nwork;
+        if (G.cycles && tid == 0) {               // PP_RRT_TIMING: candidate cells / nodes of step (2), all CTAs
+          long long m = 0;
+          for (int w = 0; w < min(nw, kWorkCap); ++w) m += s_start[s_work[w] + 1] - s_start[s_work[w]];
+          atomicAdd(reinterpret_cast<unsigned long long*>(&G.cycles[8]), static_cast<unsigned long long>(nw));
+          atomicAdd(reinterpret_cast<unsigned long long*>(&G.cycles[9]), static_cast<unsigned long long>(m));
+          atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[10]), static_cast<unsigned long long>(nw));
+          atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[11]), static_cast<unsigned long long>(m));
+          atomicAdd(reinterpret_cast<unsigned long long*>(&G.cycles[12]), 1ull);
+        }
+        if (nw > 0) {
+          if (nw <= kWorkCap) {
+#if PP_RRT_WARP_CELLS
+            for (int w = warp; w < nw; w += kT / 32) {                 // one warp per candidate cell
+              const int c = s_work[w];
+              best = scan_sorted(G, s_start[c], s_start[c + 1], lane, 32, sx, sy, best);
+            }
+#else
+            for (int w = 0; w < nw; ++w) {
+              const int c = s_work[w];
+              best = scan_sorted(G, s_start[c], s_start[c + 1], tid, kT, sx, sy, best);
+            }
+#endif
+          } else {                                                     // (more candidate cells than the list holds: all sorted nodes)
+            best = scan_sorted(G, 0, n_sorted, tid, kT, sx, sy, best);
+          }
+          best = block_min_u64(best, s_red);
+        }
+      }
+      const int near = static_cast<int>(best & 0xffffffffull);
+      RRT_TICK(0);
+      long long t_near_end = 0;
+      if (G.cycles && tid == 0) {
+        t_near_end = clock64();
+        if (n_rounds < 4096) atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[16 + 2 * n_rounds]), static_cast<unsigned long long>(t_near_end - t_round));
+      }
+      // steer (every thread, identical arithmetic) + the edge's poses shared by the warps
+      const Steer S = steer_from(A, qq, near, sx, sy);
+      if (tid == 0) s_hit = 0;
+      __syncthreads();
+      if (S.moves && S.n > 0) {
+        const int parts = kT / 32;
+        const int k_lo = static_cast<int>(static_cast<long long>(S.n) * warp / parts);
+        const int k_hi = static_cast<int>(static_cast<long long>(S.n) * (warp + 1) / parts);
+        if (k_hi > k_lo && edge_part_hit(A, S, k_lo, k_hi, s_win[warp], lane) && lane == 0) atomicOr(&s_hit, 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        A.cand_valid[t] = S.moves ? (s_hit ? 2 : 1) : 0;
+        A.cand_near[t] = near;
+        double* c = A.cand + static_cast<size_t>(t) * 5;
+        c[0] = S.nx; c[1] = S.ny; c[2] = S.yaw; c[3] = S.v_next; c[4] = S.step;
+      }
+      __syncthreads();
+      RRT_TICK(1);
+      if (G.cycles && tid == 0 && n_rounds < 4096)
+        atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[17 + 2 * n_rounds]), static_cast<unsigned long long>(clock64() - t_near_end));
+    }
+    grid_barrier(G.barrier, &s_gen);
+    RRT_TICK(2);
+    // ---- phase B: order-preserving append ---------------------------------------------------------------
+    int appended = 0, coll = 0;
+    for (int base = 0; base < k_round; base += kT) {
+      const int u = base + tid;
+      const int v = u < k_round ? __ldcg(&A.cand_valid[u]) : 0;
+      appended += __syncthreads_count(v == 1);
+      coll += __syncthreads_count(v == 2);
+    }
+    for (int t = blockIdx.x; t < k_round; t += gridDim.x) {
+      int rank = 0;
+      for (int base = 0; base < t; base += kT) {
+        const int u = base + tid;
+        rank += __syncthreads_count(u < t && __ldcg(&A.cand_valid[u]) == 1);
+      }
+      if (tid == 0 && __ldcg(&A.cand_valid[t]) == 1) {
+        const int id = n_nodes + rank;
+        const double* c = A.cand + static_cast<size_t>(t) * 5;
+        const double x = __ldcg(&c[0]), y = __ldcg(&c[1]);
+        A.nx[id] = x; A.ny[id] = y; A.nhd[id] = __ldcg(&c[2]); A.nvel[id] = __ldcg(&c[3]); A.nstep[id] = __ldcg(&c[4]);
+        A.nparent[id] = __ldcg(&A.cand_near[t]);
+        const float2 xy = make_float2(static_cast<float>(x), static_cast<float>(y));
+        A.nxy[id] = xy;
+        atomicAdd(&G.cell_count[grid_cell_of(G, xy.x, xy.y)], 1);
+        if (fabs(dm::sub(x, qq.goal_x)) <= A.P.rrt_goal_tolerance && fabs(dm::sub(y, qq.goal_y)) <= A.P.rrt_goal_tolerance)
+          atomicMin(G.goal_id, id);       // the first appended node (lowest sample index) in the goal box
+      }
+    }
+    RRT_TICK(3);
+    grid_barrier(G.barrier, &s_gen);
+    RRT_TICK(4);
+    n_nodes += appended;
+    n_samples += k_round;
+    n_rounds += 1;
+    n_coll += coll;
+    {
+      const int gid = __ldcg(G.goal_id);
+      goal_id = gid == 0x7fffffff ? -1 : gid;
+    }
+    // ---- regroup the nodes by bucket when the tail has grown ------------------------------------------------
+    if (goal_id < 0 && n_nodes >= kGridFrom && n_nodes - n_sorted > kTailMax) {
+      if (blockIdx.x == 0) {                       // exclusive scan of the per-cell counts (16 cells per thread)
+        constexpr int kPer = kGridCells / kT;
+        int sum = 0;
+#pragma unroll 8
+        for (int i = 0; i < kPer; ++i) sum += __ldcg(&G.cell_count[tid * kPer + i]);
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += o;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int run = incl - sum;
+        for (int w = 0; w < warp; ++w) run += s_scan[w];
+        for (int i = 0; i < kPer; ++i) {
+          G.cell_start[tid * kPer + i] = run;
+          G.cell_cursor[tid * kPer + i] = 0;
+          run += __ldcg(&G.cell_count[tid * kPer + i]);
+        }
+        if (tid == kT - 1) G.cell_start[kGridCells] = run;
+      }
+      grid_barrier(G.barrier, &s_gen);
+      for (int id = blockIdx.x * kT + tid; id < n_nodes; id += gridDim.x * kT) {
+        const float2 xy = __ldcg(&A.nxy[id]);
+        const int c = grid_cell_of(G, xy.x, xy.y);
+        const int pos = __ldcg(&G.cell_start[c]) + atomicAdd(&G.cell_cursor[c], 1);
+        G.sorted[pos] = make_float4(xy.x, xy.y, __int_as_float(id), 0.f);
+      }
+      grid_barrier(G.barrier, &s_gen);
+      n_sorted = n_nodes;
+      // every CTA refreshes its copy of the offsets and compacts the non-empty cells (ascending) behind it
+#pragma unroll 8
+      for (int c = tid; c <= kGridCells; c += kT) s_start[c] = __ldcg(&G.cell_start[c]);
+      if (tid == 0) s_ncells = 0;
+      __syncthreads();
+      {
+        constexpr int kPer = kGridCells / kT;                  // consecutive cells per thread
+        int cnt = 0;
+        for (int i = 0; i < kPer; ++i) cnt += s_start[tid * kPer + i + 1] > s_start[tid * kPer + i] ? 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += o;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int pos = incl - cnt;
+        for (int w = 0; w < warp; ++w) pos += s_scan[w];
+        for (int i = 0; i < kPer; ++i)
+          if (s_start[tid * kPer + i + 1] > s_start[tid * kPer + i]) s_cells[pos++] = static_cast<unsigned short>(tid * kPer + i);
+        if (tid == kT - 1) s_ncells = pos;
+      }
+      __syncthreads();
+      RRT_TICK(5);
+    }
+  }
+  if (G.cycles && blockIdx.x == 0 && tid == 0)
+    for (int c = 0; c < 6; ++c) G.cycles[c] = cyc[c];
+  if (blockIdx.x == 0 && tid == 0) {
+    RrtState st;
+    st.n_nodes = n_nodes; st.n_samples = n_samples; st.n_rounds = n_rounds; st.n_coll = n_coll; st.goal_id = goal_id; st.done = 1;
+    A.state[0] = st;
   }
 }
 
@@ -386,6 +776,7 @@ __global__ void __launch_bounds__(kT) rrt_finalize(RrtArgs A) {
 }  // namespace pp
 
 struct RrtWorkspace {
+  void* grid = nullptr;   size_t grid_bytes = 0;      // bucket grid of the persistent single-query kernel
   void* nodes = nullptr;  size_t nodes_bytes = 0;
   void* round = nullptr;  size_t round_bytes = 0;
   void* out = nullptr;    size_t out_bytes = 0;
@@ -399,6 +790,7 @@ namespace pp {
 
 void rrt_free(pp_handle* h) {
   if (!h->rrt_ws) return;
+  cudaFree(h->rrt_ws->grid);
   cudaFree(h->rrt_ws->nodes);
   cudaFree(h->rrt_ws->round);
   cudaFree(h->rrt_ws->out);
@@ -509,6 +901,63 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   PP_CUDA(cudaEventRecord(h->ev[8], s));
   rrt_init<<<n, kT, 0, s>>>(A);
   h->launches++;
+  // a lone query runs its whole round loop inside ONE cooperative kernel (grid barriers instead of launches, bucket-grid
+  // nearest neighbour); batches keep the three kernels per round below, which handle all queries of a round at once
+  static const bool no_persistent = getenv("PP_RRT_PER_ROUND_KERNELS") != nullptr;
+  bool persistent = n == 1 && !no_persistent;
+  if (persistent) {
+    int coop = 0, per_sm = 0;
+    PP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    const size_t dyn_smem = sizeof(int) * (kGridCells + 4) + sizeof(unsigned short) * kGridCells;
+    PP_CUDA(cudaFuncSetAttribute(rrt_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rrt_persistent, kT, dyn_smem));
+    if (!coop || per_sm < 1) persistent = false;
+    else {
+      const size_t g_total = al(sizeof(int) * kGridCells) * 2 + al(sizeof(int) * (kGridCells + 1)) + al(sizeof(float4) * per_q) + 512 + (16 + 2 * 4096) * sizeof(long long);
+      rc = grow_buf(&W->grid, &W->grid_bytes, g_total);
+      if (rc) return rc;
+      unsigned char* gp = static_cast<unsigned char*>(W->grid);
+      RrtPersist G;
+      G.cell_count = reinterpret_cast<int*>(gp);            gp += al(sizeof(int) * kGridCells);
+      G.cell_cursor = reinterpret_cast<int*>(gp);           gp += al(sizeof(int) * kGridCells);
+      G.cell_start = reinterpret_cast<int*>(gp);            gp += al(sizeof(int) * (kGridCells + 1));
+      G.sorted = reinterpret_cast<float4*>(gp);             gp += al(sizeof(float4) * per_q);
+      G.goal_id = reinterpret_cast<int*>(gp);
+      G.barrier = reinterpret_cast<unsigned*>(gp + 64);
+      static const bool timing = getenv("PP_RRT_TIMING") != nullptr;
+      G.cycles = timing ? reinterpret_cast<long long*>(gp + 128) : nullptr;
+      if (timing) PP_CUDA(cudaMemsetAsync(gp + 128, 0, (16 + 2 * 4096) * sizeof(long long), s));
+      G.x_lo = x_lo; G.y_lo = y_lo;
+      G.cell_x = (x_hi - x_lo) / kGridSide; G.cell_y = (y_hi - y_lo) / kGridSide;
+      G.inv_cell_x = 1.0f / G.cell_x; G.inv_cell_y = 1.0f / G.cell_y;
+      PP_CUDA(cudaMemsetAsync(G.cell_count, 0, sizeof(int) * kGridCells, s));
+      PP_CUDA(cudaMemsetAsync(G.cell_start, 0, sizeof(int) * (kGridCells + 1), s));
+      const int no_goal = 0x7fffffff;                        // (pageable source: staged before the call returns)
+      PP_CUDA(cudaMemcpyAsync(G.goal_id, &no_goal, sizeof(int), cudaMemcpyHostToDevice, s));
+      PP_CUDA(cudaMemsetAsync(G.barrier, 0, 4, s));
+      const int capacity = per_sm * h->sm_count;
+      const int grid = std::max(1, std::min(K, capacity));
+      void* kargs[2] = {&A, &G};
+      PP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rrt_persistent), dim3(grid), dim3(kT), kargs, dyn_smem, s));
+      h->launches++;
+      if (timing) {
+        static long long cyc[16 + 2 * 4096];
+        PP_CUDA(cudaMemcpyAsync(cyc, G.cycles, sizeof(cyc), cudaMemcpyDeviceToHost, s));
+        PP_CUDA(cudaStreamSynchronize(s));
+        fprintf(stderr, "[pp_rrt] step (1): mean nodes in the closest cell %.0f (max %lld), longest tail %lld\n",
+                cyc[12] ? double(cyc[13]) / cyc[12] : 0.0, cyc[14], cyc[15]);
+        long long mx_near = 0, mx_edge = 0;
+        for (int r = 0; r < 4096; ++r) { mx_near += cyc[16 + 2 * r]; mx_edge += cyc[17 + 2 * r]; }
+        fprintf(stderr, "[pp_rrt] sum over rounds of the slowest CTA: nearest %lld cycles, steer+edge %lld cycles\n", mx_near, mx_edge);
+        for (int r = 0; r < 4096; r += 50)
+          if (cyc[16 + 2 * r]) fprintf(stderr, "[pp_rrt]   round %4d: slowest nearest %lld, slowest steer+edge %lld\n", r, cyc[16 + 2 * r], cyc[17 + 2 * r]);
+        fprintf(stderr, "[pp_rrt] step (2): %lld samples, mean cells %.1f (max %lld), mean nodes %.0f (max %lld)\n", cyc[12],
+                cyc[12] ? double(cyc[8]) / cyc[12] : 0.0, cyc[10], cyc[12] ? double(cyc[9]) / cyc[12] : 0.0, cyc[11]);
+        const char* names[6] = {"nearest", "steer+edge", "barrier 1", "append", "barrier 2", "regroup"};
+        for (int c = 0; c < 6; ++c) fprintf(stderr, "[pp_rrt] CTA 0 %-10s %12lld cycles\n", names[c], cyc[c]);
+      }
+    }
+  }
   const long long max_rounds = (static_cast<long long>(P.rrt_max_samples) + K - 1) / K;
   // a lone query's round has too few samples to fill the GPU with one warp per edge: split each edge's poses
   const int ext_split = static_cast<long long>(n) * K <= 2048 ? kExtSplitMax : 1;
@@ -517,7 +966,7 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
   long long round = 0;
   long long nodes_bound = 1;   // upper bound of any query's tree size
   const int chunk = 16;        // rounds between host checks of the "all done" counter
-  while (round < max_rounds) {
+  while (!persistent && round < max_rounds) {
     for (int c = 0; c < chunk && round < max_rounds; ++c, ++round) {
       // enough node slices to occupy the GPU when there are few queries
       // slices of at least kSliceGrain nodes: a lone query's early rounds (a few thousand nodes) are spread over

@@ -145,6 +145,18 @@ def nearest(node_xy, query_xy):
     return idx, d2
 
 
+def nearest_grid(node_xy, query_xy, box, cells_per_side=64):
+    """S2 through the oracle's bucket grid (BucketGridNN); must equal nearest() on any input."""
+    node_xy = np.ascontiguousarray(node_xy, dtype=np.float32).reshape(-1, 2)
+    query_xy = np.ascontiguousarray(query_xy, dtype=np.float32).reshape(-1, 2)
+    idx = np.zeros(len(query_xy), dtype=np.int32)
+    d2 = np.zeros(len(query_xy), dtype=np.float32)
+    lib().orc_nearest_grid(C.c_int64(len(node_xy)), _p(node_xy, C.c_float), C.c_int64(len(query_xy)), _p(query_xy, C.c_float),
+                           C.c_float(box[0]), C.c_float(box[1]), C.c_float(box[2]), C.c_float(box[3]), int(cells_per_side),
+                           _p(idx, C.c_int32), _p(d2, C.c_float))
+    return idx, d2
+
+
 def find_exact(keys, queries):
     keys = np.ascontiguousarray(keys, dtype=np.float64).reshape(-1, 6)
     queries = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 6)

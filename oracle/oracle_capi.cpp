@@ -232,6 +232,14 @@ void orc_det_wrap_pi(int64_t n, const double* d, double* out) {
   for (int64_t k = 0; k < n; ++k) out[k] = detm::wrap_pi(d[k]);
 }
 
+// S2 through the bucket grid (test hook: must equal orc_nearest on any input)
+void orc_nearest_grid(int64_t n_nodes, const float* node_xy, int64_t n_query, const float* query_xy, float x_lo, float x_hi,
+                      float y_lo, float y_hi, int cells_per_side, int32_t* idx, float* d2) {
+  BucketGridNN g(x_lo, x_hi, y_lo, y_hi, cells_per_side);
+  for (int64_t k = 0; k < n_nodes; ++k) g.insert(static_cast<int>(k), node_xy[2 * k], node_xy[2 * k + 1]);
+  for (int64_t q = 0; q < n_query; ++q) idx[q] = g.nearest(node_xy, query_xy[2 * q], query_xy[2 * q + 1], &d2[q]);
+}
+
 // sampling planner; result layout as the product's pp_rrt_plan:
 //   node_state[8*id] = x y parent.x parent.y heading velocity step 0 ; node_parent = tree parent
 int orc_rrt_plan(const pp_params* p, const int8_t* cspace, const pp_query* q, pp_result* r) {

@@ -1,6 +1,7 @@
 """BASELINE configs[3]: dense-clutter 8192x8192 grid @0.1 m (1 % of the area in 16x16-cell
 blocks), 1M-sample sampling-planner run on one GPU, start / goal at opposite corners inset
-10 m.  usage: python profiles/prof_rrt_config4.py [K] [max_samples] [time_step_ms]"""
+10 m.  usage: python profiles/prof_rrt_config4.py [K] [max_samples] [time_step_ms] [goal_tolerance]
+(goal_tolerance 0 switches the goal box off: the run spends its whole sample budget)"""
 import os
 import sys
 import time
@@ -13,10 +14,11 @@ from autonomouscar_b200 import PP_COLLISION_ORIENTED, Planner, default_params, m
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 dt = float(sys.argv[3]) if len(sys.argv) > 3 else 1000.0
+tol = float(sys.argv[4]) if len(sys.argv) > 4 else 2.0
 N = 8192
 p = default_params(costmap_res=0.1, costmap_width=N, costmap_height=N, collision_mode=PP_COLLISION_ORIENTED,
                    time_step_ms=dt, rrt_samples_per_round=K, rrt_max_samples=S, max_nodes=S + 1,
-                   rrt_goal_tolerance=2.0, rrt_goal_bias=0.05)
+                   rrt_goal_tolerance=tol, rrt_goal_bias=0.05)
 t0 = time.time()
 g = worlds.block_grid(N, N, frac=0.01, block=16, seed=4, noise=False)
 half = N * 0.1 / 2

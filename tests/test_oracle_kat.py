@@ -231,3 +231,25 @@ def test_sampling_planner_oracle(oracle):
     assert r2.tree_digest == r.tree_digest
     q.query_id = 4
     assert oracle.rrt_plan(p, g, q, cap_nodes=120000).tree_digest != r.tree_digest
+
+
+def test_bucket_grid_nearest_equals_the_scan(oracle):
+    """S2 on large trees: the oracle's bucket-grid query (BucketGridNN) returns exactly what the linear scan returns --
+    minimum float32 distance, ties -> lowest index -- on uniform sets, a blob in a corner with far-away queries (the
+    early phase of a config-4 run), duplicates, points on cell borders and points outside the grid."""
+    rng = np.random.default_rng(7)
+    box = (-40.0, 60.0, -30.0, 50.0)
+    cases = []
+    cases.append((rng.uniform((-40, -30), (60, 50), (5000, 2)), rng.uniform((-40, -30), (60, 50), (3000, 2))))
+    blob = rng.normal((-35.0, -25.0), 1.5, (3000, 2))
+    cases.append((blob, rng.uniform((-40, -30), (60, 50), (3000, 2))))                       # far queries, tree in a corner
+    lattice = np.stack(np.meshgrid(np.arange(-40, 60, 100 / 64), np.arange(-30, 50, 80 / 64)), -1).reshape(-1, 2)
+    cases.append((np.concatenate([lattice, lattice]), np.concatenate([lattice[::7] + 0.5 * 100 / 64, lattice[::5]])))  # ties + borders
+    cases.append((rng.uniform(-200, 200, (4000, 2)), rng.uniform(-200, 200, (2000, 2))))     # mostly outside the grid
+    cases.append((np.array([[1.0, 2.0]]), rng.uniform(-50, 70, (100, 2))))                    # a single node
+    for nodes, queries in cases:
+        for cells in (1, 7, 64, 200):
+            a_idx, a_d = oracle.nearest(nodes, queries)
+            b_idx, b_d = oracle.nearest_grid(nodes, queries, box, cells)
+            np.testing.assert_array_equal(a_idx, b_idx)
+            np.testing.assert_array_equal(a_d, b_d)
