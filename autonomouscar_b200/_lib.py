@@ -23,7 +23,7 @@ EXPORTS = [
     "pp_last_narrow_count", "pp_bench_l2_gather", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
     "pp_group_set_grid", "pp_group_collide_batch", "pp_group_plan_batch", "pp_set_grid_bank_dev", "pp_plan_batch_banked",
     "pp_pack_flags_dev", "pp_unpack_flags_dev", "pp_plan_record_stride", "pp_plan_batch_dev", "pp_plan_records_unpack",
-    "pp_group_records_dev",
+    "pp_group_records_dev", "pp_collide_batch_q16",
 ]
 # every symbol include/prius_costmap.h declares (row N2)
 COSTMAP_EXPORTS = [
@@ -63,6 +63,7 @@ def load():
     L.pp_get_cspace.argtypes = [vp, vp, C.c_size_t]
     L.pp_collide_batch.argtypes = [vp, i64, vp, vp]
     L.pp_collide_batch_dev.argtypes = [vp, i64, vp, vp]
+    L.pp_collide_batch_q16.argtypes = [vp, i64, vp, vp, vp]
     L.pp_collide_edges_dev.argtypes = [vp, i64, vp, vp]
     L.pp_pack_flags_dev.argtypes = [vp, i64, vp, vp]
     L.pp_unpack_flags_dev.argtypes = [vp, i64, vp, vp]

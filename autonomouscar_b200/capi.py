@@ -49,6 +49,30 @@ class pp_params(C.Structure):
     ]
 
 
+class pp_pose_quant(C.Structure):
+    """pp_collide_batch_q16: x = x0 + float(qx) * dx, y = y0 + float(qy) * dy, yaw = float(qyaw) * dyaw (float32)."""
+    _fields_ = [("x0", C.c_float), ("dx", C.c_float), ("y0", C.c_float), ("dy", C.c_float), ("dyaw", C.c_float)]
+
+
+def quantise_poses(poses, x_lo, x_hi, y_lo, y_hi):
+    """float32 (x, y, yaw) -> (int16 triples, pp_pose_quant, the float32 poses the device will reconstruct)."""
+    import numpy as np
+    poses = np.asarray(poses, dtype=np.float32).reshape(-1, 3)
+    k = pp_pose_quant()
+    k.dx, k.dy = np.float32((x_hi - x_lo) / 65535.0), np.float32((y_hi - y_lo) / 65535.0)
+    k.x0, k.y0 = np.float32(x_lo + 32768.0 * float(k.dx)), np.float32(y_lo + 32768.0 * float(k.dy))
+    k.dyaw = np.float32(np.pi / 32768.0)
+    q = np.empty(poses.shape, dtype=np.int16)
+    q[:, 0] = np.clip(np.rint((poses[:, 0] - np.float32(k.x0)) / np.float32(k.dx)), -32768, 32767)
+    q[:, 1] = np.clip(np.rint((poses[:, 1] - np.float32(k.y0)) / np.float32(k.dy)), -32768, 32767)
+    q[:, 2] = np.clip(np.rint(poses[:, 2] / np.float32(k.dyaw)), -32768, 32767)
+    back = np.empty(poses.shape, dtype=np.float32)
+    back[:, 0] = np.float32(k.x0) + q[:, 0].astype(np.float32) * np.float32(k.dx)
+    back[:, 1] = np.float32(k.y0) + q[:, 1].astype(np.float32) * np.float32(k.dy)
+    back[:, 2] = q[:, 2].astype(np.float32) * np.float32(k.dyaw)
+    return q, k, back
+
+
 class pp_query(C.Structure):
     _fields_ = [
         ("goal_x", C.c_double),

@@ -148,6 +148,7 @@ int pp_destroy(pp_handle* h) {
   grid_free(h);
   cudaFree(h->d_poses);
   cudaFree(h->d_flags);
+  cudaFree(h->d_q16);
   cudaFree(h->d_visited);
   cudaFree(h->d_nn_best);
   cudaFree(h->d_count);
@@ -228,16 +229,19 @@ int pp_collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_
   return collide_batch_dev(h, n, poses_dev, out_flags_dev);
 }
 
-// Host-pointer entry point: H2D, kernels and D2H pipelined in chunks on two streams so the
-// PCIe copies overlap the gather.
-int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* out_flags_host) {
-  int rc = require_grid(h, "pp_collide_batch");
-  if (rc) return rc;
-  PP_REQUIRE(n >= 0 && (n == 0 || (poses_host && out_flags_host)), "pp_collide_batch: bad arguments");
-  if (n == 0) return PP_OK;
+// Host-pointer entry points: H2D, kernels and D2H pipelined in chunks on three streams so the PCIe copies overlap
+// the kernels.  `poses_host` (float32 triples) or `q16_host` (int16 triples + `quant`, dequantised on the device).
+static int collide_batch_host(pp_handle* h, int64_t n, const float* poses_host, const int16_t* q16_host,
+                              const pp_pose_quant* quant, uint8_t* out_flags_host) {
   PP_CUDA(cudaSetDevice(h->device));
-  rc = ensure_stage(h, n);
+  int rc = ensure_stage(h, n);
   if (rc) return rc;
+  if (q16_host && n > h->q16_cap) {
+    cudaFree(h->d_q16);
+    h->d_q16 = nullptr; h->q16_cap = 0;
+    PP_CUDA(cudaMalloc(&h->d_q16, static_cast<size_t>(n) * 3 * sizeof(int16_t)));
+    h->q16_cap = n;
+  }
   const int64_t chunk = 1 << 20;
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   cudaStream_t in = h->copy_stream, ks = h->stream, out = h->out_stream;
@@ -257,10 +261,18 @@ int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* 
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int64_t lo = c * chunk, m = (lo + chunk <= n) ? chunk : n - lo;
     cudaEvent_t up = h->chunk_ev[2 * c], done = h->chunk_ev[2 * c + 1];
-    PP_CUDA(cudaMemcpyAsync(h->d_poses + 3 * lo, poses_host + 3 * lo, static_cast<size_t>(m) * 3 * sizeof(float),
-                            cudaMemcpyHostToDevice, in));
+    if (q16_host)
+      PP_CUDA(cudaMemcpyAsync(h->d_q16 + 3 * lo, q16_host + 3 * lo, static_cast<size_t>(m) * 3 * sizeof(int16_t),
+                              cudaMemcpyHostToDevice, in));
+    else
+      PP_CUDA(cudaMemcpyAsync(h->d_poses + 3 * lo, poses_host + 3 * lo, static_cast<size_t>(m) * 3 * sizeof(float),
+                              cudaMemcpyHostToDevice, in));
     PP_CUDA(cudaEventRecord(up, in));
     PP_CUDA(cudaStreamWaitEvent(ks, up, 0));
+    if (q16_host) {
+      rc = dequant_poses_dev(h, m, h->d_q16 + 3 * lo, *quant, h->d_poses + 3 * lo);
+      if (rc) return rc;
+    }
     rc = collide_launch(h, m, h->d_poses + 3 * lo, h->d_flags + lo);
     if (rc) return rc;
     PP_CUDA(cudaEventRecord(done, ks));
@@ -279,6 +291,23 @@ int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* 
   if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->phase_ms[PP_PHASE_H2D] = ms;
   else cudaGetLastError();
   return PP_OK;
+}
+
+int pp_collide_batch(pp_handle* h, int64_t n, const float* poses_host, uint8_t* out_flags_host) {
+  int rc = require_grid(h, "pp_collide_batch");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (poses_host && out_flags_host)), "pp_collide_batch: bad arguments");
+  if (n == 0) return PP_OK;
+  return collide_batch_host(h, n, poses_host, nullptr, nullptr, out_flags_host);
+}
+
+int pp_collide_batch_q16(pp_handle* h, int64_t n, const int16_t* poses_q16_host, const pp_pose_quant* quant,
+                         uint8_t* out_flags_host) {
+  int rc = require_grid(h, "pp_collide_batch_q16");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && quant && (n == 0 || (poses_q16_host && out_flags_host)), "pp_collide_batch_q16: bad arguments");
+  if (n == 0) return PP_OK;
+  return collide_batch_host(h, n, nullptr, poses_q16_host, quant, out_flags_host);
 }
 
 int pp_pack_flags_dev(pp_handle* h, int64_t n, const uint8_t* flags_dev, uint32_t* out_bits_dev) {

@@ -253,6 +253,17 @@ collide_aabb_stream_kernel(GridDev g, const float* __restrict__ poses, uint8_t* 
   }
 }
 
+// compact host format (pp_collide_batch_q16): int16 triples -> float32 poses, one thread per pose
+__global__ void __launch_bounds__(kThreads)
+dequant_poses_kernel(const short* __restrict__ q, float* __restrict__ poses, int64_t n, pp_pose_quant k) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    poses[3 * i + 0] = __fadd_rn(k.x0, __fmul_rn(static_cast<float>(q[3 * i + 0]), k.dx));
+    poses[3 * i + 1] = __fadd_rn(k.y0, __fmul_rn(static_cast<float>(q[3 * i + 1]), k.dy));
+    poses[3 * i + 2] = __fmul_rn(static_cast<float>(q[3 * i + 2]), k.dyaw);
+  }
+}
+
 // ---- flags <-> bits (the N > 1 result gather moves 1 bit per pose instead of 1 byte) ---------------------
 // word k bit b = flags[32 k + b] != 0.  One thread per 16 flags (one 128-bit load), two threads per word.
 __global__ void __launch_bounds__(kThreads)
@@ -405,9 +416,13 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
           else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
         }
         __syncwarp();
-        if (lane == 0) flags[base + s_job_off[j]] = hit ? 1 : 0;
+        if (lane == 0 && hit) s_job_off[j] |= 0x40000000;      // verdict kept next to the pose offset, stored below
       }
       __syncthreads();
+      if (tid < nj) {                                          // one flag store per thread instead of one per warp and job
+        const int v = s_job_off[tid];
+        flags[base + (v & 0x3fffffff)] = static_cast<uint8_t>(v >> 30);
+      }                                                        // (s_job_off is next written behind the barrier that opens the next pass)
     }
   }
   if (tid == 0 && narrow_counter && local_narrow) atomicAdd(narrow_counter, local_narrow);
@@ -565,6 +580,14 @@ int collide_edges_dev(pp_handle* h, int64_t n, const float* edges, uint8_t* flag
   else
     collide_edges_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, h->stream>>>(h->grid, collide_params(h),
                                                                                     edges, flags, n);
+  h->launches++;
+  PP_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int dequant_poses_dev(pp_handle* h, int64_t n, const int16_t* q, const pp_pose_quant& k, float* poses) {
+  if (n == 0) return PP_OK;
+  dequant_poses_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, h->stream>>>(q, poses, n, k);
   h->launches++;
   PP_CUDA(cudaGetLastError());
   return PP_OK;

@@ -304,6 +304,8 @@ struct pp_handle {
   float* d_poses = nullptr;
   uint8_t* d_flags = nullptr;
   int64_t stage_cap = 0;
+  int16_t* d_q16 = nullptr;        // staging of pp_collide_batch_q16
+  int64_t q16_cap = 0;
   // compaction scratch for the two-phase ORIENTED path
   int32_t* d_count = nullptr;      // device counter
   int32_t* h_count = nullptr;      // pinned mirror
@@ -336,6 +338,7 @@ int collide_counter_reset(pp_handle* h);
 int collide_counter_fetch(pp_handle* h);
 int collide_edges_dev(pp_handle* h, int64_t n, const float* edges_dev, uint8_t* flags_dev);
 int pack_flags_dev(pp_handle* h, int64_t n, const uint8_t* flags_dev, uint32_t* bits_dev);
+int dequant_poses_dev(pp_handle* h, int64_t n, const int16_t* q_dev, const pp_pose_quant& k, float* poses_dev);
 int unpack_flags_dev(pp_handle* h, int64_t n, const uint32_t* bits_dev, uint8_t* flags_dev);
 int footprint_points_dev(pp_handle* h, double x, double y, double yaw, double* out_dev, int cap, int* n);
 int sample_poses_dev(pp_handle* h, uint64_t seed, uint32_t stream, uint64_t first, int64_t n, float x_lo,

@@ -13,12 +13,13 @@ namespace pp {
 
 // What the narrow phase needs to know about one pose, relative to the corner of the first
 // tile under its bounding box (so all lattice coordinates are in [0, 96) cells).
-struct NarrowJob {
+struct __align__(16) NarrowJob {
   int32_t oi, oj, ui, uj, vi, vj;
-  uint32_t tiles;   // t0i << 16 | t0j : first tile row / column
+  uint32_t tiles;   // (t0i * TJ + t0j) * 32: word offset of the first tile under the box in occ_tiles
   uint32_t box;     // ri0 | ri1 << 7 | rj0 << 14 | rj1 << 21 : lattice bbox relative to the tile corner
   uint32_t occ;     // bit (a*3+b): tile (t0i+a, t0j+b) is under the box AND holds an obstacle
-};
+  uint32_t m0, m1, m2;   // the box's column range [rj0, rj1] as a 96-bit mask over the window's three words
+};                       // 48 bytes: three 128-bit shared-memory loads per job
 
 // same for a wider square (the yaw-independent bound): up to 64 coarse cells wide
 __device__ __forceinline__ bool coarse_square_any(const GridDev& g, int i0, int i1, int j0, int j1) {
@@ -58,10 +59,20 @@ __device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, con
   job->oi = p.oi + ((p.ai - ci0) << kFracBits);
   job->oj = p.oj + ((p.aj - cj0) << kFracBits);
   job->ui = p.ui; job->uj = p.uj; job->vi = p.vi; job->vj = p.vj;
-  job->tiles = (static_cast<uint32_t>(t0i) << 16) | static_cast<uint32_t>(t0j);
+  job->tiles = (static_cast<uint32_t>(t0i) * static_cast<uint32_t>(g.TJ) + static_cast<uint32_t>(t0j)) * kTile;
   job->box = static_cast<uint32_t>(i0 - ci0) | (static_cast<uint32_t>(i1 - ci0) << 7) |
              (static_cast<uint32_t>(j0 - cj0) << 14) | (static_cast<uint32_t>(j1 - cj0) << 21);
   job->occ = occ;
+  {
+    const int rj0 = j0 - cj0, rj1 = j1 - cj0;
+    uint32_t m[3];
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const int lo = max(rj0 - 32 * w, 0), hi = min(rj1 - 32 * w, 31);
+      m[w] = (lo <= hi) ? ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
+    }
+    job->m0 = m[0]; job->m1 = m[1]; job->m2 = m[2];
+  }
   return true;
 }
 
@@ -75,13 +86,14 @@ constexpr int kWinWords = 3 * 96;
 // the box may be loaded as well; no lattice sample can land there.  (The tile array is padded
 // by two tiles so that the last tile row can be read three tiles wide.)
 __device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& job, uint32_t* sm, int lane) {
-  const int t0i = job.tiles >> 16, t0j = job.tiles & 0xffff;
   const int b = lane >> 3, r4 = (lane & 7) * 4;
+  // one 64-bit address for the first tile row; the next rows are TJ tiles (= TJ * 128 bytes) further
+  const uint4* row = reinterpret_cast<const uint4*>(g.occ_tiles + job.tiles) + lane;
+  const unsigned row_stride = static_cast<unsigned>(g.TJ) * (kTile / 4);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
-    if (lane < 24 && ((job.occ >> (a * 3)) & 7u))
-      w = __ldg(reinterpret_cast<const uint4*>(&g.occ_tiles[(static_cast<size_t>(t0i + a) * g.TJ + t0j) * kTile]) + lane);
+    if (lane < 24 && ((job.occ >> (a * 3)) & 7u)) w = __ldg(row + a * row_stride);
     if (lane < 24) *reinterpret_cast<uint4*>(&sm[b * 96 + a * 32 + r4]) = w;
   }
   __syncwarp();
@@ -89,19 +101,12 @@ __device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& 
 
 // exact "any occupied cell inside the lattice's bounding box" on the staged window
 __device__ __forceinline__ bool window_box_any(const NarrowJob& job, const uint32_t* sm, int lane) {
-  const int ri0 = job.box & 127, ri1 = (job.box >> 7) & 127, rj0 = (job.box >> 14) & 127, rj1 = (job.box >> 21) & 127;
-  // 96-bit column mask [rj0, rj1] split over the three words
-  uint32_t m[3];
-#pragma unroll
-  for (int w = 0; w < 3; ++w) {
-    const int lo = max(rj0 - 32 * w, 0), hi = min(rj1 - 32 * w, 31);
-    m[w] = (lo <= hi) ? ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
-  }
+  const int ri0 = job.box & 127, ri1 = (job.box >> 7) & 127;
   uint32_t any = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int r = lane + 32 * k;
-    if (r >= ri0 && r <= ri1) any |= (sm[r] & m[0]) | (sm[96 + r] & m[1]) | (sm[192 + r] & m[2]);
+    if (r >= ri0 && r <= ri1) any |= (sm[r] & job.m0) | (sm[96 + r] & job.m1) | (sm[192 + r] & job.m2);
   }
   return __any_sync(0xffffffffu, any != 0);
 }
@@ -188,6 +193,9 @@ __device__ __forceinline__ bool warp_collide_jobs(const GridDev& g, const Lattic
     j.tiles = __shfl_sync(0xffffffffu, job.tiles, src);
     j.box = __shfl_sync(0xffffffffu, job.box, src);
     j.occ = __shfl_sync(0xffffffffu, job.occ, src);
+    j.m0 = __shfl_sync(0xffffffffu, job.m0, src);
+    j.m1 = __shfl_sync(0xffffffffu, job.m1, src);
+    j.m2 = __shfl_sync(0xffffffffu, job.m2, src);
     stage_window(g, j, sm, lane);
     if (window_box_any(j, sm, lane)) hit = lattice_any(lat, j, sm, lane);
     __syncwarp();

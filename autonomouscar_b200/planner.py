@@ -112,6 +112,22 @@ class Planner:
                                              out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def collide_q16(self, poses_q16, quant, out=None):
+        """pp_collide_batch_q16: int16 (qx, qy, qyaw) host poses + pp_pose_quant -> host flags (copies inside)."""
+        if isinstance(poses_q16, torch.Tensor):
+            assert not poses_q16.is_cuda and poses_q16.dtype == torch.int16 and poses_q16.is_contiguous()
+            n = poses_q16.numel() // 3
+            if out is None:
+                out = torch.empty(n, dtype=torch.uint8, pin_memory=poses_q16.is_pinned())
+            self._check(self._L.pp_collide_batch_q16(self._h, n, _dptr(poses_q16), C.byref(quant), _dptr(out)))
+            return out
+        a = np.ascontiguousarray(poses_q16, dtype=np.int16).reshape(-1, 3)
+        if out is None:
+            out = np.zeros(len(a), dtype=np.uint8)
+        self._check(self._L.pp_collide_batch_q16(self._h, len(a), a.ctypes.data_as(C.c_void_p), C.byref(quant),
+                                                 out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def collide_dev(self, poses, out=None):
         """Device tensors; asynchronous on self.stream."""
         assert poses.is_cuda and poses.dtype == torch.float32 and poses.is_contiguous()

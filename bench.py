@@ -403,6 +403,26 @@ def run_ours(args):
     e2e_value = n * world / float(t_e.item())
     assert torch.equal(h_flags, flags.cpu()), "host-pointer path and device path disagree"
     e2e_aabb = None
+    # the same through the compact host format (pp_collide_batch_q16: int16 triples, 6 B per pose over PCIe)
+    from autonomouscar_b200.capi import quantise_poses
+    q_np, quant, back_np = quantise_poses(h_poses.numpy(), *box)
+    h_q16 = torch.empty((n, 3), dtype=torch.int16, pin_memory=True)
+    h_q16.copy_(torch.from_numpy(q_np))
+    h_flags_q = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    for _ in range(2):
+        pl.collide_q16(h_q16, quant, out=h_flags_q)
+    if multi:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pl.collide_q16(h_q16, quant, out=h_flags_q)
+    t_q = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev)
+    if multi:
+        dist.all_reduce(t_q, op=dist.ReduceOp.MAX)
+    e2e_q16 = n * world / float(t_q.item())
+    back_dev = torch.from_numpy(back_np).to(dev)
+    q16_ok = bool(torch.equal(h_flags_q, pl.collide_dev(back_dev).cpu()))
+    del back_dev, q_np, back_np
 
     # ---- secondary figures on rank 0 only: direct (no broad phase), REF_AABB, plans
     extra, roof_extra = {}, {}
@@ -531,10 +551,14 @@ def run_ours(args):
             roofline["plans"] = {k: plans[k] for k in ("batch_queries", "plan_kernel_ms_rank0", "plans_per_s_kernel_rank0")
                                  if k in plans}
         e2e = {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": n,
-               "h2d_GBps_per_rank": 12 * n / float(t_e.item()) / 1e9}
+               "h2d_GBps_per_rank": 12 * n / float(t_e.item()) / 1e9,
+               "compact_int16_poses": {"value": e2e_q16, "h2d_bytes_per_step": 6 * n, "d2h_bytes_per_step": n,
+                                       "flags_equal_float32_path_on_dequantised_poses": q16_ok,
+                                       "what": "pp_collide_batch_q16: poses quantised to 6.3 mm / 9.6e-5 rad"}}
         if plans:
-            e2e["plans"] = {k: plans[k] for k in ("batch_queries", "plans_per_s", "gathered_records_equal_single_gpu",
-                                                  "record_bytes", "single_query_ms", "found") if k in plans}
+            e2e["plans"] = {k: plans[k] for k in ("batch_queries", "plans_per_s", "plans_per_s_with_host_copy_on_rank0",
+                                                  "gathered_records_equal_single_gpu", "record_bytes", "single_query_ms",
+                                                  "found") if k in plans}
         if parity:
             roofline["parity_at_n_gpus"] = parity
         cfg = headline_config(n)
@@ -858,17 +882,22 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     torch.cuda.synchronize()
     # BASELINE configs[4]: every rank plans its block, the fixed-stride records (summary + path + profile) stay on
     # the device, ONE all-gather over NVLink; the rank that wants the results (rank 0) copies them to the host once
-    reps, dts, kms = 5, [], []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        allrec = sharding.plan_batch_gather(pl, q_arr, n_total, cap_path=CAP, buffers=buffers)
-        if rank == 0:
-            h_rec.copy_(allrec, non_blocking=True)
-        pl.sync()
-        torch.cuda.synchronize()
-        dts.append(sharding.max_over_ranks(time.perf_counter() - t0, dev))
-        kms.append(pl.last_phase_ms()[4])
+    reps, dts, dts_host, kms = 5, [], [], []
+    for with_host in (False, True):
+        for _ in range(reps):
+            if multi:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            allrec = sharding.plan_batch_gather(pl, q_arr, n_total, cap_path=CAP, buffers=buffers)
+            if with_host and rank == 0:
+                h_rec.copy_(allrec, non_blocking=True)        # the rank that wants the results on the host copies them, once
+            pl.sync()
+            torch.cuda.synchronize()
+            (dts_host if with_host else dts).append(sharding.max_over_ranks(time.perf_counter() - t0, dev))
+            kms.append(pl.last_phase_ms()[4])
     dt = sorted(dts)[len(dts) // 2]
+    dt_h = sorted(dts_host)[len(dts_host) // 2]
     rows = sharding.gathered_rows(n_total, world)
     rec_view = PlanRecords(h_rec.numpy()[rows], CAP) if rank == 0 else None
     # the same queries through the host-pointer call (pp_plan_batch: results scattered into caller arrays)
@@ -986,19 +1015,34 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
             cfg4[f"K{K4}"] = {"status": int(r4.status), "samples": int(r4.n_candidates), "nodes": int(r4.n_nodes),
                               "rounds": int(r4.n_expansions), "path_nodes": int(r4.n_path), "wall_s": w4,
                               "samples_per_s": r4.n_candidates / w4}
-            if K4 == 256 and not args.skip_cpu:
-                # parity + CPU rate on a bounded prefix of the same run (the oracle's nearest neighbour is O(N) per sample)
-                from oracle import binding as orc
-                p4.rrt_max_samples = 16384
-                pl4.close()
-                pl4 = Planner(p4, device=dev.index)
-                pl4.set_grid(g4)
-                gpre = pl4.rrt_plan(q4, cap_nodes=8, cap_path=64, want_nodes=False)
+            if K4 == 256:
+                # the whole 2^20-sample budget (goal box switched off so the run cannot end early): ~980 k nodes
+                p4f = default_params(costmap_res=0.1, costmap_width=N4, costmap_height=N4, collision_mode=PP_COLLISION_ORIENTED,
+                                     time_step_ms=1000.0, rrt_samples_per_round=K4, rrt_max_samples=1 << 20,
+                                     max_nodes=(1 << 20) + 1, rrt_goal_tolerance=0.0, rrt_goal_bias=0.05)
+                pl4f = Planner(p4f, device=dev.index)
+                pl4f.set_grid(g4)
+                pl4f.rrt_plan(q4, cap_nodes=8, cap_path=64, want_nodes=False)
                 t0 = time.perf_counter()
-                cpre = orc.rrt_plan(p4, g4, q4, cap_nodes=8, cap_path=64, want_nodes=False)
+                rf = pl4f.rrt_plan(q4, cap_nodes=8, cap_path=64, want_nodes=False)
+                wf = time.perf_counter() - t0
+                cfg4["K256_full_budget"] = {"samples": int(rf.n_candidates), "nodes": int(rf.n_nodes), "rounds": int(rf.n_expansions),
+                                            "wall_s": wf, "kernel_ms": pl4f.last_phase_ms()[4], "samples_per_s": rf.n_candidates / wf,
+                                            "us_per_round": 1e3 * pl4f.last_phase_ms()[4] / max(1, rf.n_expansions),
+                                            "tree_digest": int(rf.tree_digest)}
+                pl4f.close()
+            cfg4[f"K{K4}"]["kernel_ms"] = pl4.last_phase_ms()[4]
+            cfg4[f"K{K4}"]["us_per_round"] = 1e3 * pl4.last_phase_ms()[4] / max(1, r4.n_expansions)
+            if K4 == 256 and not args.skip_cpu:
+                # parity + CPU rate on the SAME run, whole tree: the oracle answers its nearest-neighbour queries through an
+                # exact bucket grid (oracle/sampling_ref.h), which lets it replay the 265 k-node tree in seconds
+                from oracle import binding as orc
+                t0 = time.perf_counter()
+                c4r = orc.rrt_plan(p4, g4, q4, cap_nodes=8, cap_path=65536, want_nodes=False)
                 c4 = time.perf_counter() - t0
-                cfg4["first_16384_samples"] = {"cpu_oracle_samples_per_s_1thread": 16384 / c4,
-                                               "bit_exact_vs_oracle": bool(gpre.summary() == cpre.summary())}
+                cfg4["whole_run_vs_oracle"] = {"cpu_oracle_samples_per_s_1thread": c4r.n_candidates / c4,
+                                               "bit_exact_vs_oracle": bool(r4.summary() == c4r.summary()
+                                                                           and np.array_equal(r4.path_xy, c4r.path_xy))}
             pl4.close()
         del g4
     out = None
@@ -1006,7 +1050,8 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
         found = int((rec_view.field("status") == PP_PLAN_FOUND).sum())
         k_ms = sorted(kms)[len(kms) // 2]
         out = {"batch_queries": n_total, "plans_per_s": n_total / dt, "batch_wall_s": dt,
-               "what": "pp_plan_batch_dev per rank + one all-gather of fixed-stride records + one D2H on rank 0",
+               "what": "host queries in, pp_plan_batch_dev per rank, ONE all-gather of fixed-stride records: all results on every GPU",
+               "plans_per_s_with_host_copy_on_rank0": n_total / dt_h, "host_copy_bytes": int(h_rec.numel()),
                "record_bytes": stride, "gathered_records_equal_single_gpu": records_equal,
                "plans_per_s_host_pointer_call": n_total / dt_host,
                "plan_kernel_ms_rank0": k_ms, "plans_per_s_kernel_rank0": len(qs) / (k_ms * 1e-3), "found": found,

@@ -270,3 +270,23 @@ def test_pack_unpack_flags(cuda_device):
         back = pl.unpack_flags_dev(bits, n); pl.sync()
         np.testing.assert_array_equal(back.cpu().numpy(), f)
     pl.close()
+
+
+@pytest.mark.parametrize("mode", [PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED])
+def test_compact_int16_pose_format(oracle, cuda_device, mode):
+    """pp_collide_batch_q16 (6 B per pose over PCIe): the device reconstructs float32 poses with two separately rounded
+    float32 operations per coordinate; the flags equal pp_collide_batch -- and the oracle -- on exactly those poses."""
+    from autonomouscar_b200.capi import quantise_poses
+    p = default_params(costmap_res=0.1, costmap_width=1024, costmap_height=1024, collision_mode=mode)
+    grid = worlds.block_grid(1024, 1024, frac=0.02, block=8, seed=31)
+    pl = _planner(p, grid)
+    poses = worlds.random_poses(p, 300007, seed=17, inset_m=-4.0)
+    box = worlds.pose_box(p, inset_m=-4.0)
+    q, quant, back = quantise_poses(poses, *box)
+    assert np.abs(back[:, :2] - poses[:, :2]).max() < 2e-3 and np.abs(back[:, 2] - poses[:, 2]).max() < 1e-4
+    got = pl.collide_q16(q, quant)
+    np.testing.assert_array_equal(got, pl.collide(back))
+    want, _ = oracle.collide_batch(p, grid, back)
+    np.testing.assert_array_equal(got, want)
+    assert 0.0 < want.mean() < 1.0
+    pl.close()
