@@ -136,7 +136,7 @@ def default_params(**overrides):
     p.car_width = 1.586
     p.collision_mode = PP_COLLISION_AS_SHIPPED
     p.max_expansions = 100000
-    p.max_nodes = 10000
+    p.max_nodes = 60000      # ~ what the reference reaches within its 1 s guard (LP:33-39)
     p.rrt_samples_per_round = 256
     p.rrt_max_samples = 1 << 20
     p.rrt_goal_bias = 0.05

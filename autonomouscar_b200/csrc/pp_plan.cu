@@ -64,7 +64,10 @@ struct PlanArgs {
   const pp_query* queries;
   int n_queries;
   int NC;                 // slot capacity per workspace
-  int hash_size;          // power of two
+  int hash_size;          // power of two >= 2 * NC: the room the workspace reserves for the fingerprint set
+  int hash_init;          // power of two <= hash_size: what a query starts with (cleared per query); the set is
+                          // rebuilt four times as large whenever the tree could outgrow half of it
+  int max_children;       // children one expansion can add (host bound)
   int heap_smem_entries;  // frontier entries kept in shared memory (>= 1)
   int ws_per_query;       // workspace index = query index (node arrays wanted) or CTA index
   int want_path_ids;
@@ -326,6 +329,7 @@ struct Shared {
   int n_nodes, n_closed, heap_size, n_exp, status, dup_seen, cur_id, n_vel, n_yaw, n_cand_total, n_coll_total;
   int goal_hit, path_len, truncated, done;
   int q;
+  int hash_cur;    // current size of the fingerprint set (power of two, hash_init .. hash_size)
   int fast;        // frontier mode of this attempt: 1 = unordered array + block argmin, 0 = exact binary heap
   int tie_seen;    // fast mode: some pop saw its minimum cost on more than one entry
   int top_pos, top_id;
@@ -590,12 +594,13 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
     // ---- initializePlanner (LP:84-96) ------------------------------------------------
     {
       ulonglong2* hz = reinterpret_cast<ulonglong2*>(w.hash);
-      for (int k = tid; k < A.hash_size / 2; k += kT) hz[k] = make_ulonglong2(0ull, 0ull);
+      for (int k = tid; k < A.hash_init / 2; k += kT) hz[k] = make_ulonglong2(0ull, 0ull);
     }
     if (tid == 0) {
       S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
       S.n_cand_total = 0; S.n_coll_total = 0; S.goal_hit = 0; S.path_len = 0; S.truncated = 0; S.done = 0;
       S.fast = (attempt == 0 && A.fast_frontier) ? 1 : 0;
+      S.hash_cur = A.hash_init;
       S.fx_slow = 0;
       S.tie_seen = 0; S.top_pos = 0; S.top_id = 0; S.next_valid = 0; S.next_pos = 0; S.chk_valid = 0; S.next_cost = 0; S.chk_cost = 0;
       for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
     __syncthreads();
     if (warp == 0) {
       const double k0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, Q.start_speed};
-      open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k0, 0.0, 9999999999.0, -1, lane);
+      open_single_warp0<kAllSmem>(w, heap, &S, A.hash_init, k0, 0.0, 9999999999.0, -1, lane);
     }
     __syncthreads();
 
@@ -614,6 +619,22 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       // caps replace the ros::Time guard of LP:33-39
       if (S.n_exp >= P.max_expansions || S.n_nodes >= P.max_nodes) { if (tid == 0) S.status = PP_PLAN_CAP; break; }
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }  // top() of an empty queue
+      // the fingerprint set stays at most half full: rebuilt four times as large (from the stored fingerprints)
+      // before an expansion could push it past that.  Most plans (a few thousand nodes) never leave the initial size.
+      if (2 * (S.n_nodes + A.max_children + 2) > S.hash_cur && S.hash_cur < A.hash_size) {
+        int grown = S.hash_cur;
+        while (grown < A.hash_size && 2 * (S.n_nodes + A.max_children + 2) > grown) grown *= 4;
+        if (grown > A.hash_size) grown = A.hash_size;
+        const int nn = S.n_nodes;
+        __syncthreads();
+        ulonglong2* hz = reinterpret_cast<ulonglong2*>(w.hash);
+        for (int k = tid; k < grown / 2; k += kT) hz[k] = make_ulonglong2(0ull, 0ull);
+        __syncthreads();
+        for (int id = tid; id < nn; id += kT) hash_insert(w, grown, w.fp[id]);
+        if (tid == 0) S.hash_cur = grown;
+        __syncthreads();
+      }
+      const int hash_cur = S.hash_cur;
       const int top_id = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt, true);   // LP:40 (runner-up of LP:80's pass)
       // current_node's fields are key fields, identical for every copy of the node
       const double ncx = w.cx[top_id], ncy = w.cy[top_id], npx = w.px[top_id], npy = w.py[top_id];
@@ -731,7 +752,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
             g = __dsqrt_rn(dm::add(dm::mul(ddx, ddx), dm::mul(ddy, ddy)));            // LP:162 (+ LP:139-144)
             cost = dm::add(g, calc_h(P, Q, KQ, x, y, yaw, sy, cyaw, vel));             // LP:163
             fp = key_fingerprint(k);
-            suspicious = hash_contains(w, A.hash_size, fp);
+            suspicious = hash_contains(w, hash_cur, fp);
           }
         }
         // markVisited (LP:55 -> LP:318-326) for every child getNeighbors returned, bounds-guarded
@@ -792,7 +813,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
           w.closed_seq[id] = -1;
           w.rev_last[id] = top_id;
           w.fp[id] = fp;
-          hash_insert(w, A.hash_size, fp);
+          hash_insert(w, hash_cur, fp);
           if (S.fast) {   // openNode's frontier push: a plain append, position = heap size + rank
             HeapEnt e;
             e.cost = cost; e.id = id; e.pad = 0;
@@ -813,7 +834,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         if (warp == 0) {
           double k[6];
           for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
-          open_single_warp0<kAllSmem>(w, heap, &S, A.hash_size, k, 0.0, 0.0, top_id, lane);     // LP:45
+          open_single_warp0<kAllSmem>(w, heap, &S, hash_cur, k, 0.0, 0.0, top_id, lane);     // LP:45
         }
         __syncthreads();
         if (tid == 0) S.status = PP_PLAN_FOUND;
@@ -1359,6 +1380,13 @@ int plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs, bool bank
   A.n_queries = n;
   A.NC = NC;
   A.hash_size = hash_size;
+  // a found plan of the launch-file setting holds ~4-5 k nodes: 32 K entries (256 KB) cover 16 k nodes without a
+  // rebuild (measured: a smaller start saves clearing but lengthens the probe chains: 16 K entries 10.9 ms, 32 K
+  // 10.75 ms per 8192 queries), so raising max_nodes costs a batch nothing until a tree really grows that far;
+  // a lone query starts at full size (no rebuild on the latency path)
+  A.hash_init = n == 1 ? hash_size : std::min(hash_size, 32768);
+  if (getenv("PP_PLAN_HASH_INIT")) A.hash_init = std::min(hash_size, std::max(1024, atoi(getenv("PP_PLAN_HASH_INIT"))));
+  A.max_children = static_cast<int>(max_children);
   A.heap_smem_entries = heap_entries;
   A.ws_per_query = want_nodes ? 1 : 0;
   A.want_path_ids = want_path_ids ? 1 : 0;

@@ -249,10 +249,13 @@ def run_reference(args):
     emit(line)
 
 
-# ncu --set full, collide_oriented_kernel, 2^22 poses (profiles/, see README): warp instructions and DRAM bytes per pose
-NCU_ORIENTED = {"warp_inst_per_pose": 49.4, "dram_bytes_per_pose": 12.17,
-                "source": "profiles/r1_ncu_collide_oriented_v4_broad.csv"}
-NCU_DIRECT = {"warp_inst_per_pose": 390.0, "source": "profiles/README.md (direct mode, 82 % issue active)"}
+# ncu --set full captures of this round's kernels at 2^22 poses (profiles/README.md): warp instructions and DRAM bytes per pose
+NCU_ORIENTED = {"warp_inst_per_pose": 172273538 / (1 << 22), "dram_bytes_per_pose": (51.099648e6 + 77.568e3) / (1 << 22),
+                "issue_active_pct_ncu": 68.4, "source": "profiles/r2_ncu_collide_oriented_v5.csv"}
+NCU_DIRECT = {"warp_inst_per_pose": 1435975323 / (1 << 22), "issue_active_pct_ncu": 86.1,
+              "source": "profiles/r2_ncu_collide_oriented_v5_direct.csv"}
+NCU_AABB = {"warp_inst_per_pose": 31759359 / (1 << 24), "dram_bytes_per_launch_2p24": 208.604416e6 + 13.38752e6,
+            "source": "profiles/r2_ncu_collide_aabb_stream_v3.csv"}
 
 
 # -----------------------------------------------------------------------------------------
@@ -421,7 +424,10 @@ def run_ours(args):
         dist.all_reduce(t_q, op=dist.ReduceOp.MAX)
     e2e_q16 = n * world / float(t_q.item())
     back_dev = torch.from_numpy(back_np).to(dev)
-    q16_ok = bool(torch.equal(h_flags_q, pl.collide_dev(back_dev).cpu()))
+    torch.cuda.synchronize()
+    f_back = pl.collide_dev(back_dev)
+    pl.sync()                                               # (the call is asynchronous on the handle's stream)
+    q16_ok = bool(torch.equal(h_flags_q, f_back.cpu()))
     del back_dev, q_np, back_np
 
     # ---- secondary figures on rank 0 only: direct (no broad phase), REF_AABB, plans
@@ -485,13 +491,16 @@ def run_ours(args):
                                 "algorithmic_GBps_829B_per_pose": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9,
                                 "frac_of_hbm_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / peak_hbm,
                                 "frac_of_l2_gather_peak": ALG_BYTES_ORIENTED * n / (ms_direct * 1e-3) / 1e9 / l2_gbps,
-                                "bound": "issue", "narrow_units": direct_units},
+                                "bound": "issue", "narrow_units": direct_units,
+                                "warp_inst_per_pose": NCU_DIRECT["warp_inst_per_pose"], "inst_source": NCU_DIRECT["source"],
+                                "issue_achieved_Gwarp_inst_per_s": NCU_DIRECT["warp_inst_per_pose"] * n / (ms_direct * 1e-3) / 1e9},
             "l2_gather_peak_GBps_measured": l2_gbps,
             # REF_AABB (rows A10/A11, the reference-faithful test): one map look-up per pose, HBM-stream bound
             "ref_aabb": {"kernel": "collide_aabb_stream_kernel", "poses_per_s": n / (ms_aabb * 1e-3), "kernel_ms": ms_aabb,
                          "bound": "hbm", "bytes_per_launch": stream_bytes,
                          "achieved_GBps": stream_bytes / (ms_aabb * 1e-3) / 1e9, "peak_GBps": peak_hbm,
                          "frac": stream_bytes / (ms_aabb * 1e-3) / 1e9 / peak_hbm, "hit_rate": aabb_hit,
+                         "traffic": NCU_AABB["dram_bytes_per_launch_2p24"] * n / (1 << 24), "traffic_source": NCU_AABB["source"],
                          "ms_per_call_back_to_back": ms_aabb_loop,
                          "e2e_poses_per_s_host_buffers": e2e_aabb},
         }
@@ -547,6 +556,8 @@ def run_ours(args):
                             "frac": 13 * n / (k_ms * 1e-3) / 1e9 / peak, "peak_kind": peak_kind},
                     "survey_829B_per_pose_GBps": ALG_BYTES_ORIENTED * n / (k_ms * 1e-3) / 1e9}
         roofline.update(roof_extra)
+        if "oriented_direct" in roofline:
+            roofline["oriented_direct"]["issue_frac"] = roofline["oriented_direct"]["issue_achieved_Gwarp_inst_per_s"] / issue_peak
         if plans:
             roofline["plans"] = {k: plans[k] for k in ("batch_queries", "plan_kernel_ms_rank0", "plans_per_s_kernel_rank0")
                                  if k in plans}
@@ -660,7 +671,12 @@ def bench_costmap(args):
                 rs.append(sec)
             out["cpu_reference_grids_per_s_1thread"] = len(rs) / sum(rs)
             out["cpu_reference_kind"] = "reference: local_costmap.cpp compiled from the reference sources (oracle/_ref), g++ -O2, 1 thread (the node is single-threaded)"
-            out["cells_differing_from_reference"] = int((cm.build(scenes[0]) != node.build(scenes[0])[0]).sum())
+            # parity leg: the reference node reads its tf numbers through quaternion round trips; hand the CUDA builder
+            # exactly those (a last-ulp difference in the map <- base_link transform moves road-overlay samples across
+            # cell borders) and compare the two grids
+            chk = worlds.costmap_scene(0)
+            ref.costmap_derive_inputs(chk)
+            out["cells_differing_from_reference"] = int((cm.build(chk) != node.build(chk)[0]).sum())
             node.close()
     cm.close()
     # row N3: the static global road map from the reference's own 303 road polylines (12000^2 cells)

@@ -40,8 +40,8 @@ pp_params read_params(ros::NodeHandle& pnh) {
   pnh.getParam("search_res", p.search_res);
   // extensions of this build (absent = the reference's behaviour)
   pnh.param("collision_mode", p.collision_mode, static_cast<int>(PP_COLLISION_AS_SHIPPED));
-  pnh.param("max_expansions", p.max_expansions, 100000);
-  pnh.param("max_nodes", p.max_nodes, 60000);   // ~ what the reference reaches in its 1 s budget
+  pnh.param("max_expansions", p.max_expansions, p.max_expansions);
+  pnh.param("max_nodes", p.max_nodes, p.max_nodes);   // library default: 60000 ~ what the reference reaches in its 1 s budget
   pnh.param("car_length", p.car_length, 4.7);   // LP:331-334 derive these from the URDF through tf
   pnh.param("car_width", p.car_width, 1.586);
   return p;

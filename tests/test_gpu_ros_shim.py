@@ -105,6 +105,52 @@ def test_ros_shim_publishes_what_the_reference_node_publishes(cuda_device, tmp_p
     node.close()
 
 
+def test_ros_shim_accepts_a_float32_message_resolution(cuda_device, tmp_path):
+    """nav_msgs/MapMetaData.resolution is float32: a launch-file 0.1 arrives as 0.100000001490116.  The shim forwards
+    it to pp_set_grid, which must not reject the grid over the last bits of a double (the reference never looks at
+    the message's resolution, LP:425-435).  0.1 m cells, the reference's collision code enabled: the shim still
+    publishes what the reference node publishes."""
+    from oracle import ref_binding as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not present")
+    exe = _build(tmp_path)
+    p = default_params(costmap_res=0.1, costmap_width=400, costmap_height=400, collision_mode=PP_COLLISION_REF_AABB,
+                       max_expansions=300, max_nodes=20000)
+    cs = worlds.block_grid(400, 400, frac=0.004, block=6, seed=15)
+    worlds.clear_disc(cs, p, 0.0, 0.0, 5.0)
+    msg = np.ascontiguousarray(cs.reshape(-1)[::-1])
+    gpath = str(tmp_path / "grid01.bin")
+    msg.tofile(gpath)
+    steps = [((0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (9.0, 0.5, 1.5)),
+             ((-2.0, 1.0, 0.2), (0.8, 0.0, 0.0), (8.0, -1.0, 1.5)),
+             ((0.0, 0.0, 0.0), (1.2, 0.0, 0.0), (7.0, 2.0, 1.0))]
+    lines = ["param local_costmap_res 0.1", "param local_costmap_height 40", "param local_costmap_width 40",
+             f"param collision_mode {PP_COLLISION_REF_AABB}", f"param max_expansions {p.max_expansions}",
+             f"param max_nodes {p.max_nodes}", f"grid {gpath} 400 400 {float(np.float32(0.1))!r}"]
+    for tfm, tw, nav in steps:
+        lines += ["tf %r %r %r" % tfm, "twist %r %r %r" % tw, "nav %r %r %r 1.5 1.5" % nav]
+    scen = tmp_path / "scenario01.txt"
+    scen.write_text("\n".join(lines) + "\n")
+    got = _parse(subprocess.check_output([exe, str(scen)]).decode())
+    assert len(got) == len(steps)
+    node = ref.RefNode(p, ref.AABB)
+    node.set_grid_msg(msg)
+    n_found = 0
+    for (tfm, tw, nav), g in zip(steps, got):
+        node.set_base_from_map(*tfm)
+        q = make_query(nav[0], nav[1], goal_speed=nav[2], start_speed=float(np.sqrt(tw[0] ** 2 + tw[1] ** 2 + tw[2] ** 2)))
+        r = node.plan(q)
+        if r.status != 0:
+            assert g["n_path_msgs"] == 0 and g["n_mp_msgs"] == 0
+            continue
+        n_found += 1
+        assert g["n_path_msgs"] == 1 and g["n_mp_msgs"] == 1, "the shim rejected the costmap or the plan"
+        np.testing.assert_allclose(g["path"], r.path_xy, rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(g["mp"][:, 2], r.speeds)
+    assert n_found >= 1
+    node.close()
+
+
 def test_ros_costmap_shim_publishes_the_reference_nodes_grid(cuda_device, tmp_path):
     """Row N2: ros/local_costmap_b200_node.cpp, compiled unchanged against the ROS test doubles, fed the
     same LaserScan / PointCloud / OccupancyGrid messages and tf frames as the reference's
