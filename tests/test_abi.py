@@ -176,3 +176,23 @@ def test_product_never_touches_the_oracle():
                 assert "liboracle" not in text and "oracle/build" not in text, (dirpath, f)
     out = subprocess.run(["ldd", os.path.join(pkg, "libprius_planner_b200.so")], capture_output=True, text=True).stdout
     assert "liboracle" not in out
+
+
+def test_ros_cmake_configures_without_catkin(tmp_path):
+    """ros/CMakeLists.txt guards everything ROS-specific behind find_package(catkin QUIET): on a machine without ROS
+    (this image) configuring it succeeds and skips the shims (mirrors the executable target of
+    the reference's local_planner/CMakeLists.txt:144)."""
+    import shutil
+    import subprocess
+    cmake = shutil.which("cmake")
+    if cmake is None:
+        import pytest
+        pytest.skip("no cmake in this image")
+    out = subprocess.run([cmake, "-S", os.path.join(ROOT, "ros"), "-B", str(tmp_path / "b")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    text = open(os.path.join(ROOT, "ros", "CMakeLists.txt")).read()
+    assert "find_package(catkin QUIET" in text
+    for node in ("local_planner_b200_node", "local_costmap_b200_node", "global_costmap_b200_node"):
+        assert node in text and os.path.exists(os.path.join(ROOT, "ros", node + ".cpp"))
+    if "catkin not found" not in out.stdout + out.stderr:
+        assert "catkin" in out.stdout.lower()          # a ROS machine: the shims are configured instead
