@@ -208,8 +208,11 @@ collide_aabb_stream_kernel(GridDev g, const float* __restrict__ poses, uint8_t* 
     for (int s = 0; s < kAabbStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kAabbWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int k = tid; k < n_cw; k += kAabbThreads) s_coarse[k] = __ldg(&g.aabb_coarse[k]);
-  __syncthreads();
+  __syncthreads();                                   // the barriers exist: the producer starts filling the ring at once ...
+  if (warp != kAabbWarps) {                          // ... while the consumers fetch the block summary (17.7 KB at 4096^2)
+    for (int k = tid; k < n_cw; k += kAabbWarps * 32) s_coarse[k] = __ldg(&g.aabb_coarse[k]);
+    asm volatile("bar.sync 1, %0;" ::"n"(kAabbWarps * 32) : "memory");     // consumers only
+  }
   const double half_w = static_cast<double>(g.W / 2), half_h = static_cast<double>(g.H / 2);
   const double inv_res = dm::div(1.0, g.res);
   if (warp == kAabbWarps) {

@@ -886,7 +886,7 @@ def bench_plans(pl_unused, rank, world, dev, multi, args):
     lo, hi = sharding.shard_bounds(n_total, rank, world)
     qs = qs_all[lo:hi]
     q_arr = (pp_query * len(qs))(*qs)
-    CAP = 128                                                   # path slots per record (longest path here: ~70 poses)
+    CAP = 96                                                    # path slots per record (longest path here: 73 poses)
     stride = record_stride(CAP)
     warm = PlanBatch(64, cap_path=256)
     pl.plan_batch_into((pp_query * 64)(*qs[:64]), warm)                       # warm-up
