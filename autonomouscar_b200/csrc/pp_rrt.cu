@@ -441,16 +441,21 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
   return r;
 }
 
-// minimum of (dist2, id) over the sorted records [a, b), this thread taking first, first + stride, ...: four
-// independent 16-byte loads in flight
+// minimum of (dist2, id) over the sorted records [a, b), this thread taking first, first + stride, ...: kScanDepth
+// independent 16-byte loads in flight (measured: 4 / 8 / 16 -> 20.5 / 21.1 / 22.3 ms for config 4: deeper unrolling spills; a dense bucket at the frontier holds
+// thousands of nodes and sets the duration of the whole round)
+#ifndef PP_RRT_SCAN_DEPTH
+#define PP_RRT_SCAN_DEPTH 4
+#endif
+constexpr int kScanDepth = PP_RRT_SCAN_DEPTH;
 __device__ __forceinline__ unsigned long long scan_sorted(const RrtPersist& G, int a, int b, int first, int stride, float sx,
                                                           float sy, unsigned long long best) {
-  for (int k0 = a + first; k0 < b; k0 += 4 * stride) {
-    float4 nd[4];
+  for (int k0 = a + first; k0 < b; k0 += kScanDepth * stride) {
+    float4 nd[kScanDepth];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; nd[u] = k < b ? __ldcg(&G.sorted[k]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int u = 0; u < kScanDepth; ++u) { const int k = k0 + u * stride; nd[u] = k < b ? __ldcg(&G.sorted[k]) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kScanDepth; ++u) {
       const float dx = __fsub_rn(sx, nd[u].x), dy = __fsub_rn(sy, nd[u].y);
       const unsigned long long c = k0 + u * stride < b ? pack_best(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)), __float_as_int(nd[u].z)) : kBestInit;
       best = c < best ? c : best;
