@@ -196,3 +196,36 @@ def test_ros_cmake_configures_without_catkin(tmp_path):
         assert node in text and os.path.exists(os.path.join(ROOT, "ros", node + ".cpp"))
     if "catkin not found" not in out.stdout + out.stderr:
         assert "catkin" in out.stdout.lower()          # a ROS machine: the shims are configured instead
+
+
+def test_round2_struct_layouts_and_argument_errors(lib):
+    """The round-2 additions: pp_plan_record_header / pp_pose_quant layouts as the C compiler sees them, the new
+    params field, and the argument checks of the new entry points (no device needed: a null handle is refused)."""
+    from autonomouscar_b200.capi import pp_params, pp_pose_quant
+    from autonomouscar_b200.results import RECORD_HEADER
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "prius_planner.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pp_plan_record_header), offsetof(pp_plan_record_header, tree_digest),
+         offsetof(pp_plan_record_header, cap_path), sizeof(pp_pose_quant), offsetof(pp_params, goal_test_int_abs),
+         sizeof(pp_params));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
+                               os.path.join(d, "t.c")])
+        out = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert out == [RECORD_HEADER.itemsize, RECORD_HEADER.fields["tree_digest"][1], RECORD_HEADER.fields["cap_path"][1],
+                   C.sizeof(pp_pose_quant), pp_params.goal_test_int_abs.offset, C.sizeof(pp_params)]
+    assert out[0] == 64
+    null = C.c_void_p(None)
+    buf = (C.c_uint8 * 64)()
+    assert lib.pp_plan_batch_dev(null, 1, None, 16, buf) != 0
+    assert lib.pp_pack_flags_dev(null, 8, buf, buf) == 1 and lib.pp_unpack_flags_dev(null, 8, buf, buf) == 1
+    assert lib.pp_collide_batch_q16(null, 4, buf, buf, buf) != 0
+    assert lib.pp_plan_records_unpack(None, 2, 16, None) == 1 and lib.pp_plan_records_unpack(None, -1, 16, None) == 1
+    assert lib.pp_group_records_dev(null, 0, None) == 1
+    assert lib.pp_plan_record_stride(-5) == 0
