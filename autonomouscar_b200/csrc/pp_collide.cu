@@ -311,29 +311,24 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
     flags[k] = 0;
 }
 
-// One launch resolves a whole batch.  A CTA takes 1024 consecutive poses at a time and runs
-// three phases, each with dense lanes (survivors are compacted through shared memory):
-//   1. thread per pose : one bit of the dilated 8x8 map ("any obstacle within reach of this
-//                        block, for any yaw") decides ~70 % of the poses; their flag is 0
-//   2. thread per survivor : fp64 fixed-point lattice set-up, bounding box, tile / 8x8-block
-//                        occupancy under the box -> NarrowJob or flag 0
-//   3. warp per job    : stage the occupied tiles under the box (one 128 B line each), exact
-//                        box test on the staged window, then the sample lattice
-//   NU == 0 selects the run-time lattice shape.  broad_phase == 0 ("direct") disables every
-//   pruning test: each pose that overlaps the grid runs the full lattice.
-#ifndef PP_COLLIDE_PPT
-#define PP_COLLIDE_PPT 4
-#endif
-constexpr int kPosesPerThread = PP_COLLIDE_PPT;
-constexpr int kChunk = kThreads * kPosesPerThread;
-
-__device__ __forceinline__ int warp_append(int* counter, bool pred, int lane) {
-  const unsigned bal = __ballot_sync(0xffffffffu, pred);
-  int base = 0;
-  if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  return base + __popc(bal & ((1u << lane) - 1u));
-}
+// One launch resolves a whole batch.  Every WARP works on its own: it draws blocks of 128 consecutive poses from a
+// ticket counter and runs three phases over them, each with dense lanes, passing survivors along through its own
+// slice of shared memory -- no CTA-wide barrier anywhere (with CTA-wide phases 36 % of the warp samples sat in
+// __syncthreads waiting for the slowest warp of the phase):
+//   1. lane per 4 poses : one bit of the dilated 8x8 map ("any obstacle within reach of this block, for any yaw")
+//                        decides ~70 % of the poses.  All flags of the block are stored as 0 here (one 32-bit
+//                        store per lane); the later phases only store the 1s.  Survivors queue up until there
+//                        are 32 of them.
+//   2. lane per survivor : fp64 fixed-point lattice set-up, bounding box, tile and oriented 4x4-block tests
+//                        (make_job) -> free, colliding, or a NarrowJob
+//   3. warp per job    : stage the occupied tiles under the box (one 128 B line each), exact box test on the
+//                        staged window, a cheap pass along the lattice's perimeter, then the sample lattice
+//   NU == 0 selects the run-time lattice shape.  broad_phase == 0 ("direct") disables every pruning test: each
+//   pose that overlaps the grid runs the full lattice.
+//   counters[0] += narrow-phase jobs; counters[1] = the ticket, counters[2] = CTAs finished: the last CTA to
+//   finish zeroes both for the next launch (launches of one handle are serialised on its stream).
+constexpr int kBlockPoses = 128;                  // poses per ticket: 4 per lane
+constexpr int kQueueCap = 32 + kBlockPoses;       // phase 1 runs only while fewer than 32 survivors wait
 
 #ifndef PP_LATTICE_S
 #define PP_LATTICE_S 2
@@ -344,33 +339,49 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred, int lane) {
 template <int NU, int NV, int S>
 __global__ void __launch_bounds__(kThreads, PP_COLLIDE_MIN_BLOCKS)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
-                        int64_t n, int broad_phase, unsigned long long* __restrict__ narrow_counter) {
+                        int64_t n, int broad_phase, unsigned long long* __restrict__ counters) {
   __shared__ __align__(16) uint32_t s_win[kWarpsPerBlock][kWinWords];
-  __shared__ int s_queue[kChunk];
-  __shared__ NarrowJob s_jobs[kThreads];
-  __shared__ int s_job_off[kThreads];
-  __shared__ int s_nq, s_nj;
+  __shared__ NarrowJob s_jobs[kWarpsPerBlock][32];
+  __shared__ uint32_t s_job_k[kWarpsPerBlock][32];
+  __shared__ uint32_t s_queue[kWarpsPerBlock][kQueueCap];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
   const float inv_res_f = static_cast<float>(1.0 / g.res);
   const int reach = g.reach_cells;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(counters + 1);
+  const bool vec = (reinterpret_cast<uintptr_t>(poses) & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0;
+  uint32_t* queue = s_queue[wib];
   unsigned long long local_narrow = 0;
-  const int64_t n_chunks = (n + kChunk - 1) / kChunk;
-  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int64_t base = chunk * kChunk;
-    if (tid == 0) s_nq = 0;
-    __syncthreads();
-    // ---- phase 1 ------------------------------------------------------------------------
+  int nq = 0;
+  bool more = true;
+  for (;;) {
+    // ---- phase 1: blocks of 128 poses until 32 survivors wait -----------------------------------
+    while (more && nq < 32) {
+      unsigned int blk = 0;
+      if (lane == 0) blk = atomicAdd(ticket, 1u);
+      blk = __shfl_sync(0xffffffffu, blk, 0);
+      const int64_t k0 = static_cast<int64_t>(blk) * kBlockPoses + 4 * lane;
+      if (static_cast<int64_t>(blk) * kBlockPoses >= n) { more = false; break; }
+      float x[4], y[4];
+      if (vec && k0 + 3 < n) {
+        const float4* v = reinterpret_cast<const float4*>(poses + 3 * k0);
+        const float4 a = __ldg(v), b = __ldg(v + 1), c = __ldg(v + 2);
+        x[0] = a.x; y[0] = a.y; x[1] = a.w; y[1] = b.x; x[2] = b.z; y[2] = b.w; x[3] = c.y; y[3] = c.z;
+        *reinterpret_cast<uint32_t*>(flags + k0) = 0u;
+      } else {
 #pragma unroll
-    for (int p = 0; p < kPosesPerThread; ++p) {
-      const int off = p * kThreads + tid;
-      const int64_t k = base + off;
-      bool survive = false;
-      if (k < n) {
-        survive = true;
-        if (broad_phase) {
-          const float x = poses[3 * k], y = poses[3 * k + 1];
-          const float cif = static_cast<float>(g.W / 2) - y * inv_res_f;
-          const float cjf = static_cast<float>(g.H / 2) - x * inv_res_f;
+        for (int p = 0; p < 4; ++p) {
+          const int64_t k = k0 + p;
+          x[p] = y[p] = 0.0f;
+          if (k < n) { x[p] = poses[3 * k]; y[p] = poses[3 * k + 1]; flags[k] = 0; }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        bool survive = k0 + p < n;
+        if (survive && broad_phase) {
+          const float cif = static_cast<float>(g.W / 2) - y[p] * inv_res_f;
+          const float cjf = static_cast<float>(g.H / 2) - x[p] * inv_res_f;
           if (fabsf(cif) < 1.0e6f && fabsf(cjf) < 1.0e6f) {   // (NaN / absurd poses take the exact path)
             const int ic = __float2int_rd(cif), jc = __float2int_rd(cjf);
             if (ic + reach < 0 || ic - reach >= g.W || jc + reach < 0 || jc - reach >= g.H) {
@@ -381,54 +392,62 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
             }
           }
         }
-        if (!survive) flags[k] = 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, survive);
+        if (survive) queue[nq + __popc(bal & lt)] = static_cast<uint32_t>(k0 + p);
+        nq += __popc(bal);
       }
-      const int slot = warp_append(&s_nq, survive, lane);
-      if (survive) s_queue[slot] = off;
     }
-    __syncthreads();
-    const int nq = s_nq;
-    // ---- phases 2 + 3, 256 survivors at a time ------------------------------------------------
-    for (int q0 = 0; q0 < nq; q0 += kThreads) {
-      if (tid == 0) s_nj = 0;
-      __syncthreads();
-      const int qi = q0 + tid;
-      NarrowJob job;
-      bool need = false;
-      int off = 0;
-      if (qi < nq) {
-        off = s_queue[qi];
-        const int64_t k = base + off;
-        const float x = poses[3 * k], y = poses[3 * k + 1], yaw = poses[3 * k + 2];
-        const PoseFx px = pose_to_fixed(lat, g.W, g.H, g.res, static_cast<double>(x), static_cast<double>(y),
-                                        static_cast<double>(yaw));
-        need = make_job(g, lat, px, broad_phase, &job);
-        if (!need) flags[k] = 0;
-      }
-      const int slot = warp_append(&s_nj, need, lane);
-      if (need) { s_jobs[slot] = job; s_job_off[slot] = off; }
-      __syncthreads();
-      const int nj = s_nj;
-      if (tid == 0) local_narrow += nj;
-      for (int j = wib; j < nj; j += kWarpsPerBlock) {
-        const NarrowJob jb = s_jobs[j];
-        stage_window(g, jb, s_win[wib], lane);
-        bool hit = false;
-        if (!broad_phase || window_box_any(jb, s_win[wib], lane)) {
-          if (NU > 0) hit = lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, s_win[wib], lane);
-          else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
-        }
-        __syncwarp();
-        if (lane == 0 && hit) s_job_off[j] |= 0x40000000;      // verdict kept next to the pose offset, stored below
-      }
-      __syncthreads();
-      if (tid < nj) {                                          // one flag store per thread instead of one per warp and job
-        const int v = s_job_off[tid];
-        flags[base + (v & 0x3fffffff)] = static_cast<uint8_t>(v >> 30);
-      }                                                        // (s_job_off is next written behind the barrier that opens the next pass)
+    if (nq == 0) break;
+    __syncwarp();                                            // queue entries and the zeroed flags are in place
+    // ---- phase 2: the last (up to) 32 survivors, one per lane --------------------------------------
+    const int take = nq < 32 ? nq : 32;
+    nq -= take;
+    int verdict = 0;
+    NarrowJob job;
+    uint32_t k = 0;
+    if (lane < take) {
+      k = queue[nq + lane];
+      const float px = poses[3 * static_cast<int64_t>(k)], py = poses[3 * static_cast<int64_t>(k) + 1],
+                  pyaw = poses[3 * static_cast<int64_t>(k) + 2];
+      const PoseFx fx = pose_to_fixed(lat, g.W, g.H, g.res, static_cast<double>(px), static_cast<double>(py),
+                                      static_cast<double>(pyaw));
+      verdict = make_job(g, lat, fx, broad_phase, &job);
+      if (verdict == 2) flags[k] = 1;                        // decided by the coarse maps
     }
+    const uint32_t jbal = __ballot_sync(0xffffffffu, verdict == 1);
+    if (verdict == 1) {
+      const int slot = __popc(jbal & lt);
+      s_jobs[wib][slot] = job;
+      s_job_k[wib][slot] = k;
+    }
+    const int nj = __popc(jbal);
+    local_narrow += nj;
+    __syncwarp();
+    // ---- phase 3: the warp takes the jobs one after the other ----------------------------------------
+    bool mine = false;                                       // lane j keeps job j's verdict
+    for (int j = 0; j < nj; ++j) {
+      const NarrowJob jb = s_jobs[wib][j];
+      stage_window(g, jb, s_win[wib], lane);
+      bool hit = false;
+      if (!broad_phase || window_box_any(jb, s_win[wib], lane)) {
+        // (the perimeter pass only pays where most jobs are real collisions: not in direct mode)
+        if (NU > 0) hit = (broad_phase && lattice_perimeter_any<(NU > 0 ? NU : 4), (NU > 0 ? NV : 4)>(jb, s_win[wib], lane)) ||
+                          lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, s_win[wib], lane);
+        else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
+      }
+      __syncwarp();
+      if (lane == j) mine = hit;
+    }
+    if (lane < nj && mine) flags[s_job_k[wib][lane]] = 1;
+    __syncwarp();                                            // s_jobs / s_job_k are rewritten by the next pass
   }
-  if (tid == 0 && narrow_counter && local_narrow) atomicAdd(narrow_counter, local_narrow);
+  if (lane == 0 && local_narrow) atomicAdd(counters, local_narrow);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(counters + 1) + 1;
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) { *ticket = 0u; *done = 0u; __threadfence(); }
+  }
 }
 
 // Along-edge test (row S3), thread per edge: every step evaluated by one thread.  Kept for the
@@ -468,7 +487,7 @@ collide_edges_warp_kernel(GridDev g, CollideParams cp, const float* __restrict__
       if (steps < 1) steps = 1;
       for (int base = 0; base < steps && !hit; base += 32) {
         const int k = base + lane + 1;
-        bool need = false;
+        int need = 0;
         NarrowJob job;
         if (k <= steps) {
           const double t = dm::div(static_cast<double>(k), static_cast<double>(steps));
@@ -535,14 +554,21 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
       collide_aabb_kernel<<<grid_blocks(h, n, kThreads, 8), kThreads, 0, s>>>(g, poses, flags, n);
     }
   } else {
-    static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : 64;
-    const int blocks = grid_blocks(h, n, kChunk, bps);
-    if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
-      collide_oriented_kernel<48, 17, PP_LATTICE_S><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
-    else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells
-      collide_oriented_kernel<20, 8, 4><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
-    else
-      collide_oriented_kernel<0, 0, 1><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, poses, flags, n, h->broad_phase, counter);
+    // persistent: as many CTAs as fit (4 per SM), every warp draws 128-pose blocks from the ticket counter
+    static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : PP_COLLIDE_MIN_BLOCKS;
+    constexpr int64_t kSlice = int64_t(1) << 31;     // pose indices travel as 32-bit words in shared memory
+    for (int64_t lo = 0; lo < n; lo += kSlice) {
+      const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+      const float* ps = poses + 3 * lo;
+      uint8_t* fs = flags + lo;
+      const int blocks = grid_blocks(h, m, kBlockPoses * kWarpsPerBlock, bps);
+      if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
+        collide_oriented_kernel<48, 17, PP_LATTICE_S><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+      else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells
+        collide_oriented_kernel<20, 8, 4><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+      else
+        collide_oriented_kernel<0, 0, 1><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+    }
   }
   h->launches++;
   PP_CUDA(cudaGetLastError());
@@ -550,7 +576,9 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
 }
 
 int collide_counter_reset(pp_handle* h) {
-  PP_CUDA(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->stream));
+  // the narrow-phase job count, and the ORIENTED kernel's ticket / finished-CTA words (self-resetting; cleared
+  // here as well so that an aborted launch cannot poison the next batch)
+  PP_CUDA(cudaMemsetAsync(h->d_count, 0, 2 * sizeof(unsigned long long), h->stream));
   return PP_OK;
 }
 int collide_counter_fetch(pp_handle* h) {

@@ -103,7 +103,7 @@ __global__ void build_coarse(BuildArgs a) {
   }
 }
 
-// 4x4-cell coarse occupancy: thread per (coarse row, tile column) ORs 4 tile words -> 8 bits
+// 4x4-cell coarse occupancy ("any" and "full"): thread per (coarse row, tile column) combines 4 tile words -> 8 bits
 __global__ void build_coarse4(BuildArgs a) {
   const GridDev g = build_grid(a);
   const int TJ = g.TJ;
@@ -114,15 +114,18 @@ __global__ void build_coarse4(BuildArgs a) {
     const int ci4 = static_cast<int>(k / TJ);
     const int ti = ci4 >> 3, r0 = (ci4 & 7) * 4;
     const uint32_t* t = g.occ_tiles + (static_cast<size_t>(ti) * TJ + tj) * kTile + r0;
-    const uint32_t w = t[0] | t[1] | t[2] | t[3];
-    unsigned long long bits = 0;
+    const uint32_t w = t[0] | t[1] | t[2] | t[3], wa = t[0] & t[1] & t[2] & t[3];
+    unsigned long long bits = 0, full = 0;
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
+    for (int b = 0; b < 8; ++b) {
       if ((w >> (4 * b)) & 0xfu) bits |= 1ull << b;
-    if (bits) {
-      const int cj4 = tj * 8;
-      atomicOr(&g.coarse4[static_cast<size_t>(ci4) * g.CW4 + (cj4 >> 6)], bits << (cj4 & 63));
+      if (((wa >> (4 * b)) & 0xfu) == 0xfu) full |= 1ull << b;
     }
+    const int cj4 = tj * 8;
+    const size_t at = static_cast<size_t>(ci4) * g.CW4 + (cj4 >> 6);
+    if (bits) atomicOr(&g.coarse4[at], bits << (cj4 & 63));
+    // second half of the array: blocks with all 16 cells occupied (coarse4_oriented_test's collision proof)
+    if (full) atomicOr(&g.coarse4[static_cast<size_t>(g.CI4) * g.CW4 + at], full << (cj4 & 63));
   }
 }
 
@@ -264,7 +267,7 @@ GridBank bank_strides(const GridDev& g, int n) {
   b.tile_any = up(static_cast<size_t>(g.TI) * g.TJ, 16);
   b.coarse = static_cast<size_t>(g.CI8) * g.CW8;
   b.near8 = b.coarse;
-  b.coarse4 = static_cast<size_t>(g.CI4) * g.CW4;
+  b.coarse4 = 2 * static_cast<size_t>(g.CI4) * g.CW4;               // "any" map, then "full" map
   b.aabb_map = up(static_cast<size_t>(g.aabb_nx) * g.aabb_ny, 16);
   b.aabb_coarse = up(static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr, 4);
   return b;
@@ -331,7 +334,7 @@ int grid_build(pp_handle* h, const GridDev& g, const GridBank& b, const int8_t* 
   reduce_tile_any<<<blocks(n_tiles * 32), T, 0, s>>>(a);
   // (the planner's own grid is a bank of one with ZERO strides: sizes come from the shape then)
   const size_t coarse_n = n > 1 ? b.coarse * n : static_cast<size_t>(g.CI8) * g.CW8;
-  const size_t coarse4_n = n > 1 ? b.coarse4 * n : static_cast<size_t>(g.CI4) * g.CW4;
+  const size_t coarse4_n = n > 1 ? b.coarse4 * n : 2 * static_cast<size_t>(g.CI4) * g.CW4;
   const size_t acoarse_n = n > 1 ? b.aabb_coarse * n : static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr;
   PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * coarse_n, s));
   build_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.TJ), T, 0, s>>>(a);

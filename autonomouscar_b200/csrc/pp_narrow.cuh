@@ -37,13 +37,14 @@ __device__ __forceinline__ bool coarse_square_any(const GridDev& g, int i0, int 
   return any != 0;
 }
 
-// Broad phase for one pose (one thread): false = certainly collision-free.
-__device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, const PoseFx& p, int broad_phase,
-                                         NarrowJob* job) {
-  if (!p.valid) return false;
+// Broad phase for one pose (one thread): 0 = certainly collision-free, 2 = certainly colliding (nothing written to
+// *job in either case), 1 = *job describes the pose for the narrow phase.
+__device__ __forceinline__ int make_job(const GridDev& g, const Lattice& l, const PoseFx& p, int broad_phase,
+                                        NarrowJob* job) {
+  if (!p.valid) return 0;
   int i0, i1, j0, j1;
   lattice_bbox(l, p, &i0, &i1, &j0, &j1);
-  if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return false;  // box entirely off the grid
+  if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return 0;      // box entirely off the grid
   const int t0i = (i0 + kHaloCells) >> 5, t0j = (j0 + kHaloCells) >> 5;
   const int nti = ((i1 + kHaloCells) >> 5) - t0i + 1, ntj = ((j1 + kHaloCells) >> 5) - t0j + 1;
   uint32_t occ = 0;
@@ -52,8 +53,11 @@ __device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, con
       const uint32_t any = broad_phase ? __ldg(&g.tile_any[static_cast<size_t>(t0i + a) * g.TJ + (t0j + b)]) : 1u;
       occ |= (any ? 1u : 0u) << (a * 3 + b);
     }
-  if (occ == 0) return false;                                            // no obstacle in any tile under the box
-  if (broad_phase && !coarse4_box_any(g, i0, i1, j0, j1)) return false;  // none in the 4x4 blocks under it
+  if (occ == 0) return 0;                                                // no obstacle in any tile under the box
+  if (broad_phase) {                                                     // the 4x4 blocks under the footprint decide most poses
+    const int verdict = coarse4_oriented_test(g, l, p, i0, i1, j0, j1);
+    if (verdict != 1) return verdict;
+  }
   // re-base the lattice origin from the anchor cell to the first tile's corner
   const int ci0 = t0i * kTile - kHaloCells, cj0 = t0j * kTile - kHaloCells;
   job->oi = p.oi + ((p.ai - ci0) << kFracBits);
@@ -73,7 +77,7 @@ __device__ __forceinline__ bool make_job(const GridDev& g, const Lattice& l, con
     }
     job->m0 = m[0]; job->m1 = m[1]; job->m2 = m[2];
   }
-  return true;
+  return 1;
 }
 
 // Window of the warp: 96 rows x 96 columns of occupancy bits as sm[wcol * 96 + row]
@@ -147,6 +151,30 @@ __device__ __forceinline__ bool lattice_any_fixed(const NarrowJob& job, const ui
   return false;
 }
 
+// A cheap first look along the lattice's PERIMETER: 32 samples spread over each long side (b = 0 and b = NV-1) and
+// 16 over each end (a = 0 and a = NU-1), three lookups per lane.  A solid obstacle wider than the car cannot overlap
+// the footprint without crossing its border, so nearly every real collision is proven here at a tenth of the cost of
+// the full lattice.  Every sample is a lattice sample, so a hit here is a hit of the full test; no hit proves
+// nothing and the caller goes on to the full lattice (thin or small obstacles, and the free poses).
+template <int NU, int NV>
+__device__ __forceinline__ bool lattice_perimeter_any(const NarrowJob& job, const uint32_t* sm, int lane) {
+  const int a = (lane * (NU - 1)) / 31;                    // 0 .. NU-1 over the 32 lanes
+  const int eb = ((lane & 15) * (NV - 1)) / 15;            // 0 .. NV-1 over each half warp
+  const int ea = (lane & 16) ? NU - 1 : 0;
+  const int32_t si = job.oi + a * job.ui, sj = job.oj + a * job.uj;
+  const int32_t ei = job.oi + ea * job.ui + eb * job.vi, ej = job.oj + ea * job.uj + eb * job.vj;
+  const uint32_t f[3][2] = {{static_cast<uint32_t>(si), static_cast<uint32_t>(sj)},
+                            {static_cast<uint32_t>(si + (NV - 1) * job.vi), static_cast<uint32_t>(sj + (NV - 1) * job.vj)},
+                            {static_cast<uint32_t>(ei), static_cast<uint32_t>(ej)}};
+  uint32_t hit = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t w = sm[(f[k][1] >> 29) * 96 + (f[k][0] >> kFracBits)];
+    hit |= w >> ((f[k][1] >> kFracBits) & 31u);
+  }
+  return __any_sync(0xffffffffu, (hit & 1u) != 0);
+}
+
 // any lattice shape (run-time nu, nv): lane-strided walk in (a, b) order
 __device__ __forceinline__ bool lattice_any_generic(const Lattice& l, const NarrowJob& job, const uint32_t* sm,
                                                     int lane) {
@@ -168,17 +196,19 @@ __device__ __forceinline__ bool lattice_any_generic(const Lattice& l, const Narr
 
 // run-time dispatch on the lattice shape (warp-uniform)
 __device__ __forceinline__ bool lattice_any(const Lattice& l, const NarrowJob& job, const uint32_t* sm, int lane) {
-  if (l.nu == 48 && l.nv == 17) return lattice_any_fixed<48, 17, 2>(job, sm, lane);
-  if (l.nu == 20 && l.nv == 8) return lattice_any_fixed<20, 8, 4>(job, sm, lane);
+  if (l.nu == 48 && l.nv == 17) return lattice_perimeter_any<48, 17>(job, sm, lane) || lattice_any_fixed<48, 17, 2>(job, sm, lane);
+  if (l.nu == 20 && l.nv == 8) return lattice_perimeter_any<20, 8>(job, sm, lane) || lattice_any_fixed<20, 8, 4>(job, sm, lane);
   return lattice_any_generic(l, job, sm, lane);
 }
 
-// Up to 32 poses, one per lane (`need` = this lane's pose survived the broad phase and `job`
+// Up to 32 poses, one per lane (`verdict` == 1: this lane's pose survived the broad phase and `job`
 // describes it): the warp runs the narrow phase for them in turn and returns true as soon as
 // one collides.  All lanes return the same value.
 __device__ __forceinline__ bool warp_collide_jobs(const GridDev& g, const Lattice& lat, const NarrowJob& job,
-                                                  bool need, uint32_t* sm, int lane) {
-  uint32_t todo = __ballot_sync(0xffffffffu, need);
+                                                  int verdict, uint32_t* sm, int lane) {
+  // verdict = make_job's result for this lane's pose (0 when the lane has none)
+  if (__any_sync(0xffffffffu, verdict == 2)) return true;
+  uint32_t todo = __ballot_sync(0xffffffffu, verdict == 1);
   bool hit = false;
   while (todo && !hit) {
     const int src = __ffs(todo) - 1;
@@ -208,7 +238,8 @@ __device__ __forceinline__ bool warp_collide_oriented(const GridDev& g, const La
                                                       double yaw, uint32_t* sm, int lane) {
   const PoseFx p = pose_to_fixed(lat, g.W, g.H, g.res, x, y, yaw);
   NarrowJob job;
-  if (!make_job(g, lat, p, 1, &job)) return false;
+  const int verdict = make_job(g, lat, p, 1, &job);
+  if (verdict != 1) return verdict == 2;
   stage_window(g, job, sm, lane);
   bool hit = false;
   if (window_box_any(job, sm, lane)) hit = lattice_any(lat, job, sm, lane);

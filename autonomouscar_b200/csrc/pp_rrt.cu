@@ -219,7 +219,7 @@ __device__ __forceinline__ bool edge_part_hit(const RrtArgs& A, const Steer& S, 
   bool hit = false;
   for (int base = k_lo; base < k_hi && !hit; base += 32) {
     const int k = base + lane + 1;
-    bool need = false;
+    int need = 0;
     NarrowJob job;
     if (k <= k_hi) {
       const double tt = dm::div(static_cast<double>(k), static_cast<double>(S.n));
