@@ -334,7 +334,7 @@ constexpr int kQueueCap = 32 + kBlockPoses;       // phase 1 runs only while few
 #define PP_LATTICE_S 2
 #endif
 #ifndef PP_COLLIDE_MIN_BLOCKS
-#define PP_COLLIDE_MIN_BLOCKS 4
+#define PP_COLLIDE_MIN_BLOCKS 3
 #endif
 template <int NU, int NV, int S>
 __global__ void __launch_bounds__(kThreads, PP_COLLIDE_MIN_BLOCKS)
@@ -426,15 +426,12 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
     // ---- phase 3: the warp takes the jobs one after the other ----------------------------------------
     bool mine = false;                                       // lane j keeps job j's verdict
     for (int j = 0; j < nj; ++j) {
-      const NarrowJob jb = s_jobs[wib][j];
+      const NarrowJob& jb = s_jobs[wib][j];                  // (fields are fetched where they are used)
       stage_window(g, jb, s_win[wib], lane);
-      bool hit = false;
-      if (!broad_phase || window_box_any(jb, s_win[wib], lane)) {
-        // (the perimeter pass only pays where most jobs are real collisions: not in direct mode)
-        if (NU > 0) hit = (broad_phase && lattice_perimeter_any<(NU > 0 ? NU : 4), (NU > 0 ? NV : 4)>(jb, s_win[wib], lane)) ||
-                          lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, s_win[wib], lane);
-        else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
-      }
+      bool hit;
+      if (broad_phase) hit = window_collide_fixed<NU, NV, S>(lat, jb, s_win[wib], lane);
+      else if (NU > 0) hit = lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, s_win[wib], lane);
+      else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
       __syncwarp();
       if (lane == j) mine = hit;
     }

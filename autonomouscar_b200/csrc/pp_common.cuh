@@ -60,7 +60,7 @@ struct GridDev {
   unsigned long long* coarse;
   int CI8, CW8;
   // the same per 4x4-cell block (tighter pre-test of the batch kernel's bounding box): ci4 = (i + halo) >> 2
-  unsigned long long* coarse4;
+  unsigned long long* coarse4;   // 4x4-cell blocks, word pairs: {any cell occupied, all 16 cells occupied}
   int CI4, CW4;
   // `coarse` dilated by `reach8` blocks in every direction: bit set <=> some obstacle cell lies
   // within the yaw-independent square that bounds the footprint around a pose in that block
@@ -177,85 +177,92 @@ __device__ __forceinline__ bool coarse_box_any(const GridDev& g, int i0, int i1,
   return any != 0;
 }
 
-// 4x4-cell coarse occupancy under the cell box [i0,i1] x [j0,j1] (<= 16 x 16 coarse cells)
-__device__ __forceinline__ bool coarse4_box_any(const GridDev& g, int i0, int i1, int j0, int j1) {
-  const int r0 = (i0 + kHaloCells) >> 2, r1 = (i1 + kHaloCells) >> 2;
-  const int c0 = (j0 + kHaloCells) >> 2, c1 = (j1 + kHaloCells) >> 2;
-  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 16 bits starting at bit c0
-  const unsigned long long m = ((1ull << nb) - 1ull);
-  unsigned long long any = 0;
-  for (int r = r0; r <= r1; ++r) {
-    const unsigned long long* row = g.coarse4 + static_cast<size_t>(r) * g.CW4 + w0;
-    unsigned long long bits = __ldg(row) >> sh;
-    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
-    any |= bits & m;
-  }
-  return any != 0;
-}
+// The footprint as two BANDS of columns per row.  The samples are O + a u + b v = O + s U + t V with U = (nu-1) u,
+// V = (nv-1) v and s, t in [0, 1], so with D = (di, dj) the offset from O (rows, columns) and X = cross(U, V):
+//     t X = Ui dj - Uj di   and   s X = di Vj - dj Vi,   i.e.
+//     dj in kT di + [eT0, eT1]  (kT = Uj/Ui, {0, X/Ui})     and     dj in kS di + [eS0, eS1]  (kS = Vj/Vi, {0, -X/Vi})
+// -- each band linear in di.  Over a strip of rows a band's HULL (columns it reaches for some di of the strip) and
+// its CORE (columns inside it for every di of the strip) are its values at one end of the strip or the other.  A
+// band whose divisor is under half a cell (an edge nearly parallel to the columns) is dropped: it is unbounded in
+// the hull (the bounding box still applies) and no core is formed.  Users widen hulls and narrow cores by
+// kBandMargin = 1/8 cell; all values are relative to the box or the window (< 1e4 cells in magnitude, slopes
+// <= 2 * 48 / 0.5), so float rounding stays under 0.01 cell and what the bands prove stays proven.
+#ifndef PP_COARSE4_UNROLL
+#define PP_COARSE4_UNROLL 1
+#endif
+constexpr int kCoarse4Unroll = PP_COARSE4_UNROLL;
+struct Bands {
+  float kT, eT0, eT1, kS, eS0, eS1;
+  int core;          // both bands present and the lattice dense enough for the full-block argument below
+};
+constexpr float kBandMargin = 0.125f, kBandBig = 1.0e9f;
 
-// The 4x4-cell summaries under the ORIENTED footprint instead of its bounding box.  Returns 0 = certainly free,
-// 2 = certainly colliding, 1 = the narrow phase has to look.
-//
-// The samples are O + a u + b v = O + s U + t V with U = (nu-1) u, V = (nv-1) v and s, t in [0, 1], so with
-// D = (di, dj) the offset from O and X = cross(U, V):   t X = Ui dj - Uj di   and   s X = di Vj - dj Vi,   i.e.
-//     dj in (Uj/Ui) di + [0, X/Ui]     and     dj in (Vj/Vi) di - [0, X/Vi]
-// -- two bands, each linear in di.  Over the cell rows of one coarse row (4 cells, widened by kM on either side)
-// a band's hull and its core (the columns inside the band for EVERY di of the strip) are its values at one end or
-// the other, so per coarse row
-//   * the intersection of the two hulls, widened by kM, holds every sample of the row:  no "any" bit there in any
-//     row -> free (the broad phase's bounding box is 2.6 times the footprint's area for a car at 45 degrees);
-//   * a 4x4 block whose columns lie in both cores, narrowed by kM, lies inside the footprint; if the block is fully
-//     occupied ("full" bit) a sample lands in it -- the lattice's covering radius sqrt(|u|^2 + |v|^2) / 2 is below
-//     the block's inscribed radius of 2 cells whenever |u|^2 + |v|^2 <= 4 (checked), and the lattice point nearest
-//     the block's centre is then inside the block, hence inside the footprint, hence one of the samples -> collision.
-// A band whose divisor is under half a cell (an edge nearly parallel to the columns) is left out of the hull
-// (the bounding box still applies) and then no core is formed.  All values are relative to the box (< 1e4 cells
-// in magnitude with slopes <= 2 * 48 / 0.5), so float rounding stays under 0.01 cell, far inside kM = 1/8 cell:
-// both verdicts remain proofs, and every undecided pose takes the exact test.
-__device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Lattice& l, const PoseFx& p, int i0,
-                                                     int i1, int j0, int j1) {
-  const int r0 = (i0 + kHaloCells) >> 2, r1 = (i1 + kHaloCells) >> 2;
-  const int c0 = (j0 + kHaloCells) >> 2, c1 = (j1 + kHaloCells) >> 2;
-  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 16 bits starting at bit c0
+__device__ __forceinline__ Bands footprint_bands(const Lattice& l, const PoseFx& p) {
   constexpr float q = 1.0f / static_cast<float>(1 << kFracBits);
   const float ui = static_cast<float>(p.ui) * q, uj = static_cast<float>(p.uj) * q;
   const float vi = static_cast<float>(p.vi) * q, vj = static_cast<float>(p.vj) * q;
   const float Ui = static_cast<float>(l.nu - 1) * ui, Uj = static_cast<float>(l.nu - 1) * uj;
   const float Vi = static_cast<float>(l.nv - 1) * vi, Vj = static_cast<float>(l.nv - 1) * vj;
   const float X = Ui * Vj - Uj * Vi;
-  constexpr float kM = 0.125f, kStrip = 4.0f + 2.0f * kM, kBig = 1.0e9f;
-  // hull [h0, h1] and core [k0, k1] of each band as offsets to slope * d
-  float kT = 0.0f, th0 = -kBig, th1 = kBig, tk0 = kBig, tk1 = -kBig;
-  float kS = 0.0f, sh0 = -kBig, sh1 = kBig, sk0 = kBig, sk1 = -kBig;
-  const bool dense = ui * ui + uj * uj + vi * vi + vj * vj <= 4.0f;
-  if (fabsf(Ui) >= 0.5f) {
-    const float inv = __fdividef(1.0f, Ui), e = X * inv, w = kStrip * (Uj * inv);
-    kT = Uj * inv;
-    th0 = fminf(0.0f, e) + fminf(0.0f, w); th1 = fmaxf(0.0f, e) + fmaxf(0.0f, w);
-    tk0 = fminf(0.0f, e) + fmaxf(0.0f, w); tk1 = fmaxf(0.0f, e) + fminf(0.0f, w);
+  Bands b;
+  b.kT = 0.0f; b.eT0 = -kBandBig; b.eT1 = kBandBig;
+  b.kS = 0.0f; b.eS0 = -kBandBig; b.eS1 = kBandBig;
+  const bool hasT = fabsf(Ui) >= 0.5f, hasS = fabsf(Vi) >= 0.5f;
+  if (hasT) {
+    const float inv = __fdividef(1.0f, Ui), e = X * inv;
+    b.kT = Uj * inv; b.eT0 = fminf(0.0f, e); b.eT1 = fmaxf(0.0f, e);
   }
-  if (fabsf(Vi) >= 0.5f) {
-    const float inv = __fdividef(1.0f, Vi), e = -X * inv, w = kStrip * (Vj * inv);
-    kS = Vj * inv;
-    sh0 = fminf(0.0f, e) + fminf(0.0f, w); sh1 = fmaxf(0.0f, e) + fmaxf(0.0f, w);
-    sk0 = fminf(0.0f, e) + fmaxf(0.0f, w); sk1 = fmaxf(0.0f, e) + fminf(0.0f, w);
+  if (hasS) {
+    const float inv = __fdividef(1.0f, Vi), e = -X * inv;
+    b.kS = Vj * inv; b.eS0 = fminf(0.0f, e); b.eS1 = fmaxf(0.0f, e);
   }
-  const bool core = dense && fabsf(Ui) >= 0.5f && fabsf(Vi) >= 0.5f;
+  b.core = hasT && hasS && ui * ui + uj * uj + vi * vi + vj * vj <= 4.0f;
+  return b;
+}
+
+// The 4x4-cell summaries under the ORIENTED footprint instead of its bounding box.  Returns 0 = certainly free,
+// 2 = certainly colliding, 1 = the narrow phase has to look.  Per coarse row (a strip of 4 cell rows, widened by
+// the margin on either side):
+//   * the intersection of the two hulls, widened by the margin, holds every sample of the row:  no "any" bit
+//     there in any row -> free (the bounding box is 2.6 times the footprint's area for a car at 45 degrees);
+//   * a 4x4 block whose columns lie in both cores, narrowed by the margin, lies inside the footprint; if the block
+//     is fully occupied ("full" bit) a sample lands in it -- the lattice's covering radius sqrt(|u|^2 + |v|^2) / 2
+//     is below the block's inscribed radius of 2 cells whenever |u|^2 + |v|^2 <= 4 (Bands::core), and the lattice
+//     point nearest the block's centre is then inside the block, hence inside the footprint, hence one of the
+//     samples -> collision.
+// Both verdicts are proofs; every undecided pose takes the exact test.
+// *tile_rows gets bit a set when tile row (first tile row under the box) + a holds an obstacle inside the box's
+// columns: the narrow phase loads only those rows of its window.
+__device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Bands& B, const PoseFx& p, int i0,
+                                                     int i1, int j0, int j1, uint32_t* tile_rows) {
+  const int r0 = (i0 + kHaloCells) >> 2, r1 = (i1 + kHaloCells) >> 2;
+  const int c0 = (j0 + kHaloCells) >> 2, c1 = (j1 + kHaloCells) >> 2;
+  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;            // nb <= 16 bits starting at bit c0
+  constexpr float q = 1.0f / static_cast<float>(1 << kFracBits);
+  constexpr float kM = kBandMargin, kStrip = 4.0f + 2.0f * kM;
   // columns in cells from the first coarse column of the box
   const float jbase = static_cast<float>(p.aj + kHaloCells - 4 * c0) + static_cast<float>(p.oj) * q;
-  th0 += jbase - kM; th1 += jbase + kM; sh0 += jbase - kM; sh1 += jbase + kM;
-  tk0 += jbase + kM; tk1 += jbase - kM; sk0 += jbase + kM; sk1 += jbase - kM;
+  const float wT = kStrip * B.kT, wS = kStrip * B.kS;
+  // hull [h0, h1] and core [k0, k1] of each band as offsets to slope * d
+  const float th0 = B.eT0 + fminf(0.0f, wT) + (jbase - kM), th1 = B.eT1 + fmaxf(0.0f, wT) + (jbase + kM);
+  const float sh0 = B.eS0 + fminf(0.0f, wS) + (jbase - kM), sh1 = B.eS1 + fmaxf(0.0f, wS) + (jbase + kM);
+  const float tk0 = B.core ? B.eT0 + fmaxf(0.0f, wT) + (jbase + kM) : kBandBig;    // (no core: empty in every row)
+  const float tk1 = B.eT1 + fminf(0.0f, wT) + (jbase - kM);
+  const float sk0 = B.core ? B.eS0 + fmaxf(0.0f, wS) + (jbase + kM) : kBandBig;
+  const float sk1 = B.eS1 + fminf(0.0f, wS) + (jbase - kM);
   const float dbase = kM + static_cast<float>(p.oi) * q;             // di of the strip's first row = 4 r - halo - ai - dbase
   const float jhi = static_cast<float>(4 * nb - 1);
-  const size_t full_off = static_cast<size_t>(g.CI4) * g.CW4;        // the "full" map follows the "any" map
-  uint32_t any = 0, full = 0;
+  uint32_t any = 0, full = 0, rows = 0;
+  const uint32_t box = (2u << (nb - 1)) - 1u;                        // all columns of the box
+  const int tr0 = r0 >> 3;                                           // (8 coarse rows per 32-cell tile)
   const bool two = sh + nb > 64;                                     // the box's columns straddle two words
-  if (!core) { tk0 = kBig; sk0 = kBig; }                             // (an empty core in every row)
-  // straight-line body (no data-dependent branch): the loads of successive rows overlap
-#pragma unroll 2
+  // straight-line body (no data-dependent branch): the loads of successive rows overlap.  One 128-bit load brings
+  // the "any" and the "full" word of a row (they are interleaved in memory).
+  const ulonglong2* map = reinterpret_cast<const ulonglong2*>(g.coarse4);
+#pragma unroll kCoarse4Unroll
   for (int r = r0; r <= r1; ++r) {
     const float d = static_cast<float>(4 * r - kHaloCells - p.ai) - dbase;
-    const float td = kT * d, sd = kS * d;
+    const float td = B.kT * d, sd = B.kS * d;
     const float lo = fmaxf(fmaxf(td + th0, sd + sh0), 0.0f), hi = fminf(fminf(td + th1, sd + sh1), jhi);
     // block c (cells 4c .. 4c+3 from the box's first coarse column) is inside iff 4c >= klo and 4c + 4 <= khi
     const float klo = fmaxf(fmaxf(td + tk0, sd + sk0), -4.0f), khi = fminf(fminf(td + tk1, sd + sk1), jhi + 1.0f);
@@ -263,15 +270,19 @@ __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Lat
     const int ca = __float2int_rd(klo * 0.25f) + 1, cb = __float2int_rd(khi * 0.25f) - 1;
     const uint32_t hm = (lo <= hi) ? (((2u << b) - 1u) & (0xffffffffu << a)) : 0u;
     const uint32_t km = (klo <= khi && ca <= cb) ? (((2u << cb) - 1u) & (0xffffffffu << ca)) : 0u;
-    const unsigned long long* row = g.coarse4 + static_cast<size_t>(r) * g.CW4 + w0;
-    unsigned long long bits = __ldg(row) >> sh, fb = __ldg(row + full_off) >> sh;
+    const ulonglong2* row = map + static_cast<size_t>(r) * g.CW4 + w0;
+    const ulonglong2 w = __ldg(row);
+    unsigned long long bits = w.x >> sh, fb = w.y >> sh;
     if (two) {
-      bits |= __ldg(row + 1) << (64 - sh);
-      fb |= __ldg(row + full_off + 1) << (64 - sh);
+      const ulonglong2 w2 = __ldg(row + 1);
+      bits |= w2.x << (64 - sh);
+      fb |= w2.y << (64 - sh);
     }
     any |= static_cast<uint32_t>(bits) & hm;
     full |= static_cast<uint32_t>(fb) & km;
+    rows |= (static_cast<uint32_t>(bits) & box) ? 1u << ((r >> 3) - tr0) : 0u;
   }
+  *tile_rows = rows;
   return full ? 2 : (any ? 1 : 0);
 }
 

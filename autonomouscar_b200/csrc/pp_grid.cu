@@ -122,10 +122,10 @@ __global__ void build_coarse4(BuildArgs a) {
       if (((wa >> (4 * b)) & 0xfu) == 0xfu) full |= 1ull << b;
     }
     const int cj4 = tj * 8;
-    const size_t at = static_cast<size_t>(ci4) * g.CW4 + (cj4 >> 6);
+    // word pairs: {any, full}; "full" = all 16 cells occupied (coarse4_oriented_test's collision proof)
+    const size_t at = 2 * (static_cast<size_t>(ci4) * g.CW4 + (cj4 >> 6));
     if (bits) atomicOr(&g.coarse4[at], bits << (cj4 & 63));
-    // second half of the array: blocks with all 16 cells occupied (coarse4_oriented_test's collision proof)
-    if (full) atomicOr(&g.coarse4[static_cast<size_t>(g.CI4) * g.CW4 + at], full << (cj4 & 63));
+    if (full) atomicOr(&g.coarse4[at + 1], full << (cj4 & 63));
   }
 }
 
@@ -267,7 +267,7 @@ GridBank bank_strides(const GridDev& g, int n) {
   b.tile_any = up(static_cast<size_t>(g.TI) * g.TJ, 16);
   b.coarse = static_cast<size_t>(g.CI8) * g.CW8;
   b.near8 = b.coarse;
-  b.coarse4 = 2 * static_cast<size_t>(g.CI4) * g.CW4;               // "any" map, then "full" map
+  b.coarse4 = 2 * static_cast<size_t>(g.CI4) * g.CW4;               // {any, full} word pairs
   b.aabb_map = up(static_cast<size_t>(g.aabb_nx) * g.aabb_ny, 16);
   b.aabb_coarse = up(static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr, 4);
   return b;

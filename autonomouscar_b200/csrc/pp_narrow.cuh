@@ -17,9 +17,11 @@ struct __align__(16) NarrowJob {
   int32_t oi, oj, ui, uj, vi, vj;
   uint32_t tiles;   // (t0i * TJ + t0j) * 32: word offset of the first tile under the box in occ_tiles
   uint32_t box;     // ri0 | ri1 << 7 | rj0 << 14 | rj1 << 21 : lattice bbox relative to the tile corner
-  uint32_t occ;     // bit (a*3+b): tile (t0i+a, t0j+b) is under the box AND holds an obstacle
-  uint32_t m0, m1, m2;   // the box's column range [rj0, rj1] as a 96-bit mask over the window's three words
-};                       // 48 bytes: three 128-bit shared-memory loads per job
+  uint32_t occ;     // bits 3a .. 3a+2: tile row t0i+a is under the box AND holds an obstacle in the box's columns
+  // the footprint's two bands (footprint_bands) in window coordinates, hull over ONE cell row:  the columns the
+  // samples of window row r can reach are  max(kT d + tlo, kS d + slo) .. min(kT d + thi, kS d + shi),  d = r + d0
+  float kT, kS, tlo, thi, slo, shi, d0;
+};                  // 64 bytes: four 128-bit shared-memory loads per job
 
 // same for a wider square (the yaw-independent bound): up to 64 coarse cells wide
 __device__ __forceinline__ bool coarse_square_any(const GridDev& g, int i0, int i1, int j0, int j1) {
@@ -46,17 +48,19 @@ __device__ __forceinline__ int make_job(const GridDev& g, const Lattice& l, cons
   lattice_bbox(l, p, &i0, &i1, &j0, &j1);
   if (i1 < 0 || i0 >= g.W || j1 < 0 || j0 >= g.H) return 0;      // box entirely off the grid
   const int t0i = (i0 + kHaloCells) >> 5, t0j = (j0 + kHaloCells) >> 5;
-  const int nti = ((i1 + kHaloCells) >> 5) - t0i + 1, ntj = ((j1 + kHaloCells) >> 5) - t0j + 1;
-  uint32_t occ = 0;
-  for (int a = 0; a < nti; ++a)
-    for (int b = 0; b < ntj; ++b) {
-      const uint32_t any = broad_phase ? __ldg(&g.tile_any[static_cast<size_t>(t0i + a) * g.TJ + (t0j + b)]) : 1u;
-      occ |= (any ? 1u : 0u) << (a * 3 + b);
-    }
-  if (occ == 0) return 0;                                                // no obstacle in any tile under the box
-  if (broad_phase) {                                                     // the 4x4 blocks under the footprint decide most poses
-    const int verdict = coarse4_oriented_test(g, l, p, i0, i1, j0, j1);
+  const int nti = ((i1 + kHaloCells) >> 5) - t0i + 1;
+  uint32_t occ;
+  Bands B;
+  if (broad_phase) {
+    // the 4x4 blocks under the footprint decide most poses, and tell which tile rows hold an obstacle in the box
+    B = footprint_bands(l, p);
+    uint32_t rows;
+    const int verdict = coarse4_oriented_test(g, B, p, i0, i1, j0, j1, &rows);
     if (verdict != 1) return verdict;
+    occ = ((rows & 1u) ? 7u : 0u) | ((rows & 2u) ? 56u : 0u) | ((rows & 4u) ? 448u : 0u);
+  } else {
+    B.kT = B.kS = 0.0f; B.eT0 = B.eS0 = -kBandBig; B.eT1 = B.eS1 = kBandBig; B.core = 0;
+    occ = (nti >= 3 ? 511u : (nti == 2 ? 63u : 7u));               // direct mode: every tile row under the box
   }
   // re-base the lattice origin from the anchor cell to the first tile's corner
   const int ci0 = t0i * kTile - kHaloCells, cj0 = t0j * kTile - kHaloCells;
@@ -68,14 +72,14 @@ __device__ __forceinline__ int make_job(const GridDev& g, const Lattice& l, cons
              (static_cast<uint32_t>(j0 - cj0) << 14) | (static_cast<uint32_t>(j1 - cj0) << 21);
   job->occ = occ;
   {
-    const int rj0 = j0 - cj0, rj1 = j1 - cj0;
-    uint32_t m[3];
-#pragma unroll
-    for (int w = 0; w < 3; ++w) {
-      const int lo = max(rj0 - 32 * w, 0), hi = min(rj1 - 32 * w, 31);
-      m[w] = (lo <= hi) ? ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
-    }
-    job->m0 = m[0]; job->m1 = m[1]; job->m2 = m[2];
+    constexpr float q = 1.0f / static_cast<float>(1 << kFracBits);
+    constexpr float kM = kBandMargin, kStrip = 1.0f + 2.0f * kM;
+    const float oj = static_cast<float>(job->oj) * q;
+    const float wT = kStrip * B.kT, wS = kStrip * B.kS;
+    job->kT = B.kT; job->kS = B.kS;
+    job->tlo = B.eT0 + fminf(0.0f, wT) + (oj - kM); job->thi = B.eT1 + fmaxf(0.0f, wT) + (oj + kM);
+    job->slo = B.eS0 + fminf(0.0f, wS) + (oj - kM); job->shi = B.eS1 + fmaxf(0.0f, wS) + (oj + kM);
+    job->d0 = -(static_cast<float>(job->oi) * q) - kM;
   }
   return 1;
 }
@@ -103,14 +107,26 @@ __device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& 
   __syncwarp();
 }
 
-// exact "any occupied cell inside the lattice's bounding box" on the staged window
-__device__ __forceinline__ bool window_box_any(const NarrowJob& job, const uint32_t* sm, int lane) {
+// "Any occupied cell the footprint can reach" on the staged window, cell row by cell row (lane l: rows l, l + 32,
+// l + 64): the job's bands give the column range of each row.  False proves the pose free; true sends it to the
+// lattice.  (The bounding box alone -- what this test replaced -- lets through 2.6 times the footprint's area.)
+__device__ __forceinline__ bool window_hull_any(const NarrowJob& job, const uint32_t* sm, int lane) {
   const int ri0 = job.box & 127, ri1 = (job.box >> 7) & 127;
   uint32_t any = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int r = lane + 32 * k;
-    if (r >= ri0 && r <= ri1) any |= (sm[r] & job.m0) | (sm[96 + r] & job.m1) | (sm[192 + r] & job.m2);
+    const float d = static_cast<float>(r) + job.d0;
+    const float lo = fmaxf(fmaxf(fmaf(job.kT, d, job.tlo), fmaf(job.kS, d, job.slo)), 0.0f);
+    const float hi = fminf(fminf(fmaf(job.kT, d, job.thi), fmaf(job.kS, d, job.shi)), 95.0f);
+    if (r >= ri0 && r <= ri1 && lo <= hi) {
+      const int a = static_cast<int>(lo), b = static_cast<int>(hi);
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const int lw = max(a - 32 * w, 0), hw = min(b - 32 * w, 31);
+        if (lw <= hw) any |= sm[96 * w + r] & (0xffffffffu >> (31 - hw)) & (0xffffffffu << lw);
+      }
+    }
   }
   return __any_sync(0xffffffffu, any != 0);
 }
@@ -194,11 +210,25 @@ __device__ __forceinline__ bool lattice_any_generic(const Lattice& l, const Narr
 }
 
 
-// run-time dispatch on the lattice shape (warp-uniform)
-__device__ __forceinline__ bool lattice_any(const Lattice& l, const NarrowJob& job, const uint32_t* sm, int lane) {
-  if (l.nu == 48 && l.nv == 17) return lattice_perimeter_any<48, 17>(job, sm, lane) || lattice_any_fixed<48, 17, 2>(job, sm, lane);
-  if (l.nu == 20 && l.nv == 8) return lattice_perimeter_any<20, 8>(job, sm, lane) || lattice_any_fixed<20, 8, 4>(job, sm, lane);
+// The narrow phase proper on a staged window (jobs of the broad phase): a cheap pass along the lattice's perimeter
+// proves nearly every collision; what it does not prove goes through the hull test, and only then to the full
+// lattice.  NU == 0: run-time lattice shape.
+template <int NU, int NV, int S>
+__device__ __forceinline__ bool window_collide_fixed(const Lattice& l, const NarrowJob& job, const uint32_t* sm, int lane) {
+  if (NU > 0) {
+    if (lattice_perimeter_any<(NU > 0 ? NU : 4), (NU > 0 ? NV : 4)>(job, sm, lane)) return true;
+    if (!window_hull_any(job, sm, lane)) return false;
+    return lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(job, sm, lane);
+  }
+  if (!window_hull_any(job, sm, lane)) return false;
   return lattice_any_generic(l, job, sm, lane);
+}
+
+// run-time dispatch on the lattice shape (warp-uniform)
+__device__ __forceinline__ bool window_collide(const Lattice& l, const NarrowJob& job, const uint32_t* sm, int lane) {
+  if (l.nu == 48 && l.nv == 17) return window_collide_fixed<48, 17, 2>(l, job, sm, lane);
+  if (l.nu == 20 && l.nv == 8) return window_collide_fixed<20, 8, 4>(l, job, sm, lane);
+  return window_collide_fixed<0, 0, 1>(l, job, sm, lane);
 }
 
 // Up to 32 poses, one per lane (`verdict` == 1: this lane's pose survived the broad phase and `job`
@@ -223,11 +253,15 @@ __device__ __forceinline__ bool warp_collide_jobs(const GridDev& g, const Lattic
     j.tiles = __shfl_sync(0xffffffffu, job.tiles, src);
     j.box = __shfl_sync(0xffffffffu, job.box, src);
     j.occ = __shfl_sync(0xffffffffu, job.occ, src);
-    j.m0 = __shfl_sync(0xffffffffu, job.m0, src);
-    j.m1 = __shfl_sync(0xffffffffu, job.m1, src);
-    j.m2 = __shfl_sync(0xffffffffu, job.m2, src);
+    j.kT = __shfl_sync(0xffffffffu, job.kT, src);
+    j.kS = __shfl_sync(0xffffffffu, job.kS, src);
+    j.tlo = __shfl_sync(0xffffffffu, job.tlo, src);
+    j.thi = __shfl_sync(0xffffffffu, job.thi, src);
+    j.slo = __shfl_sync(0xffffffffu, job.slo, src);
+    j.shi = __shfl_sync(0xffffffffu, job.shi, src);
+    j.d0 = __shfl_sync(0xffffffffu, job.d0, src);
     stage_window(g, j, sm, lane);
-    if (window_box_any(j, sm, lane)) hit = lattice_any(lat, j, sm, lane);
+    hit = window_collide(lat, j, sm, lane);
     __syncwarp();
   }
   return hit;
@@ -241,8 +275,7 @@ __device__ __forceinline__ bool warp_collide_oriented(const GridDev& g, const La
   const int verdict = make_job(g, lat, p, 1, &job);
   if (verdict != 1) return verdict == 2;
   stage_window(g, job, sm, lane);
-  bool hit = false;
-  if (window_box_any(job, sm, lane)) hit = lattice_any(lat, job, sm, lane);
+  const bool hit = window_collide(lat, job, sm, lane);
   __syncwarp();
   return hit;
 }

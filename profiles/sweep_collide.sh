@@ -1,6 +1,7 @@
 #!/bin/bash
-# A/B of the ORIENTED batch kernel's build parameters on the GPU box: rebuilds pp_collide.o with the given -D flags.
-# usage: profiles/sweep_collide.sh "-DPP_COLLIDE_PPT=4 -DPP_COLLIDE_MIN_BLOCKS=4" ...
+# A/B of the ORIENTED batch kernel's build parameters on the GPU box: rebuilds the objects that hold the collision
+# code with the given -D flags.
+# usage: profiles/sweep_collide.sh "-DPP_COLLIDE_MIN_BLOCKS=3 -DPP_COARSE4_UNROLL=4" ...
 cd "$(dirname "$0")/.."
 for flags in "$@"; do
   rm -f autonomouscar_b200/csrc/build/pp_collide.o
