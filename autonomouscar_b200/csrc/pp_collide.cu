@@ -327,8 +327,16 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
 //   pose that overlaps the grid runs the full lattice.
 //   counters[0] += narrow-phase jobs; counters[1] = the ticket, counters[2] = CTAs finished: the last CTA to
 //   finish zeroes both for the next launch (launches of one handle are serialised on its stream).
+#ifndef PP_WIN_DEPTH
+#define PP_WIN_DEPTH 1
+#endif
+constexpr int kWinDepth = PP_WIN_DEPTH;           // windows staged ahead of the one being tested
 constexpr int kBlockPoses = 128;                  // poses per ticket: 4 per lane
 constexpr int kQueueCap = 32 + kBlockPoses;       // phase 1 runs only while fewer than 32 survivors wait
+constexpr size_t kOrientedWarpBytes = sizeof(uint32_t) * (kWinDepth + 1) * kWinWords + sizeof(NarrowJob) * 32 +
+                                      sizeof(uint32_t) * 32 + sizeof(uint32_t) * kQueueCap;
+static_assert(kOrientedWarpBytes % 16 == 0, "warp slices of shared memory stay 16-byte aligned");
+constexpr size_t kOrientedSmem = kOrientedWarpBytes * kWarpsPerBlock;
 
 #ifndef PP_LATTICE_S
 #define PP_LATTICE_S 2
@@ -340,17 +348,19 @@ template <int NU, int NV, int S>
 __global__ void __launch_bounds__(kThreads, PP_COLLIDE_MIN_BLOCKS)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
                         int64_t n, int broad_phase, unsigned long long* __restrict__ counters) {
-  __shared__ __align__(16) uint32_t s_win[kWarpsPerBlock][kWinWords];
-  __shared__ NarrowJob s_jobs[kWarpsPerBlock][32];
-  __shared__ uint32_t s_job_k[kWarpsPerBlock][32];
-  __shared__ uint32_t s_queue[kWarpsPerBlock][kQueueCap];
+  // every warp's own slice of (dynamic) shared memory: ring of windows, jobs, their pose indices, survivor queue
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  unsigned char* mine_raw = s_raw + static_cast<size_t>(wib) * kOrientedWarpBytes;
+  uint32_t (*s_win)[kWinWords] = reinterpret_cast<uint32_t (*)[kWinWords]>(mine_raw);
+  NarrowJob* s_jobs = reinterpret_cast<NarrowJob*>(mine_raw + sizeof(uint32_t) * (kWinDepth + 1) * kWinWords);
+  uint32_t* s_job_k = reinterpret_cast<uint32_t*>(s_jobs + 32);
+  uint32_t* queue = s_job_k + 32;
   const uint32_t lt = (1u << lane) - 1u;
   const float inv_res_f = static_cast<float>(1.0 / g.res);
   const int reach = g.reach_cells;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(counters + 1);
   const bool vec = (reinterpret_cast<uintptr_t>(poses) & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0;
-  uint32_t* queue = s_queue[wib];
   unsigned long long local_narrow = 0;
   int nq = 0;
   bool more = true;
@@ -417,25 +427,36 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
     const uint32_t jbal = __ballot_sync(0xffffffffu, verdict == 1);
     if (verdict == 1) {
       const int slot = __popc(jbal & lt);
-      s_jobs[wib][slot] = job;
-      s_job_k[wib][slot] = k;
+      s_jobs[slot] = job;
+      s_job_k[slot] = k;
     }
     const int nj = __popc(jbal);
     local_narrow += nj;
     __syncwarp();
     // ---- phase 3: the warp takes the jobs one after the other ----------------------------------------
+    // The windows of the next kWinDepth jobs are on their way (asynchronous copies into a ring of windows)
+    // while the lattice of the current one runs: one commit group per job, empty past the last job.
     bool mine = false;                                       // lane j keeps job j's verdict
+#pragma unroll
+    for (int j = 0; j < kWinDepth; ++j) {
+      if (j < nj) stage_window_async(g, s_jobs[j], s_win[j], lane);
+      async_commit();
+    }
     for (int j = 0; j < nj; ++j) {
-      const NarrowJob& jb = s_jobs[wib][j];                  // (fields are fetched where they are used)
-      stage_window(g, jb, s_win[wib], lane);
-      bool hit;
-      if (broad_phase) hit = window_collide_fixed<NU, NV, S>(lat, jb, s_win[wib], lane);
-      else if (NU > 0) hit = lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, s_win[wib], lane);
-      else hit = lattice_any_generic(lat, jb, s_win[wib], lane);
+      if (j + kWinDepth < nj) stage_window_async(g, s_jobs[j + kWinDepth], s_win[(j + kWinDepth) % (kWinDepth + 1)], lane);
+      async_commit();
+      async_wait<kWinDepth>();
       __syncwarp();
+      const NarrowJob& jb = s_jobs[j];                       // (fields are fetched where they are used)
+      const uint32_t* win = s_win[j % (kWinDepth + 1)];
+      bool hit;
+      if (broad_phase) hit = window_collide_fixed<NU, NV, S>(lat, jb, win, lane);
+      else if (NU > 0) hit = lattice_any_fixed<(NU > 0 ? NU : 1), (NU > 0 ? NV : 1), S>(jb, win, lane);
+      else hit = lattice_any_generic(lat, jb, win, lane);
+      __syncwarp();                                          // (this window is refilled by the copy issued next)
       if (lane == j) mine = hit;
     }
-    if (lane < nj && mine) flags[s_job_k[wib][lane]] = 1;
+    if (lane < nj && mine) flags[s_job_k[lane]] = 1;
     __syncwarp();                                            // s_jobs / s_job_k are rewritten by the next pass
   }
   if (lane == 0 && local_narrow) atomicAdd(counters, local_narrow);
@@ -554,17 +575,23 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
     // persistent: as many CTAs as fit (4 per SM), every warp draws 128-pose blocks from the ticket counter
     static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : PP_COLLIDE_MIN_BLOCKS;
     constexpr int64_t kSlice = int64_t(1) << 31;     // pose indices travel as 32-bit words in shared memory
+    if (!h->oriented_ready) {                        // (per device: the attribute lives in the context)
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<48, 17, PP_LATTICE_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOrientedSmem)));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<20, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOrientedSmem)));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOrientedSmem)));
+      h->oriented_ready = true;
+    }
     for (int64_t lo = 0; lo < n; lo += kSlice) {
       const int64_t m = n - lo < kSlice ? n - lo : kSlice;
       const float* ps = poses + 3 * lo;
       uint8_t* fs = flags + lo;
       const int blocks = grid_blocks(h, m, kBlockPoses * kWarpsPerBlock, bps);
       if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
-        collide_oriented_kernel<48, 17, PP_LATTICE_S><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+        collide_oriented_kernel<48, 17, PP_LATTICE_S><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
       else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells
-        collide_oriented_kernel<20, 8, 4><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+        collide_oriented_kernel<20, 8, 4><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
       else
-        collide_oriented_kernel<0, 0, 1><<<blocks, kThreads, 0, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+        collide_oriented_kernel<0, 0, 1><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
     }
   }
   h->launches++;

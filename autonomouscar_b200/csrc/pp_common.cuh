@@ -390,6 +390,7 @@ struct pp_handle {
   int broad_phase = 1;
   bool plan_timing_pending = false;   // ev[8] / ev[9] of an asynchronous pp_plan_batch_dev not read yet
   bool aabb_stream_ready = false;  // dynamic shared-memory limit of collide_aabb_stream_kernel raised on this device
+  bool oriented_ready = false;     // dynamic shared-memory size of the ORIENTED batch kernels set on this device
   uint64_t launches = 0;
   float phase_ms[PP_PHASE_COUNT] = {};
   int64_t last_narrow = 0;

@@ -107,6 +107,27 @@ __device__ __forceinline__ void stage_window(const GridDev& g, const NarrowJob& 
   __syncwarp();
 }
 
+// The same staging as asynchronous copies (LDGSTS, 16 bytes per lane and tile row, zero-filled where the tile row
+// holds nothing): the caller commits the group and waits for it when it gets to the job, so the L2 round trip of
+// job j + 1 .. j + depth runs under the lattice of job j.
+__device__ __forceinline__ void stage_window_async(const GridDev& g, const NarrowJob& job, uint32_t* sm, int lane) {
+  const int b = lane >> 3, r4 = (lane & 7) * 4;
+  const uint4* row = reinterpret_cast<const uint4*>(g.occ_tiles + job.tiles) + lane;
+  const unsigned row_stride = static_cast<unsigned>(g.TJ) * (kTile / 4);
+  if (lane < 24) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const bool have = (job.occ >> (a * 3)) & 7u;
+      const uint4* src = have ? row + a * row_stride : reinterpret_cast<const uint4*>(g.occ_tiles);   // (never read when !have)
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(&sm[b * 96 + a * 32 + r4]));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(have ? 16 : 0) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // "Any occupied cell the footprint can reach" on the staged window, cell row by cell row (lane l: rows l, l + 32,
 // l + 64): the job's bands give the column range of each row.  False proves the pose free; true sends it to the
 // lattice.  (The bounding box alone -- what this test replaced -- lets through 2.6 times the footprint's area.)
