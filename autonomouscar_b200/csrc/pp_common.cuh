@@ -43,6 +43,10 @@ constexpr double kFixedOne = 16777216.0;
 // ---------------------------------------------------------------------------------------
 // device-side grid representations, built by pp_set_grid (pp_grid.cu)
 // ---------------------------------------------------------------------------------------
+#ifndef PP_NEAR_BINS
+#define PP_NEAR_BINS 16
+#endif
+constexpr int kNearBins = PP_NEAR_BINS;               // yaw bins of the batch kernel's first test (GridDev::near4)
 constexpr int kHaloCells = 128;           // zero halo around the occupancy tiles
 constexpr int kTile = 32;                 // a tile is 32 x 32 cells = 32 words = one 128 B line
 
@@ -62,10 +66,13 @@ struct GridDev {
   // the same per 4x4-cell block (tighter pre-test of the batch kernel's bounding box): ci4 = (i + halo) >> 2
   unsigned long long* coarse4;   // 4x4-cell blocks, word pairs: {any cell occupied, all 16 cells occupied}
   int CI4, CW4;
-  // `coarse` dilated by `reach8` blocks in every direction: bit set <=> some obstacle cell lies
-  // within the yaw-independent square that bounds the footprint around a pose in that block
-  unsigned long long* near8;
-  int reach_cells;          // half side of that square, in cells (footprint half diagonal + slack)
+  // kNearBins maps, one per yaw bin of pi / kNearBins (the footprint is symmetric about the pose, so yaw and
+  // yaw + pi share a bin):  near4[(bin * CI4 + ci4) * CW4 + (cj4 >> 6)] bit (cj4 & 63) is set <=> some obstacle
+  // lies in a 4x4 block that the footprint can touch, for a pose anywhere in block (ci4, cj4) at any yaw of the
+  // bin -- the "any" map dilated by the bin's structuring element (pp_grid.cu: near_span_table).  The batch
+  // kernel's first test: one bit per pose.
+  unsigned long long* near4;
+  int reach_cells;          // footprint half diagonal + slack, in cells: poses further than this from the grid are free
   // REF_AABB box-dilated map over base cells [-aabb_pad_x, W+aabb_pad_x) x [-aabb_pad_y, H+...)
   //   aabb_map[(bx+pad_x) * aabb_stride + (by+pad_y)] = 1 iff the LP:477-495 box anchored at
   //   (bx,by) contains a cell == 100
@@ -84,7 +91,7 @@ struct GridDev {
 // banks; pp_plan_batch_banked lets every query name its grid.
 struct GridBank {
   int n = 0;
-  size_t cspace = 0, occ_tiles = 0, tile_any = 0, coarse = 0, coarse4 = 0, near8 = 0, aabb_map = 0, aabb_coarse = 0;
+  size_t cspace = 0, occ_tiles = 0, tile_any = 0, coarse = 0, coarse4 = 0, near4 = 0, aabb_map = 0, aabb_coarse = 0;
 };
 __host__ __device__ inline GridDev grid_at(GridDev g, const GridBank& b, unsigned k) {
   g.cspace += k * b.cspace;
@@ -92,7 +99,7 @@ __host__ __device__ inline GridDev grid_at(GridDev g, const GridBank& b, unsigne
   g.tile_any += k * b.tile_any;
   g.coarse += k * b.coarse;
   g.coarse4 += k * b.coarse4;
-  g.near8 += k * b.near8;
+  g.near4 += k * b.near4;
   g.aabb_map += k * b.aabb_map;
   g.aabb_coarse += k * b.aabb_coarse;
   return g;
@@ -261,6 +268,10 @@ __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Ban
   const ulonglong2* map = reinterpret_cast<const ulonglong2*>(g.coarse4);
 #pragma unroll kCoarse4Unroll
   for (int r = r0; r <= r1; ++r) {
+    const ulonglong2* row = map + static_cast<size_t>(r) * g.CW4 + w0;
+    const ulonglong2 w = __ldg(row);
+    ulonglong2 w2 = make_ulonglong2(0ull, 0ull);
+    if (two) w2 = __ldg(row + 1);
     const float d = static_cast<float>(4 * r - kHaloCells - p.ai) - dbase;
     const float td = B.kT * d, sd = B.kS * d;
     const float lo = fmaxf(fmaxf(td + th0, sd + sh0), 0.0f), hi = fminf(fminf(td + th1, sd + sh1), jhi);
@@ -270,11 +281,8 @@ __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Ban
     const int ca = __float2int_rd(klo * 0.25f) + 1, cb = __float2int_rd(khi * 0.25f) - 1;
     const uint32_t hm = (lo <= hi) ? (((2u << b) - 1u) & (0xffffffffu << a)) : 0u;
     const uint32_t km = (klo <= khi && ca <= cb) ? (((2u << cb) - 1u) & (0xffffffffu << ca)) : 0u;
-    const ulonglong2* row = map + static_cast<size_t>(r) * g.CW4 + w0;
-    const ulonglong2 w = __ldg(row);
     unsigned long long bits = w.x >> sh, fb = w.y >> sh;
     if (two) {
-      const ulonglong2 w2 = __ldg(row + 1);
       bits |= w2.x << (64 - sh);
       fb |= w2.y << (64 - sh);
     }
@@ -387,6 +395,8 @@ struct pp_handle {
   int bank_cap = 0;
   uint8_t* bank_rows = nullptr;    // REF_AABB pass-1 scratch of the bank
   int* d_box_tables = nullptr;     // LP:473-476 interval tables (xlo | xhi | ylo | yhi)
+  int16_t* d_near_spans = nullptr;   // structuring elements of GridDev::near4: [bin][2 near_e + 1]{first, last} block column
+  int near_e = 0;
   int broad_phase = 1;
   bool plan_timing_pending = false;   // ev[8] / ev[9] of an asynchronous pp_plan_batch_dev not read yet
   bool aabb_stream_ready = false;  // dynamic shared-memory limit of collide_aabb_stream_kernel raised on this device

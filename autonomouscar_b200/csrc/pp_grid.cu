@@ -29,6 +29,8 @@ struct BuildArgs {
   uint8_t* rows;             // REF_AABB pass-1 scratch of grid 0, rows_stride bytes apart
   size_t rows_stride;
   const int *xlo, *xhi, *ylo, *yhi;
+  const int16_t* near_spans;  // [bin][2 near_e + 1]{first, last}: structuring elements of near4
+  int near_e;
 };
 __device__ __forceinline__ GridDev build_grid(const BuildArgs& a) { return grid_at(a.g, a.b, blockIdx.y); }
 
@@ -129,26 +131,32 @@ __global__ void build_coarse4(BuildArgs a) {
   }
 }
 
-// near8 = coarse dilated by r8 blocks (square structuring element), one thread per 64-bit word
-__global__ void dilate_coarse(BuildArgs a, int r8) {
+// near4[bin] = the 4x4-block "any" map dilated by the bin's structuring element: output block (r, c) is set iff an
+// input block (r + di, c + dj) is, for some row di in [-near_e, near_e] and dj in that row's span.  One thread per
+// 64-bit output word.
+__global__ void dilate_near4(BuildArgs a) {
   const GridDev g = build_grid(a);
-  const int CI8 = g.CI8, CW8 = g.CW8;
-  const int64_t total = static_cast<int64_t>(CI8) * CW8;
+  const int CI4 = g.CI4, CW4 = g.CW4, E = a.near_e;
+  const int64_t per_bin = static_cast<int64_t>(CI4) * CW4, total = per_bin * kNearBins;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(k % CW8), r = static_cast<int>(k / CW8);
+    const int bin = static_cast<int>(k / per_bin);
+    const int64_t kk = k - bin * per_bin;
+    const int w = static_cast<int>(kk % CW4), r = static_cast<int>(kk / CW4);
+    const int16_t* spans = a.near_spans + static_cast<size_t>(bin) * (2 * E + 1) * 2;
     unsigned long long acc = 0;
-    for (int rr = max(r - r8, 0); rr <= min(r + r8, CI8 - 1); ++rr) {
-      const unsigned long long* row = g.coarse + static_cast<size_t>(rr) * CW8;
-      const unsigned long long c = row[w], l = w > 0 ? row[w - 1] : 0ull, h = w + 1 < CW8 ? row[w + 1] : 0ull;
-      unsigned long long d = c;
-      for (int sft = 1; sft <= r8; ++sft) {        // r8 < 64
-        d |= (c << sft) | (l >> (64 - sft));       // bits moving up from lower columns
-        d |= (c >> sft) | (h << (64 - sft));       // bits moving down from higher columns
+    for (int di = -E; di <= E; ++di) {
+      const int rr = r + di, lo = spans[2 * (di + E)], hi = spans[2 * (di + E) + 1];   // |lo|, |hi| < 64
+      if (rr < 0 || rr >= CI4 || lo > hi) continue;
+      const unsigned long long* row = g.coarse4 + 2 * static_cast<size_t>(rr) * CW4;   // ("any" words of the pairs)
+      const unsigned long long c = row[2 * w], l = w > 0 ? row[2 * (w - 1)] : 0ull, h = w + 1 < CW4 ? row[2 * (w + 1)] : 0ull;
+      for (int dj = lo; dj <= hi; ++dj) {          // output bit p takes input bit p + dj
+        if (dj == 0) acc |= c;
+        else if (dj > 0) acc |= (c >> dj) | (h << (64 - dj));
+        else acc |= (c << -dj) | (l >> (64 + dj));
       }
-      acc |= d;
     }
-    g.near8[k] = acc;
+    g.near4[k] = acc;
   }
 }
 
@@ -266,7 +274,7 @@ GridBank bank_strides(const GridDev& g, int n) {
   b.occ_tiles = (static_cast<size_t>(g.TI) * g.TJ + 2) * kTile;
   b.tile_any = up(static_cast<size_t>(g.TI) * g.TJ, 16);
   b.coarse = static_cast<size_t>(g.CI8) * g.CW8;
-  b.near8 = b.coarse;
+  b.near4 = static_cast<size_t>(kNearBins) * g.CI4 * g.CW4;
   b.coarse4 = 2 * static_cast<size_t>(g.CI4) * g.CW4;               // {any, full} word pairs
   b.aabb_map = up(static_cast<size_t>(g.aabb_nx) * g.aabb_ny, 16);
   b.aabb_coarse = up(static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr, 4);
@@ -279,7 +287,7 @@ void grid_free_arrays(GridDev* g) {
   cudaFree(g->tile_any);
   cudaFree(g->coarse);
   cudaFree(g->coarse4);
-  cudaFree(g->near8);
+  cudaFree(g->near4);
   cudaFree(g->aabb_map);
   cudaFree(g->aabb_coarse);
   *g = GridDev{};
@@ -292,10 +300,61 @@ int grid_alloc(GridDev* g, const GridBank& b) {
   PP_CUDA(cudaMemset(g->occ_tiles, 0, b.occ_tiles * n * sizeof(uint32_t)));      // (the padding tiles stay zero)
   PP_CUDA(cudaMalloc(&g->tile_any, b.tile_any * n));
   PP_CUDA(cudaMalloc(&g->coarse, sizeof(unsigned long long) * b.coarse * n));
-  PP_CUDA(cudaMalloc(&g->near8, sizeof(unsigned long long) * b.near8 * n));
+  PP_CUDA(cudaMalloc(&g->near4, sizeof(unsigned long long) * b.near4 * n));
   PP_CUDA(cudaMalloc(&g->coarse4, sizeof(unsigned long long) * b.coarse4 * n));
   PP_CUDA(cudaMalloc(&g->aabb_map, b.aabb_map * n));
   PP_CUDA(cudaMalloc(&g->aabb_coarse, sizeof(uint32_t) * b.aabb_coarse * n));
+  return PP_OK;
+}
+
+// Structuring elements of near4, per yaw bin:  which 4x4 blocks (di, dj) away from the pose's block can hold a
+// lattice sample.  With the pose at continuous cell coordinates c inside its block and a sample at c + d (d in the
+// footprint rectangle R(yaw), centred on the pose: half lengths du along (sin, cos) and dv along (cos, -sin) in
+// (row, column) -- pose_to_fixed's u and v), the sample's block is (di, dj) away only if d lies in the open square
+// 4 (di, dj) + (-4, 4)^2: a rectangle-against-square overlap test (separating axes: the square's two and the
+// rectangle's two), taken over the yaws of the bin widened by 1e-3 rad (the kernel bins a float product).  The
+// rectangle is inflated by 1.5 cells (the kernel's float cell index may be one off in each axis) plus what the
+// yaw sampling step can move a corner.  Rows are stored as one span of columns {first, last} (first > last: empty).
+void near_span_table(const Lattice& lat, int* e_out, std::vector<int16_t>* table) {
+  const double du = lat.su * lat.hu, dv = lat.sv * lat.hv;
+  const int E = static_cast<int>(std::ceil((std::sqrt(du * du + dv * dv) + 1.5 + 4.0) / 4.0)) + 1;
+  const int rows = 2 * E + 1, NS = 32;
+  table->assign(static_cast<size_t>(kNearBins) * rows * 2, 0);
+  for (int b = 0; b < kNearBins; ++b) {
+    const double lo = b * M_PI / kNearBins - 1.0e-3, hi = (b + 1) * M_PI / kNearBins + 1.0e-3;
+    const double pad = 1.5 + 0.05 + (du + dv) * (hi - lo) / NS;
+    const double ha = du + pad, hb = dv + pad, hs = 4.0;
+    std::vector<int> first(rows, 1), last(rows, 0);
+    for (int k = 0; k <= NS; ++k) {
+      const double t = lo + (hi - lo) * k / NS;
+      const double ux = std::sin(t), uy = std::cos(t), vx = std::cos(t), vy = -std::sin(t);
+      for (int di = -E; di <= E; ++di)
+        for (int dj = -E; dj <= E; ++dj) {
+          const double cx = 4.0 * di, cy = 4.0 * dj;
+          if (std::fabs(cx) >= hs + ha * std::fabs(ux) + hb * std::fabs(vx)) continue;
+          if (std::fabs(cy) >= hs + ha * std::fabs(uy) + hb * std::fabs(vy)) continue;
+          if (std::fabs(cx * ux + cy * uy) >= ha + hs * (std::fabs(ux) + std::fabs(uy))) continue;
+          if (std::fabs(cx * vx + cy * vy) >= hb + hs * (std::fabs(vx) + std::fabs(vy))) continue;
+          int& f = first[di + E];
+          int& l = last[di + E];
+          if (f > l) { f = dj; l = dj; } else { f = std::min(f, dj); l = std::max(l, dj); }
+        }
+    }
+    for (int r = 0; r < rows; ++r) {
+      (*table)[(static_cast<size_t>(b) * rows + r) * 2] = static_cast<int16_t>(first[r]);
+      (*table)[(static_cast<size_t>(b) * rows + r) * 2 + 1] = static_cast<int16_t>(last[r]);
+    }
+  }
+  *e_out = E;
+}
+
+int ensure_near_spans(pp_handle* h) {
+  if (h->d_near_spans) return PP_OK;
+  std::vector<int16_t> t;
+  near_span_table(h->lat, &h->near_e, &t);
+  if (h->near_e >= 60) return PP_ERR_UNSUPPORTED;   // (spans must stay inside the neighbouring 64-bit words)
+  PP_CUDA(cudaMalloc(&h->d_near_spans, sizeof(int16_t) * t.size()));
+  PP_CUDA(cudaMemcpy(h->d_near_spans, t.data(), sizeof(int16_t) * t.size(), cudaMemcpyHostToDevice));
   return PP_OK;
 }
 
@@ -323,6 +382,9 @@ int grid_build(pp_handle* h, const GridDev& g, const GridBank& b, const int8_t* 
   BuildArgs a;
   a.g = g; a.b = b; a.src = msg_src; a.src_stride = src_stride; a.rows = rows; a.rows_stride = rows_stride;
   a.xlo = h->d_box_tables; a.xhi = a.xlo + g.aabb_nx; a.ylo = a.xhi + g.aabb_nx; a.yhi = a.ylo + g.aabb_ny;
+  const int nrc = ensure_near_spans(h);
+  if (nrc) return nrc;
+  a.near_spans = h->d_near_spans; a.near_e = h->near_e;
   auto blocks = [&](int64_t work) { return dim3(static_cast<unsigned>(blocks_for(work, T, h->sm_count, n)), ny); };
   const int64_t cells = static_cast<int64_t>(g.W) * g.H;
   if (msg_src) {
@@ -338,9 +400,9 @@ int grid_build(pp_handle* h, const GridDev& g, const GridBank& b, const int8_t* 
   const size_t acoarse_n = n > 1 ? b.aabb_coarse * n : static_cast<size_t>(g.aabb_cnbx) * g.aabb_cwpr;
   PP_CUDA(cudaMemsetAsync(g.coarse, 0, sizeof(unsigned long long) * coarse_n, s));
   build_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.TJ), T, 0, s>>>(a);
-  dilate_coarse<<<blocks(static_cast<int64_t>(g.CI8) * g.CW8), T, 0, s>>>(a, (g.reach_cells + 7) / 8);
   PP_CUDA(cudaMemsetAsync(g.coarse4, 0, sizeof(unsigned long long) * coarse4_n, s));
   build_coarse4<<<blocks(static_cast<int64_t>(g.CI4) * g.TJ), T, 0, s>>>(a);
+  dilate_near4<<<blocks(static_cast<int64_t>(kNearBins) * g.CI4 * g.CW4), T, 0, s>>>(a);
   h->launches += 3;
   aabb_pass_y<<<blocks(static_cast<int64_t>(g.W) * g.aabb_ny), T, 0, s>>>(a);
   aabb_pass_x<<<blocks(static_cast<int64_t>(g.aabb_nx) * g.aabb_ny), T, 0, s>>>(a);
@@ -358,7 +420,8 @@ void grid_free(pp_handle* h) {
   grid_free_arrays(&h->bank_grid);
   cudaFree(h->bank_rows);
   cudaFree(h->d_box_tables);
-  h->bank_rows = nullptr; h->d_box_tables = nullptr;
+  cudaFree(h->d_near_spans);
+  h->bank_rows = nullptr; h->d_box_tables = nullptr; h->d_near_spans = nullptr;
   h->bank = GridBank{};
   h->has_grid = false;
 }
