@@ -331,11 +331,7 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
 #define PP_WIN_DEPTH 1
 #endif
 constexpr int kWinDepth = PP_WIN_DEPTH;           // windows staged ahead of the one being tested
-#ifndef PP_BLOCK_QUADS
-#define PP_BLOCK_QUADS 1
-#endif
-constexpr int kBlockQuads = PP_BLOCK_QUADS;       // groups of 4 consecutive poses per lane and ticket
-constexpr int kBlockPoses = 128 * kBlockQuads;    // poses per ticket
+constexpr int kBlockPoses = 128;                  // poses per ticket: 4 consecutive poses per lane
 constexpr int kQueueCap = 32 + kBlockPoses;       // phase 1 runs only while fewer than 32 survivors wait
 constexpr size_t kOrientedWarpBytes = sizeof(uint32_t) * (kWinDepth + 1) * kWinWords + sizeof(NarrowJob) * 32 +
                                       sizeof(uint32_t) * 32 + sizeof(uint32_t) * kQueueCap;
@@ -374,59 +370,44 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
       unsigned int blk = 0;
       if (lane == 0) blk = atomicAdd(ticket, 1u);
       blk = __shfl_sync(0xffffffffu, blk, 0);
+      const int64_t k0 = static_cast<int64_t>(blk) * kBlockPoses + 4 * lane;
       if (static_cast<int64_t>(blk) * kBlockPoses >= n) { more = false; break; }
-      // kBlockQuads groups of 4 consecutive poses per lane: all their loads are issued before the first test
-      float x[kBlockQuads][4], y[kBlockQuads][4], yaw[kBlockQuads][4];
+      float x[4], y[4], yaw[4];
+      if (vec && k0 + 3 < n) {
+        const float4* v = reinterpret_cast<const float4*>(poses + 3 * k0);
+        const float4 a = __ldg(v), b = __ldg(v + 1), c = __ldg(v + 2);
+        x[0] = a.x; y[0] = a.y; yaw[0] = a.z; x[1] = a.w; y[1] = b.x; yaw[1] = b.y;
+        x[2] = b.z; y[2] = b.w; yaw[2] = c.x; x[3] = c.y; y[3] = c.z; yaw[3] = c.w;
+        *reinterpret_cast<uint32_t*>(flags + k0) = 0u;
+      } else {
 #pragma unroll
-      for (int u = 0; u < kBlockQuads; ++u) {
-        const int64_t k0 = static_cast<int64_t>(blk) * kBlockPoses + u * 128 + 4 * lane;
-        if (vec && k0 + 3 < n) {
-          const float4* v = reinterpret_cast<const float4*>(poses + 3 * k0);
-          const float4 a = __ldg(v), b = __ldg(v + 1), c = __ldg(v + 2);
-          x[u][0] = a.x; y[u][0] = a.y; yaw[u][0] = a.z; x[u][1] = a.w; y[u][1] = b.x; yaw[u][1] = b.y;
-          x[u][2] = b.z; y[u][2] = b.w; yaw[u][2] = c.x; x[u][3] = c.y; y[u][3] = c.z; yaw[u][3] = c.w;
-          *reinterpret_cast<uint32_t*>(flags + k0) = 0u;
-        } else {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int64_t k = k0 + p;
-            x[u][p] = y[u][p] = yaw[u][p] = 0.0f;
-            if (k < n) { x[u][p] = poses[3 * k]; y[u][p] = poses[3 * k + 1]; yaw[u][p] = poses[3 * k + 2]; flags[k] = 0; }
-          }
+        for (int p = 0; p < 4; ++p) {
+          const int64_t k = k0 + p;
+          x[p] = y[p] = yaw[p] = 0.0f;
+          if (k < n) { x[p] = poses[3 * k]; y[p] = poses[3 * k + 1]; yaw[p] = poses[3 * k + 2]; flags[k] = 0; }
         }
       }
-      bool survive[kBlockQuads][4];
 #pragma unroll
-      for (int u = 0; u < kBlockQuads; ++u)
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int64_t k = static_cast<int64_t>(blk) * kBlockPoses + u * 128 + 4 * lane + p;
-          bool sv = k < n;
-          if (sv && broad_phase) {
-            const float cif = static_cast<float>(g.W / 2) - y[u][p] * inv_res_f;
-            const float cjf = static_cast<float>(g.H / 2) - x[u][p] * inv_res_f;
-            if (fabsf(cif) < 1.0e6f && fabsf(cjf) < 1.0e6f && fabsf(yaw[u][p]) < 100.0f) {   // (NaN / absurd poses take the exact path)
-              const int ic = __float2int_rd(cif), jc = __float2int_rd(cjf);
-              if (ic + reach < 0 || ic - reach >= g.W || jc + reach < 0 || jc - reach >= g.H) {
-                sv = false;                                  // the footprint cannot reach the grid
-              } else {
-                const int bin = __float2int_rd(yaw[u][p] * (kNearBins / 3.14159265f)) & (kNearBins - 1);
-                const int r4 = (ic + kHaloCells) >> 2, c4 = (jc + kHaloCells) >> 2;
-                sv = (__ldg(&g.near4[(static_cast<size_t>(bin) * g.CI4 + r4) * g.CW4 + (c4 >> 6)]) >> (c4 & 63)) & 1ull;
-              }
+      for (int p = 0; p < 4; ++p) {
+        bool survive = k0 + p < n;
+        if (survive && broad_phase) {
+          const float cif = static_cast<float>(g.W / 2) - y[p] * inv_res_f;
+          const float cjf = static_cast<float>(g.H / 2) - x[p] * inv_res_f;
+          if (fabsf(cif) < 1.0e6f && fabsf(cjf) < 1.0e6f && fabsf(yaw[p]) < 100.0f) {   // (NaN / absurd poses take the exact path)
+            const int ic = __float2int_rd(cif), jc = __float2int_rd(cjf);
+            if (ic + reach < 0 || ic - reach >= g.W || jc + reach < 0 || jc - reach >= g.H) {
+              survive = false;                               // the footprint cannot reach the grid
+            } else {
+              const int bin = __float2int_rd(yaw[p] * (kNearBins / 3.14159265f)) & (kNearBins - 1);
+              const int r4 = (ic + kHaloCells) >> 2, c4 = (jc + kHaloCells) >> 2;
+              survive = (__ldg(&g.near4[(static_cast<size_t>(bin) * g.CI4 + r4) * g.CW4 + (c4 >> 6)]) >> (c4 & 63)) & 1ull;
             }
           }
-          survive[u][p] = sv;
         }
-#pragma unroll
-      for (int u = 0; u < kBlockQuads; ++u)
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const uint32_t bal = __ballot_sync(0xffffffffu, survive[u][p]);
-          if (survive[u][p])
-            queue[nq + __popc(bal & lt)] = static_cast<uint32_t>(static_cast<int64_t>(blk) * kBlockPoses + u * 128 + 4 * lane + p);
-          nq += __popc(bal);
-        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, survive);
+        if (survive) queue[nq + __popc(bal & lt)] = static_cast<uint32_t>(k0 + p);
+        nq += __popc(bal);
+      }
     }
     if (nq == 0) break;
     __syncwarp();                                            // queue entries and the zeroed flags are in place

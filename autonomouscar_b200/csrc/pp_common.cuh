@@ -268,10 +268,6 @@ __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Ban
   const ulonglong2* map = reinterpret_cast<const ulonglong2*>(g.coarse4);
 #pragma unroll kCoarse4Unroll
   for (int r = r0; r <= r1; ++r) {
-    const ulonglong2* row = map + static_cast<size_t>(r) * g.CW4 + w0;
-    const ulonglong2 w = __ldg(row);
-    ulonglong2 w2 = make_ulonglong2(0ull, 0ull);
-    if (two) w2 = __ldg(row + 1);
     const float d = static_cast<float>(4 * r - kHaloCells - p.ai) - dbase;
     const float td = B.kT * d, sd = B.kS * d;
     const float lo = fmaxf(fmaxf(td + th0, sd + sh0), 0.0f), hi = fminf(fminf(td + th1, sd + sh1), jhi);
@@ -281,8 +277,11 @@ __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Ban
     const int ca = __float2int_rd(klo * 0.25f) + 1, cb = __float2int_rd(khi * 0.25f) - 1;
     const uint32_t hm = (lo <= hi) ? (((2u << b) - 1u) & (0xffffffffu << a)) : 0u;
     const uint32_t km = (klo <= khi && ca <= cb) ? (((2u << cb) - 1u) & (0xffffffffu << ca)) : 0u;
+    const ulonglong2* row = map + static_cast<size_t>(r) * g.CW4 + w0;
+    const ulonglong2 w = __ldg(row);
     unsigned long long bits = w.x >> sh, fb = w.y >> sh;
     if (two) {
+      const ulonglong2 w2 = __ldg(row + 1);
       bits |= w2.x << (64 - sh);
       fb |= w2.y << (64 - sh);
     }

@@ -250,10 +250,10 @@ def run_reference(args):
 
 
 # ncu --set full captures of this round's kernels at 2^22 poses (profiles/README.md): warp instructions and DRAM bytes per pose
-NCU_ORIENTED = {"warp_inst_per_pose": 172273538 / (1 << 22), "dram_bytes_per_pose": (51.099648e6 + 77.568e3) / (1 << 22),
-                "issue_active_pct_ncu": 68.4, "source": "profiles/r2_ncu_collide_oriented_v5.csv"}
-NCU_DIRECT = {"warp_inst_per_pose": 1435975323 / (1 << 22), "issue_active_pct_ncu": 86.1,
-              "source": "profiles/r2_ncu_collide_oriented_v5_direct.csv"}
+NCU_ORIENTED = {"warp_inst_per_pose": 76065443 / (1 << 22), "dram_bytes_per_pose": (53.518592e6 + 157.952e3) / (1 << 22),
+                "issue_active_pct_ncu": 63.5, "source": "profiles/r2_ncu_collide_oriented_v14.csv"}
+NCU_DIRECT = {"warp_inst_per_pose": 1404516194 / (1 << 22), "issue_active_pct_ncu": 85.1,
+              "source": "profiles/r2_ncu_collide_oriented_v12_direct.csv"}
 NCU_AABB = {"warp_inst_per_pose": 31759359 / (1 << 24), "dram_bytes_per_launch_2p24": 208.604416e6 + 13.38752e6,
             "source": "profiles/r2_ncu_collide_aabb_stream_v3.csv"}
 
