@@ -104,6 +104,7 @@ struct WS {
   int* heap_id_g;
   int* closed_list;           // slot id by closing order (m_tree_closed)
   int* rev_last;              // path extraction scratch
+  unsigned long long* cmin;   // fast frontier: bit pattern of the smallest cost in every chunk of 32 entries
 };
 
 __host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
@@ -113,6 +114,7 @@ __host__ __device__ inline size_t ws_bytes(int NC, int hash_size) {
   b += sizeof(unsigned long long) * hash_size;
   b += sizeof(double) * 2 * NC;       // global heap entries (16 B each); reused to stage the reversed path
   b += sizeof(int) * NC * 4;          // closed_seq, path scratch, closed_list, path scratch
+  b += sizeof(unsigned long long) * (NC / 32 + 2);   // chunk minima of the fast frontier
   return (b + 255) & ~size_t(255);
 }
 
@@ -128,6 +130,7 @@ __device__ __forceinline__ WS ws_view(unsigned char* base, int NC, int hash_size
   w.heap_id_g = w.closed_seq + NC;
   w.closed_list = w.heap_id_g + NC;
   w.rev_last = w.closed_list + NC;
+  w.cmin = reinterpret_cast<unsigned long long*>(w.rev_last + NC);
   return w;
 }
 
@@ -335,11 +338,6 @@ struct Shared {
   int top_pos, top_id;
   int fx_len, fx_bad;   // pointer-walk extraction: path length, 1 = cannot be used
   int fx_slow;          // diagnostics: this query's path was extracted by the exact scan walk
-  // fast frontier: the runner-up found by an argmin pass serves the NEXT pop when no push happens in
-  // between (planPath pops twice in a row: LP:80, then LP:40 of the next iteration)
-  int next_valid, next_pos;
-  int chk_valid;            // a runner-up was popped from the cache; its cost must be shown unique by the next pass
-  double next_cost, chk_cost;
   long long pool_off;
   double goal_node[6];  // child.x child.y parent.x parent.y heading velocity of the terminal node
   double scratch_key[6];  // key broadcast for the exact-scan fallback
@@ -394,77 +392,59 @@ __device__ __forceinline__ void hash_insert(const WS& w, int hash_size, unsigned
 // keeps the frontier as an unordered array (pushes are plain parallel appends) and pops by a
 // block-wide argmin; if any pop ever sees its minimum cost on two entries the query is
 // re-run from scratch with the exact libstdc++ heap, so results are always the reference's.
+//
+// Two levels keep the argmin short: w.cmin[k] holds the smallest cost among entries 32 k .. 32 k + 31 (as the bit
+// pattern of the double: costs are non-negative, so the patterns order like the values).  A push is an atomicMin
+// on its chunk's word; a removal (the last entry moves into the hole) recomputes the two chunks it touches.  A pop
+// reads the chunk minima (n / 32 words, one or two per thread), then one warp reads the 32 entries of the winning
+// chunk.  The minimum is tied exactly when two chunk minima equal it or two entries of that chunk do.
+// (Before: one pass over all n entries per expansion that also found the runner-up for the next pop -- 24 % of the
+// kernel's cycles; with the chunk minima in shared memory and cached in registers the 64-register build spilled
+// and lost what the shorter pass had won.)
 // ---------------------------------------------------------------------------------------
-// One pass finds the cheapest entry AND the runner-up (c2 == c1 exactly when the minimum is tied).
-// If the previous pop came out of the runner-up cache, the pass also looks for entries that share
-// that pop's cost (`chk`): such an entry means the cached pop was tied (or a child pushed since has
-// the same cost -- a false alarm that only costs the exact re-run).
-__device__ __forceinline__ void top2_insert(double& c1, int& p1, double& c2, int& p2, double c, int p) {
-  if (p < 0) return;
-  if (p1 < 0 || c < c1) { c2 = c1; p2 = p1; c1 = c; p1 = p; }
-  else if (p2 < 0 || c < c2) { c2 = c; p2 = p; }
-}
+constexpr unsigned long long kCostInf = 0x7FF0000000000000ull;
+__device__ __forceinline__ unsigned long long cost_bits(double c) { return static_cast<unsigned long long>(__double_as_longlong(c)); }
+
 template <bool kAllSmem>
-__device__ __forceinline__ void fast_find_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt) {
-  const int n = S->heap_size;
-  const bool chk_on = S->chk_valid != 0;
-  const double chk = S->chk_cost;
-  double c1 = 0, c2 = 0;
-  int p1 = -1, p2 = -1, tie = 0;
-  for (int k = threadIdx.x; k < n; k += kT) {
-    const double c = hget<kAllSmem>(h, k).cost;
-    if (chk_on && c == chk) tie = 1;
-    top2_insert(c1, p1, c2, p2, c, k);
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double oc1 = __shfl_xor_sync(0xffffffffu, c1, off), oc2 = __shfl_xor_sync(0xffffffffu, c2, off);
-    const int op1 = __shfl_xor_sync(0xffffffffu, p1, off), op2 = __shfl_xor_sync(0xffffffffu, p2, off);
-    top2_insert(c1, p1, c2, p2, oc1, op1);
-    top2_insert(c1, p1, c2, p2, oc2, op2);
-  }
+__device__ __forceinline__ void fast_find_top(const Heap& h, const WS& w, Shared* S, unsigned long long* s_min) {
+  const int n = S->heap_size, nch = (n + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-    s_cost[2 * warp] = c1; s_pos[2 * warp] = p1;
-    s_cost[2 * warp + 1] = c2; s_pos[2 * warp + 1] = p2;
+  unsigned long long best = ~0ull;
+  for (int k = threadIdx.x; k < nch; k += kT) best = min(best, w.cmin[k]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if (lane == 0) s_min[warp] = best;
+  __syncthreads();
+  unsigned long long gmin = s_min[0];
+#pragma unroll
+  for (int ww = 1; ww < kWarps; ++ww) gmin = min(gmin, s_min[ww]);
+  int cnt = 0, mine = -1;
+  for (int k = threadIdx.x; k < nch; k += kT)
+    if (w.cmin[k] == gmin) { cnt++; mine = k; }
+  if (cnt > 0) S->top_pos = mine;                       // (the chunk for now; any one of them if several: a tie anyway)
+  if (cnt > 1) S->tie_seen = 1;
+  const int holders = __syncthreads_count(cnt > 0);     // (also orders the writes above before the reads below)
+  if (warp == 0) {
+    const int k = S->top_pos, idx = 32 * k + lane;
+    HeapEnt e;
+    e.cost = 0.0; e.id = -1; e.pad = 0;
+    if (idx < n) e = hget<kAllSmem>(h, idx);
+    const unsigned bal = __ballot_sync(0xffffffffu, idx < n && cost_bits(e.cost) == gmin);
+    __syncwarp();
+    if (lane == __ffs(bal) - 1) {
+      S->top_pos = idx;
+      S->top_id = e.id;
+      if (__popc(bal) > 1 || holders > 1) S->tie_seen = 1;
+    }
   }
-  const int any_tie = __syncthreads_or(tie);
-  if (threadIdx.x == 0) {
-    double r1 = 0, r2 = 0;
-    int q1 = -1, q2 = -1;
-    for (int w = 0; w < 2 * kWarps; ++w) top2_insert(r1, q1, r2, q2, s_cost[w], s_pos[w]);
-    S->top_pos = q1;
-    S->top_id = hget<kAllSmem>(h, q1).id;
-    if ((q2 >= 0 && r2 == r1) || any_tie) S->tie_seen = 1;
-    S->next_valid = q2 >= 0 ? 1 : 0;
-    S->next_pos = q2;
-    S->next_cost = r2;
-    S->chk_valid = 0;
-  }
-  (void)s_cnt;
   __syncthreads();
 }
 
 // frontier.top(): slot id of the cheapest entry (block-wide; all threads get the same value)
-// `use_cached`: the previous pop was the last frontier operation (no push since), so the
-// runner-up it found is the minimum now.
 template <bool kAllSmem>
-__device__ __forceinline__ int frontier_top(const Heap& h, Shared* S, double* s_cost, int* s_pos, int* s_cnt,
-                                            bool use_cached) {
+__device__ __forceinline__ int frontier_top(const Heap& h, const WS& w, Shared* S, unsigned long long* s_min) {
   if (S->fast) {
-    if (use_cached && S->next_valid) {
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        S->top_pos = S->next_pos;
-        S->top_id = hget<kAllSmem>(h, S->next_pos).id;
-        S->chk_valid = 1;                // uniqueness of this cost is established by the next pass
-        S->chk_cost = S->next_cost;
-        S->next_valid = 0;
-      }
-      __syncthreads();
-    } else {
-      fast_find_top<kAllSmem>(h, S, s_cost, s_pos, s_cnt);
-    }
+    fast_find_top<kAllSmem>(h, w, S, s_min);
     return S->top_id;
   }
   return h.s[0].id;
@@ -491,11 +471,12 @@ __device__ __forceinline__ void open_single_warp0(const WS& w, const Heap& heap,
       HeapEnt e;
       e.cost = cost; e.id = id; e.pad = 0;
       hset<kAllSmem>(heap, hsize, e);
+      atomicMin(&w.cmin[hsize >> 5], cost_bits(cost));
     }
   }
   __syncwarp();
   if (!fast) heap_sift_up_warp<kAllSmem>(heap, hsize, cost, id, lane);
-  if (lane == 0) { S->n_nodes = id + 1; S->heap_size = hsize + 1; S->next_valid = 0; }
+  if (lane == 0) { S->n_nodes = id + 1; S->heap_size = hsize + 1; }
   __syncwarp();
 }
 
@@ -522,12 +503,23 @@ __device__ __forceinline__ int close_top(const WS& w, const Heap& heap, Shared* 
       S->n_closed = S->n_closed + 1;
     }
     if (fast) {
-      if (threadIdx.x == 0) {   // remove by moving the last entry into the hole
-        const int pos = S->top_pos;
-        if (pos != hsize - 1) hset<kAllSmem>(heap, pos, hget<kAllSmem>(heap, hsize - 1));
-        if (S->next_valid && S->next_pos == hsize - 1) S->next_pos = pos;   // the runner-up was that last entry
-        S->heap_size = hsize - 1;
+      // remove by moving the last entry into the hole, then recompute the minima of the (up to) two chunks touched
+      const int pos = S->top_pos, last = hsize - 1, lane = threadIdx.x;
+      __syncwarp();
+      if (lane == 0 && pos != last) hset<kAllSmem>(heap, pos, hget<kAllSmem>(heap, last));
+      __syncwarp();
+      const int ka = pos >> 5, kb = last >> 5;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int k = pass == 0 ? ka : kb;
+        if (pass == 1 && kb == ka) break;
+        const int idx = 32 * k + lane;
+        unsigned long long v = kCostInf;
+        if (idx < last) v = cost_bits(hget<kAllSmem>(heap, idx).cost);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) w.cmin[k] = v;
       }
+      if (lane == 0) S->heap_size = last;
     } else {
       const int nsize = heap_pop_warp<kAllSmem>(heap, hsize, threadIdx.x);
       if (threadIdx.x == 0) S->heap_size = nsize;
@@ -554,8 +546,8 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
   __shared__ int s_red[kWarpsMax];
   __shared__ int s_scan[kWarpsMax];
   __shared__ unsigned long long s_dig[kWarpsMax];
-  __shared__ double s_fcost[2 * kWarpsMax];
-  __shared__ int s_fpos[2 * kWarpsMax], s_fcnt[2 * kWarpsMax];
+  __shared__ unsigned long long s_fmin[kWarpsMax];
+  __shared__ int s_fpos[kWarpsMax];
   // pointer-walk extraction: direct-mapped table over the path poses' point hashes.  Entry = pose index + 1,
   // 0 = no pose hashes here, kFxShared = more than one does (those few slots fall back to a scan of the path)
   __shared__ unsigned short s_ptab[kFxTable];
@@ -595,6 +587,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
     {
       ulonglong2* hz = reinterpret_cast<ulonglong2*>(w.hash);
       for (int k = tid; k < A.hash_init / 2; k += kT) hz[k] = make_ulonglong2(0ull, 0ull);
+      for (int k = tid; k < NC / 32 + 2; k += kT) w.cmin[k] = kCostInf;
     }
     if (tid == 0) {
       S.n_nodes = 0; S.n_closed = 0; S.heap_size = 0; S.n_exp = 0; S.status = -1; S.dup_seen = 0;
@@ -602,7 +595,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       S.fast = (attempt == 0 && A.fast_frontier) ? 1 : 0;
       S.hash_cur = A.hash_init;
       S.fx_slow = 0;
-      S.tie_seen = 0; S.top_pos = 0; S.top_id = 0; S.next_valid = 0; S.next_pos = 0; S.chk_valid = 0; S.next_cost = 0; S.chk_cost = 0;
+      S.tie_seen = 0; S.top_pos = 0; S.top_id = 0;
       for (int c = 0; c < 8; ++c) S.cyc[c] = 0;
       if (kBanked) S.gq = grid_at(A.g, A.bank, qq.reserved);
     }
@@ -635,7 +628,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         __syncthreads();
       }
       const int hash_cur = S.hash_cur;
-      const int top_id = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt, true);   // LP:40 (runner-up of LP:80's pass)
+      const int top_id = frontier_top<kAllSmem>(heap, w, &S, s_fmin);   // LP:40
       // current_node's fields are key fields, identical for every copy of the node
       const double ncx = w.cx[top_id], ncy = w.cy[top_id], npx = w.px[top_id], npy = w.py[top_id];
       const double nhd = w.hd[top_id], nvel = w.vel[top_id];
@@ -818,19 +811,13 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
             HeapEnt e;
             e.cost = cost; e.id = id; e.pad = 0;
             hset<kAllSmem>(heap, hs_base + rank, e);
+            atomicMin(&w.cmin[(hs_base + rank) >> 5], cost_bits(cost));
           }
         }
         appended += total;
         __syncthreads();
       }
       if (goal_stop) {
-        if (S.fast && S.chk_valid) {      // the pop that led here came from the runner-up cache: show it was unique
-          const double chk = S.chk_cost;
-          int tie = 0;
-          for (int k2 = tid; k2 < S.heap_size; k2 += kT) tie |= hget<kAllSmem>(heap, k2).cost == chk ? 1 : 0;
-          if (__syncthreads_or(tie) && tid == 0) S.tie_seen = 1;
-          __syncthreads();
-        }
         if (warp == 0) {
           double k[6];
           for (int c = 0; c < 6; ++c) k[c] = S.goal_node[c];
@@ -861,7 +848,6 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         }
         if (lane == 0) {
           S.heap_size = hsize;
-          if (appended > 0) S.next_valid = 0;
           S.n_nodes = base_nodes + appended;
           S.n_cand_total += n_cand;
           S.n_coll_total += collided_local;
@@ -871,7 +857,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
       PP_TICK(4);
       if (S.heap_size == 0) { if (tid == 0) S.status = PP_PLAN_EXHAUSTED; break; }
       {
-        const int top2 = frontier_top<kAllSmem>(heap, &S, s_fcost, s_fpos, s_fcnt, false);
+        const int top2 = frontier_top<kAllSmem>(heap, w, &S, s_fmin);
         __syncthreads();
         close_top<kAllSmem>(w, heap, &S, top2, s_red);                                          // LP:80
       }
