@@ -507,12 +507,12 @@ collide_edges_warp_kernel(GridDev g, CollideParams cp, const float* __restrict__
       if (steps < 1) steps = 1;
       for (int base = 0; base < steps && !hit; base += 32) {
         const int k = base + lane + 1;
-        int need = 0;
+        bool need = false;
         NarrowJob job;
         if (k <= steps) {
           const double t = dm::div(static_cast<double>(k), static_cast<double>(steps));
           const PoseFx pf = pose_to_fixed(cp.lat, g.W, g.H, g.res, dm::add(x0, dm::mul(t, dx)), dm::add(y0, dm::mul(t, dy)), yaw);
-          need = make_job(g, cp.lat, pf, 1, &job);
+          need = make_job_light(g, cp.lat, pf, &job);
         }
         hit = warp_collide_jobs(g, cp.lat, job, need, s_win[wib], lane);
       }

@@ -240,6 +240,9 @@ __device__ __forceinline__ Bands footprint_bands(const Lattice& l, const PoseFx&
 // Both verdicts are proofs; every undecided pose takes the exact test.
 // *tile_rows gets bit a set when tile row (first tile row under the box) + a holds an obstacle inside the box's
 // columns: the narrow phase loads only those rows of its window.
+// kUnroll: 1 where many warps hide the latency of a strip's load (the batch kernel: the trip counts differ per lane
+// and unrolled copies cost more than they hide), 4 where a few warps wait for one pose (edges of the sampling planner).
+template <int kUnroll>
 __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Bands& B, const PoseFx& p, int i0,
                                                      int i1, int j0, int j1, uint32_t* tile_rows) {
   const int r0 = (i0 + kHaloCells) >> 2, r1 = (i1 + kHaloCells) >> 2;
@@ -266,7 +269,7 @@ __device__ __forceinline__ int coarse4_oriented_test(const GridDev& g, const Ban
   // straight-line body (no data-dependent branch): the loads of successive rows overlap.  One 128-bit load brings
   // the "any" and the "full" word of a row (they are interleaved in memory).
   const ulonglong2* map = reinterpret_cast<const ulonglong2*>(g.coarse4);
-#pragma unroll kCoarse4Unroll
+#pragma unroll kUnroll
   for (int r = r0; r <= r1; ++r) {
     const float d = static_cast<float>(4 * r - kHaloCells - p.ai) - dbase;
     const float td = B.kT * d, sd = B.kS * d;

@@ -219,14 +219,14 @@ __device__ __forceinline__ bool edge_part_hit(const RrtArgs& A, const Steer& S, 
   bool hit = false;
   for (int base = k_lo; base < k_hi && !hit; base += 32) {
     const int k = base + lane + 1;
-    int need = 0;
+    bool need = false;
     NarrowJob job;
     if (k <= k_hi) {
       const double tt = dm::div(static_cast<double>(k), static_cast<double>(S.n));
       const double ex = dm::add(S.px, dm::mul(tt, S.dx)), ey = dm::add(S.py, dm::mul(tt, S.dy));
       if (A.cp.mode == PP_COLLISION_ORIENTED) {
         const PoseFx pf = pose_to_fixed(A.cp.lat, A.g.W, A.g.H, A.g.res, ex, ey, S.yaw);
-        need = make_job(A.g, A.cp.lat, pf, 1, &job);
+        need = make_job_light(A.g, A.cp.lat, pf, &job);
       } else if (A.cp.mode == PP_COLLISION_REF_AABB) {
         hit = aabb_hit(A.g, ex, ey);
       }
