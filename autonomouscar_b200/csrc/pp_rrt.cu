@@ -385,6 +385,7 @@ struct RrtPersist {
   float4* sorted;        // [NC]  (x, y, id as bits, 0) grouped by cell
   int* goal_id;          // atomicMin of the node ids inside the goal box (INT_MAX = none)
   unsigned* barrier;     // monotonic arrival counter of the grid barrier
+  unsigned* tickets;     // [2] sample tickets of phase A, one counter per round parity (the other one is being reset)
   float x_lo, y_lo, cell_x, cell_y, inv_cell_x, inv_cell_y;
   long long* cycles;     // PP_RRT_TIMING: SM cycles of CTA 0 per phase (nearest, edge, barrier 1, append, barrier 2, regroup), else null
 };
@@ -473,15 +474,17 @@ __global__ void __launch_bounds__(kT) rrt_persistent(RrtArgs A, RrtPersist G) {
   __shared__ int s_ncells;
   __shared__ float s_ax[kGridSide], s_ay[kGridSide];       // per-axis box distances of the current sample
   __shared__ unsigned short s_work[kWorkCap];
-  __shared__ int s_nwork, s_hit, s_scan[kT / 32];
+  __shared__ int s_nwork, s_hit, s_scan[kT / 32], s_next[2], s_mine[kT];
   __shared__ unsigned s_gen;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pp_query qq = A.queries[0];
   if (tid == 0) s_gen = 0;
   // replicated round state (identical in every CTA)
   int n_nodes = 1, n_samples = 0, n_rounds = 0, n_coll = 0, n_sorted = 0, goal_id = -1;
-  if (blockIdx.x == 0 && tid == 0)                       // node 0 (written by rrt_init) joins its bucket
+  if (blockIdx.x == 0 && tid == 0) {                     // node 0 (written by rrt_init) joins its bucket
     atomicAdd(&G.cell_count[grid_cell_of(G, static_cast<float>(qq.start_x), static_cast<float>(qq.start_y))], 1);
+    G.tickets[0] = gridDim.x; G.tickets[1] = gridDim.x;  // every CTA's first sample of a round is its own index
+  }
   grid_barrier(G.barrier, &s_gen);
   const int max_samples = A.P.rrt_max_samples, max_nodes = A.P.max_nodes;
 
@@ -491,7 +494,14 @@ __global__ void __launch_bounds__(kT) rrt_persistent(RrtArgs A, RrtPersist G) {
   while (goal_id < 0 && n_samples < max_samples && n_nodes < max_nodes) {
     const int k_round = min(A.K, max_samples - n_samples);
     // ---- phase A ---------------------------------------------------------------------------------------
-    for (int t = blockIdx.x; t < k_round; t += gridDim.x) {
+    // Samples are handed out by ticket (the searches differ in length: with a fixed share per CTA a third of the
+    // round was spent waiting at the barrier below).  The next ticket is requested before the work on the current
+    // sample starts, so the atomic's round trip is never waited for.
+    if (blockIdx.x == 0 && tid == 0) G.tickets[(n_rounds + 1) & 1] = gridDim.x;   // next round's counter: idle now
+    unsigned* ticket = &G.tickets[n_rounds & 1];
+    int it = 0;
+    for (int t = blockIdx.x; t < k_round; ++it) {
+      if (tid == 0) s_next[it & 1] = static_cast<int>(atomicAdd(ticket, 1u));
       const long long t_round = G.cycles ? clock64() : 0;
       float sx, sy;
       draw_sample(A, qq, static_cast<long long>(n_samples) + t, &sx, &sy);
@@ -599,35 +609,45 @@ __global__ void __launch_bounds__(kT) rrt_persistent(RrtArgs A, RrtPersist G) {
       RRT_TICK(1);
       if (G.cycles && tid == 0 && n_rounds < 4096)
         atomicMax(reinterpret_cast<unsigned long long*>(&G.cycles[17 + 2 * n_rounds]), static_cast<unsigned long long>(clock64() - t_near_end));
+      t = s_next[it & 1];                                  // (written before this iteration's barriers, rewritten two iterations on)
     }
     grid_barrier(G.barrier, &s_gen);
     RRT_TICK(2);
     // ---- phase B: order-preserving append ---------------------------------------------------------------
+    // every CTA ranks all candidates of the round (one ballot scan per kT of them); the nodes a CTA appends are
+    // those whose sample index is congruent to its own, one thread per node
     int appended = 0, coll = 0;
     for (int base = 0; base < k_round; base += kT) {
       const int u = base + tid;
       const int v = u < k_round ? __ldcg(&A.cand_valid[u]) : 0;
-      appended += __syncthreads_count(v == 1);
-      coll += __syncthreads_count(v == 2);
+      const unsigned bal = __ballot_sync(0xffffffffu, v == 1);
+      if (lane == 0) s_scan[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int ww = 0; ww < kT / 32; ++ww) {
+        const int c = s_scan[ww];
+        if (ww < warp) before += c;
+        total += c;
+      }
+      if (u < k_round && u % static_cast<int>(gridDim.x) == static_cast<int>(blockIdx.x))
+        s_mine[u / gridDim.x] = v == 1 ? appended + before + __popc(bal & ((1u << lane) - 1u)) : -1;
+      appended += total;
+      coll += __syncthreads_count(v == 2);                 // (also: s_scan is free again, s_mine is written)
     }
-    for (int t = blockIdx.x; t < k_round; t += gridDim.x) {
-      int rank = 0;
-      for (int base = 0; base < t; base += kT) {
-        const int u = base + tid;
-        rank += __syncthreads_count(u < t && __ldcg(&A.cand_valid[u]) == 1);
-      }
-      if (tid == 0 && __ldcg(&A.cand_valid[t]) == 1) {
-        const int id = n_nodes + rank;
-        const double* c = A.cand + static_cast<size_t>(t) * 5;
-        const double x = __ldcg(&c[0]), y = __ldcg(&c[1]);
-        A.nx[id] = x; A.ny[id] = y; A.nhd[id] = __ldcg(&c[2]); A.nvel[id] = __ldcg(&c[3]); A.nstep[id] = __ldcg(&c[4]);
-        A.nparent[id] = __ldcg(&A.cand_near[t]);
-        const float2 xy = make_float2(static_cast<float>(x), static_cast<float>(y));
-        A.nxy[id] = xy;
-        atomicAdd(&G.cell_count[grid_cell_of(G, xy.x, xy.y)], 1);
-        if (fabs(dm::sub(x, qq.goal_x)) <= A.P.rrt_goal_tolerance && fabs(dm::sub(y, qq.goal_y)) <= A.P.rrt_goal_tolerance)
-          atomicMin(G.goal_id, id);       // the first appended node (lowest sample index) in the goal box
-      }
+    const int n_mine = blockIdx.x < static_cast<unsigned>(k_round) ? (k_round - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    if (tid < n_mine && s_mine[tid] >= 0) {
+      const int t = blockIdx.x + tid * gridDim.x;
+      const int id = n_nodes + s_mine[tid];
+      const double* c = A.cand + static_cast<size_t>(t) * 5;
+      const double x = __ldcg(&c[0]), y = __ldcg(&c[1]);
+      A.nx[id] = x; A.ny[id] = y; A.nhd[id] = __ldcg(&c[2]); A.nvel[id] = __ldcg(&c[3]); A.nstep[id] = __ldcg(&c[4]);
+      A.nparent[id] = __ldcg(&A.cand_near[t]);
+      const float2 xy = make_float2(static_cast<float>(x), static_cast<float>(y));
+      A.nxy[id] = xy;
+      atomicAdd(&G.cell_count[grid_cell_of(G, xy.x, xy.y)], 1);
+      if (fabs(dm::sub(x, qq.goal_x)) <= A.P.rrt_goal_tolerance && fabs(dm::sub(y, qq.goal_y)) <= A.P.rrt_goal_tolerance)
+        atomicMin(G.goal_id, id);         // the first appended node (lowest sample index) in the goal box
     }
     RRT_TICK(3);
     grid_barrier(G.barrier, &s_gen);
@@ -929,6 +949,7 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
       G.sorted = reinterpret_cast<float4*>(gp);             gp += al(sizeof(float4) * per_q);
       G.goal_id = reinterpret_cast<int*>(gp);
       G.barrier = reinterpret_cast<unsigned*>(gp + 64);
+      G.tickets = reinterpret_cast<unsigned*>(gp + 96);
       static const bool timing = getenv("PP_RRT_TIMING") != nullptr;
       G.cycles = timing ? reinterpret_cast<long long*>(gp + 128) : nullptr;
       if (timing) PP_CUDA(cudaMemsetAsync(gp + 128, 0, (16 + 2 * 4096) * sizeof(long long), s));
@@ -941,7 +962,8 @@ int rrt_plan_batch(pp_handle* h, int n, const pp_query* qs, pp_result* rs) {
       PP_CUDA(cudaMemcpyAsync(G.goal_id, &no_goal, sizeof(int), cudaMemcpyHostToDevice, s));
       PP_CUDA(cudaMemsetAsync(G.barrier, 0, 4, s));
       const int capacity = per_sm * h->sm_count;
-      const int grid = std::max(1, std::min(K, capacity));
+      static const int cta_cap = getenv("PP_RRT_CTAS") ? atoi(getenv("PP_RRT_CTAS")) : 0;   // (experiments: fewer CTAs, more tickets each)
+      const int grid = std::max(1, std::min(std::min(K, capacity), cta_cap > 0 ? cta_cap : capacity));
       void* kargs[2] = {&A, &G};
       PP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rrt_persistent), dim3(grid), dim3(kT), kargs, dyn_smem, s));
       h->launches++;

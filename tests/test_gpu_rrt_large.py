@@ -119,3 +119,37 @@ def test_config4_full_sample_budget_digest_equals_the_oracle(oracle, cuda_device
     assert ref.status == PP_PLAN_CAP and ref.n_candidates == 1 << 20 and ref.n_nodes > 900000
     assert got.summary() == ref.summary()
     pl.close()
+
+
+_TICKET_SCRIPT = r"""
+import sys
+from autonomouscar_b200 import PP_COLLISION_ORIENTED, Planner, default_params, make_query, worlds
+N = 2048
+p = default_params(costmap_res=0.1, costmap_width=N, costmap_height=N, collision_mode=PP_COLLISION_ORIENTED,
+                   time_step_ms=1000.0, rrt_samples_per_round=256, rrt_max_samples=40000, max_nodes=40001,
+                   rrt_goal_tolerance=0.0)
+g = worlds.block_grid(N, N, frac=0.01, block=16, seed=4, noise=False)
+half = N * 0.1 / 2
+worlds.clear_disc(g, p, -half + 10.0, -half + 10.0, 6.0)
+pl = Planner(p, device=0)
+pl.set_grid(g)
+r = pl.rrt_plan(make_query(half - 10.0, half - 10.0, start_x=-half + 10.0, start_y=-half + 10.0, start_heading=0.785,
+                           start_speed=1.0, seed=7), cap_nodes=8, cap_path=64, want_nodes=False)
+print("DIGEST", r.n_nodes, r.n_candidates, r.n_collisions, r.tree_digest)
+"""
+
+
+def test_sample_tickets_do_not_change_the_tree(cuda_device):
+    """The cooperative kernel hands samples to CTAs by ticket: the tree must not depend on how many CTAs there are
+    (PP_RRT_CTAS is read once per process, hence the child processes) nor on the kernel arrangement."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env_extra in ({}, {"PP_RRT_CTAS": "5"}, {"PP_RRT_CTAS": "37"}, {"PP_RRT_PER_ROUND_KERNELS": "1"}):
+        env = dict(os.environ, PYTHONPATH=root, **env_extra)
+        out = subprocess.run([sys.executable, "-c", _TICKET_SCRIPT], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append([ln for ln in out.stdout.splitlines() if ln.startswith("DIGEST")][-1])
+    assert outs[0].split()[1] != "1" and len(set(outs)) == 1, outs
