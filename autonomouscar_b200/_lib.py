@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libprius_planner_b200.so")
 EXPORTS = [
     "pp_default_params", "pp_abi_version", "pp_last_error", "pp_create", "pp_destroy", "pp_get_params",
     "pp_set_collision_mode", "pp_set_grid", "pp_set_grid_dev", "pp_get_cspace", "pp_collide_batch",
-    "pp_collide_batch_dev", "pp_collide_edges_dev", "pp_footprint_points", "pp_sample_poses_dev",
+    "pp_collide_batch_dev", "pp_collide_batch_bits_dev", "pp_collide_edges_dev", "pp_footprint_points", "pp_sample_poses_dev",
     "pp_philox4x32_10", "pp_nearest_dev", "pp_find_exact_dev", "pp_plan", "pp_plan_batch", "pp_rrt_plan",
     "pp_rrt_plan_batch", "pp_get_visited", "pp_sync", "pp_stream", "pp_launch_count", "pp_last_phase_ms",
     "pp_last_narrow_count", "pp_bench_l2_gather", "pp_set_broad_phase", "pp_group_create", "pp_group_destroy", "pp_group_size",
@@ -63,6 +63,7 @@ def load():
     L.pp_get_cspace.argtypes = [vp, vp, C.c_size_t]
     L.pp_collide_batch.argtypes = [vp, i64, vp, vp]
     L.pp_collide_batch_dev.argtypes = [vp, i64, vp, vp]
+    L.pp_collide_batch_bits_dev.argtypes = [vp, i64, vp, vp]
     L.pp_collide_batch_q16.argtypes = [vp, i64, vp, vp, vp]
     L.pp_collide_edges_dev.argtypes = [vp, i64, vp, vp]
     L.pp_pack_flags_dev.argtypes = [vp, i64, vp, vp]

@@ -232,6 +232,20 @@ int pp_collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_
   return collide_batch_dev(h, n, poses_dev, out_flags_dev);
 }
 
+int pp_collide_batch_bits_dev(pp_handle* h, int64_t n, const float* poses_dev, uint32_t* out_bits_dev) {
+  int rc = require_grid(h, "pp_collide_batch_bits_dev");
+  if (rc) return rc;
+  PP_REQUIRE(n >= 0 && (n == 0 || (poses_dev && out_bits_dev)), "pp_collide_batch_bits_dev: bad arguments");
+  PP_CUDA(cudaSetDevice(h->device));
+  if (h->P.collision_mode == PP_COLLISION_ORIENTED)     // the kernel writes the bits itself
+    return collide_batch_dev(h, n, poses_dev, reinterpret_cast<uint8_t*>(out_bits_dev), true);
+  rc = ensure_stage(h, n);                              // the other modes: byte flags into the staging buffer, then packed
+  if (rc) return rc;
+  rc = collide_batch_dev(h, n, poses_dev, h->d_flags);
+  if (rc) return rc;
+  return pack_flags_dev(h, n, h->d_flags, out_bits_dev);
+}
+
 // Host-pointer entry points: H2D, kernels and D2H pipelined in chunks on three streams so the PCIe copies overlap
 // the kernels.  `poses_host` (float32 triples) or `q16_host` (int16 triples + `quant`, dequantised on the device).
 static int collide_batch_host(pp_handle* h, int64_t n, const float* poses_host, const int16_t* q16_host,

@@ -344,10 +344,14 @@ constexpr size_t kOrientedSmem = kOrientedWarpBytes * kWarpsPerBlock;
 #ifndef PP_COLLIDE_MIN_BLOCKS
 #define PP_COLLIDE_MIN_BLOCKS 3
 #endif
-template <int NU, int NV, int S>
+// kBits: the output is ONE BIT per pose (bit b of word k = pose 32 k + b, what pp_pack_flags_dev makes of the byte
+// flags): `flags` then points at ceil(n / 32) words.  Phase 1 zeroes the four words of its block, colliding poses
+// OR their bit in.  For results that leave the device (the N > 1 gather) this saves the byte array and the pack pass.
+template <int NU, int NV, int S, bool kBits>
 __global__ void __launch_bounds__(kThreads, PP_COLLIDE_MIN_BLOCKS)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
                         int64_t n, int broad_phase, unsigned long long* __restrict__ counters) {
+  uint32_t* bits = reinterpret_cast<uint32_t*>(flags);
   // every warp's own slice of (dynamic) shared memory: ring of windows, jobs, their pose indices, survivor queue
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -378,14 +382,18 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
         const float4 a = __ldg(v), b = __ldg(v + 1), c = __ldg(v + 2);
         x[0] = a.x; y[0] = a.y; yaw[0] = a.z; x[1] = a.w; y[1] = b.x; yaw[1] = b.y;
         x[2] = b.z; y[2] = b.w; yaw[2] = c.x; x[3] = c.y; y[3] = c.z; yaw[3] = c.w;
-        *reinterpret_cast<uint32_t*>(flags + k0) = 0u;
+        if (!kBits) *reinterpret_cast<uint32_t*>(flags + k0) = 0u;
       } else {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const int64_t k = k0 + p;
           x[p] = y[p] = yaw[p] = 0.0f;
-          if (k < n) { x[p] = poses[3 * k]; y[p] = poses[3 * k + 1]; yaw[p] = poses[3 * k + 2]; flags[k] = 0; }
+          if (k < n) { x[p] = poses[3 * k]; y[p] = poses[3 * k + 1]; yaw[p] = poses[3 * k + 2]; if (!kBits) flags[k] = 0; }
         }
+      }
+      if (kBits && lane < kBlockPoses / 32) {
+        const int64_t wd = static_cast<int64_t>(blk) * (kBlockPoses / 32) + lane;
+        if (wd * 32 < n) bits[wd] = 0u;
       }
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -424,7 +432,10 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
       const PoseFx fx = pose_to_fixed(lat, g.W, g.H, g.res, static_cast<double>(px), static_cast<double>(py),
                                       static_cast<double>(pyaw));
       verdict = make_job(g, lat, fx, broad_phase, &job);
-      if (verdict == 2) flags[k] = 1;                        // decided by the coarse maps
+      if (verdict == 2) {                                    // decided by the coarse maps
+        if (kBits) atomicOr(&bits[k >> 5], 1u << (k & 31u));
+        else flags[k] = 1;
+      }
     }
     const uint32_t jbal = __ballot_sync(0xffffffffu, verdict == 1);
     if (verdict == 1) {
@@ -458,7 +469,11 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
       __syncwarp();                                          // (this window is refilled by the copy issued next)
       if (lane == j) mine = hit;
     }
-    if (lane < nj && mine) flags[s_job_k[lane]] = 1;
+    if (lane < nj && mine) {
+      const uint32_t k = s_job_k[lane];
+      if (kBits) atomicOr(&bits[k >> 5], 1u << (k & 31u));
+      else flags[k] = 1;
+    }
     __syncwarp();                                            // s_jobs / s_job_k are rewritten by the next pass
   }
   if (lane == 0 && local_narrow) atomicAdd(counters, local_narrow);
@@ -547,11 +562,12 @@ int grid_blocks(const pp_handle* h, int64_t work_items, int per_block, int block
 }  // namespace
 
 // one launch over n device-resident poses; the caller owns counter reset / read-back
-int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) {
+int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags, bool bits_out) {
   if (n == 0) return PP_OK;
   cudaStream_t s = h->stream;
   const int mode = h->P.collision_mode;
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(h->d_count);
+  if (bits_out && mode != PP_COLLISION_ORIENTED) return PP_ERR_INVALID;   // (pp_collide_batch_bits_dev packs the other modes' flags)
   if (mode == PP_COLLISION_AS_SHIPPED) {
     fill_zero_kernel<<<grid_blocks(h, n, kThreads * 16, 8), kThreads, 0, s>>>(flags, n);
   } else if (mode == PP_COLLISION_REF_AABB) {
@@ -578,22 +594,29 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) 
     static const int bps = getenv("PP_COLLIDE_BLOCKS_PER_SM") ? atoi(getenv("PP_COLLIDE_BLOCKS_PER_SM")) : PP_COLLIDE_MIN_BLOCKS;
     constexpr int64_t kSlice = int64_t(1) << 31;     // pose indices travel as 32-bit words in shared memory
     if (!h->oriented_ready) {                        // (per device: the attribute lives in the context)
-      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<48, 17, PP_LATTICE_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOrientedSmem)));
-      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<20, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOrientedSmem)));
-      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kOrientedSmem)));
+      const int sm = static_cast<int>(kOrientedSmem);
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<48, 17, PP_LATTICE_S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<20, 8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<0, 0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<48, 17, PP_LATTICE_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<20, 8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      PP_CUDA(cudaFuncSetAttribute(collide_oriented_kernel<0, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       h->oriented_ready = true;
     }
     for (int64_t lo = 0; lo < n; lo += kSlice) {
       const int64_t m = n - lo < kSlice ? n - lo : kSlice;
       const float* ps = poses + 3 * lo;
-      uint8_t* fs = flags + lo;
+      uint8_t* fs = bits_out ? flags + lo / 8 : flags + lo;      // (slices start on a multiple of 32 poses)
       const int blocks = grid_blocks(h, m, kBlockPoses * kWarpsPerBlock, bps);
-      if (h->lat.nu == 48 && h->lat.nv == 17)        // 4.7 m x 1.586 m at 0.1 m cells
-        collide_oriented_kernel<48, 17, PP_LATTICE_S><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
-      else if (h->lat.nu == 20 && h->lat.nv == 8)    // the same car at the launch file's 0.25 m cells
-        collide_oriented_kernel<20, 8, 4><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
-      else
-        collide_oriented_kernel<0, 0, 1><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);
+#define PP_LAUNCH_ORIENTED(NU, NV, S)                                                                                         \
+  do {                                                                                                                        \
+    if (bits_out) collide_oriented_kernel<NU, NV, S, true><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter); \
+    else collide_oriented_kernel<NU, NV, S, false><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);        \
+  } while (0)
+      if (h->lat.nu == 48 && h->lat.nv == 17) PP_LAUNCH_ORIENTED(48, 17, PP_LATTICE_S);   // 4.7 m x 1.586 m at 0.1 m cells
+      else if (h->lat.nu == 20 && h->lat.nv == 8) PP_LAUNCH_ORIENTED(20, 8, 4);          // the same car at the launch file's 0.25 m cells
+      else PP_LAUNCH_ORIENTED(0, 0, 1);
+#undef PP_LAUNCH_ORIENTED
     }
   }
   h->launches++;
@@ -613,14 +636,14 @@ int collide_counter_fetch(pp_handle* h) {
   return PP_OK;
 }
 
-int collide_batch_dev(pp_handle* h, int64_t n, const float* poses, uint8_t* flags) {
+int collide_batch_dev(pp_handle* h, int64_t n, const float* poses, uint8_t* flags, bool bits_out) {
   if (n == 0) return PP_OK;
   cudaStream_t s = h->stream;
   const bool counted = h->P.collision_mode == PP_COLLISION_ORIENTED;   // only the ORIENTED kernel counts narrow-phase jobs
   int rc = counted ? collide_counter_reset(h) : PP_OK;
   if (rc) return rc;
   PP_CUDA(cudaEventRecord(h->ev[2], s));
-  rc = collide_launch(h, n, poses, flags);
+  rc = collide_launch(h, n, poses, flags, bits_out);
   if (rc) return rc;
   PP_CUDA(cudaEventRecord(h->ev[3], s));
   rc = counted ? collide_counter_fetch(h) : PP_OK;

@@ -438,8 +438,8 @@ inline CollideParams collide_params(const pp_handle* h) {
 int grid_upload(pp_handle* h, const int8_t* data, bool data_on_device, int layout);
 int grid_bank_upload(pp_handle* h, int n, const int8_t* grids_dev, int layout);
 void grid_free(pp_handle* h);
-int collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev);
-int collide_launch(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev);
+int collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev, bool bits_out = false);
+int collide_launch(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* flags_dev, bool bits_out = false);   // bits_out: ORIENTED only
 int collide_counter_reset(pp_handle* h);
 int collide_counter_fetch(pp_handle* h);
 int collide_edges_dev(pp_handle* h, int64_t n, const float* edges_dev, uint8_t* flags_dev);

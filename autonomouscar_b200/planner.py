@@ -40,6 +40,18 @@ class Planner:
         s = C.c_void_p()
         self._check(self._L.pp_stream(self._h, C.byref(s)))
         self.stream = torch.cuda.ExternalStream(s.value, device=self.torch_device)
+        self._pending = {}     # tensors in use by calls still queued on self.stream (see _dev)
+
+    def _dev(self, t):
+        """Device pointer of a tensor handed to an ASYNCHRONOUS entry point.  The call runs on self.stream, which
+        torch's caching allocator does not know about: a temporary freed right after the call could be handed out
+        again (and overwritten on torch's stream) before the kernel has read it.  The planner therefore holds a
+        reference until its stream is next synchronised (sync(), or here once a few thousand have piled up)."""
+        if t.is_cuda:
+            if len(self._pending) >= 4096:
+                self.sync()
+            self._pending[t.data_ptr()] = t
+        return C.c_void_p(t.data_ptr())
 
     def _check(self, rc):
         if rc != PP_OK:
@@ -47,8 +59,9 @@ class Planner:
 
     def close(self):
         if self._h is not None:
-            self._L.pp_destroy(self._h)
+            self._L.pp_destroy(self._h)      # (synchronises the handle's stream)
             self._h = None
+            self._pending.clear()
 
     def __del__(self):
         try:
@@ -134,7 +147,17 @@ class Planner:
         n = poses.numel() // 3
         if out is None:
             out = torch.empty(n, dtype=torch.uint8, device=poses.device)
-        self._check(self._L.pp_collide_batch_dev(self._h, n, _dptr(poses), _dptr(out)))
+        self._check(self._L.pp_collide_batch_dev(self._h, n, self._dev(poses), self._dev(out)))
+        return out
+
+    def collide_bits_dev(self, poses, out=None):
+        """collide_dev with one bit per pose as the result (int32 words, bit b of word k = pose 32k + b): what
+        pack_flags_dev(collide_dev(poses)) returns, written by the batch kernel itself in ORIENTED mode."""
+        assert poses.is_cuda and poses.dtype == torch.float32 and poses.is_contiguous()
+        n = poses.numel() // 3
+        if out is None:
+            out = torch.empty((n + 31) // 32, dtype=torch.int32, device=poses.device)
+        self._check(self._L.pp_collide_batch_bits_dev(self._h, n, self._dev(poses), self._dev(out)))
         return out
 
     def pack_flags_dev(self, flags, out=None):
@@ -142,13 +165,13 @@ class Planner:
         n = flags.numel()
         if out is None:
             out = torch.empty((n + 31) // 32, dtype=torch.int32, device=flags.device)
-        self._check(self._L.pp_pack_flags_dev(self._h, n, _dptr(flags), _dptr(out)))
+        self._check(self._L.pp_pack_flags_dev(self._h, n, self._dev(flags), self._dev(out)))
         return out
 
     def unpack_flags_dev(self, bits, n, out=None):
         if out is None:
             out = torch.empty(n, dtype=torch.uint8, device=bits.device)
-        self._check(self._L.pp_unpack_flags_dev(self._h, n, _dptr(bits), _dptr(out)))
+        self._check(self._L.pp_unpack_flags_dev(self._h, n, self._dev(bits), self._dev(out)))
         return out
 
     def collide_edges_dev(self, edges, out=None):
@@ -156,7 +179,7 @@ class Planner:
         n = edges.numel() // 5
         if out is None:
             out = torch.empty(n, dtype=torch.uint8, device=edges.device)
-        self._check(self._L.pp_collide_edges_dev(self._h, n, _dptr(edges), _dptr(out)))
+        self._check(self._L.pp_collide_edges_dev(self._h, n, self._dev(edges), self._dev(out)))
         return out
 
     def footprint_points(self, x, y, yaw, capacity=4096):
@@ -171,7 +194,7 @@ class Planner:
         if out is None:
             out = torch.empty((n, 3), dtype=torch.float32, device=self.torch_device)
         self._check(self._L.pp_sample_poses_dev(self._h, seed, stream, first, n, x_lo, x_hi, y_lo, y_hi,
-                                                _dptr(out)))
+                                                self._dev(out)))
         return out
 
     def philox(self, ctr, key):
@@ -186,16 +209,16 @@ class Planner:
         nq = query_xy.numel() // 2
         idx = torch.empty(nq, dtype=torch.int32, device=query_xy.device)
         d2 = torch.empty(nq, dtype=torch.float32, device=query_xy.device)
-        self._check(self._L.pp_nearest_dev(self._h, node_xy.numel() // 2, _dptr(node_xy), nq, _dptr(query_xy),
-                                           _dptr(idx), _dptr(d2)))
+        self._check(self._L.pp_nearest_dev(self._h, node_xy.numel() // 2, self._dev(node_xy), nq, self._dev(query_xy),
+                                           self._dev(idx), self._dev(d2)))
         return idx, d2
 
     def find_exact_dev(self, keys, queries):
         assert keys.is_cuda and queries.is_cuda and keys.dtype == torch.float64
         nq = queries.numel() // 6
         idx = torch.empty(nq, dtype=torch.int32, device=queries.device)
-        self._check(self._L.pp_find_exact_dev(self._h, keys.numel() // 6, _dptr(keys), nq, _dptr(queries),
-                                              _dptr(idx)))
+        self._check(self._L.pp_find_exact_dev(self._h, keys.numel() // 6, self._dev(keys), nq, self._dev(queries),
+                                              self._dev(idx)))
         return idx
 
     # ---- planning ----------------------------------------------------------------------
@@ -235,7 +258,7 @@ class Planner:
         if out is None:
             out = torch.empty((n, stride), dtype=torch.uint8, device=self.torch_device)
         assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= n * stride
-        self._check(self._L.pp_plan_batch_dev(self._h, int(n), queries_array, int(cap_path), _dptr(out)))
+        self._check(self._L.pp_plan_batch_dev(self._h, int(n), queries_array, int(cap_path), self._dev(out)))
         return out
 
     def rrt_plan(self, query, **caps):
@@ -260,6 +283,7 @@ class Planner:
     # ---- plumbing ------------------------------------------------------------------------
     def sync(self):
         self._check(self._L.pp_sync(self._h))
+        self._pending.clear()
 
     def launch_count(self):
         v = C.c_uint64()

@@ -226,6 +226,12 @@ int pp_collide_batch_q16(pp_handle* h, int64_t n, const int16_t* poses_q16_host,
                          uint8_t* out_flags_host);
 /* device pointers; asynchronous on the handle's stream; pp_sync() to wait */
 int pp_collide_batch_dev(pp_handle* h, int64_t n, const float* poses_dev, uint8_t* out_flags_dev);
+/* pp_collide_batch_dev with ONE BIT per pose as the result: bit b of out_bits_dev[k] = pose 32 k + b, exactly what
+   pp_pack_flags_dev makes of pp_collide_batch_dev's flags; ceil(n / 32) words, the unused bits of the last word
+   are 0.  In ORIENTED mode the batch kernel writes the bits itself (no byte array, no second pass): the form in
+   which results leave the device for a gather.  Asynchronous on the handle's stream. */
+int pp_collide_batch_bits_dev(pp_handle* h, int64_t n, const float* poses_dev, uint32_t* out_bits_dev);
+
 /* Result flags as one bit per pose (word k bit b = flag 32k + b; (n + 31) / 32 words, the unused bits of the
    last word are 0): what the multi-GPU result gather moves (NCCL only to gather
    results -- 2 MiB instead of 16 MiB per 2^24 poses).  Asynchronous on the handle's stream; flags_dev must be

@@ -273,6 +273,29 @@ def test_pack_unpack_flags(cuda_device):
 
 
 @pytest.mark.parametrize("mode", [PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED])
+def test_bit_results_equal_packed_flags(cuda_device, mode):
+    """pp_collide_batch_bits_dev (in ORIENTED mode the batch kernel ORs the bits in itself): the words equal
+    pp_pack_flags_dev of pp_collide_batch_dev's flags, for ragged lengths, a reused (dirty) output buffer, with and
+    without the broad phase, and poses off the grid."""
+    p = default_params(costmap_res=0.1, costmap_width=1024, costmap_height=1024, collision_mode=mode)
+    grid = worlds.block_grid(1024, 1024, frac=0.02, block=8, seed=31)
+    pl = _planner(p, grid)
+    for n in (1, 31, 32, 127, 128, 129, 4099, 300007):
+        poses = torch.from_numpy(worlds.random_poses(p, n, seed=n, inset_m=-6.0)).cuda()
+        torch.cuda.synchronize()                         # (the upload runs on torch's stream, the kernels on the handle's)
+        for broad in (1, 0) if n <= 4099 else (1,):
+            pl.set_broad_phase(bool(broad))
+            want = pl.pack_flags_dev(pl.collide_dev(poses))
+            out = torch.full(((n + 31) // 32,), -1, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()                     # (the fill runs on torch's stream, the kernel on the handle's)
+            got = pl.collide_bits_dev(poses, out=out)
+            pl.sync()
+            assert torch.equal(got, want), (n, broad)
+    pl.set_broad_phase(True)
+    pl.close()
+
+
+@pytest.mark.parametrize("mode", [PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED])
 def test_compact_int16_pose_format(oracle, cuda_device, mode):
     """pp_collide_batch_q16 (6 B per pose over PCIe): the device reconstructs float32 poses with two separately rounded
     float32 operations per coordinate; the flags equal pp_collide_batch -- and the oracle -- on exactly those poses."""
