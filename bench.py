@@ -300,7 +300,7 @@ def run_ours(args):
     # inputs resident in HBM before the timed region: the Philox sampler fills them (row S1), stream = rank
     poses = pl.sample_poses_dev(2018, rank, 0, n, *box)
     # two result buffers: the NCCL gather of step k overlaps the kernel of step k+1.  What is gathered is one BIT
-    # per pose (pp_collide_batch_bits_dev): 2 MiB per rank instead of 16 MiB
+    # per pose (pp_pack_flags_dev): 2 MiB per rank instead of 16 MiB
     flags2 = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
     bits2 = [torch.empty(n_words, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
     gathered2 = [torch.empty(n_words * world, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
@@ -314,18 +314,19 @@ def run_ours(args):
         step_no[0] += 1
         if multi and gather_done[i] is not None:
             pl.stream.wait_event(gather_done[i])        # the buffer's previous gather has finished
+        pl.collide_dev(poses, out=flags2[i])
         if multi:
-            # result gather (north_star: NCCL only to gather results), ordered after the kernel, which writes the
-            # bit per pose itself (pp_collide_batch_bits_dev: no byte flags, no pack pass)
-            pl.collide_bits_dev(poses, out=bits2[i])
+            # result gather (north_star: NCCL only to gather results), ordered after the kernels.  (Measured both
+            # ways: with the bits written by the batch kernel itself, pp_collide_batch_bits_dev, the step is 12 us
+            # longer at N = 2 and 27 us at N = 8 -- the next step's persistent kernel then takes every SM before the
+            # all-gather kernel of this step gets one, and the gather ends up behind it instead of beside it.)
+            pl.pack_flags_dev(flags2[i], out=bits2[i])
             ev = torch.cuda.Event()
             ev.record(pl.stream)
             torch.cuda.current_stream().wait_event(ev)
             dist.all_gather_into_tensor(gathered2[i], bits2[i])
             gather_done[i] = torch.cuda.Event()
             gather_done[i].record(torch.cuda.current_stream())
-        else:
-            pl.collide_dev(poses, out=flags2[i])
         return i
 
     def barrier():
@@ -588,7 +589,7 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s_timed_region": wall,
             "run": {"hit_rate": hit_rate, "broad_phase": True, "rank_cpu_affinity": numa,
-                    "gather": "1 bit per pose written by the batch kernel (pp_collide_batch_bits_dev), ncclAllGather" if multi else None, "parity": parity},
+                    "gather": "1 bit per pose (pp_pack_flags_dev), ncclAllGather" if multi else None, "parity": parity},
             "extra": extra,
             "plans": plans,
             "costmap": costmap,
