@@ -305,6 +305,25 @@ def run_ours(args):
     bits2 = [torch.empty(n_words, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
     gathered2 = [torch.empty(n_words * world, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
     gather_done = [None, None]
+    # How the bits travel.  "symm": every rank PULLS its peers' 2 MiB over NVLink with the copy engines (peer memory
+    # mapped through torch's symmetric memory, two signal-pad barriers around the copies) -- no SM is involved, so the
+    # gather runs beside the next step's persistent kernel, which leaves no SM free for a collective's kernel.
+    # "nccl": one ncclAllGather (its kernel ends up queued behind the next step's kernel: measured 0.937 weak scaling
+    # at N = 8).  The symmetric-memory set-up falls back to NCCL when the platform refuses it.
+    gather_kind, symm_hdl, side = None, None, None
+    if multi:
+        gather_kind = "nccl"
+        if args.gather == "symm":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                sb = [symm.empty(n_words, dtype=torch.int32, device=dev) for _ in range(2)]
+                symm_hdl = [symm.rendezvous(b, dist.group.WORLD) for b in sb]
+                bits2 = sb
+                side = torch.cuda.Stream(device=dev, priority=-1)
+                gather_kind = "symm"
+            except Exception as exc:   # noqa: BLE001 -- any failure of the optional transport means NCCL
+                print(f"[bench] symmetric memory unavailable ({type(exc).__name__}: {exc}); gathering with NCCL", file=sys.stderr)
+                symm_hdl = None
     flags = flags2[0]
     step_no = [0]
     pl.sync()
@@ -323,10 +342,22 @@ def run_ours(args):
             pl.pack_flags_dev(flags2[i], out=bits2[i])
             ev = torch.cuda.Event()
             ev.record(pl.stream)
-            torch.cuda.current_stream().wait_event(ev)
-            dist.all_gather_into_tensor(gathered2[i], bits2[i])
-            gather_done[i] = torch.cuda.Event()
-            gather_done[i].record(torch.cuda.current_stream())
+            if symm_hdl is not None:
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    hdl, rows = symm_hdl[i], gathered2[i].view(world, n_words)
+                    hdl.barrier()                                  # every rank's bits of this step are in place
+                    for sft in range(world):
+                        r = (rank - sft) % world
+                        rows[r].copy_(hdl.get_buffer(r, (n_words,), torch.int32))   # D2D copy: copy engine, NVLink
+                    hdl.barrier()                                  # every rank has pulled: the buffer may be rewritten
+                    gather_done[i] = torch.cuda.Event()
+                    gather_done[i].record(side)
+            else:
+                torch.cuda.current_stream().wait_event(ev)
+                dist.all_gather_into_tensor(gathered2[i], bits2[i])
+                gather_done[i] = torch.cuda.Event()
+                gather_done[i].record(torch.cuda.current_stream())
         return i
 
     def barrier():
@@ -351,7 +382,7 @@ def run_ours(args):
         last = step()
     if multi:
         evj = torch.cuda.Event()
-        evj.record(torch.cuda.current_stream())
+        evj.record(side if symm_hdl is not None else torch.cuda.current_stream())
         pl.stream.wait_event(evj)
     e1.record(pl.stream)
     barrier()
@@ -589,7 +620,7 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s_timed_region": wall,
             "run": {"hit_rate": hit_rate, "broad_phase": True, "rank_cpu_affinity": numa,
-                    "gather": "1 bit per pose (pp_pack_flags_dev), ncclAllGather" if multi else None, "parity": parity},
+                    "gather": ({"symm": "1 bit per pose (pp_pack_flags_dev), pulled from the peers over NVLink by the copy engines (symmetric memory)", "nccl": "1 bit per pose (pp_pack_flags_dev), ncclAllGather"}[gather_kind] if multi else None), "parity": parity},
             "extra": extra,
             "plans": plans,
             "costmap": costmap,
@@ -1156,6 +1187,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=N_POSES)
     ap.add_argument("--queries", type=int, default=1024, help="plan queries per GPU")
+    ap.add_argument("--gather", default="symm", choices=["symm", "nccl"], help="N > 1: transport of the result bits")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-plans", action="store_true")
     args = ap.parse_args()
