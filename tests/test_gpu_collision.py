@@ -53,6 +53,56 @@ def test_collide_matches_oracle(oracle, cuda_device, res, W, H, mode):
     pl.close()
 
 
+@pytest.mark.parametrize("res,W,H", [(0.1, 700, 520), (0.25, 300, 300), (0.2, 400, 333), (0.125, 512, 512)])
+@pytest.mark.parametrize("world", ["cells", "solid", "mixed"])
+def test_oriented_proofs_stress(oracle, cuda_device, res, W, H, world):
+    """The batch kernel decides most poses by proofs (yaw-binned dilated maps, oriented 4x4-block hull and core,
+    perimeter pass, cell-level hull): poses chosen to sit on their edges -- yaws on the bin borders (k pi / 16) and
+    one ulp either side, axis-aligned yaws (a band of the footprint drops out), |yaw| beyond the binned range, poses
+    hugging single-cell obstacles (no 4x4 block is full) and solid areas (nearly every block is), lattice shapes other
+    than the two templated ones -- must agree with the oracle bit for bit, with and without the broad phase."""
+    p = default_params(costmap_res=res, costmap_width=W, costmap_height=H, collision_mode=PP_COLLISION_ORIENTED)
+    rng = np.random.default_rng(W * 7 + H + len(world))
+    if world == "cells":
+        grid = worlds.cell_noise_grid(W, H, p=0.004, seed=W + 1)
+    elif world == "solid":
+        grid = np.zeros((W, H), dtype=np.int8)
+        for _ in range(6):
+            i, j = rng.integers(0, W - 60), rng.integers(0, H - 60)
+            grid[i:i + rng.integers(20, 60), j:j + rng.integers(20, 60)] = 100
+    else:
+        grid = worlds.block_grid(W, H, frac=0.02, block=5, seed=H + 3)
+        grid[rng.random(grid.shape) < 0.001] = 100
+    n = 40000
+    poses = worlds.random_poses(p, n, seed=11, inset_m=-5.0)
+    k = rng.integers(-40, 40, size=n)
+    border = (k * (np.pi / 16)).astype(np.float32)
+    kind = rng.integers(0, 6, size=n)
+    yaw = poses[:, 2].copy()
+    yaw = np.where(kind == 0, border, yaw)
+    yaw = np.where(kind == 1, np.nextafter(border, np.float32(10.0)), yaw)
+    yaw = np.where(kind == 2, np.nextafter(border, np.float32(-10.0)), yaw)
+    yaw = np.where(kind == 3, (rng.integers(-3, 4, size=n) * (np.pi / 2)).astype(np.float32), yaw)
+    yaw = np.where((kind == 4) & (rng.random(n) < 0.2), (yaw * 60.0).astype(np.float32), yaw)   # |yaw| up to ~190 rad
+    poses[:, 2] = yaw.astype(np.float32)
+    # half of the poses hug an obstacle cell: within ~3 m of one, where the proofs are undecided most often
+    occ = np.argwhere(grid == 100)
+    pick = occ[rng.integers(0, len(occ), size=n // 2)]
+    poses[: n // 2, 1] = ((W // 2 - pick[:, 0]) * res + rng.uniform(-3.0, 3.0, n // 2)).astype(np.float32)
+    poses[: n // 2, 0] = ((H // 2 - pick[:, 1]) * res + rng.uniform(-3.0, 3.0, n // 2)).astype(np.float32)
+    pl = _planner(p, grid)
+    want, _ = oracle.collide_batch(p, grid, poses)
+    assert 0.02 < want.mean() < 0.98
+    d = torch.from_numpy(poses).cuda()
+    torch.cuda.synchronize()
+    f1 = pl.collide_dev(d); pl.sync()
+    np.testing.assert_array_equal(f1.cpu().numpy(), want)
+    pl.set_broad_phase(False)
+    f2 = pl.collide_dev(d); pl.sync()
+    np.testing.assert_array_equal(f2.cpu().numpy(), want)
+    pl.close()
+
+
 def test_as_shipped_is_always_false(cuda_device):
     # LP:445: the shipped reference returns false unconditionally
     p = default_params(collision_mode=PP_COLLISION_AS_SHIPPED)
