@@ -1,11 +1,14 @@
 // pp_narrow.cuh -- warp-cooperative ORIENTED footprint test shared by the batch collision
 // kernel (pp_collide.cu) and the sampling planner's edge kernel (pp_rrt.cu).
 //
-//   broad phase  (one thread):  fixed-point lattice set-up, bounding box, tile / 8x8-block
-//                               occupancy under the box           -> NarrowJob or "free"
-//   narrow phase (one warp):    stage the <= 3x3 tiles under the box into shared memory
-//                               (each tile = one coalesced 128 B line), exact box test,
-//                               then the nu x nv sample lattice split over the 32 lanes
+//   broad phase  (one thread):  fixed-point lattice set-up, bounding box, then
+//       make_job        (batch kernel)   the oriented 4x4-block test: free / colliding / NarrowJob
+//       make_job_light  (edges)          tile flags + 4x4 blocks under the bounding box: free / NarrowJob
+//   narrow phase (one warp):    the three tile rows under the box staged into shared memory (each tile = one
+//       coalesced 128 B line), then
+//       window_collide_fixed (batch)     perimeter pass, cell-level hull test, the nu x nv sample lattice
+//       window_box_collide   (edges)     exact box test, the sample lattice
+#pragma once
 #pragma once
 #include "pp_common.cuh"
 
@@ -22,22 +25,6 @@ struct __align__(16) NarrowJob {
   // samples of window row r can reach are  max(kT d + tlo, kS d + slo) .. min(kT d + thi, kS d + shi),  d = r + d0
   float kT, kS, tlo, thi, slo, shi, d0;
 };                  // 64 bytes: four 128-bit shared-memory loads per job
-
-// same for a wider square (the yaw-independent bound): up to 64 coarse cells wide
-__device__ __forceinline__ bool coarse_square_any(const GridDev& g, int i0, int i1, int j0, int j1) {
-  const int r0 = (i0 + kHaloCells) >> 3, r1 = (i1 + kHaloCells) >> 3;
-  const int c0 = (j0 + kHaloCells) >> 3, c1 = (j1 + kHaloCells) >> 3;
-  const int w0 = c0 >> 6, sh = c0 & 63, nb = c1 - c0 + 1;
-  const unsigned long long m = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
-  unsigned long long any = 0;
-  for (int r = r0; r <= r1; ++r) {
-    const unsigned long long* row = g.coarse + static_cast<size_t>(r) * g.CW8 + w0;
-    unsigned long long bits = __ldg(row) >> sh;
-    if (sh + nb > 64) bits |= __ldg(row + 1) << (64 - sh);
-    any |= bits & m;
-  }
-  return any != 0;
-}
 
 // Broad phase for one pose (one thread): 0 = certainly collision-free, 2 = certainly colliding (nothing written to
 // *job in either case), 1 = *job describes the pose for the narrow phase.
