@@ -543,7 +543,10 @@ int pp_last_narrow_count(pp_handle* h, int64_t* out) {
   if (!h || !out) return PP_ERR_INVALID;
   PP_CUDA(cudaSetDevice(h->device));
   PP_CUDA(cudaStreamSynchronize(h->stream));
-  if (h->last_narrow < 0) h->last_narrow = static_cast<int64_t>(*reinterpret_cast<unsigned long long*>(h->h_count));
+  if (h->last_narrow < 0) {
+    const volatile unsigned long long* pub = reinterpret_cast<const volatile unsigned long long*>(h->h_count);
+    h->last_narrow = static_cast<int64_t>(pub[1] - pub[0]);   // {total before the call, total now}
+  }
   *out = h->last_narrow;
   return PP_OK;
 }

@@ -325,8 +325,9 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
 //                        staged window, a cheap pass along the lattice's perimeter, then the sample lattice
 //   NU == 0 selects the run-time lattice shape.  broad_phase == 0 ("direct") disables every pruning test: each
 //   pose that overlaps the grid runs the full lattice.
-//   counters[0] += narrow-phase jobs; counters[1] = the ticket, counters[2] = CTAs finished: the last CTA to
-//   finish zeroes both for the next launch (launches of one handle are serialised on its stream).
+//   counters[3] += narrow-phase jobs of this launch; the low / high half of counters[1] = the ticket / the CTAs
+//   finished: the last CTA to finish zeroes both, folds counters[3] into the running total counters[0] and
+//   publishes it to pinned host memory (launches of one handle are serialised on its stream).
 #ifndef PP_WIN_DEPTH
 #define PP_WIN_DEPTH 1
 #endif
@@ -350,7 +351,8 @@ constexpr size_t kOrientedSmem = kOrientedWarpBytes * kWarpsPerBlock;
 template <int NU, int NV, int S, bool kBits>
 __global__ void __launch_bounds__(kThreads, PP_COLLIDE_MIN_BLOCKS)
 collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses, uint8_t* __restrict__ flags,
-                        int64_t n, int broad_phase, unsigned long long* __restrict__ counters) {
+                        int64_t n, int broad_phase, unsigned long long* __restrict__ counters,
+                        unsigned long long* __restrict__ host_pub, int first_of_call) {
   uint32_t* bits = reinterpret_cast<uint32_t*>(flags);
   // every warp's own slice of (dynamic) shared memory: ring of windows, jobs, their pose indices, survivor queue
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -476,12 +478,24 @@ collide_oriented_kernel(GridDev g, Lattice lat, const float* __restrict__ poses,
     }
     __syncwarp();                                            // s_jobs / s_job_k are rewritten by the next pass
   }
-  if (lane == 0 && local_narrow) atomicAdd(counters, local_narrow);
+  if (lane == 0 && local_narrow) atomicAdd(counters + 3, local_narrow);
   __syncthreads();
   if (tid == 0) {
     unsigned int* done = reinterpret_cast<unsigned int*>(counters + 1) + 1;
     __threadfence();
-    if (atomicAdd(done, 1u) == gridDim.x - 1) { *ticket = 0u; *done = 0u; __threadfence(); }
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      // the last CTA of the launch: everything is left ready for the next launch (no memset between launches), and
+      // the job counts go straight to the pinned host words {total before this call, total now} -- a call may be
+      // several launches; pp_last_narrow_count takes the difference once the stream is idle.
+      __threadfence();
+      const unsigned long long before = counters[0];
+      const unsigned long long now = before + *reinterpret_cast<volatile unsigned long long*>(counters + 3);
+      counters[0] = now; counters[3] = 0ull;
+      *ticket = 0u; *done = 0u;
+      if (first_of_call) host_pub[0] = before;
+      host_pub[1] = now;
+      __threadfence_system();
+    }
   }
 }
 
@@ -608,10 +622,13 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags, 
       const float* ps = poses + 3 * lo;
       uint8_t* fs = bits_out ? flags + lo / 8 : flags + lo;      // (slices start on a multiple of 32 poses)
       const int blocks = grid_blocks(h, m, kBlockPoses * kWarpsPerBlock, bps);
+      unsigned long long* pub = reinterpret_cast<unsigned long long*>(h->h_count);   // (pinned: the device writes through UVA)
+      const int first = h->narrow_first ? 1 : 0;
+      h->narrow_first = false;
 #define PP_LAUNCH_ORIENTED(NU, NV, S)                                                                                         \
   do {                                                                                                                        \
-    if (bits_out) collide_oriented_kernel<NU, NV, S, true><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter); \
-    else collide_oriented_kernel<NU, NV, S, false><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter);        \
+    if (bits_out) collide_oriented_kernel<NU, NV, S, true><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter, pub, first); \
+    else collide_oriented_kernel<NU, NV, S, false><<<blocks, kThreads, kOrientedSmem, s>>>(h->grid, h->lat, ps, fs, m, h->broad_phase, counter, pub, first);        \
   } while (0)
       if (h->lat.nu == 48 && h->lat.nv == 17) PP_LAUNCH_ORIENTED(48, 17, PP_LATTICE_S);   // 4.7 m x 1.586 m at 0.1 m cells
       else if (h->lat.nu == 20 && h->lat.nv == 8) PP_LAUNCH_ORIENTED(20, 8, 4);          // the same car at the launch file's 0.25 m cells
@@ -624,15 +641,15 @@ int collide_launch(pp_handle* h, int64_t n, const float* poses, uint8_t* flags, 
   return PP_OK;
 }
 
+// A "call" may be several launches (chunks of the host pipeline, slices of a huge batch): the first ORIENTED launch
+// after this publishes the running total it starts from, every launch publishes the total it ends with
+// (collide_oriented_kernel's last CTA), and pp_last_narrow_count takes the difference.  No stream operation.
 int collide_counter_reset(pp_handle* h) {
-  // the narrow-phase job count, and the ORIENTED kernel's ticket / finished-CTA words (self-resetting; cleared
-  // here as well so that an aborted launch cannot poison the next batch)
-  PP_CUDA(cudaMemsetAsync(h->d_count, 0, 2 * sizeof(unsigned long long), h->stream));
+  h->narrow_first = true;
   return PP_OK;
 }
 int collide_counter_fetch(pp_handle* h) {
-  PP_CUDA(cudaMemcpyAsync(h->h_count, h->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-  h->last_narrow = -1;  // resolved from the pinned mirror after the next sync
+  h->last_narrow = -1;  // resolved from the pinned words once the stream is idle
   return PP_OK;
 }
 

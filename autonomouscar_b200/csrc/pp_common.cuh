@@ -406,6 +406,7 @@ struct pp_handle {
   uint64_t launches = 0;
   float phase_ms[PP_PHASE_COUNT] = {};
   int64_t last_narrow = 0;
+  bool narrow_first = true;        // the next ORIENTED launch is the first of a call (see collide_counter_reset)
   // staging for the host-pointer collide entry point
   float* d_poses = nullptr;
   uint8_t* d_flags = nullptr;
