@@ -311,6 +311,7 @@ def run_ours(args):
     # "nccl": one ncclAllGather (its kernel ends up queued behind the next step's kernel: measured 0.937 weak scaling
     # at N = 8).  The symmetric-memory set-up falls back to NCCL when the platform refuses it.
     gather_kind, symm_hdl, side = None, None, None
+    bits_kernel = False
     if multi:
         gather_kind = "nccl"
         if args.gather == "symm":
@@ -321,6 +322,7 @@ def run_ours(args):
                 bits2 = sb
                 side = torch.cuda.Stream(device=dev, priority=-1)
                 gather_kind = "symm"
+                bits_kernel = not args.pack_pass
             except Exception as exc:   # noqa: BLE001 -- any failure of the optional transport means NCCL
                 print(f"[bench] symmetric memory unavailable ({type(exc).__name__}: {exc}); gathering with NCCL", file=sys.stderr)
                 symm_hdl = None
@@ -333,13 +335,17 @@ def run_ours(args):
         step_no[0] += 1
         if multi and gather_done[i] is not None:
             pl.stream.wait_event(gather_done[i])        # the buffer's previous gather has finished
-        pl.collide_dev(poses, out=flags2[i])
+        if multi and bits_kernel:
+            pl.collide_bits_dev(poses, out=bits2[i])            # the batch kernel writes the bit per pose itself
+        else:
+            pl.collide_dev(poses, out=flags2[i])
         if multi:
-            # result gather (north_star: NCCL only to gather results), ordered after the kernels.  (Measured both
-            # ways: with the bits written by the batch kernel itself, pp_collide_batch_bits_dev, the step is 12 us
-            # longer at N = 2 and 27 us at N = 8 -- the next step's persistent kernel then takes every SM before the
-            # all-gather kernel of this step gets one, and the gather ends up behind it instead of beside it.)
-            pl.pack_flags_dev(flags2[i], out=bits2[i])
+            # result gather (north_star: NCCL only to gather results), ordered after the kernels.  (With NCCL the
+            # kernel-written bits, pp_collide_batch_bits_dev, made the step 12 us longer at N = 2 and 27 us at N = 8:
+            # the next step's persistent kernel then takes every SM before the all-gather kernel of this step gets
+            # one.  The copy-engine gather needs no SM, and there the bits kernel saves the pack pass.)
+            if not bits_kernel:
+                pl.pack_flags_dev(flags2[i], out=bits2[i])
             ev = torch.cuda.Event()
             ev.record(pl.stream)
             if symm_hdl is not None:
@@ -620,7 +626,7 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s_timed_region": wall,
             "run": {"hit_rate": hit_rate, "broad_phase": True, "rank_cpu_affinity": numa,
-                    "gather": ({"symm": "1 bit per pose (pp_pack_flags_dev), pulled from the peers over NVLink by the copy engines (symmetric memory)", "nccl": "1 bit per pose (pp_pack_flags_dev), ncclAllGather"}[gather_kind] if multi else None), "parity": parity},
+                    "gather": ({"symm": "1 bit per pose (" + ("pp_collide_batch_bits_dev" if bits_kernel else "pp_pack_flags_dev") + "), pulled from the peers over NVLink by the copy engines (symmetric memory)", "nccl": "1 bit per pose (pp_pack_flags_dev), ncclAllGather"}[gather_kind] if multi else None), "parity": parity},
             "extra": extra,
             "plans": plans,
             "costmap": costmap,
@@ -1188,6 +1194,7 @@ def main():
     ap.add_argument("--poses", type=int, default=N_POSES)
     ap.add_argument("--queries", type=int, default=1024, help="plan queries per GPU")
     ap.add_argument("--gather", default="symm", choices=["symm", "nccl"], help="N > 1: transport of the result bits")
+    ap.add_argument("--pack-pass", action="store_true", help="N > 1 with --gather symm: byte flags + pp_pack_flags_dev instead of the bits kernel")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-plans", action="store_true")
     args = ap.parse_args()
