@@ -390,11 +390,15 @@ struct RrtPersist {
   long long* cycles;     // PP_RRT_TIMING: SM cycles of CTA 0 per phase (nearest, edge, barrier 1, append, barrier 2, regroup), else null
 };
 
+// Arrival = one release-add, waiting = acquire-loads: the CTA's writes (ordered before thread 0 by the block barrier)
+// become visible with the add, and what the other CTAs wrote before theirs is visible after the load that sees the
+// target -- the same guarantees as fence + atomic + spin + fence, without the two full memory barriers.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned* generation) {
   __syncthreads();
   if (threadIdx.x == 0) {
     *generation += 1;
     const unsigned target = *generation * gridDim.x;
+#ifdef PP_RRT_FENCE_BARRIER
     __threadfence();                                   // this CTA's writes are visible before it arrives
     atomicAdd(counter, 1u);
     unsigned spins = 0;
@@ -402,6 +406,14 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned* genera
       if (++spins > (1u << 28)) __trap();              // a CTA that never arrives is a bug, not something to wait out
     }
     __threadfence();                                   // (gpu-scope fence: also drops this SM's stale L1 lines)
+#else
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned seen = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (++spins > (1u << 28)) __trap();              // a CTA that never arrives is a bug, not something to wait out
+    } while (seen < target);
+#endif
   }
   __syncthreads();
 }
