@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "pp_common.cuh"
+#include "pp_near_spans.h"
 
 namespace pp {
 
@@ -307,51 +308,10 @@ int grid_alloc(GridDev* g, const GridBank& b) {
   return PP_OK;
 }
 
-// Structuring elements of near4, per yaw bin:  which 4x4 blocks (di, dj) away from the pose's block can hold a
-// lattice sample.  With the pose at continuous cell coordinates c inside its block and a sample at c + d (d in the
-// footprint rectangle R(yaw), centred on the pose: half lengths du along (sin, cos) and dv along (cos, -sin) in
-// (row, column) -- pose_to_fixed's u and v), the sample's block is (di, dj) away only if d lies in the open square
-// 4 (di, dj) + (-4, 4)^2: a rectangle-against-square overlap test (separating axes: the square's two and the
-// rectangle's two), taken over the yaws of the bin widened by 1e-3 rad (the kernel bins a float product).  The
-// rectangle is inflated by 1.5 cells (the kernel's float cell index may be one off in each axis) plus what the
-// yaw sampling step can move a corner.  Rows are stored as one span of columns {first, last} (first > last: empty).
-void near_span_table(const Lattice& lat, int* e_out, std::vector<int16_t>* table) {
-  const double du = lat.su * lat.hu, dv = lat.sv * lat.hv;
-  const int E = static_cast<int>(std::ceil((std::sqrt(du * du + dv * dv) + 1.5 + 4.0) / 4.0)) + 1;
-  const int rows = 2 * E + 1, NS = 32;
-  table->assign(static_cast<size_t>(kNearBins) * rows * 2, 0);
-  for (int b = 0; b < kNearBins; ++b) {
-    const double lo = b * M_PI / kNearBins - 1.0e-3, hi = (b + 1) * M_PI / kNearBins + 1.0e-3;
-    const double pad = 1.5 + 0.05 + (du + dv) * (hi - lo) / NS;
-    const double ha = du + pad, hb = dv + pad, hs = 4.0;
-    std::vector<int> first(rows, 1), last(rows, 0);
-    for (int k = 0; k <= NS; ++k) {
-      const double t = lo + (hi - lo) * k / NS;
-      const double ux = std::sin(t), uy = std::cos(t), vx = std::cos(t), vy = -std::sin(t);
-      for (int di = -E; di <= E; ++di)
-        for (int dj = -E; dj <= E; ++dj) {
-          const double cx = 4.0 * di, cy = 4.0 * dj;
-          if (std::fabs(cx) >= hs + ha * std::fabs(ux) + hb * std::fabs(vx)) continue;
-          if (std::fabs(cy) >= hs + ha * std::fabs(uy) + hb * std::fabs(vy)) continue;
-          if (std::fabs(cx * ux + cy * uy) >= ha + hs * (std::fabs(ux) + std::fabs(uy))) continue;
-          if (std::fabs(cx * vx + cy * vy) >= hb + hs * (std::fabs(vx) + std::fabs(vy))) continue;
-          int& f = first[di + E];
-          int& l = last[di + E];
-          if (f > l) { f = dj; l = dj; } else { f = std::min(f, dj); l = std::max(l, dj); }
-        }
-    }
-    for (int r = 0; r < rows; ++r) {
-      (*table)[(static_cast<size_t>(b) * rows + r) * 2] = static_cast<int16_t>(first[r]);
-      (*table)[(static_cast<size_t>(b) * rows + r) * 2 + 1] = static_cast<int16_t>(last[r]);
-    }
-  }
-  *e_out = E;
-}
-
 int ensure_near_spans(pp_handle* h) {
   if (h->d_near_spans) return PP_OK;
   std::vector<int16_t> t;
-  near_span_table(h->lat, &h->near_e, &t);
+  near_span_table(h->lat.su * h->lat.hu, h->lat.sv * h->lat.hv, kNearBins, &h->near_e, &t);
   if (h->near_e >= 60) return PP_ERR_UNSUPPORTED;   // (spans must stay inside the neighbouring 64-bit words)
   PP_CUDA(cudaMalloc(&h->d_near_spans, sizeof(int16_t) * t.size()));
   PP_CUDA(cudaMemcpy(h->d_near_spans, t.data(), sizeof(int16_t) * t.size(), cudaMemcpyHostToDevice));
