@@ -763,10 +763,10 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         }
         if (unsupported) break;
         if (my_visit >= 0) A.visited[my_visit] = 1;   // only reached when the goal test did not end the plan
-        collided_local += collided ? 1 : 0;
         // LP:56-72.  A fingerprint never seen before cannot equal any node: open it.  A seen
         // fingerprint takes the exact scan (rare).
         for (;;) {
+          if (!__syncthreads_or(suspicious)) break;          // (the common case: one barrier instead of two + a reduction)
           const int owner = block_min(suspicious ? tid : kIntMax, s_red);
           if (owner == kIntMax) break;
           if (tid == owner) {
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         // order-preserving compaction of the survivors of this chunk
         const unsigned bal = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) s_scan[warp] = __popc(bal);
-        __syncthreads();
+        collided_local += __syncthreads_count(collided);      // (the barrier of the scan also counts the collisions)
         int before = 0, total = 0;
         for (int ww = 0; ww < kWarps; ++ww) {
           const int v = s_scan[ww];
@@ -828,7 +828,6 @@ __global__ void __launch_bounds__(kBatchCtas ? 128 : kTMax, kBatchCtas ? kBatchC
         break;
       }
       if (unsupported) { if (tid == 0) S.status = PP_PLAN_BROKEN; break; }
-      collided_local = block_sum(collided_local, s_red);
       PP_TICK(3);
       // openNode for every survivor, in order: frontier pushes by warp 0 (LP:62 / LP:70).  The
       // costs are fetched 32 at a time (one L2 round trip) and handed out by shuffle.
