@@ -3,7 +3,8 @@
 The hot path shards naturally: poses of a batch and plan queries are independent
 (SURVEY.md section 8(e)).  Every rank owns a contiguous block of the input, works on it
 with NO data-path collective, and the results are gathered with one all-gather (NCCL over
-NVLink on the GPU box; the same code runs on gloo/CPU tensors in the tests).
+NVLink on the GPU box; the same code runs on gloo/CPU tensors in the tests) or, for the packed
+collision flags, pulled from the peers by the copy engines (ResultGather).
 """
 import torch
 import torch.distributed as dist
@@ -40,6 +41,66 @@ def gather_blocks(local, n_total, group=None):
         lo, hi = shard_bounds(n_total, r, world)
         pieces.append(out[r * per: r * per + (hi - lo)])
     return torch.cat(pieces, dim=0)
+
+
+class ResultGather:
+    """All-gather of equal-sized per-rank result blocks (the packed collision flags) that does not need an SM.
+
+    transport "symm": the send buffers live in symmetric peer memory (torch.distributed._symmetric_memory: every
+    rank's buffer mapped into every rank's address space).  A gather is a signal-pad barrier (all ranks' blocks are
+    in place), one plain device-to-device copy per peer -- copy engines over NVLink, pulled -- and a second barrier
+    (everyone has pulled: the send buffer may be rewritten), all on a side stream.  It therefore runs beside a
+    persistent kernel that occupies every SM, where a collective's own kernel would have to wait for it.
+    transport "nccl" (also the fallback when the platform refuses the peer mappings): one all_gather_into_tensor.
+
+    `slots` send / receive buffer pairs allow the gather of one step to overlap the work of the next:
+        g = ResultGather(n_words, torch.int32, device); kernel writes g.send[i]; ev = g.gather(i, after=event_of_kernel)
+    `ev` completes when g.all[i] (shape [world, n]) holds every rank's block and g.send[i] may be rewritten."""
+
+    def __init__(self, n, dtype, device, group=None, transport="symm", slots=2):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n, self.dtype, self.device = int(n), dtype, device
+        self.transport, self.handles, self.stream = "nccl", None, None
+        if transport == "symm" and device.type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                send = [symm.empty(self.n, dtype=dtype, device=device) for _ in range(slots)]
+                self.handles = [symm.rendezvous(b, self.group) for b in send]
+                self.send = send
+                self.stream = torch.cuda.Stream(device=device, priority=-1)
+                self.transport = "symm"
+            except Exception as exc:   # noqa: BLE001 -- any failure of the optional transport means NCCL
+                self.why_not_symm = f"{type(exc).__name__}: {exc}"
+                self.handles = None
+        if self.handles is None:
+            self.send = [torch.empty(self.n, dtype=dtype, device=device) for _ in range(slots)]
+        self.all = [torch.empty((self.world, self.n), dtype=dtype, device=device) for _ in range(slots)]
+
+    def gather(self, slot, after=None):
+        """Enqueue the gather of send[slot] into all[slot]; `after` = CUDA event the producer recorded.  Returns the
+        event that marks its completion."""
+        done = torch.cuda.Event()
+        if self.handles is not None:
+            if after is not None:
+                self.stream.wait_event(after)
+            else:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                hdl, rows = self.handles[slot], self.all[slot]
+                hdl.barrier()
+                for shift in range(self.world):
+                    r = (self.rank - shift) % self.world
+                    rows[r].copy_(hdl.get_buffer(r, (self.n,), self.dtype))
+                hdl.barrier()
+                done.record(self.stream)
+        else:
+            cur = torch.cuda.current_stream(self.device)
+            if after is not None:
+                cur.wait_event(after)
+            dist.all_gather_into_tensor(self.all[slot].view(-1), self.send[slot], group=self.group)
+            done.record(cur)
+        return done
 
 
 def plan_batch_gather(planner, queries, n_total, cap_path=128, group=None, buffers=None):

@@ -302,30 +302,24 @@ def run_ours(args):
     # two result buffers: the NCCL gather of step k overlaps the kernel of step k+1.  What is gathered is one BIT
     # per pose (pp_pack_flags_dev): 2 MiB per rank instead of 16 MiB
     flags2 = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
-    bits2 = [torch.empty(n_words, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
-    gathered2 = [torch.empty(n_words * world, dtype=torch.int32, device=dev) if multi else None for _ in range(2)]
     gather_done = [None, None]
-    # How the bits travel.  "symm": every rank PULLS its peers' 2 MiB over NVLink with the copy engines (peer memory
-    # mapped through torch's symmetric memory, two signal-pad barriers around the copies) -- no SM is involved, so the
-    # gather runs beside the next step's persistent kernel, which leaves no SM free for a collective's kernel.
-    # "nccl": one ncclAllGather (its kernel ends up queued behind the next step's kernel: measured 0.937 weak scaling
-    # at N = 8).  The symmetric-memory set-up falls back to NCCL when the platform refuses it.
-    gather_kind, symm_hdl, side = None, None, None
+    # How the bits travel (sharding.ResultGather).  "symm": every rank PULLS its peers' 2 MiB over NVLink with the
+    # copy engines (peer memory mapped through torch's symmetric memory, two signal-pad barriers around the copies)
+    # -- no SM is involved, so the gather runs beside the next step's persistent kernel, which leaves no SM free for
+    # a collective's kernel.  "nccl": one ncclAllGather (its kernel ends up queued behind the next step's kernel:
+    # measured 0.937 weak scaling at N = 8).  The symmetric-memory set-up falls back to NCCL when the platform
+    # refuses it.
+    gather_kind, rg = None, None
     bits_kernel = False
     if multi:
-        gather_kind = "nccl"
-        if args.gather == "symm":
-            try:
-                import torch.distributed._symmetric_memory as symm
-                sb = [symm.empty(n_words, dtype=torch.int32, device=dev) for _ in range(2)]
-                symm_hdl = [symm.rendezvous(b, dist.group.WORLD) for b in sb]
-                bits2 = sb
-                side = torch.cuda.Stream(device=dev, priority=-1)
-                gather_kind = "symm"
-                bits_kernel = not args.pack_pass
-            except Exception as exc:   # noqa: BLE001 -- any failure of the optional transport means NCCL
-                print(f"[bench] symmetric memory unavailable ({type(exc).__name__}: {exc}); gathering with NCCL", file=sys.stderr)
-                symm_hdl = None
+        from autonomouscar_b200.sharding import ResultGather
+        rg = ResultGather(n_words, torch.int32, dev, transport=args.gather, slots=2)
+        gather_kind = rg.transport
+        if args.gather == "symm" and gather_kind != "symm":
+            print(f"[bench] symmetric memory unavailable ({rg.why_not_symm}); gathering with NCCL", file=sys.stderr)
+        bits_kernel = gather_kind == "symm" and not args.pack_pass
+    bits2 = rg.send if multi else [None, None]
+    gathered2 = [a.view(-1) for a in rg.all] if multi else [None, None]
     flags = flags2[0]
     step_no = [0]
     pl.sync()
@@ -348,22 +342,7 @@ def run_ours(args):
                 pl.pack_flags_dev(flags2[i], out=bits2[i])
             ev = torch.cuda.Event()
             ev.record(pl.stream)
-            if symm_hdl is not None:
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    hdl, rows = symm_hdl[i], gathered2[i].view(world, n_words)
-                    hdl.barrier()                                  # every rank's bits of this step are in place
-                    for sft in range(world):
-                        r = (rank - sft) % world
-                        rows[r].copy_(hdl.get_buffer(r, (n_words,), torch.int32))   # D2D copy: copy engine, NVLink
-                    hdl.barrier()                                  # every rank has pulled: the buffer may be rewritten
-                    gather_done[i] = torch.cuda.Event()
-                    gather_done[i].record(side)
-            else:
-                torch.cuda.current_stream().wait_event(ev)
-                dist.all_gather_into_tensor(gathered2[i], bits2[i])
-                gather_done[i] = torch.cuda.Event()
-                gather_done[i].record(torch.cuda.current_stream())
+            gather_done[i] = rg.gather(i, after=ev)
         return i
 
     def barrier():
@@ -387,9 +366,7 @@ def run_ours(args):
     for _ in range(args.steps):
         last = step()
     if multi:
-        evj = torch.cuda.Event()
-        evj.record(side if symm_hdl is not None else torch.cuda.current_stream())
-        pl.stream.wait_event(evj)
+        pl.stream.wait_event(gather_done[last])
     e1.record(pl.stream)
     barrier()
     wall = time.perf_counter() - t0

@@ -56,6 +56,24 @@ def _worker(rank, world, port, n, ret):
         from autonomouscar_b200 import rollout
         from test_rollout import _starts
         trace = sharding.rollout_sharded(_starts(37), rollout.plan_batch_cuda(pl), 5, torch.device("cuda", rank))
+        # the packed flags through ResultGather, both transports, two slots each used twice: every rank checks that
+        # it holds every rank's bits (equal-sized blocks: the first `per` poses of each shard)
+        per = (n // world) // 32 * 32
+        mine = torch.from_numpy(poses[lo:lo + per]).cuda(rank)
+        torch.cuda.synchronize()
+        want_bits = pl.pack_flags_dev(pl.collide_dev(mine))
+        pl.sync()
+        for transport in ("symm", "nccl"):
+            rg = sharding.ResultGather(per // 32, torch.int32, torch.device("cuda", rank), transport=transport, slots=2)
+            for it in range(4):
+                slot = it & 1
+                pl.collide_bits_dev(mine, out=rg.send[slot])
+                ev = torch.cuda.Event()
+                ev.record(pl.stream)
+                rg.gather(slot, after=ev).synchronize()
+                assert torch.equal(rg.all[slot][rank], want_bits), (transport, it)
+                ret[f"bits_{transport}_{it}_{rank}"] = rg.all[slot].cpu().numpy().copy()
+            ret[f"transport_{transport}_{rank}"] = rg.transport
         if rank == 0:
             ret["flags"] = flags.cpu().numpy().copy()
             ret["recs"] = recs.cpu().numpy().copy()
@@ -87,6 +105,17 @@ def test_nccl_gather_equals_single_gpu(cuda_device):
     pl.sync()
     np.testing.assert_array_equal(ret["full"], one.cpu().numpy())      # gathered paths byte-identical to the 1-GPU run
     assert 0 < want.sum() < n
+    # ResultGather: every rank ended up with the same [world, words] block, equal to the single-GPU bits of each shard
+    per = (n // world) // 32 * 32
+    for transport in ("symm", "nccl"):
+        for it in range(4):
+            blocks = [ret[f"bits_{transport}_{it}_{r}"] for r in range(world)]
+            for r in range(world):
+                lo, _ = sharding.shard_bounds(n, r, world)
+                bits = np.packbits(want[lo:lo + per], bitorder="little").view(np.int32)
+                for b in blocks:
+                    np.testing.assert_array_equal(b[r], bits)
+    assert ret["transport_nccl_0"] == "nccl"
     from autonomouscar_b200 import rollout
     from test_rollout import _starts
     np.testing.assert_array_equal(ret["trace"], rollout.RouteRollout(_starts(37)).run(rollout.plan_batch_cuda(pl), 5))
