@@ -61,7 +61,7 @@ class ResultGather:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.n, self.dtype, self.device = int(n), dtype, device
-        self.transport, self.handles, self.stream = "nccl", None, None
+        self.transport, self.handles, self.stream = ("nccl" if device.type == "cuda" else "collective"), None, None
         if transport == "symm" and device.type == "cuda":
             try:
                 import torch.distributed._symmetric_memory as symm
@@ -79,7 +79,10 @@ class ResultGather:
 
     def gather(self, slot, after=None):
         """Enqueue the gather of send[slot] into all[slot]; `after` = CUDA event the producer recorded.  Returns the
-        event that marks its completion."""
+        event that marks its completion (None for CPU tensors: the collective has completed on return)."""
+        if self.device.type != "cuda":
+            dist.all_gather_into_tensor(self.all[slot].view(-1), self.send[slot], group=self.group)
+            return None
         done = torch.cuda.Event()
         if self.handles is not None:
             if after is not None:

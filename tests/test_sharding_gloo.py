@@ -47,10 +47,19 @@ def _worker(rank, world, port, n, ret):
         rec = torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1).repeat(1, 5)
         rec_all = sharding.gather_blocks(rec, n)
         slow = sharding.max_over_ranks(1.0 + rank, torch.device("cpu"))
+        # the equal-block result gather (bench.py's flag bits) on its plain-collective path: two slots, used twice
+        rg = sharding.ResultGather(8, torch.int32, torch.device("cpu"), transport="symm", slots=2)
+        rg_ok = rg.transport == "collective"
+        for it in range(4):
+            rg.send[it & 1].copy_(torch.arange(8, dtype=torch.int32) + 100 * rank + it)
+            assert rg.gather(it & 1) is None
+            for r in range(world):
+                rg_ok = rg_ok and bool(torch.equal(rg.all[it & 1][r], torch.arange(8, dtype=torch.int32) + 100 * r + it))
         if rank == 0:
             ret["flags"] = gathered.numpy().copy()
             ret["rec_ok"] = bool(torch.equal(rec_all[:, 0], torch.arange(n)))
             ret["slow"] = slow
+        ret[f"rg_ok_{rank}"] = rg_ok
     finally:
         dist.destroy_process_group()
 
@@ -67,6 +76,7 @@ def test_two_rank_gather_restores_input_order(oracle, n):
     np.testing.assert_array_equal(ret["flags"], want)
     assert 0 < want.sum() < n
     assert ret["rec_ok"] and ret["slow"] == 2.0
+    assert ret["rg_ok_0"] and ret["rg_ok_1"]
 
 
 def _rollout_worker(rank, world, port, n, ticks, ret):
