@@ -34,6 +34,10 @@ for res, W, H in ((0.1, 333, 517), (0.25, 300, 300)):
     pl.set_collision_mode(PP_COLLISION_REF_AABB)
     f = pl.collide_dev(torch.from_numpy(big).cuda())
     pl.unpack_flags_dev(pl.pack_flags_dev(f), f.numel())
+    for m in (PP_COLLISION_REF_AABB, PP_COLLISION_ORIENTED):          # bits written by the kernel / packed afterwards
+        pl.set_collision_mode(m)
+        pl.collide_bits_dev(torch.from_numpy(big).cuda())
+    pl.set_collision_mode(PP_COLLISION_REF_AABB)
     q16, quant, _ = quantise_poses(big, *worlds.pose_box(p, inset_m=-6.0))
     pl.collide_q16(q16, quant)
     pl.set_collision_mode(PP_COLLISION_ORIENTED)
