@@ -315,14 +315,16 @@ fill_zero_kernel(uint8_t* __restrict__ flags, int64_t n) {
 // ticket counter and runs three phases over them, each with dense lanes, passing survivors along through its own
 // slice of shared memory -- no CTA-wide barrier anywhere (with CTA-wide phases 36 % of the warp samples sat in
 // __syncthreads waiting for the slowest warp of the phase):
-//   1. lane per 4 poses : one bit of the dilated 4x4-block map of the pose's yaw bin ("any obstacle the bounding
-//                        box of the footprint can touch from this block at such a yaw") decides ~80 % of the poses.  All flags of the block are stored as 0 here (one 32-bit
-//                        store per lane); the later phases only store the 1s.  Survivors queue up until there
-//                        are 32 of them.
-//   2. lane per survivor : fp64 fixed-point lattice set-up, bounding box, tile and oriented 4x4-block tests
-//                        (make_job) -> free, colliding, or a NarrowJob
-//   3. warp per job    : stage the occupied tiles under the box (one 128 B line each), exact box test on the
-//                        staged window, a cheap pass along the lattice's perimeter, then the sample lattice
+//   1. lane per 4 poses : one bit of the 4x4-block map of the pose's yaw bin, dilated by the oriented footprint
+//                        ("can the footprint, from anywhere in this block and at such a yaw, touch a block that
+//                        holds an obstacle?") decides ~88 % of the poses.  All flags of the block are stored as 0
+//                        here (one 32-bit store per lane); the later phases only store the 1s.  Survivors queue
+//                        up until there are 32 of them.
+//   2. lane per survivor : fp64 fixed-point lattice set-up, bounding box, oriented 4x4-block tests (make_job)
+//                        -> free, colliding, or a NarrowJob
+//   3. warp per job    : the tile rows under the box staged one job ahead (cp.async, one 128 B line per tile), a
+//                        cheap pass along the lattice's perimeter, the hull test at cell resolution on the staged
+//                        window, then the sample lattice
 //   NU == 0 selects the run-time lattice shape.  broad_phase == 0 ("direct") disables every pruning test: each
 //   pose that overlaps the grid runs the full lattice.
 //   counters[3] += narrow-phase jobs of this launch; the low / high half of counters[1] = the ticket / the CTAs
